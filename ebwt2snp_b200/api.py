@@ -1,0 +1,367 @@
+"""ctypes binding of the C ABI (include/ebwt2snp_b200.h) -- the host-side mirror used by the tests
+and bench.py.  The names follow the reference's functions for this path:
+
+    cluster_lm   <-> ref:ebwt2clust.cpp:68-139      statistics  <-> ref:clust2snp.cpp:877-966
+    find_events  <-> ref:clust2snp.cpp:788-872      to_file     <-> ref:clust2snp.cpp:633-780
+
+There is no CPU fallback and nothing here imports oracle/: if the CUDA library is missing the
+import of this module raises, and if no B200 is visible `Context()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libebwt2snp_b200.so")
+MAX_C_LEN = 150
+MAX_K = 128
+HIST_BINS = MAX_C_LEN + 1
+
+OK, ERR_CUDA, ERR_ARG, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = range(6)
+
+
+class E2SError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"e2s error {code}: {msg}")
+        self.code = code
+
+
+class ClusterSummary(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "n_local", "global_off", "n_global", "n_end", "n_written", "head_end", "any_event", "open_start",
+        "end_nm2_start", "tail_lcp_nm2", "tail_lcp_nm1", "tail_bwt_nm1", "k", "min_len")]
+
+
+SUMMARY_WORDS = C.sizeof(ClusterSummary) // 8
+
+
+class ClusterMerged(C.Structure):
+    _fields_ = [
+        ("record_offset", C.c_uint64), ("total_written", C.c_uint64), ("n_clust_out", C.c_uint64),
+        ("phantom_lcp", C.c_uint32), ("n_prepend", C.c_uint32), ("n_append", C.c_uint32), ("n_adopt", C.c_uint32),
+        ("prepend_start", C.c_uint64), ("prepend_len", C.c_uint64), ("prepend_written", C.c_uint64),
+        ("append_start", C.c_uint64 * 2), ("append_len", C.c_uint64 * 2),
+        ("adopt_start", C.c_uint64 * 3), ("adopt_len", C.c_uint64 * 3),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [("hist", C.c_uint64 * HIST_BINS), ("n_clust", C.c_uint64), ("n_bases", C.c_uint64),
+                ("last_len", C.c_uint64), ("max_len", C.c_uint64), ("max_clust_length", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class SnpParams(C.Structure):
+    _fields_ = [("k_left", C.c_int32), ("k_right", C.c_int32), ("mcov_out", C.c_int32), ("max_gap", C.c_int32),
+                ("consensus_reads", C.c_int32), ("max_err", C.c_int32), ("max_snvs", C.c_int32),
+                ("reserved", C.c_int32), ("pval", C.c_double), ("nr_reads1", C.c_uint64)]
+
+
+class Event(C.Structure):
+    _fields_ = [("D", C.c_int32), ("gap", C.c_int32), ("supp0", C.c_int32), ("supp1", C.c_int32),
+                ("right_len", C.c_int32), ("keep", C.c_int32), ("cluster_start", C.c_uint64),
+                ("left0", C.c_char * MAX_K), ("left1", C.c_char * MAX_K), ("right", C.c_char * MAX_K)]
+
+
+class SnpCounts(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_analysed", "n_flagged", "n_candidates", "n_variants", "n_events", "saw_n")]
+
+
+class PipelineResult(C.Structure):
+    _fields_ = [("n_written", C.c_uint64), ("n_clust_out", C.c_uint64), ("max_clust_length", C.c_int32),
+                ("reserved", C.c_int32), ("snp", SnpCounts), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+# every symbol include/ebwt2snp_b200.h declares (tests/test_abi.py checks the list against the header)
+SYMBOLS = [
+    "e2s_version", "e2s_ctx_create", "e2s_ctx_destroy", "e2s_last_error", "e2s_ctx_set_stream",
+    "e2s_ctx_synchronize", "e2s_ctx_launch_count", "e2s_shard_create", "e2s_shard_destroy", "e2s_shard_load_gesa",
+    "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_shard_seal", "e2s_reads_stage", "e2s_reads_stage_dev",
+    "e2s_cluster_run", "e2s_cluster_merge", "e2s_cluster_finalize", "e2s_cluster_lm", "e2s_cluster_count",
+    "e2s_cluster_fetch", "e2s_cluster_fetch_packed", "e2s_clusters_stage_packed", "e2s_clusters_stage",
+    "e2s_statistics", "e2s_statistics_finish", "e2s_snp_default_params", "e2s_find_events", "e2s_events_fetch",
+    "e2s_events_format", "e2s_free", "e2s_pipeline_host",
+]
+
+_lib = None
+
+
+def load_library():
+    """Loads the in-tree CUDA library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m ebwt2snp_b200.build` "
+                          "(there is no CPU fallback for this package)")
+    lib = C.CDLL(LIB_PATH)
+    lib.e2s_last_error.restype = C.c_char_p
+    lib.e2s_last_error.argtypes = [C.c_void_p]
+    lib.e2s_ctx_launch_count.restype = C.c_uint64
+    lib.e2s_ctx_launch_count.argtypes = [C.c_void_p]
+    lib.e2s_ctx_destroy.restype = None
+    lib.e2s_shard_destroy.restype = None
+    lib.e2s_free.restype = None
+    lib.e2s_snp_default_params.restype = None
+    lib.e2s_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.e2s_ctx_destroy.argtypes = [C.c_void_p]
+    lib.e2s_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.e2s_ctx_synchronize.argtypes = [C.c_void_p]
+    lib.e2s_shard_create.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.e2s_shard_destroy.argtypes = [C.c_void_p]
+    lib.e2s_shard_load_gesa.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
+    lib.e2s_shard_load_soa.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64]
+    lib.e2s_shard_load_soa_dev.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64]
+    lib.e2s_shard_seal.argtypes = [C.c_void_p]
+    lib.e2s_reads_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.e2s_reads_stage_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
+    lib.e2s_cluster_run.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(ClusterSummary)]
+    lib.e2s_cluster_merge.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ClusterMerged)]
+    lib.e2s_cluster_finalize.argtypes = [C.c_void_p, C.POINTER(ClusterMerged)]
+    lib.e2s_cluster_lm.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.e2s_cluster_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.e2s_cluster_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.e2s_cluster_fetch_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.e2s_clusters_stage_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.e2s_clusters_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.e2s_statistics.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.e2s_statistics_finish.argtypes = [C.POINTER(Stats), C.c_uint64, C.c_int, C.c_double]
+    lib.e2s_snp_default_params.argtypes = [C.POINTER(SnpParams)]
+    lib.e2s_find_events.argtypes = [C.c_void_p, C.POINTER(SnpParams), C.c_int, C.POINTER(SnpCounts)]
+    lib.e2s_events_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.e2s_events_format.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(SnpParams), C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_size_t)]
+    lib.e2s_free.argtypes = [C.c_void_p]
+    lib.e2s_pipeline_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(SnpParams), C.c_void_p,
+                                      C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PipelineResult)]
+    _lib = lib
+    return lib
+
+
+def default_params(nr_reads1=0, **kw) -> SnpParams:
+    p = SnpParams()
+    load_library().e2s_snp_default_params(C.byref(p))
+    p.nr_reads1 = nr_reads1
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    """pointer of a numpy array / torch tensor / int / None"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+def cluster_merge(summaries, my) -> ClusterMerged:
+    """Host-only (no CUDA): e2s_cluster_merge over a list of ClusterSummary."""
+    lib = load_library()
+    arr = (ClusterSummary * len(summaries))(*summaries)
+    out = ClusterMerged()
+    rc = lib.e2s_cluster_merge(C.cast(arr, C.c_void_p), len(summaries), my, C.byref(out))
+    if rc:
+        raise E2SError(rc, lib.e2s_last_error(None).decode())
+    return out
+
+
+def statistics_finish(st: Stats, last_len, mcov_out=5, pval=0.99) -> Stats:
+    lib = load_library()
+    rc = lib.e2s_statistics_finish(C.byref(st), int(last_len), int(mcov_out), float(pval))
+    if rc:
+        raise E2SError(rc, lib.e2s_last_error(None).decode())
+    return st
+
+
+def events_format(events, params: SnpParams, first_id=1) -> bytes:
+    """to_file(): .snp text of the kept events (host-only)."""
+    lib = load_library()
+    n = len(events)
+    arr = (Event * n)(*events) if n else None
+    text, ln = C.c_void_p(), C.c_size_t()
+    rc = lib.e2s_events_format(C.cast(arr, C.c_void_p) if n else None, n, first_id, C.byref(params), C.byref(text), C.byref(ln))
+    if rc:
+        raise E2SError(rc, lib.e2s_last_error(None).decode())
+    data = C.string_at(text, ln.value)
+    lib.e2s_free(text)
+    return data
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.e2s_ctx_create(device, C.byref(h))
+        if rc:
+            raise E2SError(rc, self.lib.e2s_last_error(None).decode())
+        self.h = h
+        if stream is not None:
+            self._ck(self.lib.e2s_ctx_set_stream(self.h, C.c_void_p(stream)))
+
+    def _ck(self, rc):
+        if rc:
+            raise E2SError(rc, self.lib.e2s_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.e2s_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._ck(self.lib.e2s_ctx_synchronize(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.e2s_ctx_launch_count(self.h))
+
+    def stage_reads(self, bases, offsets, device=False, n_bases=None):
+        n_reads = len(offsets) - 1
+        if device:
+            self._keep = (bases, offsets)
+            self._ck(self.lib.e2s_reads_stage_dev(self.h, _ptr(bases), _ptr(offsets), n_reads, int(n_bases)))
+        else:
+            bases = np.ascontiguousarray(bases, dtype=np.uint8).reshape(-1)
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+            self._ck(self.lib.e2s_reads_stage(self.h, _ptr(bases), _ptr(offsets), n_reads))
+            self.synchronize()
+
+    def shard(self, n_local, global_off=0, n_global=None):
+        return Shard(self, n_local, global_off, n_local if n_global is None else n_global)
+
+    def pipeline_host(self, gesa_records, n, reads_bases, reads_off, params, k=16, min_len=2, x=4, y=4, z=4,
+                      rec10=None, events=None):
+        """ebwt2clust + clust2snp from host buffers (pointers may be pinned torch tensors / numpy arrays)."""
+        res = PipelineResult()
+        n_reads = (len(reads_off) - 1) if reads_off is not None else 0
+        cap_r = (rec10.nbytes // 10) if rec10 is not None else 0
+        cap_e = len(events) if events is not None else 0
+        self._ck(self.lib.e2s_pipeline_host(self.h, _ptr(gesa_records), n, x, y, z, _ptr(reads_bases), _ptr(reads_off),
+                                            n_reads, k, min_len, C.byref(params), _ptr(rec10), cap_r,
+                                            C.cast(events, C.c_void_p) if events is not None else None, cap_e,
+                                            C.byref(res)))
+        return res
+
+
+class Shard:
+    """A contiguous eBWT range resident on the GPU (see the header)."""
+
+    def __init__(self, ctx: Context, n_local, global_off, n_global):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.n_local, self.global_off, self.n_global = int(n_local), int(global_off), int(n_global)
+        h = C.c_void_p()
+        ctx._ck(self.lib.e2s_shard_create(ctx.h, self.n_local, self.global_off, self.n_global, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.e2s_shard_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- residency ---------------------------------------------------------------------
+    def load_gesa(self, records, first=0, count=None, x=4, y=4, z=4):
+        rs = x + y + z + 1
+        if count is None:
+            count = records.nbytes // rs if isinstance(records, np.ndarray) else records.numel() * records.element_size() // rs
+        self.ctx._ck(self.lib.e2s_shard_load_gesa(self.h, _ptr(records), int(first), int(count), x, y, z))
+        self.ctx.synchronize()
+
+    def load_soa(self, lcp, text, suff, bwt, first=0, device=False):
+        count = len(lcp) if lcp is not None else len(bwt)
+        if device:
+            self.ctx._ck(self.lib.e2s_shard_load_soa_dev(self.h, _ptr(lcp), _ptr(text), _ptr(suff), _ptr(bwt), int(first), count))
+        else:
+            arrs = [None if a is None else np.ascontiguousarray(a, dtype=t) for a, t in
+                    ((lcp, np.uint32), (text, np.uint32), (suff, np.uint32), (bwt, np.uint8))]
+            self.ctx._ck(self.lib.e2s_shard_load_soa(self.h, *[_ptr(a) for a in arrs], int(first), count))
+        self.ctx.synchronize()
+
+    def seal(self):
+        self.ctx._ck(self.lib.e2s_shard_seal(self.h))
+
+    # ---- phase 1 -----------------------------------------------------------------------
+    def cluster_run(self, k=16, min_len=2) -> ClusterSummary:
+        s = ClusterSummary()
+        self.ctx._ck(self.lib.e2s_cluster_run(self.h, k, min_len, C.byref(s)))
+        return s
+
+    def cluster_finalize(self, merged: ClusterMerged):
+        self.ctx._ck(self.lib.e2s_cluster_finalize(self.h, C.byref(merged)))
+
+    def cluster_lm(self, k=16, min_len=2):
+        """-> (n_written, n_clust_out) ; ref:ebwt2clust.cpp:68-139"""
+        nw, nc = C.c_uint64(), C.c_uint64()
+        self.ctx._ck(self.lib.e2s_cluster_lm(self.h, k, min_len, C.byref(nw), C.byref(nc)))
+        return nw.value, nc.value
+
+    def cluster_count(self):
+        m = C.c_uint64()
+        self.ctx._ck(self.lib.e2s_cluster_count(self.h, C.byref(m)))
+        return m.value
+
+    def cluster_fetch(self):
+        m = self.cluster_count()
+        start = np.empty(m, dtype=np.uint64)
+        ln = np.empty(m, dtype=np.uint16)
+        mm = C.c_uint64()
+        if m:
+            self.ctx._ck(self.lib.e2s_cluster_fetch(self.h, _ptr(start), _ptr(ln), m, C.byref(mm)))
+        return start, ln
+
+    def cluster_fetch_packed(self) -> bytes:
+        m = self.cluster_count()
+        buf = np.empty(m * 10 + 1, dtype=np.uint8)
+        mm = C.c_uint64()
+        self.ctx._ck(self.lib.e2s_cluster_fetch_packed(self.h, _ptr(buf), m, C.byref(mm)))
+        return buf[: m * 10].tobytes()
+
+    # ---- phase 2 -----------------------------------------------------------------------
+    def stage_clusters(self, start, ln):
+        start = np.ascontiguousarray(start, dtype=np.uint64)
+        ln = np.ascontiguousarray(ln, dtype=np.uint16)
+        self.ctx._ck(self.lib.e2s_clusters_stage(self.h, _ptr(start), _ptr(ln), len(ln)))
+
+    def stage_clusters_packed(self, data: bytes):
+        buf = np.frombuffer(data, dtype=np.uint8)
+        self.ctx._ck(self.lib.e2s_clusters_stage_packed(self.h, _ptr(buf), len(data) // 10))
+
+    def statistics(self, mcov_out=5, pval=0.99, finish=True) -> Stats:
+        st = Stats()
+        self.ctx._ck(self.lib.e2s_statistics(self.h, C.byref(st)))
+        if finish:
+            statistics_finish(st, st.last_len, mcov_out, pval)
+        return st
+
+    def find_events(self, params: SnpParams, max_clust_length) -> SnpCounts:
+        cnt = SnpCounts()
+        self.ctx._ck(self.lib.e2s_find_events(self.h, C.byref(params), int(max_clust_length), C.byref(cnt)))
+        return cnt
+
+    def events(self):
+        n = C.c_uint64()
+        self.ctx._ck(self.lib.e2s_events_fetch(self.h, None, 0, C.byref(n)))
+        arr = (Event * n.value)()
+        if n.value:
+            self.ctx._ck(self.lib.e2s_events_fetch(self.h, C.cast(arr, C.c_void_p), n.value, C.byref(n)))
+        return list(arr)

@@ -1,0 +1,885 @@
+// C ABI (include/ebwt2snp_b200.h): contexts, shard residency, orchestration of the kernels,
+// and the host-only integer logic (shard merge + tail/phantom rule, statistics loop, .snp text).
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+
+using namespace e2s;
+
+struct e2s_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    std::string err;
+    uint64_t launches = 0;
+    // read collection
+    uint8_t* d_bases = nullptr;
+    uint64_t* d_off = nullptr;
+    uint64_t n_reads = 0, n_bases = 0;
+    bool reads_owned = false;
+    // staging
+    uint8_t* d_raw = nullptr;
+    size_t raw_cap = 0;
+    // cached shard for e2s_pipeline_host
+    e2s_shard* cached = nullptr;
+};
+
+struct e2s_shard {
+    e2s_ctx* ctx = nullptr;
+    uint64_t n_local = 0, global_off = 0, n_global = 0;
+    uint64_t alloc_r = 0;  // elements available from local position 0
+    uint32_t *lcp_a = nullptr, *text_a = nullptr, *suff_a = nullptr;
+    uint8_t* bwt_a = nullptr;
+    uint32_t *lcp = nullptr, *text = nullptr, *suff = nullptr;  // local position 0
+    uint8_t* bwt = nullptr;
+    bool sealed = false;
+    // record list
+    uint64_t* d_start = nullptr;
+    uint16_t* d_len = nullptr;
+    uint64_t rec_cap = 0;
+    uint64_t m_own = 0;     // records produced by the scan (or staged)
+    uint64_t m_list = 0;    // records phase 2 analyses = own + adopted
+    bool have_clusters = false, staged = false, finalized = false;
+    e2s_cluster_merged merged;
+    // scan scratch
+    uint64_t* d_desc = nullptr;
+    size_t desc_cap = 0;
+    ClusterDev* d_res = nullptr;
+    unsigned long long* d_hist = nullptr;
+    int variant = 0;
+    // phase 2
+    SnpWork* work = nullptr;
+    std::vector<e2s_event> events;
+    bool have_events = false;
+};
+
+static thread_local std::string g_err;
+
+static int fail(e2s_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(e2s_ctx* ctx, cudaError_t e, const char* what) {
+    return fail(ctx, E2S_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(ctx, x)                                      \
+    do {                                                \
+        cudaError_t _e = (x);                           \
+        if (_e != cudaSuccess) return cuda_fail(ctx, _e, #x); \
+    } while (0)
+
+extern "C" {
+
+int e2s_version(void) { return E2S_VERSION; }
+
+const char* e2s_last_error(const e2s_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int e2s_ctx_create(int device, e2s_ctx** out) {
+    if (!out) return fail(nullptr, E2S_ERR_ARG, "e2s_ctx_create: out == NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, E2S_ERR_CUDA,
+                    std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, E2S_ERR_ARG, "e2s_ctx_create: bad device index");
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, E2S_ERR_CUDA, "device is not sm_100 class: the kernels are built for sm_100a only");
+    CU(nullptr, cudaSetDevice(device));
+    e2s_ctx* c = new e2s_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return cuda_fail(nullptr, e, "cudaStreamCreate");
+    }
+    c->own_stream = true;
+    *out = c;
+    return E2S_OK;
+}
+
+void e2s_ctx_destroy(e2s_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->cached) e2s_shard_destroy(c->cached);
+    if (c->reads_owned) {
+        cudaFree(c->d_bases);
+        cudaFree(c->d_off);
+    }
+    cudaFree(c->d_raw);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int e2s_ctx_set_stream(e2s_ctx* c, void* s) {
+    if (!c) return fail(nullptr, E2S_ERR_ARG, "ctx == NULL");
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = static_cast<cudaStream_t>(s);
+    c->own_stream = false;
+    return E2S_OK;
+}
+
+int e2s_ctx_synchronize(e2s_ctx* c) {
+    if (!c) return fail(nullptr, E2S_ERR_ARG, "ctx == NULL");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return E2S_OK;
+}
+
+uint64_t e2s_ctx_launch_count(const e2s_ctx* c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// shard residency
+// ---------------------------------------------------------------------------------------------
+static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t n_global, e2s_shard** out) {
+    if (!c || !out) return fail(c, E2S_ERR_ARG, "e2s_shard_create: NULL argument");
+    *out = nullptr;
+    if (n_local < 2 || global_off + n_local > n_global || (global_off != 0 && global_off < 2))
+        return fail(c, E2S_ERR_ARG, "e2s_shard_create: need n_local >= 2 and a range inside [0, n_global)");
+    CU(c, cudaSetDevice(c->device));
+    e2s_shard* s = new e2s_shard();
+    s->ctx = c;
+    s->n_local = n_local;
+    s->global_off = global_off;
+    s->n_global = n_global;
+    s->alloc_r = round_up(n_local, 8192) + 8192;
+    const size_t ne = size_t(PAD_L) + s->alloc_r;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->lcp_a), ne * 4);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->text_a), ne * 4);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->suff_a), ne * 4);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->bwt_a), ne);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_res), sizeof(ClusterDev));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_hist), (E2S_HIST_BINS + 1) * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        e2s_shard_destroy(s);
+        return fail(c, E2S_ERR_NOMEM, std::string("shard allocation: ") + cudaGetErrorString(e));
+    }
+    s->lcp = s->lcp_a + PAD_L;
+    s->text = s->text_a + PAD_L;
+    s->suff = s->suff_a + PAD_L;
+    s->bwt = s->bwt_a + PAD_L;
+    // only the pads need defined contents (left halo of shard 0 = 0; right pad is read, never used)
+    CU(c, cudaMemsetAsync(s->lcp_a, 0, PAD_L * 4, c->stream));
+    CU(c, cudaMemsetAsync(s->text_a, 0, PAD_L * 4, c->stream));
+    CU(c, cudaMemsetAsync(s->suff_a, 0, PAD_L * 4, c->stream));
+    CU(c, cudaMemsetAsync(s->bwt_a, 0, PAD_L, c->stream));
+    const size_t tail = size_t(s->alloc_r - n_local);
+    CU(c, cudaMemsetAsync(s->lcp + n_local, 0, tail * 4, c->stream));
+    CU(c, cudaMemsetAsync(s->text + n_local, 0, tail * 4, c->stream));
+    CU(c, cudaMemsetAsync(s->suff + n_local, 0, tail * 4, c->stream));
+    CU(c, cudaMemsetAsync(s->bwt + n_local, 0, tail, c->stream));
+    s->work = snp_work_create();
+    *out = s;
+    return E2S_OK;
+}
+
+void e2s_shard_destroy(e2s_shard* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->lcp_a);
+    cudaFree(s->text_a);
+    cudaFree(s->suff_a);
+    cudaFree(s->bwt_a);
+    cudaFree(s->d_start);
+    cudaFree(s->d_len);
+    cudaFree(s->d_desc);
+    cudaFree(s->d_res);
+    cudaFree(s->d_hist);
+    snp_work_destroy(s->work);
+    if (s->ctx->cached == s) s->ctx->cached = nullptr;
+    delete s;
+}
+
+// the global range a shard keeps: 2 positions of left halo, MAX_C_LEN + 1 of right halo
+static void keep_range(const e2s_shard* s, uint64_t* lo, uint64_t* hi) {
+    *lo = s->global_off >= 2 ? s->global_off - 2 : 0;
+    uint64_t h = s->global_off + s->n_local + MAX_C_LEN + 1;
+    *hi = h < s->n_global ? h : s->n_global;
+}
+
+int e2s_shard_load_gesa(e2s_shard* s, const void* records, uint64_t first, uint64_t count, int x, int y, int z) {
+    if (!s || !records) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_shard_load_gesa: NULL argument");
+    e2s_ctx* c = s->ctx;
+    auto ok = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8; };
+    if (!ok(x) || !ok(y) || !ok(z)) return fail(c, E2S_ERR_ARG, "field byte sizes must be 1, 2, 4 or 8");
+    CU(c, cudaSetDevice(c->device));
+    uint64_t lo, hi;
+    keep_range(s, &lo, &hi);
+    uint64_t a = first > lo ? first : lo, b = first + count < hi ? first + count : hi;
+    if (a >= b) return E2S_OK;
+    const int rs = x + y + z + 1;
+    const uint64_t chunk = uint64_t(1) << 24;  // records per H2D chunk (multiple of 16)
+    const size_t need = size_t(chunk < (b - a) ? chunk : round_up(b - a, 16)) * rs + 64;
+    if (need > c->raw_cap) {
+        cudaFree(c->d_raw);
+        c->d_raw = nullptr;
+        c->raw_cap = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->d_raw), need);
+        if (e != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "raw staging buffer");
+        c->raw_cap = need;
+    }
+    const uint8_t* src = static_cast<const uint8_t*>(records);
+    for (uint64_t p = a; p < b; p += chunk) {
+        const uint64_t cnt = b - p < chunk ? b - p : chunk;
+        CU(c, cudaMemcpyAsync(c->d_raw, src + (p - first) * rs, size_t(cnt) * rs, cudaMemcpyHostToDevice, c->stream));
+        const int64_t l = int64_t(p) - int64_t(s->global_off);  // local index, may be -2 / -1
+        CU(c, launch_unpack_gesa(c->d_raw, cnt, x, y, z, s->lcp + l, s->text + l, s->suff + l, s->bwt + l, c->stream));
+        ++c->launches;
+    }
+    s->sealed = false;
+    return E2S_OK;
+}
+
+static int load_soa(e2s_shard* s, const uint32_t* lcp, const uint32_t* text, const uint32_t* suff, const uint8_t* bwt,
+                    uint64_t first, uint64_t count, cudaMemcpyKind kind) {
+    if (!s) return fail(nullptr, E2S_ERR_ARG, "shard == NULL");
+    e2s_ctx* c = s->ctx;
+    CU(c, cudaSetDevice(c->device));
+    uint64_t lo, hi;
+    keep_range(s, &lo, &hi);
+    uint64_t a = first > lo ? first : lo, b = first + count < hi ? first + count : hi;
+    if (a >= b) return E2S_OK;
+    const int64_t l = int64_t(a) - int64_t(s->global_off);
+    const uint64_t so = a - first, cnt = b - a;
+    if (lcp) CU(c, cudaMemcpyAsync(s->lcp + l, lcp + so, cnt * 4, kind, c->stream));
+    if (text) CU(c, cudaMemcpyAsync(s->text + l, text + so, cnt * 4, kind, c->stream));
+    if (suff) CU(c, cudaMemcpyAsync(s->suff + l, suff + so, cnt * 4, kind, c->stream));
+    if (bwt) CU(c, cudaMemcpyAsync(s->bwt + l, bwt + so, cnt, kind, c->stream));
+    s->sealed = false;
+    return E2S_OK;
+}
+
+int e2s_shard_load_soa(e2s_shard* s, const uint32_t* lcp, const uint32_t* text, const uint32_t* suff, const uint8_t* bwt,
+                       uint64_t first, uint64_t count) {
+    return load_soa(s, lcp, text, suff, bwt, first, count, cudaMemcpyHostToDevice);
+}
+int e2s_shard_load_soa_dev(e2s_shard* s, const uint32_t* lcp, const uint32_t* text, const uint32_t* suff,
+                           const uint8_t* bwt, uint64_t first, uint64_t count) {
+    return load_soa(s, lcp, text, suff, bwt, first, count, cudaMemcpyDeviceToDevice);
+}
+
+int e2s_shard_seal(e2s_shard* s) {
+    if (!s) return fail(nullptr, E2S_ERR_ARG, "shard == NULL");
+    e2s_ctx* c = s->ctx;
+    CU(c, cudaSetDevice(c->device));
+    if (s->global_off + s->n_local == s->n_global) {
+        CU(c, launch_fill_phantom(s->lcp, s->text, s->suff, s->bwt, s->n_local, HALO_R, c->stream));
+        ++c->launches;
+    }
+    s->sealed = true;
+    return E2S_OK;
+}
+
+int e2s_reads_stage(e2s_ctx* c, const uint8_t* bases, const uint64_t* off, uint64_t n_reads) {
+    if (!c || !bases || !off) return fail(c, E2S_ERR_ARG, "e2s_reads_stage: NULL argument");
+    CU(c, cudaSetDevice(c->device));
+    if (c->reads_owned) {
+        cudaFree(c->d_bases);
+        cudaFree(c->d_off);
+    }
+    c->d_bases = nullptr;
+    c->d_off = nullptr;
+    c->reads_owned = true;
+    const uint64_t nb = off[n_reads];
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->d_bases), nb + 16);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->d_off), (n_reads + 1) * 8);
+    if (e != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "reads allocation");
+    CU(c, cudaMemcpyAsync(c->d_bases, bases, nb, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    c->n_reads = n_reads;
+    c->n_bases = nb;
+    return E2S_OK;
+}
+
+int e2s_reads_stage_dev(e2s_ctx* c, const uint8_t* d_bases, const uint64_t* d_off, uint64_t n_reads, uint64_t n_bases) {
+    if (!c || !d_bases || !d_off) return fail(c, E2S_ERR_ARG, "e2s_reads_stage_dev: NULL argument");
+    if (c->reads_owned) {
+        cudaFree(c->d_bases);
+        cudaFree(c->d_off);
+    }
+    c->reads_owned = false;
+    c->d_bases = const_cast<uint8_t*>(d_bases);
+    c->d_off = const_cast<uint64_t*>(d_off);
+    c->n_reads = n_reads;
+    c->n_bases = n_bases;
+    return E2S_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 1
+// ---------------------------------------------------------------------------------------------
+static int ensure_records(e2s_shard* s, uint64_t cap) {
+    if (cap <= s->rec_cap && s->d_start) return E2S_OK;
+    cudaFree(s->d_start);
+    cudaFree(s->d_len);
+    s->d_start = nullptr;
+    s->d_len = nullptr;
+    s->rec_cap = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->d_start), cap * 8);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_len), cap * 2 + 16);
+    if (e != cudaSuccess) return fail(s->ctx, E2S_ERR_NOMEM, "cluster record buffers");
+    s->rec_cap = cap;
+    return E2S_OK;
+}
+
+int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summary* sum) {
+    if (!s || !sum) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_cluster_run: NULL argument");
+    e2s_ctx* c = s->ctx;
+    if (k == 0) return fail(c, E2S_ERR_ARG, "k must be >= 1 (the CLI maps 0 to the default 16)");
+    CU(c, cudaSetDevice(c->device));
+    const char* env = getenv("E2S_CLUSTER_VARIANT");
+    s->variant = env ? atoi(env) : 0;
+    const uint64_t T = uint64_t(cluster_tile_positions(s->variant));
+    const uint64_t num_tiles = (s->n_local + T - 1) / T;
+    if (num_tiles > 0x7fffffffull) return fail(c, E2S_ERR_UNSUPPORTED, "shard too large");
+    if (num_tiles * 2 > s->desc_cap) {
+        cudaFree(s->d_desc);
+        s->d_desc = nullptr;
+        s->desc_cap = 0;
+        if (cudaMalloc(reinterpret_cast<void**>(&s->d_desc), num_tiles * 2 * 8) != cudaSuccess)
+            return fail(c, E2S_ERR_NOMEM, "tile descriptors");
+        s->desc_cap = num_tiles * 2;
+    }
+    if (!s->d_start) {
+        int rc = ensure_records(s, s->n_local / 8 + 4096);
+        if (rc) return rc;
+    }
+    ClusterDev h;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CU(c, cudaMemsetAsync(s->d_desc, 0, num_tiles * 2 * 8, c->stream));
+        CU(c, cudaMemsetAsync(s->d_res, 0, sizeof(ClusterDev), c->stream));
+        ClusterParams p;
+        p.lcp = s->lcp;
+        p.n_local = s->n_local;
+        p.global_off = s->global_off;
+        p.n_global = s->n_global;
+        p.k = k;
+        p.min_len = min_len;
+        p.out_start = s->d_start;
+        p.out_len = s->d_len;
+        p.cap = s->rec_cap - 4;  // room for adopted records
+        p.desc_state = s->d_desc;
+        p.desc_cnt = s->d_desc + num_tiles;
+        p.res = s->d_res;
+        p.num_tiles = uint32_t(num_tiles);
+        int grid = 0;
+        CU(c, launch_cluster(p, s->alloc_r / 16, c->sm_count, c->stream, s->variant, &grid));
+        ++c->launches;
+        CU(c, cudaMemcpyAsync(&h, s->d_res, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        if (!h.overflow) break;
+        if (attempt == 1) return fail(c, E2S_ERR_STATE, "record buffer overflow after resize");
+        int rc = ensure_records(s, h.n_written + 4096);
+        if (rc) return rc;
+    }
+    memset(sum, 0, sizeof *sum);
+    sum->n_local = s->n_local;
+    sum->global_off = s->global_off;
+    sum->n_global = s->n_global;
+    sum->n_end = h.n_end;
+    sum->n_written = h.n_written;
+    sum->head_end = h.head_end;
+    sum->any_event = h.any_event;
+    sum->open_start = h.any_event ? h.open_start : 0;
+    sum->end_nm2_start = h.end_nm2_start;
+    sum->k = k;
+    sum->min_len = uint64_t(int64_t(min_len));
+    if (s->global_off + s->n_local == s->n_global) {
+        uint32_t t[2];
+        uint8_t b;
+        CU(c, cudaMemcpyAsync(t, s->lcp + s->n_local - 2, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(&b, s->bwt + s->n_local - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        sum->tail_lcp_nm2 = t[0];
+        sum->tail_lcp_nm1 = t[1];
+        sum->tail_bwt_nm1 = b;
+    }
+    s->m_own = h.n_written;
+    s->m_list = h.n_written;
+    s->have_clusters = true;
+    s->staged = false;
+    s->finalized = false;
+    s->have_events = false;
+    memset(&s->merged, 0, sizeof s->merged);
+    return E2S_OK;
+}
+
+// Host-only: chain the shards' open-cluster states, resolve head records, apply the tail rule with
+// the post-EOF phantom record (ref:ebwt2clust.cpp:90-135).
+int e2s_cluster_merge(const e2s_cluster_summary* all, int n_shards, int my, e2s_cluster_merged* out) {
+    if (!all || !out || n_shards < 1 || my < 0 || my >= n_shards) return fail(nullptr, E2S_ERR_ARG, "e2s_cluster_merge: bad argument");
+    memset(out, 0, sizeof *out);
+    const uint64_t n = all[0].n_global;
+    const uint32_t k = uint32_t(all[0].k);
+    const int64_t min_len = int64_t(all[0].min_len);
+    uint64_t expect = 0;
+    for (int g = 0; g < n_shards; ++g) {
+        if (all[g].global_off != expect || all[g].n_global != n || all[g].k != all[0].k || all[g].min_len != all[0].min_len)
+            return fail(nullptr, E2S_ERR_ARG, "e2s_cluster_merge: shards are not a partition of [0, n_global)");
+        expect += all[g].n_local;
+    }
+    if (expect != n) return fail(nullptr, E2S_ERR_ARG, "e2s_cluster_merge: shards do not cover n_global");
+    auto owner = [&](uint64_t pos) {
+        for (int g = 0; g < n_shards; ++g)
+            if (pos < all[g].global_off + all[g].n_local) return g;
+        return n_shards - 1;  // position n (phantom-only cluster) stays with the last shard
+    };
+    auto adopt = [&](uint64_t st, uint64_t len) {
+        if (owner(st) == my && out->n_adopt < 3) {
+            out->adopt_start[out->n_adopt] = st;
+            out->adopt_len[out->n_adopt] = len;
+            out->n_adopt++;
+        }
+    };
+    uint64_t s_open = 0;  // 1 + global start of the open cluster, 0 = none
+    uint64_t offset = 0, closed = 0;
+    uint64_t last_head_start = 0;
+    for (int g = 0; g < n_shards; ++g) {
+        if (g == my) out->record_offset = offset;
+        if (all[g].head_end) {
+            if (!s_open) return fail(nullptr, E2S_ERR_STATE, "e2s_cluster_merge: END without START (inconsistent summaries)");
+            const uint64_t st = s_open - 1, en = all[g].head_end - 1;
+            const uint64_t len = (en - st + 1) & 0xffff;
+            const bool written = int64_t(len) >= min_len;
+            if (g == my) {
+                out->n_prepend = 1;
+                out->prepend_start = st;
+                out->prepend_len = len;
+                out->prepend_written = written;
+            }
+            if (written) {
+                offset += 1;
+                adopt(st, len);
+            }
+            last_head_start = st;
+            s_open = 0;
+        }
+        offset += all[g].n_written;
+        closed += all[g].n_end;
+        if (all[g].any_event) s_open = all[g].open_start;
+    }
+    // tail: position n-1 with the phantom record as its right neighbour, then position n
+    const e2s_cluster_summary& L = all[n_shards - 1];
+    const uint32_t e1 = uint32_t(L.tail_lcp_nm2), e2 = uint32_t(L.tail_lcp_nm1);
+    uint32_t P;
+    if (L.end_nm2_start == ~0ull) P = uint32_t(last_head_start);
+    else if (L.end_nm2_start) P = uint32_t(L.end_nm2_start - 1);
+    else P = (e2 & 0xFFFFFF00u) | uint32_t(L.tail_bwt_nm1 & 0xff);
+    out->phantom_lcp = P;
+    uint32_t na = 0;
+    auto tail_record = [&](uint64_t st, uint64_t en) {
+        const uint64_t len = (en - st + 1) & 0xffff;
+        ++closed;
+        if (int64_t(len) >= min_len) {
+            offset += 1;
+            if (my == n_shards - 1) {
+                out->append_start[na] = st;
+                out->append_len[na] = len;
+                ++na;
+            }
+            adopt(st, len);
+        }
+    };
+    if (s_open && ((e1 > e2 && e2 <= P) || P < k)) {
+        tail_record(s_open - 1, n - 1);
+        s_open = 0;
+    }
+    if (!s_open && P >= k) s_open = n + 1;
+    if (s_open) tail_record(s_open - 1, n);
+    out->n_append = na;
+    out->total_written = offset;
+    out->n_clust_out = closed;
+    return E2S_OK;
+}
+
+int e2s_cluster_finalize(e2s_shard* s, const e2s_cluster_merged* mg) {
+    if (!s || !mg) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_cluster_finalize: NULL argument");
+    e2s_ctx* c = s->ctx;
+    if (!s->have_clusters || s->staged) return fail(c, E2S_ERR_STATE, "e2s_cluster_finalize: run e2s_cluster_run first");
+    CU(c, cudaSetDevice(c->device));
+    s->merged = *mg;
+    uint64_t st[3];
+    uint16_t ln[3];
+    for (uint32_t i = 0; i < mg->n_adopt; ++i) {
+        st[i] = mg->adopt_start[i];
+        ln[i] = uint16_t(mg->adopt_len[i]);
+    }
+    if (mg->n_adopt) {
+        CU(c, cudaMemcpyAsync(s->d_start + s->m_own, st, mg->n_adopt * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(s->d_len + s->m_own, ln, mg->n_adopt * 2, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));  // st/ln live on this stack frame
+    }
+    s->m_list = s->m_own + mg->n_adopt;
+    s->finalized = true;
+    return E2S_OK;
+}
+
+int e2s_cluster_lm(e2s_shard* s, uint32_t k, int32_t min_len, uint64_t* n_written, uint64_t* n_clust_out) {
+    if (!s) return fail(nullptr, E2S_ERR_ARG, "shard == NULL");
+    if (s->global_off != 0 || s->n_local != s->n_global)
+        return fail(s->ctx, E2S_ERR_ARG, "e2s_cluster_lm needs the whole eBWT in one shard; use run + merge + finalize");
+    e2s_cluster_summary sum;
+    int rc = e2s_cluster_run(s, k, min_len, &sum);
+    if (rc) return rc;
+    e2s_cluster_merged mg;
+    rc = e2s_cluster_merge(&sum, 1, 0, &mg);
+    if (rc) {
+        s->ctx->err = g_err;
+        return rc;
+    }
+    rc = e2s_cluster_finalize(s, &mg);
+    if (rc) return rc;
+    if (n_written) *n_written = mg.total_written;
+    if (n_clust_out) *n_clust_out = mg.n_clust_out;
+    return E2S_OK;
+}
+
+// records of this shard in .clusters order: [head] + own + [tail]
+static uint64_t out_count(const e2s_shard* s) {
+    if (s->staged) return s->m_own;
+    return s->m_own + (s->merged.n_prepend && s->merged.prepend_written ? 1 : 0) + s->merged.n_append;
+}
+
+int e2s_cluster_count(const e2s_shard* s, uint64_t* m) {
+    if (!s || !m) return fail(nullptr, E2S_ERR_ARG, "NULL argument");
+    if (!s->have_clusters) return fail(s->ctx, E2S_ERR_STATE, "no clusters yet");
+    *m = out_count(s);
+    return E2S_OK;
+}
+
+int e2s_cluster_fetch(e2s_shard* s, uint64_t* start, uint16_t* len, uint64_t cap, uint64_t* m) {
+    if (!s || !start || !len || !m) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
+    e2s_ctx* c = s->ctx;
+    if (!s->have_clusters) return fail(c, E2S_ERR_STATE, "no clusters yet");
+    const uint64_t total = out_count(s);
+    *m = total;
+    if (cap < total) return fail(c, E2S_ERR_ARG, "e2s_cluster_fetch: capacity too small");
+    CU(c, cudaSetDevice(c->device));
+    uint64_t o = 0;
+    if (!s->staged && s->merged.n_prepend && s->merged.prepend_written) {
+        start[o] = s->merged.prepend_start;
+        len[o] = uint16_t(s->merged.prepend_len);
+        ++o;
+    }
+    if (s->m_own) {
+        CU(c, cudaMemcpyAsync(start + o, s->d_start, s->m_own * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(len + o, s->d_len, s->m_own * 2, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        o += s->m_own;
+    }
+    if (!s->staged)
+        for (uint32_t i = 0; i < s->merged.n_append; ++i) {
+            start[o] = s->merged.append_start[i];
+            len[o] = uint16_t(s->merged.append_len[i]);
+            ++o;
+        }
+    return E2S_OK;
+}
+
+int e2s_cluster_fetch_packed(e2s_shard* s, void* rec10, uint64_t cap, uint64_t* m) {
+    if (!s || !rec10 || !m) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
+    if (!s->have_clusters) return fail(s->ctx, E2S_ERR_STATE, "no clusters yet");
+    const uint64_t total = out_count(s);
+    *m = total;
+    if (cap < total) return fail(s->ctx, E2S_ERR_ARG, "e2s_cluster_fetch_packed: capacity too small");
+    std::vector<uint64_t> st(total);
+    std::vector<uint16_t> ln(total);
+    int rc = e2s_cluster_fetch(s, st.data(), ln.data(), total, m);
+    if (rc) return rc;
+    uint8_t* o = static_cast<uint8_t*>(rec10);
+    for (uint64_t i = 0; i < total; ++i) {
+        memcpy(o + i * 10, &st[i], 8);
+        memcpy(o + i * 10 + 8, &ln[i], 2);
+    }
+    return E2S_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 2
+// ---------------------------------------------------------------------------------------------
+int e2s_clusters_stage(e2s_shard* s, const uint64_t* start, const uint16_t* len, uint64_t m) {
+    if (!s || (m && (!start || !len))) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
+    e2s_ctx* c = s->ctx;
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_records(s, m + 8);
+    if (rc) return rc;
+    if (m) {
+        CU(c, cudaMemcpyAsync(s->d_start, start, m * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(s->d_len, len, m * 2, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    s->m_own = s->m_list = m;
+    s->have_clusters = true;
+    s->staged = true;
+    s->finalized = true;
+    s->have_events = false;
+    memset(&s->merged, 0, sizeof s->merged);
+    return E2S_OK;
+}
+
+int e2s_clusters_stage_packed(e2s_shard* s, const void* rec10, uint64_t m) {
+    if (!s || (m && !rec10)) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
+    std::vector<uint64_t> st(m);
+    std::vector<uint16_t> ln(m);
+    const uint8_t* r = static_cast<const uint8_t*>(rec10);
+    for (uint64_t i = 0; i < m; ++i) {
+        memcpy(&st[i], r + i * 10, 8);
+        memcpy(&ln[i], r + i * 10 + 8, 2);
+    }
+    return e2s_clusters_stage(s, st.data(), ln.data(), m);
+}
+
+int e2s_statistics(e2s_shard* s, e2s_stats* st) {
+    if (!s || !st) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
+    e2s_ctx* c = s->ctx;
+    if (!s->have_clusters) return fail(c, E2S_ERR_STATE, "no clusters yet");
+    CU(c, cudaSetDevice(c->device));
+    memset(st, 0, sizeof *st);
+    unsigned long long h[E2S_HIST_BINS + 1];
+    CU(c, cudaMemsetAsync(s->d_hist, 0, sizeof h, c->stream));
+    CU(c, launch_len_hist(s->d_len, s->m_own, s->d_hist, c->stream, c->sm_count));
+    ++c->launches;
+    CU(c, cudaMemcpyAsync(h, s->d_hist, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    uint16_t last = 0;
+    if (s->m_own) CU(c, cudaMemcpyAsync(&last, s->d_len + s->m_own - 1, 2, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < E2S_HIST_BINS; ++i) st->hist[i] = h[i];
+    st->n_bases = h[E2S_HIST_BINS];
+    st->n_clust = s->m_own;
+    st->last_len = last;
+    auto add = [&](uint64_t l) {
+        if (l <= E2S_MAX_C_LEN) st->hist[l]++;
+        st->n_bases += l;
+        st->n_clust++;
+        st->last_len = l;
+    };
+    if (!s->staged) {
+        if (s->merged.n_prepend && s->merged.prepend_written) {
+            const uint64_t keep_last = st->last_len;
+            add(s->merged.prepend_len);
+            if (s->m_own) st->last_len = keep_last;  // the head record comes first, not last
+        }
+        for (uint32_t i = 0; i < s->merged.n_append; ++i) add(s->merged.append_len[i]);
+    }
+    return E2S_OK;
+}
+
+// ref:clust2snp.cpp:889-946: the last record is counted twice; then the pval loop
+int e2s_statistics_finish(e2s_stats* st, uint64_t last_len, int mcov_out, double pval) {
+    if (!st) return fail(nullptr, E2S_ERR_ARG, "NULL argument");
+    if (st->n_clust == 0) return fail(nullptr, E2S_ERR_UNSUPPORTED, "empty .clusters (the reference divides by zero here)");
+    if (last_len <= E2S_MAX_C_LEN) st->hist[last_len]++;
+    st->n_clust++;
+    st->n_bases += last_len;
+    st->max_len = 0;
+    for (int i = 0; i < E2S_HIST_BINS; ++i)
+        if (st->hist[i]) st->max_len = uint64_t(i);
+    int mcl = 2 * mcov_out;
+    if (mcl < 0 || mcl > E2S_MAX_C_LEN) return fail(nullptr, E2S_ERR_UNSUPPORTED, "2*mcov_out outside [0,150]");
+    uint64_t cumulative = st->hist[mcl] * uint64_t(mcl);
+    while (double(cumulative) / double(st->n_bases) < pval && mcl < E2S_MAX_C_LEN) {
+        mcl++;
+        cumulative += st->hist[mcl] * uint64_t(mcl);
+    }
+    st->max_clust_length = mcl;
+    return E2S_OK;
+}
+
+void e2s_snp_default_params(e2s_snp_params* p) {
+    memset(p, 0, sizeof *p);
+    p->k_left = 31;
+    p->k_right = 30;
+    p->mcov_out = 5;
+    p->max_gap = 10;
+    p->consensus_reads = 20;
+    p->max_err = 2;
+    p->max_snvs = 3;
+    p->pval = 0.99;
+}
+
+int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length, e2s_snp_counts* counts) {
+    if (!s || !p || !counts) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
+    e2s_ctx* c = s->ctx;
+    if (!s->have_clusters || !s->finalized) return fail(c, E2S_ERR_STATE, "clusters not computed / staged yet");
+    if (!s->sealed) return fail(c, E2S_ERR_STATE, "call e2s_shard_seal after loading the shard");
+    if (!c->d_bases) return fail(c, E2S_ERR_STATE, "stage the reads first (e2s_reads_stage)");
+    if (p->k_left < 1 || p->k_left > E2S_MAX_K || p->k_right < 1 || p->k_right > E2S_MAX_K || p->max_gap < 1 ||
+        p->max_gap > p->k_left || p->max_gap > 255 || p->mcov_out < 1 || 2 * p->mcov_out > E2S_MAX_C_LEN ||
+        p->consensus_reads < 1 || max_clust_length > E2S_MAX_C_LEN)
+        return fail(c, E2S_ERR_UNSUPPORTED, "clust2snp parameters outside the supported range (DESIGN.md)");
+    CU(c, cudaSetDevice(c->device));
+    s->have_events = false;
+    s->events.clear();
+    if (s->staged && s->m_list > 1) {
+        // the reference assumes position-ordered, disjoint records (ref:clust2snp.cpp:818-833)
+        SnpDev* chk = nullptr;
+        CU(c, cudaMalloc(reinterpret_cast<void**>(&chk), sizeof(SnpDev)));
+        cudaMemsetAsync(chk, 0, sizeof(SnpDev), c->stream);
+        launch_check_sorted(s->d_start, s->d_len, s->m_list, chk, c->stream, c->sm_count);
+        ++c->launches;
+        SnpDev h;
+        cudaMemcpyAsync(&h, chk, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        cudaFree(chk);
+        if (e != cudaSuccess) return cuda_fail(c, e, "check_sorted");
+        if (h.unsorted) return fail(c, E2S_ERR_UNSUPPORTED, ".clusters records are not position-ordered and disjoint");
+    }
+    SnpArrays a;
+    a.lcp = s->lcp;
+    a.text = s->text;
+    a.suff = s->suff;
+    a.bwt = s->bwt;
+    a.n_local = s->n_local;
+    a.global_off = s->global_off;
+    a.cl_start = s->d_start;
+    a.cl_len = s->d_len;
+    a.m = s->m_list;
+    const char* err = "";
+    cudaError_t e = snp_run(s->work, a, *p, max_clust_length, c->d_bases, c->d_off, c->n_reads, c->sm_count, c->stream,
+                            counts, &c->launches, &err);
+    if (e == cudaErrorInvalidValue && err && strstr(err, "outside the staged reads")) return fail(c, E2S_ERR_UNSUPPORTED, err);
+    if (e != cudaSuccess) return cuda_fail(c, e, err);
+    // candidates are few: bring them to the host now and keep the variants
+    uint64_t nv = 0;
+    e = snp_fetch_events(s->work, nullptr, 0, &nv, c->stream);
+    if (e != cudaSuccess) return cuda_fail(c, e, "snp_fetch_events");
+    s->events.resize(nv);
+    if (nv) {
+        e = snp_fetch_events(s->work, s->events.data(), nv, &nv, c->stream);
+        if (e != cudaSuccess) return cuda_fail(c, e, "snp_fetch_events");
+    }
+    counts->n_variants = nv;
+    counts->n_events = 0;
+    for (auto& ev : s->events) counts->n_events += ev.keep ? 1 : 0;
+    s->have_events = true;
+    return E2S_OK;
+}
+
+int e2s_events_fetch(e2s_shard* s, e2s_event* events, uint64_t cap, uint64_t* n) {
+    if (!s || !n) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
+    if (!s->have_events) return fail(s->ctx, E2S_ERR_STATE, "run e2s_find_events first");
+    *n = s->events.size();
+    if (!events) return E2S_OK;
+    if (cap < s->events.size()) return fail(s->ctx, E2S_ERR_ARG, "e2s_events_fetch: capacity too small");
+    if (!s->events.empty()) memcpy(events, s->events.data(), s->events.size() * sizeof(e2s_event));
+    return E2S_OK;
+}
+
+// to_file(): ref:clust2snp.cpp:633-780
+int e2s_events_format(const e2s_event* ev, uint64_t n, uint64_t first_id, const e2s_snp_params* p, char** text, size_t* len) {
+    if ((!ev && n) || !p || !text || !len) return fail(nullptr, E2S_ERR_ARG, "NULL argument");
+    std::string out;
+    out.reserve(size_t(n) * 200);
+    uint64_t id = first_id;
+    const int kl = p->k_left;
+    for (uint64_t i = 0; i < n; ++i) {
+        const e2s_event& e = ev[i];
+        if (!e.keep) continue;
+        std::string type;
+        if (e.gap == 0) {
+            type += e.left0[kl - 1];
+            type += '/';
+            type += e.left1[kl - 1];
+        } else if (e.gap > 0) {
+            type.append(e.left0 + kl - e.gap, size_t(e.gap));
+            type += '/';
+        } else {
+            type += '/';
+            type.append(e.left1 + kl + e.gap, size_t(-e.gap));
+        }
+        for (int path = 0; path < 2; ++path) {
+            out += e.gap != 0 ? (path ? ">INDEL_lower_path_" : ">INDEL_higher_path_") : (path ? ">SNP_lower_path_" : ">SNP_higher_path_");
+            out += std::to_string(id);
+            out += "|P_1:";
+            out += std::to_string(e.right_len);
+            out += "_";
+            out += type;
+            out += "|";
+            out += std::to_string(path ? e.supp1 : e.supp0);
+            out += "|nb_pol_1\n";
+            int skip = 0;
+            if (path == 0 && e.gap < 0) skip = -e.gap;
+            if (path == 1 && e.gap > 0) skip = e.gap;
+            out.append((path ? e.left1 : e.left0) + skip, size_t(kl - skip));
+            out.append(e.right, size_t(e.right_len));
+            out += '\n';
+        }
+        ++id;
+    }
+    char* buf = static_cast<char*>(malloc(out.size() + 1));
+    if (!buf) return fail(nullptr, E2S_ERR_NOMEM, "malloc");
+    memcpy(buf, out.data(), out.size());
+    buf[out.size()] = 0;
+    *text = buf;
+    *len = out.size();
+    return E2S_OK;
+}
+
+void e2s_free(void* p) { free(p); }
+
+// ---------------------------------------------------------------------------------------------
+// end to end over host buffers
+// ---------------------------------------------------------------------------------------------
+int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, int z, const uint8_t* read_bases,
+                      const uint64_t* read_off, uint64_t n_reads, uint32_t k, int32_t min_len, const e2s_snp_params* p,
+                      void* rec10, uint64_t cap_records, e2s_event* events, uint64_t cap_events, e2s_pipeline_result* res) {
+    if (!c || !gesa || !p || !res) return fail(c, E2S_ERR_ARG, "NULL argument");
+    memset(res, 0, sizeof *res);
+    int rc;
+    e2s_shard* s = c->cached;
+    if (!s || s->n_local != n || s->n_global != n) {
+        if (s) e2s_shard_destroy(s);
+        c->cached = nullptr;
+        rc = e2s_shard_create(c, n, 0, n, &s);
+        if (rc) return rc;
+        c->cached = s;
+    }
+    const int rs = x + y + z + 1;
+    if ((rc = e2s_shard_load_gesa(s, gesa, 0, n, x, y, z))) return rc;
+    if ((rc = e2s_shard_seal(s))) return rc;
+    res->h2d_bytes += n * uint64_t(rs);
+    if ((rc = e2s_cluster_lm(s, k, min_len, &res->n_written, &res->n_clust_out))) return rc;
+    if (rec10) {
+        uint64_t m = 0;
+        if ((rc = e2s_cluster_fetch_packed(s, rec10, cap_records, &m))) return rc;
+        res->d2h_bytes += m * 10;
+    }
+    if (res->n_written == 0) return fail(c, E2S_ERR_UNSUPPORTED, "no clusters (the reference divides by zero here)");
+    e2s_stats st;
+    if ((rc = e2s_statistics(s, &st))) return rc;
+    if ((rc = e2s_statistics_finish(&st, st.last_len, p->mcov_out, p->pval))) {
+        c->err = g_err;
+        return rc;
+    }
+    res->max_clust_length = st.max_clust_length;
+    if (read_bases) {
+        if ((rc = e2s_reads_stage(c, read_bases, read_off, n_reads))) return rc;
+        res->h2d_bytes += read_off[n_reads] + (n_reads + 1) * 8;
+    }
+    if ((rc = e2s_find_events(s, p, st.max_clust_length, &res->snp))) return rc;
+    res->d2h_bytes += res->snp.n_candidates * 128;
+    if (events) {
+        uint64_t nv = 0;
+        if ((rc = e2s_events_fetch(s, events, cap_events, &nv))) return rc;
+    }
+    return E2S_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// Internal declarations shared by the .cu translation units (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ebwt2snp_b200.h"
+
+namespace e2s {
+
+// ---- phase 1 ---------------------------------------------------------------------------------
+struct ClusterDev {  // device-resident accumulators of one e2s_cluster_run (zeroed before the launch)
+    unsigned long long n_end;
+    unsigned long long n_written;
+    unsigned long long head_end;       // 1 + global END position, 0 = none
+    unsigned long long any_event;
+    unsigned long long open_start;     // 1 + global START, 0 = none
+    unsigned long long end_nm2_start;  // 1 + START of the cluster closed at n_global-2; ~0 = head; 0 = none
+    unsigned long long overflow;
+    unsigned long long pad;
+};
+
+struct ClusterParams {
+    const uint32_t* lcp;  // local position 0 (PAD_L readable elements before it)
+    uint64_t n_local, global_off, n_global;
+    uint32_t k;
+    int32_t min_len;
+    uint64_t* out_start;
+    uint16_t* out_len;
+    uint64_t cap;
+    uint64_t* desc_state;
+    uint64_t* desc_cnt;
+    ClusterDev* res;
+    uint32_t num_tiles;
+};
+
+cudaError_t launch_cluster(const ClusterParams& p, uint64_t rows_alloc16, int sm_count, cudaStream_t stream,
+                           int variant, int* grid_out);
+int cluster_tile_positions(int variant);
+
+// ---- staging -----------------------------------------------------------------------------------
+// AoS records -> SoA.  d_rec: `count` records of (y+z+x+1) bytes; outputs are pointers to the element
+// that receives record 0 (any may be null).
+cudaError_t launch_unpack_gesa(const uint8_t* d_rec, uint64_t count, int x, int y, int z, uint32_t* lcp, uint32_t* text,
+                               uint32_t* suff, uint8_t* bwt, cudaStream_t stream);
+cudaError_t launch_fill_phantom(uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt, uint64_t n_local,
+                                uint64_t count, cudaStream_t stream);
+
+// ---- phase 2 -----------------------------------------------------------------------------------
+struct SnpDev {  // device counters of one e2s_find_events
+    unsigned long long n_analysed;
+    unsigned long long n_flagged;
+    unsigned long long n_slots_valid;
+    unsigned long long saw_n;
+    unsigned long long bad_ref;
+    unsigned long long unsorted;
+    unsigned long long pad[2];
+};
+
+struct SnpArrays {
+    const uint32_t* lcp;
+    const uint32_t* text;
+    const uint32_t* suff;
+    const uint8_t* bwt;   // all: local position 0
+    uint64_t n_local, global_off;
+    const uint64_t* cl_start;  // global starts, sorted
+    const uint16_t* cl_len;
+    uint64_t m;
+};
+
+struct CandSlot {  // one (flagged cluster, allele pair) slot written by K3b
+    uint32_t n0, n1;
+    uint32_t valid;
+    uint32_t pad;
+    uint64_t right_idx, right_pos;
+    uint64_t cluster_start;
+    // followed in the slot arrays by idx/pos lists (see snp.cu)
+};
+
+cudaError_t launch_len_hist(const uint16_t* len, uint64_t m, unsigned long long* hist /*151 + n_bases*/,
+                            cudaStream_t stream, int sm_count);
+cudaError_t launch_check_sorted(const uint64_t* start, const uint16_t* len, uint64_t m, SnpDev* dev,
+                                cudaStream_t stream, int sm_count);
+
+struct SnpWork;  // opaque scratch owned by the shard (snp.cu)
+SnpWork* snp_work_create();
+void snp_work_destroy(SnpWork* w);
+// Runs K3a/K3b/K4; returns events on the device inside `w`.  Synchronises the stream a few times
+// (it needs small counts on the host to size the next launch).
+cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int max_clust_length,
+                    const uint8_t* d_read_bases, const uint64_t* d_read_off, uint64_t n_reads, int sm_count,
+                    cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err);
+cudaError_t snp_fetch_events(SnpWork* w, e2s_event* host, uint64_t cap, uint64_t* n, cudaStream_t stream);
+
+}  // namespace e2s

@@ -1,0 +1,811 @@
+// Phase 2 (clust2snp): per-cluster analysis and SNP/indel calling.
+//
+//   k_len_hist       statistics(): length histogram                      ref:clust2snp.cpp:889-909
+//   k_tile_first     merge-path style partition of the cluster list over position tiles
+//   k_cluster_scan   K3a: per-cluster 2x4 nucleotide histogram (sample = gSA text id < nreads1),
+//                    first-argmax LCP and the find_variants filters        ref:clust2snp.cpp:377-429
+//   k_flag_*         ordered compaction of the flagged clusters
+//   k_candidates     K3b: ordered (ballot/popc) selection of the first <= c supporting reads per
+//                    sample and allele pair                                ref:clust2snp.cpp:431-496
+//   k_compact_slots  candidates in reference order
+//   k_events         K4: gSA-driven gather of read contexts, consensus, support, distance()
+//                                                  ref:clust2snp.cpp:541-624, 254-302, include.hpp:334-371
+//
+// K3a is the only kernel that touches every position: it streams text/lcp/bwt tiles (+150-record
+// overhang) into shared memory with the TMA engine (cp.async.bulk, STAGES tiles in flight per CTA) and
+// lets 8-lane groups reduce one cluster each out of shared memory.  Algorithmic traffic:
+// 10 B/cluster + 9 B/position inside analysed clusters; the streamed traffic is
+// 9 B/position because non-cluster positions ride along in the tiles.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace e2s {
+
+constexpr uint32_t FULL = 0xffffffffu;
+
+// ref:include.hpp:265-279: ACGT/acgt -> 0..3, everything else (incl. '$') -> 0.  N/n is flagged.
+__device__ __forceinline__ uint32_t base_code(uint32_t c) {
+    const uint32_t u = c & 0xDFu;
+    return uint32_t(u == 'C') + 2u * uint32_t(u == 'G') + 3u * uint32_t(u == 'T');
+}
+__device__ __forceinline__ bool is_n(uint32_t c) { return (c & 0xDFu) == 'N'; }
+
+// ---------------------------------------------------------------------------------------------
+// statistics
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_len_hist(const uint16_t* __restrict__ len, uint64_t m, unsigned long long* out) {
+    __shared__ unsigned int h[MAX_C_LEN + 1];
+    for (int i = threadIdx.x; i <= MAX_C_LEN; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    unsigned long long bases = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m; i += uint64_t(gridDim.x) * blockDim.x) {
+        uint32_t l = len[i];
+        bases += l;
+        if (l <= MAX_C_LEN) atomicAdd(&h[l], 1u);
+    }
+    for (int d = 16; d > 0; d >>= 1) bases += __shfl_xor_sync(FULL, bases, d);
+    if ((threadIdx.x & 31) == 0 && bases) atomicAdd(&out[MAX_C_LEN + 1], bases);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= MAX_C_LEN; i += blockDim.x)
+        if (h[i]) atomicAdd(&out[i], (unsigned long long)h[i]);
+}
+
+cudaError_t launch_len_hist(const uint16_t* len, uint64_t m, unsigned long long* hist, cudaStream_t stream, int sm_count) {
+    if (m == 0) return cudaSuccess;
+    uint64_t blocks = (m + 256 * 16 - 1) / (256 * 16);
+    if (blocks > uint64_t(sm_count) * 8) blocks = uint64_t(sm_count) * 8;
+    k_len_hist<<<unsigned(blocks), 256, 0, stream>>>(len, m, hist);
+    return cudaGetLastError();
+}
+
+__global__ void k_check_sorted(const uint64_t* __restrict__ start, const uint16_t* __restrict__ len, uint64_t m, SnpDev* dev) {
+    bool bad = false;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i + 1 < m; i += uint64_t(gridDim.x) * blockDim.x)
+        bad |= start[i] + len[i] > start[i + 1];
+    if (bad) dev->unsorted = 1;
+}
+
+cudaError_t launch_check_sorted(const uint64_t* start, const uint16_t* len, uint64_t m, SnpDev* dev, cudaStream_t stream,
+                                int sm_count) {
+    if (m < 2) return cudaSuccess;
+    uint64_t blocks = (m + 256 * 8 - 1) / (256 * 8);
+    if (blocks > uint64_t(sm_count) * 8) blocks = uint64_t(sm_count) * 8;
+    k_check_sorted<<<unsigned(blocks), 256, 0, stream>>>(start, len, m, dev);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3a
+// ---------------------------------------------------------------------------------------------
+constexpr int SC_THREADS = 256;
+constexpr int SC_T = 2048;                 // positions per tile
+constexpr int SC_SPAN = SC_T + HALO_R;     // positions staged per tile
+constexpr int SC_STAGES = 3;
+constexpr int SC_G = 8;                    // lanes per cluster
+constexpr int SC_BATCH = 1024;             // cluster records staged per batch
+constexpr int SC_STAGE_BYTES = SC_SPAN * 9;
+
+struct ScanParams {
+    SnpArrays a;
+    const uint64_t* tile_first;  // num_tiles + 1
+    uint32_t num_tiles;
+    uint32_t min_len, max_len;   // 2*mcov_out, max_clust_length
+    uint32_t mcov;
+    uint32_t k_right;
+    uint32_t nr1_lo;             // min(nr_reads1, 2^32-1)
+    uint32_t nr1_big;            // nr_reads1 >= 2^32: everything is sample 0
+    uint32_t* flag_words;
+    SnpDev* dev;
+};
+
+__global__ void k_tile_first(const uint64_t* __restrict__ cl_start, uint64_t m, uint64_t global_off, uint32_t num_tiles,
+                             uint64_t* __restrict__ tile_first) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > num_tiles) return;
+    const uint64_t key = global_off + uint64_t(t) * SC_T;
+    uint64_t lo = 0, hi = m;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (cl_start[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    tile_first[t] = lo;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_cluster_scan(ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full_bar[SC_STAGES];
+    __shared__ uint32_t s_cs[SC_BATCH];
+    __shared__ uint16_t s_cl[SC_BATCH];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int gl = lane & (SC_G - 1);          // lane in group
+    const int group = tid / SC_G;              // group in CTA
+    constexpr int NGROUPS = SC_THREADS / SC_G;
+    const uint32_t gmask = ((1u << SC_G) - 1u) << (lane & ~(SC_G - 1));
+
+    if (tid == 0) {
+        for (int s = 0; s < SC_STAGES; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int s, uint64_t t) {
+        uint8_t* st = smem + size_t(s) * SC_STAGE_BYTES;
+        const uint64_t base = t * SC_T;
+        mbar_expect_tx(&full_bar[s], SC_STAGE_BYTES);
+        bulk_g2s(st, p.a.text + base, SC_SPAN * 4, &full_bar[s]);
+        bulk_g2s(st + SC_SPAN * 4, p.a.lcp + base, SC_SPAN * 4, &full_bar[s]);
+        bulk_g2s(st + SC_SPAN * 8, p.a.bwt + base, SC_SPAN, &full_bar[s]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < SC_STAGES; ++s) {
+            uint64_t t = uint64_t(blockIdx.x) + uint64_t(s) * gridDim.x;
+            if (t < p.num_tiles) issue(s, t);
+        }
+    }
+
+    unsigned long long n_analysed = 0;
+    uint32_t saw_n = 0;
+    uint32_t it = 0;
+    for (uint64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int stage = it % SC_STAGES;
+        const uint32_t parity = (it / SC_STAGES) & 1;
+        const uint8_t* st = smem + size_t(stage) * SC_STAGE_BYTES;
+        const uint32_t* s_text = reinterpret_cast<const uint32_t*>(st);
+        const uint32_t* s_lcp = reinterpret_cast<const uint32_t*>(st + SC_SPAN * 4);
+        const uint8_t* s_bwt = st + SC_SPAN * 8;
+        const uint64_t c_lo = p.tile_first[t], c_hi = p.tile_first[t + 1];
+        const uint64_t tile_gbase = p.a.global_off + t * SC_T;
+
+        bool waited = false;
+        for (uint64_t cb = c_lo; cb < c_hi; cb += SC_BATCH) {
+            const uint32_t nb = uint32_t(c_hi - cb < SC_BATCH ? c_hi - cb : SC_BATCH);
+            __syncthreads();  // previous batch consumed
+            for (uint32_t i = tid; i < nb; i += SC_THREADS) {
+                s_cs[i] = uint32_t(p.a.cl_start[cb + i] - tile_gbase);
+                s_cl[i] = p.a.cl_len[cb + i];
+            }
+            __syncthreads();
+            if (!waited) {
+                mbar_wait(&full_bar[stage], parity);
+                waited = true;
+            }
+            for (uint32_t c = group; c < nb; c += NGROUPS) {
+                const uint32_t len = s_cl[c];
+                if (len < p.min_len || len > p.max_len) continue;
+                const uint32_t rel = s_cs[c];
+                unsigned long long acc = 0, best = 0;
+                for (uint32_t j = gl; j < len; j += SC_G) {
+                    const uint32_t tx = s_text[rel + j];
+                    const uint32_t lc = s_lcp[rel + j];
+                    const uint32_t b = s_bwt[rel + j];
+                    const uint32_t sample = (tx >= p.nr1_lo) & (p.nr1_big ^ 1u);
+                    saw_n |= is_n(b);
+                    acc += 1ull << (8 * (sample * 4 + base_code(b)));
+                    const unsigned long long key = (uint64_t(lc) << 8) | (255u - j);
+                    best = key > best ? key : best;
+                }
+#pragma unroll
+                for (int d = SC_G / 2; d > 0; d >>= 1) {
+                    acc += __shfl_xor_sync(gmask, acc, d);
+                    unsigned long long o = __shfl_xor_sync(gmask, best, d);
+                    best = o > best ? o : best;
+                }
+                if (gl == 0) {
+                    ++n_analysed;
+                    if ((best >> 8) >= p.k_right) {
+                        uint32_t f0 = 0, f1 = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            f0 |= uint32_t(((acc >> (8 * b)) & 0xff) >= p.mcov) << b;
+                            f1 |= uint32_t(((acc >> (8 * (b + 4))) & 0xff) >= p.mcov) << b;
+                        }
+                        const bool ok = f0 && f1 && __popc(f0) <= 2 && __popc(f1) <= 2 && f0 != f1 && __popc(f0 | f1) <= 3;
+                        if (ok) {
+                            const uint64_t ci = cb + c;
+                            atomicOr(&p.flag_words[ci >> 5], 1u << (ci & 31));
+                        }
+                    }
+                }
+            }
+        }
+        if (!waited) mbar_wait(&full_bar[stage], parity);  // keep the barrier phases in step
+        __syncthreads();                                    // everyone is done with the stage
+        if (tid == 0) {
+            uint64_t tn = t + uint64_t(SC_STAGES) * gridDim.x;
+            if (tn < p.num_tiles) issue(stage, tn);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        n_analysed += __shfl_xor_sync(FULL, n_analysed, d);
+        saw_n |= __shfl_xor_sync(FULL, saw_n, d);
+    }
+    if (lane == 0) {
+        if (n_analysed) atomicAdd(&p.dev->n_analysed, n_analysed);
+        if (saw_n) atomicOr(&p.dev->saw_n, 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ordered compaction of flagged clusters (bitmask -> ascending index list)
+// ---------------------------------------------------------------------------------------------
+constexpr int FC_THREADS = 256;
+constexpr int FC_WORDS = 4096;  // words per block
+
+__global__ void __launch_bounds__(FC_THREADS) k_flag_count(const uint32_t* __restrict__ words, uint64_t n_words,
+                                                           uint32_t* __restrict__ block_sum) {
+    __shared__ uint32_t s[FC_THREADS / 32];
+    const uint64_t w0 = uint64_t(blockIdx.x) * FC_WORDS;
+    uint32_t c = 0;
+    for (uint32_t i = threadIdx.x; i < FC_WORDS; i += FC_THREADS)
+        if (w0 + i < n_words) c += __popc(words[w0 + i]);
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int i = 0; i < FC_THREADS / 32; ++i) tot += s[i];
+        block_sum[blockIdx.x] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(FC_THREADS) k_flag_emit(const uint32_t* __restrict__ words, uint64_t n_words,
+                                                          const uint32_t* __restrict__ block_sum,
+                                                          uint64_t* __restrict__ out_idx, SnpDev* dev) {
+    __shared__ uint64_t s_base;
+    __shared__ uint32_t s_red[FC_THREADS / 32];
+    __shared__ uint32_t s_w[FC_THREADS / 32];
+    // my block's exclusive prefix = sum of the preceding block sums
+    uint64_t part = 0;
+    for (uint32_t i = threadIdx.x; i < blockIdx.x; i += FC_THREADS) part += block_sum[i];
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = uint32_t(part);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t b = 0;
+        for (int i = 0; i < FC_THREADS / 32; ++i) b += s_red[i];
+        s_base = b;
+        if (blockIdx.x == gridDim.x - 1) dev->n_flagged = b + block_sum[blockIdx.x];
+    }
+    __syncthreads();
+    uint64_t base = s_base;
+    const uint64_t w0 = uint64_t(blockIdx.x) * FC_WORDS;
+    for (uint32_t r = 0; r < FC_WORDS / FC_THREADS; ++r) {
+        const uint64_t wi = w0 + r * FC_THREADS + threadIdx.x;
+        uint32_t w = wi < n_words ? words[wi] : 0;
+        uint32_t c = __popc(w), inc = c;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if ((threadIdx.x & 31) >= d) inc += o;
+        }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        uint32_t off = inc - c, tot = 0;
+        for (int i = 0; i < FC_THREADS / 32; ++i) {
+            if (i < int(threadIdx.x >> 5)) off += s_w[i];
+            tot += s_w[i];
+        }
+        uint64_t o = base + off;
+        while (w) {
+            int b = __ffs(w) - 1;
+            w &= w - 1;
+            out_idx[o++] = wi * 32 + b;
+        }
+        base += tot;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b: candidates of the flagged clusters
+// ---------------------------------------------------------------------------------------------
+struct CandParams {
+    SnpArrays a;
+    const uint64_t* flagged;  // cluster indices, ascending
+    uint64_t n_flagged;
+    uint32_t mcov, k_left, k_right, cap;  // cap = min(consensus_reads, 150)
+    uint32_t nr1_lo, nr1_big;
+    CandSlot* slots;       // 4 per flagged cluster
+    uint32_t* slot_text;   // [slot][2][cap]
+    uint32_t* slot_pos;    // [slot][2][cap]
+};
+
+__global__ void __launch_bounds__(128) k_candidates(CandParams p) {
+    const uint64_t f = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (f >= p.n_flagged) return;
+    const uint64_t ci = p.flagged[f];
+    const uint64_t start = p.a.cl_start[ci];
+    const uint32_t len = p.a.cl_len[ci];
+    const uint64_t lp = start - p.a.global_off;  // local position
+    const uint32_t* text = p.a.text + lp;
+    const uint32_t* lcp = p.a.lcp + lp;
+    const uint32_t* suff = p.a.suff + lp;
+    const uint8_t* bwt = p.a.bwt + lp;
+
+    unsigned long long acc = 0, best = 0;
+    for (uint32_t j = lane; j < len; j += 32) {
+        const uint32_t sample = (text[j] >= p.nr1_lo) & (p.nr1_big ^ 1u);
+        acc += 1ull << (8 * (sample * 4 + base_code(bwt[j])));
+        const unsigned long long key = (uint64_t(lcp[j]) << 8) | (255u - j);
+        best = key > best ? key : best;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        acc += __shfl_xor_sync(FULL, acc, d);
+        unsigned long long o = __shfl_xor_sync(FULL, best, d);
+        best = o > best ? o : best;
+    }
+    uint32_t fr[2][2], nf[2] = {0, 0};
+    for (int s = 0; s < 2; ++s)
+        for (int b = 0; b < 4; ++b)
+            if (((acc >> (8 * (s * 4 + b))) & 0xff) >= p.mcov && nf[s] < 2) fr[s][nf[s]++] = b;
+    const uint32_t jbest = 255u - uint32_t(best & 0xff);
+    const uint64_t right_idx = text[jbest], right_pos = suff[jbest];
+
+    for (uint32_t i0 = 0; i0 < 2; ++i0) {
+        for (uint32_t i1 = 0; i1 < 2; ++i1) {
+            const uint64_t slot = f * 4 + i0 * 2 + i1;
+            CandSlot hdr;
+            hdr.n0 = hdr.n1 = hdr.valid = hdr.pad = 0;
+            hdr.right_idx = right_idx;
+            hdr.right_pos = right_pos;
+            hdr.cluster_start = start;
+            if (i0 < nf[0] && i1 < nf[1] && fr[0][i0] != fr[1][i1]) {
+                const uint32_t c0 = "ACGT"[fr[0][i0]], c1 = "ACGT"[fr[1][i1]];
+                uint32_t n0 = 0, n1 = 0;
+                uint32_t* t0 = p.slot_text + (slot * 2 + 0) * p.cap;
+                uint32_t* t1 = p.slot_text + (slot * 2 + 1) * p.cap;
+                uint32_t* p0 = p.slot_pos + (slot * 2 + 0) * p.cap;
+                uint32_t* p1 = p.slot_pos + (slot * 2 + 1) * p.cap;
+                for (uint32_t j0 = 0; j0 < len; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    bool q0 = false, q1 = false;
+                    uint32_t tx = 0, sf = 0;
+                    if (j < len) {
+                        tx = text[j];
+                        sf = suff[j];
+                        const uint32_t ch = bwt[j];
+                        const uint32_t sample = (tx >= p.nr1_lo) & (p.nr1_big ^ 1u);
+                        const bool common = sf >= p.k_left && lcp[j] >= p.k_right;
+                        q0 = common && ch == c0 && sample == 0;  // raw byte compare, ref:clust2snp.cpp:455,466
+                        q1 = common && ch == c1 && sample == 1;
+                    }
+                    const uint32_t b0 = __ballot_sync(FULL, q0), b1 = __ballot_sync(FULL, q1);
+                    const uint32_t lt = (1u << lane) - 1u;
+                    if (q0) {
+                        uint32_t r = n0 + __popc(b0 & lt);
+                        if (r < p.cap) { t0[r] = tx; p0[r] = sf - p.k_left; }
+                    }
+                    if (q1) {
+                        uint32_t r = n1 + __popc(b1 & lt);
+                        if (r < p.cap) { t1[r] = tx; p1[r] = sf - p.k_left; }
+                    }
+                    n0 += __popc(b0);
+                    n1 += __popc(b1);
+                }
+                hdr.n0 = n0 < p.cap ? n0 : p.cap;
+                hdr.n1 = n1 < p.cap ? n1 : p.cap;
+                hdr.valid = (n0 > 0 && n1 > 0) ? 1u : 0u;
+            }
+            if (lane == 0) p.slots[slot] = hdr;
+        }
+    }
+}
+
+// valid slots, in order (single block: the list is tiny)
+__global__ void __launch_bounds__(1024) k_compact_slots(const CandSlot* __restrict__ slots, uint64_t n_slots,
+                                                        uint64_t* __restrict__ cand, SnpDev* dev) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint64_t s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (uint64_t i0 = 0; i0 < n_slots; i0 += 1024) {
+        const uint64_t i = i0 + threadIdx.x;
+        const uint32_t v = (i < n_slots) ? slots[i].valid : 0u;
+        const uint32_t b = __ballot_sync(FULL, v);
+        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(b);
+        __syncthreads();
+        uint32_t off = __popc(b & ((1u << (threadIdx.x & 31)) - 1u)), tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            if (w < int(threadIdx.x >> 5)) off += s_w[w];
+            tot += s_w[w];
+        }
+        if (v) cand[s_base + off] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) dev->n_slots_valid = s_base;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: contexts, consensus, support, distance
+// ---------------------------------------------------------------------------------------------
+struct PackedEventHdr {  // followed by left0[k_left] left1[k_left] right[k_right]
+    int32_t D, gap, supp0, supp1, right_len, flags;  // flags bit0 = variant (supp0>0 && supp1>0), bit1 = keep
+    uint64_t cluster_start;
+};
+
+struct EventParams {
+    const CandSlot* slots;
+    const uint32_t* slot_text;
+    const uint32_t* slot_pos;
+    const uint64_t* cand;
+    uint64_t n_cand;
+    uint32_t cap;
+    int32_t k_left, k_right, max_gap, max_err, max_snvs;
+    const uint8_t* bases;
+    const uint64_t* off;
+    uint64_t n_reads;
+    uint8_t* out;
+    uint32_t stride;
+    SnpDev* dev;
+};
+
+constexpr int EV_WARPS = 4;
+
+__global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
+    __shared__ uint64_t s_base[EV_WARPS][MAX_C_LEN];
+    __shared__ char s_cons[EV_WARPS][2][E2S_MAX_K];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t c = uint64_t(blockIdx.x) * EV_WARPS + w;
+    if (c >= p.n_cand) return;
+    const uint64_t slot = p.cand[c];
+    const CandSlot hdr = p.slots[slot];
+    const int kl = p.k_left;
+    bool bad = false;
+    uint32_t saw_n = 0;
+    int supp[2];
+
+    for (int s = 0; s < 2; ++s) {
+        const uint32_t nr = s ? hdr.n1 : hdr.n0;
+        const uint32_t* lt = p.slot_text + (slot * 2 + s) * p.cap;
+        const uint32_t* lp = p.slot_pos + (slot * 2 + s) * p.cap;
+        for (uint32_t j = lane; j < nr; j += 32) {
+            const uint64_t r = lt[j];
+            uint64_t b = 0;
+            if (r >= p.n_reads) bad = true;
+            else {
+                b = p.off[r] + lp[j];
+                if (b + uint64_t(kl) > p.off[r + 1]) bad = true;
+            }
+            s_base[w][j] = b;
+        }
+        bad = __any_sync(FULL, bad);
+        __syncwarp();
+        if (bad) break;
+        // cons::increment, ref:include.hpp:349-358: lane i owns context positions i, i+32, ...
+        for (int i = lane; i < kl; i += 32) {
+            uint32_t cnt[4] = {0, 0, 0, 0};
+            uint32_t cur = 'A';
+            for (uint32_t j = 0; j < nr; ++j) {
+                const uint32_t ch = p.bases[s_base[w][j] + i];
+                saw_n |= is_n(ch);
+                const uint32_t b = base_code(ch);
+                cnt[b]++;
+                if (cnt[b] > cnt[base_code(cur)]) cur = ch;
+            }
+            s_cons[w][s][i] = char(cur);
+        }
+        __syncwarp();
+        // support: reads within max_err mismatches of the consensus, ref:clust2snp.cpp:556-567
+        int sp = 0;
+        for (uint32_t j = 0; j < nr; ++j) {
+            int d = 0;
+            for (int i = lane; i < kl; i += 32) d += (uint8_t(s_cons[w][s][i]) != p.bases[s_base[w][j] + i]);
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+            sp += (d <= p.max_err);
+        }
+        supp[s] = sp;
+        __syncwarp();
+    }
+    if (bad) {
+        if (lane == 0) p.dev->bad_ref = 1;
+        return;
+    }
+    if (__any_sync(FULL, saw_n) && lane == 0) atomicOr(&p.dev->saw_n, 1ull);
+
+    uint8_t* o = p.out + c * p.stride;
+    PackedEventHdr* oh = reinterpret_cast<PackedEventHdr*>(o);
+    char* o_l0 = reinterpret_cast<char*>(o + sizeof(PackedEventHdr));
+    char* o_l1 = o_l0 + kl;
+    char* o_r = o_l1 + kl;
+    const bool variant = supp[0] > 0 && supp[1] > 0;
+
+    // right context = reads[idx].substr(pos, k_right), ref:clust2snp.cpp:604
+    int rl = 0;
+    if (variant) {
+        if (hdr.right_idx >= p.n_reads) bad = true;
+        else {
+            const uint64_t rb = p.off[hdr.right_idx], re = p.off[hdr.right_idx + 1];
+            if (hdr.right_pos > re - rb) bad = true;
+            else {
+                uint64_t avail = re - rb - hdr.right_pos;
+                rl = int(avail < uint64_t(p.k_right) ? avail : uint64_t(p.k_right));
+                for (int i = lane; i < rl; i += 32) o_r[i] = char(p.bases[rb + hdr.right_pos + i]);
+            }
+        }
+        if (bad) {
+            if (lane == 0) p.dev->bad_ref = 1;
+            return;
+        }
+    }
+    for (int i = lane; i < kl; i += 32) {
+        o_l0[i] = s_cons[w][0][i];
+        o_l1[i] = s_cons[w][1][i];
+    }
+
+    // distance(), ref:clust2snp.cpp:254-302.  g = 0: plain Hamming; g >= 1: drop g chars on the right of a / of b
+    const char* a = s_cons[w][0];
+    const char* b = s_cons[w][1];
+    uint32_t best_ab = 0xffffffffu, best_ba = 0xffffffffu;  // (dist << 8) | g : min => smallest dist, then smallest g
+    int d0 = 0;
+    for (int g = lane; g <= p.max_gap; g += 32) {
+        int dab = 0, dba = 0;
+        const int n = kl - g;  // compared length, right aligned
+        for (int i = 0; i < n; ++i) {
+            dab += a[kl - g - 1 - i] != b[kl - 1 - i];
+            dba += a[kl - 1 - i] != b[kl - g - 1 - i];
+        }
+        if (g == 0) d0 = dab;
+        else {
+            uint32_t kab = (uint32_t(dab + g) << 8) | uint32_t(g), kba = (uint32_t(dba + g) << 8) | uint32_t(g);
+            best_ab = kab < best_ab ? kab : best_ab;
+            best_ba = kba < best_ba ? kba : best_ba;
+        }
+    }
+    d0 = __shfl_sync(FULL, d0, 0);
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        uint32_t x = __shfl_xor_sync(FULL, best_ab, o2), y = __shfl_xor_sync(FULL, best_ba, o2);
+        best_ab = x < best_ab ? x : best_ab;
+        best_ba = y < best_ba ? y : best_ba;
+    }
+    int D, gap;
+    const int min_ab = int(best_ab >> 8), g_ab = int(best_ab & 0xff), min_ba = int(best_ba >> 8), g_ba = int(best_ba & 0xff);
+    if (d0 < min_ab && d0 < min_ba) { D = d0; gap = 0; }
+    else if (min_ab < min_ba) { D = min_ab - g_ab; gap = g_ab; }
+    else { D = min_ba - g_ba; gap = -g_ba; }
+    if (lane == 0) {
+        oh->D = D;
+        oh->gap = gap;
+        oh->supp0 = supp[0];
+        oh->supp1 = supp[1];
+        oh->right_len = rl;
+        oh->flags = (variant ? 1 : 0) | ((variant && D <= p.max_snvs) ? 2 : 0);
+        oh->cluster_start = hdr.cluster_start;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------
+struct SnpWork {
+    uint64_t* tile_first = nullptr; size_t tile_first_cap = 0;
+    uint32_t* flag_words = nullptr; size_t flag_cap = 0;
+    uint32_t* block_sum = nullptr; size_t block_sum_cap = 0;
+    uint64_t* flagged = nullptr; size_t flagged_cap = 0;
+    CandSlot* slots = nullptr; size_t slots_cap = 0;
+    uint32_t* slot_text = nullptr; uint32_t* slot_pos = nullptr; size_t slot_list_cap = 0;
+    uint64_t* cand = nullptr; size_t cand_cap = 0;
+    uint8_t* events = nullptr; size_t events_cap = 0;
+    SnpDev* dev = nullptr;
+    uint64_t n_cand = 0;
+    uint32_t stride = 0;
+    int k_left = 0, k_right = 0;
+};
+
+SnpWork* snp_work_create() { return new SnpWork(); }
+
+void snp_work_destroy(SnpWork* w) {
+    if (!w) return;
+    cudaFree(w->tile_first); cudaFree(w->flag_words); cudaFree(w->block_sum); cudaFree(w->flagged);
+    cudaFree(w->slots); cudaFree(w->slot_text); cudaFree(w->slot_pos); cudaFree(w->cand); cudaFree(w->events);
+    cudaFree(w->dev);
+    delete w;
+}
+
+template <typename T>
+static cudaError_t ensure(T*& ptr, size_t& cap, size_t need) {
+    if (need <= cap && ptr) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    size_t n = need + need / 4 + 64;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ptr), n * sizeof(T));
+    cap = e == cudaSuccess ? n : 0;
+    return e;
+}
+
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { *err = #x; return _e; } } while (0)
+
+cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int max_clust_length,
+                    const uint8_t* d_read_bases, const uint64_t* d_read_off, uint64_t n_reads, int sm_count,
+                    cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err) {
+    memset(counts, 0, sizeof *counts);
+    w->n_cand = 0;
+    w->k_left = p.k_left;
+    w->k_right = p.k_right;
+    if (!w->dev) CK(cudaMalloc(reinterpret_cast<void**>(&w->dev), sizeof(SnpDev)));
+    CK(cudaMemsetAsync(w->dev, 0, sizeof(SnpDev), stream));
+    if (a.m == 0 || a.n_local == 0) return cudaSuccess;
+
+    const uint32_t nr1_big = p.nr_reads1 > 0xffffffffull ? 1u : 0u;
+    const uint32_t nr1_lo = nr1_big ? 0xffffffffu : uint32_t(p.nr_reads1);
+    const uint32_t num_tiles = uint32_t((a.n_local + SC_T - 1) / SC_T);
+
+    CK(ensure(w->tile_first, w->tile_first_cap, size_t(num_tiles) + 1));
+    const uint64_t n_words = (a.m + 31) / 32;
+    CK(ensure(w->flag_words, w->flag_cap, size_t(n_words)));
+    CK(cudaMemsetAsync(w->flag_words, 0, n_words * 4, stream));
+    const uint32_t n_fblocks = uint32_t((n_words + FC_WORDS - 1) / FC_WORDS);
+    CK(ensure(w->block_sum, w->block_sum_cap, size_t(n_fblocks)));
+
+    k_tile_first<<<(num_tiles + 1 + 255) / 256, 256, 0, stream>>>(a.cl_start, a.m, a.global_off, num_tiles, w->tile_first);
+    CK(cudaGetLastError());
+    ++*launches;
+
+    ScanParams sp;
+    sp.a = a;
+    sp.tile_first = w->tile_first;
+    sp.num_tiles = num_tiles;
+    sp.min_len = uint32_t(2 * p.mcov_out);
+    sp.max_len = uint32_t(max_clust_length);
+    sp.mcov = uint32_t(p.mcov_out);
+    sp.k_right = uint32_t(p.k_right);
+    sp.nr1_lo = nr1_lo;
+    sp.nr1_big = nr1_big;
+    sp.flag_words = w->flag_words;
+    sp.dev = w->dev;
+    {
+        const size_t smem = size_t(SC_STAGES) * SC_STAGE_BYTES;
+        CK(cudaFuncSetAttribute(k_cluster_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_scan, SC_THREADS, smem));
+        if (occ < 1) occ = 1;
+        uint64_t grid = uint64_t(sm_count) * occ;
+        if (grid > num_tiles) grid = num_tiles;
+        k_cluster_scan<<<unsigned(grid), SC_THREADS, smem, stream>>>(sp);
+        CK(cudaGetLastError());
+        ++*launches;
+    }
+    k_flag_count<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum);
+    CK(cudaGetLastError());
+    ++*launches;
+    // the flagged list can be as long as m in theory; size it after counting
+    SnpDev hd;
+    {
+        // upper bound on the host needs the block sums: do emit in a second step once n_flagged is known
+        uint32_t* h_sums = static_cast<uint32_t*>(malloc(size_t(n_fblocks) * 4));
+        if (!h_sums) { *err = "malloc"; return cudaErrorMemoryAllocation; }
+        cudaError_t e = cudaMemcpyAsync(h_sums, w->block_sum, size_t(n_fblocks) * 4, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        uint64_t nf = 0;
+        for (uint32_t i = 0; i < n_fblocks; ++i) nf += h_sums[i];
+        free(h_sums);
+        if (e != cudaSuccess) { *err = "flag sums D2H"; return e; }
+        CK(ensure(w->flagged, w->flagged_cap, size_t(nf)));
+        k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum, w->flagged, w->dev);
+        CK(cudaGetLastError());
+        ++*launches;
+        counts->n_flagged = nf;
+    }
+    const uint64_t nf = counts->n_flagged;
+    const uint32_t cap = uint32_t(p.consensus_reads < MAX_C_LEN ? p.consensus_reads : MAX_C_LEN);
+    const uint64_t n_slots = nf * 4;
+    if (nf > 0) {
+        CK(ensure(w->slots, w->slots_cap, size_t(n_slots)));
+        if (size_t(n_slots) * 2 * cap > w->slot_list_cap || !w->slot_text) {
+            cudaFree(w->slot_text); cudaFree(w->slot_pos);
+            w->slot_text = w->slot_pos = nullptr;
+            size_t n = size_t(n_slots) * 2 * cap;
+            n += n / 4 + 64;
+            CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_text), n * 4));
+            CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_pos), n * 4));
+            w->slot_list_cap = n;
+        }
+        CK(ensure(w->cand, w->cand_cap, size_t(n_slots)));
+        CandParams cp;
+        cp.a = a;
+        cp.flagged = w->flagged;
+        cp.n_flagged = nf;
+        cp.mcov = uint32_t(p.mcov_out);
+        cp.k_left = uint32_t(p.k_left);
+        cp.k_right = uint32_t(p.k_right);
+        cp.cap = cap;
+        cp.nr1_lo = nr1_lo;
+        cp.nr1_big = nr1_big;
+        cp.slots = w->slots;
+        cp.slot_text = w->slot_text;
+        cp.slot_pos = w->slot_pos;
+        k_candidates<<<unsigned((nf + 3) / 4), 128, 0, stream>>>(cp);
+        CK(cudaGetLastError());
+        ++*launches;
+        k_compact_slots<<<1, 1024, 0, stream>>>(w->slots, n_slots, w->cand, w->dev);
+        CK(cudaGetLastError());
+        ++*launches;
+    }
+    CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    counts->n_analysed = hd.n_analysed;
+    counts->n_candidates = hd.n_slots_valid;
+    counts->saw_n = hd.saw_n;
+    const uint64_t nc = hd.n_slots_valid;
+    w->n_cand = nc;
+    w->stride = uint32_t((sizeof(PackedEventHdr) + 2 * size_t(p.k_left) + size_t(p.k_right) + 15) & ~size_t(15));
+    if (nc > 0) {
+        CK(ensure(w->events, w->events_cap, size_t(nc) * w->stride));
+        EventParams ep;
+        ep.slots = w->slots;
+        ep.slot_text = w->slot_text;
+        ep.slot_pos = w->slot_pos;
+        ep.cand = w->cand;
+        ep.n_cand = nc;
+        ep.cap = cap;
+        ep.k_left = p.k_left;
+        ep.k_right = p.k_right;
+        ep.max_gap = p.max_gap;
+        ep.max_err = p.max_err;
+        ep.max_snvs = p.max_snvs;
+        ep.bases = d_read_bases;
+        ep.off = d_read_off;
+        ep.n_reads = n_reads;
+        ep.out = w->events;
+        ep.stride = w->stride;
+        ep.dev = w->dev;
+        k_events<<<unsigned((nc + EV_WARPS - 1) / EV_WARPS), EV_WARPS * 32, 0, stream>>>(ep);
+        CK(cudaGetLastError());
+        ++*launches;
+        CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        counts->saw_n = hd.saw_n;
+        if (hd.bad_ref) { *err = "a candidate references a read/offset outside the staged reads"; return cudaErrorInvalidValue; }
+    }
+    return cudaSuccess;
+}
+
+// D2H of the packed candidates, then keep the variants (supp0>0 && supp1>0) in order
+cudaError_t snp_fetch_events(SnpWork* w, e2s_event* host, uint64_t cap, uint64_t* n, cudaStream_t stream) {
+    *n = 0;
+    if (w->n_cand == 0) return cudaSuccess;
+    const size_t bytes = size_t(w->n_cand) * w->stride;
+    uint8_t* tmp = static_cast<uint8_t*>(malloc(bytes));
+    if (!tmp) return cudaErrorMemoryAllocation;
+    cudaError_t e = cudaMemcpyAsync(tmp, w->events, bytes, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { free(tmp); return e; }
+    uint64_t k = 0;
+    for (uint64_t c = 0; c < w->n_cand; ++c) {
+        const uint8_t* o = tmp + c * w->stride;
+        const PackedEventHdr* h = reinterpret_cast<const PackedEventHdr*>(o);
+        if (!(h->flags & 1)) continue;
+        if (host && k < cap) {
+            e2s_event* ev = &host[k];
+            memset(ev, 0, sizeof *ev);
+            ev->D = h->D;
+            ev->gap = h->gap;
+            ev->supp0 = h->supp0;
+            ev->supp1 = h->supp1;
+            ev->right_len = h->right_len;
+            ev->keep = (h->flags & 2) ? 1 : 0;
+            ev->cluster_start = h->cluster_start;
+            const char* s = reinterpret_cast<const char*>(o + sizeof(PackedEventHdr));
+            memcpy(ev->left0, s, size_t(w->k_left));
+            memcpy(ev->left1, s + w->k_left, size_t(w->k_left));
+            memcpy(ev->right, s + 2 * w->k_left, size_t(h->right_len));
+        }
+        ++k;
+    }
+    free(tmp);
+    *n = k;
+    return cudaSuccess;
+}
+
+}  // namespace e2s

@@ -196,15 +196,18 @@ def build_egsa(reads: np.ndarray, device="cpu", chunk: int = 1 << 27):
 GESA_DTYPE_444 = np.dtype([("text", "<u4"), ("suff", "<u4"), ("lcp", "<u4"), ("bwt", "u1")])
 
 
+def _np(a):
+    return a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
+
+
 def gesa_records(egsa, x=4, y=4, z=4) -> np.ndarray:
     """Interleave into the on-disk record order text(y) suff(z) lcp(x) bwt(1), little endian."""
     dt = np.dtype([("text", f"<u{y}"), ("suff", f"<u{z}"), ("lcp", f"<u{x}"), ("bwt", "u1")])
     n = int(egsa["n"])
     rec = np.empty(n, dtype=dt)
     for name in ("text", "suff", "lcp"):
-        v = egsa[name].cpu().numpy().view(np.uint32)
-        rec[name] = v  # narrowing cast truncates like the file would
-    rec["bwt"] = egsa["bwt"].cpu().numpy()
+        rec[name] = _np(egsa[name]).view(np.uint32)  # narrowing cast truncates like the file would
+    rec["bwt"] = _np(egsa["bwt"])
     return rec
 
 
@@ -214,12 +217,12 @@ def write_gesa(path, egsa, x=4, y=4, z=4):
 
 def write_bcr(prefix, egsa, x=4, y=4, z=4):
     """BCR triple: .out (bwt), .out.lcp (lcp), .out.pairSA (suff(z) then text(y)) ref:include.hpp:157-188."""
-    egsa["bwt"].cpu().numpy().tofile(prefix + ".out")
-    egsa["lcp"].cpu().numpy().view(np.uint32).astype(f"<u{x}").tofile(prefix + ".out.lcp")
+    _np(egsa["bwt"]).tofile(prefix + ".out")
+    _np(egsa["lcp"]).view(np.uint32).astype(f"<u{x}").tofile(prefix + ".out.lcp")
     dt = np.dtype([("suff", f"<u{z}"), ("text", f"<u{y}")])
     rec = np.empty(int(egsa["n"]), dtype=dt)
-    rec["suff"] = egsa["suff"].cpu().numpy().view(np.uint32)
-    rec["text"] = egsa["text"].cpu().numpy().view(np.uint32)
+    rec["suff"] = _np(egsa["suff"]).view(np.uint32)
+    rec["text"] = _np(egsa["text"]).view(np.uint32)
     rec.tofile(prefix + ".out.pairSA")
 
 

@@ -1,0 +1,237 @@
+/*
+ * ebwt2snp_b200.h -- C ABI of the B200 (sm_100a) implementation of the ebwt2snp hot path:
+ * ebwt2clust's eBWT/LCP scan into positional clusters and clust2snp's per-cluster SNP/indel
+ * calling (reference: nicolaprezza/ebwt2snp; `ref:` citations are file:line in that tree).
+ *
+ * The reference exposes no plugin / FFI interface: its contract for this path is the process
+ * boundary of the two CLIs (argv + files).  This header is the thin layer between those CLIs
+ * (re-implemented in ebwt2snp_b200/host/) and the CUDA kernels; each entry point names the
+ * reference function whose work it takes over.  INTEGRATION.md shows the binding a maintainer
+ * of the reference would add to call it from ebwt2clust.cpp / clust2snp.cpp.
+ *
+ * Conventions: plain C types, caller-owned host buffers, int status return (0 = E2S_OK),
+ * no exceptions cross the boundary, no torch types.  A context is bound to one CUDA device
+ * and one stream; calls on one context are not thread-safe.  There is NO CPU fallback:
+ * every compute entry point fails with E2S_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Positions are eBWT positions (= EGSA records).  A *shard* is a contiguous range
+ * [global_off, global_off + n_local) of the n_global positions, resident in HBM as
+ * structure-of-arrays (lcp u32, text u32, suff u32, bwt u8) with the halos the kernels need
+ * (2 left / 1 right LCP values for the cluster flags, E2S_MAX_C_LEN records on the right for
+ * the per-cluster analysis).  One GPU holds one shard at a time; multi-GPU = one shard per
+ * GPU (or per process) plus e2s_cluster_merge() on the all-gathered summaries.
+ */
+#ifndef EBWT2SNP_B200_H
+#define EBWT2SNP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E2S_VERSION 100
+
+/* status codes */
+#define E2S_OK 0
+#define E2S_ERR_CUDA 1        /* CUDA runtime error / no device (message in e2s_last_error) */
+#define E2S_ERR_ARG 2         /* invalid argument */
+#define E2S_ERR_NOMEM 3       /* host or device allocation failed */
+#define E2S_ERR_UNSUPPORTED 4 /* input outside the supported domain (documented in DESIGN.md) */
+#define E2S_ERR_STATE 5       /* call sequence error (e.g. clusters not computed yet) */
+
+#define E2S_MAX_C_LEN 150 /* ref:clust2snp.cpp:32  max_clust_length_def (the -M option is unreachable) */
+#define E2S_MAX_K 128     /* largest -L / -R context length supported by the event records */
+#define E2S_HIST_BINS (E2S_MAX_C_LEN + 1)
+
+typedef struct e2s_ctx e2s_ctx;
+typedef struct e2s_shard e2s_shard;
+
+/* ---------------------------------------------------------------------------------------
+ * context
+ * ------------------------------------------------------------------------------------- */
+int e2s_version(void);
+int e2s_ctx_create(int device, e2s_ctx **out);
+void e2s_ctx_destroy(e2s_ctx *ctx);
+/* last error message of the context (or of the calling thread when ctx == NULL) */
+const char *e2s_last_error(const e2s_ctx *ctx);
+/* use an existing CUDA stream (cudaStream_t passed as void*) instead of the context's own */
+int e2s_ctx_set_stream(e2s_ctx *ctx, void *cuda_stream);
+int e2s_ctx_synchronize(e2s_ctx *ctx);
+/* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
+uint64_t e2s_ctx_launch_count(const e2s_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------
+ * shard residency  (replaces egsa_stream: ref:include.hpp:32-219)
+ * ------------------------------------------------------------------------------------- */
+int e2s_shard_create(e2s_ctx *ctx, uint64_t n_local, uint64_t global_off, uint64_t n_global, e2s_shard **out);
+void e2s_shard_destroy(e2s_shard *sh);
+
+/* Host array-of-structs EGSA records exactly as in X.gesa: text(y) suff(z) lcp(x) bwt(1),
+ * little endian, x,y,z in {1,2,4,8} (values wider than 32 bits truncated as ref:include.hpp:131,140,149).
+ * `records` holds `count` records, the first being global position `first`.  May be called
+ * repeatedly with consecutive chunks; the shard keeps what falls in
+ * [global_off - 2, global_off + n_local + E2S_MAX_C_LEN + 1) and ignores the rest.
+ * The copy is H2D of the raw bytes followed by a de-interleave kernel. */
+int e2s_shard_load_gesa(e2s_shard *sh, const void *records, uint64_t first, uint64_t count, int x, int y, int z);
+
+/* Host structure-of-arrays (BCR-like: ref:include.hpp:157-188).  Arrays may be NULL to skip a field. */
+int e2s_shard_load_soa(e2s_shard *sh, const uint32_t *lcp, const uint32_t *text, const uint32_t *suff,
+                       const uint8_t *bwt, uint64_t first, uint64_t count);
+/* Same, from DEVICE pointers on the context's device (device-to-device copies). */
+int e2s_shard_load_soa_dev(e2s_shard *sh, const uint32_t *d_lcp, const uint32_t *d_text, const uint32_t *d_suff,
+                           const uint8_t *d_bwt, uint64_t first, uint64_t count);
+/* Call once after the last load: on the last shard fills the records past n_global with the
+ * reference's post-EOF phantom record (ref:clust2snp.cpp:827-833). */
+int e2s_shard_seal(e2s_shard *sh);
+
+/* the read collection (FASTA bases), needed by e2s_find_events only: ref:clust2snp.cpp:147-212 */
+int e2s_reads_stage(e2s_ctx *ctx, const uint8_t *bases, const uint64_t *offsets /* n_reads+1 */, uint64_t n_reads);
+int e2s_reads_stage_dev(e2s_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+                        uint64_t n_bases);
+
+/* ---------------------------------------------------------------------------------------
+ * phase 1: ebwt2clust  (cluster_lm + append_entry: ref:ebwt2clust.cpp:54-139)
+ * ------------------------------------------------------------------------------------- */
+
+/* What one shard knows after its scan; plain u64 words so it can be all-gathered as is. */
+typedef struct {
+    uint64_t n_local, global_off, n_global;
+    uint64_t n_end;          /* closures (ENDs) inside the shard, head included */
+    uint64_t n_written;      /* records with both ends known locally and length >= min_len */
+    uint64_t head_end;       /* 1 + global position of an END whose START precedes the shard; 0 = none */
+    uint64_t any_event;      /* shard contains at least one START or END */
+    uint64_t open_start;     /* 1 + global START still open at the end of the shard; 0 = none */
+    uint64_t end_nm2_start;  /* last shard: 1 + START of the cluster closed at n_global-2, 0 = none,
+                                ~0 = that cluster is this shard's head (START unknown locally) */
+    uint64_t tail_lcp_nm2, tail_lcp_nm1, tail_bwt_nm1; /* last shard: lcp[n-2], lcp[n-1], bwt[n-1] */
+    uint64_t k, min_len;
+} e2s_cluster_summary;
+
+/* Result of merging all shard summaries, from the point of view of shard `my`. */
+typedef struct {
+    uint64_t record_offset;  /* index in the global .clusters of this shard's first record */
+    uint64_t total_written;  /* records in the global .clusters */
+    uint64_t n_clust_out;    /* closures, as printed by ref:ebwt2clust.cpp:137 (low 32 bits are printed) */
+    uint32_t phantom_lcp;    /* the post-EOF lcp value P that was applied */
+    uint32_t n_prepend;      /* 0/1: this shard's head record (goes before its own records) */
+    uint32_t n_append;       /* 0..2: tail records (last shard only; go after its own records) */
+    uint32_t n_adopt;        /* 0..3: records written by a later shard (its head) or by the tail rule whose START
+                                lies in this shard: phase 2 analyses them here */
+    uint64_t prepend_start; uint64_t prepend_len; uint64_t prepend_written; /* written = passes min_len */
+    uint64_t append_start[2]; uint64_t append_len[2];
+    uint64_t adopt_start[3]; uint64_t adopt_len[3];
+} e2s_cluster_merged;
+
+/* K1+K2 on the shard: LCP boundary stencil + decoupled look-back scan + compaction.
+ * Records stay on the device; *summary is written on the host. */
+int e2s_cluster_run(e2s_shard *sh, uint32_t k, int32_t min_len, e2s_cluster_summary *summary);
+/* Host-only integer logic (no CUDA): resolve shard heads, the tail + phantom rule, offsets. */
+int e2s_cluster_merge(const e2s_cluster_summary *all, int n_shards, int my, e2s_cluster_merged *out);
+/* Apply the merge to the device-resident record list of the shard (prepend/append records). */
+int e2s_cluster_finalize(e2s_shard *sh, const e2s_cluster_merged *merged);
+/* Single-shard convenience = run + merge(1 shard) + finalize; the whole of ebwt2clust's cluster_lm. */
+int e2s_cluster_lm(e2s_shard *sh, uint32_t k, int32_t min_len, uint64_t *n_written, uint64_t *n_clust_out);
+
+/* number of records in the shard's device list / copy them out (global start, wrapped u16 length) */
+int e2s_cluster_count(const e2s_shard *sh, uint64_t *m);
+int e2s_cluster_fetch(e2s_shard *sh, uint64_t *start, uint16_t *len, uint64_t cap, uint64_t *m);
+/* same, as the 10-byte records of the .clusters file (ref:ebwt2clust.cpp:58-59) */
+int e2s_cluster_fetch_packed(e2s_shard *sh, void *rec10, uint64_t cap_records, uint64_t *m);
+
+/* ---------------------------------------------------------------------------------------
+ * phase 2: clust2snp
+ * ------------------------------------------------------------------------------------- */
+
+/* Replace the shard's record list by records read from a .clusters file (clust2snp accepts the
+ * output of any ebwt2clust run).  Records must be position-ordered and disjoint (what
+ * ebwt2clust writes); anything else returns E2S_ERR_UNSUPPORTED. */
+int e2s_clusters_stage_packed(e2s_shard *sh, const void *rec10, uint64_t m);
+int e2s_clusters_stage(e2s_shard *sh, const uint64_t *start, const uint16_t *len, uint64_t m);
+
+/* statistics(): ref:clust2snp.cpp:877-966.  The device part is the length histogram of the
+ * shard's records; e2s_statistics_finish adds the reference's double count of the last record
+ * and runs the pval loop (one IEEE double division per step, on the host as in the reference). */
+typedef struct {
+    uint64_t hist[E2S_HIST_BINS];
+    uint64_t n_clust, n_bases;
+    uint64_t last_len;  /* length of the shard's last record (valid if n_clust > 0) */
+    uint64_t max_len;   /* filled by e2s_statistics_finish */
+    int32_t max_clust_length;
+    int32_t reserved;
+} e2s_stats;
+int e2s_statistics(e2s_shard *sh, e2s_stats *st);
+int e2s_statistics_finish(e2s_stats *sum_over_shards, uint64_t last_len_global, int mcov_out, double pval);
+
+typedef struct {
+    int32_t k_left;          /* -L 31 */
+    int32_t k_right;         /* -R 30 */
+    int32_t mcov_out;        /* -m 5  */
+    int32_t max_gap;         /* -g 10 */
+    int32_t consensus_reads; /* -c 20 */
+    int32_t max_err;         /* -e 2  */
+    int32_t max_snvs;        /* 3: ref:clust2snp.cpp:648 tests max_snvs_def, -v is dead */
+    int32_t reserved;
+    double pval;             /* -p 0.99 */
+    uint64_t nr_reads1;      /* -n */
+} e2s_snp_params;
+void e2s_snp_default_params(e2s_snp_params *p);
+
+/* one candidate that survived the support test (variant_t + distance(): ref:clust2snp.cpp:124-137,254-302) */
+typedef struct {
+    int32_t D;       /* mismatches outside the indel */
+    int32_t gap;     /* 0 SNP, >0 insert in sample 0, <0 insert in sample 1 */
+    int32_t supp0, supp1;
+    int32_t right_len;
+    int32_t keep;    /* 1 iff D <= max_snvs: the event is written to .snp */
+    uint64_t cluster_start; /* provenance: global start of the cluster */
+    char left0[E2S_MAX_K];
+    char left1[E2S_MAX_K];
+    char right[E2S_MAX_K];
+} e2s_event;
+
+typedef struct {
+    uint64_t n_analysed;   /* clusters passing 2m <= len <= max_clust_length */
+    uint64_t n_flagged;    /* of those, clusters passing find_variants' filters (ref:clust2snp.cpp:396-429) */
+    uint64_t n_candidates; /* "Done. C potential variants detected" ref:clust2snp.cpp:859 */
+    uint64_t n_variants;   /* supp0 > 0 and supp1 > 0, ref:clust2snp.cpp:595 */
+    uint64_t n_events;     /* D <= 3, written to .snp */
+    uint64_t saw_n;        /* an N/n met in BWT or contexts: the reference is non-deterministic there */
+} e2s_snp_counts;
+
+/* find_events(): K3 (per-cluster 2x4 histogram, first-argmax LCP, filters, ordered candidate
+ * enumeration) + K4 (gSA-driven context gather, consensus, support, distance).
+ * ref:clust2snp.cpp:367-500, 505-628, 254-302. */
+int e2s_find_events(e2s_shard *sh, const e2s_snp_params *p, int max_clust_length, e2s_snp_counts *counts);
+/* the n_variants surviving candidates in reference order */
+int e2s_events_fetch(e2s_shard *sh, e2s_event *events, uint64_t cap, uint64_t *n);
+/* to_file(): ref:clust2snp.cpp:633-780.  Host-only text formatting of the kept events; ids start
+ * at first_id (1 for a single shard).  *text is malloc'ed: release with e2s_free. */
+int e2s_events_format(const e2s_event *events, uint64_t n, uint64_t first_id, const e2s_snp_params *p,
+                      char **text, size_t *len);
+void e2s_free(void *p);
+
+/* ---------------------------------------------------------------------------------------
+ * end-to-end convenience over host buffers (what bench.py's `e2e` times)
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t n_written, n_clust_out;
+    int32_t max_clust_length;
+    int32_t reserved;
+    e2s_snp_counts snp;
+    uint64_t h2d_bytes, d2h_bytes;
+} e2s_pipeline_result;
+
+/* ebwt2clust + clust2snp on one GPU from host buffers: .gesa records + reads in, .clusters
+ * records (10-byte, into rec10 if non-NULL) and events out. */
+int e2s_pipeline_host(e2s_ctx *ctx, const void *gesa_records, uint64_t n, int x, int y, int z,
+                      const uint8_t *read_bases, const uint64_t *read_off, uint64_t n_reads,
+                      uint32_t k, int32_t min_len, const e2s_snp_params *p,
+                      void *rec10, uint64_t cap_records, e2s_event *events, uint64_t cap_events,
+                      e2s_pipeline_result *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EBWT2SNP_B200_H */

@@ -1,0 +1,129 @@
+"""-m gpu: the CUDA path, called through the C ABI, against the oracle (bit-exact: all integer work)."""
+import os
+
+import numpy as np
+import pytest
+
+from ebwt2snp_b200 import api, synth
+from oracle import oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def run_cluster(ctx, lcp, bwt, k, m):
+    n = len(lcp)
+    sh = ctx.shard(n)
+    sh.load_soa(lcp, None, None, bwt)
+    sh.seal()
+    nw, nc = sh.cluster_lm(k, m)
+    s, l = sh.cluster_fetch()
+    sh.close()
+    assert nw == len(s)
+    return s, l, nc
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_cluster_fuzz(ctx, variant, monkeypatch):
+    monkeypatch.setenv("E2S_CLUSTER_VARIANT", str(variant))
+    rng = np.random.default_rng(100 + variant)
+    sizes = [2, 3, 4, 5, 17, 255, 256, 257, 4095, 4096, 4097, 8191, 8192, 8193, 12289, 40000, 70001, 300000]
+    for it, n in enumerate(sizes * 2):
+        k = int(rng.choice([1, 2, 3, 5, 16, 70]))
+        m = int(rng.choice([1, 2, 3, 8]))
+        lcp = H.random_lcp(rng, n, k, it % 5)
+        bwt = rng.choice(H.BWT_ALPHABET, size=n)
+        es, el, enc, _ = O.cluster_lm(lcp, bwt, k, m)
+        s, l, nc = run_cluster(ctx, lcp, bwt, k, m)
+        assert nc == enc, (n, k, m, it)
+        assert np.array_equal(s, es) and np.array_equal(l, el), (n, k, m, it)
+
+
+def test_cluster_long_wrap(ctx):
+    """a 70 000-long run: length wraps mod 2^16 (ref:ebwt2clust.cpp:104)"""
+    n = 200000
+    lcp = np.zeros(n, dtype=np.uint32)
+    lcp[1000:71000] = 40
+    lcp[100000:100010] = 20
+    bwt = np.full(n, ord("A"), dtype=np.uint8)
+    es, el, enc, _ = O.cluster_lm(lcp, bwt, 16, 2)
+    s, l, nc = run_cluster(ctx, lcp, bwt, 16, 2)
+    assert nc == enc and np.array_equal(s, es) and np.array_equal(l, el)
+    assert 70000 - 65536 in set(el.tolist())
+
+
+def test_cluster_sharded(ctx):
+    """shards run one after the other on the same GPU + host merge == single pass"""
+    rng = np.random.default_rng(7)
+    for it in range(24):
+        n = int(rng.integers(30, 30000))
+        k = int(rng.choice([2, 5, 16]))
+        m = int(rng.choice([1, 2, 3]))
+        lcp = H.random_lcp(rng, n, k, it % 5)
+        bwt = rng.choice(H.BWT_ALPHABET, size=n)
+        es, el, enc, _ = O.cluster_lm(lcp, bwt, k, m)
+        nsh = int(rng.integers(2, 6))
+        cuts = sorted(set([0, n] + [int(c) for c in rng.integers(2, n - 2, size=nsh - 1)]))
+        cuts = [c for i, c in enumerate(cuts) if i == 0 or c - cuts[i - 1] >= 2 or c == n]
+        if n - cuts[-2] < 2:
+            cuts.pop(-2)
+        sums, recs = [], []
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            sh = ctx.shard(hi - lo, lo, n)
+            a, b = max(0, lo - 2), min(n, hi + 151)
+            sh.load_soa(lcp[a:b], None, None, bwt[a:b], first=a)
+            sh.seal()
+            sums.append(sh.cluster_run(k, m))
+            mg1 = api.cluster_merge([sums[-1]], 0) if (lo == 0 and hi == n) else None
+            # own records only (no merge applied yet)
+            sh.cluster_finalize(api.ClusterMerged())
+            recs.append(sh.cluster_fetch())
+            # emulation agrees with the kernel's summary
+            es_, rs_, rl_ = H.emulate_shard(lcp, bwt, lo, hi, k, m)
+            for f, _ in api.ClusterSummary._fields_:
+                assert getattr(sums[-1], f) == getattr(es_, f), (f, it, lo, hi)
+            assert np.array_equal(recs[-1][0], rs_) and np.array_equal(recs[-1][1], rl_)
+            sh.close()
+        S, L, mg = H.assemble(sums, recs)
+        assert mg.n_clust_out == enc, (it, cuts)
+        assert np.array_equal(S, es) and np.array_equal(L, el), (it, cuts)
+
+
+@pytest.mark.parametrize("name,seed", [("tiny", 1), ("tiny", 2), ("small", 1)])
+def test_pipeline_vs_oracle(ctx, name, seed):
+    rs, e = H.dataset(name, seed)
+    n = e["n"]
+    k, m = 16, 2
+    es, el, enc, _ = O.cluster_lm(e["lcp"], e["bwt"], k, m)
+    sh = ctx.shard(n)
+    rec = synth.gesa_records(e)
+    sh.load_gesa(rec.view(np.uint8).reshape(-1), 0, n)
+    sh.seal()
+    nw, nc = sh.cluster_lm(k, m)
+    s, l = sh.cluster_fetch()
+    assert nc == enc and np.array_equal(s, es) and np.array_equal(l, el)
+    assert sh.cluster_fetch_packed() == O.clusters_to_bytes(es, el)
+
+    for kw in ({}, {"mcov_out": 3}, {"consensus_reads": 3, "max_gap": 4}, {"k_left": 25, "k_right": 20, "max_err": 1}):
+        p = api.default_params(rs.nreads1, **kw)
+        op = O.default_params(rs.nreads1, **kw)
+        st = sh.statistics(p.mcov_out, p.pval)
+        ost = O.statistics(es, el, op.mcov_out, op.pval)
+        assert list(st.hist) == list(ost.hist) and st.n_clust == ost.n_clust and st.n_bases == ost.n_bases
+        assert st.max_clust_length == ost.max_clust_length and st.max_len == ost.max_len
+        off = O.uniform_read_offsets(*rs.reads.shape)
+        ctx.stage_reads(rs.reads, off)
+        cnt = sh.find_events(p, st.max_clust_length)
+        otext, ores = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+        assert (cnt.n_analysed, cnt.n_candidates, cnt.n_variants, cnt.n_events) == (
+            ores.n_analysed, ores.n_candidates, ores.n_variants, ores.n_events), kw
+        text = api.events_format(sh.events(), p)
+        assert text == otext, kw
+    sh.close()
