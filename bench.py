@@ -1,0 +1,477 @@
+#!/usr/bin/env python
+"""bench.py -- eBWT positions/s of the ebwt2clust + clust2snp hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C2]
+
+One "step" = one full pass of the hot path (cluster scan -> merge -> statistics -> per-cluster
+SNP calling) over the shard(s) resident in HBM.  `value` is device-resident throughput (CUDA
+events on the launch stream, max over ranks); `e2e` is the same metric through the C-ABI call a
+CLI makes (e2s_pipeline_host) from pinned HOST buffers, H2D + D2H inside the timed region.
+`--impl reference` times the unmodified reference binaries (oracle/_ref, single-threaded like
+the reference) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ebwt_positions_per_s"
+UNIT = "positions/s"
+K_DEF, M_DEF = 16, 2  # ebwt2clust defaults (ref:ebwt2clust.cpp:18-19)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# data
+# --------------------------------------------------------------------------------------------
+
+def make_dataset(workload, seed, scale, device):
+    from ebwt2snp_b200 import synth
+    t0 = time.time()
+    rs = synth.make_config(workload, seed=seed, scale=scale)
+    eg = synth.build_egsa(rs.reads, device=device)
+    log(f"[data] {workload} scale={scale} seed={seed}: reads={rs.reads.shape} n={eg['n']} built on {device} "
+        f"in {time.time() - t0:.1f}s")
+    return rs, eg
+
+
+def aos_records_pinned(eg, torch):
+    """13-byte .gesa records (text suff lcp bwt) in pinned host memory, interleaved on the device."""
+    n = int(eg["n"])
+    dev = eg["lcp"].device
+    rec = torch.empty((n, 13), dtype=torch.uint8, device=dev)
+    rec[:, 0:4] = eg["text"].view(torch.uint8).view(n, 4)
+    rec[:, 4:8] = eg["suff"].view(torch.uint8).view(n, 4)
+    rec[:, 8:12] = eg["lcp"].view(torch.uint8).view(n, 4)
+    rec[:, 12] = eg["bwt"]
+    host = torch.empty(n * 13, dtype=torch.uint8, pin_memory=True)
+    host.copy_(rec.view(-1))
+    del rec
+    return host
+
+
+# --------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: oracle/_ref binaries on a bounded sample
+# --------------------------------------------------------------------------------------------
+
+def reference_sample(workload, seed, target_positions, device):
+    """Writes a scaled-down instance of the workload (same coverage / read length) to a tmp dir."""
+    from ebwt2snp_b200 import synth
+    full = synth.CONFIGS[workload]
+    n_full = full["reads_per_sample"] * 2 * (2 if full["rc"] else 1) * (full["L"] + 1)
+    scale = min(1.0, target_positions / n_full)
+    rs, eg = make_dataset(workload, seed, scale, device)
+    d = tempfile.mkdtemp(prefix="e2s_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    fasta = synth.write_dataset(d, rs, eg)
+    return d, fasta, rs, eg, scale
+
+
+def run_reference_once(fasta, nreads1):
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    r1, ncl = O.ref_ebwt2clust(fasta)  # defaults -k 16 -m 2, -x 4 -y 4 -z 4
+    t1 = time.perf_counter()
+    r2, info = O.ref_clust2snp(fasta, nreads1)
+    t2 = time.perf_counter()
+    if r1.returncode != 0 or info["returncode"] != 0:
+        raise RuntimeError(f"reference failed: {r1.returncode} {info}")
+    return t1 - t0, t2 - t1, ncl, info
+
+
+def cpu_baseline_leg(args, device, check_ctx=None):
+    """Times the reference on a bounded sample; optionally checks the CUDA path on the same files."""
+    from oracle import oracle as O
+    if not O.ref_available():
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+    d, fasta, rs, eg, scale = reference_sample(args.workload, args.seed + 1000, args.cpu_positions, device)
+    try:
+        n = int(eg["n"])
+        tc, ts, ncl, info = run_reference_once(fasta, rs.nreads1)
+        out = {"value": n / (tc + ts), "unit": UNIT, "cores": 1, "kind": "reference",
+               "host_cores_total": os.cpu_count(),
+               "sample": f"{args.workload} scaled x{scale:.4f}: n={n} positions, ebwt2clust {tc:.2f}s + clust2snp {ts:.2f}s "
+                         f"(oracle/_ref, 1 thread: the reference is single-threaded)",
+               "ebwt2clust_positions_per_s": n / tc, "clust2snp_positions_per_s": n / ts}
+        if check_ctx is not None:
+            from ebwt2snp_b200 import api
+            sh = check_ctx.shard(n)
+            sh.load_soa(eg["lcp"], eg["text"], eg["suff"], eg["bwt"], device=True)
+            sh.seal()
+            sh.cluster_lm(K_DEF, M_DEF)
+            same_cl = sh.cluster_fetch_packed() == open(fasta + ".clusters", "rb").read()
+            p = api.default_params(rs.nreads1)
+            st = sh.statistics(p.mcov_out, p.pval)
+            check_ctx.stage_reads(rs.reads, O.uniform_read_offsets(*rs.reads.shape))
+            sh.find_events(p, st.max_clust_length)
+            snp = api.events_format(sh.events(), p)
+            same_snp = snp == open(os.path.join(d, "ALL.snp"), "rb").read()
+            out["parity_vs_reference_on_sample"] = bool(same_cl and same_snp)
+            sh.close()
+        return out
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    if not O.ref_available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binaries missing"}))
+        return
+    try:
+        import torch
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    except Exception:
+        device = "cpu"
+    d, fasta, rs, eg, scale = reference_sample(args.workload, args.seed + 1000, args.cpu_positions, device)
+    try:
+        n = int(eg["n"])
+        for _ in range(args.warmup):
+            run_reference_once(fasta, rs.nreads1)
+        t0 = time.perf_counter()
+        tcs = tss = 0.0
+        for _ in range(args.steps):
+            tc, ts, _, _ = run_reference_once(fasta, rs.nreads1)
+            tcs += tc
+            tss += ts
+        dt = time.perf_counter() - t0
+        v = n * args.steps / dt
+        sample = (f"{args.workload} scaled x{scale:.4f}: n={n} positions per step, ebwt2clust {tcs / args.steps:.2f}s + "
+                  f"clust2snp {tss / args.steps:.2f}s per step (oracle/_ref, 1 thread: the reference is single-threaded)")
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sample_positions": n},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample,
+                             "host_cores_total": os.cpu_count()},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def workload_name(args):
+    from ebwt2snp_b200 import synth
+    c = synth.CONFIGS[args.workload]
+    return (f"{args.workload}: synthetic {c['G']} bp genome, 2 samples x {c['reads_per_sample']} reads of {c['L']} bp"
+            f"{' + reverse complements' if c['rc'] else ''}, {c['n_snps']} SNPs, {c['n_indels']} indels; "
+            f"ebwt2clust -k 16 -m 2, clust2snp defaults, -x 4 -y 4 -z 4")
+
+
+# --------------------------------------------------------------------------------------------
+# the B200 arm
+# --------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-positions", type=float, default=3e7, help="size of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from ebwt2snp_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+
+    # ---- data: every rank owns one C2-size tile of a global eBWT of world * n positions (weak scaling) ----
+    rs, eg = make_dataset(args.workload, args.seed + rank, args.scale, dev)
+    n = int(eg["n"])
+    n_all = [n]
+    if world > 1:
+        t = torch.tensor([n], dtype=torch.int64, device=dev)
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        n_all = [int(x.item()) for x in g]
+    global_off, n_global = sum(n_all[:rank]), sum(n_all)
+
+    stream = torch.cuda.Stream(device=dev)
+    ctx = api.Context(local, stream.cuda_stream)
+    sh = ctx.shard(n, global_off, n_global)
+    sh.load_soa(eg["lcp"], eg["text"], eg["suff"], eg["bwt"], first=global_off, device=True)
+    if world > 1:
+        # halo exchange over NCCL: my left neighbour's last 2 records, my right neighbour's first 151
+        H = api.MAX_C_LEN + 1
+        edge = torch.zeros((2 + H) * 4, dtype=torch.int32, device=dev)  # [lcp,text,suff,bwt] x (tail2 + head151)
+        def pack(a, b):
+            return torch.cat([eg["lcp"][a:b], eg["text"][a:b], eg["suff"][a:b], eg["bwt"][a:b].to(torch.int32)])
+        mine = torch.cat([pack(n - 2, n), pack(0, H)])
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        if rank > 0:
+            t2 = allv[rank - 1][:8].view(4, 2)
+            sh.load_soa(t2[0].contiguous(), t2[1].contiguous(), t2[2].contiguous(), t2[3].to(torch.uint8).contiguous(),
+                        first=global_off - 2, device=True)
+        if rank < world - 1:
+            h = allv[rank + 1][8:].view(4, H)
+            sh.load_soa(h[0].contiguous(), h[1].contiguous(), h[2].contiguous(), h[3].to(torch.uint8).contiguous(),
+                        first=global_off + n, device=True)
+        del edge
+    sh.seal()
+    reads_dev = torch.from_numpy(rs.reads).to(dev).view(-1)
+    R, L = rs.reads.shape
+    off_dev = (torch.arange(R + 1, dtype=torch.int64, device=dev) * L)
+    ctx.stage_reads(reads_dev, off_dev, device=True, n_bases=R * L)
+    params = api.default_params(rs.nreads1)
+
+    host_rec = None
+    if not args.no_e2e:
+        host_rec = aos_records_pinned(eg, torch)
+    # generator arrays are no longer needed on the device
+    for kk in ("lcp", "text", "suff", "bwt"):
+        eg[kk] = None
+    torch.cuda.empty_cache()
+
+    W = api.SUMMARY_WORDS
+
+    def step():
+        """one pass of the hot path over the resident shard(s)"""
+        s = sh.cluster_run(K_DEF, M_DEF)
+        if world > 1:
+            mine = torch.from_numpy(np.frombuffer(bytes(s), dtype=np.int64).copy()).to(dev)
+            allv = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allv, mine)  # NCCL over NVLink: W u64 words per shard
+            sums = [api.ClusterSummary.from_buffer_copy(a.cpu().numpy().tobytes()) for a in allv]
+        else:
+            sums = [s]
+        mg = api.cluster_merge(sums, rank)
+        sh.cluster_finalize(mg)
+        st = sh.statistics(finish=False)
+        last_len = st.last_len
+        if world > 1:
+            v = torch.tensor(list(st.hist) + [st.n_clust, st.n_bases, st.last_len], dtype=torch.int64, device=dev)
+            allv = [torch.zeros_like(v) for _ in range(world)]
+            dist.all_gather(allv, v)
+            tot = torch.stack(allv).sum(0).tolist()
+            for i in range(api.HIST_BINS):
+                st.hist[i] = tot[i]
+            st.n_clust, st.n_bases = tot[api.HIST_BINS], tot[api.HIST_BINS + 1]
+            for a in allv:  # the globally last record
+                if int(a[api.HIST_BINS]) > 0:
+                    last_len = int(a[api.HIST_BINS + 2])
+        api.statistics_finish(st, last_len, params.mcov_out, params.pval)
+        cnt = sh.find_events(params, st.max_clust_length)
+        if world > 1:  # global event ids = exclusive prefix of the per-shard kept-event counts
+            v = torch.tensor([cnt.n_events], dtype=torch.int64, device=dev)
+            allv = [torch.zeros_like(v) for _ in range(world)]
+            dist.all_gather(allv, v)
+        return mg, st, cnt
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            mg, st, cnt = step()
+        sync_all()
+        ctx.timing(True)
+        ctx.kernel_time(api.KERNEL_CLUSTER)
+        ctx.kernel_time(api.KERNEL_SCAN)
+        launches0 = ctx.launches
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            mg, st, cnt = step()
+        ev1.record(stream)
+        sync_all()
+        ms = ev0.elapsed_time(ev1)
+        clocks = sampler.stop()
+        launches = ctx.launches - launches0
+        k_cl_ms, k_cl_n = ctx.kernel_time(api.KERNEL_CLUSTER)
+        k_sc_ms, k_sc_n = ctx.kernel_time(api.KERNEL_SCAN)
+        ctx.timing(False)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_global * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the two kernels that touch every position (this rank's shard) ----
+    peak, peak_src = hbm_peak()
+    m_own = sh.cluster_count()
+    lo, hi = 2 * params.mcov_out, st.max_clust_length
+    # positions inside analysed clusters: from the (global) histogram, scaled to this shard for world > 1
+    pos_analysed = sum(int(st.hist[l]) * l for l in range(lo, hi + 1)) / world
+    bytes_cluster = 4 * n + 10 * m_own
+    bytes_scan = 10 * m_own + 9 * pos_analysed
+    kern = {}
+    if k_cl_n:
+        kern["k_cluster"] = {"ms": k_cl_ms / k_cl_n, "alg_bytes": bytes_cluster,
+                             "GBps": bytes_cluster / (k_cl_ms / k_cl_n * 1e-3) / 1e9}
+    if k_sc_n:
+        kern["k_cluster_scan"] = {"ms": k_sc_ms / k_sc_n, "alg_bytes": bytes_scan,
+                                  "GBps": bytes_scan / (k_sc_ms / k_sc_n * 1e-3) / 1e9,
+                                  "streamed_bytes": 9 * n + 10 * m_own,
+                                  "streamed_GBps": (9 * n + 10 * m_own) / (k_sc_ms / k_sc_n * 1e-3) / 1e9}
+    dom = max(kern, key=lambda kname: kern[kname]["ms"]) if kern else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "ms_per_launch": kern[dom]["ms"], "alg_bytes_per_launch": kern[dom]["alg_bytes"],
+                    "kernels": kern, "kernel_share_of_step": (k_cl_ms + k_sc_ms) / ms if ms else None}
+
+    # ---- e2e: the C-ABI pipeline call from pinned host buffers, copies inside the timed region ----
+    e2e = None
+    if host_rec is not None:
+        reads_pin = torch.from_numpy(rs.reads).view(-1).pin_memory()
+        off_pin = (torch.arange(R + 1, dtype=torch.int64) * L).pin_memory()
+        sh.close()  # free the resident shard: the pipeline call owns its own
+        torch.cuda.empty_cache()
+        rec10 = torch.empty((m_own + 16) * 10, dtype=torch.uint8, pin_memory=True)
+        evbuf = (api.Event * (int(cnt.n_variants) + 16))()
+        rec10_np = rec10.numpy()
+        for _ in range(1):
+            res = ctx.pipeline_host(host_rec, n, reads_pin, off_pin, params, K_DEF, M_DEF, rec10=rec10_np, events=evbuf)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            res = ctx.pipeline_host(host_rec, n, reads_pin, off_pin, params, K_DEF, M_DEF, rec10=rec10_np, events=evbuf)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": n_global * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(res.h2d_bytes),
+               "d2h_bytes_per_step": int(res.d2h_bytes), "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "steps": args.e2e_steps, "api": "e2s_pipeline_host (13-byte .gesa records + reads in, .clusters records + events out)",
+               "h2d_GBps": res.h2d_bytes * args.e2e_steps / dt / 1e9,
+               "n_events": int(res.snp.n_events), "n_written": int(res.n_written)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_leg(args, dev, check_ctx=ctx)
+
+    if rank == 0:
+        c_ratio = m_own / n
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "positions_per_gpu": n, "positions_total": n_global,
+                       "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; NCCL all-gather of shard summaries",
+                       "l2": "inputs (13 B/position, >= 7 GB per GPU at C2) exceed the 126 MB L2; no flush needed",
+                       "scale": args.scale},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "results": {"n_written": int(mg.total_written), "n_clust_out": int(mg.n_clust_out),
+                        "max_clust_length": int(st.max_clust_length), "n_analysed_rank0": int(cnt.n_analysed),
+                        "n_candidates_rank0": int(cnt.n_candidates), "n_events_rank0": int(cnt.n_events),
+                        "clusters_per_position": c_ratio, "fraction_in_analysed_clusters": pos_analysed / n},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,7 @@ MAX_C_LEN = 150
 MAX_K = 128
 HIST_BINS = MAX_C_LEN + 1
 
+KERNEL_CLUSTER, KERNEL_SCAN = 0, 1
 OK, ERR_CUDA, ERR_ARG, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = range(6)
 
 
@@ -78,7 +79,7 @@ class PipelineResult(C.Structure):
 # every symbol include/ebwt2snp_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
     "e2s_version", "e2s_ctx_create", "e2s_ctx_destroy", "e2s_last_error", "e2s_ctx_set_stream",
-    "e2s_ctx_synchronize", "e2s_ctx_launch_count", "e2s_shard_create", "e2s_shard_destroy", "e2s_shard_load_gesa",
+    "e2s_ctx_synchronize", "e2s_ctx_launch_count", "e2s_ctx_timing", "e2s_ctx_kernel_time", "e2s_shard_create", "e2s_shard_destroy", "e2s_shard_load_gesa",
     "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_shard_seal", "e2s_reads_stage", "e2s_reads_stage_dev",
     "e2s_cluster_run", "e2s_cluster_merge", "e2s_cluster_finalize", "e2s_cluster_lm", "e2s_cluster_count",
     "e2s_cluster_fetch", "e2s_cluster_fetch_packed", "e2s_clusters_stage_packed", "e2s_clusters_stage",
@@ -110,6 +111,8 @@ def load_library():
     lib.e2s_ctx_destroy.argtypes = [C.c_void_p]
     lib.e2s_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.e2s_ctx_synchronize.argtypes = [C.c_void_p]
+    lib.e2s_ctx_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.e2s_ctx_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.e2s_shard_create.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
     lib.e2s_shard_destroy.argtypes = [C.c_void_p]
     lib.e2s_shard_load_gesa.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
@@ -229,6 +232,15 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.e2s_ctx_launch_count(self.h))
+
+    def timing(self, enable=True):
+        self._ck(self.lib.e2s_ctx_timing(self.h, int(enable)))
+
+    def kernel_time(self, kernel):
+        """(total ms, launches) of KERNEL_CLUSTER / KERNEL_SCAN since the last call (CUDA events on the stream)"""
+        ms, cnt = C.c_double(), C.c_uint64()
+        self._ck(self.lib.e2s_ctx_kernel_time(self.h, kernel, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     def stage_reads(self, bases, offsets, device=False, n_bases=None):
         n_reads = len(offsets) - 1

@@ -32,6 +32,7 @@ struct e2s_ctx {
     size_t raw_cap = 0;
     // cached shard for e2s_pipeline_host
     e2s_shard* cached = nullptr;
+    KernelTimer timer;
 };
 
 struct e2s_shard {
@@ -141,6 +142,38 @@ int e2s_ctx_synchronize(e2s_ctx* c) {
 }
 
 uint64_t e2s_ctx_launch_count(const e2s_ctx* c) { return c ? c->launches : 0; }
+
+int e2s_ctx_timing(e2s_ctx* c, int enable) {
+    if (!c) return fail(nullptr, E2S_ERR_ARG, "ctx == NULL");
+    c->timer.enabled = enable != 0;
+    return E2S_OK;
+}
+
+int e2s_ctx_kernel_time(e2s_ctx* c, int kernel, double* total_ms, uint64_t* launches) {
+    if (!c || !total_ms || !launches || kernel < 0 || kernel >= E2S_KERNEL_COUNT) return fail(c, E2S_ERR_ARG, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    double ms = 0;
+    uint64_t cnt = 0;
+    std::vector<KernelTimer::Rec> keep;
+    for (auto& r : c->timer.recs) {
+        if (r.id != kernel) {
+            keep.push_back(r);
+            continue;
+        }
+        float t = 0;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            ms += t;
+            ++cnt;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    c->timer.recs.swap(keep);
+    *total_ms = ms;
+    *launches = cnt;
+    return E2S_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // shard residency
@@ -380,7 +413,10 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
         p.res = s->d_res;
         p.num_tiles = uint32_t(num_tiles);
         int grid = 0;
-        CU(c, launch_cluster(p, s->alloc_r / 16, c->sm_count, c->stream, s->variant, &grid));
+        c->timer.begin(E2S_KERNEL_CLUSTER, c->stream);
+        cudaError_t le = launch_cluster(p, s->alloc_r / 16, c->sm_count, c->stream, s->variant, &grid);
+        c->timer.end(c->stream);
+        CU(c, le);
         ++c->launches;
         CU(c, cudaMemcpyAsync(&h, s->d_res, sizeof h, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
@@ -753,7 +789,7 @@ int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length,
     a.m = s->m_list;
     const char* err = "";
     cudaError_t e = snp_run(s->work, a, *p, max_clust_length, c->d_bases, c->d_off, c->n_reads, c->sm_count, c->stream,
-                            counts, &c->launches, &err);
+                            counts, &c->launches, &err, &c->timer);
     if (e == cudaErrorInvalidValue && err && strstr(err, "outside the staged reads")) return fail(c, E2S_ERR_UNSUPPORTED, err);
     if (e != cudaSuccess) return cuda_fail(c, e, err);
     // candidates are few: bring them to the host now and keep the variants

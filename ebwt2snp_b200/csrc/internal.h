@@ -6,7 +6,29 @@
 
 #include "../../include/ebwt2snp_b200.h"
 
+#include <vector>
+
 namespace e2s {
+
+// CUDA-event timing of selected kernels on the launch stream (enabled by e2s_ctx_timing)
+struct KernelTimer {
+    bool enabled = false;
+    struct Rec { int id; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    void begin(int id, cudaStream_t s) {
+        if (!enabled) return;
+        Rec r;
+        r.id = id;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, s);
+        recs.push_back(r);
+    }
+    void end(cudaStream_t s) {
+        if (!enabled || recs.empty()) return;
+        cudaEventRecord(recs.back().b, s);
+    }
+};
 
 // ---- phase 1 ---------------------------------------------------------------------------------
 struct ClusterDev {  // device-resident accumulators of one e2s_cluster_run (zeroed before the launch)
@@ -89,7 +111,8 @@ void snp_work_destroy(SnpWork* w);
 // (it needs small counts on the host to size the next launch).
 cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int max_clust_length,
                     const uint8_t* d_read_bases, const uint64_t* d_read_off, uint64_t n_reads, int sm_count,
-                    cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err);
+                    cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err,
+                    KernelTimer* timer);
 cudaError_t snp_fetch_events(SnpWork* w, e2s_event* host, uint64_t cap, uint64_t* n, cudaStream_t stream);
 
 }  // namespace e2s

@@ -628,7 +628,8 @@ static cudaError_t ensure(T*& ptr, size_t& cap, size_t need) {
 
 cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int max_clust_length,
                     const uint8_t* d_read_bases, const uint64_t* d_read_off, uint64_t n_reads, int sm_count,
-                    cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err) {
+                    cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err,
+                    KernelTimer* timer) {
     memset(counts, 0, sizeof *counts);
     w->n_cand = 0;
     w->k_left = p.k_left;
@@ -672,7 +673,9 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
         if (occ < 1) occ = 1;
         uint64_t grid = uint64_t(sm_count) * occ;
         if (grid > num_tiles) grid = num_tiles;
+        if (timer) timer->begin(E2S_KERNEL_SCAN, stream);
         k_cluster_scan<<<unsigned(grid), SC_THREADS, smem, stream>>>(sp);
+        if (timer) timer->end(stream);
         CK(cudaGetLastError());
         ++*launches;
     }

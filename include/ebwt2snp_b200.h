@@ -61,6 +61,14 @@ int e2s_ctx_set_stream(e2s_ctx *ctx, void *cuda_stream);
 int e2s_ctx_synchronize(e2s_ctx *ctx);
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 uint64_t e2s_ctx_launch_count(const e2s_ctx *ctx);
+/* Per-kernel device time, measured with CUDA events recorded on the context's stream around the
+ * two kernels that touch every position (bench.py's roofline).  e2s_ctx_kernel_time synchronises
+ * the stream, returns the time and launch count accumulated since the last call and resets them. */
+#define E2S_KERNEL_CLUSTER 0 /* K1+K2: LCP stencil + look-back scan + compaction */
+#define E2S_KERNEL_SCAN 1    /* K3a: per-cluster histogram / filters */
+#define E2S_KERNEL_COUNT 2
+int e2s_ctx_timing(e2s_ctx *ctx, int enable);
+int e2s_ctx_kernel_time(e2s_ctx *ctx, int kernel, double *total_ms, uint64_t *launches);
 
 /* ---------------------------------------------------------------------------------------
  * shard residency  (replaces egsa_stream: ref:include.hpp:32-219)
