@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 METRIC = "ebwt_positions_per_s"
 UNIT = "positions/s"
 K_DEF, M_DEF = 16, 2  # ebwt2clust defaults (ref:ebwt2clust.cpp:18-19)
+KERNELS = {0: "k_lcp_flags", 1: "k_cluster_emit", 2: "k_code_scan", 3: "k_cluster_exact"}
 
 
 def log(*a):
@@ -365,8 +366,8 @@ def main():
             mg, st, cnt = step()
         sync_all()
         ctx.timing(True)
-        ctx.kernel_time(api.KERNEL_CLUSTER)
-        ctx.kernel_time(api.KERNEL_SCAN)
+        for kid in KERNELS:
+            ctx.kernel_time(kid)
         launches0 = ctx.launches
         sampler = ClockSampler(local)
         sampler.start()
@@ -380,8 +381,7 @@ def main():
         ms = ev0.elapsed_time(ev1)
         clocks = sampler.stop()
         launches = ctx.launches - launches0
-        k_cl_ms, k_cl_n = ctx.kernel_time(api.KERNEL_CLUSTER)
-        k_sc_ms, k_sc_n = ctx.kernel_time(api.KERNEL_SCAN)
+        ktimes = {kid: ctx.kernel_time(kid) for kid in KERNELS}
         ctx.timing(False)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -395,17 +395,26 @@ def main():
     lo, hi = 2 * params.mcov_out, st.max_clust_length
     # positions inside analysed clusters: from the (global) histogram, scaled to this shard for world > 1
     pos_analysed = sum(int(st.hist[l]) * l for l in range(lo, hi + 1)) / world
-    bytes_cluster = 4 * n + 10 * m_own
-    bytes_scan = 10 * m_own + 9 * pos_analysed
+    # algorithmic bytes per launch (DESIGN.md "Kernels"): what the kernel has to move for this shard
+    alg = {
+        api.KERNEL_FLAGS: 4 * n + n / 4,                # LCP read once + 2 bit masks written
+        api.KERNEL_EMIT: n / 4 + 10 * m_own,            # bit masks read + 10-byte records written
+        api.KERNEL_SCAN: pos_analysed + 10 * m_own,     # BWT byte of positions in analysed clusters + record list
+        api.KERNEL_EXACT: 0,
+    }
+    streamed = {api.KERNEL_SCAN: n + 10 * m_own}        # the tiles also carry the positions outside clusters
     kern = {}
-    if k_cl_n:
-        kern["k_cluster"] = {"ms": k_cl_ms / k_cl_n, "alg_bytes": bytes_cluster,
-                             "GBps": bytes_cluster / (k_cl_ms / k_cl_n * 1e-3) / 1e9}
-    if k_sc_n:
-        kern["k_cluster_scan"] = {"ms": k_sc_ms / k_sc_n, "alg_bytes": bytes_scan,
-                                  "GBps": bytes_scan / (k_sc_ms / k_sc_n * 1e-3) / 1e9,
-                                  "streamed_bytes": 9 * n + 10 * m_own,
-                                  "streamed_GBps": (9 * n + 10 * m_own) / (k_sc_ms / k_sc_n * 1e-3) / 1e9}
+    ksum_ms = 0.0
+    for kid, name in KERNELS.items():
+        tot_ms, cnt_l = ktimes[kid]
+        if not cnt_l:
+            continue
+        ksum_ms += tot_ms
+        per = tot_ms / cnt_l
+        kern[name] = {"ms": per, "alg_bytes": alg[kid], "GBps": alg[kid] / (per * 1e-3) / 1e9}
+        if kid in streamed:
+            kern[name]["streamed_bytes"] = streamed[kid]
+            kern[name]["streamed_GBps"] = streamed[kid] / (per * 1e-3) / 1e9
     dom = max(kern, key=lambda kname: kern[kname]["ms"]) if kern else None
     traffic = None
     try:
@@ -418,7 +427,7 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
                     "frac": kern[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
                     "ms_per_launch": kern[dom]["ms"], "alg_bytes_per_launch": kern[dom]["alg_bytes"],
-                    "kernels": kern, "kernel_share_of_step": (k_cl_ms + k_sc_ms) / ms if ms else None}
+                    "kernels": kern, "kernel_share_of_step": ksum_ms / ms if ms else None}
 
     # ---- e2e: the C-ABI pipeline call from pinned host buffers, copies inside the timed region ----
     e2e = None

@@ -20,7 +20,7 @@ MAX_C_LEN = 150
 MAX_K = 128
 HIST_BINS = MAX_C_LEN + 1
 
-KERNEL_CLUSTER, KERNEL_SCAN = 0, 1
+KERNEL_FLAGS, KERNEL_EMIT, KERNEL_SCAN, KERNEL_EXACT = 0, 1, 2, 3
 OK, ERR_CUDA, ERR_ARG, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = range(6)
 
 
@@ -237,7 +237,7 @@ class Context:
         self._ck(self.lib.e2s_ctx_timing(self.h, int(enable)))
 
     def kernel_time(self, kernel):
-        """(total ms, launches) of KERNEL_CLUSTER / KERNEL_SCAN since the last call (CUDA events on the stream)"""
+        """(total ms, launches) of KERNEL_FLAGS / _EMIT / _SCAN / _EXACT since the last call (CUDA events on the stream)"""
         ms, cnt = C.c_double(), C.c_uint64()
         self._ck(self.lib.e2s_ctx_kernel_time(self.h, kernel, C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value

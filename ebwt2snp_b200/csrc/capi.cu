@@ -53,6 +53,8 @@ struct e2s_shard {
     bool have_clusters = false, staged = false, finalized = false;
     e2s_cluster_merged merged;
     // scan scratch
+    uint32_t* d_flags = nullptr;  // START words then END words
+    uint64_t flag_words = 0;
     uint64_t* d_desc = nullptr;
     size_t desc_cap = 0;
     ClusterDev* d_res = nullptr;
@@ -233,6 +235,7 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->d_start);
     cudaFree(s->d_len);
     cudaFree(s->d_desc);
+    cudaFree(s->d_flags);
     cudaFree(s->d_res);
     cudaFree(s->d_hist);
     snp_work_destroy(s->work);
@@ -379,9 +382,7 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
     CU(c, cudaSetDevice(c->device));
     const char* env = getenv("E2S_CLUSTER_VARIANT");
     s->variant = env ? atoi(env) : 0;
-    const uint64_t T = uint64_t(cluster_tile_positions(s->variant));
-    const uint64_t num_tiles = (s->n_local + T - 1) / T;
-    if (num_tiles > 0x7fffffffull) return fail(c, E2S_ERR_UNSUPPORTED, "shard too large");
+    const uint64_t num_tiles = emit_num_tiles(s->n_local);
     if (num_tiles * 2 > s->desc_cap) {
         cudaFree(s->d_desc);
         s->d_desc = nullptr;
@@ -390,20 +391,44 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
             return fail(c, E2S_ERR_NOMEM, "tile descriptors");
         s->desc_cap = num_tiles * 2;
     }
+    if (!s->d_flags) {
+        s->flag_words = flags_words_needed(s->n_local);
+        if (cudaMalloc(reinterpret_cast<void**>(&s->d_flags), s->flag_words * 2 * 4) != cudaSuccess)
+            return fail(c, E2S_ERR_NOMEM, "flag masks");
+        // K1 overwrites the words of its tiles; the tail up to K2's tile size stays zero
+        CU(c, cudaMemsetAsync(s->d_flags, 0, s->flag_words * 2 * 4, c->stream));
+    }
     if (!s->d_start) {
         int rc = ensure_records(s, s->n_local / 8 + 4096);
         if (rc) return rc;
+    }
+    // K1: LCP -> START/END masks
+    {
+        FlagParams fp;
+        fp.lcp = s->lcp;
+        fp.n_local = s->n_local;
+        fp.global_off = s->global_off;
+        fp.n_global = s->n_global;
+        fp.k = k;
+        fp.num_tiles = 0;
+        fp.s_words = s->d_flags;
+        fp.e_words = s->d_flags + s->flag_words;
+        c->timer.begin(E2S_KERNEL_FLAGS, c->stream);
+        cudaError_t le = launch_flags(fp, s->alloc_r / 32, c->sm_count, c->stream, s->variant);
+        c->timer.end(c->stream);
+        CU(c, le);
+        ++c->launches;
     }
     ClusterDev h;
     for (int attempt = 0; attempt < 2; ++attempt) {
         CU(c, cudaMemsetAsync(s->d_desc, 0, num_tiles * 2 * 8, c->stream));
         CU(c, cudaMemsetAsync(s->d_res, 0, sizeof(ClusterDev), c->stream));
-        ClusterParams p;
-        p.lcp = s->lcp;
-        p.n_local = s->n_local;
+        EmitParams p;
+        p.s_words = s->d_flags;
+        p.e_words = s->d_flags + s->flag_words;
+        p.num_tiles = num_tiles;
         p.global_off = s->global_off;
         p.n_global = s->n_global;
-        p.k = k;
         p.min_len = min_len;
         p.out_start = s->d_start;
         p.out_len = s->d_len;
@@ -411,10 +436,8 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
         p.desc_state = s->d_desc;
         p.desc_cnt = s->d_desc + num_tiles;
         p.res = s->d_res;
-        p.num_tiles = uint32_t(num_tiles);
-        int grid = 0;
-        c->timer.begin(E2S_KERNEL_CLUSTER, c->stream);
-        cudaError_t le = launch_cluster(p, s->alloc_r / 16, c->sm_count, c->stream, s->variant, &grid);
+        c->timer.begin(E2S_KERNEL_EMIT, c->stream);
+        cudaError_t le = launch_emit(p, c->sm_count, c->stream);
         c->timer.end(c->stream);
         CU(c, le);
         ++c->launches;

@@ -42,10 +42,20 @@ struct ClusterDev {  // device-resident accumulators of one e2s_cluster_run (zer
     unsigned long long pad;
 };
 
-struct ClusterParams {
+struct FlagParams {  // K1
     const uint32_t* lcp;  // local position 0 (PAD_L readable elements before it)
     uint64_t n_local, global_off, n_global;
     uint32_t k;
+    uint32_t num_tiles;  // filled by the launcher
+    uint32_t* s_words;   // START bit mask, bit i of word w = local position 32 w + i
+    uint32_t* e_words;   // END bit mask
+};
+
+struct EmitParams {  // K2
+    const uint32_t* s_words;
+    const uint32_t* e_words;
+    uint64_t num_tiles;
+    uint64_t global_off, n_global;
     int32_t min_len;
     uint64_t* out_start;
     uint16_t* out_len;
@@ -53,12 +63,12 @@ struct ClusterParams {
     uint64_t* desc_state;
     uint64_t* desc_cnt;
     ClusterDev* res;
-    uint32_t num_tiles;
 };
 
-cudaError_t launch_cluster(const ClusterParams& p, uint64_t rows_alloc16, int sm_count, cudaStream_t stream,
-                           int variant, int* grid_out);
-int cluster_tile_positions(int variant);
+uint64_t flags_words_needed(uint64_t n_local);
+uint64_t emit_num_tiles(uint64_t n_local);
+cudaError_t launch_flags(const FlagParams& p, uint64_t rows_alloc32, int sm_count, cudaStream_t stream, int variant);
+cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
 
 // ---- staging -----------------------------------------------------------------------------------
 // AoS records -> SoA.  d_rec: `count` records of (y+z+x+1) bytes; outputs are pointers to the element
@@ -71,12 +81,13 @@ cudaError_t launch_fill_phantom(uint32_t* lcp, uint32_t* text, uint32_t* suff, u
 // ---- phase 2 -----------------------------------------------------------------------------------
 struct SnpDev {  // device counters of one e2s_find_events
     unsigned long long n_analysed;
+    unsigned long long n_survivors;  // clusters that pass the base-code prefilter
     unsigned long long n_flagged;
     unsigned long long n_slots_valid;
     unsigned long long saw_n;
     unsigned long long bad_ref;
     unsigned long long unsorted;
-    unsigned long long pad[2];
+    unsigned long long pad[1];
 };
 
 struct SnpArrays {

@@ -2,20 +2,25 @@
 //
 //   k_len_hist       statistics(): length histogram                      ref:clust2snp.cpp:889-909
 //   k_tile_first     merge-path style partition of the cluster list over position tiles
-//   k_cluster_scan   K3a: per-cluster 2x4 nucleotide histogram (sample = gSA text id < nreads1),
+//   k_code_scan      K3a: exact prefilter of find_variants on the BWT byte alone.  A cluster whose
+//                    records show at most ONE base code (base_to_int, ref:include.hpp:265-279) with
+//                    >= mcov_out occurrences over both samples cannot pass ref:clust2snp.cpp:402-429:
+//                    counts[s][c] <= total[c] < mcov_out for every other code, so both frequent sets are
+//                    subsets of one letter and are either empty or equal.  Only clusters with >= 2
+//                    frequent codes (true variants, repeats) go on to the exact test.
+//   k_cluster_exact  K3x: per-cluster 2x4 nucleotide histogram (sample = gSA text id < nreads1),
 //                    first-argmax LCP and the find_variants filters        ref:clust2snp.cpp:377-429
-//   k_flag_*         ordered compaction of the flagged clusters
+//   k_flag_*         ordered compaction of a cluster bit mask into an index list
 //   k_candidates     K3b: ordered (ballot/popc) selection of the first <= c supporting reads per
 //                    sample and allele pair                                ref:clust2snp.cpp:431-496
 //   k_compact_slots  candidates in reference order
 //   k_events         K4: gSA-driven gather of read contexts, consensus, support, distance()
 //                                                  ref:clust2snp.cpp:541-624, 254-302, include.hpp:334-371
 //
-// K3a is the only kernel that touches every position: it streams text/lcp/bwt tiles (+150-record
-// overhang) into shared memory with the TMA engine (cp.async.bulk, STAGES tiles in flight per CTA) and
-// lets 8-lane groups reduce one cluster each out of shared memory.  Algorithmic traffic:
-// 10 B/cluster + 9 B/position inside analysed clusters; the streamed traffic is
-// 9 B/position because non-cluster positions ride along in the tiles.
+// K3a is the only phase-2 kernel that touches every position: it streams 16384-byte BWT tiles (+150
+// byte overhang) into shared memory with the TMA engine (cp.async.bulk, STAGES tiles in flight per
+// CTA), turns them into two bit-planes of the 2-bit base code and answers every cluster of the tile
+// with a few range popcounts (one thread per cluster).  Traffic: 1 B/position + 10 B/cluster.
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -81,15 +86,14 @@ cudaError_t launch_check_sorted(const uint64_t* start, const uint16_t* len, uint
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3a
+// K3a: base-code prefilter over the BWT
 // ---------------------------------------------------------------------------------------------
-constexpr int SC_THREADS = 256;
-constexpr int SC_T = 2048;                 // positions per tile
-constexpr int SC_SPAN = SC_T + HALO_R;     // positions staged per tile
-constexpr int SC_STAGES = 3;
-constexpr int SC_G = 8;                    // lanes per cluster
-constexpr int SC_BATCH = 1024;             // cluster records staged per batch
-constexpr int SC_STAGE_BYTES = SC_SPAN * 9;
+constexpr int PS_THREADS = 256;
+constexpr int PS_T = 16384;                  // positions per tile
+constexpr int PS_SPAN = PS_T + HALO_R;       // bytes staged per tile (multiple of 16)
+constexpr int PS_STAGES = 3;
+constexpr int PS_CHUNKS = PS_SPAN / 16;      // 16-byte chunks per tile
+constexpr int PS_PLANE_WORDS = (PS_SPAN + 31) / 32 + 3;
 
 struct ScanParams {
     SnpArrays a;
@@ -97,10 +101,7 @@ struct ScanParams {
     uint32_t num_tiles;
     uint32_t min_len, max_len;   // 2*mcov_out, max_clust_length
     uint32_t mcov;
-    uint32_t k_right;
-    uint32_t nr1_lo;             // min(nr_reads1, 2^32-1)
-    uint32_t nr1_big;            // nr_reads1 >= 2^32: everything is sample 0
-    uint32_t* flag_words;
+    uint32_t* flag_words;        // out: bit per cluster = needs the exact test
     SnpDev* dev;
 };
 
@@ -108,7 +109,7 @@ __global__ void k_tile_first(const uint64_t* __restrict__ cl_start, uint64_t m, 
                              uint64_t* __restrict__ tile_first) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > num_tiles) return;
-    const uint64_t key = global_off + uint64_t(t) * SC_T;
+    const uint64_t key = global_off + uint64_t(t) * PS_T;
     uint64_t lo = 0, hi = m;
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
@@ -118,121 +119,171 @@ __global__ void k_tile_first(const uint64_t* __restrict__ cl_start, uint64_t m, 
     tile_first[t] = lo;
 }
 
-__global__ void __launch_bounds__(SC_THREADS) k_cluster_scan(ScanParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t full_bar[SC_STAGES];
-    __shared__ uint32_t s_cs[SC_BATCH];
-    __shared__ uint16_t s_cl[SC_BATCH];
+// 0x80 in every byte of u that equals the corresponding byte of pat (exact, no cross-byte borrow)
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t u, uint32_t pat) {
+    const uint32_t t = u ^ pat;
+    return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+}
+// four byte flags (0x80 each) -> 4 bits
+__device__ __forceinline__ uint32_t nibble(uint32_t f) { return (((f >> 7) * 0x01020408u) >> 24) & 0xFu; }
 
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int gl = lane & (SC_G - 1);          // lane in group
-    const int group = tid / SC_G;              // group in CTA
-    constexpr int NGROUPS = SC_THREADS / SC_G;
-    const uint32_t gmask = ((1u << SC_G) - 1u) << (lane & ~(SC_G - 1));
+__global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full_bar[PS_STAGES];
+    __shared__ __align__(16) uint16_t s_b0[PS_PLANE_WORDS * 2];  // bit 0 of the base code (C, T)
+    __shared__ __align__(16) uint16_t s_b1[PS_PLANE_WORDS * 2];  // bit 1 of the base code (G, T)
+    const int tid = threadIdx.x, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < SC_STAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < PS_STAGES; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
     }
+    for (int i = tid; i < PS_PLANE_WORDS * 2; i += PS_THREADS) s_b0[i] = s_b1[i] = 0;
     __syncthreads();
-
     auto issue = [&](int s, uint64_t t) {
-        uint8_t* st = smem + size_t(s) * SC_STAGE_BYTES;
-        const uint64_t base = t * SC_T;
-        mbar_expect_tx(&full_bar[s], SC_STAGE_BYTES);
-        bulk_g2s(st, p.a.text + base, SC_SPAN * 4, &full_bar[s]);
-        bulk_g2s(st + SC_SPAN * 4, p.a.lcp + base, SC_SPAN * 4, &full_bar[s]);
-        bulk_g2s(st + SC_SPAN * 8, p.a.bwt + base, SC_SPAN, &full_bar[s]);
+        mbar_expect_tx(&full_bar[s], PS_SPAN);
+        bulk_g2s(smem + size_t(s) * PS_SPAN, p.a.bwt + t * PS_T, PS_SPAN, &full_bar[s]);
     };
     if (tid == 0) {
-        for (int s = 0; s < SC_STAGES; ++s) {
+        for (int s = 0; s < PS_STAGES; ++s) {
             uint64_t t = uint64_t(blockIdx.x) + uint64_t(s) * gridDim.x;
             if (t < p.num_tiles) issue(s, t);
         }
     }
+    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(s_b0);
+    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(s_b1);
 
     unsigned long long n_analysed = 0;
-    uint32_t saw_n = 0;
     uint32_t it = 0;
     for (uint64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-        const int stage = it % SC_STAGES;
-        const uint32_t parity = (it / SC_STAGES) & 1;
-        const uint8_t* st = smem + size_t(stage) * SC_STAGE_BYTES;
-        const uint32_t* s_text = reinterpret_cast<const uint32_t*>(st);
-        const uint32_t* s_lcp = reinterpret_cast<const uint32_t*>(st + SC_SPAN * 4);
-        const uint8_t* s_bwt = st + SC_SPAN * 8;
+        const int stage = it % PS_STAGES;
+        const uint32_t parity = (it / PS_STAGES) & 1;
+        const uint8_t* st = smem + size_t(stage) * PS_SPAN;
         const uint64_t c_lo = p.tile_first[t], c_hi = p.tile_first[t + 1];
-        const uint64_t tile_gbase = p.a.global_off + t * SC_T;
-
-        bool waited = false;
-        for (uint64_t cb = c_lo; cb < c_hi; cb += SC_BATCH) {
-            const uint32_t nb = uint32_t(c_hi - cb < SC_BATCH ? c_hi - cb : SC_BATCH);
-            __syncthreads();  // previous batch consumed
-            for (uint32_t i = tid; i < nb; i += SC_THREADS) {
-                s_cs[i] = uint32_t(p.a.cl_start[cb + i] - tile_gbase);
-                s_cl[i] = p.a.cl_len[cb + i];
-            }
-            __syncthreads();
-            if (!waited) {
-                mbar_wait(&full_bar[stage], parity);
-                waited = true;
-            }
-            for (uint32_t c = group; c < nb; c += NGROUPS) {
-                const uint32_t len = s_cl[c];
-                if (len < p.min_len || len > p.max_len) continue;
-                const uint32_t rel = s_cs[c];
-                unsigned long long acc = 0, best = 0;
-                for (uint32_t j = gl; j < len; j += SC_G) {
-                    const uint32_t tx = s_text[rel + j];
-                    const uint32_t lc = s_lcp[rel + j];
-                    const uint32_t b = s_bwt[rel + j];
-                    const uint32_t sample = (tx >= p.nr1_lo) & (p.nr1_big ^ 1u);
-                    saw_n |= is_n(b);
-                    acc += 1ull << (8 * (sample * 4 + base_code(b)));
-                    const unsigned long long key = (uint64_t(lc) << 8) | (255u - j);
-                    best = key > best ? key : best;
-                }
-#pragma unroll
-                for (int d = SC_G / 2; d > 0; d >>= 1) {
-                    acc += __shfl_xor_sync(gmask, acc, d);
-                    unsigned long long o = __shfl_xor_sync(gmask, best, d);
-                    best = o > best ? o : best;
-                }
-                if (gl == 0) {
-                    ++n_analysed;
-                    if ((best >> 8) >= p.k_right) {
-                        uint32_t f0 = 0, f1 = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            f0 |= uint32_t(((acc >> (8 * b)) & 0xff) >= p.mcov) << b;
-                            f1 |= uint32_t(((acc >> (8 * (b + 4))) & 0xff) >= p.mcov) << b;
-                        }
-                        const bool ok = f0 && f1 && __popc(f0) <= 2 && __popc(f1) <= 2 && f0 != f1 && __popc(f0 | f1) <= 3;
-                        if (ok) {
-                            const uint64_t ci = cb + c;
-                            atomicOr(&p.flag_words[ci >> 5], 1u << (ci & 31));
-                        }
-                    }
-                }
-            }
+        const uint64_t tile_gbase = p.a.global_off + t * PS_T;
+        // my first cluster record: issue the loads before waiting for the tile
+        uint64_t c = c_lo + tid;
+        uint64_t c_start = 0;
+        uint32_t c_len = 0;
+        if (c < c_hi) {
+            c_start = p.a.cl_start[c];
+            c_len = p.a.cl_len[c];
         }
-        if (!waited) mbar_wait(&full_bar[stage], parity);  // keep the barrier phases in step
-        __syncthreads();                                    // everyone is done with the stage
+        mbar_wait(&full_bar[stage], parity);
+        // ---- bit planes of the base code: A=00 C=01 G=10 T=11, everything else 00 ----
+        for (int ch = tid; ch < PS_CHUNKS; ch += PS_THREADS) {
+            const uint4 q = lds128(st + ch * 16);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            uint32_t b0 = 0, b1 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t u = w[j] & 0xDFDFDFDFu;  // case-insensitive
+                const uint32_t eC = eq_bytes(u, 0x43434343u), eG = eq_bytes(u, 0x47474747u), eT = eq_bytes(u, 0x54545454u);
+                b0 |= nibble(eC | eT) << (4 * j);
+                b1 |= nibble(eG | eT) << (4 * j);
+            }
+            s_b0[ch] = uint16_t(b0);
+            s_b1[ch] = uint16_t(b1);
+        }
+        __syncthreads();  // planes complete; the byte tile is no longer needed
         if (tid == 0) {
-            uint64_t tn = t + uint64_t(SC_STAGES) * gridDim.x;
+            uint64_t tn = t + uint64_t(PS_STAGES) * gridDim.x;
             if (tn < p.num_tiles) issue(stage, tn);
         }
+        // ---- one thread per cluster: total count of each base code by range popcounts ----
+        while (c < c_hi) {
+            const uint64_t cn = c + PS_THREADS;
+            uint64_t n_start = 0;
+            uint32_t n_len = 0;
+            if (cn < c_hi) {  // prefetch the next record
+                n_start = p.a.cl_start[cn];
+                n_len = p.a.cl_len[cn];
+            }
+            if (c_len >= p.min_len && c_len <= p.max_len) {
+                ++n_analysed;
+                const uint32_t lo = uint32_t(c_start - tile_gbase), hi = lo + c_len;  // [lo, hi)
+                uint32_t nC = 0, nG = 0, nT = 0;
+                for (uint32_t wi = lo >> 5; wi <= (hi - 1) >> 5; ++wi) {
+                    uint32_t mask = FULL;
+                    if (wi == (lo >> 5)) mask &= FULL << (lo & 31);
+                    if (wi == ((hi - 1) >> 5)) mask &= FULL >> (31 - ((hi - 1) & 31));
+                    const uint32_t x0 = w0[wi] & mask, x1 = w1[wi] & mask;
+                    nT += __popc(x0 & x1);
+                    nC += __popc(x0 & ~x1);
+                    nG += __popc(x1 & ~x0);
+                }
+                const uint32_t nA = c_len - nC - nG - nT;
+                const uint32_t frequent = uint32_t(nA >= p.mcov) + uint32_t(nC >= p.mcov) + uint32_t(nG >= p.mcov) +
+                                          uint32_t(nT >= p.mcov);
+                if (frequent >= 2) atomicOr(&p.flag_words[c >> 5], 1u << (c & 31));
+            }
+            c = cn;
+            c_start = n_start;
+            c_len = n_len;
+        }
+        __syncthreads();  // planes are rebuilt by the next tile
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        n_analysed += __shfl_xor_sync(FULL, n_analysed, d);
-        saw_n |= __shfl_xor_sync(FULL, saw_n, d);
+    for (int d = 16; d > 0; d >>= 1) n_analysed += __shfl_xor_sync(FULL, n_analysed, d);
+    if (lane == 0 && n_analysed) atomicAdd(&p.dev->n_analysed, n_analysed);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3x: exact find_variants filters for the clusters that survived the prefilter
+// ---------------------------------------------------------------------------------------------
+constexpr int EX_THREADS = 256;
+constexpr int EX_G = 8;  // lanes per cluster
+
+struct ExactParams {
+    SnpArrays a;
+    const uint64_t* list;      // cluster indices to test
+    const unsigned long long* n_list;  // device-resident length of the list
+    uint32_t mcov, k_right;
+    uint32_t nr1_lo, nr1_big;
+    uint32_t* flag_words;      // out: bit per cluster = passes the find_variants filters
+    SnpDev* dev;
+};
+
+__global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (EX_G - 1);
+    const uint32_t gmask = ((1u << EX_G) - 1u) << (lane & ~(EX_G - 1));
+    const uint64_t n_list = *p.n_list;
+    const uint64_t groups = uint64_t(gridDim.x) * (EX_THREADS / EX_G);
+    uint32_t saw_n = 0;
+    for (uint64_t i = (uint64_t(blockIdx.x) * EX_THREADS + threadIdx.x) / EX_G; i < n_list; i += groups) {
+        const uint64_t ci = p.list[i];
+        const uint64_t lp = p.a.cl_start[ci] - p.a.global_off;
+        const uint32_t len = p.a.cl_len[ci];
+        unsigned long long acc = 0, best = 0;
+        for (uint32_t j = gl; j < len; j += EX_G) {
+            const uint32_t tx = p.a.text[lp + j];
+            const uint32_t lc = p.a.lcp[lp + j];
+            const uint32_t b = p.a.bwt[lp + j];
+            const uint32_t sample = (tx >= p.nr1_lo) & (p.nr1_big ^ 1u);
+            saw_n |= is_n(b);
+            acc += 1ull << (8 * (sample * 4 + base_code(b)));
+            const unsigned long long key = (uint64_t(lc) << 8) | (255u - j);
+            best = key > best ? key : best;
+        }
+#pragma unroll
+        for (int d = EX_G / 2; d > 0; d >>= 1) {
+            acc += __shfl_xor_sync(gmask, acc, d);
+            unsigned long long o = __shfl_xor_sync(gmask, best, d);
+            best = o > best ? o : best;
+        }
+        if (gl == 0 && (best >> 8) >= p.k_right) {
+            uint32_t f0 = 0, f1 = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                f0 |= uint32_t(((acc >> (8 * b)) & 0xff) >= p.mcov) << b;
+                f1 |= uint32_t(((acc >> (8 * (b + 4))) & 0xff) >= p.mcov) << b;
+            }
+            const bool ok = f0 && f1 && __popc(f0) <= 2 && __popc(f1) <= 2 && f0 != f1 && __popc(f0 | f1) <= 3;
+            if (ok) atomicOr(&p.flag_words[ci >> 5], 1u << (ci & 31));
+        }
     }
-    if (lane == 0) {
-        if (n_analysed) atomicAdd(&p.dev->n_analysed, n_analysed);
-        if (saw_n) atomicOr(&p.dev->saw_n, 1ull);
-    }
+    if (__any_sync(__activemask(), saw_n) && saw_n) atomicOr(&p.dev->saw_n, 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -260,7 +311,8 @@ __global__ void __launch_bounds__(FC_THREADS) k_flag_count(const uint32_t* __res
 
 __global__ void __launch_bounds__(FC_THREADS) k_flag_emit(const uint32_t* __restrict__ words, uint64_t n_words,
                                                           const uint32_t* __restrict__ block_sum,
-                                                          uint64_t* __restrict__ out_idx, SnpDev* dev) {
+                                                          uint64_t* __restrict__ out_idx,
+                                                          unsigned long long* out_count) {
     __shared__ uint64_t s_base;
     __shared__ uint32_t s_red[FC_THREADS / 32];
     __shared__ uint32_t s_w[FC_THREADS / 32];
@@ -274,7 +326,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_flag_emit(const uint32_t* __rest
         uint64_t b = 0;
         for (int i = 0; i < FC_THREADS / 32; ++i) b += s_red[i];
         s_base = b;
-        if (blockIdx.x == gridDim.x - 1) dev->n_flagged = b + block_sum[blockIdx.x];
+        if (blockIdx.x == gridDim.x - 1) *out_count = b + block_sum[blockIdx.x];
     }
     __syncthreads();
     uint64_t base = s_base;
@@ -592,6 +644,8 @@ struct SnpWork {
     uint64_t* tile_first = nullptr; size_t tile_first_cap = 0;
     uint32_t* flag_words = nullptr; size_t flag_cap = 0;
     uint32_t* block_sum = nullptr; size_t block_sum_cap = 0;
+    uint32_t* flag_words2 = nullptr; size_t flag2_cap = 0;
+    uint64_t* survivors = nullptr; size_t survivors_cap = 0;
     uint64_t* flagged = nullptr; size_t flagged_cap = 0;
     CandSlot* slots = nullptr; size_t slots_cap = 0;
     uint32_t* slot_text = nullptr; uint32_t* slot_pos = nullptr; size_t slot_list_cap = 0;
@@ -607,6 +661,7 @@ SnpWork* snp_work_create() { return new SnpWork(); }
 
 void snp_work_destroy(SnpWork* w) {
     if (!w) return;
+    cudaFree(w->flag_words2); cudaFree(w->survivors);
     cudaFree(w->tile_first); cudaFree(w->flag_words); cudaFree(w->block_sum); cudaFree(w->flagged);
     cudaFree(w->slots); cudaFree(w->slot_text); cudaFree(w->slot_pos); cudaFree(w->cand); cudaFree(w->events);
     cudaFree(w->dev);
@@ -640,52 +695,76 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
 
     const uint32_t nr1_big = p.nr_reads1 > 0xffffffffull ? 1u : 0u;
     const uint32_t nr1_lo = nr1_big ? 0xffffffffu : uint32_t(p.nr_reads1);
-    const uint32_t num_tiles = uint32_t((a.n_local + SC_T - 1) / SC_T);
+    const uint32_t num_tiles = uint32_t((a.n_local + PS_T - 1) / PS_T);
 
     CK(ensure(w->tile_first, w->tile_first_cap, size_t(num_tiles) + 1));
     const uint64_t n_words = (a.m + 31) / 32;
     CK(ensure(w->flag_words, w->flag_cap, size_t(n_words)));
+    CK(ensure(w->flag_words2, w->flag2_cap, size_t(n_words)));
     CK(cudaMemsetAsync(w->flag_words, 0, n_words * 4, stream));
+    CK(cudaMemsetAsync(w->flag_words2, 0, n_words * 4, stream));
     const uint32_t n_fblocks = uint32_t((n_words + FC_WORDS - 1) / FC_WORDS);
     CK(ensure(w->block_sum, w->block_sum_cap, size_t(n_fblocks)));
+    CK(ensure(w->survivors, w->survivors_cap, size_t(a.m)));
 
     k_tile_first<<<(num_tiles + 1 + 255) / 256, 256, 0, stream>>>(a.cl_start, a.m, a.global_off, num_tiles, w->tile_first);
     CK(cudaGetLastError());
     ++*launches;
 
-    ScanParams sp;
-    sp.a = a;
-    sp.tile_first = w->tile_first;
-    sp.num_tiles = num_tiles;
-    sp.min_len = uint32_t(2 * p.mcov_out);
-    sp.max_len = uint32_t(max_clust_length);
-    sp.mcov = uint32_t(p.mcov_out);
-    sp.k_right = uint32_t(p.k_right);
-    sp.nr1_lo = nr1_lo;
-    sp.nr1_big = nr1_big;
-    sp.flag_words = w->flag_words;
-    sp.dev = w->dev;
+    // K3a: base-code prefilter (BWT bytes only)
     {
-        const size_t smem = size_t(SC_STAGES) * SC_STAGE_BYTES;
-        CK(cudaFuncSetAttribute(k_cluster_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        ScanParams sp;
+        sp.a = a;
+        sp.tile_first = w->tile_first;
+        sp.num_tiles = num_tiles;
+        sp.min_len = uint32_t(2 * p.mcov_out);
+        sp.max_len = uint32_t(max_clust_length);
+        sp.mcov = uint32_t(p.mcov_out);
+        sp.flag_words = w->flag_words;
+        sp.dev = w->dev;
+        const size_t smem = size_t(PS_STAGES) * PS_SPAN;
+        CK(cudaFuncSetAttribute(k_code_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_scan, SC_THREADS, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_code_scan, PS_THREADS, smem));
         if (occ < 1) occ = 1;
         uint64_t grid = uint64_t(sm_count) * occ;
         if (grid > num_tiles) grid = num_tiles;
         if (timer) timer->begin(E2S_KERNEL_SCAN, stream);
-        k_cluster_scan<<<unsigned(grid), SC_THREADS, smem, stream>>>(sp);
+        k_code_scan<<<unsigned(grid), PS_THREADS, smem, stream>>>(sp);
         if (timer) timer->end(stream);
         CK(cudaGetLastError());
         ++*launches;
     }
+    // survivors of the prefilter, in order (the list can be as long as m: sized for the worst case)
     k_flag_count<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum);
     CK(cudaGetLastError());
+    k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum, w->survivors, &w->dev->n_survivors);
+    CK(cudaGetLastError());
+    *launches += 2;
+    // K3x: exact filters on the survivors (list length stays on the device)
+    {
+        ExactParams ep;
+        ep.a = a;
+        ep.list = w->survivors;
+        ep.n_list = &w->dev->n_survivors;
+        ep.mcov = uint32_t(p.mcov_out);
+        ep.k_right = uint32_t(p.k_right);
+        ep.nr1_lo = nr1_lo;
+        ep.nr1_big = nr1_big;
+        ep.flag_words = w->flag_words2;
+        ep.dev = w->dev;
+        if (timer) timer->begin(E2S_KERNEL_EXACT, stream);
+        k_cluster_exact<<<unsigned(sm_count) * 4, EX_THREADS, 0, stream>>>(ep);
+        if (timer) timer->end(stream);
+        CK(cudaGetLastError());
+        ++*launches;
+    }
+    k_flag_count<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->block_sum);
+    CK(cudaGetLastError());
     ++*launches;
-    // the flagged list can be as long as m in theory; size it after counting
     SnpDev hd;
     {
-        // upper bound on the host needs the block sums: do emit in a second step once n_flagged is known
+        // the flagged list sizes the candidate slots: its length is needed on the host
         uint32_t* h_sums = static_cast<uint32_t*>(malloc(size_t(n_fblocks) * 4));
         if (!h_sums) { *err = "malloc"; return cudaErrorMemoryAllocation; }
         cudaError_t e = cudaMemcpyAsync(h_sums, w->block_sum, size_t(n_fblocks) * 4, cudaMemcpyDeviceToHost, stream);
@@ -695,7 +774,7 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
         free(h_sums);
         if (e != cudaSuccess) { *err = "flag sums D2H"; return e; }
         CK(ensure(w->flagged, w->flagged_cap, size_t(nf)));
-        k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum, w->flagged, w->dev);
+        k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->block_sum, w->flagged, &w->dev->n_flagged);
         CK(cudaGetLastError());
         ++*launches;
         counts->n_flagged = nf;

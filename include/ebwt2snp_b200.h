@@ -62,11 +62,13 @@ int e2s_ctx_synchronize(e2s_ctx *ctx);
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 uint64_t e2s_ctx_launch_count(const e2s_ctx *ctx);
 /* Per-kernel device time, measured with CUDA events recorded on the context's stream around the
- * two kernels that touch every position (bench.py's roofline).  e2s_ctx_kernel_time synchronises
+ * kernels that touch every position (bench.py's roofline).  e2s_ctx_kernel_time synchronises
  * the stream, returns the time and launch count accumulated since the last call and resets them. */
-#define E2S_KERNEL_CLUSTER 0 /* K1+K2: LCP stencil + look-back scan + compaction */
-#define E2S_KERNEL_SCAN 1    /* K3a: per-cluster histogram / filters */
-#define E2S_KERNEL_COUNT 2
+#define E2S_KERNEL_FLAGS 0 /* K1: LCP boundary stencil -> START/END bit masks */
+#define E2S_KERNEL_EMIT 1  /* K2: look-back scan over the masks + record compaction */
+#define E2S_KERNEL_SCAN 2  /* K3a: per-cluster base-code prefilter over the BWT */
+#define E2S_KERNEL_EXACT 3 /* K3x: exact 2x4 histogram / filters of the surviving clusters */
+#define E2S_KERNEL_COUNT 4
 int e2s_ctx_timing(e2s_ctx *ctx, int enable);
 int e2s_ctx_kernel_time(e2s_ctx *ctx, int kernel, double *total_ms, uint64_t *launches);
 
