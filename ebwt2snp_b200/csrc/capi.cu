@@ -58,6 +58,10 @@ struct e2s_shard {
     uint64_t* d_desc = nullptr;
     size_t desc_cap = 0;
     ClusterDev* d_res = nullptr;
+    ClusterDev h_res;           // host copy of the last scan's accumulators (incl. length histogram)
+    bool have_scan_stats = false;
+    uint8_t* d_packed = nullptr;
+    uint64_t packed_cap = 0;
     unsigned long long* d_hist = nullptr;
     int variant = 0;
     // phase 2
@@ -236,6 +240,7 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->d_len);
     cudaFree(s->d_desc);
     cudaFree(s->d_flags);
+    cudaFree(s->d_packed);
     cudaFree(s->d_res);
     cudaFree(s->d_hist);
     snp_work_destroy(s->work);
@@ -436,6 +441,9 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
         p.desc_state = s->d_desc;
         p.desc_cnt = s->d_desc + num_tiles;
         p.res = s->d_res;
+        const bool is_last = s->global_off + s->n_local == s->n_global;
+        p.tail_lcp = is_last ? s->lcp + s->n_local - 2 : nullptr;
+        p.tail_bwt = is_last ? s->bwt + s->n_local - 1 : nullptr;
         c->timer.begin(E2S_KERNEL_EMIT, c->stream);
         cudaError_t le = launch_emit(p, c->sm_count, c->stream);
         c->timer.end(c->stream);
@@ -460,16 +468,11 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
     sum->end_nm2_start = h.end_nm2_start;
     sum->k = k;
     sum->min_len = uint64_t(int64_t(min_len));
-    if (s->global_off + s->n_local == s->n_global) {
-        uint32_t t[2];
-        uint8_t b;
-        CU(c, cudaMemcpyAsync(t, s->lcp + s->n_local - 2, 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaMemcpyAsync(&b, s->bwt + s->n_local - 1, 1, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-        sum->tail_lcp_nm2 = t[0];
-        sum->tail_lcp_nm1 = t[1];
-        sum->tail_bwt_nm1 = b;
-    }
+    sum->tail_lcp_nm2 = h.tail_lcp_nm2;
+    sum->tail_lcp_nm1 = h.tail_lcp_nm1;
+    sum->tail_bwt_nm1 = h.tail_bwt_nm1;
+    s->h_res = h;
+    s->have_scan_stats = true;
     s->m_own = h.n_written;
     s->m_list = h.n_written;
     s->have_clusters = true;
@@ -574,16 +577,9 @@ int e2s_cluster_finalize(e2s_shard* s, const e2s_cluster_merged* mg) {
     if (!s->have_clusters || s->staged) return fail(c, E2S_ERR_STATE, "e2s_cluster_finalize: run e2s_cluster_run first");
     CU(c, cudaSetDevice(c->device));
     s->merged = *mg;
-    uint64_t st[3];
-    uint16_t ln[3];
-    for (uint32_t i = 0; i < mg->n_adopt; ++i) {
-        st[i] = mg->adopt_start[i];
-        ln[i] = uint16_t(mg->adopt_len[i]);
-    }
     if (mg->n_adopt) {
-        CU(c, cudaMemcpyAsync(s->d_start + s->m_own, st, mg->n_adopt * 8, cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaMemcpyAsync(s->d_len + s->m_own, ln, mg->n_adopt * 2, cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));  // st/ln live on this stack frame
+        CU(c, launch_put_records(s->d_start, s->d_len, s->m_own, mg->adopt_start, mg->adopt_len, int(mg->n_adopt), c->stream));
+        ++c->launches;
     }
     s->m_list = s->m_own + mg->n_adopt;
     s->finalized = true;
@@ -654,19 +650,37 @@ int e2s_cluster_fetch(e2s_shard* s, uint64_t* start, uint16_t* len, uint64_t cap
 
 int e2s_cluster_fetch_packed(e2s_shard* s, void* rec10, uint64_t cap, uint64_t* m) {
     if (!s || !rec10 || !m) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
-    if (!s->have_clusters) return fail(s->ctx, E2S_ERR_STATE, "no clusters yet");
+    e2s_ctx* c = s->ctx;
+    if (!s->have_clusters) return fail(c, E2S_ERR_STATE, "no clusters yet");
     const uint64_t total = out_count(s);
     *m = total;
-    if (cap < total) return fail(s->ctx, E2S_ERR_ARG, "e2s_cluster_fetch_packed: capacity too small");
-    std::vector<uint64_t> st(total);
-    std::vector<uint16_t> ln(total);
-    int rc = e2s_cluster_fetch(s, st.data(), ln.data(), total, m);
-    if (rc) return rc;
+    if (cap < total) return fail(c, E2S_ERR_ARG, "e2s_cluster_fetch_packed: capacity too small");
+    CU(c, cudaSetDevice(c->device));
     uint8_t* o = static_cast<uint8_t*>(rec10);
-    for (uint64_t i = 0; i < total; ++i) {
-        memcpy(o + i * 10, &st[i], 8);
-        memcpy(o + i * 10 + 8, &ln[i], 2);
+    auto put = [&](uint64_t st, uint64_t ln) {
+        const uint16_t l16 = uint16_t(ln);
+        memcpy(o, &st, 8);
+        memcpy(o + 8, &l16, 2);
+        o += 10;
+    };
+    if (!s->staged && s->merged.n_prepend && s->merged.prepend_written) put(s->merged.prepend_start, s->merged.prepend_len);
+    if (s->m_own) {  // pack on the device, one D2H straight into the caller's buffer
+        if (s->m_own > s->packed_cap) {
+            cudaFree(s->d_packed);
+            s->d_packed = nullptr;
+            s->packed_cap = 0;
+            if (cudaMalloc(reinterpret_cast<void**>(&s->d_packed), s->m_own * 10 + 16) != cudaSuccess)
+                return fail(c, E2S_ERR_NOMEM, "packed record buffer");
+            s->packed_cap = s->m_own;
+        }
+        CU(c, launch_pack_records(s->d_start, s->d_len, s->m_own, s->d_packed, c->stream, c->sm_count));
+        ++c->launches;
+        CU(c, cudaMemcpyAsync(o, s->d_packed, s->m_own * 10, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        o += s->m_own * 10;
     }
+    if (!s->staged)
+        for (uint32_t i = 0; i < s->merged.n_append; ++i) put(s->merged.append_start[i], s->merged.append_len[i]);
     return E2S_OK;
 }
 
@@ -687,6 +701,7 @@ int e2s_clusters_stage(e2s_shard* s, const uint64_t* start, const uint16_t* len,
     s->m_own = s->m_list = m;
     s->have_clusters = true;
     s->staged = true;
+    s->have_scan_stats = false;
     s->finalized = true;
     s->have_events = false;
     memset(&s->merged, 0, sizeof s->merged);
@@ -711,6 +726,12 @@ int e2s_statistics(e2s_shard* s, e2s_stats* st) {
     if (!s->have_clusters) return fail(c, E2S_ERR_STATE, "no clusters yet");
     CU(c, cudaSetDevice(c->device));
     memset(st, 0, sizeof *st);
+    if (!s->staged && s->have_scan_stats) {  // the scan accumulated the histogram of its own records
+        for (int i = 0; i < E2S_HIST_BINS; ++i) st->hist[i] = s->h_res.hist[i];
+        st->n_bases = s->h_res.n_bases;
+        st->n_clust = s->m_own;
+        st->last_len = s->h_res.last_rec & 0xffff;
+    } else {
     unsigned long long h[E2S_HIST_BINS + 1];
     CU(c, cudaMemsetAsync(s->d_hist, 0, sizeof h, c->stream));
     CU(c, launch_len_hist(s->d_len, s->m_own, s->d_hist, c->stream, c->sm_count));
@@ -723,6 +744,7 @@ int e2s_statistics(e2s_shard* s, e2s_stats* st) {
     st->n_bases = h[E2S_HIST_BINS];
     st->n_clust = s->m_own;
     st->last_len = last;
+    }
     auto add = [&](uint64_t l) {
         if (l <= E2S_MAX_C_LEN) st->hist[l]++;
         st->n_bases += l;

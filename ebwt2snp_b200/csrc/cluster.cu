@@ -16,13 +16,14 @@
 //     conflict free), STAGES tiles in flight per CTA behind mbarriers; every thread owns 32 consecutive
 //     positions in registers and writes one 32-bit word per mask (a warp writes 128 contiguous bytes).
 //     Traffic: 4 B/position read + 0.25 B/position written.  No inter-CTA dependency.
-// K2  k_cluster_emit: decoupled look-back over the bit masks (0.25 B/position read; 65536 positions per
-//     tile, so 16x fewer descriptors than positions-per-tile of K1 would give).  Two chained scans:
+// K2  k_cluster_emit: decoupled look-back over the bit masks (0.25 B/position read; 262144 positions per
+//     tile, so 32x fewer descriptors than K1's tile size would give).  Two chained scans:
 //       #1 "cluster still open, started at s" state (a tile containing any event publishes its inclusive
 //          state immediately, so chains stop at the nearest tile with an event);
 //       #2 exclusive sum of kept-record counts = output offset (classic aggregate/inclusive descriptors,
-//          warp-parallel windows of 32 predecessors).
-//     Records are written compacted in position order: 10 B per record.
+//          warp-parallel windows of 64 predecessors).
+//     Records are written compacted in position order: 10 B per record; their length histogram
+//     (statistics(), ref:clust2snp.cpp:899-907) is accumulated on the way.
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -174,50 +175,64 @@ __global__ void __launch_bounds__(FL_THREADS) k_lcp_flags(const __grid_constant_
 // =============================================================================================
 // K2: look-back scan over the bit masks + compaction
 // =============================================================================================
-constexpr int EM_THREADS = 256;
+constexpr int EM_THREADS = 512;
 constexpr int EM_WARPS = EM_THREADS / 32;
-constexpr int EM_WPT = 8;                              // 32-bit words per thread
-constexpr int EM_TILE_WORDS = EM_THREADS * EM_WPT;     // 2048 words = 65536 positions
+constexpr int EM_WPT = 16;                             // 32-bit words per thread
+constexpr int EM_TILE_WORDS = EM_THREADS * EM_WPT;     // 8192 words = 262144 positions
 
 // payload encoding of the open-cluster state
 constexpr uint64_t OPEN_NONE = 0;
 constexpr uint64_t OPEN_UNKNOWN = 1;  // open, but started before this shard
 constexpr uint64_t OPEN_BIAS = 2;     // payload = global start + 2
 
-// nearest predecessor whose state is final (warp-parallel window of 32 descriptors)
+__device__ __forceinline__ uint64_t desc_wait(const uint64_t* d) {
+    uint64_t v;
+    while (((v = desc_load(d)) >> ST_SHIFT) == ST_INVALID) __nanosleep(20);
+    return v;
+}
+
+// nearest predecessor whose state is final (warp-parallel windows of 64 descriptors, 2 per lane)
 __device__ __forceinline__ uint64_t lookback_state(const uint64_t* desc, int64_t t, uint64_t init, int lane) {
     int64_t j = t - 1;
+    const uint64_t virt = (ST_INCLUSIVE << ST_SHIFT) | init;  // virtual tile -1
     while (true) {
-        const int64_t idx = j - lane;
-        uint64_t d = (ST_INCLUSIVE << ST_SHIFT) | init;  // virtual tile -1
-        if (idx >= 0)
-            while (((d = desc_load(desc + idx)) >> ST_SHIFT) == ST_INVALID) __nanosleep(20);
-        const uint32_t incl = __ballot_sync(FULL, (d >> ST_SHIFT) == ST_INCLUSIVE);
-        if (incl) {
-            const int src = __ffs(incl) - 1;
-            return __shfl_sync(FULL, d, src) & ST_PAYLOAD;
-        }
-        j -= 32;
+        const int64_t i0 = j - lane, i1 = j - 32 - lane;
+        const uint64_t d0 = i0 >= 0 ? desc_wait(desc + i0) : virt;
+        const uint32_t inc0 = __ballot_sync(FULL, (d0 >> ST_SHIFT) == ST_INCLUSIVE);
+        if (inc0) return __shfl_sync(FULL, d0, __ffs(inc0) - 1) & ST_PAYLOAD;
+        const uint64_t d1 = i1 >= 0 ? desc_wait(desc + i1) : virt;
+        const uint32_t inc1 = __ballot_sync(FULL, (d1 >> ST_SHIFT) == ST_INCLUSIVE);
+        if (inc1) return __shfl_sync(FULL, d1, __ffs(inc1) - 1) & ST_PAYLOAD;
+        j -= 64;
     }
 }
 
-// exclusive sum of the predecessors' aggregates
+// exclusive sum of the predecessors' aggregates (windows of 64 descriptors, both loads in flight together)
 __device__ __forceinline__ uint64_t lookback_sum(const uint64_t* desc, int64_t t, int lane) {
     uint64_t prefix = 0;
     int64_t j = t - 1;
+    const uint64_t virt = ST_INCLUSIVE << ST_SHIFT;  // virtual tile -1: inclusive 0
     while (true) {
-        const int64_t idx = j - lane;
-        uint64_t d = (ST_INCLUSIVE << ST_SHIFT);  // virtual tile -1: inclusive 0
-        if (idx >= 0)
-            while (((d = desc_load(desc + idx)) >> ST_SHIFT) == ST_INVALID) __nanosleep(20);
-        const uint32_t incl = __ballot_sync(FULL, (d >> ST_SHIFT) == ST_INCLUSIVE);
-        const int first = incl ? __ffs(incl) - 1 : 31;
-        uint64_t c = lane <= first ? (d & ST_PAYLOAD) : 0;
+        const int64_t i0 = j - lane, i1 = j - 32 - lane;
+        uint64_t d0 = virt, d1 = virt;
+        if (i0 >= 0) d0 = desc_load(desc + i0);
+        if (i1 >= 0) d1 = desc_load(desc + i1);
+        if (i0 >= 0 && (d0 >> ST_SHIFT) == ST_INVALID) d0 = desc_wait(desc + i0);
+        const uint32_t inc0 = __ballot_sync(FULL, (d0 >> ST_SHIFT) == ST_INCLUSIVE);
+        const int f0 = inc0 ? __ffs(inc0) - 1 : 31;
+        uint64_t c = lane <= f0 ? (d0 & ST_PAYLOAD) : 0;
+        uint32_t inc1 = 0;
+        if (!inc0) {  // uniform branch
+            if (i1 >= 0 && (d1 >> ST_SHIFT) == ST_INVALID) d1 = desc_wait(desc + i1);
+            inc1 = __ballot_sync(FULL, (d1 >> ST_SHIFT) == ST_INCLUSIVE);
+            const int f1 = inc1 ? __ffs(inc1) - 1 : 31;
+            c += lane <= f1 ? (d1 & ST_PAYLOAD) : 0;
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
         prefix += c;
-        if (incl) return prefix;
-        j -= 32;
+        if (inc0 | inc1) return prefix;
+        j -= 64;
     }
 }
 
@@ -226,9 +241,13 @@ __global__ void __launch_bounds__(EM_THREADS) k_cluster_emit(EmitParams p) {
     __shared__ uint32_t s_wcnt[EM_WARPS];
     __shared__ uint64_t s_x;
     __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_tot;
+    __shared__ unsigned int s_hist[E2S_HIST_BINS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    unsigned long long acc_end = 0;
+    for (int i = tid; i < E2S_HIST_BINS; i += EM_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    unsigned long long acc_end = 0, acc_bases = 0;
     uint32_t acc_any = 0;
 
     for (uint64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -356,6 +375,7 @@ __global__ void __launch_bounds__(EM_THREADS) k_cluster_emit(EmitParams p) {
             if (lane == 0) {
                 desc_store(&p.desc_cnt[t], ST_INCLUSIVE, prefix + tot);
                 s_prefix = prefix;
+                s_tot = tot;
                 if (t == p.num_tiles - 1) p.res->n_written = prefix + tot;
             }
         }
@@ -365,6 +385,7 @@ __global__ void __launch_bounds__(EM_THREADS) k_cluster_emit(EmitParams p) {
         if (n_e) {
             uint64_t o = s_prefix + off;
             uint64_t cur = cur0;
+            uint32_t last_len = 0;
 #pragma unroll
             for (int j = 0; j < EM_WPT; ++j) {
                 const uint64_t gp = gbase + uint64_t(j) * 32;
@@ -386,6 +407,9 @@ __global__ void __launch_bounds__(EM_THREADS) k_cluster_emit(EmitParams p) {
                                 p.res->overflow = 1;
                             }
                             ++o;
+                            last_len = len;
+                            acc_bases += len;
+                            if (len <= MAX_C_LEN) atomicAdd(&s_hist[len], 1u);
                         }
                         if (ge_pos + 2 == p.n_global) p.res->end_nm2_start = st + 1;
                     } else {  // OPEN_UNKNOWN: the shard's head END (OPEN_NONE cannot happen)
@@ -398,18 +422,76 @@ __global__ void __launch_bounds__(EM_THREADS) k_cluster_emit(EmitParams p) {
                     cur = hs > he ? (gp + hs + OPEN_BIAS) : OPEN_NONE;
                 }
             }
+            // the thread holding the tile's last kept record reports it (o = its index + 1)
+            if (cnt && o == s_prefix + s_tot) atomicMax(&p.res->last_rec, (unsigned long long)((o << 16) | last_len));
         }
     }
 
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         acc_end += __shfl_xor_sync(FULL, acc_end, d);
+        acc_bases += __shfl_xor_sync(FULL, acc_bases, d);
         acc_any |= __shfl_xor_sync(FULL, acc_any, d);
     }
     if (lane == 0) {
         if (acc_end) atomicAdd(&p.res->n_end, acc_end);
+        if (acc_bases) atomicAdd(&p.res->n_bases, acc_bases);
         if (acc_any) atomicOr(&p.res->any_event, 1ull);
     }
+    __syncthreads();
+    for (int i = tid; i < E2S_HIST_BINS; i += EM_THREADS)
+        if (s_hist[i]) atomicAdd(&p.res->hist[i], (unsigned long long)s_hist[i]);
+    if (blockIdx.x == 0 && tid == 0 && p.tail_lcp) {
+        p.res->tail_lcp_nm2 = p.tail_lcp[0];
+        p.res->tail_lcp_nm1 = p.tail_lcp[1];
+        p.res->tail_bwt_nm1 = p.tail_bwt[0];
+    }
+}
+
+// ---- tiny list helpers -----------------------------------------------------------------------
+struct PutArgs {
+    uint64_t st[3];
+    uint64_t ln[3];
+    int n;
+};
+__global__ void k_put_records(uint64_t* d_start, uint16_t* d_len, uint64_t at, PutArgs a) {
+    if (int(threadIdx.x) < a.n) {
+        d_start[at + threadIdx.x] = a.st[threadIdx.x];
+        d_len[at + threadIdx.x] = uint16_t(a.ln[threadIdx.x]);
+    }
+}
+cudaError_t launch_put_records(uint64_t* d_start, uint16_t* d_len, uint64_t at, const uint64_t* st, const uint64_t* ln,
+                               int n, cudaStream_t stream) {
+    PutArgs a;
+    a.n = n;
+    for (int i = 0; i < 3; ++i) {
+        a.st[i] = i < n ? st[i] : 0;
+        a.ln[i] = i < n ? ln[i] : 0;
+    }
+    k_put_records<<<1, 32, 0, stream>>>(d_start, d_len, at, a);
+    return cudaGetLastError();
+}
+
+// .clusters file layout: u64 start LE + u16 length LE = 10 bytes, no padding (ref:ebwt2clust.cpp:58-59)
+__global__ void k_pack_records(const uint64_t* __restrict__ st, const uint16_t* __restrict__ ln, uint64_t m,
+                               uint16_t* __restrict__ out) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t s = st[i];
+        uint16_t* o = out + i * 5;
+        o[0] = uint16_t(s);
+        o[1] = uint16_t(s >> 16);
+        o[2] = uint16_t(s >> 32);
+        o[3] = uint16_t(s >> 48);
+        o[4] = ln[i];
+    }
+}
+cudaError_t launch_pack_records(const uint64_t* d_start, const uint16_t* d_len, uint64_t m, uint8_t* d_out,
+                                cudaStream_t stream, int sm_count) {
+    if (m == 0) return cudaSuccess;
+    uint64_t blocks = (m + 255) / 256;
+    if (blocks > uint64_t(sm_count) * 16) blocks = uint64_t(sm_count) * 16;
+    k_pack_records<<<unsigned(blocks), 256, 0, stream>>>(d_start, d_len, m, reinterpret_cast<uint16_t*>(d_out));
+    return cudaGetLastError();
 }
 
 // =============================================================================================
@@ -482,7 +564,7 @@ cudaError_t launch_emit(const EmitParams& p0, int sm_count, cudaStream_t stream)
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_emit, EM_THREADS, 0);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    if (occ > 2) occ = 2;  // persistent and fully resident: tiles spin on their predecessors' descriptors
+    if (occ > 1) occ = 1;  // persistent and fully resident: tiles spin on their predecessors' descriptors
     uint64_t grid = uint64_t(sm_count) * occ;
     if (grid > p.num_tiles) grid = p.num_tiles;
     k_cluster_emit<<<dim3(unsigned(grid)), dim3(EM_THREADS), 0, stream>>>(p);

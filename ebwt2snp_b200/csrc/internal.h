@@ -39,7 +39,10 @@ struct ClusterDev {  // device-resident accumulators of one e2s_cluster_run (zer
     unsigned long long open_start;     // 1 + global START, 0 = none
     unsigned long long end_nm2_start;  // 1 + START of the cluster closed at n_global-2; ~0 = head; 0 = none
     unsigned long long overflow;
-    unsigned long long pad;
+    unsigned long long last_rec;       // (index of the last kept record + 1) << 16 | its length
+    unsigned long long tail_lcp_nm2, tail_lcp_nm1, tail_bwt_nm1;  // last shard: lcp[n-2], lcp[n-1], bwt[n-1]
+    unsigned long long n_bases;        // sum of the kept records' lengths
+    unsigned long long hist[E2S_HIST_BINS];  // their length histogram (lengths <= 150)
 };
 
 struct FlagParams {  // K1
@@ -63,12 +66,19 @@ struct EmitParams {  // K2
     uint64_t* desc_state;
     uint64_t* desc_cnt;
     ClusterDev* res;
+    const uint32_t* tail_lcp;  // &lcp[n_global-2] when this is the last shard, else null
+    const uint8_t* tail_bwt;   // &bwt[n_global-1]
 };
 
 uint64_t flags_words_needed(uint64_t n_local);
 uint64_t emit_num_tiles(uint64_t n_local);
 cudaError_t launch_flags(const FlagParams& p, uint64_t rows_alloc32, int sm_count, cudaStream_t stream, int variant);
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
+// small helpers: append up to 3 records to the device list / pack the list into 10-byte file records
+cudaError_t launch_put_records(uint64_t* d_start, uint16_t* d_len, uint64_t at, const uint64_t* st, const uint64_t* ln,
+                               int n, cudaStream_t stream);
+cudaError_t launch_pack_records(const uint64_t* d_start, const uint16_t* d_len, uint64_t m, uint8_t* d_out,
+                                cudaStream_t stream, int sm_count);
 
 // ---- staging -----------------------------------------------------------------------------------
 // AoS records -> SoA.  d_rec: `count` records of (y+z+x+1) bytes; outputs are pointers to the element

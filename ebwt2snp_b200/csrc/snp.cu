@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_flag_emit(const uint32_t* __rest
 struct CandParams {
     SnpArrays a;
     const uint64_t* flagged;  // cluster indices, ascending
-    uint64_t n_flagged;
+    const unsigned long long* n_flagged;  // device-resident length of the list
     uint32_t mcov, k_left, k_right, cap;  // cap = min(consensus_reads, 150)
     uint32_t nr1_lo, nr1_big;
     CandSlot* slots;       // 4 per flagged cluster
@@ -374,7 +374,7 @@ struct CandParams {
 __global__ void __launch_bounds__(128) k_candidates(CandParams p) {
     const uint64_t f = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (f >= p.n_flagged) return;
+    if (f >= *p.n_flagged) return;
     const uint64_t ci = p.flagged[f];
     const uint64_t start = p.a.cl_start[ci];
     const uint32_t len = p.a.cl_len[ci];
@@ -454,10 +454,12 @@ __global__ void __launch_bounds__(128) k_candidates(CandParams p) {
 }
 
 // valid slots, in order (single block: the list is tiny)
-__global__ void __launch_bounds__(1024) k_compact_slots(const CandSlot* __restrict__ slots, uint64_t n_slots,
+__global__ void __launch_bounds__(1024) k_compact_slots(const CandSlot* __restrict__ slots,
+                                                        const unsigned long long* __restrict__ n_flagged,
                                                         uint64_t* __restrict__ cand, SnpDev* dev) {
     __shared__ uint32_t s_w[32];
     __shared__ uint64_t s_base;
+    const uint64_t n_slots = *n_flagged * 4;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     for (uint64_t i0 = 0; i0 < n_slots; i0 += 1024) {
@@ -492,7 +494,7 @@ struct EventParams {
     const uint32_t* slot_text;
     const uint32_t* slot_pos;
     const uint64_t* cand;
-    uint64_t n_cand;
+    const unsigned long long* n_cand;  // device-resident number of candidates
     uint32_t cap;
     int32_t k_left, k_right, max_gap, max_err, max_snvs;
     const uint8_t* bases;
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
     __shared__ char s_cons[EV_WARPS][2][E2S_MAX_K];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t c = uint64_t(blockIdx.x) * EV_WARPS + w;
-    if (c >= p.n_cand) return;
+    if (c >= *p.n_cand) return;
     const uint64_t slot = p.cand[c];
     const CandSlot hdr = p.slots[slot];
     const int kl = p.k_left;
@@ -652,6 +654,7 @@ struct SnpWork {
     uint64_t* cand = nullptr; size_t cand_cap = 0;
     uint8_t* events = nullptr; size_t events_cap = 0;
     SnpDev* dev = nullptr;
+    uint8_t* h_events = nullptr; size_t h_events_cap = 0;  // host copy of the packed candidates
     uint64_t n_cand = 0;
     uint32_t stride = 0;
     int k_left = 0, k_right = 0;
@@ -665,6 +668,7 @@ void snp_work_destroy(SnpWork* w) {
     cudaFree(w->tile_first); cudaFree(w->flag_words); cudaFree(w->block_sum); cudaFree(w->flagged);
     cudaFree(w->slots); cudaFree(w->slot_text); cudaFree(w->slot_pos); cudaFree(w->cand); cudaFree(w->events);
     cudaFree(w->dev);
+    free(w->h_events);
     delete w;
 }
 
@@ -735,13 +739,20 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
         CK(cudaGetLastError());
         ++*launches;
     }
-    // survivors of the prefilter, in order (the list can be as long as m: sized for the worst case)
+    // survivors of the prefilter, in order
     k_flag_count<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum);
     CK(cudaGetLastError());
     k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum, w->survivors, &w->dev->n_survivors);
     CK(cudaGetLastError());
     *launches += 2;
-    // K3x: exact filters on the survivors (list length stays on the device)
+    SnpDev hd;
+    CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));  // sync 1: the survivor count sizes everything downstream
+    counts->n_analysed = hd.n_analysed;
+    const uint64_t nu = hd.n_survivors;
+    if (nu == 0) return cudaSuccess;
+
+    // K3x: exact filters on the survivors
     {
         ExactParams ep;
         ep.a = a;
@@ -753,8 +764,10 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
         ep.nr1_big = nr1_big;
         ep.flag_words = w->flag_words2;
         ep.dev = w->dev;
+        uint64_t grid = (nu + (EX_THREADS / EX_G) - 1) / (EX_THREADS / EX_G);
+        if (grid > uint64_t(sm_count) * 8) grid = uint64_t(sm_count) * 8;
         if (timer) timer->begin(E2S_KERNEL_EXACT, stream);
-        k_cluster_exact<<<unsigned(sm_count) * 4, EX_THREADS, 0, stream>>>(ep);
+        k_cluster_exact<<<unsigned(grid), EX_THREADS, 0, stream>>>(ep);
         if (timer) timer->end(stream);
         CK(cudaGetLastError());
         ++*launches;
@@ -762,9 +775,9 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     k_flag_count<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->block_sum);
     CK(cudaGetLastError());
     ++*launches;
-    SnpDev hd;
-    {
-        // the flagged list sizes the candidate slots: its length is needed on the host
+    uint64_t nf_bound = nu;  // flagged clusters are a subset of the survivors
+    if (nu > (uint64_t(1) << 20)) {
+        // unusually many survivors: fetch the exact count rather than sizing the slot arrays by the bound
         uint32_t* h_sums = static_cast<uint32_t*>(malloc(size_t(n_fblocks) * 4));
         if (!h_sums) { *err = "malloc"; return cudaErrorMemoryAllocation; }
         cudaError_t e = cudaMemcpyAsync(h_sums, w->block_sum, size_t(n_fblocks) * 4, cudaMemcpyDeviceToHost, stream);
@@ -773,31 +786,33 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
         for (uint32_t i = 0; i < n_fblocks; ++i) nf += h_sums[i];
         free(h_sums);
         if (e != cudaSuccess) { *err = "flag sums D2H"; return e; }
-        CK(ensure(w->flagged, w->flagged_cap, size_t(nf)));
-        k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->block_sum, w->flagged, &w->dev->n_flagged);
-        CK(cudaGetLastError());
-        ++*launches;
-        counts->n_flagged = nf;
+        nf_bound = nf;
     }
-    const uint64_t nf = counts->n_flagged;
+    CK(ensure(w->flagged, w->flagged_cap, size_t(nf_bound) + 1));
+    k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->block_sum, w->flagged, &w->dev->n_flagged);
+    CK(cudaGetLastError());
+    ++*launches;
+
     const uint32_t cap = uint32_t(p.consensus_reads < MAX_C_LEN ? p.consensus_reads : MAX_C_LEN);
-    const uint64_t n_slots = nf * 4;
-    if (nf > 0) {
-        CK(ensure(w->slots, w->slots_cap, size_t(n_slots)));
-        if (size_t(n_slots) * 2 * cap > w->slot_list_cap || !w->slot_text) {
+    const uint64_t n_slots_bound = nf_bound * 4;
+    w->stride = uint32_t((sizeof(PackedEventHdr) + 2 * size_t(p.k_left) + size_t(p.k_right) + 15) & ~size_t(15));
+    if (nf_bound > 0) {
+        CK(ensure(w->slots, w->slots_cap, size_t(n_slots_bound)));
+        if (size_t(n_slots_bound) * 2 * cap > w->slot_list_cap || !w->slot_text) {
             cudaFree(w->slot_text); cudaFree(w->slot_pos);
             w->slot_text = w->slot_pos = nullptr;
-            size_t n = size_t(n_slots) * 2 * cap;
+            size_t n = size_t(n_slots_bound) * 2 * cap;
             n += n / 4 + 64;
             CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_text), n * 4));
             CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_pos), n * 4));
             w->slot_list_cap = n;
         }
-        CK(ensure(w->cand, w->cand_cap, size_t(n_slots)));
+        CK(ensure(w->cand, w->cand_cap, size_t(n_slots_bound)));
+        CK(ensure(w->events, w->events_cap, size_t(n_slots_bound) * w->stride));
         CandParams cp;
         cp.a = a;
         cp.flagged = w->flagged;
-        cp.n_flagged = nf;
+        cp.n_flagged = &w->dev->n_flagged;
         cp.mcov = uint32_t(p.mcov_out);
         cp.k_left = uint32_t(p.k_left);
         cp.k_right = uint32_t(p.k_right);
@@ -807,29 +822,16 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
         cp.slots = w->slots;
         cp.slot_text = w->slot_text;
         cp.slot_pos = w->slot_pos;
-        k_candidates<<<unsigned((nf + 3) / 4), 128, 0, stream>>>(cp);
+        k_candidates<<<unsigned((nf_bound + 3) / 4), 128, 0, stream>>>(cp);
         CK(cudaGetLastError());
-        ++*launches;
-        k_compact_slots<<<1, 1024, 0, stream>>>(w->slots, n_slots, w->cand, w->dev);
+        k_compact_slots<<<1, 1024, 0, stream>>>(w->slots, &w->dev->n_flagged, w->cand, w->dev);
         CK(cudaGetLastError());
-        ++*launches;
-    }
-    CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    counts->n_analysed = hd.n_analysed;
-    counts->n_candidates = hd.n_slots_valid;
-    counts->saw_n = hd.saw_n;
-    const uint64_t nc = hd.n_slots_valid;
-    w->n_cand = nc;
-    w->stride = uint32_t((sizeof(PackedEventHdr) + 2 * size_t(p.k_left) + size_t(p.k_right) + 15) & ~size_t(15));
-    if (nc > 0) {
-        CK(ensure(w->events, w->events_cap, size_t(nc) * w->stride));
         EventParams ep;
         ep.slots = w->slots;
         ep.slot_text = w->slot_text;
         ep.slot_pos = w->slot_pos;
         ep.cand = w->cand;
-        ep.n_cand = nc;
+        ep.n_cand = &w->dev->n_slots_valid;
         ep.cap = cap;
         ep.k_left = p.k_left;
         ep.k_right = p.k_right;
@@ -842,27 +844,36 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
         ep.out = w->events;
         ep.stride = w->stride;
         ep.dev = w->dev;
-        k_events<<<unsigned((nc + EV_WARPS - 1) / EV_WARPS), EV_WARPS * 32, 0, stream>>>(ep);
+        k_events<<<unsigned((n_slots_bound + EV_WARPS - 1) / EV_WARPS), EV_WARPS * 32, 0, stream>>>(ep);
         CK(cudaGetLastError());
-        ++*launches;
-        CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        counts->saw_n = hd.saw_n;
-        if (hd.bad_ref) { *err = "a candidate references a read/offset outside the staged reads"; return cudaErrorInvalidValue; }
+        *launches += 3;
+    }
+    CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));  // sync 2: counts
+    counts->n_flagged = hd.n_flagged;
+    counts->n_candidates = hd.n_slots_valid;
+    counts->saw_n = hd.saw_n;
+    if (hd.bad_ref) { *err = "a candidate references a read/offset outside the staged reads"; return cudaErrorInvalidValue; }
+    w->n_cand = hd.n_slots_valid;
+    if (w->n_cand) {
+        const size_t bytes = size_t(w->n_cand) * w->stride;
+        if (bytes > w->h_events_cap) {
+            free(w->h_events);
+            w->h_events = static_cast<uint8_t*>(malloc(bytes + bytes / 4));
+            w->h_events_cap = w->h_events ? bytes + bytes / 4 : 0;
+            if (!w->h_events) { *err = "malloc"; return cudaErrorMemoryAllocation; }
+        }
+        CK(cudaMemcpyAsync(w->h_events, w->events, bytes, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));  // sync 3: the packed candidates
     }
     return cudaSuccess;
 }
 
-// D2H of the packed candidates, then keep the variants (supp0>0 && supp1>0) in order
-cudaError_t snp_fetch_events(SnpWork* w, e2s_event* host, uint64_t cap, uint64_t* n, cudaStream_t stream) {
+// expands the host copy of the packed candidates, keeping the variants (supp0>0 && supp1>0) in order
+cudaError_t snp_fetch_events(SnpWork* w, e2s_event* host, uint64_t cap, uint64_t* n, cudaStream_t) {
     *n = 0;
     if (w->n_cand == 0) return cudaSuccess;
-    const size_t bytes = size_t(w->n_cand) * w->stride;
-    uint8_t* tmp = static_cast<uint8_t*>(malloc(bytes));
-    if (!tmp) return cudaErrorMemoryAllocation;
-    cudaError_t e = cudaMemcpyAsync(tmp, w->events, bytes, cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) { free(tmp); return e; }
+    const uint8_t* tmp = w->h_events;
     uint64_t k = 0;
     for (uint64_t c = 0; c < w->n_cand; ++c) {
         const uint8_t* o = tmp + c * w->stride;
@@ -885,7 +896,6 @@ cudaError_t snp_fetch_events(SnpWork* w, e2s_event* host, uint64_t cap, uint64_t
         }
         ++k;
     }
-    free(tmp);
     *n = k;
     return cudaSuccess;
 }
