@@ -21,7 +21,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-cudart", "static"] + ARCH
 
 CU_SOURCES = ["capi.cu", "cluster.cu", "snp.cu", "unpack.cu"]
-CLI_SOURCES = {"ebwt2clust": ["ebwt2clust_main.cpp", "host_io.cpp"], "clust2snp": ["clust2snp_main.cpp", "host_io.cpp"]}
+CLI_SOURCES = {"ebwt2clust": ["ebwt2clust_main.cpp"], "clust2snp": ["clust2snp_main.cpp"]}
 
 
 def _newer(target, sources):

@@ -59,6 +59,7 @@ struct e2s_shard {
     size_t desc_cap = 0;
     ClusterDev* d_res = nullptr;
     ClusterDev h_res;           // host copy of the last scan's accumulators (incl. length histogram)
+    ClusterDev* h_pin = nullptr; // pinned staging for that copy
     bool have_scan_stats = false;
     uint8_t* d_packed = nullptr;
     uint64_t packed_cap = 0;
@@ -241,6 +242,7 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->d_desc);
     cudaFree(s->d_flags);
     cudaFree(s->d_packed);
+    cudaFreeHost(s->h_pin);
     cudaFree(s->d_res);
     cudaFree(s->d_hist);
     snp_work_destroy(s->work);
@@ -424,7 +426,8 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
         CU(c, le);
         ++c->launches;
     }
-    ClusterDev h;
+    if (!s->h_pin) CU(c, cudaHostAlloc(reinterpret_cast<void**>(&s->h_pin), sizeof(ClusterDev), cudaHostAllocDefault));
+    ClusterDev& h = *s->h_pin;
     for (int attempt = 0; attempt < 2; ++attempt) {
         CU(c, cudaMemsetAsync(s->d_desc, 0, num_tiles * 2 * 8, c->stream));
         CU(c, cudaMemsetAsync(s->d_res, 0, sizeof(ClusterDev), c->stream));

@@ -654,7 +654,8 @@ struct SnpWork {
     uint64_t* cand = nullptr; size_t cand_cap = 0;
     uint8_t* events = nullptr; size_t events_cap = 0;
     SnpDev* dev = nullptr;
-    uint8_t* h_events = nullptr; size_t h_events_cap = 0;  // host copy of the packed candidates
+    SnpDev* h_dev = nullptr;                                // pinned staging of the counters
+    uint8_t* h_events = nullptr; size_t h_events_cap = 0;  // pinned host copy of the packed candidates
     uint64_t n_cand = 0;
     uint32_t stride = 0;
     int k_left = 0, k_right = 0;
@@ -668,7 +669,8 @@ void snp_work_destroy(SnpWork* w) {
     cudaFree(w->tile_first); cudaFree(w->flag_words); cudaFree(w->block_sum); cudaFree(w->flagged);
     cudaFree(w->slots); cudaFree(w->slot_text); cudaFree(w->slot_pos); cudaFree(w->cand); cudaFree(w->events);
     cudaFree(w->dev);
-    free(w->h_events);
+    cudaFreeHost(w->h_dev);
+    cudaFreeHost(w->h_events);
     delete w;
 }
 
@@ -694,6 +696,7 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     w->k_left = p.k_left;
     w->k_right = p.k_right;
     if (!w->dev) CK(cudaMalloc(reinterpret_cast<void**>(&w->dev), sizeof(SnpDev)));
+    if (!w->h_dev) CK(cudaHostAlloc(reinterpret_cast<void**>(&w->h_dev), sizeof(SnpDev), cudaHostAllocDefault));
     CK(cudaMemsetAsync(w->dev, 0, sizeof(SnpDev), stream));
     if (a.m == 0 || a.n_local == 0) return cudaSuccess;
 
@@ -745,7 +748,7 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum, w->survivors, &w->dev->n_survivors);
     CK(cudaGetLastError());
     *launches += 2;
-    SnpDev hd;
+    SnpDev& hd = *w->h_dev;
     CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));  // sync 1: the survivor count sizes everything downstream
     counts->n_analysed = hd.n_analysed;
@@ -858,10 +861,11 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     if (w->n_cand) {
         const size_t bytes = size_t(w->n_cand) * w->stride;
         if (bytes > w->h_events_cap) {
-            free(w->h_events);
-            w->h_events = static_cast<uint8_t*>(malloc(bytes + bytes / 4));
-            w->h_events_cap = w->h_events ? bytes + bytes / 4 : 0;
-            if (!w->h_events) { *err = "malloc"; return cudaErrorMemoryAllocation; }
+            cudaFreeHost(w->h_events);
+            w->h_events = nullptr;
+            w->h_events_cap = 0;
+            CK(cudaHostAlloc(reinterpret_cast<void**>(&w->h_events), bytes + bytes / 4, cudaHostAllocDefault));
+            w->h_events_cap = bytes + bytes / 4;
         }
         CK(cudaMemcpyAsync(w->h_events, w->events, bytes, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));  // sync 3: the packed candidates

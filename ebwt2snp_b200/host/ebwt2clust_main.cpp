@@ -1,0 +1,134 @@
+// ebwt2clust -- drop-in for the reference CLI (ref:ebwt2clust.cpp:141-198): same options, same index
+// files, same X.clusters output and stdout lines; the scan itself runs on the GPU(s) through the C ABI.
+// E2S_GPUS=N shards the eBWT over N GPUs of the box (contiguous ranges, host-side merge of the summaries).
+#include <getopt.h>
+
+#include <iostream>
+#include <thread>
+
+#include "host_io.hpp"
+
+static const int min_def = 2, K_def = 16, lcp_def = 1, da_def = 4, pos_def = 1;
+
+static void help() {
+    std::cout << "ebwt2clust [options]\nOptions:\n"
+              << "-h         Print this help\n"
+              << "-i <arg>   Input fasta file (REQUIRED)\n"
+              << "-k <arg>   Minimum LCP required in clusters (default: " << K_def << ")\n"
+              << "-m <arg>   Discard clusters smaller than this value (default: " << min_def << ")\n"
+              << "-x <arg>   Byte size of LCP integers in input EGSA/BCR file (default: " << lcp_def << ").\n"
+              << "-y <arg>   Byte size of DA integers (read number) in input EGSA/BCR file (default: " << da_def << ").\n"
+              << "-z <arg>   Byte size of pos integers (position in read) in input EGSA/BCR file (default: " << pos_def << ").\n\n"
+              << "The Enhanced Generalized Suffix Array of the reads must exist next to the input file, either as\n"
+              << "<input>.gesa (github.com/felipelouza/egsa) or as the BCR triple <input>.out, .out.lcp, .out.pairSA\n"
+              << "(github.com/giovannarosone/BCR_LCP_GSA). Output goes to <input>.clusters.\n"
+              << "B200 build: set E2S_GPUS=N to shard the eBWT over N GPUs." << std::endl;
+    exit(0);  // the reference exits 0 from help(), also on errors (ref:ebwt2clust.cpp:51)
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) help();
+    int k = 0, min_len = 0, lcp = 0, da = 0, pos = 0;
+    std::string input;
+    int opt;
+    while ((opt = getopt(argc, argv, "hk:i:m:x:y:z:")) != -1) {
+        switch (opt) {
+            case 'h': help(); break;
+            case 'k': k = atoi(optarg); break;
+            case 'm': min_len = atoi(optarg); break;
+            case 'i': input = optarg; break;
+            case 'x': lcp = atoi(optarg); break;
+            case 'y': da = atoi(optarg); break;
+            case 'z': pos = atoi(optarg); break;
+            default: help(); return -1;
+        }
+    }
+    // 0 means "use the default" (ref:ebwt2clust.cpp:175-180)
+    lcp = lcp == 0 ? lcp_def : lcp;
+    da = da == 0 ? da_def : da;
+    pos = pos == 0 ? pos_def : pos;
+    k = k == 0 ? K_def : k;
+    min_len = min_len == 0 ? min_def : min_len;
+    if (input.empty()) help();
+
+    host::Index idx;
+    if (!idx.open(input, lcp, da, pos)) {
+        std::cout << "Error: missing index files." << std::endl;  // ref:include.hpp:72-77
+        return 1;
+    }
+    std::cout << "This is ebwt2clust. Input file: " << input << std::endl;
+    auto ok = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8; };
+    if (!ok(lcp) || !ok(da) || !ok(pos)) {
+        std::cerr << "ebwt2clust: -x/-y/-z must be 1, 2, 4 or 8" << std::endl;
+        return 2;
+    }
+    if (idx.n < 2) {
+        std::cerr << "ebwt2clust: the index holds fewer than 2 records" << std::endl;
+        return 2;
+    }
+
+    const std::vector<uint64_t> cuts = host::shard_cuts(idx.n, host::gpu_count_from_env());
+    const int G = int(cuts.size()) - 1;
+    std::vector<e2s_ctx*> ctx(size_t(G), nullptr);
+    std::vector<e2s_shard*> sh(size_t(G), nullptr);
+    std::vector<e2s_cluster_summary> sums(static_cast<size_t>(G));
+    std::vector<int> rc(size_t(G), 0);
+    std::vector<std::string> errs(static_cast<size_t>(G));
+    auto work = [&](int g) {
+        int r = e2s_ctx_create(g, &ctx[size_t(g)]);
+        if (r) { rc[size_t(g)] = r; errs[size_t(g)] = e2s_last_error(nullptr); return; }
+        const uint64_t lo = cuts[size_t(g)], hi = cuts[size_t(g) + 1];
+        r = e2s_shard_create(ctx[size_t(g)], hi - lo, lo, idx.n, &sh[size_t(g)]);
+        const uint64_t a = lo >= 2 ? lo - 2 : 0, b = hi + E2S_MAX_C_LEN + 1 < idx.n ? hi + E2S_MAX_C_LEN + 1 : idx.n;
+        if (!r) r = idx.load(sh[size_t(g)], a, b - a);
+        if (!r) r = e2s_shard_seal(sh[size_t(g)]);
+        if (!r) r = e2s_cluster_run(sh[size_t(g)], uint32_t(k), min_len, &sums[size_t(g)]);
+        if (r) { rc[size_t(g)] = r; errs[size_t(g)] = e2s_last_error(ctx[size_t(g)]); }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g) th.emplace_back(work, g);
+        for (auto& t : th) t.join();
+    }
+    for (int g = 0; g < G; ++g)
+        if (rc[size_t(g)]) {
+            std::cerr << "ebwt2clust: GPU " << g << ": " << errs[size_t(g)] << std::endl;
+            return 2;
+        }
+
+    FILE* out = fopen((input + ".clusters").c_str(), "wb");
+    if (!out) {
+        std::cerr << "ebwt2clust: cannot write " << input << ".clusters" << std::endl;
+        return 2;
+    }
+    uint64_t n_clust_out = 0;
+    std::vector<uint8_t> buf;
+    for (int g = 0; g < G; ++g) {
+        e2s_cluster_merged mg;
+        int r = e2s_cluster_merge(sums.data(), G, g, &mg);
+        if (!r) r = e2s_cluster_finalize(sh[size_t(g)], &mg);
+        uint64_t m = 0;
+        if (!r) r = e2s_cluster_count(sh[size_t(g)], &m);
+        if (!r) {
+            buf.resize(size_t(m) * 10 + 16);
+            r = e2s_cluster_fetch_packed(sh[size_t(g)], buf.data(), m, &m);
+        }
+        if (r) {
+            std::cerr << "ebwt2clust: " << (e2s_last_error(ctx[size_t(g)])[0] ? e2s_last_error(ctx[size_t(g)]) : e2s_last_error(nullptr)) << std::endl;
+            return 2;
+        }
+        if (m && fwrite(buf.data(), 10, size_t(m), out) != size_t(m)) {
+            std::cerr << "ebwt2clust: short write" << std::endl;
+            return 2;
+        }
+        n_clust_out = mg.n_clust_out;
+    }
+    fclose(out);
+    for (int g = 0; g < G; ++g) {
+        e2s_shard_destroy(sh[size_t(g)]);
+        e2s_ctx_destroy(ctx[size_t(g)]);
+    }
+    // the reference counts closures in an unsigned int (ref:ebwt2clust.cpp:88,137)
+    std::cout << "Done. " << static_cast<unsigned int>(n_clust_out) << " clusters saved to output file." << std::endl;
+    return 0;
+}

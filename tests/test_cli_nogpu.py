@@ -1,0 +1,42 @@
+"""not gpu: CLI behaviour that is decided before any GPU work (SURVEY.md §8(b) 'Errors' row)."""
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "ebwt2snp_b200", "bin")
+
+
+def run(tool, *args):
+    return subprocess.run([os.path.join(BIN, tool), *args], capture_output=True, text=True)
+
+
+def test_help_exits_zero(built):
+    for tool in ("ebwt2clust", "clust2snp"):
+        for args in ([], ["-h"], ["-Q"]):
+            r = run(tool, *args)
+            assert r.returncode == 0 and tool + " [options]" in r.stdout, (tool, args)  # ref:ebwt2clust.cpp:51
+    assert run("ebwt2clust", "-k", "3").returncode == 0           # no -i  -> help
+    assert run("clust2snp", "-i", "x.fasta", "-n", "0").returncode == 0  # -n 0 -> help (ref:clust2snp.cpp:1045)
+    # -M and -b are not in the option string: help, exit 0 (ref:clust2snp.cpp:976,981,996)
+    assert "clust2snp [options]" in run("clust2snp", "-i", "x", "-n", "3", "-M", "100").stdout
+    assert "clust2snp [options]" in run("clust2snp", "-i", "x", "-n", "3", "-b").stdout
+
+
+def test_missing_index_exits_one(built):
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "none.fasta")
+        for tool, extra in (("ebwt2clust", []), ("clust2snp", ["-n", "5"])):
+            r = run(tool, "-i", fa, *extra)
+            assert r.returncode == 1 and "Error: missing index files." in r.stdout  # ref:include.hpp:72-77
+
+
+def test_missing_clusters_prints_help(built):
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "r.fasta")
+        open(fa + ".gesa", "wb").write(b"\0" * 26)
+        r = run("clust2snp", "-i", fa, "-n", "5", "-x", "4", "-y", "4", "-z", "4")
+        assert r.returncode == 0 and "ERROR: Could not find BWT clusters file" in r.stdout  # ref:clust2snp.cpp:1063-1068
+        assert "Output events will be stored" not in r.stdout

@@ -1,0 +1,68 @@
+"""not gpu: the oracle restatement (oracle/oracle.c) against the golden vectors produced by the unmodified
+reference, against the reference's own two known answers, and -- where oracle/_ref is present -- live."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import golden_util as GU
+from tests import helpers as H
+
+
+def test_phase1_golden(built):
+    n = 0
+    for c in GU.phase1_cases():
+        s, l, ncl, _ = O.cluster_lm(c["lcp"], c["bwt"], c["k"], c["m"])
+        assert O.clusters_to_bytes(s, l) == c["clusters"]
+        assert ncl == c["n_clust_out"]
+        n += 1
+    assert n == 72
+
+
+@pytest.mark.parametrize("name", ["micro_a", "micro_b"])
+def test_micro_golden(built, name):
+    g = GU.micro(name)
+    e = g["egsa"]
+    s, l, ncl, _ = O.cluster_lm(e["lcp"], e["bwt"], g["k"], g["m"])
+    assert O.clusters_to_bytes(s, l) == g["clusters"] and ncl == g["n_clust_out"]
+    off = O.uniform_read_offsets(*g["reads"].shape)
+    for v in g["variants"]:
+        p = O.default_params(g["nreads1"], **GU.params_kw(v["args"]))
+        st = O.statistics(s, l, p.mcov_out, p.pval)
+        assert (2 * p.mcov_out, st.max_clust_length) == v["allowed"]
+        text, res = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], s, l, p, st.max_clust_length, g["reads"], off)
+        if v["rc"] == 0:
+            assert res.n_candidates == v["ncand"] and text == v["snp"], v["args"]
+        else:  # the reference crashed: zero candidates (ref:clust2snp.cpp:531)
+            assert res.n_candidates == 0
+
+
+def test_distance_known_answers(built):
+    # the only golden vectors in the reference tree: ref:clust2snp.cpp:250-251
+    for g in (2, 3, 8):
+        assert O.distance(b"ACCTACTG", b"TTACTTAC", g) == (1, 2)
+        assert O.distance(b"TTACTTAC", b"ACCTACTG", g) == (1, -2)
+    assert O.distance(b"ACGTACGT", b"ACGTACGT", 10 if False else 8) == (0, 0)
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+def test_phase1_live_vs_reference(built):
+    rng = np.random.default_rng(5)
+    dt = np.dtype([("text", "<u4"), ("suff", "<u4"), ("lcp", "<u4"), ("bwt", "u1")])
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "X.fasta")
+        open(fa, "w").write(">a\nA\n")
+        for it in range(40):
+            n = int(rng.integers(2, 2000))
+            k = int(rng.choice([1, 2, 3, 5, 16, 70]))
+            m = int(rng.choice([1, 2, 3, 8]))
+            lcp = H.random_lcp(rng, n, k, it % 5)
+            bwt = rng.choice(H.BWT_ALPHABET, size=n)
+            rec = np.zeros(n, dtype=dt)
+            rec["lcp"], rec["bwt"] = lcp, bwt
+            rec.tofile(fa + ".gesa")
+            r, ncl = O.ref_ebwt2clust(fa, k=k, m=m)
+            s, l, nc, _ = O.cluster_lm(lcp, bwt, k, m)
+            assert O.clusters_to_bytes(s, l) == open(fa + ".clusters", "rb").read() and nc == ncl
