@@ -260,7 +260,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from ebwt2snp_b200 import api
+    from ebwt2snp_b200 import api, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -288,24 +288,12 @@ def main():
     ctx = api.Context(local, stream.cuda_stream)
     sh = ctx.shard(n, global_off, n_global)
     sh.load_soa(eg["lcp"], eg["text"], eg["suff"], eg["bwt"], first=global_off, device=True)
-    if world > 1:
-        # halo exchange over NCCL: my left neighbour's last 2 records, my right neighbour's first 151
-        H = api.MAX_C_LEN + 1
-        edge = torch.zeros((2 + H) * 4, dtype=torch.int32, device=dev)  # [lcp,text,suff,bwt] x (tail2 + head151)
-        def pack(a, b):
-            return torch.cat([eg["lcp"][a:b], eg["text"][a:b], eg["suff"][a:b], eg["bwt"][a:b].to(torch.int32)])
-        mine = torch.cat([pack(n - 2, n), pack(0, H)])
-        allv = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
-        if rank > 0:
-            t2 = allv[rank - 1][:8].view(4, 2)
-            sh.load_soa(t2[0].contiguous(), t2[1].contiguous(), t2[2].contiguous(), t2[3].to(torch.uint8).contiguous(),
-                        first=global_off - 2, device=True)
-        if rank < world - 1:
-            h = allv[rank + 1][8:].view(4, H)
-            sh.load_soa(h[0].contiguous(), h[1].contiguous(), h[2].contiguous(), h[3].to(torch.uint8).contiguous(),
-                        first=global_off + n, device=True)
-        del edge
+    # halo exchange over NCCL: my left neighbour's last 2 records, my right neighbour's first 151
+    left, right = sharding.exchange_halo(eg["lcp"], eg["text"], eg["suff"], eg["bwt"], dev)
+    if left is not None:
+        sh.load_soa(left["lcp"], left["text"], left["suff"], left["bwt"], first=global_off - sharding.HALO_L, device=True)
+    if right is not None:
+        sh.load_soa(right["lcp"], right["text"], right["suff"], right["bwt"], first=global_off + n, device=True)
     sh.seal()
     reads_dev = torch.from_numpy(rs.reads).to(dev).view(-1)
     R, L = rs.reads.shape
@@ -321,39 +309,10 @@ def main():
         eg[kk] = None
     torch.cuda.empty_cache()
 
-    W = api.SUMMARY_WORDS
-
     def step():
-        """one pass of the hot path over the resident shard(s)"""
-        s = sh.cluster_run(K_DEF, M_DEF)
-        if world > 1:
-            mine = torch.from_numpy(np.frombuffer(bytes(s), dtype=np.int64).copy()).to(dev)
-            allv = [torch.zeros_like(mine) for _ in range(world)]
-            dist.all_gather(allv, mine)  # NCCL over NVLink: W u64 words per shard
-            sums = [api.ClusterSummary.from_buffer_copy(a.cpu().numpy().tobytes()) for a in allv]
-        else:
-            sums = [s]
-        mg = api.cluster_merge(sums, rank)
-        sh.cluster_finalize(mg)
-        st = sh.statistics(finish=False)
-        last_len = st.last_len
-        if world > 1:
-            v = torch.tensor(list(st.hist) + [st.n_clust, st.n_bases, st.last_len], dtype=torch.int64, device=dev)
-            allv = [torch.zeros_like(v) for _ in range(world)]
-            dist.all_gather(allv, v)
-            tot = torch.stack(allv).sum(0).tolist()
-            for i in range(api.HIST_BINS):
-                st.hist[i] = tot[i]
-            st.n_clust, st.n_bases = tot[api.HIST_BINS], tot[api.HIST_BINS + 1]
-            for a in allv:  # the globally last record
-                if int(a[api.HIST_BINS]) > 0:
-                    last_len = int(a[api.HIST_BINS + 2])
-        api.statistics_finish(st, last_len, params.mcov_out, params.pval)
-        cnt = sh.find_events(params, st.max_clust_length)
-        if world > 1:  # global event ids = exclusive prefix of the per-shard kept-event counts
-            v = torch.tensor([cnt.n_events], dtype=torch.int64, device=dev)
-            allv = [torch.zeros_like(v) for _ in range(world)]
-            dist.all_gather(allv, v)
+        """one pass of the hot path over the resident shard(s): K1, K2, summaries all-gather + merge, statistics
+        all-gather, K3a/K3x/K3b/K4, event-count all-gather (ebwt2snp_b200/sharding.py)"""
+        mg, st, cnt, _first_id = sharding.hot_path_step(sh, params, K_DEF, M_DEF, dev)
         return mg, st, cnt
 
     def sync_all():

@@ -68,7 +68,8 @@ struct e2s_shard {
     // phase 2
     SnpWork* work = nullptr;
     std::vector<e2s_event> events;
-    bool have_events = false;
+    uint64_t n_variants = 0;
+    bool have_events = false, events_expanded = false;
 };
 
 static thread_local std::string g_err;
@@ -192,6 +193,7 @@ int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t
     *out = nullptr;
     if (n_local < 2 || global_off + n_local > n_global || (global_off != 0 && global_off < 2))
         return fail(c, E2S_ERR_ARG, "e2s_shard_create: need n_local >= 2 and a range inside [0, n_global)");
+    if (n_global >= (uint64_t(1) << 47)) return fail(c, E2S_ERR_UNSUPPORTED, "e2s_shard_create: n_global must be < 2^47 positions");
     CU(c, cudaSetDevice(c->device));
     e2s_shard* s = new e2s_shard();
     s->ctx = c;
@@ -840,18 +842,10 @@ int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length,
                             counts, &c->launches, &err, &c->timer);
     if (e == cudaErrorInvalidValue && err && strstr(err, "outside the staged reads")) return fail(c, E2S_ERR_UNSUPPORTED, err);
     if (e != cudaSuccess) return cuda_fail(c, e, err);
-    // candidates are few: bring them to the host now and keep the variants
-    uint64_t nv = 0;
-    e = snp_fetch_events(s->work, nullptr, 0, &nv, c->stream);
-    if (e != cudaSuccess) return cuda_fail(c, e, "snp_fetch_events");
-    s->events.resize(nv);
-    if (nv) {
-        e = snp_fetch_events(s->work, s->events.data(), nv, &nv, c->stream);
-        if (e != cudaSuccess) return cuda_fail(c, e, "snp_fetch_events");
-    }
-    counts->n_variants = nv;
-    counts->n_events = 0;
-    for (auto& ev : s->events) counts->n_events += ev.keep ? 1 : 0;
+    // the packed candidates are already in pinned host memory (K4 wrote them there); they are expanded
+    // into e2s_event records when e2s_events_fetch asks for them
+    s->n_variants = counts->n_variants;
+    s->events_expanded = false;
     s->have_events = true;
     return E2S_OK;
 }
@@ -859,7 +853,16 @@ int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length,
 int e2s_events_fetch(e2s_shard* s, e2s_event* events, uint64_t cap, uint64_t* n) {
     if (!s || !n) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
     if (!s->have_events) return fail(s->ctx, E2S_ERR_STATE, "run e2s_find_events first");
-    *n = s->events.size();
+    *n = s->n_variants;
+    if (!events) return E2S_OK;
+    if (!s->events_expanded) {
+        uint64_t nv = 0;
+        s->events.resize(s->n_variants);
+        cudaError_t e = snp_fetch_events(s->work, s->events.data(), s->n_variants, &nv, s->ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(s->ctx, e, "snp_fetch_events");
+        if (nv != s->n_variants) return fail(s->ctx, E2S_ERR_STATE, "event count mismatch between device counter and packed records");
+        s->events_expanded = true;
+    }
     if (!events) return E2S_OK;
     if (cap < s->events.size()) return fail(s->ctx, E2S_ERR_ARG, "e2s_events_fetch: capacity too small");
     if (!s->events.empty()) memcpy(events, s->events.data(), s->events.size() * sizeof(e2s_event));

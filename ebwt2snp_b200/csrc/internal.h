@@ -39,6 +39,7 @@ struct ClusterDev {  // device-resident accumulators of one e2s_cluster_run (zer
     unsigned long long open_start;     // 1 + global START, 0 = none
     unsigned long long end_nm2_start;  // 1 + START of the cluster closed at n_global-2; ~0 = head; 0 = none
     unsigned long long overflow;
+    unsigned long long ticket;         // K2's tile dispenser
     unsigned long long last_rec;       // (index of the last kept record + 1) << 16 | its length
     unsigned long long tail_lcp_nm2, tail_lcp_nm1, tail_bwt_nm1;  // last shard: lcp[n-2], lcp[n-1], bwt[n-1]
     unsigned long long n_bases;        // sum of the kept records' lengths
@@ -97,6 +98,8 @@ struct SnpDev {  // device counters of one e2s_find_events
     unsigned long long saw_n;
     unsigned long long bad_ref;
     unsigned long long unsorted;
+    unsigned long long n_variants;   // candidates with supp0 > 0 and supp1 > 0
+    unsigned long long n_events;     // of those, D <= max_snvs
     unsigned long long pad[1];
 };
 
@@ -128,8 +131,9 @@ cudaError_t launch_check_sorted(const uint64_t* start, const uint16_t* len, uint
 struct SnpWork;  // opaque scratch owned by the shard (snp.cu)
 SnpWork* snp_work_create();
 void snp_work_destroy(SnpWork* w);
-// Runs K3a/K3b/K4; returns events on the device inside `w`.  Synchronises the stream a few times
-// (it needs small counts on the host to size the next launch).
+// Runs K3a/K3x/K3b/K4 back to back on the stream with device-resident counts and synchronises ONCE at the
+// end; the packed events are written by K4 straight into pinned host memory.  If a capacity guess
+// (survivor / flagged lists) was too small the pass is repeated with larger buffers.
 cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int max_clust_length,
                     const uint8_t* d_read_bases, const uint64_t* d_read_off, uint64_t n_reads, int sm_count,
                     cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err,

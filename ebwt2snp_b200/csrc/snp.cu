@@ -238,6 +238,7 @@ struct ExactParams {
     SnpArrays a;
     const uint64_t* list;      // cluster indices to test
     const unsigned long long* n_list;  // device-resident length of the list
+    uint64_t cap_list;         // capacity of the list (the pass is repeated when it was too small)
     uint32_t mcov, k_right;
     uint32_t nr1_lo, nr1_big;
     uint32_t* flag_words;      // out: bit per cluster = passes the find_variants filters
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
     const int lane = threadIdx.x & 31;
     const int gl = lane & (EX_G - 1);
     const uint32_t gmask = ((1u << EX_G) - 1u) << (lane & ~(EX_G - 1));
-    const uint64_t n_list = *p.n_list;
+    const uint64_t n_list = *p.n_list < p.cap_list ? *p.n_list : p.cap_list;
     const uint64_t groups = uint64_t(gridDim.x) * (EX_THREADS / EX_G);
     uint32_t saw_n = 0;
     for (uint64_t i = (uint64_t(blockIdx.x) * EX_THREADS + threadIdx.x) / EX_G; i < n_list; i += groups) {
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_flag_count(const uint32_t* __res
 
 __global__ void __launch_bounds__(FC_THREADS) k_flag_emit(const uint32_t* __restrict__ words, uint64_t n_words,
                                                           const uint32_t* __restrict__ block_sum,
-                                                          uint64_t* __restrict__ out_idx,
+                                                          uint64_t* __restrict__ out_idx, uint64_t cap,
                                                           unsigned long long* out_count) {
     __shared__ uint64_t s_base;
     __shared__ uint32_t s_red[FC_THREADS / 32];
@@ -350,7 +351,8 @@ __global__ void __launch_bounds__(FC_THREADS) k_flag_emit(const uint32_t* __rest
         while (w) {
             int b = __ffs(w) - 1;
             w &= w - 1;
-            out_idx[o++] = wi * 32 + b;
+            if (o < cap) out_idx[o] = wi * 32 + b;  // the caller compares *out_count with cap and retries if it was too small
+            ++o;
         }
         base += tot;
         __syncthreads();
@@ -369,12 +371,16 @@ struct CandParams {
     CandSlot* slots;       // 4 per flagged cluster
     uint32_t* slot_text;   // [slot][2][cap]
     uint32_t* slot_pos;    // [slot][2][cap]
+    uint32_t* valid_words; // bit per slot (zeroed by the caller)
+    uint64_t cap_flagged;  // capacity of the flagged list / slot arrays
 };
 
 __global__ void __launch_bounds__(128) k_candidates(CandParams p) {
-    const uint64_t f = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (f >= *p.n_flagged) return;
+    uint64_t n_f = *p.n_flagged;
+    if (n_f > p.cap_flagged) n_f = p.cap_flagged;  // overflow is reported by the host, which retries with more room
+    const uint64_t warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t f = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; f < n_f; f += warps) {
     const uint64_t ci = p.flagged[f];
     const uint64_t start = p.a.cl_start[ci];
     const uint32_t len = p.a.cl_len[ci];
@@ -448,32 +454,46 @@ __global__ void __launch_bounds__(128) k_candidates(CandParams p) {
                 hdr.n1 = n1 < p.cap ? n1 : p.cap;
                 hdr.valid = (n0 > 0 && n1 > 0) ? 1u : 0u;
             }
-            if (lane == 0) p.slots[slot] = hdr;
+            if (lane == 0) {
+                p.slots[slot] = hdr;
+                if (hdr.valid) atomicOr(&p.valid_words[slot >> 5], 1u << (slot & 31));
+            }
         }
+    }
     }
 }
 
-// valid slots, in order (single block: the list is tiny)
-__global__ void __launch_bounds__(1024) k_compact_slots(const CandSlot* __restrict__ slots,
-                                                        const unsigned long long* __restrict__ n_flagged,
+// valid slots, in order: ordered compaction of the slot bit mask (single block: a few thousand words)
+__global__ void __launch_bounds__(1024) k_compact_slots(const uint32_t* __restrict__ valid_words, uint64_t n_words,
                                                         uint64_t* __restrict__ cand, SnpDev* dev) {
     __shared__ uint32_t s_w[32];
     __shared__ uint64_t s_base;
-    const uint64_t n_slots = *n_flagged * 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
-    for (uint64_t i0 = 0; i0 < n_slots; i0 += 1024) {
-        const uint64_t i = i0 + threadIdx.x;
-        const uint32_t v = (i < n_slots) ? slots[i].valid : 0u;
-        const uint32_t b = __ballot_sync(FULL, v);
-        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(b);
-        __syncthreads();
-        uint32_t off = __popc(b & ((1u << (threadIdx.x & 31)) - 1u)), tot = 0;
-        for (int w = 0; w < 32; ++w) {
-            if (w < int(threadIdx.x >> 5)) off += s_w[w];
-            tot += s_w[w];
+    for (uint64_t i0 = 0; i0 < n_words; i0 += 1024) {
+        const uint64_t wi = i0 + threadIdx.x;
+        uint32_t w = wi < n_words ? valid_words[wi] : 0u;
+        const uint32_t c = __popc(w);
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += o;
         }
-        if (v) cand[s_base + off] = i;
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        uint32_t off = inc - c, tot = 0;
+        for (int q = 0; q < 32; ++q) {
+            if (q < warp) off += s_w[q];
+            tot += s_w[q];
+        }
+        uint64_t o = s_base + off;
+        while (w) {
+            const int b = __ffs(w) - 1;
+            w &= w - 1;
+            cand[o++] = wi * 32 + b;
+        }
         __syncthreads();
         if (threadIdx.x == 0) s_base += tot;
         __syncthreads();
@@ -511,8 +531,9 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
     __shared__ uint64_t s_base[EV_WARPS][MAX_C_LEN];
     __shared__ char s_cons[EV_WARPS][2][E2S_MAX_K];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t c = uint64_t(blockIdx.x) * EV_WARPS + w;
-    if (c >= *p.n_cand) return;
+    const uint64_t n_cand = *p.n_cand;
+    for (uint64_t c = uint64_t(blockIdx.x) * EV_WARPS + w; c < n_cand; c += uint64_t(gridDim.x) * EV_WARPS) {
+    __syncwarp();
     const uint64_t slot = p.cand[c];
     const CandSlot hdr = p.slots[slot];
     const int kl = p.k_left;
@@ -636,6 +657,9 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
         oh->right_len = rl;
         oh->flags = (variant ? 1 : 0) | ((variant && D <= p.max_snvs) ? 2 : 0);
         oh->cluster_start = hdr.cluster_start;
+        if (variant) atomicAdd(&p.dev->n_variants, 1ull);
+        if (variant && D <= p.max_snvs) atomicAdd(&p.dev->n_events, 1ull);
+    }
     }
 }
 
@@ -651,11 +675,13 @@ struct SnpWork {
     uint64_t* flagged = nullptr; size_t flagged_cap = 0;
     CandSlot* slots = nullptr; size_t slots_cap = 0;
     uint32_t* slot_text = nullptr; uint32_t* slot_pos = nullptr; size_t slot_list_cap = 0;
+    uint32_t* valid_words = nullptr; size_t valid_cap = 0;
     uint64_t* cand = nullptr; size_t cand_cap = 0;
-    uint8_t* events = nullptr; size_t events_cap = 0;
     SnpDev* dev = nullptr;
     SnpDev* h_dev = nullptr;                                // pinned staging of the counters
-    uint8_t* h_events = nullptr; size_t h_events_cap = 0;  // pinned host copy of the packed candidates
+    uint8_t* h_events = nullptr; size_t h_events_cap = 0;  // pinned + mapped: K4 writes the packed candidates here
+    uint8_t* d_events = nullptr;                            // device view of h_events
+    uint64_t want_survivors = 0, want_flagged = 0;          // capacity guesses, grown when a pass overflows
     uint64_t n_cand = 0;
     uint32_t stride = 0;
     int k_left = 0, k_right = 0;
@@ -667,7 +693,7 @@ void snp_work_destroy(SnpWork* w) {
     if (!w) return;
     cudaFree(w->flag_words2); cudaFree(w->survivors);
     cudaFree(w->tile_first); cudaFree(w->flag_words); cudaFree(w->block_sum); cudaFree(w->flagged);
-    cudaFree(w->slots); cudaFree(w->slot_text); cudaFree(w->slot_pos); cudaFree(w->cand); cudaFree(w->events);
+    cudaFree(w->slots); cudaFree(w->slot_text); cudaFree(w->slot_pos); cudaFree(w->valid_words); cudaFree(w->cand);
     cudaFree(w->dev);
     cudaFreeHost(w->h_dev);
     cudaFreeHost(w->h_events);
@@ -697,179 +723,182 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     w->k_right = p.k_right;
     if (!w->dev) CK(cudaMalloc(reinterpret_cast<void**>(&w->dev), sizeof(SnpDev)));
     if (!w->h_dev) CK(cudaHostAlloc(reinterpret_cast<void**>(&w->h_dev), sizeof(SnpDev), cudaHostAllocDefault));
-    CK(cudaMemsetAsync(w->dev, 0, sizeof(SnpDev), stream));
     if (a.m == 0 || a.n_local == 0) return cudaSuccess;
 
     const uint32_t nr1_big = p.nr_reads1 > 0xffffffffull ? 1u : 0u;
     const uint32_t nr1_lo = nr1_big ? 0xffffffffu : uint32_t(p.nr_reads1);
     const uint32_t num_tiles = uint32_t((a.n_local + PS_T - 1) / PS_T);
+    const uint64_t n_words = (a.m + 31) / 32;
+    const uint32_t n_fblocks = uint32_t((n_words + FC_WORDS - 1) / FC_WORDS);
+    const uint32_t cap = uint32_t(p.consensus_reads < MAX_C_LEN ? p.consensus_reads : MAX_C_LEN);
+    w->stride = uint32_t((sizeof(PackedEventHdr) + 2 * size_t(p.k_left) + size_t(p.k_right) + 15) & ~size_t(15));
 
     CK(ensure(w->tile_first, w->tile_first_cap, size_t(num_tiles) + 1));
-    const uint64_t n_words = (a.m + 31) / 32;
     CK(ensure(w->flag_words, w->flag_cap, size_t(n_words)));
     CK(ensure(w->flag_words2, w->flag2_cap, size_t(n_words)));
-    CK(cudaMemsetAsync(w->flag_words, 0, n_words * 4, stream));
-    CK(cudaMemsetAsync(w->flag_words2, 0, n_words * 4, stream));
-    const uint32_t n_fblocks = uint32_t((n_words + FC_WORDS - 1) / FC_WORDS);
     CK(ensure(w->block_sum, w->block_sum_cap, size_t(n_fblocks)));
-    CK(ensure(w->survivors, w->survivors_cap, size_t(a.m)));
+    // first guesses: clusters with two frequent base codes are variants and repeats, a small fraction of all
+    if (!w->want_survivors) w->want_survivors = a.m / 64 + 4096;
+    if (!w->want_flagged) w->want_flagged = a.m / 256 + 2048;
 
-    k_tile_first<<<(num_tiles + 1 + 255) / 256, 256, 0, stream>>>(a.cl_start, a.m, a.global_off, num_tiles, w->tile_first);
-    CK(cudaGetLastError());
-    ++*launches;
-
-    // K3a: base-code prefilter (BWT bytes only)
-    {
-        ScanParams sp;
-        sp.a = a;
-        sp.tile_first = w->tile_first;
-        sp.num_tiles = num_tiles;
-        sp.min_len = uint32_t(2 * p.mcov_out);
-        sp.max_len = uint32_t(max_clust_length);
-        sp.mcov = uint32_t(p.mcov_out);
-        sp.flag_words = w->flag_words;
-        sp.dev = w->dev;
-        const size_t smem = size_t(PS_STAGES) * PS_SPAN;
-        CK(cudaFuncSetAttribute(k_code_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_code_scan, PS_THREADS, smem));
-        if (occ < 1) occ = 1;
-        uint64_t grid = uint64_t(sm_count) * occ;
-        if (grid > num_tiles) grid = num_tiles;
-        if (timer) timer->begin(E2S_KERNEL_SCAN, stream);
-        k_code_scan<<<unsigned(grid), PS_THREADS, smem, stream>>>(sp);
-        if (timer) timer->end(stream);
-        CK(cudaGetLastError());
-        ++*launches;
-    }
-    // survivors of the prefilter, in order
-    k_flag_count<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum);
-    CK(cudaGetLastError());
-    k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum, w->survivors, &w->dev->n_survivors);
-    CK(cudaGetLastError());
-    *launches += 2;
     SnpDev& hd = *w->h_dev;
-    CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));  // sync 1: the survivor count sizes everything downstream
-    counts->n_analysed = hd.n_analysed;
-    const uint64_t nu = hd.n_survivors;
-    if (nu == 0) return cudaSuccess;
-
-    // K3x: exact filters on the survivors
-    {
-        ExactParams ep;
-        ep.a = a;
-        ep.list = w->survivors;
-        ep.n_list = &w->dev->n_survivors;
-        ep.mcov = uint32_t(p.mcov_out);
-        ep.k_right = uint32_t(p.k_right);
-        ep.nr1_lo = nr1_lo;
-        ep.nr1_big = nr1_big;
-        ep.flag_words = w->flag_words2;
-        ep.dev = w->dev;
-        uint64_t grid = (nu + (EX_THREADS / EX_G) - 1) / (EX_THREADS / EX_G);
-        if (grid > uint64_t(sm_count) * 8) grid = uint64_t(sm_count) * 8;
-        if (timer) timer->begin(E2S_KERNEL_EXACT, stream);
-        k_cluster_exact<<<unsigned(grid), EX_THREADS, 0, stream>>>(ep);
-        if (timer) timer->end(stream);
-        CK(cudaGetLastError());
-        ++*launches;
-    }
-    k_flag_count<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->block_sum);
-    CK(cudaGetLastError());
-    ++*launches;
-    uint64_t nf_bound = nu;  // flagged clusters are a subset of the survivors
-    if (nu > (uint64_t(1) << 20)) {
-        // unusually many survivors: fetch the exact count rather than sizing the slot arrays by the bound
-        uint32_t* h_sums = static_cast<uint32_t*>(malloc(size_t(n_fblocks) * 4));
-        if (!h_sums) { *err = "malloc"; return cudaErrorMemoryAllocation; }
-        cudaError_t e = cudaMemcpyAsync(h_sums, w->block_sum, size_t(n_fblocks) * 4, cudaMemcpyDeviceToHost, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        uint64_t nf = 0;
-        for (uint32_t i = 0; i < n_fblocks; ++i) nf += h_sums[i];
-        free(h_sums);
-        if (e != cudaSuccess) { *err = "flag sums D2H"; return e; }
-        nf_bound = nf;
-    }
-    CK(ensure(w->flagged, w->flagged_cap, size_t(nf_bound) + 1));
-    k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->block_sum, w->flagged, &w->dev->n_flagged);
-    CK(cudaGetLastError());
-    ++*launches;
-
-    const uint32_t cap = uint32_t(p.consensus_reads < MAX_C_LEN ? p.consensus_reads : MAX_C_LEN);
-    const uint64_t n_slots_bound = nf_bound * 4;
-    w->stride = uint32_t((sizeof(PackedEventHdr) + 2 * size_t(p.k_left) + size_t(p.k_right) + 15) & ~size_t(15));
-    if (nf_bound > 0) {
-        CK(ensure(w->slots, w->slots_cap, size_t(n_slots_bound)));
-        if (size_t(n_slots_bound) * 2 * cap > w->slot_list_cap || !w->slot_text) {
+    for (int attempt = 0;; ++attempt) {
+        const uint64_t cap_surv = w->want_survivors < a.m ? w->want_survivors : a.m;
+        const uint64_t cap_flag = w->want_flagged < cap_surv ? w->want_flagged : cap_surv;
+        const uint64_t n_slots = cap_flag * 4;
+        const uint64_t n_vwords = (n_slots + 31) / 32;
+        CK(ensure(w->survivors, w->survivors_cap, size_t(cap_surv)));
+        CK(ensure(w->flagged, w->flagged_cap, size_t(cap_flag)));
+        CK(ensure(w->slots, w->slots_cap, size_t(n_slots)));
+        if (size_t(n_slots) * 2 * cap > w->slot_list_cap || !w->slot_text) {
             cudaFree(w->slot_text); cudaFree(w->slot_pos);
             w->slot_text = w->slot_pos = nullptr;
-            size_t n = size_t(n_slots_bound) * 2 * cap;
-            n += n / 4 + 64;
+            w->slot_list_cap = 0;
+            const size_t n = size_t(n_slots) * 2 * cap;
             CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_text), n * 4));
             CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_pos), n * 4));
             w->slot_list_cap = n;
         }
-        CK(ensure(w->cand, w->cand_cap, size_t(n_slots_bound)));
-        CK(ensure(w->events, w->events_cap, size_t(n_slots_bound) * w->stride));
-        CandParams cp;
-        cp.a = a;
-        cp.flagged = w->flagged;
-        cp.n_flagged = &w->dev->n_flagged;
-        cp.mcov = uint32_t(p.mcov_out);
-        cp.k_left = uint32_t(p.k_left);
-        cp.k_right = uint32_t(p.k_right);
-        cp.cap = cap;
-        cp.nr1_lo = nr1_lo;
-        cp.nr1_big = nr1_big;
-        cp.slots = w->slots;
-        cp.slot_text = w->slot_text;
-        cp.slot_pos = w->slot_pos;
-        k_candidates<<<unsigned((nf_bound + 3) / 4), 128, 0, stream>>>(cp);
-        CK(cudaGetLastError());
-        k_compact_slots<<<1, 1024, 0, stream>>>(w->slots, &w->dev->n_flagged, w->cand, w->dev);
-        CK(cudaGetLastError());
-        EventParams ep;
-        ep.slots = w->slots;
-        ep.slot_text = w->slot_text;
-        ep.slot_pos = w->slot_pos;
-        ep.cand = w->cand;
-        ep.n_cand = &w->dev->n_slots_valid;
-        ep.cap = cap;
-        ep.k_left = p.k_left;
-        ep.k_right = p.k_right;
-        ep.max_gap = p.max_gap;
-        ep.max_err = p.max_err;
-        ep.max_snvs = p.max_snvs;
-        ep.bases = d_read_bases;
-        ep.off = d_read_off;
-        ep.n_reads = n_reads;
-        ep.out = w->events;
-        ep.stride = w->stride;
-        ep.dev = w->dev;
-        k_events<<<unsigned((n_slots_bound + EV_WARPS - 1) / EV_WARPS), EV_WARPS * 32, 0, stream>>>(ep);
-        CK(cudaGetLastError());
-        *launches += 3;
-    }
-    CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));  // sync 2: counts
-    counts->n_flagged = hd.n_flagged;
-    counts->n_candidates = hd.n_slots_valid;
-    counts->saw_n = hd.saw_n;
-    if (hd.bad_ref) { *err = "a candidate references a read/offset outside the staged reads"; return cudaErrorInvalidValue; }
-    w->n_cand = hd.n_slots_valid;
-    if (w->n_cand) {
-        const size_t bytes = size_t(w->n_cand) * w->stride;
-        if (bytes > w->h_events_cap) {
+        CK(ensure(w->valid_words, w->valid_cap, size_t(n_vwords)));
+        CK(ensure(w->cand, w->cand_cap, size_t(n_slots)));
+        if (size_t(n_slots) * w->stride > w->h_events_cap) {
             cudaFreeHost(w->h_events);
             w->h_events = nullptr;
             w->h_events_cap = 0;
-            CK(cudaHostAlloc(reinterpret_cast<void**>(&w->h_events), bytes + bytes / 4, cudaHostAllocDefault));
-            w->h_events_cap = bytes + bytes / 4;
+            const size_t bytes = size_t(n_slots) * w->stride;
+            CK(cudaHostAlloc(reinterpret_cast<void**>(&w->h_events), bytes, cudaHostAllocMapped));
+            CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&w->d_events), w->h_events, 0));
+            w->h_events_cap = bytes;
         }
-        CK(cudaMemcpyAsync(w->h_events, w->events, bytes, cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));  // sync 3: the packed candidates
+
+        CK(cudaMemsetAsync(w->dev, 0, sizeof(SnpDev), stream));
+        CK(cudaMemsetAsync(w->flag_words, 0, n_words * 4, stream));
+        CK(cudaMemsetAsync(w->flag_words2, 0, n_words * 4, stream));
+        CK(cudaMemsetAsync(w->valid_words, 0, n_vwords * 4, stream));
+
+        k_tile_first<<<(num_tiles + 1 + 255) / 256, 256, 0, stream>>>(a.cl_start, a.m, a.global_off, num_tiles, w->tile_first);
+        CK(cudaGetLastError());
+        ++*launches;
+        {   // K3a: base-code prefilter (BWT bytes only)
+            ScanParams sp;
+            sp.a = a;
+            sp.tile_first = w->tile_first;
+            sp.num_tiles = num_tiles;
+            sp.min_len = uint32_t(2 * p.mcov_out);
+            sp.max_len = uint32_t(max_clust_length);
+            sp.mcov = uint32_t(p.mcov_out);
+            sp.flag_words = w->flag_words;
+            sp.dev = w->dev;
+            const size_t smem = size_t(PS_STAGES) * PS_SPAN;
+            CK(cudaFuncSetAttribute(k_code_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            int occ = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_code_scan, PS_THREADS, smem));
+            if (occ < 1) occ = 1;
+            uint64_t grid = uint64_t(sm_count) * occ;
+            if (grid > num_tiles) grid = num_tiles;
+            if (timer) timer->begin(E2S_KERNEL_SCAN, stream);
+            k_code_scan<<<unsigned(grid), PS_THREADS, smem, stream>>>(sp);
+            if (timer) timer->end(stream);
+            CK(cudaGetLastError());
+            ++*launches;
+        }
+        // survivors of the prefilter, in order
+        k_flag_count<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum);
+        CK(cudaGetLastError());
+        k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum, w->survivors, cap_surv,
+                                                          &w->dev->n_survivors);
+        CK(cudaGetLastError());
+        *launches += 2;
+        {   // K3x: exact filters on the survivors
+            ExactParams ep;
+            ep.a = a;
+            ep.list = w->survivors;
+            ep.n_list = &w->dev->n_survivors;
+            ep.cap_list = cap_surv;
+            ep.mcov = uint32_t(p.mcov_out);
+            ep.k_right = uint32_t(p.k_right);
+            ep.nr1_lo = nr1_lo;
+            ep.nr1_big = nr1_big;
+            ep.flag_words = w->flag_words2;
+            ep.dev = w->dev;
+            if (timer) timer->begin(E2S_KERNEL_EXACT, stream);
+            k_cluster_exact<<<unsigned(sm_count) * 8, EX_THREADS, 0, stream>>>(ep);
+            if (timer) timer->end(stream);
+            CK(cudaGetLastError());
+            ++*launches;
+        }
+        k_flag_count<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->block_sum);
+        CK(cudaGetLastError());
+        k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->block_sum, w->flagged, cap_flag,
+                                                          &w->dev->n_flagged);
+        CK(cudaGetLastError());
+        *launches += 2;
+        {
+            CandParams cp;
+            cp.a = a;
+            cp.flagged = w->flagged;
+            cp.n_flagged = &w->dev->n_flagged;
+            cp.cap_flagged = cap_flag;
+            cp.mcov = uint32_t(p.mcov_out);
+            cp.k_left = uint32_t(p.k_left);
+            cp.k_right = uint32_t(p.k_right);
+            cp.cap = cap;
+            cp.nr1_lo = nr1_lo;
+            cp.nr1_big = nr1_big;
+            cp.slots = w->slots;
+            cp.slot_text = w->slot_text;
+            cp.slot_pos = w->slot_pos;
+            cp.valid_words = w->valid_words;
+            uint64_t blocks = (cap_flag + 3) / 4;
+            if (blocks > uint64_t(sm_count) * 16) blocks = uint64_t(sm_count) * 16;
+            k_candidates<<<unsigned(blocks), 128, 0, stream>>>(cp);
+            CK(cudaGetLastError());
+            k_compact_slots<<<1, 1024, 0, stream>>>(w->valid_words, n_vwords, w->cand, w->dev);
+            CK(cudaGetLastError());
+            EventParams ep;
+            ep.slots = w->slots;
+            ep.slot_text = w->slot_text;
+            ep.slot_pos = w->slot_pos;
+            ep.cand = w->cand;
+            ep.n_cand = &w->dev->n_slots_valid;
+            ep.cap = cap;
+            ep.k_left = p.k_left;
+            ep.k_right = p.k_right;
+            ep.max_gap = p.max_gap;
+            ep.max_err = p.max_err;
+            ep.max_snvs = p.max_snvs;
+            ep.bases = d_read_bases;
+            ep.off = d_read_off;
+            ep.n_reads = n_reads;
+            ep.out = w->d_events;
+            ep.stride = w->stride;
+            ep.dev = w->dev;
+            uint64_t eblocks = (n_slots + EV_WARPS - 1) / EV_WARPS;
+            if (eblocks > uint64_t(sm_count) * 16) eblocks = uint64_t(sm_count) * 16;
+            k_events<<<unsigned(eblocks), EV_WARPS * 32, 0, stream>>>(ep);
+            CK(cudaGetLastError());
+            *launches += 3;
+        }
+        CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));  // the only synchronisation of the pass
+        if (hd.n_survivors <= cap_surv && hd.n_flagged <= cap_flag) break;
+        if (attempt >= 2) { *err = "phase 2 capacity did not converge"; return cudaErrorUnknown; }
+        if (hd.n_survivors > cap_surv) w->want_survivors = hd.n_survivors + hd.n_survivors / 8 + 1024;
+        // flagged clusters are a subset of the survivors; when the survivor list overflowed the flagged count is a lower bound
+        if (hd.n_flagged > cap_flag || hd.n_survivors > cap_surv) {
+            uint64_t guess = hd.n_flagged + hd.n_flagged / 8 + 1024;
+            if (hd.n_survivors > cap_surv) guess = guess * (hd.n_survivors / cap_surv + 1);
+            if (guess > w->want_flagged) w->want_flagged = guess;
+        }
     }
+    counts->n_analysed = hd.n_analysed;
+    counts->n_flagged = hd.n_flagged;
+    counts->n_candidates = hd.n_slots_valid;
+    counts->n_variants = hd.n_variants;
+    counts->n_events = hd.n_events;
+    counts->saw_n = hd.saw_n;
+    if (hd.bad_ref) { *err = "a candidate references a read/offset outside the staged reads"; return cudaErrorInvalidValue; }
+    w->n_cand = hd.n_slots_valid;
     return cudaSuccess;
 }
 

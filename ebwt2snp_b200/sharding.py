@@ -63,8 +63,8 @@ def exchange_summaries(summary: api.ClusterSummary, device, group=None):
 
 def merge_clusters(summary: api.ClusterSummary, device, group=None):
     """-> (merged view of this rank, list of all summaries); ref:ebwt2clust.cpp:90-135 across shards"""
-    rank, _ = _world(group)
-    sums = exchange_summaries(summary, device, group)
+    rank, world = _world(group)
+    sums = [summary] if world == 1 else exchange_summaries(summary, device, group)
     return api.cluster_merge(sums, rank), sums
 
 
@@ -72,6 +72,9 @@ def merge_statistics(st: api.Stats, mcov_out, pval, device, group=None) -> api.S
     """step 3: global statistics() = sum of the shards' histograms; the reference's double count of the
     last record (ref:clust2snp.cpp:889) uses the LAST record of the global file, i.e. of the last
     shard that has any record.  Runs the pval loop (one IEEE double division per step, on the host)."""
+    if _world(group)[1] == 1:
+        api.statistics_finish(st, st.last_len, mcov_out, pval)
+        return st
     words = list(st.hist) + [st.n_clust, st.n_bases, st.last_len]
     gathered = all_gather_words(words, device, group)
     tot = api.Stats()
@@ -90,7 +93,9 @@ def merge_statistics(st: api.Stats, mcov_out, pval, device, group=None) -> api.S
 
 def event_id_offset(n_events, device, group=None):
     """step 4: -> (first id_nr of this rank's kept events, total kept events); ids start at 1 (ref:clust2snp.cpp:637)"""
-    rank, _ = _world(group)
+    rank, world = _world(group)
+    if world == 1:
+        return 1, int(n_events)
     counts = [g[0] for g in all_gather_words([int(n_events)], device, group)]
     return 1 + sum(counts[:rank]), sum(counts)
 

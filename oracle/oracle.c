@@ -77,6 +77,15 @@ static int append_entry(uint64_t *start_out, uint16_t *len_out, uint64_t cap, ui
 /* ref:ebwt2clust.cpp:68-139 */
 int oracle_cluster_lm(const uint32_t *lcp, const uint8_t *bwt, uint64_t n, uint32_t k, int min_len,
                       uint64_t *start_out, uint16_t *len_out, uint64_t cap, oracle_cluster_result *res) {
+    return oracle_cluster_lm_x(lcp, bwt, n, k, min_len, 4, start_out, len_out, cap, res);
+}
+
+/* Same with the LCP field width of the input file (-x): the failed post-EOF read only touches a temporary of
+ * that width (ref:include.hpp:126-155), so the phantom value is the 4-byte rule truncated to lcp_bytes
+ * (measured against oracle/_ref for -x 1, 2, 4, 8: tests/test_oracle_golden.py). */
+int oracle_cluster_lm_x(const uint32_t *lcp, const uint8_t *bwt, uint64_t n, uint32_t k, int min_len, int lcp_bytes,
+                        uint64_t *start_out, uint16_t *len_out, uint64_t cap, oracle_cluster_result *res) {
+    const uint32_t pmask = lcp_bytes == 1 ? 0xFFu : (lcp_bytes == 2 ? 0xFFFFu : 0xFFFFFFFFu);
     uint64_t m = 0;
     uint32_t n_clust_out = 0;
     res->n_written = 0;
@@ -100,7 +109,7 @@ int oracle_cluster_lm(const uint32_t *lcp, const uint8_t *bwt, uint64_t n, uint3
             /* phantom record: stack residue.  If the PREVIOUS iteration closed a cluster (i.e. a
              * cluster ended at index n-2), append_entry's spilled `start` shares the stack slot of
              * the inlined read_el's 4-byte buffer, so the failed read leaves (u32)start there. */
-            e3 = closed_prev ? (uint32_t)closed_prev_start : oracle_phantom_field(lcp, bwt, n);
+            e3 = (closed_prev ? (uint32_t)closed_prev_start : oracle_phantom_field(lcp, bwt, n)) & pmask;
             res->phantom_lcp = e3;
             eof = 1;
         }

@@ -72,6 +72,9 @@ void oracle_default_params(oracle_params *p);
 int oracle_cluster_lm(const uint32_t *lcp, const uint8_t *bwt, uint64_t n, uint32_t k, int min_len,
                       uint64_t *start_out, uint16_t *len_out, uint64_t cap, oracle_cluster_result *res);
 
+int oracle_cluster_lm_x(const uint32_t *lcp, const uint8_t *bwt, uint64_t n, uint32_t k, int min_len, int lcp_bytes,
+                        uint64_t *start_out, uint16_t *len_out, uint64_t cap, oracle_cluster_result *res);
+
 /* the phantom record consumed after EOF, exposed for tests */
 uint32_t oracle_phantom_field(const uint32_t *lcp, const uint8_t *bwt, uint64_t n);
 

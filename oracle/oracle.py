@@ -73,7 +73,7 @@ def default_params(nr_reads1=0, **kw) -> Params:
     return p
 
 
-def cluster_lm(lcp, bwt, k=16, min_len=2):
+def cluster_lm(lcp, bwt, k=16, min_len=2, x=4):
     """-> (start u64[], len u16[], n_clust_out, phantom_lcp); ref:ebwt2clust.cpp:68-139."""
     lcp = np.ascontiguousarray(lcp, dtype=np.uint32)
     bwt = np.ascontiguousarray(bwt, dtype=np.uint8)
@@ -81,8 +81,8 @@ def cluster_lm(lcp, bwt, k=16, min_len=2):
     start = np.empty(n + 1, dtype=np.uint64)
     ln = np.empty(n + 1, dtype=np.uint16)
     res = ClusterResult()
-    rc = lib().oracle_cluster_lm(_p(lcp, C.c_uint32), _p(bwt, C.c_uint8), C.c_uint64(n), C.c_uint32(k), C.c_int(min_len),
-                                 _p(start, C.c_uint64), _p(ln, C.c_uint16), C.c_uint64(n + 1), C.byref(res))
+    rc = lib().oracle_cluster_lm_x(_p(lcp, C.c_uint32), _p(bwt, C.c_uint8), C.c_uint64(n), C.c_uint32(k), C.c_int(min_len),
+                                   C.c_int(x), _p(start, C.c_uint64), _p(ln, C.c_uint16), C.c_uint64(n + 1), C.byref(res))
     if rc:
         raise ValueError("oracle_cluster_lm: input outside the reference's domain")
     m = res.n_written

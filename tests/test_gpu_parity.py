@@ -37,7 +37,7 @@ def test_cluster_fuzz(ctx, variant, monkeypatch):
     sizes = [2, 3, 4, 5, 17, 255, 256, 257, 4095, 4096, 4097, 8191, 8192, 8193, 12289, 40000, 70001, 300000]
     for it, n in enumerate(sizes * 2):
         k = int(rng.choice([1, 2, 3, 5, 16, 70]))
-        m = int(rng.choice([1, 2, 3, 8]))
+        m = int(rng.choice([1, 2, 3, 8, 33, 34, 200, -3]))  # <= 33: bit-parallel kept count, else the dense count path
         lcp = H.random_lcp(rng, n, k, it % 5)
         bwt = rng.choice(H.BWT_ALPHABET, size=n)
         es, el, enc, _ = O.cluster_lm(lcp, bwt, k, m)
@@ -57,6 +57,15 @@ def test_cluster_long_wrap(ctx):
     s, l, nc = run_cluster(ctx, lcp, bwt, 16, 2)
     assert nc == enc and np.array_equal(s, es) and np.array_equal(l, el)
     assert 70000 - 65536 in set(el.tolist())
+    # lengths 65536 (wraps to 0), 65537 (wraps to 1) and 65538 against every kind of min_len
+    for run in (65535, 65536, 65537, 65538, 131072, 131073):
+        for m in (-1, 1, 2, 3, 40):
+            lcp = np.zeros(n, dtype=np.uint32)
+            lcp[777:777 + run] = 40
+            lcp[190000:190003] = 17
+            es, el, enc, _ = O.cluster_lm(lcp, bwt, 16, m)
+            s, l, nc = run_cluster(ctx, lcp, bwt, 16, m)
+            assert nc == enc and np.array_equal(s, es) and np.array_equal(l, el), (run, m)
 
 
 def test_cluster_sharded(ctx):
@@ -65,7 +74,7 @@ def test_cluster_sharded(ctx):
     for it in range(24):
         n = int(rng.integers(30, 30000))
         k = int(rng.choice([2, 5, 16]))
-        m = int(rng.choice([1, 2, 3]))
+        m = int(rng.choice([1, 2, 3, 40]))
         lcp = H.random_lcp(rng, n, k, it % 5)
         bwt = rng.choice(H.BWT_ALPHABET, size=n)
         es, el, enc, _ = O.cluster_lm(lcp, bwt, k, m)
