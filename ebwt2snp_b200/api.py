@@ -33,7 +33,7 @@ class E2SError(RuntimeError):
 class ClusterSummary(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_local", "global_off", "n_global", "n_end", "n_written", "head_end", "any_event", "open_start",
-        "end_nm2_start", "tail_lcp_nm2", "tail_lcp_nm1", "tail_bwt_nm1", "k", "min_len")]
+        "end_nm2_start", "tail_lcp_nm2", "tail_lcp_nm1", "tail_bwt_nm1", "k", "min_len", "lcp_bytes")]
 
 
 SUMMARY_WORDS = C.sizeof(ClusterSummary) // 8
@@ -80,7 +80,7 @@ class PipelineResult(C.Structure):
 SYMBOLS = [
     "e2s_version", "e2s_ctx_create", "e2s_ctx_destroy", "e2s_last_error", "e2s_ctx_set_stream",
     "e2s_ctx_synchronize", "e2s_ctx_launch_count", "e2s_ctx_timing", "e2s_ctx_kernel_time", "e2s_shard_create", "e2s_shard_destroy", "e2s_shard_load_gesa",
-    "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_shard_seal", "e2s_reads_stage", "e2s_reads_stage_dev",
+    "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_shard_set_layout", "e2s_shard_seal", "e2s_reads_stage", "e2s_reads_stage_dev",
     "e2s_cluster_run", "e2s_cluster_merge", "e2s_cluster_finalize", "e2s_cluster_lm", "e2s_cluster_count",
     "e2s_cluster_fetch", "e2s_cluster_fetch_packed", "e2s_clusters_stage_packed", "e2s_clusters_stage",
     "e2s_statistics", "e2s_statistics_finish", "e2s_snp_default_params", "e2s_find_events", "e2s_events_fetch",
@@ -119,6 +119,7 @@ def load_library():
     lib.e2s_shard_load_soa.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64]
     lib.e2s_shard_load_soa_dev.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64]
     lib.e2s_shard_seal.argtypes = [C.c_void_p]
+    lib.e2s_shard_set_layout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.e2s_reads_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     lib.e2s_reads_stage_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
     lib.e2s_cluster_run.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(ClusterSummary)]
@@ -309,6 +310,10 @@ class Shard:
             self.ctx._ck(self.lib.e2s_shard_load_soa(self.h, *[_ptr(a) for a in arrs], int(first), count))
         self.ctx.synchronize()
 
+    def set_layout(self, x=4, y=4, z=4, bcr=False):
+        """byte widths / format of the index files the arrays came from (the reference's phantom record depends on it)"""
+        self.ctx._ck(self.lib.e2s_shard_set_layout(self.h, x, y, z, int(bcr)))
+
     def seal(self):
         self.ctx._ck(self.lib.e2s_shard_seal(self.h))
 
@@ -367,7 +372,11 @@ class Shard:
 
     def find_events(self, params: SnpParams, max_clust_length) -> SnpCounts:
         cnt = SnpCounts()
-        self.ctx._ck(self.lib.e2s_find_events(self.h, C.byref(params), int(max_clust_length), C.byref(cnt)))
+        try:
+            self.ctx._ck(self.lib.e2s_find_events(self.h, C.byref(params), int(max_clust_length), C.byref(cnt)))
+        except E2SError as e:
+            e.counts = cnt  # the counters up to the failure (e.g. candidates found before a read lookup failed)
+            raise
         return cnt
 
     def events(self):

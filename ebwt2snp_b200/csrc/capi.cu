@@ -44,6 +44,7 @@ struct e2s_shard {
     uint32_t *lcp = nullptr, *text = nullptr, *suff = nullptr;  // local position 0
     uint8_t* bwt = nullptr;
     bool sealed = false;
+    int lay_x = 4, lay_y = 4, lay_z = 4, lay_bcr = 0;  // layout of the index files (phantom record only)
     // record list
     uint64_t* d_start = nullptr;
     uint16_t* d_len = nullptr;
@@ -269,6 +270,7 @@ int e2s_shard_load_gesa(e2s_shard* s, const void* records, uint64_t first, uint6
     keep_range(s, &lo, &hi);
     uint64_t a = first > lo ? first : lo, b = first + count < hi ? first + count : hi;
     if (a >= b) return E2S_OK;
+    s->lay_x = x; s->lay_y = y; s->lay_z = z; s->lay_bcr = 0;
     const int rs = x + y + z + 1;
     const uint64_t chunk = uint64_t(1) << 24;  // records per H2D chunk (multiple of 16)
     const size_t need = size_t(chunk < (b - a) ? chunk : round_up(b - a, 16)) * rs + 64;
@@ -320,12 +322,22 @@ int e2s_shard_load_soa_dev(e2s_shard* s, const uint32_t* lcp, const uint32_t* te
     return load_soa(s, lcp, text, suff, bwt, first, count, cudaMemcpyDeviceToDevice);
 }
 
+int e2s_shard_set_layout(e2s_shard* s, int x, int y, int z, int bcr) {
+    if (!s) return fail(nullptr, E2S_ERR_ARG, "shard == NULL");
+    auto ok = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8; };
+    if (!ok(x) || !ok(y) || !ok(z)) return fail(s->ctx, E2S_ERR_ARG, "field byte sizes must be 1, 2, 4 or 8");
+    s->lay_x = x; s->lay_y = y; s->lay_z = z; s->lay_bcr = bcr ? 1 : 0;
+    s->sealed = false;
+    return E2S_OK;
+}
+
 int e2s_shard_seal(e2s_shard* s) {
     if (!s) return fail(nullptr, E2S_ERR_ARG, "shard == NULL");
     e2s_ctx* c = s->ctx;
     CU(c, cudaSetDevice(c->device));
     if (s->global_off + s->n_local == s->n_global) {
-        CU(c, launch_fill_phantom(s->lcp, s->text, s->suff, s->bwt, s->n_local, HALO_R, c->stream));
+        CU(c, launch_fill_phantom(s->lcp, s->text, s->suff, s->bwt, s->n_local, HALO_R, s->lay_x, s->lay_y, s->lay_z,
+                                  s->lay_bcr, c->stream));
         ++c->launches;
     }
     s->sealed = true;
@@ -473,6 +485,7 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
     sum->end_nm2_start = h.end_nm2_start;
     sum->k = k;
     sum->min_len = uint64_t(int64_t(min_len));
+    sum->lcp_bytes = uint64_t(s->lay_x);
     sum->tail_lcp_nm2 = h.tail_lcp_nm2;
     sum->tail_lcp_nm1 = h.tail_lcp_nm1;
     sum->tail_bwt_nm1 = h.tail_bwt_nm1;
@@ -549,6 +562,9 @@ int e2s_cluster_merge(const e2s_cluster_summary* all, int n_shards, int my, e2s_
     if (L.end_nm2_start == ~0ull) P = uint32_t(last_head_start);
     else if (L.end_nm2_start) P = uint32_t(L.end_nm2_start - 1);
     else P = (e2 & 0xFFFFFF00u) | uint32_t(L.tail_bwt_nm1 & 0xff);
+    // the failed read only touches a temporary of the LCP field's width (ref:include.hpp:126-155)
+    if (L.lcp_bytes == 1) P &= 0xFFu;
+    else if (L.lcp_bytes == 2) P &= 0xFFFFu;
     out->phantom_lcp = P;
     uint32_t na = 0;
     auto tail_record = [&](uint64_t st, uint64_t en) {

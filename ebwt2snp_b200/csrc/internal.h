@@ -87,7 +87,7 @@ cudaError_t launch_pack_records(const uint64_t* d_start, const uint16_t* d_len, 
 cudaError_t launch_unpack_gesa(const uint8_t* d_rec, uint64_t count, int x, int y, int z, uint32_t* lcp, uint32_t* text,
                                uint32_t* suff, uint8_t* bwt, cudaStream_t stream);
 cudaError_t launch_fill_phantom(uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt, uint64_t n_local,
-                                uint64_t count, cudaStream_t stream);
+                                uint64_t count, int x, int y, int z, int bcr, cudaStream_t stream);
 
 // ---- phase 2 -----------------------------------------------------------------------------------
 struct SnpDev {  // device counters of one e2s_find_events

@@ -58,23 +58,38 @@ cudaError_t launch_unpack_gesa(const uint8_t* d_rec, uint64_t count, int x, int 
     return cudaGetLastError();
 }
 
-// The record "read" after EOF: every 4-byte field holds
-// (lcp[n-1] & 0xFFFFFF00) | bwt[n-1], the byte field holds bwt[n-1].
+// The record "read" after EOF.  read_el's temporaries share one 8-byte stack slot and a
+// failed read leaves it as the last valid record left it: byte 0 = bwt[n-1] (read last); byte b >= 1 = byte b of
+// the last-read field wider than b: lcp, then suff, then text for the EGSA record order (text suff lcp), lcp, then
+// text, then suff for the BCR order (suff text lcp).  The phantom field of width w is the low w bytes of the slot
+// (measured against the reference for ten width combinations in both formats: tests/golden, phantom_tail cases).
 __global__ void k_fill_phantom(uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt, uint64_t n_local,
-                               uint64_t count) {
-    const uint8_t b = bwt[n_local - 1];
-    const uint32_t ph = (lcp[n_local - 1] & 0xFFFFFF00u) | b;
+                               uint64_t count, int x, int y, int z, int bcr) {
+    const uint8_t b0 = bwt[n_local - 1];
+    const uint32_t l = lcp[n_local - 1], t = text[n_local - 1], sf = suff[n_local - 1];
+    uint32_t slot = b0;  // bytes 4..7 never reach a 32-bit field
+    for (int b = 1; b < 4; ++b) {
+        uint32_t v = 0;
+        if (b < x) v = l;
+        else if (!bcr && b < z) v = sf;
+        else if (b < y) v = t;
+        else if (bcr && b < z) v = sf;
+        slot |= v & (0xffu << (8 * b));
+    }
+    const uint32_t px = x >= 4 ? slot : slot & ((1u << (8 * x)) - 1u);
+    const uint32_t py = y >= 4 ? slot : slot & ((1u << (8 * y)) - 1u);
+    const uint32_t pz = z >= 4 ? slot : slot & ((1u << (8 * z)) - 1u);
     for (uint64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += uint64_t(gridDim.x) * blockDim.x) {
-        lcp[n_local + i] = ph;
-        text[n_local + i] = ph;
-        suff[n_local + i] = ph;
-        bwt[n_local + i] = b;
+        lcp[n_local + i] = px;
+        text[n_local + i] = py;
+        suff[n_local + i] = pz;
+        bwt[n_local + i] = b0;
     }
 }
 
 cudaError_t launch_fill_phantom(uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt, uint64_t n_local,
-                                uint64_t count, cudaStream_t stream) {
-    k_fill_phantom<<<1, 256, 0, stream>>>(lcp, text, suff, bwt, n_local, count);
+                                uint64_t count, int x, int y, int z, int bcr, cudaStream_t stream) {
+    k_fill_phantom<<<1, 256, 0, stream>>>(lcp, text, suff, bwt, n_local, count, x, y, z, bcr);
     return cudaGetLastError();
 }
 

@@ -138,6 +138,7 @@ int main(int argc, char** argv) {
         r = e2s_shard_create(ctx[size_t(g)], hi - lo, lo, idx.n, &sh[size_t(g)]);
         const uint64_t a = lo >= 2 ? lo - 2 : 0, b = hi + E2S_MAX_C_LEN + 1 < idx.n ? hi + E2S_MAX_C_LEN + 1 : idx.n;
         if (!r) r = idx.load(sh[size_t(g)], a, b - a);
+        if (!r) r = e2s_shard_set_layout(sh[size_t(g)], idx.x, idx.y, idx.z, idx.bcr ? 1 : 0);
         if (!r) r = e2s_shard_seal(sh[size_t(g)]);
         if (!r) r = e2s_clusters_stage_packed(sh[size_t(g)], cl.data + rcut[size_t(g)] * 10, rcut[size_t(g) + 1] - rcut[size_t(g)]);
         if (!r) r = e2s_statistics(sh[size_t(g)], &stats[size_t(g)]);

@@ -81,6 +81,7 @@ int main(int argc, char** argv) {
         r = e2s_shard_create(ctx[size_t(g)], hi - lo, lo, idx.n, &sh[size_t(g)]);
         const uint64_t a = lo >= 2 ? lo - 2 : 0, b = hi + E2S_MAX_C_LEN + 1 < idx.n ? hi + E2S_MAX_C_LEN + 1 : idx.n;
         if (!r) r = idx.load(sh[size_t(g)], a, b - a);
+        if (!r) r = e2s_shard_set_layout(sh[size_t(g)], idx.x, idx.y, idx.z, idx.bcr ? 1 : 0);
         if (!r) r = e2s_shard_seal(sh[size_t(g)]);
         if (!r) r = e2s_cluster_run(sh[size_t(g)], uint32_t(k), min_len, &sums[size_t(g)]);
         if (r) { rc[size_t(g)] = r; errs[size_t(g)] = e2s_last_error(ctx[size_t(g)]); }

@@ -92,6 +92,11 @@ int e2s_shard_load_soa(e2s_shard *sh, const uint32_t *lcp, const uint32_t *text,
 /* Same, from DEVICE pointers on the context's device (device-to-device copies). */
 int e2s_shard_load_soa_dev(e2s_shard *sh, const uint32_t *d_lcp, const uint32_t *d_text, const uint32_t *d_suff,
                            const uint8_t *d_bwt, uint64_t first, uint64_t count);
+/* Layout of the index files the shard was loaded from: byte widths of lcp (x), text (y), suff (z) and whether it
+ * was the BCR triple.  Only the reference's post-EOF phantom record depends on it.
+ * e2s_shard_load_gesa sets (x, y, z, 0) itself; SoA loads default to (4, 4, 4, 0).  Call before e2s_shard_seal. */
+int e2s_shard_set_layout(e2s_shard *sh, int x, int y, int z, int bcr);
+
 /* Call once after the last load: on the last shard fills the records past n_global with the
  * reference's post-EOF phantom record (ref:clust2snp.cpp:827-833). */
 int e2s_shard_seal(e2s_shard *sh);
@@ -117,6 +122,7 @@ typedef struct {
                                 ~0 = that cluster is this shard's head (START unknown locally) */
     uint64_t tail_lcp_nm2, tail_lcp_nm1, tail_bwt_nm1; /* last shard: lcp[n-2], lcp[n-1], bwt[n-1] */
     uint64_t k, min_len;
+    uint64_t lcp_bytes;      /* -x of the index files: the post-EOF phantom LCP is truncated to this width */
 } e2s_cluster_summary;
 
 /* Result of merging all shard summaries, from the point of view of shard `my`. */

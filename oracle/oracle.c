@@ -356,12 +356,47 @@ static int emit_event(sbuf *o, uint64_t id_nr, const char *l0, const char *l1, i
     return 0;
 }
 
-/* ref:clust2snp.cpp:788-872 (find_events), :505-628 (extract_variants), :633-780 (to_file) */
+/* The record "read" after EOF, for any field widths.  read_el's four temporaries
+ * (ref:include.hpp:126-155 / :159-188) share one 8-byte stack slot; a failed read leaves it untouched, so the
+ * phantom field of width w is the low w bytes of what the LAST VALID record left there: byte 0 = bwt[n-1]
+ * (read last), byte b >= 1 = byte b of the last-read field that is wider than b -- lcp, then (EGSA order
+ * text, suff, lcp) suff, then text; in BCR order (suff, text, lcp) text before suff.  Measured against
+ * oracle/_ref by bisection on -n for ten width combinations in both file formats (tests/golden/make_golden.py,
+ * phantom_tail cases). */
+uint64_t oracle_phantom_slot(uint32_t lcp_last, uint32_t text_last, uint32_t suff_last, uint8_t bwt_last,
+                             int x, int y, int z, int bcr) {
+    uint64_t slot = bwt_last;
+    for (int b = 1; b < 8; ++b) {
+        uint64_t v = 0; /* 8-byte fields: bytes 4..7 of the file value are not kept by this restatement (always 0 here) */
+        if (b < x) v = b < 4 ? (lcp_last >> (8 * b)) & 0xff : 0;
+        else if (!bcr && b < z) v = b < 4 ? (suff_last >> (8 * b)) & 0xff : 0;
+        else if (b < y) v = b < 4 ? (text_last >> (8 * b)) & 0xff : 0;
+        else if (bcr && b < z) v = b < 4 ? (suff_last >> (8 * b)) & 0xff : 0;
+        slot |= v << (8 * b);
+    }
+    return slot;
+}
+static uint32_t slot_field(uint64_t slot, int w) {
+    return (uint32_t)(w >= 4 ? slot : slot & ((1ull << (8 * w)) - 1));
+}
+
 int oracle_find_events(const uint32_t *lcp, const uint32_t *text, const uint32_t *suff, const uint8_t *bwt,
                        uint64_t n, const uint64_t *start, const uint16_t *len, uint64_t m,
                        const oracle_params *p, int max_clust_length,
                        const uint8_t *read_bases, const uint64_t *read_off, uint64_t n_reads,
                        char **snp_text, size_t *snp_len, oracle_snp_result *res) {
+    return oracle_find_events_w(lcp, text, suff, bwt, n, start, len, m, p, max_clust_length, read_bases, read_off, n_reads,
+                                4, 4, 4, 0, snp_text, snp_len, res);
+}
+
+/* ref:clust2snp.cpp:788-872 (find_events), :505-628 (extract_variants), :633-780 (to_file); x, y, z = byte widths of
+ * lcp / text / suff in the index files, bcr = 1 for the BCR triple (they only matter for the phantom record) */
+int oracle_find_events_w(const uint32_t *lcp, const uint32_t *text, const uint32_t *suff, const uint8_t *bwt,
+                         uint64_t n, const uint64_t *start, const uint16_t *len, uint64_t m,
+                         const oracle_params *p, int max_clust_length,
+                         const uint8_t *read_bases, const uint64_t *read_off, uint64_t n_reads,
+                         int x, int y, int z, int bcr,
+                         char **snp_text, size_t *snp_len, oracle_snp_result *res) {
     memset(res, 0, sizeof *res);
     *snp_text = NULL;
     *snp_len = 0;
@@ -369,7 +404,7 @@ int oracle_find_events(const uint32_t *lcp, const uint32_t *text, const uint32_t
     cand_vec cands = {0, 0, 0};
     t_gsa *cl = (t_gsa *)malloc(65536 * sizeof *cl);
     if (!cl) return -1;
-    const uint32_t ph = oracle_phantom_field(lcp, bwt, n);
+    const uint64_t slot = oracle_phantom_slot(lcp[n - 1], text[n - 1], suff[n - 1], bwt[n - 1], x, y, z, bcr);
     int rc = 0;
 
     /* forward-only cursor over the EGSA; `e` is always record i (the phantom one for i >= n) */
@@ -383,7 +418,12 @@ int oracle_find_events(const uint32_t *lcp, const uint32_t *text, const uint32_t
             while (i < st + length) {                /* :827-833 */
                 t_gsa e;
                 if (i < n) { e.text = text[i]; e.suff = suff[i]; e.lcp = lcp[i]; e.bwt = bwt[i]; }
-                else { e.text = e.suff = e.lcp = ph; e.bwt = bwt[n - 1]; }
+                else {
+                    e.text = slot_field(slot, y);
+                    e.suff = slot_field(slot, z);
+                    e.lcp = slot_field(slot, x);
+                    e.bwt = bwt[n - 1];
+                }
                 cl[cnt++] = e;
                 ++i;
             }

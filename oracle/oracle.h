@@ -8,7 +8,7 @@
  *
  * Parity status: PINNED.  The restatement is validated byte-for-byte against the reference
  * itself, compiled unmodified from /root/reference into oracle/_ref/ by oracle/Makefile
- * (tests/test_oracle_vs_ref.py fuzzes both phases; tests/golden/ holds outputs of oracle/_ref
+ * (tests/test_oracle_golden.py fuzzes it live where oracle/_ref exists; tests/golden/ holds outputs of oracle/_ref
  * committed together with the script that produced them, tests/golden/make_golden.py).
  * The reference tree ships no golden vectors of its own except the two distance() examples
  * in ref:clust2snp.cpp:250-251, which tests/test_oracle_golden.py checks.
@@ -90,6 +90,16 @@ int oracle_find_events(const uint32_t *lcp, const uint32_t *text, const uint32_t
                        const oracle_params *p, int max_clust_length,
                        const uint8_t *read_bases, const uint64_t *read_off, uint64_t n_reads,
                        char **snp_text, size_t *snp_len, oracle_snp_result *res);
+
+/* same for index files with other field widths / the BCR triple (only the phantom record depends on them) */
+int oracle_find_events_w(const uint32_t *lcp, const uint32_t *text, const uint32_t *suff, const uint8_t *bwt,
+                         uint64_t n, const uint64_t *start, const uint16_t *len, uint64_t m,
+                         const oracle_params *p, int max_clust_length,
+                         const uint8_t *read_bases, const uint64_t *read_off, uint64_t n_reads,
+                         int x, int y, int z, int bcr,
+                         char **snp_text, size_t *snp_len, oracle_snp_result *res);
+uint64_t oracle_phantom_slot(uint32_t lcp_last, uint32_t text_last, uint32_t suff_last, uint8_t bwt_last,
+                             int x, int y, int z, int bcr);
 
 /* distance(), ref:clust2snp.cpp:254-302 (equal-length strings) */
 void oracle_distance(const char *a, const char *b, int len, int max_gap, int *D, int *gap);

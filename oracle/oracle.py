@@ -100,8 +100,9 @@ def statistics(start, ln, mcov_out=5, pval=0.99) -> Stats:
     return st
 
 
-def find_events(lcp, text, suff, bwt, start, ln, params: Params, max_clust_length, read_bases, read_off):
-    """-> (snp_bytes, SnpResult); ref:clust2snp.cpp:788-872."""
+def find_events(lcp, text, suff, bwt, start, ln, params: Params, max_clust_length, read_bases, read_off,
+                x=4, y=4, z=4, bcr=False, strict=True):
+    """-> (snp_bytes, SnpResult); ref:clust2snp.cpp:788-872.  x/y/z/bcr: layout of the index files (phantom record only)."""
     lcp = np.ascontiguousarray(lcp, dtype=np.uint32)
     text = np.ascontiguousarray(text, dtype=np.uint32)
     suff = np.ascontiguousarray(suff, dtype=np.uint32)
@@ -113,12 +114,15 @@ def find_events(lcp, text, suff, bwt, start, ln, params: Params, max_clust_lengt
     out = C.c_char_p()
     out_len = C.c_size_t()
     res = SnpResult()
-    rc = lib().oracle_find_events(_p(lcp, C.c_uint32), _p(text, C.c_uint32), _p(suff, C.c_uint32), _p(bwt, C.c_uint8),
-                                  C.c_uint64(len(lcp)), _p(start, C.c_uint64), _p(ln, C.c_uint16), C.c_uint64(len(ln)),
-                                  C.byref(params), C.c_int(max_clust_length), _p(read_bases, C.c_uint8),
-                                  _p(read_off, C.c_uint64), C.c_uint64(len(read_off) - 1),
-                                  C.byref(out), C.byref(out_len), C.byref(res))
+    rc = lib().oracle_find_events_w(_p(lcp, C.c_uint32), _p(text, C.c_uint32), _p(suff, C.c_uint32), _p(bwt, C.c_uint8),
+                                    C.c_uint64(len(lcp)), _p(start, C.c_uint64), _p(ln, C.c_uint16), C.c_uint64(len(ln)),
+                                    C.byref(params), C.c_int(max_clust_length), _p(read_bases, C.c_uint8),
+                                    _p(read_off, C.c_uint64), C.c_uint64(len(read_off) - 1),
+                                    C.c_int(x), C.c_int(y), C.c_int(z), C.c_int(int(bcr)),
+                                    C.byref(out), C.byref(out_len), C.byref(res))
     if rc:
+        if not strict:  # the candidate count is printed by the reference before it crashes (ref:clust2snp.cpp:859)
+            return None, res
         raise ValueError(f"oracle_find_events: input the reference would crash on (flags={res.flags})")
     data = C.string_at(out, out_len.value)
     lib().oracle_free(out)

@@ -27,6 +27,8 @@ MICRO = {
     "micro_a": dict(gen=dict(G=6000, reads_per_sample=1200, L=100, n_snps=12, n_indels=3, rc=True, seed=11), k=16, m=2),
     "micro_b": dict(gen=dict(G=4000, reads_per_sample=1500, L=64, n_snps=10, n_indels=2, rc=False, seed=12), k=12, m=3),
 }
+# index layouts beyond the 4/4/4 .gesa of the main fixtures: (x, y, z, bcr)
+LAYOUTS = [(1, 4, 1, False), (2, 4, 2, False), (4, 4, 4, True), (1, 4, 1, True), (8, 8, 8, False)]
 SNP_VARIANTS = [
     [], ["-m", "3"], ["-c", "3", "-g", "4"], ["-L", "25", "-R", "20", "-e", "1"], ["-p", "0.5"], ["-v", "0"],
 ]
@@ -77,6 +79,44 @@ def phase1_fuzz(d):
                         out=np.concatenate(outs), meta=np.array(meta, dtype=np.int64))
 
 
+def phase1_fuzz_widths(d):
+    """ebwt2clust with -x 1 / 2 / 8 (and narrow y, z): the post-EOF phantom LCP is truncated to the field width."""
+    rng = np.random.default_rng(4048)
+    fa = os.path.join(d, "W.fasta")
+    open(fa, "w").write(">a\nA\n")
+    alphabet = np.frombuffer(b"ACGT$acgt\x00\xff", dtype=np.uint8)
+    lcps, bwts, meta, outs = [], [], [], []
+    combos = [(1, 4, 1), (1, 4, 4), (2, 4, 4), (8, 4, 4), (1, 1, 1), (2, 2, 2), (8, 8, 8), (4, 4, 1)]
+    for it in range(96):
+        x, y, z = combos[it % len(combos)]
+        n = int(rng.integers(3, 60)) if it % 3 == 0 else int(rng.integers(60, 1200))
+        k = int(rng.choice([1, 2, 3, 5, 16, 70]))
+        m = int(rng.choice([1, 2, 3, 8]))
+        mode = (it // len(combos)) % 4
+        if mode == 0:
+            lcp = rng.integers(0, 2 * k + 2, size=n)
+        elif mode == 1:
+            lcp = rng.integers(0, 70000, size=n)
+        elif mode == 2:
+            lcp = np.maximum(0, np.cumsum(rng.integers(-3, 4, size=n)) + k)
+        else:
+            lcp = rng.integers(k, k + 3, size=n)
+        lcp = np.minimum(lcp, (1 << (8 * min(x, 4))) - 1).astype(np.uint32)
+        bwt = rng.choice(alphabet, size=n)
+        text = rng.integers(0, 200, size=n)
+        suff = rng.integers(0, 100, size=n)
+        open(fa + ".gesa", "wb").write(_gesa_bytes(lcp, text, suff, bwt, x, y, z))
+        r, ncl = O.ref_ebwt2clust(fa, k=k, m=m, x=x, y=y, z=z)
+        assert r.returncode == 0
+        out = np.frombuffer(open(fa + ".clusters", "rb").read(), dtype=np.uint8)
+        lcps.append(lcp)
+        bwts.append(bwt)
+        outs.append(out)
+        meta.append((n, k, m, ncl, len(out), x, y, z))
+    np.savez_compressed(os.path.join(HERE, "phase1_fuzz_widths.npz"), lcp=np.concatenate(lcps), bwt=np.concatenate(bwts),
+                        out=np.concatenate(outs), meta=np.array(meta, dtype=np.int64))
+
+
 def micro(name, cfg, d):
     rs = synth.make_read_set(**cfg["gen"])
     e = synth.build_egsa(rs.reads)
@@ -96,6 +136,22 @@ def micro(name, cfg, d):
         res[f"v{vi}_allowed"] = np.array(info.get("allowed", (-1, -1)), dtype=np.int64)
         res[f"v{vi}_ncand"] = np.int64(info.get("n_candidates", -1))
         res[f"v{vi}_snp"] = np.frombuffer(open(snp_path, "rb").read() if os.path.exists(snp_path) else b"", dtype=np.uint8)
+    # the same read set through other index layouts (narrow fields, BCR triple): the phantom record differs
+    for j, (x, y, z, bcr) in enumerate(LAYOUTS):
+        d2 = os.path.join(d, f"lay{j}")
+        fa2 = synth.write_dataset(d2, rs, e, name=name + ".fasta", x=x, y=y, z=z, bcr=bcr)
+        r, ncl2 = O.ref_ebwt2clust(fa2, k=cfg["k"], m=cfg["m"], x=x, y=y, z=z)
+        assert r.returncode == 0
+        r, info = O.ref_clust2snp(fa2, rs.nreads1, x=x, y=y, z=z, timeout=600)
+        sp = os.path.join(d2, name + ".snp")
+        res[f"lay{j}_spec"] = np.array([x, y, z, int(bcr)], dtype=np.int64)
+        res[f"lay{j}_nclust"] = np.int64(ncl2)
+        res[f"lay{j}_clusters"] = np.frombuffer(open(fa2 + ".clusters", "rb").read(), dtype=np.uint8)
+        res[f"lay{j}_rc"] = np.int64(info["returncode"])
+        res[f"lay{j}_allowed"] = np.array(info.get("allowed", (-1, -1)), dtype=np.int64)
+        res[f"lay{j}_ncand"] = np.int64(info.get("n_candidates", -1))
+        res[f"lay{j}_snp"] = np.frombuffer(open(sp, "rb").read() if os.path.exists(sp) else b"", dtype=np.uint8)
+    res["n_layouts"] = np.int64(len(LAYOUTS))
     gen = cfg["gen"]
     np.savez_compressed(os.path.join(HERE, name + ".npz"), reads2bit=pack2(rs.reads), shape=np.array(rs.reads.shape),
                         nreads1=np.int64(rs.nreads1), gen=np.array(repr(gen)), k=np.int64(cfg["k"]), m=np.int64(cfg["m"]),
@@ -105,11 +161,94 @@ def micro(name, cfg, d):
           "events(v0) =", bytes(res["v0_snp"]).count(b">") // 2)
 
 
+def _gesa_bytes(lcp, text, suff, bwt, x, y, z):
+    n = len(lcp)
+    out = np.zeros((n, x + y + z + 1), dtype=np.uint8)
+
+    def put(col, arr, w):
+        a = np.asarray(arr, dtype=np.uint64)
+        for b in range(w):
+            out[:, col + b] = (a >> np.uint64(8 * b)) & np.uint64(0xFF)
+    put(0, text, y)
+    put(y, suff, z)
+    put(y + z, lcp, x)
+    out[:, y + z + x] = bwt
+    return out.tobytes()
+
+
+def phantom_tail(d):
+    """Hand-made index whose LAST cluster reaches position n (the post-EOF phantom record) and passes the
+    find_variants filters only if the phantom record lands in sample 1: counts[0]['A'] = 5, counts[1]['C'] = 4 (+1).
+    The number of candidates the reference prints for a few -n values reads out the phantom's `text` field."""
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    fa = os.path.join(d, "T.fasta")
+    open(fa, "w").write(">a\nACGT\n")
+    combos = [(4, 4, 4), (1, 4, 1), (1, 4, 4), (2, 4, 2), (4, 4, 1), (8, 8, 8), (1, 1, 1), (2, 2, 2), (1, 2, 4), (4, 2, 1), (2, 4, 4)]
+    rows, arrays = [], {}
+    ci = 0
+    for bcr in (False, True):
+        for (x, y, z) in combos:
+            mk = lambda w: (1 << (8 * min(w, 4))) - 1
+            lcpv, sufv, txtv = 0x11223344 & mk(x), 0x55667788 & mk(z), 0x0003BBCC & mk(y)
+            n = 40
+            V = lcpv if lcpv >= 16 else 40
+            lcp = np.zeros(n, dtype=np.uint64)
+            text = np.zeros(n, dtype=np.uint64)
+            suff = np.full(n, 50 & mk(z), dtype=np.uint64)
+            bwt = np.full(n, ord("G"), dtype=np.uint8)
+            lcp[n - 9:] = V
+            bwt[n - 9:n - 4] = ord("A")
+            bwt[n - 4:] = ord("C")
+            text[n - 4:] = txtv
+            suff[n - 4:] = 3
+            suff[n - 1] = sufv
+            for suffix in (".gesa", ".out", ".out.lcp", ".out.pairSA", ".clusters"):
+                if os.path.exists(fa + suffix):
+                    os.remove(fa + suffix)
+            if bcr:
+                bwt.tofile(fa + ".out")
+                lcp.astype(f"<u{x}").tofile(fa + ".out.lcp")
+                rec = np.empty(n, dtype=np.dtype([("s", f"<u{z}"), ("t", f"<u{y}")]))
+                rec["s"], rec["t"] = suff, text
+                rec.tofile(fa + ".out.pairSA")
+            else:
+                open(fa + ".gesa", "wb").write(_gesa_bytes(lcp, text, suff, bwt, x, y, z))
+            r = subprocess.run([os.path.join(ref, "ebwt2clust"), "-i", fa, "-x", str(x), "-y", str(y), "-z", str(z)],
+                               capture_output=True, text=True, timeout=60)
+            assert r.returncode == 0
+            clusters = np.frombuffer(open(fa + ".clusters", "rb").read(), dtype=np.uint8)
+            slot = O.lib().oracle_phantom_slot  # the model under test: only used to choose informative -n values
+            slot.restype = __import__("ctypes").c_uint64
+            sv = slot(int(lcp[-1]) & 0xFFFFFFFF, int(text[-1]) & 0xFFFFFFFF, int(suff[-1]) & 0xFFFFFFFF, int(bwt[-1]), x, y, z, int(bcr))
+            ptext = sv & mk(y)
+            probes = sorted({1, max(1, ptext - 1), max(1, ptext), ptext + 1, max(1, txtv), txtv + 1})
+            for n1 in probes:
+                cmd = [os.path.join(ref, "clust2snp"), "-i", fa, "-n", str(n1), "-x", str(x), "-y", str(y), "-z", str(z), "-L", "1", "-R", "1"]
+                try:
+                    out = subprocess.run(cmd, capture_output=True, text=True, timeout=5).stdout
+                except subprocess.TimeoutExpired as ex:  # the reference goes on to build a huge read table: the count is already printed
+                    out = ex.stdout.decode() if isinstance(ex.stdout, bytes) else (ex.stdout or "")
+                nc = -1
+                for line in out.splitlines():
+                    if line.startswith("Done. ") and "potential" in line:
+                        nc = int(line.split()[1])
+                assert nc >= 0, (x, y, z, bcr, n1)
+                rows.append((ci, x, y, z, int(bcr), n1, nc))
+            arrays[f"c{ci}_lcp"], arrays[f"c{ci}_text"], arrays[f"c{ci}_suff"], arrays[f"c{ci}_bwt"] = lcp, text, suff, bwt
+            arrays[f"c{ci}_clusters"] = clusters
+            ci += 1
+    np.savez_compressed(os.path.join(HERE, "phantom_tail.npz"), rows=np.array(rows, dtype=np.int64), n_cases=np.int64(ci), **arrays)
+    print("phantom_tail:", ci, "cases,", len(rows), "readouts; candidates seen:", sorted({r[-1] for r in rows}))
+
+
 if __name__ == "__main__":
     assert O.ref_available(), "oracle/_ref missing: run `make -C oracle ref` where /root/reference exists"
     d = tempfile.mkdtemp(prefix="golden_")
     try:
         phase1_fuzz(d)
+        phantom_tail(d)
+        phase1_fuzz_widths(d)
         for name, cfg in MICRO.items():
             micro(name, cfg, d)
     finally:

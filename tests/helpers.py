@@ -45,13 +45,14 @@ def flags(lcp, k):
     return start, end
 
 
-def emulate_shard(lcp, bwt, lo, hi, k, min_len):
+def emulate_shard(lcp, bwt, lo, hi, k, min_len, lcp_bytes=4):
     """What e2s_cluster_run reports for the shard [lo, hi) of the global arrays: (summary, start[], len[])."""
     n = len(lcp)
     start, end = flags(lcp, k)
     s = api.ClusterSummary()
     s.n_local, s.global_off, s.n_global = hi - lo, lo, n
     s.k, s.min_len = k, min_len & 0xFFFFFFFFFFFFFFFF
+    s.lcp_bytes = lcp_bytes
     st_pos = np.flatnonzero(start[lo:hi]) + lo
     en_pos = np.flatnonzero(end[lo:hi]) + lo
     s.n_end = len(en_pos)

@@ -6,6 +6,7 @@ import pytest
 
 from ebwt2snp_b200 import api, synth
 from oracle import oracle as O
+from tests import golden_util as GU
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -136,3 +137,90 @@ def test_pipeline_vs_oracle(ctx, name, seed):
         text = api.events_format(sh.events(), p)
         assert text == otext, kw
     sh.close()
+
+
+def _load_layout(ctx, e, lay):
+    """shard loaded the way the CLI would for this index layout"""
+    n = e["n"]
+    sh = ctx.shard(n)
+    if lay["bcr"]:
+        sh.load_soa(e["lcp"], e["text"], e["suff"], e["bwt"])
+        sh.set_layout(lay["x"], lay["y"], lay["z"], True)
+    else:
+        rec = synth.gesa_records(e, lay["x"], lay["y"], lay["z"])
+        sh.load_gesa(rec.view(np.uint8).reshape(-1), 0, n, x=lay["x"], y=lay["y"], z=lay["z"])
+    sh.seal()
+    return sh
+
+
+@pytest.mark.parametrize("name", ["micro_a", "micro_b"])
+def test_golden_vs_reference_outputs(ctx, name):
+    """the committed outputs of the UNMODIFIED reference (tests/golden): default layout x 6 option sets, and 5 other
+    index layouts (narrow fields, 8-byte fields, BCR triple)"""
+    g = GU.micro(name)
+    e = g["egsa"]
+    off = O.uniform_read_offsets(*g["reads"].shape)
+    ctx.stage_reads(g["reads"], off)
+    base = dict(x=4, y=4, z=4, bcr=False)
+    sh = _load_layout(ctx, e, base)
+    nw, nc = sh.cluster_lm(g["k"], g["m"])
+    assert sh.cluster_fetch_packed() == g["clusters"] and (nc & 0xFFFFFFFF) == g["n_clust_out"]
+    for v in g["variants"]:
+        p = api.default_params(g["nreads1"], **GU.params_kw(v["args"]))
+        st = sh.statistics(p.mcov_out, p.pval)
+        assert (2 * p.mcov_out, st.max_clust_length) == v["allowed"]
+        cnt = sh.find_events(p, st.max_clust_length)
+        if v["rc"] == 0:
+            assert cnt.n_candidates == v["ncand"] and api.events_format(sh.events(), p) == v["snp"], v["args"]
+        else:
+            assert cnt.n_candidates == 0
+    sh.close()
+    for lay in g["layouts"]:
+        sh = _load_layout(ctx, e, lay)
+        nw, nc = sh.cluster_lm(g["k"], g["m"])
+        assert sh.cluster_fetch_packed() == lay["clusters"] and (nc & 0xFFFFFFFF) == lay["n_clust_out"], lay
+        p = api.default_params(g["nreads1"])
+        st = sh.statistics(p.mcov_out, p.pval)
+        assert (2 * p.mcov_out, st.max_clust_length) == lay["allowed"]
+        cnt = sh.find_events(p, st.max_clust_length)
+        assert cnt.n_candidates == lay["ncand"] and api.events_format(sh.events(), p) == lay["snp"], lay
+        sh.close()
+
+
+def test_phantom_tail_vs_reference(ctx):
+    """the post-EOF phantom record for 11 width combinations x {EGSA, BCR}: candidate counts printed by the reference"""
+    reads = np.frombuffer(b"ACGT", dtype=np.uint8).reshape(1, 4)
+    ctx.stage_reads(reads, O.uniform_read_offsets(1, 4))
+    checked = 0
+    for c in GU.phantom_tail_cases():
+        n = len(c["lcp"])
+        sh = ctx.shard(n)
+        sh.load_soa(c["lcp"], c["text"], c["suff"], c["bwt"])
+        sh.set_layout(c["x"], c["y"], c["z"], c["bcr"])
+        sh.seal()
+        sh.cluster_lm(16, 2)
+        assert sh.cluster_fetch_packed() == c["clusters"], c["ci"]
+        for n1, ncand in c["readouts"]:
+            p = api.default_params(n1, k_left=1, k_right=1, max_gap=1)
+            st = sh.statistics(p.mcov_out, p.pval)
+            try:
+                cnt = sh.find_events(p, st.max_clust_length)
+            except api.E2SError as err:  # the candidate's reads do not exist (the reference goes on to crash there)
+                assert err.code == api.ERR_UNSUPPORTED
+                cnt = err.counts
+            assert cnt.n_candidates == ncand, (c["x"], c["y"], c["z"], c["bcr"], n1)
+            checked += 1
+        sh.close()
+    assert checked == 132
+
+
+def test_phase1_golden_gpu(ctx):
+    for c in list(GU.phase1_cases()) + list(GU.phase1_width_cases()):
+        n = len(c["lcp"])
+        sh = ctx.shard(n)
+        sh.load_soa(c["lcp"], None, None, c["bwt"])
+        sh.set_layout(c.get("x", 4), c.get("y", 4), c.get("z", 4), False)
+        sh.seal()
+        nw, nc = sh.cluster_lm(c["k"], c["m"])
+        assert sh.cluster_fetch_packed() == c["clusters"] and (nc & 0xFFFFFFFF) == c["n_clust_out"], (n, c["k"], c["m"])
+        sh.close()

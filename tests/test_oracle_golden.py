@@ -21,6 +21,50 @@ def test_phase1_golden(built):
     assert n == 72
 
 
+def test_phase1_widths_golden(built):
+    """-x 1 / 2 / 8: the phantom LCP is truncated to the field width"""
+    n = 0
+    for c in GU.phase1_width_cases():
+        s, l, ncl, _ = O.cluster_lm(c["lcp"], c["bwt"], c["k"], c["m"], x=c["x"])
+        assert O.clusters_to_bytes(s, l) == c["clusters"] and ncl == c["n_clust_out"], (c["x"], c["y"], c["z"], n)
+        n += 1
+    assert n == 96
+
+
+def test_phantom_tail_golden(built):
+    """the phantom record's fields for 11 width combinations x {EGSA, BCR}, read out of the reference through -n"""
+    n = 0
+    for c in GU.phantom_tail_cases():
+        s, l, _, _ = O.cluster_lm(c["lcp"], c["bwt"], 16, 2, x=c["x"])
+        assert O.clusters_to_bytes(s, l) == c["clusters"]
+        reads = np.frombuffer(b"ACGT", dtype=np.uint8).reshape(1, 4)
+        for n1, ncand in c["readouts"]:
+            p = O.default_params(n1, k_left=1, k_right=1, max_gap=1)  # -g only matters after the count is printed
+            st = O.statistics(s, l, p.mcov_out, p.pval)
+            _, res = O.find_events(c["lcp"], c["text"], c["suff"], c["bwt"], s, l, p, st.max_clust_length, reads,
+                                   O.uniform_read_offsets(1, 4), x=c["x"], y=c["y"], z=c["z"], bcr=c["bcr"], strict=False)
+            assert res.n_candidates == ncand, (c["x"], c["y"], c["z"], c["bcr"], n1)
+            n += 1
+    assert n == 132
+
+
+@pytest.mark.parametrize("name", ["micro_a", "micro_b"])
+def test_micro_layouts_golden(built, name):
+    """the same read sets through narrow-field .gesa files and the BCR triple"""
+    g = GU.micro(name)
+    e = g["egsa"]
+    off = O.uniform_read_offsets(*g["reads"].shape)
+    for lay in g["layouts"]:
+        s, l, ncl, _ = O.cluster_lm(e["lcp"], e["bwt"], g["k"], g["m"], x=lay["x"])
+        assert O.clusters_to_bytes(s, l) == lay["clusters"] and ncl == lay["n_clust_out"], lay
+        p = O.default_params(g["nreads1"])
+        st = O.statistics(s, l, p.mcov_out, p.pval)
+        assert (2 * p.mcov_out, st.max_clust_length) == lay["allowed"]
+        text, res = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], s, l, p, st.max_clust_length, g["reads"], off,
+                                  x=lay["x"], y=lay["y"], z=lay["z"], bcr=lay["bcr"])
+        assert lay["rc"] == 0 and res.n_candidates == lay["ncand"] and text == lay["snp"]
+
+
 @pytest.mark.parametrize("name", ["micro_a", "micro_b"])
 def test_micro_golden(built, name):
     g = GU.micro(name)
