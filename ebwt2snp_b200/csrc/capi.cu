@@ -27,9 +27,11 @@ struct e2s_ctx {
     uint64_t* d_off = nullptr;
     uint64_t n_reads = 0, n_bases = 0;
     bool reads_owned = false;
-    // staging
-    uint8_t* d_raw = nullptr;
+    // staging: two raw-record buffers, the H2D copies run on their own stream ahead of the de-interleave kernels
+    uint8_t* d_raw[2] = {nullptr, nullptr};
     size_t raw_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_unpacked[2] = {nullptr, nullptr}, ev_start = nullptr;
     // cached shard for e2s_pipeline_host
     e2s_shard* cached = nullptr;
     KernelTimer timer;
@@ -130,7 +132,14 @@ void e2s_ctx_destroy(e2s_ctx* c) {
         cudaFree(c->d_bases);
         cudaFree(c->d_off);
     }
-    cudaFree(c->d_raw);
+    cudaFree(c->d_raw[0]);
+    cudaFree(c->d_raw[1]);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_unpacked[i]) cudaEventDestroy(c->ev_unpacked[i]);
+    }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -272,22 +281,42 @@ int e2s_shard_load_gesa(e2s_shard* s, const void* records, uint64_t first, uint6
     if (a >= b) return E2S_OK;
     s->lay_x = x; s->lay_y = y; s->lay_z = z; s->lay_bcr = 0;
     const int rs = x + y + z + 1;
-    const uint64_t chunk = uint64_t(1) << 24;  // records per H2D chunk (multiple of 16)
+    const uint64_t chunk = uint64_t(1) << 22;  // records per H2D chunk (multiple of 16)
     const size_t need = size_t(chunk < (b - a) ? chunk : round_up(b - a, 16)) * rs + 64;
     if (need > c->raw_cap) {
-        cudaFree(c->d_raw);
-        c->d_raw = nullptr;
+        CU(c, cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(c->d_raw[i]);
+            c->d_raw[i] = nullptr;
+        }
         c->raw_cap = 0;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->d_raw), need);
-        if (e != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "raw staging buffer");
+        for (int i = 0; i < 2; ++i)
+            if (cudaMalloc(reinterpret_cast<void**>(&c->d_raw[i]), need) != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "raw staging buffer");
         c->raw_cap = need;
     }
+    if (!c->copy_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&c->ev_unpacked[i], cudaEventDisableTiming));
+        }
+        CU(c, cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+    }
+    // the copy stream starts after everything already queued on the context's stream (earlier unpack kernels read d_raw)
+    CU(c, cudaEventRecord(c->ev_start, c->stream));
+    CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
     const uint8_t* src = static_cast<const uint8_t*>(records);
-    for (uint64_t p = a; p < b; p += chunk) {
+    uint64_t i = 0;
+    for (uint64_t p = a; p < b; p += chunk, ++i) {
         const uint64_t cnt = b - p < chunk ? b - p : chunk;
-        CU(c, cudaMemcpyAsync(c->d_raw, src + (p - first) * rs, size_t(cnt) * rs, cudaMemcpyHostToDevice, c->stream));
+        const int buf = int(i & 1);
+        if (i >= 2) CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_unpacked[buf], 0));  // the kernel that read this buffer is done
+        CU(c, cudaMemcpyAsync(c->d_raw[buf], src + (p - first) * rs, size_t(cnt) * rs, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(c, cudaEventRecord(c->ev_copied[buf], c->copy_stream));
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0));
         const int64_t l = int64_t(p) - int64_t(s->global_off);  // local index, may be -2 / -1
-        CU(c, launch_unpack_gesa(c->d_raw, cnt, x, y, z, s->lcp + l, s->text + l, s->suff + l, s->bwt + l, c->stream));
+        CU(c, launch_unpack_gesa(c->d_raw[buf], cnt, x, y, z, s->lcp + l, s->text + l, s->suff + l, s->bwt + l, c->stream));
+        CU(c, cudaEventRecord(c->ev_unpacked[buf], c->stream));
         ++c->launches;
     }
     s->sealed = false;
@@ -404,13 +433,10 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
     const char* env = getenv("E2S_CLUSTER_VARIANT");
     s->variant = env ? atoi(env) : 0;
     const uint64_t num_tiles = emit_num_tiles(s->n_local);
-    if (num_tiles * 2 > s->desc_cap) {
-        cudaFree(s->d_desc);
-        s->d_desc = nullptr;
-        s->desc_cap = 0;
-        if (cudaMalloc(reinterpret_cast<void**>(&s->d_desc), num_tiles * 2 * 8) != cudaSuccess)
-            return fail(c, E2S_ERR_NOMEM, "tile descriptors");
-        s->desc_cap = num_tiles * 2;
+    if (!s->d_desc) {
+        if (cudaMalloc(reinterpret_cast<void**>(&s->d_desc), emit_desc_words() * 8) != cudaSuccess)
+            return fail(c, E2S_ERR_NOMEM, "chunk descriptors");
+        s->desc_cap = emit_desc_words();
     }
     if (!s->d_flags) {
         s->flag_words = flags_words_needed(s->n_local);
@@ -443,7 +469,7 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
     if (!s->h_pin) CU(c, cudaHostAlloc(reinterpret_cast<void**>(&s->h_pin), sizeof(ClusterDev), cudaHostAllocDefault));
     ClusterDev& h = *s->h_pin;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        CU(c, cudaMemsetAsync(s->d_desc, 0, num_tiles * 2 * 8, c->stream));
+        CU(c, cudaMemsetAsync(s->d_desc, 0, s->desc_cap * 8, c->stream));
         CU(c, cudaMemsetAsync(s->d_res, 0, sizeof(ClusterDev), c->stream));
         EmitParams p;
         p.s_words = s->d_flags;
@@ -455,8 +481,14 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
         p.out_start = s->d_start;
         p.out_len = s->d_len;
         p.cap = s->rec_cap - 4;  // room for adopted records
-        p.desc_state = s->d_desc;
-        p.desc_cnt = s->d_desc + num_tiles;
+        p.desc = s->d_desc;
+        p.dbg = nullptr;
+        uint64_t* d_dbg = nullptr;
+        const char* dbg_path = getenv("E2S_EMIT_DEBUG");  // developer aid: per-chunk phase time stamps of K2
+        if (dbg_path && cudaMalloc(reinterpret_cast<void**>(&d_dbg), emit_desc_words() * 4) == cudaSuccess) {
+            cudaMemsetAsync(d_dbg, 0, emit_desc_words() * 4, c->stream);
+            p.dbg = d_dbg;
+        }
         p.res = s->d_res;
         const bool is_last = s->global_off + s->n_local == s->n_global;
         p.tail_lcp = is_last ? s->lcp + s->n_local - 2 : nullptr;
@@ -468,6 +500,17 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
         ++c->launches;
         CU(c, cudaMemcpyAsync(&h, s->d_res, sizeof h, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
+        if (d_dbg) {
+            std::vector<uint64_t> hd(emit_desc_words() / 2);
+            cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
+            if (FILE* f = fopen(dbg_path, "w")) {
+                for (size_t i = 0; i + 3 < hd.size(); i += 4)
+                    if (hd[i]) fprintf(f, "%zu %llu %llu %llu %llu\n", i / 4, (unsigned long long)hd[i], (unsigned long long)hd[i + 1],
+                                       (unsigned long long)hd[i + 2], (unsigned long long)hd[i + 3]);
+                fclose(f);
+            }
+            cudaFree(d_dbg);
+        }
         if (!h.overflow) break;
         if (attempt == 1) return fail(c, E2S_ERR_STATE, "record buffer overflow after resize");
         int rc = ensure_records(s, h.n_written + 4096);

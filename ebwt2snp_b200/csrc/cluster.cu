@@ -173,130 +173,56 @@ __global__ void __launch_bounds__(FL_THREADS) k_lcp_flags(const __grid_constant_
 }
 
 // =============================================================================================
-// K2: look-back scan over the bit masks + compaction
+// K2: chunked reduce-then-scan over the bit masks + compaction
 // =============================================================================================
-// START and END bits alternate (S <= E < S' <= E' ...), so inside a tile the j-th END pairs with the
-// (j - open_in)-th START, where open_in says whether a cluster is still open when the tile begins (its
-// START then comes from the look-back).  The kernel therefore never walks bits cluster by cluster:
-//   1. every thread loads 4+4 mask words (128 positions), popcounts them, and a block scan gives each
-//      thread the ordinal of its first START / END;
-//   2. the bit positions are scattered by ordinal into two shared lists (16-bit tile-local positions);
-//   3. a dense, END-centric pass (one lane per record, all lanes busy) forms (start, len), applies the
-//      min_len test on the wrapped length, ranks the kept records with ballot/popc and writes them
-//      coalesced at the offset the second look-back provides.
-// Tiles with more than EM_CAP ENDs (adversarial inputs only) take the same steps in windows of EM_CAP.
+// START and END bits alternate (S <= E < S' <= E' ...): every END closes the cluster opened by the nearest
+// START at or before it.  The grid cuts the shard's mask words into one contiguous CHUNK per CTA and makes
+// two passes over its chunk with ONE exchange in between, so no tile ever waits for another tile:
+//   pass 1  counts the records the chunk will keep.  Which ENDs are dropped by the min_len test is a
+//           bit-parallel function of the masks (a START within min_len - 1 positions, min_len <= 33), so
+//           this is a pure streaming popcount pass (no barriers except one vote per tile, see `flagged`).
+//   exchange every CTA publishes (kept count, first/last START and END of the chunk) -- values that do not
+//           depend on any other chunk -- resolves the one END that may close a cluster opened in an earlier
+//           chunk (exact wrapped-length test), publishes its final count and sums the final counts of the
+//           chunks before it: depth-2 dependency, no chain.
+//   pass 2  re-reads the chunk (L2), scatters the END positions with their output ranks into shared memory
+//           and writes the records with one lane per record: the START is found by a backward search in the
+//           tile's START mask (shared memory), offsets are running sums inside the CTA.
+// Exactness: the bit-parallel count is exact unless the wrapped length (L mod 2^16) matters, i.e. a cluster
+// is >= 65503 long.  Such a cluster implies >= 7 of the 8 warps of some tile see no event at all; pass 1
+// votes on that per tile and the chunk then falls back to the EXACT routine (also used for min_len > 33),
+// which pairs and tests every END individually in both passes.
 constexpr int EM_THREADS = 256;
 constexpr int EM_WARPS = EM_THREADS / 32;
 constexpr int EM_WPT = 4;                               // 32-bit words per thread and mask (one uint4)
 constexpr int EM_TILE_WORDS = EM_THREADS * EM_WPT;      // 1024 words = 32768 positions
 constexpr int EM_TILE_POS = EM_TILE_WORDS * 32;
-constexpr int EM_CAP = 2048;                            // ENDs per window
-constexpr int EM_EPT = EM_CAP / EM_THREADS;             // dense entries per thread and window
-constexpr int EM_ROWS = EM_CAP / 32;
+constexpr int EM_CAP = 2048;                            // ENDs per scatter window
+constexpr int EM_DESC_WORDS = 8;                        // u64 words per chunk descriptor
+constexpr int EM_MAX_CHUNKS = 148 * 8 * 2;              // upper bound of the grid (descriptor allocation)
 
 // payload encoding of the open-cluster state
 constexpr uint64_t OPEN_NONE = 0;
-constexpr uint64_t OPEN_UNKNOWN = 1;  // open, but started before this shard
+constexpr uint64_t OPEN_UNKNOWN = 1;  // open or not is decided by an earlier shard
 constexpr uint64_t OPEN_BIAS = 2;     // payload = global start + 2
 
-// Look-back windows: every lane keeps LB_R descriptor loads in flight, so one round trip to L2 covers
-// 32 * LB_R predecessors.  (The tile rate of the whole grid is bounded by window size / window latency x
-// tiles in flight: with 64-wide windows the scan was latency bound, profiles/r1_v4_emit.)  A lane only
-// polls a descriptor that is still INVALID when it lies before the nearest INCLUSIVE one.
-constexpr int LB_R = 4;
+// chunk descriptor words
+enum { CD_A = 0, CD_FIRST_E = 1, CD_FIRST_S = 2, CD_LAST_S = 3, CD_LAST_E = 4, CD_B = 5 };
+constexpr uint64_t CD_VALID = uint64_t(1) << 63;
 
-__device__ __forceinline__ uint32_t desc_status(uint64_t d) { return uint32_t(d >> ST_SHIFT); }
-
-// nearest predecessor whose open-cluster state is final
-__device__ __forceinline__ uint64_t lookback_state(const uint64_t* desc, int64_t t, uint64_t init, int lane) {
-    int64_t j = t - 1;
-    const uint64_t virt = (ST_INCLUSIVE << ST_SHIFT) | init;  // virtual tile -1
-    while (true) {
-        uint64_t d[LB_R];
-#pragma unroll
-        for (int r = 0; r < LB_R; ++r) {
-            const int64_t i = j - 32 * r - lane;
-            d[r] = i >= 0 ? desc_load(desc + i) : virt;
-        }
-#pragma unroll
-        for (int r = 0; r < LB_R; ++r) {
-            const int64_t i = j - 32 * r - lane;
-            while (true) {
-                const uint32_t inc = __ballot_sync(FULL, desc_status(d[r]) == ST_INCLUSIVE);
-                const uint32_t inv = __ballot_sync(FULL, desc_status(d[r]) == ST_INVALID);
-                const uint32_t before = inc ? ((1u << (__ffs(inc) - 1)) - 1u) : FULL;  // lanes nearer than the first INCLUSIVE
-                if (!(inv & before)) {
-                    if (inc) return __shfl_sync(FULL, d[r], __ffs(inc) - 1) & ST_PAYLOAD;
-                    break;  // 32 pass-through tiles: next round
-                }
-                if (desc_status(d[r]) == ST_INVALID && ((before >> lane) & 1u)) {
-                    __nanosleep(20);
-                    d[r] = desc_load(desc + i);
-                }
-            }
-        }
-        j -= 32 * LB_R;
-    }
+__device__ __forceinline__ void st_release(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-
-// exclusive sum of the predecessors' aggregates back to the nearest INCLUSIVE descriptor
-__device__ __forceinline__ uint64_t lookback_sum(const uint64_t* desc, int64_t t, int lane) {
-    uint64_t acc = 0;  // per-lane partial sum, reduced once at the end
-    int64_t j = t - 1;
-    const uint64_t virt = ST_INCLUSIVE << ST_SHIFT;  // virtual tile -1: inclusive 0
-    bool done = false;
-    while (!done) {
-        uint64_t d[LB_R];
-#pragma unroll
-        for (int r = 0; r < LB_R; ++r) {
-            const int64_t i = j - 32 * r - lane;
-            d[r] = i >= 0 ? desc_load(desc + i) : virt;
-        }
-#pragma unroll
-        for (int r = 0; r < LB_R; ++r) {
-            if (done) break;
-            const int64_t i = j - 32 * r - lane;
-            while (true) {
-                const uint32_t inc = __ballot_sync(FULL, desc_status(d[r]) == ST_INCLUSIVE);
-                const uint32_t inv = __ballot_sync(FULL, desc_status(d[r]) == ST_INVALID);
-                const int f = inc ? __ffs(inc) - 1 : 32;
-                const uint32_t upto = f >= 31 ? FULL : ((2u << f) - 1u);  // lanes 0..f (f = 32: all)
-                if (!(inv & upto)) {
-                    if ((upto >> lane) & 1u) acc += d[r] & ST_PAYLOAD;
-                    done = inc != 0;
-                    break;
-                }
-                if (desc_status(d[r]) == ST_INVALID && ((upto >> lane) & 1u)) {
-                    __nanosleep(20);
-                    d[r] = desc_load(desc + i);
-                }
-            }
-        }
-        j -= 32 * LB_R;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-    return acc;
+__device__ __forceinline__ uint64_t ld_acquire(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
-
-struct EmitShared {
-    uint16_t spos[EM_CAP + 2];  // spos[1 + q] = tile-local position of START ordinal (win + q); spos[0]: ordinal win - 1
-    uint16_t epos[EM_CAP];      // epos[q]     = tile-local position of END   ordinal (win + q)
-    uint16_t erank[EM_CAP];     // FAST: rank of that END among the tile's kept records, 0xFFFF = dropped (shorter than min_len)
-    uint32_t wsum[EM_WARPS];    // per warp: #START | #END << 16
-    uint32_t wlast[EM_WARPS];   // per warp: 0 = no event, else 0x80000000 | (1 + tile-local position of a START left open)
-    uint32_t wfirst[EM_WARPS];  // per warp: 0 = no event, else 0x80000000 | (first event is an END without START)
-    uint32_t wfirst_end[EM_WARPS];  // per warp: tile-local position of its first END, ~0 = none
-    uint32_t wdrop[EM_WARPS];   // per warp: ENDs whose cluster is shorter than min_len (bit-parallel count)
-    uint32_t rowcnt[EM_ROWS];
-    uint32_t rowbase[EM_ROWS];
-    uint32_t round_total;
-    uint32_t adj;               // FAST: 1 if the tile's first END (cluster carried in) turned out not to be kept
-    unsigned long long tile;    // ticket of the tile being processed
-    uint64_t x;                 // open state entering the tile (payload encoding)
-    uint64_t prefix;            // records kept before this tile
-    unsigned int hist[E2S_HIST_BINS];
-};
+__device__ __forceinline__ uint64_t wait_valid(const uint64_t* p) {
+    uint64_t v;
+    while (!((v = ld_acquire(p)) & CD_VALID)) __nanosleep(40);
+    return v;
+}
 
 // the wrapped length test of append_entry (ref:ebwt2clust.cpp:56,104)
 __device__ __forceinline__ bool keep_len(uint64_t st, uint64_t gend, int32_t min_len, uint32_t* len) {
@@ -304,389 +230,521 @@ __device__ __forceinline__ bool keep_len(uint64_t st, uint64_t gend, int32_t min
     return int(*len) >= min_len;
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(EM_THREADS, FAST ? 4 : 1) k_cluster_emit(EmitParams p) {
+// highest / lowest set bit of a 128-bit value held in 4 words (word 0 = lowest positions); -1 / 128 if none
+__device__ __forceinline__ int top_bit128(const uint32_t w[4]) {
+    const unsigned long long hi = (uint64_t(w[3]) << 32) | w[2], lo = (uint64_t(w[1]) << 32) | w[0];
+    return hi ? 127 - __clzll(hi) : (lo ? 63 - __clzll(lo) : -1);
+}
+__device__ __forceinline__ int low_bit128(const uint32_t w[4]) {
+    const unsigned long long hi = (uint64_t(w[3]) << 32) | w[2], lo = (uint64_t(w[1]) << 32) | w[0];
+    return lo ? __ffsll(lo) - 1 : (hi ? 63 + __ffsll(hi) : 128);
+}
+
+struct EmitShared {
+    uint32_t smask[EM_TILE_WORDS];  // START mask of the tile (backward search for the START of an END)
+    uint32_t emask[EM_TILE_WORDS];  // END mask of the tile
+    uint16_t ek[EM_CAP];            // ek[q] = tile-local position of the tile's (win + q)-th listed END (bit-parallel mode: kept ENDs only)
+    uint32_t wsum[EM_WARPS];        // per warp: #END | #dropped << 16
+    alignas(8) uint8_t wev[2][EM_WARPS];  // pass 1: per warp, bit 0 = has a START, bit 1 = has an END (double buffered)
+    uint8_t wfirst_end[EM_WARPS];         // pass 1, rare path: the warp's first event is an END
+    int t_last_s, t_last_e, t_first_s, t_first_e;  // tile-local positions, -1 / NO_POS = none (written by warp 0)
+    uint32_t row_kept;              // EXACT: running kept count of the tile
+    unsigned long long red[6];      // block reductions of pass 1
+    uint64_t x_in, prefix, carried_pos;
+    uint32_t adj;
+    unsigned int hist[E2S_HIST_BINS];
+};
+
+constexpr int NO_POS = 0x7fffffff;
+constexpr uint64_t NO_TILE = ~0ull;
+
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool has_zero_byte(uint32_t x) { return ((x - 0x01010101u) & ~x & 0x80808080u) != 0; }
+
+__global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
     __shared__ EmitShared sh;
+    __shared__ unsigned long long s_chunk;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    // min_len <= 33: which ENDs are dropped is a bit-parallel function of the masks (a START within
-    // min_len - 1 positions), so the tile's kept count is known right after the load and the offset
-    // look-back overlaps the rest of the tile.  Larger min_len: count in the dense pass first.
-    constexpr bool fast_count = FAST;  // the launcher picks FAST iff min_len <= 33
     const int spread = p.min_len >= 2 ? p.min_len - 2 : -1;  // extra positions a START shadows; -1: nothing is dropped
 
     for (int i = tid; i < E2S_HIST_BINS; i += EM_THREADS) sh.hist[i] = 0;
-    if (tid == 0) sh.tile = atomicAdd(&p.res->ticket, 1ull);
-    unsigned long long acc_end = 0, acc_bases = 0;
-    uint32_t acc_any = 0;
+    // Chunks are handed out by a ticket, so every chunk with a smaller id is owned by a CTA that is already
+    // running: the spin-waits of the exchange cannot deadlock whatever else occupies the SMs.
+    if (tid == 0) s_chunk = atomicAdd(&p.res->ticket, 1ull);
+    __syncthreads();
+    const uint64_t c = s_chunk, n_chunks = gridDim.x;
+    if (p.dbg && tid == 0) p.dbg[c * 4 + 0] = global_ns();
+    const uint64_t tpc = (p.num_tiles + n_chunks - 1) / n_chunks;  // tiles per chunk
+    const uint64_t t_lo = c * tpc < p.num_tiles ? c * tpc : p.num_tiles;
+    const uint64_t t_hi = t_lo + tpc < p.num_tiles ? t_lo + tpc : p.num_tiles;
+    uint64_t* my_desc = p.desc + c * EM_DESC_WORDS;
+    bool exact = p.min_len > 33;  // CTA-uniform
 
-    // Tiles are handed out by a ticket counter, so a tile is only ever waited for by CTAs that started
-    // after its owner did: the look-back spin-waits cannot deadlock whatever else occupies the SMs.
-    for (;;) {
-        __syncthreads();  // (T) ticket visible; shared state of the previous tile is no longer read
-        const uint64_t t = sh.tile;
-        if (t >= p.num_tiles) break;
+    // D = ENDs of clusters shorter than min_len: a START at the same position or up to `spread` positions before.
+    // `pv` = START word preceding S[0] (0 at the start of the chunk: an END shadowed from an earlier chunk is the
+    // chunk's first END, which the exchange tests exactly).
+    auto dropped_mask = [&](const uint32_t S[EM_WPT], const uint32_t E[EM_WPT], uint32_t pv, uint32_t D[EM_WPT]) {
+#pragma unroll
+        for (int j = 0; j < EM_WPT; ++j) {
+            uint32_t sp = 0;
+            if (spread >= 0) {
+                sp = S[j];
+                const uint32_t prev = j ? S[j - 1] : pv;
+                for (int d = 1; d <= spread; ++d) sp |= __funnelshift_l(prev, S[j], d);
+            }
+            D[j] = E[j] & sp;
+        }
+    };
+    auto prev_word = [&](uint64_t t, uint64_t word0, uint32_t my_last_word) -> uint32_t {
+        if (spread <= 0) return 0u;  // uniform: only the shifted copies look at the previous word
+        uint32_t pv = __shfl_up_sync(FULL, my_last_word, 1);
+        if (lane == 0) pv = (tid == 0 && t == t_lo) ? 0u : __ldg(p.s_words + word0 - 1);
+        return pv;
+    };
+    // global position of the first / last set bit of `mask` inside tile t (block-wide; ~0 / 0 = none; last is 1 + position)
+    auto locate = [&](const uint32_t* mask, uint64_t t, bool want_first) -> unsigned long long {
+        __syncthreads();
+        if (tid == 0) sh.red[0] = want_first ? ~0ull : 0ull;
+        __syncthreads();
+        if (t != NO_TILE) {
+            const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(mask + t * EM_TILE_WORDS + uint64_t(tid) * EM_WPT));
+            const uint32_t M[EM_WPT] = {m4.x, m4.y, m4.z, m4.w};
+            const uint64_t gbase = p.global_off + t * uint64_t(EM_TILE_POS) + uint64_t(tid) * (EM_WPT * 32);
+            if (want_first) {
+                const int b = low_bit128(M);
+                if (b < 128) atomicMin(&sh.red[0], (unsigned long long)(gbase + b));
+            } else {
+                const int b = top_bit128(M);
+                if (b >= 0) atomicMax(&sh.red[0], (unsigned long long)(gbase + b + 1));
+            }
+        }
+        __syncthreads();
+        return sh.red[0];
+    };
+
+    // ================= pass 1 (bit-parallel): kept count, first / last events of the chunk =================
+    unsigned long long kept_prov = 0, n_end_chunk = 0;
+    unsigned long long first_e = ~0ull, first_s = ~0ull, last_s = 0, last_e = 0;  // first: global position; last: 1 + global position
+    if (!exact) {
+        uint32_t kept_t = 0, ends_t = 0;
+        uint64_t ft_s = NO_TILE, ft_e = NO_TILE, lt_s = NO_TILE, lt_e = NO_TILE;  // first / last tile in which my warp saw a START / END
+        bool flagged = false, seen = false;
+        uint32_t run = 0;  // consecutive 4096-position blocks without any event (block-uniform)
+        uint4 s4 = make_uint4(0, 0, 0, 0), e4 = s4;
+        if (t_lo < t_hi) {
+            const uint64_t w0 = t_lo * EM_TILE_WORDS + uint64_t(tid) * EM_WPT;
+            s4 = __ldg(reinterpret_cast<const uint4*>(p.s_words + w0));
+            e4 = __ldg(reinterpret_cast<const uint4*>(p.e_words + w0));
+        }
+        for (uint64_t t = t_lo; t < t_hi; ++t) {
+            const uint64_t word0 = t * EM_TILE_WORDS + uint64_t(tid) * EM_WPT;
+            const uint32_t S[EM_WPT] = {s4.x, s4.y, s4.z, s4.w};
+            const uint32_t E[EM_WPT] = {e4.x, e4.y, e4.z, e4.w};
+            if (t + 1 < t_hi) {  // next tile's loads stay in flight across the barrier
+                s4 = __ldg(reinterpret_cast<const uint4*>(p.s_words + word0 + EM_TILE_WORDS));
+                e4 = __ldg(reinterpret_cast<const uint4*>(p.e_words + word0 + EM_TILE_WORDS));
+            }
+            uint32_t D[EM_WPT];
+            dropped_mask(S, E, prev_word(t, word0, S[EM_WPT - 1]), D);
+            uint32_t ce = 0, cd = 0;
+#pragma unroll
+            for (int j = 0; j < EM_WPT; ++j) {
+                ce += __popc(E[j]);
+                cd += __popc(D[j]);
+            }
+            ends_t += ce;
+            kept_t += ce - cd;
+            const bool any_s = __any_sync(FULL, (S[0] | S[1] | S[2] | S[3]) != 0), any_e = __any_sync(FULL, ce != 0);
+            if (any_s) {
+                lt_s = t;
+                if (ft_s == NO_TILE) ft_s = t;
+            }
+            if (any_e) {
+                lt_e = t;
+                if (ft_e == NO_TILE) ft_e = t;
+            }
+            // Wrap watch: a cluster of >= 65503 positions leaves >= 14 consecutive aligned 4096-position blocks (one
+            // per warp and tile) without any event between its START and its END.
+            if (lane == 0) sh.wev[t & 1][warp] = uint8_t(uint32_t(any_s) | (uint32_t(any_e) << 1));
+            __syncthreads();
+            const uint2 ev = *reinterpret_cast<const uint2*>(sh.wev[t & 1]);
+            if (run == 0 && !has_zero_byte(ev.x) && !has_zero_byte(ev.y)) {  // every warp saw an event: the usual case
+                run = 0;
+                seen = true;
+            } else {
+                // rare (block-uniform): some 4096-position block is empty or a run of empty blocks is pending.  A run matters
+                // only if it lies INSIDE a cluster, i.e. the first event after it is an END that no START precedes.
+                {
+                    const int fs = low_bit128(S), fe = low_bit128(E);
+                    const int wfs = __reduce_min_sync(FULL, fs < 128 ? lane * 128 + fs : NO_POS);
+                    const int wfe = __reduce_min_sync(FULL, fe < 128 ? lane * 128 + fe : NO_POS);
+                    if (lane == 0) sh.wfirst_end[warp] = uint8_t(wfe < wfs);
+                }
+                __syncthreads();
+                for (int w = 0; w < EM_WARPS; ++w) {
+                    const uint32_t b = ((w < 4 ? ev.x : ev.y) >> (8 * (w & 3))) & 0xffu;
+                    if (!b) {
+                        ++run;
+                    } else {
+                        if (run >= 14 && seen && sh.wfirst_end[w]) flagged = true;
+                        run = 0;
+                        seen = true;
+                    }
+                }
+            }
+        }
+        if (flagged) {
+            exact = true;  // a cluster may be long enough for its 16-bit length to wrap: count exactly below
+        } else {
+            if (tid < 6) sh.red[tid] = (tid == 2 || tid == 3) ? ~0ull : 0ull;
+            __syncthreads();
+            const uint32_t wk = __reduce_add_sync(FULL, kept_t), we = __reduce_add_sync(FULL, ends_t);
+            if (lane == 0) {
+                atomicAdd(&sh.red[0], (unsigned long long)wk);
+                atomicAdd(&sh.red[1], (unsigned long long)we);
+                if (ft_e != NO_TILE) atomicMin(&sh.red[2], (unsigned long long)ft_e);
+                if (ft_s != NO_TILE) atomicMin(&sh.red[3], (unsigned long long)ft_s);
+                if (lt_s != NO_TILE) atomicMax(&sh.red[4], (unsigned long long)lt_s + 1);
+                if (lt_e != NO_TILE) atomicMax(&sh.red[5], (unsigned long long)lt_e + 1);
+            }
+            __syncthreads();
+            kept_prov = sh.red[0];
+            n_end_chunk = sh.red[1];
+            const uint64_t tfe = sh.red[2], tfs = sh.red[3], tls = sh.red[4], tle = sh.red[5];
+            // exact positions of the chunk's first / last START and END: one look at the four tiles that hold them
+            first_e = locate(p.e_words, tfe, true);
+            first_s = locate(p.s_words, tfs, true);
+            last_s = locate(p.s_words, tls ? tls - 1 : NO_TILE, false);
+            last_e = locate(p.e_words, tle ? tle - 1 : NO_TILE, false);
+        }
+    }
+
+    // ================= the tile routine: pass 2, and pass 1 of EXACT chunks =================
+    // Processes tile t with the open state X entering it; updates X to the state leaving the tile and returns the
+    // tile's kept count (block-uniform).  write: records go to out[obase + rank].
+    //   carried_pos : global position of the chunk's first END if its START lies before the chunk (known after
+    //                 the exchange), ~0 otherwise;  adj = 1 if that END turned out not to be kept
+    //   resolved    : X is authoritative (false in pass 1 of an EXACT chunk until an event has been seen)
+    unsigned long long acc_bases = 0;
+    struct TileInfo { int first_s, first_e, last_s, last_e; uint32_t n_end; };
+    auto tile_pass = [&](uint64_t t, uint64_t& X, bool resolved, uint64_t obase, bool write, uint64_t carried_pos,
+                         uint32_t adj, uint64_t chunk_end, TileInfo* info) -> uint32_t {
+        __syncthreads();  // shared state of the previous tile is no longer read
         const uint64_t word0 = t * EM_TILE_WORDS + uint64_t(tid) * EM_WPT;
         const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(p.s_words + word0));
         const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(p.e_words + word0));
         const uint32_t S[EM_WPT] = {s4.x, s4.y, s4.z, s4.w};
         const uint32_t E[EM_WPT] = {e4.x, e4.y, e4.z, e4.w};
         const uint64_t tile_gbase = p.global_off + t * uint64_t(EM_TILE_POS);
-
-        // ---- 1. counts, ordinals, first / last event --------------------------------------------------
-        uint32_t cS = 0, cE = 0, cD = 0, last = 0, first = 0, first_end = ~0u;
-        uint32_t D[EM_WPT] = {0, 0, 0, 0};  // FAST: ENDs of clusters shorter than min_len
-#pragma unroll
-        for (int j = EM_WPT - 1; j >= 0; --j) {
-            if (S[j] | E[j]) {
-                const uint32_t fs = __ffs(S[j]), fe = __ffs(E[j]);  // 1-based, 0 = none
-                first = 0x80000000u | uint32_t(fe && (!fs || fe < fs));
-            }
-            if (E[j]) first_end = uint32_t((tid * EM_WPT + j) * 32 + __ffs(E[j]) - 1);
-        }
-        uint32_t s_prev = __shfl_up_sync(FULL, S[EM_WPT - 1], 1);
-        if (lane == 0) s_prev = (fast_count && spread > 0 && tid > 0) ? __ldg(p.s_words + word0 - 1) : 0u;
+        reinterpret_cast<uint4*>(sh.smask)[tid] = s4;
+        reinterpret_cast<uint4*>(sh.emask)[tid] = e4;
+        uint32_t D[EM_WPT] = {0, 0, 0, 0};
+        if (!exact) dropped_mask(S, E, prev_word(t, word0, S[EM_WPT - 1]), D);
+        uint32_t cE = 0, cD = 0;
 #pragma unroll
         for (int j = 0; j < EM_WPT; ++j) {
-            cS += __popc(S[j]);
             cE += __popc(E[j]);
-            if (S[j] | E[j]) {
-                const int hs = 31 - __clz(S[j]), he = 31 - __clz(E[j]);  // -1 when the word has none
-                last = 0x80000000u | (hs > he ? uint32_t((tid * EM_WPT + j) * 32 + hs + 1) : 0u);
-            }
-            if (fast_count && spread >= 0) {
-                uint32_t sp = S[j];
-                const uint32_t pv = j ? S[j - 1] : s_prev;
-                for (int d = 1; d <= spread; ++d) sp |= __funnelshift_l(pv, S[j], d);
-                D[j] = E[j] & sp;
-                cD += __popc(D[j]);
-            }
+            cD += __popc(D[j]);
         }
-        const uint32_t pk = cS | (cE << 16);
+        const uint32_t pk = cE | (cD << 16);
         uint32_t inc = pk;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(FULL, inc, d);
             if (lane >= d) inc += o;
         }
-        const uint32_t evm = __ballot_sync(FULL, last != 0);
-        const uint32_t wl = evm ? __shfl_sync(FULL, last, 31 - __clz(evm)) : 0u;
-        const uint32_t wf = evm ? __shfl_sync(FULL, first, __ffs(evm) - 1) : 0u;
-        const uint32_t enm = __ballot_sync(FULL, cE != 0);
-        const uint32_t wfe = enm ? __shfl_sync(FULL, first_end, __ffs(enm) - 1) : ~0u;
-        uint32_t dinc = cD;  // inclusive scan of the dropped counts (FAST only)
-        if (fast_count && spread >= 0) {
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(FULL, dinc, d);
-                if (lane >= d) dinc += o;
+        if (lane == 31) sh.wsum[warp] = inc;
+        if (tid == 0) sh.row_kept = 0;
+        __syncthreads();  // (1) masks and the per-warp sums
+        if (warp == 0) {
+            // last (and, for pass 1 of an EXACT chunk, first) START / END of the tile: warp-wide search in the shared masks
+            auto top_of = [&](const uint32_t* m) -> int {
+                for (int b0 = EM_TILE_WORDS - 32; b0 >= 0; b0 -= 32) {
+                    const uint32_t w = m[b0 + lane];
+                    const uint32_t bal = __ballot_sync(FULL, w != 0);
+                    if (bal) {
+                        const int hl = 31 - __clz(bal);
+                        return (b0 + hl) * 32 + 31 - __clz(__shfl_sync(FULL, w, hl));
+                    }
+                }
+                return -1;
+            };
+            auto low_of = [&](const uint32_t* m) -> int {
+                for (int b0 = 0; b0 < EM_TILE_WORDS; b0 += 32) {
+                    const uint32_t w = m[b0 + lane];
+                    const uint32_t bal = __ballot_sync(FULL, w != 0);
+                    if (bal) {
+                        const int ll = __ffs(bal) - 1;
+                        return (b0 + ll) * 32 + __ffs(__shfl_sync(FULL, w, ll)) - 1;
+                    }
+                }
+                return NO_POS;
+            };
+            const int ls = top_of(sh.smask), le = top_of(sh.emask);
+            int fs = NO_POS, fe = NO_POS;
+            if (info) {
+                fs = low_of(sh.smask);
+                fe = low_of(sh.emask);
+            }
+            if (lane == 0) {
+                sh.t_last_s = ls;
+                sh.t_last_e = le;
+                sh.t_first_s = fs;
+                sh.t_first_e = fe;
             }
         }
-        const uint32_t wd = dinc;  // lane 31 holds the warp total
-        if (lane == 31) {
-            sh.wsum[warp] = inc;
-            sh.wlast[warp] = wl;
-            sh.wfirst[warp] = wf;
-            sh.wfirst_end[warp] = wfe;
-            sh.wdrop[warp] = wd;
-        }
-        __syncthreads();  // (1)
-        uint32_t base = inc - pk, tot = 0, tlast = 0, tfirst = 0, tfirst_end = ~0u, ndrop = 0, myDbase = dinc - cD;
-#pragma unroll
-        for (int q = EM_WARPS - 1; q >= 0; --q) {
-            if (sh.wfirst[q]) tfirst = sh.wfirst[q];
-            if (sh.wfirst_end[q] != ~0u) tfirst_end = sh.wfirst_end[q];
-        }
+        uint32_t base = inc - pk, tot = 0;
 #pragma unroll
         for (int q = 0; q < EM_WARPS; ++q) {
-            const uint32_t ws = sh.wsum[q], wq = sh.wlast[q];
+            const uint32_t ws = sh.wsum[q];
             if (q < warp) base += ws;
             tot += ws;
-            ndrop += sh.wdrop[q];
-            if (q < warp) myDbase += sh.wdrop[q];
-            if (wq) tlast = wq;
         }
-        const uint32_t nE = tot >> 16;
-        const uint32_t mySbase = base & 0xffffu, myEbase = base >> 16;
-        const bool has = tlast != 0;
-        if (tid == 0) {
-            acc_end += nE;
-            acc_any |= tlast;
-        }
+        const uint32_t nE = tot & 0xffffu, nD = tot >> 16;
+        const uint32_t myEbase = base & 0xffffu, myDbase = base >> 16;
+        const bool carried_here = carried_pos - tile_gbase < uint64_t(EM_TILE_POS);  // the chunk's carried-in END lies in this tile
 
-        // ---- 2. warp 0: open state entering the tile (look-back #1) and, when the kept count is already
-        //         known, the output offset (look-back #2); the other warps go on to the scatter ------------
-        if (warp == 0) {
-            const uint32_t op = tlast & 0x7fffffffu;
-            if (lane == 0) {
-                if (has) desc_store(&p.desc_state[t], ST_INCLUSIVE, op ? (tile_gbase + (op - 1) + OPEN_BIAS) : OPEN_NONE);
-                else desc_store(&p.desc_state[t], ST_AGGREGATE, 0);
-            }
-            uint64_t X = lookback_state(p.desc_state, int64_t(t), p.global_off == 0 ? OPEN_NONE : OPEN_UNKNOWN, lane);
-            if (lane == 0) {
-                if (!has) desc_store(&p.desc_state[t], ST_INCLUSIVE, X);
-                if (t == p.num_tiles - 1)  // state after the whole shard
-                    p.res->open_start = has ? (op ? (tile_gbase + (op - 1) + 1) : 0) : (X >= OPEN_BIAS ? X - OPEN_BIAS + 1 : 0);
-            }
-            // nothing seen since the start of a later shard: open iff this tile begins with an END
-            if (X == OPEN_UNKNOWN && !(tfirst & 1u)) X = OPEN_NONE;
-            if (lane == 0) sh.x = X;
-            if (fast_count || nE == 0) {
-                uint32_t total = nE - ndrop;
-                uint32_t adj = 0;
-                if (nE && X != OPEN_NONE) {  // the first END closes a cluster that started before the tile: exact test
-                    uint32_t len;
-                    const bool k = X >= OPEN_BIAS && keep_len(X - OPEN_BIAS, tile_gbase + tfirst_end, p.min_len, &len);
-                    adj = k ? 0u : 1u;
-                    total -= adj;
-                }
-                if (lane == 0) sh.adj = adj;
-                if (lane == 0 && t > 0) desc_store(&p.desc_cnt[t], ST_AGGREGATE, total);
-                const uint64_t prefix = t > 0 ? lookback_sum(p.desc_cnt, int64_t(t), lane) : 0;
-                if (lane == 0) {
-                    desc_store(&p.desc_cnt[t], ST_INCLUSIVE, prefix + total);
-                    sh.prefix = prefix;
-                    sh.round_total = total;
-                    if (t == p.num_tiles - 1) p.res->n_written = prefix + total;
-                }
-            }
-        }
-        if (nE == 0) {  // nothing closes in this tile (block-uniform)
-            if (tid == 0) sh.tile = atomicAdd(&p.res->ticket, 1ull);
-            continue;
-        }
+        // START of the cluster closed by the END at tile-local position e: nearest START bit at or before e
+        auto find_start = [&](uint32_t e, bool* in_tile, bool* known) -> uint64_t {
+            int w = int(e >> 5);
+            uint32_t m = sh.smask[w] & ((2u << (e & 31)) - 1u);
+            while (!m && w > 0) m = sh.smask[--w];
+            *in_tile = m != 0;
+            *known = true;
+            if (m) return tile_gbase + uint32_t(w) * 32u + uint32_t(31 - __clz(m));
+            *known = X >= OPEN_BIAS;
+            return X - OPEN_BIAS;
+        };
 
-        // scatter of the bit positions of window [win, win + EM_CAP) into the shared lists (independent of open_in)
-        auto extract = [&](uint32_t win) {
-            if (myEbase < win + EM_CAP && myEbase + cE > win) {
-                uint32_t ord = myEbase - win;  // may wrap below 0: the unsigned compare rejects those
-                uint32_t krank = myEbase - myDbase;  // kept ENDs of the tile before mine
+        // The list holds the ENDs that will be written: all of them in EXACT mode (D = 0), the kept ones otherwise
+        // (the carried-in END counts as kept until the exchange has tested it).
+        const uint32_t nL = nE - nD, cL = cE - cD, myLbase = myEbase - myDbase;
+        if (write && !exact && nD && p.n_global - 2 - tile_gbase < uint64_t(EM_TILE_POS)) {
+            // A dropped END at position n_global - 2 still decides the reference's post-EOF phantom value.
+            const uint32_t e = uint32_t(p.n_global - 2 - tile_gbase);
+            if (tid == 0 && ((sh.emask[e >> 5] >> (e & 31)) & 1u)) {
+                bool in_tile, known;
+                const uint64_t st = find_start(e, &in_tile, &known);
+                p.res->end_nm2_start = known ? st + 1 : ~0ull;
+            }
+        }
+        for (uint32_t win = 0; win < nL; win += EM_CAP) {  // one iteration unless the tile lists > EM_CAP ENDs
+            if (win) __syncthreads();  // the previous window's list is no longer read
+            if (myLbase < win + EM_CAP && myLbase + cL > win) {
+                uint32_t ord = myLbase - win;  // may wrap below 0: the unsigned compare rejects those
 #pragma unroll
-                for (int j = 0; j < EM_WPT; ++j) {
-                    uint32_t m = E[j];
+                for (int h = 0; h < EM_WPT / 2; ++h) {
+                    unsigned long long m = (uint64_t(E[2 * h + 1] & ~D[2 * h + 1]) << 32) | (E[2 * h] & ~D[2 * h]);
                     while (m) {
-                        const int b = __ffs(m) - 1;
+                        const int b = __ffsll(m) - 1;
                         m &= m - 1;
-                        const uint32_t dropped = (D[j] >> b) & 1u;
-                        if (ord < EM_CAP) {
-                            sh.epos[ord] = uint16_t((tid * EM_WPT + j) * 32 + b);
-                            if (fast_count) sh.erank[ord] = dropped ? uint16_t(0xFFFF) : uint16_t(krank);
-                        }
-                        krank += 1u - dropped;
+                        if (ord < EM_CAP) sh.ek[ord] = uint16_t((tid * EM_WPT + 2 * h) * 32 + b);
                         ++ord;
                     }
                 }
             }
-            if (mySbase < win + EM_CAP && mySbase + cS + 1 > win) {
-                uint32_t ord = mySbase + 1 - win;  // slot 0 = START ordinal win - 1
-#pragma unroll
-                for (int j = 0; j < EM_WPT; ++j) {
-                    uint32_t m = S[j];
-                    while (m) {
-                        const int b = __ffs(m) - 1;
-                        m &= m - 1;
-                        if (ord < EM_CAP + 1) sh.spos[ord] = uint16_t((tid * EM_WPT + j) * 32 + b);
-                        ++ord;
-                    }
-                }
-            }
-        };
-
-        // dense pass over one window: one lane per END; records in registers (start | len << 48, ~0 = head END),
-        // kept mask, per-row kept counts and their exclusive scan.  Returns the kept count of the window.
-        uint64_t rec[EM_EPT];
-        uint32_t kept;
-        auto count_round = [&](uint32_t win, uint64_t X) -> uint32_t {
-            const uint32_t cntw = nE - win < EM_CAP ? nE - win : EM_CAP;
-            const uint32_t open_in = X != OPEN_NONE;
-            kept = 0;
-#pragma unroll
-            for (int i = 0; i < EM_EPT; ++i) {
-                const uint32_t q = uint32_t(tid) + uint32_t(i) * EM_THREADS;  // row = warp + EM_WARPS * i
-                rec[i] = 0;
-                if (uint32_t(i) * EM_THREADS + uint32_t(warp) * 32 < cntw) {  // warp-uniform
-                    bool k = false;
-                    if (q < cntw) {
-                        const uint64_t gend = tile_gbase + sh.epos[q];
-                        if (q == 0 && win == 0 && open_in) {
-                            if (X >= OPEN_BIAS) {
-                                uint32_t len;
-                                k = keep_len(X - OPEN_BIAS, gend, p.min_len, &len);
-                                rec[i] = (X - OPEN_BIAS) | (uint64_t(len) << 48);
-                            } else {
-                                rec[i] = ~0ull;  // the shard's head END: its START is in an earlier shard
-                            }
-                        } else {
-                            const uint64_t st = tile_gbase + sh.spos[q + 1 - open_in];
-                            uint32_t len;
-                            k = keep_len(st, gend, p.min_len, &len);
-                            rec[i] = st | (uint64_t(len) << 48);
-                        }
-                    }
-                    const uint32_t bal = __ballot_sync(FULL, k);
-                    if (lane == 0) sh.rowcnt[warp + EM_WARPS * i] = __popc(bal);
-                    kept |= uint32_t(k) << i;
-                } else if (lane == 0) {
-                    sh.rowcnt[warp + EM_WARPS * i] = 0;
-                }
-            }
-            __syncthreads();
-            if (warp == 0) {  // exclusive scan of the row counts
-                static_assert(EM_ROWS == 64, "two rows per lane");
-                const uint32_t c0 = sh.rowcnt[2 * lane], c1 = sh.rowcnt[2 * lane + 1];
-                const uint32_t s2 = c0 + c1;
-                uint32_t in2 = s2;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(FULL, in2, d);
-                    if (lane >= d) in2 += o;
-                }
-                sh.rowbase[2 * lane] = in2 - s2;
-                sh.rowbase[2 * lane + 1] = in2 - s2 + c0;
-                if (lane == 31 && !fast_count) sh.round_total = in2;
-            }
-            __syncthreads();
-            return fast_count ? 0u : sh.round_total;
-        };
-
-        // writes the kept records of the window held in rec[] at out index obase + rank
-        auto write_round = [&](uint32_t win, uint64_t obase, uint64_t tile_end_index) -> uint32_t {
-            const uint32_t cntw = nE - win < EM_CAP ? nE - win : EM_CAP;
-            uint32_t my_kept = 0;
-#pragma unroll
-            for (int i = 0; i < EM_EPT; ++i) {
-                if (uint32_t(i) * EM_THREADS + uint32_t(warp) * 32 >= cntw) continue;  // warp-uniform
-                const bool k = (kept >> i) & 1u;
-                const uint32_t bal = __ballot_sync(FULL, k);
-                const uint32_t q = uint32_t(tid) + uint32_t(i) * EM_THREADS;
-                if (q < cntw) {
-                    const uint64_t gend = tile_gbase + sh.epos[q];
-                    if (rec[i] == ~0ull) {  // head END of the shard
-                        p.res->head_end = gend + 1;
-                        if (gend + 2 == p.n_global) p.res->end_nm2_start = ~0ull;
-                    } else {
-                        const uint64_t st = rec[i] & 0xffffffffffffull;
-                        const uint32_t len = uint32_t(rec[i] >> 48);
-                        if (gend + 2 == p.n_global) p.res->end_nm2_start = st + 1;
-                        if (k) {
-                            const uint64_t o = obase + sh.rowbase[warp + EM_WARPS * i] + __popc(bal & lt_mask);
-                            if (o < p.cap) {
-                                p.out_start[o] = st;
-                                p.out_len[o] = uint16_t(len);
-                            } else {
-                                p.res->overflow = 1;
-                            }
-                            ++my_kept;
-                            acc_bases += len;
-                            if (len <= MAX_C_LEN) atomicAdd(&sh.hist[len], 1u);
-                            if (o + 1 == tile_end_index) atomicMax(&p.res->last_rec, (unsigned long long)(((o + 1) << 16) | len));
-                        }
-                    }
-                }
-            }
-            return my_kept;
-        };
-
-        extract(0);
-        __syncthreads();  // (2) lists, sh.x (and, when the count was bit-parallel, sh.prefix / sh.round_total) are ready
-        const uint64_t X = sh.x;
-        // The next ticket is taken only now: a claimed tile stays INVALID for its successors until its owner gets to
-        // it, so claiming before the look-backs are done would make every successor wait for this whole tile.
-        unsigned long long next_ticket = 0;
-        if (tid == 0) next_ticket = atomicAdd(&p.res->ticket, 1ull);
-        if constexpr (fast_count) {
-            // dense write: the rank of every kept END is already in the list, the offset in sh.prefix
-            const uint64_t prefix = sh.prefix, tile_end = prefix + sh.round_total;
-            const uint32_t open_in = X != OPEN_NONE, adj = sh.adj;
-            for (uint32_t win = 0; win < nE; win += EM_CAP) {  // one iteration unless the tile has > EM_CAP ENDs
-                if (win) {
-                    __syncthreads();  // the previous window's lists are no longer read
-                    extract(win);
-                    __syncthreads();
-                }
-                const uint32_t cntw = nE - win < EM_CAP ? nE - win : EM_CAP;
+            __syncthreads();  // (2) list
+            const uint32_t cntw = nL - win < EM_CAP ? nL - win : EM_CAP;
+            if (!exact) {
+                if (!write) continue;
+                // dense pass: one lane per kept END; its rank in the tile is its place in the list
                 for (uint32_t q = tid; q < cntw; q += EM_THREADS) {
-                    const uint64_t gend = tile_gbase + sh.epos[q];
-                    uint32_t r = sh.erank[q];
-                    uint64_t st;
-                    uint32_t len;
-                    bool k;
-                    if (q == 0 && win == 0 && open_in) {
-                        if (X < OPEN_BIAS) {  // the shard's head END: its START is in an earlier shard
+                    const uint32_t e = sh.ek[q];
+                    const uint64_t gend = tile_gbase + e;
+                    uint32_t r = win + q;
+                    bool in_tile, known;
+                    const uint64_t st = find_start(e, &in_tile, &known);
+                    uint32_t len = uint32_t(gend - st + 1) & 0xffffu;  // (no wrap unless carried in: a bit-parallel chunk has no cluster >= 65503)
+                    if (gend == carried_pos) {  // resolved by the exchange (exact wrapped-length test)
+                        if (gend + 2 == p.n_global) p.res->end_nm2_start = known ? st + 1 : ~0ull;
+                        if (!known) {           // the shard's head END: its START is in an earlier shard
                             p.res->head_end = gend + 1;
-                            if (gend + 2 == p.n_global) p.res->end_nm2_start = ~0ull;
                             continue;
                         }
-                        st = X - OPEN_BIAS;
-                        k = keep_len(st, gend, p.min_len, &len);
+                        if (adj) continue;      // not kept after all
                     } else {
-                        st = tile_gbase + sh.spos[q + 1 - open_in];
-                        len = uint32_t(gend - st + 1);  // <= 32768: no wrap inside a tile
-                        k = r != 0xFFFFu;
-                        r -= adj;
+                        if (carried_here) r -= adj;
+                        if (gend + 2 == p.n_global) p.res->end_nm2_start = st + 1;
                     }
-                    if (gend + 2 == p.n_global) p.res->end_nm2_start = st + 1;
-                    if (k) {
-                        const uint64_t o = prefix + r;
-                        if (o < p.cap) {
-                            p.out_start[o] = st;
-                            p.out_len[o] = uint16_t(len);
+                    const uint64_t o = obase + r;
+                    if (o < p.cap) {
+                        p.out_start[o] = st;
+                        p.out_len[o] = uint16_t(len);
+                    } else {
+                        p.res->overflow = 1;
+                    }
+                    acc_bases += len;
+                    if (len <= MAX_C_LEN) atomicAdd(&sh.hist[len], 1u);
+                    if (o + 1 == chunk_end) atomicMax(&p.res->last_rec, (unsigned long long)(((o + 1) << 16) | len));
+                }
+            } else if (warp == 0) {
+                // EXACT: one warp pairs, tests and ranks every END in order (min_len > 33, or a very long cluster nearby)
+                uint32_t running = sh.row_kept;
+                for (uint32_t q0 = 0; q0 < cntw; q0 += 32) {
+                    const uint32_t q = q0 + lane;
+                    bool k = false, head = false;
+                    uint64_t st = 0, gend = 0;
+                    uint32_t len = 0;
+                    if (q < cntw) {
+                        const uint32_t e = sh.ek[q];
+                        gend = tile_gbase + e;
+                        bool in_tile, known;
+                        st = find_start(e, &in_tile, &known);
+                        if (!in_tile && !resolved) k = true;  // the chunk's first END before the exchange: provisional, fixed there
+                        else if (!known) head = true;
+                        else k = keep_len(st, gend, p.min_len, &len);
+                    }
+                    const uint32_t bal = __ballot_sync(FULL, k);
+                    if (write && q < cntw) {
+                        if (head) {
+                            p.res->head_end = gend + 1;
+                            if (gend + 2 == p.n_global) p.res->end_nm2_start = ~0ull;
                         } else {
-                            p.res->overflow = 1;
+                            if (gend + 2 == p.n_global) p.res->end_nm2_start = st + 1;
+                            if (k) {
+                                const uint64_t o = obase + running + __popc(bal & ((1u << lane) - 1u));
+                                if (o < p.cap) {
+                                    p.out_start[o] = st;
+                                    p.out_len[o] = uint16_t(len);
+                                } else {
+                                    p.res->overflow = 1;
+                                }
+                                acc_bases += len;
+                                if (len <= MAX_C_LEN) atomicAdd(&sh.hist[len], 1u);
+                                if (o + 1 == chunk_end) atomicMax(&p.res->last_rec, (unsigned long long)(((o + 1) << 16) | len));
+                            }
                         }
-                        acc_bases += len;
-                        if (len <= MAX_C_LEN) atomicAdd(&sh.hist[len], 1u);
-                        if (o + 1 == tile_end) atomicMax(&p.res->last_rec, (unsigned long long)(((o + 1) << 16) | len));
                     }
+                    running += __popc(bal);
                 }
-            }
-        } else {
-            // count all windows, publish, look back, then recompute and write
-            uint32_t total = count_round(0, X);
-            for (uint32_t win = EM_CAP; win < nE; win += EM_CAP) {
-                extract(win);
-                __syncthreads();
-                total += count_round(win, X);
-            }
-            if (warp == 0) {
-                if (lane == 0 && t > 0) desc_store(&p.desc_cnt[t], ST_AGGREGATE, total);
-                const uint64_t prefix = t > 0 ? lookback_sum(p.desc_cnt, int64_t(t), lane) : 0;
-                if (lane == 0) {
-                    desc_store(&p.desc_cnt[t], ST_INCLUSIVE, prefix + total);
-                    sh.prefix = prefix;
-                    if (t == p.num_tiles - 1) p.res->n_written = prefix + total;
-                }
-            }
-            __syncthreads();
-            const uint64_t prefix = sh.prefix;
-            uint64_t obase = prefix;
-            for (uint32_t win = 0; win < nE; win += EM_CAP) {
-                if (nE > EM_CAP) {  // the lists hold the last window: rebuild (single-window tiles still hold window 0)
-                    __syncthreads();
-                    extract(win);
-                    __syncthreads();
-                    const uint32_t c = count_round(win, X);
-                    write_round(win, obase, prefix + total);
-                    obase += c;
-                } else {
-                    write_round(win, obase, prefix + total);
-                }
+                if (lane == 0) sh.row_kept = running;
             }
         }
-        if (tid == 0) sh.tile = next_ticket;
+        if (exact || nL == 0) __syncthreads();  // row_kept / warp 0's tile summary (otherwise ordered by barrier (2))
+        const uint32_t tile_kept = exact ? sh.row_kept : nL - (carried_here ? adj : 0u);
+        const int t_last_s = sh.t_last_s, t_last_e = sh.t_last_e;
+        if (info) {
+            info->last_s = t_last_s;
+            info->last_e = t_last_e;
+            info->first_s = sh.t_first_s;
+            info->first_e = sh.t_first_e;
+            info->n_end = nE;
+        }
+        if (t_last_s >= 0 || t_last_e >= 0)  // state leaving the tile
+            X = t_last_s > t_last_e ? tile_gbase + uint64_t(t_last_s) + OPEN_BIAS : OPEN_NONE;
+        return tile_kept;
+    };
+
+    // ================= pass 1 of EXACT chunks =================
+    if (exact) {
+        uint64_t X = OPEN_UNKNOWN;  // unresolved until the exchange: an END without START so far is the chunk's first END
+        bool seen = false;
+        kept_prov = 0;
+        n_end_chunk = 0;
+        first_e = first_s = ~0ull;
+        last_s = last_e = 0;
+        for (uint64_t t = t_lo; t < t_hi; ++t) {
+            TileInfo ti;
+            kept_prov += tile_pass(t, X, seen, 0, false, ~0ull, 0, ~0ull, &ti);
+            const uint64_t tile_gbase = p.global_off + t * uint64_t(EM_TILE_POS);
+            n_end_chunk += ti.n_end;
+            if (ti.last_s >= 0) last_s = tile_gbase + uint64_t(ti.last_s) + 1;
+            if (ti.last_e >= 0) last_e = tile_gbase + uint64_t(ti.last_e) + 1;
+            if (first_e == ~0ull && ti.first_e != NO_POS) first_e = tile_gbase + uint64_t(ti.first_e);
+            if (first_s == ~0ull && ti.first_s != NO_POS) first_s = tile_gbase + uint64_t(ti.first_s);
+            if (ti.last_s >= 0 || ti.last_e >= 0) seen = true;
+        }
+    }
+
+    // ================= exchange =================
+    if (p.dbg && tid == 0) p.dbg[c * 4 + 1] = global_ns();
+    if (warp == 0) {
+        if (lane == 0) {
+            my_desc[CD_FIRST_E] = first_e;
+            my_desc[CD_FIRST_S] = first_s;
+            my_desc[CD_LAST_S] = last_s;
+            my_desc[CD_LAST_E] = last_e;
+            st_release(&my_desc[CD_A], CD_VALID | kept_prov);
+        }
+        // open state entering the chunk: the nearest earlier chunk that has any event decides
+        uint64_t X = p.global_off == 0 ? OPEN_NONE : OPEN_UNKNOWN;
+        for (int64_t j = int64_t(c) - 1; j >= 0; --j) {
+            const uint64_t* d = p.desc + uint64_t(j) * EM_DESC_WORDS;
+            wait_valid(d + CD_A);
+            const uint64_t ls = desc_load(d + CD_LAST_S), le = desc_load(d + CD_LAST_E);
+            if (ls | le) {
+                X = ls > le ? (ls - 1) + OPEN_BIAS : OPEN_NONE;
+                break;
+            }
+        }
+        // the chunk's first END closes a cluster opened before the chunk iff no START precedes it in the chunk
+        const bool carried = first_e != ~0ull && (first_s == ~0ull || first_e < first_s);
+        if (X == OPEN_UNKNOWN && !carried && (first_e != ~0ull || first_s != ~0ull)) X = OPEN_NONE;  // the chunk starts with a START
+        uint32_t adj = 0;
+        if (carried) {
+            uint32_t len;
+            const bool k = X >= OPEN_BIAS && keep_len(X - OPEN_BIAS, first_e, p.min_len, &len);
+            adj = k ? 0u : 1u;
+        }
+        const uint64_t kept_final = kept_prov - adj;
+        if (lane == 0) st_release(&my_desc[CD_B], CD_VALID | kept_final);
+        // records kept by the chunks before mine
+        uint64_t acc = 0;
+        for (int64_t j0 = int64_t(c) - 1 - lane; j0 >= 0; j0 -= 32 * 4) {  // 4 loads in flight per lane; the count sits in the polled word
+            uint64_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t j = j0 - 32 * u;
+                v[u] = j >= 0 ? desc_load(p.desc + uint64_t(j) * EM_DESC_WORDS + CD_B) : CD_VALID;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t j = j0 - 32 * u;
+                while (!(v[u] & CD_VALID)) {
+                    __nanosleep(40);
+                    v[u] = desc_load(p.desc + uint64_t(j) * EM_DESC_WORDS + CD_B);
+                }
+                acc += v[u] & ~CD_VALID;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        if (lane == 0) {
+            sh.x_in = X;
+            sh.prefix = acc;
+            sh.adj = adj;
+            sh.carried_pos = carried ? first_e : ~0ull;
+            sh.red[0] = kept_final;
+            atomicAdd(&p.res->n_written, (unsigned long long)kept_final);
+            if (n_end_chunk) atomicAdd(&p.res->n_end, n_end_chunk);
+            if (last_s | last_e) atomicOr(&p.res->any_event, 1ull);
+        }
+    }
+    __syncthreads();
+
+    // ================= pass 2 =================
+    if (p.dbg && tid == 0) p.dbg[c * 4 + 2] = global_ns();
+    {
+        uint64_t X = sh.x_in, obase = sh.prefix;
+        const uint64_t chunk_end = sh.prefix + sh.red[0], carried_pos = sh.carried_pos;
+        const uint32_t adj = sh.adj;
+        for (uint64_t t = t_lo; t < t_hi; ++t) obase += tile_pass(t, X, true, obase, true, carried_pos, adj, chunk_end, nullptr);
+        if (c == n_chunks - 1 && tid == 0)  // state after the whole shard
+            p.res->open_start = X >= OPEN_BIAS ? X - OPEN_BIAS + 1 : 0;
     }
 
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc_bases += __shfl_xor_sync(FULL, acc_bases, d);
     if (lane == 0 && acc_bases) atomicAdd(&p.res->n_bases, acc_bases);
-    if (tid == 0) {
-        if (acc_end) atomicAdd(&p.res->n_end, acc_end);
-        if (acc_any) atomicOr(&p.res->any_event, 1ull);
-    }
     __syncthreads();
     for (int i = tid; i < E2S_HIST_BINS; i += EM_THREADS)
         if (sh.hist[i]) atomicAdd(&p.res->hist[i], (unsigned long long)sh.hist[i]);
-    if (blockIdx.x == 0 && tid == 0 && p.tail_lcp) {
+    if (p.dbg && tid == 0) p.dbg[c * 4 + 3] = global_ns();
+    if (c == 0 && tid == 0 && p.tail_lcp) {
         p.res->tail_lcp_nm2 = p.tail_lcp[0];
         p.res->tail_lcp_nm1 = p.tail_lcp[1];
         p.res->tail_bwt_nm1 = p.tail_bwt[0];
@@ -803,18 +861,18 @@ cudaError_t launch_flags(const FlagParams& p, uint64_t rows_alloc32, int sm_coun
     }
 }
 
+uint64_t emit_desc_words() { return uint64_t(EM_MAX_CHUNKS) * EM_DESC_WORDS; }
+
 cudaError_t launch_emit(const EmitParams& p0, int sm_count, cudaStream_t stream) {
     EmitParams p = p0;
-    const bool fast = p.min_len <= 33;
     int occ = 0;
-    cudaError_t e = fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_emit<true>, EM_THREADS, 0)
-                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_emit<false>, EM_THREADS, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_emit, EM_THREADS, 0);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    uint64_t grid = uint64_t(sm_count) * occ;
+    uint64_t grid = uint64_t(sm_count) * occ;  // one chunk per CTA
     if (grid > p.num_tiles) grid = p.num_tiles;
-    if (fast) k_cluster_emit<true><<<dim3(unsigned(grid)), dim3(EM_THREADS), 0, stream>>>(p);
-    else k_cluster_emit<false><<<dim3(unsigned(grid)), dim3(EM_THREADS), 0, stream>>>(p);
+    if (grid > EM_MAX_CHUNKS) grid = EM_MAX_CHUNKS;
+    k_cluster_emit<<<dim3(unsigned(grid)), dim3(EM_THREADS), 0, stream>>>(p);
     return cudaGetLastError();
 }
 

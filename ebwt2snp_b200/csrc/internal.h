@@ -64,8 +64,8 @@ struct EmitParams {  // K2
     uint64_t* out_start;
     uint16_t* out_len;
     uint64_t cap;
-    uint64_t* desc_state;
-    uint64_t* desc_cnt;
+    uint64_t* desc;      // chunk descriptors (emit_desc_words() words, zeroed before the launch)
+    uint64_t* dbg;       // optional: 4 globaltimer stamps per chunk (start, pass 1 done, exchange done, end); null = off
     ClusterDev* res;
     const uint32_t* tail_lcp;  // &lcp[n_global-2] when this is the last shard, else null
     const uint8_t* tail_bwt;   // &bwt[n_global-1]
@@ -73,6 +73,7 @@ struct EmitParams {  // K2
 
 uint64_t flags_words_needed(uint64_t n_local);
 uint64_t emit_num_tiles(uint64_t n_local);
+uint64_t emit_desc_words();
 cudaError_t launch_flags(const FlagParams& p, uint64_t rows_alloc32, int sm_count, cudaStream_t stream, int variant);
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
 // small helpers: append up to 3 records to the device list / pack the list into 10-byte file records
