@@ -96,6 +96,54 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(local, torch):
+    """Host staging buffers should live on the GPU's NUMA node: a pinned buffer on the far socket costs 2-4x of the
+    PCIe rate (seen as 12-21 GB/s instead of 54 GB/s on some boxes).  Prefer that node for this process' memory
+    (set_mempolicy MPOL_PREFERRED) and, when the container allows it, run on its CPUs."""
+    info = {"gpu_node": None, "cpus_bound": False, "mempolicy": False}
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info["gpu_node"] = node
+        if node < 0:
+            return info
+        try:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus |= set(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["cpus_bound"] = True
+        except Exception:
+            pass
+        try:
+            libc = C.CDLL(None, use_errno=True)
+            mask = C.c_ulong(1 << node)
+            rc = libc.syscall(238, 1, C.byref(mask), C.c_ulong(64))  # set_mempolicy(MPOL_PREFERRED, {node})
+            info["mempolicy"] = rc == 0
+        except Exception:
+            pass
+    except Exception:
+        pass
+    return info
+
+
+def h2d_probe(torch, dev, mb=1024):
+    """pinned host -> device copy rate of this box right now (GB/s), for reading the e2e number"""
+    a = torch.empty(mb << 20, dtype=torch.uint8, pin_memory=True)
+    b = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
+    b.copy_(a, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        b.copy_(a, non_blocking=True)
+    torch.cuda.synchronize()
+    return 2 * a.numel() / (time.perf_counter() - t0) / 1e9
+
+
 # --------------------------------------------------------------------------------------------
 # data
 # --------------------------------------------------------------------------------------------
@@ -269,6 +317,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local, torch)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
@@ -410,7 +459,9 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        probe = h2d_probe(torch, dev)
         e2e = {"value": n_global * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(res.h2d_bytes),
+               "h2d_probe_GBps": probe, "numa": numa,
                "d2h_bytes_per_step": int(res.d2h_bytes), "ms_per_step": 1e3 * dt / args.e2e_steps,
                "steps": args.e2e_steps, "api": "e2s_pipeline_host (13-byte .gesa records + reads in, .clusters records + events out)",
                "h2d_GBps": res.h2d_bytes * args.e2e_steps / dt / 1e9,

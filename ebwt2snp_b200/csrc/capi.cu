@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <string>
 #include <vector>
@@ -26,6 +27,7 @@ struct e2s_ctx {
     uint8_t* d_bases = nullptr;
     uint64_t* d_off = nullptr;
     uint64_t n_reads = 0, n_bases = 0;
+    uint64_t reads_cap_bases = 0, reads_cap_off = 0;
     bool reads_owned = false;
     // staging: two raw-record buffers, the H2D copies run on their own stream ahead of the de-interleave kernels
     uint8_t* d_raw[2] = {nullptr, nullptr};
@@ -67,6 +69,7 @@ struct e2s_shard {
     uint8_t* d_packed = nullptr;
     uint64_t packed_cap = 0;
     unsigned long long* d_hist = nullptr;
+    uint32_t* d_bwt_flag = nullptr;  // != 0: the BWT holds bytes the bit-sliced base code does not cover (set at seal)
     int variant = 0;
     // phase 2
     SnpWork* work = nullptr;
@@ -219,6 +222,7 @@ int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->bwt_a), ne);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_res), sizeof(ClusterDev));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_hist), (E2S_HIST_BINS + 1) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_bwt_flag), 4);
     if (e != cudaSuccess) {
         e2s_shard_destroy(s);
         return fail(c, E2S_ERR_NOMEM, std::string("shard allocation: ") + cudaGetErrorString(e));
@@ -257,6 +261,7 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFreeHost(s->h_pin);
     cudaFree(s->d_res);
     cudaFree(s->d_hist);
+    cudaFree(s->d_bwt_flag);
     snp_work_destroy(s->work);
     if (s->ctx->cached == s) s->ctx->cached = nullptr;
     delete s;
@@ -369,6 +374,9 @@ int e2s_shard_seal(e2s_shard* s) {
                                   s->lay_bcr, c->stream));
         ++c->launches;
     }
+    // which plane builder K3a may use: one streaming look at the shard's BWT bytes (incl. the right halo / phantom)
+    CU(c, launch_bwt_alphabet(s->bwt, s->n_local + HALO_R, s->d_bwt_flag, c->stream, c->sm_count));
+    ++c->launches;
     s->sealed = true;
     return E2S_OK;
 }
@@ -376,17 +384,22 @@ int e2s_shard_seal(e2s_shard* s) {
 int e2s_reads_stage(e2s_ctx* c, const uint8_t* bases, const uint64_t* off, uint64_t n_reads) {
     if (!c || !bases || !off) return fail(c, E2S_ERR_ARG, "e2s_reads_stage: NULL argument");
     CU(c, cudaSetDevice(c->device));
-    if (c->reads_owned) {
-        cudaFree(c->d_bases);
-        cudaFree(c->d_off);
-    }
-    c->d_bases = nullptr;
-    c->d_off = nullptr;
-    c->reads_owned = true;
     const uint64_t nb = off[n_reads];
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->d_bases), nb + 16);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->d_off), (n_reads + 1) * 8);
-    if (e != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "reads allocation");
+    if (!c->reads_owned || nb + 16 > c->reads_cap_bases || (n_reads + 1) > c->reads_cap_off) {  // reuse the buffers when they fit
+        if (c->reads_owned) {
+            cudaFree(c->d_bases);
+            cudaFree(c->d_off);
+        }
+        c->d_bases = nullptr;
+        c->d_off = nullptr;
+        c->reads_owned = true;
+        c->reads_cap_bases = c->reads_cap_off = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->d_bases), nb + 16);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->d_off), (n_reads + 1) * 8);
+        if (e != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "reads allocation");
+        c->reads_cap_bases = nb + 16;
+        c->reads_cap_off = n_reads + 1;
+    }
     CU(c, cudaMemcpyAsync(c->d_bases, bases, nb, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     c->n_reads = n_reads;
@@ -401,6 +414,7 @@ int e2s_reads_stage_dev(e2s_ctx* c, const uint8_t* d_bases, const uint64_t* d_of
         cudaFree(c->d_off);
     }
     c->reads_owned = false;
+    c->reads_cap_bases = c->reads_cap_off = 0;
     c->d_bases = const_cast<uint8_t*>(d_bases);
     c->d_off = const_cast<uint64_t*>(d_off);
     c->n_reads = n_reads;
@@ -891,6 +905,7 @@ int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length,
     a.text = s->text;
     a.suff = s->suff;
     a.bwt = s->bwt;
+    a.bwt_not_simple = s->d_bwt_flag;
     a.n_local = s->n_local;
     a.global_off = s->global_off;
     a.cl_start = s->d_start;
@@ -988,6 +1003,18 @@ int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, in
                       void* rec10, uint64_t cap_records, e2s_event* events, uint64_t cap_events, e2s_pipeline_result* res) {
     if (!c || !gesa || !p || !res) return fail(c, E2S_ERR_ARG, "NULL argument");
     memset(res, 0, sizeof *res);
+    // developer aid: E2S_PIPELINE_DEBUG=1 prints the wall time of every stage (with a stream sync after each)
+    const bool dbg = getenv("E2S_PIPELINE_DEBUG") != nullptr;
+    struct timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    auto lap = [&](const char* what) {
+        if (!dbg) return;
+        cudaStreamSynchronize(c->stream);
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "[e2s_pipeline_host] %-28s %9.3f ms\n", what, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+        t0 = t1;
+    };
     int rc;
     e2s_shard* s = c->cached;
     if (!s || s->n_local != n || s->n_global != n) {
@@ -997,16 +1024,25 @@ int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, in
         if (rc) return rc;
         c->cached = s;
     }
+    lap("shard (cached after 1st call)");
     const int rs = x + y + z + 1;
     if ((rc = e2s_shard_load_gesa(s, gesa, 0, n, x, y, z))) return rc;
     if ((rc = e2s_shard_seal(s))) return rc;
     res->h2d_bytes += n * uint64_t(rs);
+    lap("H2D records + de-interleave");
+    if (read_bases) {  // queued behind the records on the copy engine; the kernels below do not wait for it
+        if ((rc = e2s_reads_stage(c, read_bases, read_off, n_reads))) return rc;
+        res->h2d_bytes += read_off[n_reads] + (n_reads + 1) * 8;
+    }
+    lap("H2D reads");
     if ((rc = e2s_cluster_lm(s, k, min_len, &res->n_written, &res->n_clust_out))) return rc;
+    lap("K1 + K2 + merge");
     if (rec10) {
         uint64_t m = 0;
         if ((rc = e2s_cluster_fetch_packed(s, rec10, cap_records, &m))) return rc;
         res->d2h_bytes += m * 10;
     }
+    lap("pack + D2H .clusters records");
     if (res->n_written == 0) return fail(c, E2S_ERR_UNSUPPORTED, "no clusters (the reference divides by zero here)");
     e2s_stats st;
     if ((rc = e2s_statistics(s, &st))) return rc;
@@ -1015,16 +1051,14 @@ int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, in
         return rc;
     }
     res->max_clust_length = st.max_clust_length;
-    if (read_bases) {
-        if ((rc = e2s_reads_stage(c, read_bases, read_off, n_reads))) return rc;
-        res->h2d_bytes += read_off[n_reads] + (n_reads + 1) * 8;
-    }
     if ((rc = e2s_find_events(s, p, st.max_clust_length, &res->snp))) return rc;
     res->d2h_bytes += res->snp.n_candidates * 128;
+    lap("statistics + K3 + K4");
     if (events) {
         uint64_t nv = 0;
         if ((rc = e2s_events_fetch(s, events, cap_events, &nv))) return rc;
     }
+    lap("events to caller");
     return E2S_OK;
 }
 

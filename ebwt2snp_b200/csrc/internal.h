@@ -109,6 +109,7 @@ struct SnpArrays {
     const uint32_t* text;
     const uint32_t* suff;
     const uint8_t* bwt;   // all: local position 0
+    const uint32_t* bwt_not_simple;  // device flag written at seal (k_bwt_alphabet): 0 = the bit-sliced base code is exact; may be null
     uint64_t n_local, global_off;
     const uint64_t* cl_start;  // global starts, sorted
     const uint16_t* cl_len;
@@ -124,6 +125,7 @@ struct CandSlot {  // one (flagged cluster, allele pair) slot written by K3b
     // followed in the slot arrays by idx/pos lists (see snp.cu)
 };
 
+cudaError_t launch_bwt_alphabet(const uint8_t* bwt, uint64_t count, uint32_t* flag, cudaStream_t stream, int sm_count);
 cudaError_t launch_len_hist(const uint16_t* len, uint64_t m, unsigned long long* hist /*151 + n_bases*/,
                             cudaStream_t stream, int sm_count);
 cudaError_t launch_check_sorted(const uint64_t* start, const uint16_t* len, uint64_t m, SnpDev* dev,

@@ -101,7 +101,8 @@ struct ScanParams {
     uint32_t num_tiles;
     uint32_t min_len, max_len;   // 2*mcov_out, max_clust_length
     uint32_t mcov;
-    uint32_t* flag_words;        // out: bit per cluster = needs the exact test
+    uint64_t* survivors;         // out: clusters that need the exact test (unordered; dev->n_survivors counts them)
+    uint64_t cap_surv;
     SnpDev* dev;
 };
 
@@ -126,6 +127,47 @@ __device__ __forceinline__ uint32_t eq_bytes(uint32_t u, uint32_t pat) {
 }
 // four byte flags (0x80 each) -> 4 bits
 __device__ __forceinline__ uint32_t nibble(uint32_t f) { return (((f >> 7) * 0x01020408u) >> 24) & 0xFu; }
+
+// Bit-sliced base code of four bytes, valid for the bytes k_bwt_alphabet accepts: with u = byte & 0xDF,
+//   bit 1 of the code (G, T) = u.bit2 & u.bit6        bit 0 (C, T) = (u.bit1 & ~u.bit2) | u.bit4
+// (A = 0x41, C = 0x43, G = 0x47, T = 0x54; '$' = 0x24 and NUL give 0 like every non-ACGT byte must).  Result: bit 0 of each byte.
+__device__ __forceinline__ uint32_t fast_b1(uint32_t w) {
+    const uint32_t u = w & 0xDFDFDFDFu;
+    return (u >> 2) & (u >> 6) & 0x01010101u;
+}
+__device__ __forceinline__ uint32_t fast_b0(uint32_t w) {
+    const uint32_t u = w & 0xDFDFDFDFu;
+    return (((u >> 1) & ~(u >> 2)) | (u >> 4)) & 0x01010101u;
+}
+
+// Runs once when a shard is sealed: *flag != 0 iff some BWT byte's exact base code (base_code) differs from the
+// bit-sliced one above, in which case K3a keeps the per-byte equality tests.
+__global__ void __launch_bounds__(256) k_bwt_alphabet(const uint8_t* __restrict__ bwt, uint64_t count, uint32_t* flag) {
+    bool bad = false;
+    for (uint64_t i = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 16; i < count; i += uint64_t(gridDim.x) * blockDim.x * 16) {
+        const uint4 q = *reinterpret_cast<const uint4*>(bwt + i);  // the arrays are padded: a 16-byte read never leaves the allocation
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t f0 = fast_b0(w[j]), f1 = fast_b1(w[j]);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (i + 4 * j + b < count) {
+                    const uint32_t code = base_code((w[j] >> (8 * b)) & 0xffu);
+                    bad |= code != (((f0 >> (8 * b)) & 1u) | (((f1 >> (8 * b)) & 1u) << 1));
+                }
+            }
+        }
+    }
+    if (bad) *flag = 1u;
+}
+
+cudaError_t launch_bwt_alphabet(const uint8_t* bwt, uint64_t count, uint32_t* flag, cudaStream_t stream, int sm_count) {
+    cudaError_t e = cudaMemsetAsync(flag, 0, 4, stream);
+    if (e != cudaSuccess) return e;
+    k_bwt_alphabet<<<unsigned(sm_count) * 8, 256, 0, stream>>>(bwt, count, flag);
+    return cudaGetLastError();
+}
 
 __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -152,6 +194,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
     }
     const uint32_t* w0 = reinterpret_cast<const uint32_t*>(s_b0);
     const uint32_t* w1 = reinterpret_cast<const uint32_t*>(s_b1);
+    const bool simple = p.a.bwt_not_simple && *p.a.bwt_not_simple == 0;  // block-uniform
 
     unsigned long long n_analysed = 0;
     uint32_t it = 0;
@@ -171,19 +214,36 @@ __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
         }
         mbar_wait(&full_bar[stage], parity);
         // ---- bit planes of the base code: A=00 C=01 G=10 T=11, everything else 00 ----
-        for (int ch = tid; ch < PS_CHUNKS; ch += PS_THREADS) {
-            const uint4 q = lds128(st + ch * 16);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-            uint32_t b0 = 0, b1 = 0;
+        if (simple) {
+            // the shard's BWT was proven (k_bwt_alphabet, at seal) to hold only bytes on which the code is a plain
+            // function of four bits of the case-folded byte (ACGT, acgt, '$', NUL, ...): no per-byte equality tests
+            for (int ch = tid; ch < PS_CHUNKS; ch += PS_THREADS) {
+                const uint4 q = lds128(st + ch * 16);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                uint32_t b0 = 0, b1 = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t u = w[j] & 0xDFDFDFDFu;  // case-insensitive
-                const uint32_t eC = eq_bytes(u, 0x43434343u), eG = eq_bytes(u, 0x47474747u), eT = eq_bytes(u, 0x54545454u);
-                b0 |= nibble(eC | eT) << (4 * j);
-                b1 |= nibble(eG | eT) << (4 * j);
+                for (int j = 0; j < 4; ++j) {
+                    b0 |= ((fast_b0(w[j]) * 0x01020408u) >> 24) << (4 * j);
+                    b1 |= ((fast_b1(w[j]) * 0x01020408u) >> 24) << (4 * j);
+                }
+                s_b0[ch] = uint16_t(b0);
+                s_b1[ch] = uint16_t(b1);
             }
-            s_b0[ch] = uint16_t(b0);
-            s_b1[ch] = uint16_t(b1);
+        } else {
+            for (int ch = tid; ch < PS_CHUNKS; ch += PS_THREADS) {
+                const uint4 q = lds128(st + ch * 16);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                uint32_t b0 = 0, b1 = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t u = w[j] & 0xDFDFDFDFu;  // case-insensitive
+                    const uint32_t eC = eq_bytes(u, 0x43434343u), eG = eq_bytes(u, 0x47474747u), eT = eq_bytes(u, 0x54545454u);
+                    b0 |= nibble(eC | eT) << (4 * j);
+                    b1 |= nibble(eG | eT) << (4 * j);
+                }
+                s_b0[ch] = uint16_t(b0);
+                s_b1[ch] = uint16_t(b1);
+            }
         }
         __syncthreads();  // planes complete; the byte tile is no longer needed
         if (tid == 0) {
@@ -215,7 +275,10 @@ __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
                 const uint32_t nA = c_len - nC - nG - nT;
                 const uint32_t frequent = uint32_t(nA >= p.mcov) + uint32_t(nC >= p.mcov) + uint32_t(nG >= p.mcov) +
                                           uint32_t(nT >= p.mcov);
-                if (frequent >= 2) atomicOr(&p.flag_words[c >> 5], 1u << (c & 31));
+                if (frequent >= 2) {  // rare (variants, repeats): plain atomic append, the exact test does not need an order
+                    const unsigned long long at = atomicAdd(&p.dev->n_survivors, 1ull);
+                    if (at < p.cap_surv) p.survivors[at] = c;
+                }
             }
             c = cn;
             c_start = n_start;
@@ -293,63 +356,81 @@ __global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
 constexpr int FC_THREADS = 256;
 constexpr int FC_WORDS = 4096;  // words per block
 
-__global__ void __launch_bounds__(FC_THREADS) k_flag_count(const uint32_t* __restrict__ words, uint64_t n_words,
-                                                           uint32_t* __restrict__ block_sum) {
-    __shared__ uint32_t s[FC_THREADS / 32];
-    const uint64_t w0 = uint64_t(blockIdx.x) * FC_WORDS;
+// One launch: every block counts the set bits of its FC_WORDS words, publishes the count, sums the counts of the
+// blocks before it (they do not depend on anything, so there is no chain) and writes the indices of its set bits in
+// ascending order.  Block ids come from a ticket, so a block only ever waits for blocks that are already running.
+// sync[0] = ticket, sync[1 + b] = VALID | count of block b   (zeroed by the caller)
+constexpr unsigned long long FC_VALID = 1ull << 63;
+
+__global__ void __launch_bounds__(FC_THREADS) k_flag_compact(const uint32_t* __restrict__ words, uint64_t n_words,
+                                                             unsigned long long* sync, uint64_t* __restrict__ out_idx,
+                                                             uint64_t cap, unsigned long long* out_count) {
+    __shared__ unsigned long long s_bid, s_base;
+    __shared__ uint32_t s_w[FC_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        s_bid = atomicAdd(&sync[0], 1ull);
+        s_base = 0;
+    }
+    __syncthreads();
+    const uint64_t bid = s_bid, w0 = bid * FC_WORDS;
+    uint32_t wv[FC_WORDS / FC_THREADS];
     uint32_t c = 0;
-    for (uint32_t i = threadIdx.x; i < FC_WORDS; i += FC_THREADS)
-        if (w0 + i < n_words) c += __popc(words[w0 + i]);
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+#pragma unroll
+    for (int r = 0; r < FC_WORDS / FC_THREADS; ++r) {
+        const uint64_t wi = w0 + uint64_t(r) * FC_THREADS + threadIdx.x;
+        wv[r] = wi < n_words ? words[wi] : 0u;
+        c += __popc(wv[r]);
+    }
+    c = __reduce_add_sync(FULL, c);
+    if (lane == 0) s_w[warp] = c;
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t tot = 0;
-        for (int i = 0; i < FC_THREADS / 32; ++i) tot += s[i];
-        block_sum[blockIdx.x] = tot;
+        for (int i = 0; i < FC_THREADS / 32; ++i) tot += s_w[i];
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&sync[1 + bid]), "l"(FC_VALID | tot) : "memory");
     }
-}
-
-__global__ void __launch_bounds__(FC_THREADS) k_flag_emit(const uint32_t* __restrict__ words, uint64_t n_words,
-                                                          const uint32_t* __restrict__ block_sum,
-                                                          uint64_t* __restrict__ out_idx, uint64_t cap,
-                                                          unsigned long long* out_count) {
-    __shared__ uint64_t s_base;
-    __shared__ uint32_t s_red[FC_THREADS / 32];
-    __shared__ uint32_t s_w[FC_THREADS / 32];
-    // my block's exclusive prefix = sum of the preceding block sums
-    uint64_t part = 0;
-    for (uint32_t i = threadIdx.x; i < blockIdx.x; i += FC_THREADS) part += block_sum[i];
+    // counts of the blocks before mine
+    unsigned long long part = 0;
+    for (uint64_t i = threadIdx.x; i < bid; i += FC_THREADS) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&sync[1 + i]) : "memory");
+        } while (!(v & FC_VALID));
+        part += v & ~FC_VALID;
+    }
+#pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = uint32_t(part);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint64_t b = 0;
-        for (int i = 0; i < FC_THREADS / 32; ++i) b += s_red[i];
-        s_base = b;
-        if (blockIdx.x == gridDim.x - 1) *out_count = b + block_sum[blockIdx.x];
-    }
+    if (lane == 0 && part) atomicAdd(&s_base, part);
     __syncthreads();
     uint64_t base = s_base;
-    const uint64_t w0 = uint64_t(blockIdx.x) * FC_WORDS;
-    for (uint32_t r = 0; r < FC_WORDS / FC_THREADS; ++r) {
-        const uint64_t wi = w0 + r * FC_THREADS + threadIdx.x;
-        uint32_t w = wi < n_words ? words[wi] : 0;
-        uint32_t c = __popc(w), inc = c;
+    if (bid == gridDim.x - 1 && threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int i = 0; i < FC_THREADS / 32; ++i) tot += s_w[i];
+        *out_count = base + tot;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < FC_WORDS / FC_THREADS; ++r) {
+        const uint64_t wi = w0 + uint64_t(r) * FC_THREADS + threadIdx.x;
+        uint32_t w = wv[r];
+        const uint32_t cw = __popc(w);
+        uint32_t inc = cw;
+#pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(FULL, inc, d);
-            if ((threadIdx.x & 31) >= d) inc += o;
+            const uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += o;
         }
-        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+        if (lane == 31) s_w[warp] = inc;
         __syncthreads();
-        uint32_t off = inc - c, tot = 0;
+        uint32_t off = inc - cw, tot = 0;
         for (int i = 0; i < FC_THREADS / 32; ++i) {
-            if (i < int(threadIdx.x >> 5)) off += s_w[i];
+            if (i < warp) off += s_w[i];
             tot += s_w[i];
         }
         uint64_t o = base + off;
         while (w) {
-            int b = __ffs(w) - 1;
+            const int b = __ffs(w) - 1;
             w &= w - 1;
             if (o < cap) out_idx[o] = wi * 32 + b;  // the caller compares *out_count with cap and retries if it was too small
             ++o;
@@ -526,10 +607,13 @@ struct EventParams {
 };
 
 constexpr int EV_WARPS = 4;
+constexpr int EV_B = 8;  // reads gathered per batch
+constexpr int EV_REC_MAX = 32 + 3 * E2S_MAX_K;  // packed record: header + left0 + left1 + right, stride is a multiple of 16
 
 __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
     __shared__ uint64_t s_base[EV_WARPS][MAX_C_LEN];
     __shared__ char s_cons[EV_WARPS][2][E2S_MAX_K];
+    __shared__ __align__(16) uint8_t s_rec[EV_WARPS][EV_REC_MAX];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t n_cand = *p.n_cand;
     for (uint64_t c = uint64_t(blockIdx.x) * EV_WARPS + w; c < n_cand; c += uint64_t(gridDim.x) * EV_WARPS) {
@@ -559,26 +643,44 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
         __syncwarp();
         if (bad) break;
         // cons::increment, ref:include.hpp:349-358: lane i owns context positions i, i+32, ...
+        // (the gathers are issued EV_B reads at a time so that their latencies overlap; the updates stay in list order)
         for (int i = lane; i < kl; i += 32) {
-            uint32_t cnt[4] = {0, 0, 0, 0};
+            uint32_t cnt = 0;  // four 8-bit counters (<= 150 reads), one per base code
             uint32_t cur = 'A';
-            for (uint32_t j = 0; j < nr; ++j) {
-                const uint32_t ch = p.bases[s_base[w][j] + i];
-                saw_n |= is_n(ch);
-                const uint32_t b = base_code(ch);
-                cnt[b]++;
-                if (cnt[b] > cnt[base_code(cur)]) cur = ch;
+            for (uint32_t j0 = 0; j0 < nr; j0 += EV_B) {
+                uint32_t ch[EV_B];
+#pragma unroll
+                for (int u = 0; u < EV_B; ++u) ch[u] = j0 + u < nr ? p.bases[s_base[w][j0 + u] + i] : 0u;
+#pragma unroll
+                for (int u = 0; u < EV_B; ++u) {
+                    if (j0 + u < nr) {
+                        saw_n |= is_n(ch[u]);
+                        const uint32_t b = base_code(ch[u]);
+                        cnt += 1u << (8 * b);
+                        if (((cnt >> (8 * b)) & 0xffu) > ((cnt >> (8 * base_code(cur))) & 0xffu)) cur = ch[u];
+                    }
+                }
             }
             s_cons[w][s][i] = char(cur);
         }
         __syncwarp();
         // support: reads within max_err mismatches of the consensus, ref:clust2snp.cpp:556-567
         int sp = 0;
-        for (uint32_t j = 0; j < nr; ++j) {
-            int d = 0;
-            for (int i = lane; i < kl; i += 32) d += (uint8_t(s_cons[w][s][i]) != p.bases[s_base[w][j] + i]);
-            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
-            sp += (d <= p.max_err);
+        for (uint32_t j0 = 0; j0 < nr; j0 += EV_B) {
+            int d[EV_B];
+#pragma unroll
+            for (int u = 0; u < EV_B; ++u) d[u] = 0;
+            for (int i = lane; i < kl; i += 32) {
+                const uint8_t c = uint8_t(s_cons[w][s][i]);
+#pragma unroll
+                for (int u = 0; u < EV_B; ++u)
+                    if (j0 + u < nr) d[u] += (c != p.bases[s_base[w][j0 + u] + i]);
+            }
+#pragma unroll
+            for (int u = 0; u < EV_B; ++u) {
+                for (int o = 16; o > 0; o >>= 1) d[u] += __shfl_xor_sync(FULL, d[u], o);
+                sp += (j0 + u < nr && d[u] <= p.max_err);
+            }
         }
         supp[s] = sp;
         __syncwarp();
@@ -589,7 +691,9 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
     }
     if (__any_sync(FULL, saw_n) && lane == 0) atomicOr(&p.dev->saw_n, 1ull);
 
-    uint8_t* o = p.out + c * p.stride;
+    // the record is assembled in shared memory and leaves the SM as whole 16-byte vectors: the destination is pinned
+    // HOST memory, where byte-sized stores would each become a PCIe transaction
+    uint8_t* o = s_rec[w];
     PackedEventHdr* oh = reinterpret_cast<PackedEventHdr*>(o);
     char* o_l0 = reinterpret_cast<char*>(o + sizeof(PackedEventHdr));
     char* o_l1 = o_l0 + kl;
@@ -660,6 +764,12 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
         if (variant) atomicAdd(&p.dev->n_variants, 1ull);
         if (variant && D <= p.max_snvs) atomicAdd(&p.dev->n_events, 1ull);
     }
+    __syncwarp();
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(s_rec[w]);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + c * p.stride);
+        for (uint32_t i = lane; i < p.stride / 16; i += 32) dst[i] = src[i];
+    }
     }
 }
 
@@ -668,8 +778,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
 // ---------------------------------------------------------------------------------------------
 struct SnpWork {
     uint64_t* tile_first = nullptr; size_t tile_first_cap = 0;
-    uint32_t* flag_words = nullptr; size_t flag_cap = 0;
-    uint32_t* block_sum = nullptr; size_t block_sum_cap = 0;
+    unsigned long long* fc_sync = nullptr; size_t fc_sync_cap = 0;
     uint32_t* flag_words2 = nullptr; size_t flag2_cap = 0;
     uint64_t* survivors = nullptr; size_t survivors_cap = 0;
     uint64_t* flagged = nullptr; size_t flagged_cap = 0;
@@ -692,7 +801,7 @@ SnpWork* snp_work_create() { return new SnpWork(); }
 void snp_work_destroy(SnpWork* w) {
     if (!w) return;
     cudaFree(w->flag_words2); cudaFree(w->survivors);
-    cudaFree(w->tile_first); cudaFree(w->flag_words); cudaFree(w->block_sum); cudaFree(w->flagged);
+    cudaFree(w->tile_first); cudaFree(w->fc_sync); cudaFree(w->flagged);
     cudaFree(w->slots); cudaFree(w->slot_text); cudaFree(w->slot_pos); cudaFree(w->valid_words); cudaFree(w->cand);
     cudaFree(w->dev);
     cudaFreeHost(w->h_dev);
@@ -734,9 +843,8 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     w->stride = uint32_t((sizeof(PackedEventHdr) + 2 * size_t(p.k_left) + size_t(p.k_right) + 15) & ~size_t(15));
 
     CK(ensure(w->tile_first, w->tile_first_cap, size_t(num_tiles) + 1));
-    CK(ensure(w->flag_words, w->flag_cap, size_t(n_words)));
     CK(ensure(w->flag_words2, w->flag2_cap, size_t(n_words)));
-    CK(ensure(w->block_sum, w->block_sum_cap, size_t(n_fblocks)));
+    CK(ensure(w->fc_sync, w->fc_sync_cap, size_t(n_fblocks) + 1));
     // first guesses: clusters with two frequent base codes are variants and repeats, a small fraction of all
     if (!w->want_survivors) w->want_survivors = a.m / 64 + 4096;
     if (!w->want_flagged) w->want_flagged = a.m / 256 + 2048;
@@ -772,8 +880,8 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
         }
 
         CK(cudaMemsetAsync(w->dev, 0, sizeof(SnpDev), stream));
-        CK(cudaMemsetAsync(w->flag_words, 0, n_words * 4, stream));
         CK(cudaMemsetAsync(w->flag_words2, 0, n_words * 4, stream));
+        CK(cudaMemsetAsync(w->fc_sync, 0, (size_t(n_fblocks) + 1) * 8, stream));
         CK(cudaMemsetAsync(w->valid_words, 0, n_vwords * 4, stream));
 
         k_tile_first<<<(num_tiles + 1 + 255) / 256, 256, 0, stream>>>(a.cl_start, a.m, a.global_off, num_tiles, w->tile_first);
@@ -787,7 +895,8 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             sp.min_len = uint32_t(2 * p.mcov_out);
             sp.max_len = uint32_t(max_clust_length);
             sp.mcov = uint32_t(p.mcov_out);
-            sp.flag_words = w->flag_words;
+            sp.survivors = w->survivors;
+            sp.cap_surv = cap_surv;
             sp.dev = w->dev;
             const size_t smem = size_t(PS_STAGES) * PS_SPAN;
             CK(cudaFuncSetAttribute(k_code_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -802,13 +911,6 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             CK(cudaGetLastError());
             ++*launches;
         }
-        // survivors of the prefilter, in order
-        k_flag_count<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum);
-        CK(cudaGetLastError());
-        k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words, n_words, w->block_sum, w->survivors, cap_surv,
-                                                          &w->dev->n_survivors);
-        CK(cudaGetLastError());
-        *launches += 2;
         {   // K3x: exact filters on the survivors
             ExactParams ep;
             ep.a = a;
@@ -827,12 +929,11 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             CK(cudaGetLastError());
             ++*launches;
         }
-        k_flag_count<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->block_sum);
+        // clusters that pass the filters, in eBWT order (the candidate order of the reference)
+        k_flag_compact<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->fc_sync, w->flagged, cap_flag,
+                                                            &w->dev->n_flagged);
         CK(cudaGetLastError());
-        k_flag_emit<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->block_sum, w->flagged, cap_flag,
-                                                          &w->dev->n_flagged);
-        CK(cudaGetLastError());
-        *launches += 2;
+        ++*launches;
         {
             CandParams cp;
             cp.a = a;
