@@ -220,14 +220,17 @@ __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
             for (int ch = tid; ch < PS_CHUNKS; ch += PS_THREADS) {
                 const uint4 q = lds128(st + ch * 16);
                 const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                uint32_t b0 = 0, b1 = 0;
+                // one multiply per word gathers both planes: with the bit-0 flags of plane 0 at bit 0 and those of plane 1
+                // at bit 4 of every byte, (x * 0x01020408) >> 24 = plane-1 nibble << 4 | plane-0 nibble (no two partial
+                // products meet, so there are no carries)
+                uint32_t B = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    b0 |= ((fast_b0(w[j]) * 0x01020408u) >> 24) << (4 * j);
-                    b1 |= ((fast_b1(w[j]) * 0x01020408u) >> 24) << (4 * j);
-                }
-                s_b0[ch] = uint16_t(b0);
-                s_b1[ch] = uint16_t(b1);
+                for (int j = 0; j < 4; ++j) B |= (((fast_b0(w[j]) | (fast_b1(w[j]) << 4)) * 0x01020408u) >> 24) << (8 * j);
+                uint32_t lo = B & 0x0F0F0F0Fu, hi = (B >> 4) & 0x0F0F0F0Fu;  // byte j = nibble of word j
+                lo = (lo | (lo >> 4)) & 0x00FF00FFu;
+                hi = (hi | (hi >> 4)) & 0x00FF00FFu;
+                s_b0[ch] = uint16_t(lo | (lo >> 8));
+                s_b1[ch] = uint16_t(hi | (hi >> 8));
             }
         } else {
             for (int ch = tid; ch < PS_CHUNKS; ch += PS_THREADS) {

@@ -42,23 +42,43 @@ def _world(group=None):
     return dist.get_rank(group), dist.get_world_size(group)
 
 
+_STAGE = {}
+
+
+def _staging(n_words, world, device):
+    """reusable buffers of one collective: pinned host send/recv + device send/recv (int64 words)"""
+    key = (n_words, world, str(device))
+    if key not in _STAGE:
+        pin = torch.device(device).type == "cuda"
+        _STAGE[key] = (torch.empty(n_words, dtype=torch.int64, pin_memory=pin),
+                       torch.empty(n_words * world, dtype=torch.int64, pin_memory=pin),
+                       torch.empty(n_words, dtype=torch.int64, device=device),
+                       torch.empty(n_words * world, dtype=torch.int64, device=device))
+    return _STAGE[key]
+
+
 def all_gather_words(words, device, group=None):
-    """all-gather of a short list of unsigned 64-bit words; returns one list of python ints per rank"""
+    """all-gather of a short list of unsigned 64-bit words (one collective, one host synchronisation);
+    returns a (world, n_words) uint64 numpy array"""
     rank, world = _world(group)
-    w = np.asarray(words, dtype=np.uint64)
+    w = np.ascontiguousarray(words, dtype=np.uint64)
     if world == 1:
-        return [[int(x) for x in w]]
-    mine = torch.from_numpy(w.view(np.int64).copy()).to(device)
-    out = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(out, mine, group=group)
-    return [[int(x) for x in t.cpu().numpy().view(np.uint64)] for t in out]
+        return w.reshape(1, -1).copy()
+    h_send, h_recv, d_send, d_recv = _staging(len(w), world, device)
+    h_send.numpy()[:] = w.view(np.int64)
+    d_send.copy_(h_send, non_blocking=True)
+    dist.all_gather_into_tensor(d_recv, d_send, group=group)
+    h_recv.copy_(d_recv, non_blocking=True)
+    if torch.device(device).type == "cuda":
+        torch.cuda.current_stream(device).synchronize()
+    return h_recv.numpy().view(np.uint64).reshape(world, len(w)).copy()
 
 
 def exchange_summaries(summary: api.ClusterSummary, device, group=None):
     """step 2: every rank gets the scan summaries of all shards, in rank (= eBWT) order"""
     words = np.frombuffer(bytes(summary), dtype=np.uint64)
     gathered = all_gather_words(words, device, group)
-    return [api.ClusterSummary.from_buffer_copy(np.asarray(g, dtype=np.uint64).tobytes()) for g in gathered]
+    return [api.ClusterSummary.from_buffer_copy(g.tobytes()) for g in gathered]
 
 
 def merge_clusters(summary: api.ClusterSummary, device, group=None):
@@ -77,15 +97,22 @@ def merge_statistics(st: api.Stats, mcov_out, pval, device, group=None) -> api.S
         return st
     words = list(st.hist) + [st.n_clust, st.n_bases, st.last_len]
     gathered = all_gather_words(words, device, group)
+    return _sum_statistics(gathered, mcov_out, pval)
+
+
+def _sum_statistics(rows, mcov_out, pval) -> api.Stats:
+    """rows[g] = hist[151], n_clust, n_bases, last_len of shard g's records in file order"""
     tot = api.Stats()
+    H = api.HIST_BINS
+    hist = rows[:, :H].sum(axis=0)
+    for i in range(H):
+        tot.hist[i] = int(hist[i])
+    tot.n_clust = int(rows[:, H].sum())
+    tot.n_bases = int(rows[:, H + 1].sum())
     last_len = 0
-    for g in gathered:
-        for i in range(api.HIST_BINS):
-            tot.hist[i] += g[i]
-        tot.n_clust += g[api.HIST_BINS]
-        tot.n_bases += g[api.HIST_BINS + 1]
-        if g[api.HIST_BINS] > 0:
-            last_len = g[api.HIST_BINS + 2]
+    for g in rows:
+        if g[H] > 0:
+            last_len = int(g[H + 2])
     tot.last_len = last_len
     api.statistics_finish(tot, last_len, mcov_out, pval)
     return tot
@@ -96,7 +123,7 @@ def event_id_offset(n_events, device, group=None):
     rank, world = _world(group)
     if world == 1:
         return 1, int(n_events)
-    counts = [g[0] for g in all_gather_words([int(n_events)], device, group)]
+    counts = [int(g[0]) for g in all_gather_words([int(n_events)], device, group)]
     return 1 + sum(counts[:rank]), sum(counts)
 
 
@@ -130,14 +157,54 @@ def exchange_halo(lcp, text, suff, bwt, device, group=None):
     return left, right
 
 
+def exchange_and_merge(summary: api.ClusterSummary, own: api.Stats, mcov_out, pval, device, group=None):
+    """ONE collective between the phases: every rank contributes its scan summary and the length histogram of its OWN
+    records; every rank then runs the (host, integer) merge for all shards, adds the records the merge creates at shard
+    heads / at the tail to the histogram itself and finishes statistics().
+    -> (ClusterMerged of this rank, global Stats with max_clust_length)"""
+    rank, world = _world(group)
+    s = summary
+    H = api.HIST_BINS
+    words = np.concatenate([np.frombuffer(bytes(s), dtype=np.uint64),
+                            np.array(list(own.hist) + [own.n_clust, own.n_bases, own.last_len], dtype=np.uint64)])
+    rows = all_gather_words(words, device, group)
+    W = api.SUMMARY_WORDS
+    sums = [api.ClusterSummary.from_buffer_copy(r[:W].tobytes()) for r in rows]
+    stat_rows = rows[:, W:].copy()
+    mg = None
+    for g in range(world):
+        mg_g = api.cluster_merge(sums, g)
+        extra = ([mg_g.prepend_len] if mg_g.n_prepend and mg_g.prepend_written else []) + \
+                [mg_g.append_len[i] for i in range(mg_g.n_append)]
+        for ln in extra:
+            if ln <= api.MAX_C_LEN:
+                stat_rows[g, ln] += 1
+            stat_rows[g, H] += 1
+            stat_rows[g, H + 1] += ln
+        if mg_g.n_append:                       # file order inside a shard: [head record] own records [tail records]
+            stat_rows[g, H + 2] = mg_g.append_len[mg_g.n_append - 1]
+        elif rows[g, W + H] == 0 and extra:     # only a head record
+            stat_rows[g, H + 2] = extra[-1]
+        if g == rank:
+            mg = mg_g
+    st = _sum_statistics(stat_rows, mcov_out, pval)
+    return mg, st
+
+
 def hot_path_step(shard: "api.Shard", params: api.SnpParams, k, min_len, device, group=None):
     """One pass of the hot path on this rank's resident shard, collectives included.
     -> (ClusterMerged, Stats (global), SnpCounts (this shard), first event id of this shard)"""
+    rank, world = _world(group)
     s = shard.cluster_run(k, min_len)
-    mg, _ = merge_clusters(s, device, group)
+    if world == 1:
+        mg = api.cluster_merge([s], 0)
+        shard.cluster_finalize(mg)
+        st = shard.statistics(params.mcov_out, params.pval)
+        cnt = shard.find_events(params, st.max_clust_length)
+        return mg, st, cnt, 1
+    own = shard.statistics(finish=False)  # before finalize: the shard's own records only
+    mg, st = exchange_and_merge(s, own, params.mcov_out, params.pval, device, group)
     shard.cluster_finalize(mg)
-    st = shard.statistics(finish=False)
-    st = merge_statistics(st, params.mcov_out, params.pval, device, group)
     cnt = shard.find_events(params, st.max_clust_length)
     first_id, _ = event_id_offset(cnt.n_events, device, group)
     return mg, st, cnt, first_id

@@ -77,6 +77,20 @@ def _worker(rank, world, port, seed, q):
                 assert list(tot.hist) == list(ost.hist)
                 assert (tot.n_clust, tot.n_bases, tot.max_clust_length) == (ost.n_clust, ost.n_bases, ost.max_clust_length)
 
+            # ---- steps 2 + 3 in ONE collective (what hot_path_step does): own-record histogram in, merged view + global stats out ----
+            own = api.Stats()
+            for v in rl.tolist():
+                if v <= api.MAX_C_LEN:
+                    own.hist[v] += 1
+            own.n_clust, own.n_bases = len(rl), int(rl.astype(np.int64).sum())
+            own.last_len = int(rl[-1]) if len(rl) else 0
+            if len(es):
+                mg2, tot2 = sharding.exchange_and_merge(summary, own, 2, 0.9, dev)
+                assert bytes(mg2) == bytes(mg)
+                ost = O.statistics(es, el, 2, 0.9)
+                assert list(tot2.hist) == list(ost.hist), (it, cuts)
+                assert (tot2.n_clust, tot2.n_bases, tot2.max_clust_length) == (ost.n_clust, ost.n_bases, ost.max_clust_length), (it, cuts)
+
             # ---- step 4: event ids ----
             fake_events = int(rng.integers(0, 50)) + rank  # differs per rank
             first, total = sharding.event_id_offset(fake_events, dev)
