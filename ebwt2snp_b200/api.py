@@ -84,7 +84,7 @@ SYMBOLS = [
     "e2s_cluster_run", "e2s_cluster_merge", "e2s_cluster_finalize", "e2s_cluster_lm", "e2s_cluster_count",
     "e2s_cluster_fetch", "e2s_cluster_fetch_packed", "e2s_clusters_stage_packed", "e2s_clusters_stage",
     "e2s_statistics", "e2s_statistics_finish", "e2s_snp_default_params", "e2s_find_events", "e2s_events_fetch",
-    "e2s_events_format", "e2s_free", "e2s_pipeline_host",
+    "e2s_events_format", "e2s_free", "e2s_pipeline_resident", "e2s_pipeline_host",
 ]
 
 _lib = None
@@ -139,6 +139,7 @@ def load_library():
     lib.e2s_events_format.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(SnpParams), C.POINTER(C.c_void_p),
                                       C.POINTER(C.c_size_t)]
     lib.e2s_free.argtypes = [C.c_void_p]
+    lib.e2s_pipeline_resident.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(SnpParams), C.POINTER(PipelineResult)]
     lib.e2s_pipeline_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(SnpParams), C.c_void_p,
                                       C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PipelineResult)]
@@ -378,6 +379,12 @@ class Shard:
             e.counts = cnt  # the counters up to the failure (e.g. candidates found before a read lookup failed)
             raise
         return cnt
+
+    def pipeline_resident(self, params: SnpParams, k=16, min_len=2) -> PipelineResult:
+        """cluster_lm + statistics + find_events on a sealed whole-eBWT shard in one C call"""
+        res = PipelineResult()
+        self.ctx._ck(self.lib.e2s_pipeline_resident(self.h, k, min_len, C.byref(params), C.byref(res)))
+        return res
 
     def events(self):
         n = C.c_uint64()

@@ -998,6 +998,29 @@ void e2s_free(void* p) { free(p); }
 // ---------------------------------------------------------------------------------------------
 // end to end over host buffers
 // ---------------------------------------------------------------------------------------------
+// ebwt2clust + clust2snp on a sealed shard that holds the whole eBWT (one GPU), reads already staged
+int e2s_pipeline_resident(e2s_shard* s, uint32_t k, int32_t min_len, const e2s_snp_params* p, e2s_pipeline_result* res) {
+    if (!s || !p || !res) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
+    e2s_ctx* c = s->ctx;
+    int rc;
+    const uint64_t h2d = res->h2d_bytes, d2h = res->d2h_bytes;
+    memset(res, 0, sizeof *res);
+    res->h2d_bytes = h2d;
+    res->d2h_bytes = d2h;
+    if ((rc = e2s_cluster_lm(s, k, min_len, &res->n_written, &res->n_clust_out))) return rc;
+    if (res->n_written == 0) return fail(c, E2S_ERR_UNSUPPORTED, "no clusters (the reference divides by zero here)");
+    e2s_stats st;
+    if ((rc = e2s_statistics(s, &st))) return rc;
+    if ((rc = e2s_statistics_finish(&st, st.last_len, p->mcov_out, p->pval))) {
+        c->err = g_err;
+        return rc;
+    }
+    res->max_clust_length = st.max_clust_length;
+    if ((rc = e2s_find_events(s, p, st.max_clust_length, &res->snp))) return rc;
+    res->d2h_bytes += res->snp.n_candidates * 128;
+    return E2S_OK;
+}
+
 int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, int z, const uint8_t* read_bases,
                       const uint64_t* read_off, uint64_t n_reads, uint32_t k, int32_t min_len, const e2s_snp_params* p,
                       void* rec10, uint64_t cap_records, e2s_event* events, uint64_t cap_events, e2s_pipeline_result* res) {
@@ -1035,25 +1058,14 @@ int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, in
         res->h2d_bytes += read_off[n_reads] + (n_reads + 1) * 8;
     }
     lap("H2D reads");
-    if ((rc = e2s_cluster_lm(s, k, min_len, &res->n_written, &res->n_clust_out))) return rc;
-    lap("K1 + K2 + merge");
+    if ((rc = e2s_pipeline_resident(s, k, min_len, p, res))) return rc;
+    lap("K1 K2 merge statistics K3 K4");
     if (rec10) {
         uint64_t m = 0;
         if ((rc = e2s_cluster_fetch_packed(s, rec10, cap_records, &m))) return rc;
         res->d2h_bytes += m * 10;
     }
     lap("pack + D2H .clusters records");
-    if (res->n_written == 0) return fail(c, E2S_ERR_UNSUPPORTED, "no clusters (the reference divides by zero here)");
-    e2s_stats st;
-    if ((rc = e2s_statistics(s, &st))) return rc;
-    if ((rc = e2s_statistics_finish(&st, st.last_len, p->mcov_out, p->pval))) {
-        c->err = g_err;
-        return rc;
-    }
-    res->max_clust_length = st.max_clust_length;
-    if ((rc = e2s_find_events(s, p, st.max_clust_length, &res->snp))) return rc;
-    res->d2h_bytes += res->snp.n_candidates * 128;
-    lap("statistics + K3 + K4");
     if (events) {
         uint64_t nv = 0;
         if ((rc = e2s_events_fetch(s, events, cap_events, &nv))) return rc;

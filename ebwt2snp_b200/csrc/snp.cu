@@ -140,6 +140,14 @@ __device__ __forceinline__ uint32_t fast_b0(uint32_t w) {
     return (((u >> 1) & ~(u >> 2)) | (u >> 4)) & 0x01010101u;
 }
 
+// both at once: plane 0 at bit 0 and plane 1 at bit 4 of every byte  (fast_b0(w) | fast_b1(w) << 4 with shared shifts)
+__device__ __forceinline__ uint32_t fast_b01(uint32_t w) {
+    const uint32_t u = w & 0xDFDFDFDFu, b = u >> 2;
+    const uint32_t x = ((u >> 1) & ~b) | (u >> 4);  // bit 0 of every byte: plane 0
+    const uint32_t y = (u << 2) & b;                // bit 4 of every byte: u.bit2 & u.bit6
+    return (x & 0x01010101u) | (y & 0x10101010u);
+}
+
 // Runs once when a shard is sealed: *flag != 0 iff some BWT byte's exact base code (base_code) differs from the
 // bit-sliced one above, in which case K3a keeps the per-byte equality tests.
 __global__ void __launch_bounds__(256) k_bwt_alphabet(const uint8_t* __restrict__ bwt, uint64_t count, uint32_t* flag) {
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
                 // products meet, so there are no carries)
                 uint32_t B = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) B |= (((fast_b0(w[j]) | (fast_b1(w[j]) << 4)) * 0x01020408u) >> 24) << (8 * j);
+                for (int j = 0; j < 4; ++j) B |= ((fast_b01(w[j]) * 0x01020408u) >> 24) << (8 * j);
                 uint32_t lo = B & 0x0F0F0F0Fu, hi = (B >> 4) & 0x0F0F0F0Fu;  // byte j = nibble of word j
                 lo = (lo | (lo >> 4)) & 0x00FF00FFu;
                 hi = (hi | (hi >> 4)) & 0x00FF00FFu;

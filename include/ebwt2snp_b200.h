@@ -239,6 +239,11 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
 } e2s_pipeline_result;
 
+/* ebwt2clust + clust2snp on a sealed shard that holds the whole eBWT of one GPU, reads already staged:
+ * cluster_lm + statistics + find_events (ref:ebwt2clust.cpp:194, ref:clust2snp.cpp:1080-1081) in one call.
+ * Records and events stay on the shard (e2s_cluster_fetch*, e2s_events_fetch). */
+int e2s_pipeline_resident(e2s_shard *sh, uint32_t k, int32_t min_len, const e2s_snp_params *p, e2s_pipeline_result *res);
+
 /* ebwt2clust + clust2snp on one GPU from host buffers: .gesa records + reads in, .clusters
  * records (10-byte, into rec10 if non-NULL) and events out. */
 int e2s_pipeline_host(e2s_ctx *ctx, const void *gesa_records, uint64_t n, int x, int y, int z,
