@@ -22,6 +22,8 @@ CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-cudart", "
 
 CU_SOURCES = ["capi.cu", "cluster.cu", "snp.cu", "unpack.cu"]
 CLI_SOURCES = {"ebwt2clust": ["ebwt2clust_main.cpp"], "clust2snp": ["clust2snp_main.cpp"]}
+# text post-processors of the .snp format (no GPU work, no library): SURVEY.md 8(f) rank 3
+TEXT_TOOLS = {"filter_snp": ["filter_snp_main.cpp"], "snp2fastq": ["snp2fastq_main.cpp"]}
 
 
 def _newer(target, sources):
@@ -70,6 +72,12 @@ def build_clis(force=False, verbose=False):
         if force or _newer(exe, deps):
             _run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), *srcs, "-o", exe,
                   "-L", LIB_DIR, "-lebwt2snp_b200", "-Wl,-rpath,$ORIGIN/../lib", "-ldl", "-lpthread", "-lrt"], verbose)
+        out.append(exe)
+    for name, files in TEXT_TOOLS.items():
+        srcs = [os.path.join(HOST, f) for f in files]
+        exe = os.path.join(BIN_DIR, name)
+        if force or _newer(exe, srcs + [os.path.join(HOST, "snp_text.hpp")]):
+            _run(["g++", "-O2", "-std=c++17", "-I", HOST, *srcs, "-o", exe], verbose)
         out.append(exe)
     return out
 

@@ -859,6 +859,10 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     // first guesses: clusters with two frequent base codes are variants and repeats, a small fraction of all
     if (!w->want_survivors) w->want_survivors = a.m / 64 + 4096;
     if (!w->want_flagged) w->want_flagged = a.m / 256 + 2048;
+    if (const char* dbg = getenv("E2S_SNP_FIRST_CAPACITY")) {  // test hook: start from a tiny guess to exercise the retry path
+        const uint64_t v = strtoull(dbg, nullptr, 10);
+        if (v) w->want_survivors = w->want_flagged = v;
+    }
 
     SnpDev& hd = *w->h_dev;
     for (int attempt = 0;; ++attempt) {

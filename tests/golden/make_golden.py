@@ -242,6 +242,50 @@ def phantom_tail(d):
     print("phantom_tail:", ci, "cases,", len(rows), "readouts; candidates seen:", sorted({r[-1] for r in rows}))
 
 
+def snp_text_tools(d):
+    """filter_snp / snp2fastq of the reference on the fixtures' .snp files and on damaged copies of them
+    (missing fields keep the previous group's value in the reference: its variables persist)."""
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    rng = np.random.default_rng(77)
+    inputs = []
+    for name in MICRO:
+        z = np.load(os.path.join(HERE, name + ".npz"))
+        inputs.append(bytes(z["v0_snp"]))
+        inputs.append(bytes(z["v2_snp"]))
+    base = inputs[0].decode().split("\n")
+    for _ in range(6):  # damaged variants: cut bars / underscores / colons out of some header lines, drop trailing newline
+        lines = list(base[:4 * int(rng.integers(3, 12))])
+        for i in range(0, len(lines), 2):
+            if rng.random() < 0.4:
+                ch = str(rng.choice(["|", "_", ":"]))
+                parts = lines[i].split(ch)
+                if len(parts) > 2:
+                    cut = int(rng.integers(1, len(parts)))
+                    lines[i] = ch.join(parts[:cut])
+            if rng.random() < 0.15:
+                lines[i] += "|"
+        text = "\n".join(lines) + ("\n" if rng.random() < 0.5 else "")
+        inputs.append(text.encode())
+    out = {"n": np.int64(len(inputs))}
+    for j, data in enumerate(inputs):
+        path = os.path.join(d, f"t{j}.snp")
+        open(path, "wb").write(data)
+        out[f"in{j}"] = np.frombuffer(data, dtype=np.uint8)
+        for M in (0, 5, 9):
+            r = subprocess.run([os.path.join(ref, "filter_snp"), path, str(M)], capture_output=True, timeout=60)
+            assert r.returncode == 0
+            out[f"filter{j}_{M}"] = np.frombuffer(r.stdout, dtype=np.uint8)
+        for flag in ([], ["-i"]):
+            if os.path.exists(path + ".fastq"):
+                os.remove(path + ".fastq")
+            r = subprocess.run([os.path.join(ref, "snp2fastq"), path, *flag], capture_output=True, timeout=60)
+            assert r.returncode == 0
+            out[f"fastq{j}_{len(flag)}"] = np.frombuffer(open(path + ".fastq", "rb").read(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "snp_text.npz"), **out)
+    print("snp_text:", len(inputs), "inputs")
+
+
 if __name__ == "__main__":
     assert O.ref_available(), "oracle/_ref missing: run `make -C oracle ref` where /root/reference exists"
     d = tempfile.mkdtemp(prefix="golden_")
@@ -251,6 +295,7 @@ if __name__ == "__main__":
         phase1_fuzz_widths(d)
         for name, cfg in MICRO.items():
             micro(name, cfg, d)
+        snp_text_tools(d)
     finally:
         shutil.rmtree(d, ignore_errors=True)
     print("golden vectors written to", HERE)

@@ -224,3 +224,44 @@ def test_phase1_golden_gpu(ctx):
         nw, nc = sh.cluster_lm(c["k"], c["m"])
         assert sh.cluster_fetch_packed() == c["clusters"] and (nc & 0xFFFFFFFF) == c["n_clust_out"], (n, c["k"], c["m"])
         sh.close()
+
+
+def test_phase2_capacity_retry(ctx, monkeypatch):
+    """the survivor / flagged lists start from a capacity guess; an overflow must be detected and the pass repeated"""
+    rs, e = H.dataset("small", 1)
+    n = e["n"]
+    es, el, _, _ = O.cluster_lm(e["lcp"], e["bwt"], 16, 2)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    ctx.stage_reads(rs.reads, off)
+    p, op = api.default_params(rs.nreads1), O.default_params(rs.nreads1)
+    ost = O.statistics(es, el, op.mcov_out, op.pval)
+    otext, ores = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+    assert ores.n_candidates > 8
+    for first_cap in ("1", "7"):
+        monkeypatch.setenv("E2S_SNP_FIRST_CAPACITY", first_cap)
+        sh = ctx.shard(n)
+        sh.load_soa(e["lcp"], e["text"], e["suff"], e["bwt"])
+        sh.seal()
+        sh.cluster_lm(16, 2)
+        st = sh.statistics(p.mcov_out, p.pval)
+        cnt = sh.find_events(p, st.max_clust_length)
+        assert cnt.n_candidates == ores.n_candidates and api.events_format(sh.events(), p) == otext
+        sh.close()
+
+
+def test_rejects_unsorted_clusters(ctx):
+    """the reference silently mis-joins unsorted / overlapping records (ref:clust2snp.cpp:818-833); here: E2S_ERR_UNSUPPORTED"""
+    rs, e = H.dataset("tiny", 1)
+    n = e["n"]
+    ctx.stage_reads(rs.reads, O.uniform_read_offsets(*rs.reads.shape))
+    sh = ctx.shard(n)
+    sh.load_soa(e["lcp"], e["text"], e["suff"], e["bwt"])
+    sh.seal()
+    sh.stage_clusters(np.array([500, 100, 900], dtype=np.uint64), np.array([20, 20, 20], dtype=np.uint16))
+    with pytest.raises(api.E2SError) as ei:
+        sh.find_events(api.default_params(rs.nreads1), 150)
+    assert ei.value.code == api.ERR_UNSUPPORTED
+    sh.stage_clusters(np.array([100, 110], dtype=np.uint64), np.array([20, 20], dtype=np.uint16))  # overlap
+    with pytest.raises(api.E2SError):
+        sh.find_events(api.default_params(rs.nreads1), 150)
+    sh.close()
