@@ -363,7 +363,8 @@ def main():
         all-gather, K3a/K3x/K3b/K4, event-count all-gather (ebwt2snp_b200/sharding.py)"""
         if world == 1:  # the same sequence inside the library: one C call, no Python between the kernels
             return sh.pipeline_resident(params, K_DEF, M_DEF)
-        mg, st, cnt, _first_id = sharding.hot_path_step(sh, params, K_DEF, M_DEF, dev)
+        mg, st, cnt, ids = sharding.hot_path_step(sh, params, K_DEF, M_DEF, dev)
+        step.ids = ids  # the id all-gather is enqueued; it is read (resolve) after the timed loop's last step
         return mg, st, cnt
 
     def sync_all():
@@ -398,6 +399,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         mg, st, cnt = out
+        step.ids.resolve()
     else:  # the one-call step returns the pipeline result; the histogram is still on the shard
         import types
         mg = types.SimpleNamespace(total_written=out.n_written, n_clust_out=out.n_clust_out)

@@ -841,12 +841,19 @@ static cudaError_t launch_flags_t(const FlagParams& p0, uint64_t rows_alloc32, i
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     const size_t smem = size_t(STAGES) * FL_T * 4 + 1024;
     auto kern = k_lcp_flags<STAGES>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) return e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FL_THREADS, smem);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    static int occ_dev[64] = {0};  // function attributes are per device: cached per device ordinal
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& occ = occ_dev[dev & 63];
+    if (!occ) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        int o = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, FL_THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (o < 1) return cudaErrorLaunchOutOfResources;
+        occ = o;
+    }
     uint64_t grid = uint64_t(sm_count) * occ;
     if (grid > p.num_tiles) grid = p.num_tiles;
     kern<<<dim3(unsigned(grid)), dim3(FL_THREADS), smem, stream>>>(tmap, p);
@@ -865,10 +872,17 @@ uint64_t emit_desc_words() { return uint64_t(EM_MAX_CHUNKS) * EM_DESC_WORDS; }
 
 cudaError_t launch_emit(const EmitParams& p0, int sm_count, cudaStream_t stream) {
     EmitParams p = p0;
-    int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_emit, EM_THREADS, 0);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    static int occ_dev[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& occ = occ_dev[dev & 63];
+    if (!occ) {
+        int o = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_cluster_emit, EM_THREADS, 0);
+        if (e != cudaSuccess) return e;
+        if (o < 1) return cudaErrorLaunchOutOfResources;
+        occ = o;
+    }
     uint64_t grid = uint64_t(sm_count) * occ;  // one chunk per CTA
     if (grid > p.num_tiles) grid = p.num_tiles;
     if (grid > EM_MAX_CHUNKS) grid = EM_MAX_CHUNKS;

@@ -789,13 +789,14 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
 // ---------------------------------------------------------------------------------------------
 struct SnpWork {
     uint64_t* tile_first = nullptr; size_t tile_first_cap = 0;
-    unsigned long long* fc_sync = nullptr; size_t fc_sync_cap = 0;
-    uint32_t* flag_words2 = nullptr; size_t flag2_cap = 0;
+    uint8_t* zero_blk = nullptr; size_t zero_cap = 0;  // everything a pass needs zeroed, in one block: one memset
+    unsigned long long* fc_sync = nullptr;              // (views into zero_blk)
+    uint32_t* flag_words2 = nullptr;
     uint64_t* survivors = nullptr; size_t survivors_cap = 0;
     uint64_t* flagged = nullptr; size_t flagged_cap = 0;
     CandSlot* slots = nullptr; size_t slots_cap = 0;
     uint32_t* slot_text = nullptr; uint32_t* slot_pos = nullptr; size_t slot_list_cap = 0;
-    uint32_t* valid_words = nullptr; size_t valid_cap = 0;
+    uint32_t* valid_words = nullptr;
     uint64_t* cand = nullptr; size_t cand_cap = 0;
     SnpDev* dev = nullptr;
     SnpDev* h_dev = nullptr;                                // pinned staging of the counters
@@ -811,10 +812,9 @@ SnpWork* snp_work_create() { return new SnpWork(); }
 
 void snp_work_destroy(SnpWork* w) {
     if (!w) return;
-    cudaFree(w->flag_words2); cudaFree(w->survivors);
-    cudaFree(w->tile_first); cudaFree(w->fc_sync); cudaFree(w->flagged);
-    cudaFree(w->slots); cudaFree(w->slot_text); cudaFree(w->slot_pos); cudaFree(w->valid_words); cudaFree(w->cand);
-    cudaFree(w->dev);
+    cudaFree(w->zero_blk); cudaFree(w->survivors);
+    cudaFree(w->tile_first); cudaFree(w->flagged);
+    cudaFree(w->slots); cudaFree(w->slot_text); cudaFree(w->slot_pos); cudaFree(w->cand);
     cudaFreeHost(w->h_dev);
     cudaFreeHost(w->h_events);
     delete w;
@@ -841,7 +841,6 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     w->n_cand = 0;
     w->k_left = p.k_left;
     w->k_right = p.k_right;
-    if (!w->dev) CK(cudaMalloc(reinterpret_cast<void**>(&w->dev), sizeof(SnpDev)));
     if (!w->h_dev) CK(cudaHostAlloc(reinterpret_cast<void**>(&w->h_dev), sizeof(SnpDev), cudaHostAllocDefault));
     if (a.m == 0 || a.n_local == 0) return cudaSuccess;
 
@@ -854,8 +853,6 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     w->stride = uint32_t((sizeof(PackedEventHdr) + 2 * size_t(p.k_left) + size_t(p.k_right) + 15) & ~size_t(15));
 
     CK(ensure(w->tile_first, w->tile_first_cap, size_t(num_tiles) + 1));
-    CK(ensure(w->flag_words2, w->flag2_cap, size_t(n_words)));
-    CK(ensure(w->fc_sync, w->fc_sync_cap, size_t(n_fblocks) + 1));
     // first guesses: clusters with two frequent base codes are variants and repeats, a small fraction of all
     if (!w->want_survivors) w->want_survivors = a.m / 64 + 4096;
     if (!w->want_flagged) w->want_flagged = a.m / 256 + 2048;
@@ -882,7 +879,17 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_pos), n * 4));
             w->slot_list_cap = n;
         }
-        CK(ensure(w->valid_words, w->valid_cap, size_t(n_vwords)));
+        {   // SnpDev | fc_sync | flag_words2 | valid_words, 16-byte aligned pieces of one zeroed block
+            auto up16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+            const size_t o_sync = up16(sizeof(SnpDev)), o_flag = o_sync + up16((size_t(n_fblocks) + 1) * 8);
+            const size_t o_valid = o_flag + up16(size_t(n_words) * 4), total = o_valid + up16(size_t(n_vwords) * 4);
+            CK(ensure(w->zero_blk, w->zero_cap, total));
+            w->dev = reinterpret_cast<SnpDev*>(w->zero_blk);
+            w->fc_sync = reinterpret_cast<unsigned long long*>(w->zero_blk + o_sync);
+            w->flag_words2 = reinterpret_cast<uint32_t*>(w->zero_blk + o_flag);
+            w->valid_words = reinterpret_cast<uint32_t*>(w->zero_blk + o_valid);
+            CK(cudaMemsetAsync(w->zero_blk, 0, total, stream));
+        }
         CK(ensure(w->cand, w->cand_cap, size_t(n_slots)));
         if (size_t(n_slots) * w->stride > w->h_events_cap) {
             cudaFreeHost(w->h_events);
@@ -894,10 +901,6 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             w->h_events_cap = bytes;
         }
 
-        CK(cudaMemsetAsync(w->dev, 0, sizeof(SnpDev), stream));
-        CK(cudaMemsetAsync(w->flag_words2, 0, n_words * 4, stream));
-        CK(cudaMemsetAsync(w->fc_sync, 0, (size_t(n_fblocks) + 1) * 8, stream));
-        CK(cudaMemsetAsync(w->valid_words, 0, n_vwords * 4, stream));
 
         k_tile_first<<<(num_tiles + 1 + 255) / 256, 256, 0, stream>>>(a.cl_start, a.m, a.global_off, num_tiles, w->tile_first);
         CK(cudaGetLastError());
@@ -914,10 +917,16 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             sp.cap_surv = cap_surv;
             sp.dev = w->dev;
             const size_t smem = size_t(PS_STAGES) * PS_SPAN;
-            CK(cudaFuncSetAttribute(k_code_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            int occ = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_code_scan, PS_THREADS, smem));
-            if (occ < 1) occ = 1;
+            static int occ_dev[64] = {0};  // function attributes are per device
+            int dev = 0;
+            cudaGetDevice(&dev);
+            int& occ = occ_dev[dev & 63];
+            if (!occ) {
+                CK(cudaFuncSetAttribute(k_code_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+                int o = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_code_scan, PS_THREADS, smem));
+                occ = o < 1 ? 1 : o;
+            }
             uint64_t grid = uint64_t(sm_count) * occ;
             if (grid > num_tiles) grid = num_tiles;
             if (timer) timer->begin(E2S_KERNEL_SCAN, stream);

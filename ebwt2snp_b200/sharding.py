@@ -127,6 +127,35 @@ def event_id_offset(n_events, device, group=None):
     return 1 + sum(counts[:rank]), sum(counts)
 
 
+class EventIdOffset:
+    """Step 4 without a host synchronisation: the all-gather of the kept-event counts is enqueued on the stream and the
+    result is only read when the ids are needed (when the .snp text is formatted)."""
+
+    def __init__(self, n_events, device, group=None):
+        self.rank, self.world = _world(group)
+        self.n = int(n_events)
+        self._out = None
+        if self.world > 1:
+            h_send, h_recv, d_send, d_recv = _staging(1, self.world, device)
+            h_send[0] = self.n
+            d_send.copy_(h_send, non_blocking=True)
+            dist.all_gather_into_tensor(d_recv, d_send, group=group)
+            h_recv.copy_(d_recv, non_blocking=True)
+            self._out = (h_recv, torch.cuda.Event() if torch.device(device).type == "cuda" else None)
+            if self._out[1] is not None:
+                self._out[1].record()
+
+    def resolve(self):
+        """-> (first id_nr of this rank's kept events, total kept events)"""
+        if self.world == 1:
+            return 1, self.n
+        h_recv, ev = self._out
+        if ev is not None:
+            ev.synchronize()
+        counts = [int(x) for x in h_recv.numpy()]
+        return 1 + sum(counts[:self.rank]), sum(counts)
+
+
 def exchange_halo(lcp, text, suff, bwt, device, group=None):
     """step 1 for shards that were BORN on their GPUs (bench.py): returns
     (left: dict of 2-element tensors from the previous rank or None,
@@ -193,7 +222,7 @@ def exchange_and_merge(summary: api.ClusterSummary, own: api.Stats, mcov_out, pv
 
 def hot_path_step(shard: "api.Shard", params: api.SnpParams, k, min_len, device, group=None):
     """One pass of the hot path on this rank's resident shard, collectives included.
-    -> (ClusterMerged, Stats (global), SnpCounts (this shard), first event id of this shard)"""
+    -> (ClusterMerged, Stats (global), SnpCounts (this shard), EventIdOffset: .resolve() gives the first id_nr of this shard)"""
     rank, world = _world(group)
     s = shard.cluster_run(k, min_len)
     if world == 1:
@@ -201,10 +230,10 @@ def hot_path_step(shard: "api.Shard", params: api.SnpParams, k, min_len, device,
         shard.cluster_finalize(mg)
         st = shard.statistics(params.mcov_out, params.pval)
         cnt = shard.find_events(params, st.max_clust_length)
-        return mg, st, cnt, 1
+        return mg, st, cnt, EventIdOffset(cnt.n_events, device, group)
     own = shard.statistics(finish=False)  # before finalize: the shard's own records only
     mg, st = exchange_and_merge(s, own, params.mcov_out, params.pval, device, group)
     shard.cluster_finalize(mg)
     cnt = shard.find_events(params, st.max_clust_length)
-    first_id, _ = event_id_offset(cnt.n_events, device, group)
-    return mg, st, cnt, first_id
+    ids = EventIdOffset(cnt.n_events, device, group)  # enqueued, not waited for
+    return mg, st, cnt, ids

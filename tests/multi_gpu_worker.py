@@ -39,7 +39,8 @@ def main():
         off = O.uniform_read_offsets(*rs.reads.shape)
         ctx.stage_reads(rs.reads, off)
         p = api.default_params(rs.nreads1)
-        mg, st, cnt, first_id = sharding.hot_path_step(sh, p, k, m, dev)
+        mg, st, cnt, ids = sharding.hot_path_step(sh, p, k, m, dev)
+        first_id, total_events = ids.resolve()
         recs = sh.cluster_fetch_packed()
         text = api.events_format(sh.events(), p, first_id=first_id)
         gathered = [None] * world
