@@ -95,24 +95,23 @@ def merge_statistics(st: api.Stats, mcov_out, pval, device, group=None) -> api.S
     if _world(group)[1] == 1:
         api.statistics_finish(st, st.last_len, mcov_out, pval)
         return st
-    words = list(st.hist) + [st.n_clust, st.n_bases, st.last_len]
-    gathered = all_gather_words(words, device, group)
+    gathered = all_gather_words(_stats_words(st), device, group)
     return _sum_statistics(gathered, mcov_out, pval)
+
+
+def _stats_words(st: api.Stats):
+    """the 154 leading u64 words of an e2s_stats (hist[151], n_clust, n_bases, last_len) as a numpy view"""
+    return np.frombuffer(st, dtype=np.uint64, count=api.HIST_BINS + 3)
 
 
 def _sum_statistics(rows, mcov_out, pval) -> api.Stats:
     """rows[g] = hist[151], n_clust, n_bases, last_len of shard g's records in file order"""
     tot = api.Stats()
     H = api.HIST_BINS
-    hist = rows[:, :H].sum(axis=0)
-    for i in range(H):
-        tot.hist[i] = int(hist[i])
-    tot.n_clust = int(rows[:, H].sum())
-    tot.n_bases = int(rows[:, H + 1].sum())
-    last_len = 0
-    for g in rows:
-        if g[H] > 0:
-            last_len = int(g[H + 2])
+    w = _stats_words(tot)
+    w[:H + 2] = rows[:, :H + 2].sum(axis=0)
+    nz = np.flatnonzero(rows[:, H])
+    last_len = int(rows[nz[-1], H + 2]) if len(nz) else 0
     tot.last_len = last_len
     api.statistics_finish(tot, last_len, mcov_out, pval)
     return tot
@@ -194,8 +193,7 @@ def exchange_and_merge(summary: api.ClusterSummary, own: api.Stats, mcov_out, pv
     rank, world = _world(group)
     s = summary
     H = api.HIST_BINS
-    words = np.concatenate([np.frombuffer(bytes(s), dtype=np.uint64),
-                            np.array(list(own.hist) + [own.n_clust, own.n_bases, own.last_len], dtype=np.uint64)])
+    words = np.concatenate([np.frombuffer(s, dtype=np.uint64), _stats_words(own)])
     rows = all_gather_words(words, device, group)
     W = api.SUMMARY_WORDS
     sums = [api.ClusterSummary.from_buffer_copy(r[:W].tobytes()) for r in rows]
