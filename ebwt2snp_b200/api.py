@@ -83,7 +83,7 @@ SYMBOLS = [
     "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_shard_set_layout", "e2s_shard_seal", "e2s_reads_stage", "e2s_reads_stage_dev",
     "e2s_cluster_run", "e2s_cluster_merge", "e2s_cluster_finalize", "e2s_cluster_lm", "e2s_cluster_count",
     "e2s_cluster_fetch", "e2s_cluster_fetch_packed", "e2s_clusters_stage_packed", "e2s_clusters_stage",
-    "e2s_statistics", "e2s_statistics_finish", "e2s_snp_default_params", "e2s_find_events", "e2s_events_fetch",
+    "e2s_statistics", "e2s_statistics_finish", "e2s_exchange_finish", "e2s_snp_default_params", "e2s_find_events", "e2s_events_fetch",
     "e2s_events_format", "e2s_free", "e2s_pipeline_resident", "e2s_pipeline_host",
 ]
 
@@ -133,6 +133,8 @@ def load_library():
     lib.e2s_clusters_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     lib.e2s_statistics.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.e2s_statistics_finish.argtypes = [C.POINTER(Stats), C.c_uint64, C.c_int, C.c_double]
+    lib.e2s_exchange_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                        C.POINTER(ClusterMerged), C.POINTER(Stats)]
     lib.e2s_snp_default_params.argtypes = [C.POINTER(SnpParams)]
     lib.e2s_find_events.argtypes = [C.c_void_p, C.POINTER(SnpParams), C.c_int, C.POINTER(SnpCounts)]
     lib.e2s_events_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -178,6 +180,20 @@ def cluster_merge(summaries, my) -> ClusterMerged:
     if rc:
         raise E2SError(rc, lib.e2s_last_error(None).decode())
     return out
+
+
+def exchange_finish(sum_rows, stat_rows, my, mcov_out=5, pval=0.99):
+    """e2s_exchange_finish over contiguous arrays of ClusterSummary / Stats records (numpy uint8/uint64 buffers or
+    ctypes arrays): -> (ClusterMerged of shard `my`, global Stats)"""
+    lib = load_library()
+    n = len(sum_rows)
+    mg, tot = ClusterMerged(), Stats()
+    rc = lib.e2s_exchange_finish(_ptr(sum_rows) if not isinstance(sum_rows, C.Array) else C.cast(sum_rows, C.c_void_p),
+                                 _ptr(stat_rows) if not isinstance(stat_rows, C.Array) else C.cast(stat_rows, C.c_void_p),
+                                 n, my, int(mcov_out), float(pval), C.byref(mg), C.byref(tot))
+    if rc:
+        raise E2SError(rc, lib.e2s_last_error(None).decode())
+    return mg, tot
 
 
 def statistics_finish(st: Stats, last_len, mcov_out=5, pval=0.99) -> Stats:

@@ -861,6 +861,42 @@ int e2s_statistics_finish(e2s_stats* st, uint64_t last_len, int mcov_out, double
     return E2S_OK;
 }
 
+// Host-only: what every rank does with the all-gathered (summary, own-record statistics) rows between the phases.
+int e2s_exchange_finish(const e2s_cluster_summary* sums, const e2s_stats* own, int n_shards, int my, int mcov_out, double pval,
+                        e2s_cluster_merged* mine, e2s_stats* total) {
+    if (!sums || !own || !mine || !total || n_shards < 1 || my < 0 || my >= n_shards)
+        return fail(nullptr, E2S_ERR_ARG, "e2s_exchange_finish: bad argument");
+    memset(total, 0, sizeof *total);
+    uint64_t last_len = 0;
+    bool any = false;
+    for (int g = 0; g < n_shards; ++g) {
+        e2s_cluster_merged mg;
+        int rc = e2s_cluster_merge(sums, n_shards, g, &mg);
+        if (rc) return rc;
+        if (g == my) *mine = mg;
+        // records of shard g in file order: [head record] own records [tail records]
+        e2s_stats st = own[g];
+        auto add = [&](uint64_t l, bool is_last) {
+            if (l <= E2S_MAX_C_LEN) st.hist[l]++;
+            st.n_bases += l;
+            st.n_clust++;
+            if (is_last) st.last_len = l;
+        };
+        if (mg.n_prepend && mg.prepend_written) add(mg.prepend_len, own[g].n_clust == 0);
+        for (uint32_t i = 0; i < mg.n_append; ++i) add(mg.append_len[i], true);
+        for (int i = 0; i < E2S_HIST_BINS; ++i) total->hist[i] += st.hist[i];
+        total->n_clust += st.n_clust;
+        total->n_bases += st.n_bases;
+        if (st.n_clust) {
+            last_len = st.last_len;
+            any = true;
+        }
+    }
+    total->last_len = last_len;
+    if (!any) return fail(nullptr, E2S_ERR_UNSUPPORTED, "empty .clusters (the reference divides by zero here)");
+    return e2s_statistics_finish(total, last_len, mcov_out, pval);
+}
+
 void e2s_snp_default_params(e2s_snp_params* p) {
     memset(p, 0, sizeof *p);
     p->k_left = 31;

@@ -191,31 +191,12 @@ def exchange_and_merge(summary: api.ClusterSummary, own: api.Stats, mcov_out, pv
     heads / at the tail to the histogram itself and finishes statistics().
     -> (ClusterMerged of this rank, global Stats with max_clust_length)"""
     rank, world = _world(group)
-    s = summary
-    H = api.HIST_BINS
-    words = np.concatenate([np.frombuffer(s, dtype=np.uint64), _stats_words(own)])
+    W, SW = api.SUMMARY_WORDS, C.sizeof(api.Stats) // 8
+    words = np.concatenate([np.frombuffer(summary, dtype=np.uint64), np.frombuffer(own, dtype=np.uint64)])
     rows = all_gather_words(words, device, group)
-    W = api.SUMMARY_WORDS
-    sums = [api.ClusterSummary.from_buffer_copy(r[:W].tobytes()) for r in rows]
-    stat_rows = rows[:, W:].copy()
-    mg = None
-    for g in range(world):
-        mg_g = api.cluster_merge(sums, g)
-        extra = ([mg_g.prepend_len] if mg_g.n_prepend and mg_g.prepend_written else []) + \
-                [mg_g.append_len[i] for i in range(mg_g.n_append)]
-        for ln in extra:
-            if ln <= api.MAX_C_LEN:
-                stat_rows[g, ln] += 1
-            stat_rows[g, H] += 1
-            stat_rows[g, H + 1] += ln
-        if mg_g.n_append:                       # file order inside a shard: [head record] own records [tail records]
-            stat_rows[g, H + 2] = mg_g.append_len[mg_g.n_append - 1]
-        elif rows[g, W + H] == 0 and extra:     # only a head record
-            stat_rows[g, H + 2] = extra[-1]
-        if g == rank:
-            mg = mg_g
-    st = _sum_statistics(stat_rows, mcov_out, pval)
-    return mg, st
+    sum_rows = np.ascontiguousarray(rows[:, :W])
+    stat_rows = np.ascontiguousarray(rows[:, W:W + SW])
+    return api.exchange_finish(sum_rows, stat_rows, rank, mcov_out, pval)
 
 
 def hot_path_step(shard: "api.Shard", params: api.SnpParams, k, min_len, device, group=None):

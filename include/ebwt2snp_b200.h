@@ -180,6 +180,12 @@ typedef struct {
 int e2s_statistics(e2s_shard *sh, e2s_stats *st);
 int e2s_statistics_finish(e2s_stats *sum_over_shards, uint64_t last_len_global, int mcov_out, double pval);
 
+/* Multi-shard glue between the phases, host-only: given the all-gathered scan summaries and the statistics of every
+ * shard's OWN records (e2s_statistics before e2s_cluster_finalize), runs e2s_cluster_merge for all shards, adds the
+ * records the merge creates at shard heads / at the tail and finishes statistics().  *mine = merged view of shard `my`. */
+int e2s_exchange_finish(const e2s_cluster_summary *sums, const e2s_stats *own, int n_shards, int my, int mcov_out, double pval,
+                        e2s_cluster_merged *mine, e2s_stats *total);
+
 typedef struct {
     int32_t k_left;          /* -L 31 */
     int32_t k_right;         /* -R 30 */
