@@ -69,6 +69,12 @@ struct e2s_shard {
     uint8_t* d_packed = nullptr;
     uint64_t packed_cap = 0;
     unsigned long long* d_hist = nullptr;
+    // fused prefilter (pipeline mode): armed by e2s_pipeline_resident with clust2snp's -m before the scan
+    uint32_t pf_arm = 0;             // mcov to use in the next e2s_cluster_run, 0 = plain scan
+    uint32_t pf_mcov = 0;            // what the last scan used
+    uint64_t* d_pf_list = nullptr;
+    uint64_t pf_cap = 0, pf_count = 0;
+    bool pf_ok = false;              // the list is complete (no overflow) and belongs to the current record list
     uint32_t* d_bwt_flag = nullptr;  // != 0: the BWT holds bytes the bit-sliced base code does not cover (set at seal)
     int variant = 0;
     // phase 2
@@ -213,7 +219,7 @@ int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t
     s->n_local = n_local;
     s->global_off = global_off;
     s->n_global = n_global;
-    s->alloc_r = round_up(n_local, 8192) + 8192;
+    s->alloc_r = round_up(n_local, 32768) + 8192;  // whole K2 tiles (32768 positions) + one K1 tile of slack
     const size_t ne = size_t(PAD_L) + s->alloc_r;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->lcp_a), ne * 4);
@@ -262,6 +268,7 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->d_res);
     cudaFree(s->d_hist);
     cudaFree(s->d_bwt_flag);
+    cudaFree(s->d_pf_list);
     snp_work_destroy(s->work);
     if (s->ctx->cached == s) s->ctx->cached = nullptr;
     delete s;
@@ -439,6 +446,13 @@ static int ensure_records(e2s_shard* s, uint64_t cap) {
     return E2S_OK;
 }
 
+int e2s_cluster_prefilter(e2s_shard* s, int mcov_out) {
+    if (!s) return fail(nullptr, E2S_ERR_ARG, "shard == NULL");
+    if (mcov_out < 0 || 2 * mcov_out > E2S_MAX_C_LEN) return fail(s->ctx, E2S_ERR_ARG, "e2s_cluster_prefilter: need 0 <= 2 * mcov_out <= 150");
+    s->pf_arm = uint32_t(mcov_out);
+    return E2S_OK;
+}
+
 int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summary* sum) {
     if (!s || !sum) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_cluster_run: NULL argument");
     e2s_ctx* c = s->ctx;
@@ -496,6 +510,24 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
         p.out_len = s->d_len;
         p.cap = s->rec_cap - 4;  // room for adopted records
         p.desc = s->d_desc;
+        p.bwt = s->bwt;
+        p.bwt_not_simple = s->d_bwt_flag;
+        p.pf_mcov = (s->pf_arm && s->sealed) ? s->pf_arm : 0;
+        p.pf_list = nullptr;
+        p.pf_cap = 0;
+        if (p.pf_mcov) {
+            const uint64_t want = s->rec_cap / 16 + 4096;
+            if (want > s->pf_cap) {
+                cudaFree(s->d_pf_list);
+                s->d_pf_list = nullptr;
+                s->pf_cap = 0;
+                if (cudaMalloc(reinterpret_cast<void**>(&s->d_pf_list), (want + 8) * 8) != cudaSuccess)
+                    return fail(c, E2S_ERR_NOMEM, "prefilter survivor list");
+                s->pf_cap = want;
+            }
+            p.pf_list = s->d_pf_list;
+            p.pf_cap = s->pf_cap;
+        }
         p.dbg = nullptr;
         uint64_t* d_dbg = nullptr;
         const char* dbg_path = getenv("E2S_EMIT_DEBUG");  // developer aid: per-chunk phase time stamps of K2
@@ -547,6 +579,9 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
     sum->tail_lcp_nm1 = h.tail_lcp_nm1;
     sum->tail_bwt_nm1 = h.tail_bwt_nm1;
     s->h_res = h;
+    s->pf_mcov = (s->pf_arm && s->sealed) ? s->pf_arm : 0;
+    s->pf_count = h.n_pf;
+    s->pf_ok = s->pf_mcov != 0 && h.n_pf <= s->pf_cap;
     s->have_scan_stats = true;
     s->m_own = h.n_written;
     s->m_list = h.n_written;
@@ -777,6 +812,7 @@ int e2s_clusters_stage(e2s_shard* s, const uint64_t* start, const uint16_t* len,
         CU(c, cudaStreamSynchronize(c->stream));
     }
     s->m_own = s->m_list = m;
+    s->pf_ok = false;
     s->have_clusters = true;
     s->staged = true;
     s->have_scan_stats = false;
@@ -947,9 +983,28 @@ int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length,
     a.cl_start = s->d_start;
     a.cl_len = s->d_len;
     a.m = s->m_list;
+    // K2 already ran the BWT prefilter for this -m (fused mode): its survivors + the records adopted from the merge
+    // (which K2 did not see) replace k_tile_first + K3a
+    const uint64_t* pre_list = nullptr;
+    uint64_t pre_count = 0;
+    if (!s->staged && s->pf_ok && s->pf_mcov == uint32_t(p->mcov_out) && max_clust_length <= E2S_MAX_C_LEN) {
+        uint64_t extra[4];
+        const uint64_t n_extra = s->m_list - s->m_own;  // <= 3, appended behind the shard's own records
+        for (uint64_t i = 0; i < n_extra && i < 4; ++i) extra[i] = s->m_own + i;
+        if (n_extra) CU(c, cudaMemcpyAsync(s->d_pf_list + s->pf_count, extra, n_extra * 8, cudaMemcpyHostToDevice, c->stream));
+        pre_list = s->d_pf_list;
+        pre_count = s->pf_count + n_extra;
+    }
     const char* err = "";
     cudaError_t e = snp_run(s->work, a, *p, max_clust_length, c->d_bases, c->d_off, c->n_reads, c->sm_count, c->stream,
-                            counts, &c->launches, &err, &c->timer);
+                            counts, &c->launches, &err, &c->timer, pre_list, pre_count);
+    if (pre_list && e == cudaSuccess) {  // K3a's count of length-passing clusters, from the scan's own histogram
+        uint64_t na = 0;
+        for (int l = 2 * p->mcov_out; l <= max_clust_length; ++l) na += s->h_res.hist[l];
+        for (uint32_t i = 0; i < s->merged.n_adopt; ++i)
+            na += int64_t(s->merged.adopt_len[i]) >= 2 * p->mcov_out && int64_t(s->merged.adopt_len[i]) <= max_clust_length;
+        counts->n_analysed = na;
+    }
     if (e == cudaErrorInvalidValue && err && strstr(err, "outside the staged reads")) return fail(c, E2S_ERR_UNSUPPORTED, err);
     if (e != cudaSuccess) return cuda_fail(c, e, err);
     // the packed candidates are already in pinned host memory (K4 wrote them there); they are expanded
@@ -1043,7 +1098,13 @@ int e2s_pipeline_resident(e2s_shard* s, uint32_t k, int32_t min_len, const e2s_s
     memset(res, 0, sizeof *res);
     res->h2d_bytes = h2d;
     res->d2h_bytes = d2h;
-    if ((rc = e2s_cluster_lm(s, k, min_len, &res->n_written, &res->n_clust_out))) return rc;
+    // both phases in one call: K2 can run clust2snp's BWT prefilter while it writes the records (set E2S_NO_FUSED_PREFILTER
+    // to keep the two phases apart as the CLIs have to)
+    const uint32_t arm_before = s->pf_arm;
+    s->pf_arm = (getenv("E2S_NO_FUSED_PREFILTER") || p->mcov_out < 1 || 2 * p->mcov_out > E2S_MAX_C_LEN) ? 0u : uint32_t(p->mcov_out);
+    rc = e2s_cluster_lm(s, k, min_len, &res->n_written, &res->n_clust_out);
+    s->pf_arm = arm_before;
+    if (rc) return rc;
     if (res->n_written == 0) return fail(c, E2S_ERR_UNSUPPORTED, "no clusters (the reference divides by zero here)");
     e2s_stats st;
     if ((rc = e2s_statistics(s, &st))) return rc;

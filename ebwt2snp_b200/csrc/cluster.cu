@@ -31,6 +31,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "planes.cuh"
 
 namespace e2s {
 
@@ -198,6 +199,10 @@ constexpr int EM_WPT = 4;                               // 32-bit words per thre
 constexpr int EM_TILE_WORDS = EM_THREADS * EM_WPT;      // 1024 words = 32768 positions
 constexpr int EM_TILE_POS = EM_TILE_WORDS * 32;
 constexpr int EM_CAP = 2048;                            // ENDs per scatter window
+constexpr int EM_PF_HALO = 160;                         // BWT bytes before the tile (clusters <= 150 long that end in it), multiple of 16
+constexpr int EM_PF_BYTES = EM_TILE_POS + EM_PF_HALO;   // BWT window of one tile
+constexpr int EM_PF_CHUNKS = EM_PF_BYTES / 16;
+constexpr int EM_PF_SMEM = EM_PF_BYTES + 2 * EM_PF_CHUNKS * 2 + 16;  // window + two 16-bit plane arrays (dynamic shared memory)
 constexpr int EM_DESC_WORDS = 8;                        // u64 words per chunk descriptor
 constexpr int EM_MAX_CHUNKS = 148 * 8 * 2;              // upper bound of the grid (descriptor allocation)
 
@@ -268,10 +273,21 @@ __device__ __forceinline__ bool has_zero_byte(uint32_t x) { return ((x - 0x01010
 __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
     __shared__ EmitShared sh;
     __shared__ unsigned long long s_chunk;
+    __shared__ uint64_t pf_bar;
+    extern __shared__ __align__(128) uint8_t pf_smem[];  // fused prefilter only: BWT window, then the two planes
+    const bool pf = p.pf_mcov != 0;
+    uint16_t* pf_b0 = reinterpret_cast<uint16_t*>(pf_smem + EM_PF_BYTES);
+    uint16_t* pf_b1 = pf_b0 + EM_PF_CHUNKS;
+    uint32_t pf_parity = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int spread = p.min_len >= 2 ? p.min_len - 2 : -1;  // extra positions a START shadows; -1: nothing is dropped
 
     for (int i = tid; i < E2S_HIST_BINS; i += EM_THREADS) sh.hist[i] = 0;
+    if (pf && tid == 0) {
+        mbar_init(&pf_bar, 1);
+        fence_mbar_init();
+    }
+    const bool pf_simple = pf && p.bwt_not_simple && *p.bwt_not_simple == 0;
     // Chunks are handed out by a ticket, so every chunk with a smaller id is owned by a CTA that is already
     // running: the spin-waits of the exchange cannot deadlock whatever else occupies the SMs.
     if (tid == 0) s_chunk = atomicAdd(&p.res->ticket, 1ull);
@@ -440,6 +456,11 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
         const uint32_t S[EM_WPT] = {s4.x, s4.y, s4.z, s4.w};
         const uint32_t E[EM_WPT] = {e4.x, e4.y, e4.z, e4.w};
         const uint64_t tile_gbase = p.global_off + t * uint64_t(EM_TILE_POS);
+        const bool pf_tile = pf && write;
+        if (pf_tile && tid == 0) {  // BWT bytes of the tile and of the 160 positions before it, by the bulk-copy engine
+            mbar_expect_tx(&pf_bar, EM_PF_BYTES);
+            bulk_g2s(pf_smem, p.bwt + (int64_t(t) * EM_TILE_POS - EM_PF_HALO), EM_PF_BYTES, &pf_bar);
+        }
         reinterpret_cast<uint4*>(sh.smask)[tid] = s4;
         reinterpret_cast<uint4*>(sh.emask)[tid] = e4;
         uint32_t D[EM_WPT] = {0, 0, 0, 0};
@@ -497,6 +518,11 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
                 sh.t_first_e = fe;
             }
         }
+        if (pf_tile) {  // bit planes of the base code for the prefilter (planes.cuh); read by the dense pass after barrier (2)
+            mbar_wait(&pf_bar, pf_parity);
+            pf_parity ^= 1u;
+            build_planes(pf_smem, EM_PF_CHUNKS, pf_b0, pf_b1, pf_simple, tid, EM_THREADS);
+        }
         uint32_t base = inc - pk, tot = 0;
 #pragma unroll
         for (int q = 0; q < EM_WARPS; ++q) {
@@ -520,6 +546,15 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
             return X - OPEN_BIAS;
         };
 
+        // fused prefilter of find_variants on a record just written at index o (ref:clust2snp.cpp:402-429, planes.cuh)
+        auto prefilter = [&](uint64_t st, uint32_t len, uint64_t o) {
+            if (len < 2 * p.pf_mcov || len > uint32_t(MAX_C_LEN)) return;
+            const uint32_t lo = uint32_t(st + EM_PF_HALO - tile_gbase);  // window coordinates; st >= tile_gbase - 149
+            if (frequent_codes(reinterpret_cast<const uint32_t*>(pf_b0), reinterpret_cast<const uint32_t*>(pf_b1), lo, lo + len, p.pf_mcov) >= 2) {
+                const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
+                if (at < p.pf_cap) p.pf_list[at] = o;
+            }
+        };
         // The list holds the ENDs that will be written: all of them in EXACT mode (D = 0), the kept ones otherwise
         // (the carried-in END counts as kept until the exchange has tested it).
         const uint32_t nL = nE - nD, cL = cE - cD, myLbase = myEbase - myDbase;
@@ -580,6 +615,7 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
                     acc_bases += len;
                     if (len <= MAX_C_LEN) atomicAdd(&sh.hist[len], 1u);
                     if (o + 1 == chunk_end) atomicMax(&p.res->last_rec, (unsigned long long)(((o + 1) << 16) | len));
+                    if (pf_tile) prefilter(st, len, o);
                 }
             } else if (warp == 0) {
                 // EXACT: one warp pairs, tests and ranks every END in order (min_len > 33, or a very long cluster nearby)
@@ -616,6 +652,7 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
                                 acc_bases += len;
                                 if (len <= MAX_C_LEN) atomicAdd(&sh.hist[len], 1u);
                                 if (o + 1 == chunk_end) atomicMax(&p.res->last_rec, (unsigned long long)(((o + 1) << 16) | len));
+                                if (pf_tile) prefilter(st, len, o);
                             }
                         }
                     }
@@ -872,13 +909,17 @@ uint64_t emit_desc_words() { return uint64_t(EM_MAX_CHUNKS) * EM_DESC_WORDS; }
 
 cudaError_t launch_emit(const EmitParams& p0, int sm_count, cudaStream_t stream) {
     EmitParams p = p0;
-    static int occ_dev[64] = {0};
+    const int mode = p.pf_mcov ? 1 : 0;  // the fused prefilter needs the BWT window + planes in dynamic shared memory
+    const size_t smem = mode ? size_t(EM_PF_SMEM) : 0;
+    static int occ_dev[64][2] = {{0}};  // function attributes are per device
     int dev = 0;
     cudaGetDevice(&dev);
-    int& occ = occ_dev[dev & 63];
+    int& occ = occ_dev[dev & 63][mode];
     if (!occ) {
+        cudaError_t e = cudaFuncSetAttribute(k_cluster_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EM_PF_SMEM));
+        if (e != cudaSuccess) return e;
         int o = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_cluster_emit, EM_THREADS, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_cluster_emit, EM_THREADS, smem);
         if (e != cudaSuccess) return e;
         if (o < 1) return cudaErrorLaunchOutOfResources;
         occ = o;
@@ -886,7 +927,7 @@ cudaError_t launch_emit(const EmitParams& p0, int sm_count, cudaStream_t stream)
     uint64_t grid = uint64_t(sm_count) * occ;  // one chunk per CTA
     if (grid > p.num_tiles) grid = p.num_tiles;
     if (grid > EM_MAX_CHUNKS) grid = EM_MAX_CHUNKS;
-    k_cluster_emit<<<dim3(unsigned(grid)), dim3(EM_THREADS), 0, stream>>>(p);
+    k_cluster_emit<<<dim3(unsigned(grid)), dim3(EM_THREADS), smem, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -11,7 +11,8 @@ namespace e2s {
 // Every per-position array is allocated with PAD_L elements before local position 0 and
 // enough elements after n_local for the right halo, rounded up so that every tile the
 // kernels touch is fully inside the allocation and 16-byte aligned.
-constexpr int PAD_L = 16;        // >= 2 (left LCP halo), multiple of 16 so byte arrays stay 16B aligned
+constexpr int PAD_L = 176;       // >= 2 (left LCP halo) and >= 160 (K2's fused prefilter reads the BWT bytes of clusters that end in a
+                                 // tile but start up to 149 positions before it); multiple of 16 so byte arrays stay 16B aligned
 constexpr int HALO_R = 160;      // >= E2S_MAX_C_LEN + 1, multiple of 16
 constexpr int MAX_C_LEN = 150;
 

@@ -39,7 +39,8 @@ struct ClusterDev {  // device-resident accumulators of one e2s_cluster_run (zer
     unsigned long long open_start;     // 1 + global START, 0 = none
     unsigned long long end_nm2_start;  // 1 + START of the cluster closed at n_global-2; ~0 = head; 0 = none
     unsigned long long overflow;
-    unsigned long long ticket;         // K2's tile dispenser
+    unsigned long long ticket;         // K2's chunk dispenser
+    unsigned long long n_pf;           // fused prefilter: clusters appended to (or dropped from, beyond its capacity) the survivor list
     unsigned long long last_rec;       // (index of the last kept record + 1) << 16 | its length
     unsigned long long tail_lcp_nm2, tail_lcp_nm1, tail_bwt_nm1;  // last shard: lcp[n-2], lcp[n-1], bwt[n-1]
     unsigned long long n_bases;        // sum of the kept records' lengths
@@ -65,6 +66,12 @@ struct EmitParams {  // K2
     uint16_t* out_len;
     uint64_t cap;
     uint64_t* desc;      // chunk descriptors (emit_desc_words() words, zeroed before the launch)
+    // fused BWT prefilter of find_variants (pipeline mode: the caller already knows clust2snp's -m); pf_mcov = 0: off
+    const uint8_t* bwt;             // local position 0 (PAD_L readable bytes before it)
+    const uint32_t* bwt_not_simple; // seal-time alphabet flag (planes.cuh)
+    uint32_t pf_mcov;
+    uint64_t* pf_list;              // out: indices (in this shard's record list) of clusters that need the exact test, unordered
+    uint64_t pf_cap;
     uint64_t* dbg;       // optional: 4 globaltimer stamps per chunk (start, pass 1 done, exchange done, end); null = off
     ClusterDev* res;
     const uint32_t* tail_lcp;  // &lcp[n_global-2] when this is the last shard, else null
@@ -137,10 +144,11 @@ void snp_work_destroy(SnpWork* w);
 // Runs K3a/K3x/K3b/K4 back to back on the stream with device-resident counts and synchronises ONCE at the
 // end; the packed events are written by K4 straight into pinned host memory.  If a capacity guess
 // (survivor / flagged lists) was too small the pass is repeated with larger buffers.
+// pre_list / pre_count: survivors of the prefilter when K2 already ran it (fused mode), else null / 0.
 cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int max_clust_length,
                     const uint8_t* d_read_bases, const uint64_t* d_read_off, uint64_t n_reads, int sm_count,
                     cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err,
-                    KernelTimer* timer);
+                    KernelTimer* timer, const uint64_t* pre_list, uint64_t pre_count);
 cudaError_t snp_fetch_events(SnpWork* w, e2s_event* host, uint64_t cap, uint64_t* n, cudaStream_t stream);
 
 }  // namespace e2s

@@ -29,6 +29,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "planes.cuh"
 
 namespace e2s {
 
@@ -120,34 +121,6 @@ __global__ void k_tile_first(const uint64_t* __restrict__ cl_start, uint64_t m, 
     tile_first[t] = lo;
 }
 
-// 0x80 in every byte of u that equals the corresponding byte of pat (exact, no cross-byte borrow)
-__device__ __forceinline__ uint32_t eq_bytes(uint32_t u, uint32_t pat) {
-    const uint32_t t = u ^ pat;
-    return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
-}
-// four byte flags (0x80 each) -> 4 bits
-__device__ __forceinline__ uint32_t nibble(uint32_t f) { return (((f >> 7) * 0x01020408u) >> 24) & 0xFu; }
-
-// Bit-sliced base code of four bytes, valid for the bytes k_bwt_alphabet accepts: with u = byte & 0xDF,
-//   bit 1 of the code (G, T) = u.bit2 & u.bit6        bit 0 (C, T) = (u.bit1 & ~u.bit2) | u.bit4
-// (A = 0x41, C = 0x43, G = 0x47, T = 0x54; '$' = 0x24 and NUL give 0 like every non-ACGT byte must).  Result: bit 0 of each byte.
-__device__ __forceinline__ uint32_t fast_b1(uint32_t w) {
-    const uint32_t u = w & 0xDFDFDFDFu;
-    return (u >> 2) & (u >> 6) & 0x01010101u;
-}
-__device__ __forceinline__ uint32_t fast_b0(uint32_t w) {
-    const uint32_t u = w & 0xDFDFDFDFu;
-    return (((u >> 1) & ~(u >> 2)) | (u >> 4)) & 0x01010101u;
-}
-
-// both at once: plane 0 at bit 0 and plane 1 at bit 4 of every byte  (fast_b0(w) | fast_b1(w) << 4 with shared shifts)
-__device__ __forceinline__ uint32_t fast_b01(uint32_t w) {
-    const uint32_t u = w & 0xDFDFDFDFu, b = u >> 2;
-    const uint32_t x = ((u >> 1) & ~b) | (u >> 4);  // bit 0 of every byte: plane 0
-    const uint32_t y = (u << 2) & b;                // bit 4 of every byte: u.bit2 & u.bit6
-    return (x & 0x01010101u) | (y & 0x10101010u);
-}
-
 // Runs once when a shard is sealed: *flag != 0 iff some BWT byte's exact base code (base_code) differs from the
 // bit-sliced one above, in which case K3a keeps the per-byte equality tests.
 __global__ void __launch_bounds__(256) k_bwt_alphabet(const uint8_t* __restrict__ bwt, uint64_t count, uint32_t* flag) {
@@ -222,40 +195,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
         }
         mbar_wait(&full_bar[stage], parity);
         // ---- bit planes of the base code: A=00 C=01 G=10 T=11, everything else 00 ----
-        if (simple) {
-            // the shard's BWT was proven (k_bwt_alphabet, at seal) to hold only bytes on which the code is a plain
-            // function of four bits of the case-folded byte (ACGT, acgt, '$', NUL, ...): no per-byte equality tests
-            for (int ch = tid; ch < PS_CHUNKS; ch += PS_THREADS) {
-                const uint4 q = lds128(st + ch * 16);
-                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                // one multiply per word gathers both planes: with the bit-0 flags of plane 0 at bit 0 and those of plane 1
-                // at bit 4 of every byte, (x * 0x01020408) >> 24 = plane-1 nibble << 4 | plane-0 nibble (no two partial
-                // products meet, so there are no carries)
-                uint32_t B = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) B |= ((fast_b01(w[j]) * 0x01020408u) >> 24) << (8 * j);
-                uint32_t lo = B & 0x0F0F0F0Fu, hi = (B >> 4) & 0x0F0F0F0Fu;  // byte j = nibble of word j
-                lo = (lo | (lo >> 4)) & 0x00FF00FFu;
-                hi = (hi | (hi >> 4)) & 0x00FF00FFu;
-                s_b0[ch] = uint16_t(lo | (lo >> 8));
-                s_b1[ch] = uint16_t(hi | (hi >> 8));
-            }
-        } else {
-            for (int ch = tid; ch < PS_CHUNKS; ch += PS_THREADS) {
-                const uint4 q = lds128(st + ch * 16);
-                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                uint32_t b0 = 0, b1 = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t u = w[j] & 0xDFDFDFDFu;  // case-insensitive
-                    const uint32_t eC = eq_bytes(u, 0x43434343u), eG = eq_bytes(u, 0x47474747u), eT = eq_bytes(u, 0x54545454u);
-                    b0 |= nibble(eC | eT) << (4 * j);
-                    b1 |= nibble(eG | eT) << (4 * j);
-                }
-                s_b0[ch] = uint16_t(b0);
-                s_b1[ch] = uint16_t(b1);
-            }
-        }
+        build_planes(st, PS_CHUNKS, s_b0, s_b1, simple, tid, PS_THREADS);
         __syncthreads();  // planes complete; the byte tile is no longer needed
         if (tid == 0) {
             uint64_t tn = t + uint64_t(PS_STAGES) * gridDim.x;
@@ -272,21 +212,8 @@ __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
             }
             if (c_len >= p.min_len && c_len <= p.max_len) {
                 ++n_analysed;
-                const uint32_t lo = uint32_t(c_start - tile_gbase), hi = lo + c_len;  // [lo, hi)
-                uint32_t nC = 0, nG = 0, nT = 0;
-                for (uint32_t wi = lo >> 5; wi <= (hi - 1) >> 5; ++wi) {
-                    uint32_t mask = FULL;
-                    if (wi == (lo >> 5)) mask &= FULL << (lo & 31);
-                    if (wi == ((hi - 1) >> 5)) mask &= FULL >> (31 - ((hi - 1) & 31));
-                    const uint32_t x0 = w0[wi] & mask, x1 = w1[wi] & mask;
-                    nT += __popc(x0 & x1);
-                    nC += __popc(x0 & ~x1);
-                    nG += __popc(x1 & ~x0);
-                }
-                const uint32_t nA = c_len - nC - nG - nT;
-                const uint32_t frequent = uint32_t(nA >= p.mcov) + uint32_t(nC >= p.mcov) + uint32_t(nG >= p.mcov) +
-                                          uint32_t(nT >= p.mcov);
-                if (frequent >= 2) {  // rare (variants, repeats): plain atomic append, the exact test does not need an order
+                const uint32_t lo = uint32_t(c_start - tile_gbase);
+                if (frequent_codes(w0, w1, lo, lo + c_len, p.mcov) >= 2) {  // rare (variants, repeats): plain atomic append, the exact test does not need an order
                     const unsigned long long at = atomicAdd(&p.dev->n_survivors, 1ull);
                     if (at < p.cap_surv) p.survivors[at] = c;
                 }
@@ -311,8 +238,10 @@ constexpr int EX_G = 8;  // lanes per cluster
 struct ExactParams {
     SnpArrays a;
     const uint64_t* list;      // cluster indices to test
-    const unsigned long long* n_list;  // device-resident length of the list
+    const unsigned long long* n_list;  // device-resident length of the list; null: n_list_host
+    uint64_t n_list_host;
     uint64_t cap_list;         // capacity of the list (the pass is repeated when it was too small)
+    uint32_t min_len, max_len; // 2 * mcov_out, max_clust_length (a fused prefilter only knew max_len <= 150)
     uint32_t mcov, k_right;
     uint32_t nr1_lo, nr1_big;
     uint32_t* flag_words;      // out: bit per cluster = passes the find_variants filters
@@ -323,13 +252,15 @@ __global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
     const int lane = threadIdx.x & 31;
     const int gl = lane & (EX_G - 1);
     const uint32_t gmask = ((1u << EX_G) - 1u) << (lane & ~(EX_G - 1));
-    const uint64_t n_list = *p.n_list < p.cap_list ? *p.n_list : p.cap_list;
+    const uint64_t n_avail = p.n_list ? *p.n_list : p.n_list_host;
+    const uint64_t n_list = n_avail < p.cap_list ? n_avail : p.cap_list;
     const uint64_t groups = uint64_t(gridDim.x) * (EX_THREADS / EX_G);
     uint32_t saw_n = 0;
     for (uint64_t i = (uint64_t(blockIdx.x) * EX_THREADS + threadIdx.x) / EX_G; i < n_list; i += groups) {
         const uint64_t ci = p.list[i];
         const uint64_t lp = p.a.cl_start[ci] - p.a.global_off;
         const uint32_t len = p.a.cl_len[ci];
+        if (len < p.min_len || len > p.max_len) continue;  // group-uniform
         unsigned long long acc = 0, best = 0;
         for (uint32_t j = gl; j < len; j += EX_G) {
             const uint32_t tx = p.a.text[lp + j];
@@ -836,7 +767,7 @@ static cudaError_t ensure(T*& ptr, size_t& cap, size_t need) {
 cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int max_clust_length,
                     const uint8_t* d_read_bases, const uint64_t* d_read_off, uint64_t n_reads, int sm_count,
                     cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err,
-                    KernelTimer* timer) {
+                    KernelTimer* timer, const uint64_t* pre_list, uint64_t pre_count) {
     memset(counts, 0, sizeof *counts);
     w->n_cand = 0;
     w->k_left = p.k_left;
@@ -902,6 +833,7 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
         }
 
 
+        if (!pre_list) {
         k_tile_first<<<(num_tiles + 1 + 255) / 256, 256, 0, stream>>>(a.cl_start, a.m, a.global_off, num_tiles, w->tile_first);
         CK(cudaGetLastError());
         ++*launches;
@@ -935,12 +867,16 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             CK(cudaGetLastError());
             ++*launches;
         }
+        }
         {   // K3x: exact filters on the survivors
             ExactParams ep;
             ep.a = a;
-            ep.list = w->survivors;
-            ep.n_list = &w->dev->n_survivors;
-            ep.cap_list = cap_surv;
+            ep.list = pre_list ? pre_list : w->survivors;
+            ep.n_list = pre_list ? nullptr : &w->dev->n_survivors;
+            ep.n_list_host = pre_count;
+            ep.cap_list = pre_list ? pre_count : cap_surv;
+            ep.min_len = uint32_t(2 * p.mcov_out);
+            ep.max_len = uint32_t(max_clust_length);
             ep.mcov = uint32_t(p.mcov_out);
             ep.k_right = uint32_t(p.k_right);
             ep.nr1_lo = nr1_lo;

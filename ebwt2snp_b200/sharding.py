@@ -203,6 +203,7 @@ def hot_path_step(shard: "api.Shard", params: api.SnpParams, k, min_len, device,
     """One pass of the hot path on this rank's resident shard, collectives included.
     -> (ClusterMerged, Stats (global), SnpCounts (this shard), EventIdOffset: .resolve() gives the first id_nr of this shard)"""
     rank, world = _world(group)
+    shard.cluster_prefilter(params.mcov_out)  # both phases run here: K2 applies the BWT prefilter while it writes the records
     s = shard.cluster_run(k, min_len)
     if world == 1:
         mg = api.cluster_merge([s], 0)

@@ -140,6 +140,12 @@ typedef struct {
     uint64_t adopt_start[3]; uint64_t adopt_len[3];
 } e2s_cluster_merged;
 
+/* Fused mode for callers that run both phases on resident data: from now on e2s_cluster_run also applies clust2snp's
+ * BWT-only prefilter for this -m (find_variants, ref:clust2snp.cpp:402-429) while it writes the records, and a later
+ * e2s_find_events with the same -m skips its own pass over the BWT.  0 switches it off (the default; the CLIs, which
+ * are separate processes as in the reference, never use it).  Results are identical either way. */
+int e2s_cluster_prefilter(e2s_shard *sh, int mcov_out);
+
 /* K1+K2 on the shard: LCP boundary stencil + decoupled look-back scan + compaction.
  * Records stay on the device; *summary is written on the host. */
 int e2s_cluster_run(e2s_shard *sh, uint32_t k, int32_t min_len, e2s_cluster_summary *summary);

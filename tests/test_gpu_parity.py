@@ -265,3 +265,57 @@ def test_rejects_unsorted_clusters(ctx):
     with pytest.raises(api.E2SError):
         sh.find_events(api.default_params(rs.nreads1), 150)
     sh.close()
+
+
+@pytest.mark.parametrize("name,seed", [("tiny", 3), ("small", 2)])
+def test_fused_prefilter_equals_two_phase(ctx, name, seed, monkeypatch):
+    """e2s_pipeline_resident / e2s_cluster_prefilter: K2 runs clust2snp's BWT prefilter while writing the records.
+    Same events as the two-phase path and as the oracle, for several -m, incl. sharded runs (adopted records)."""
+    rs, e = H.dataset(name, seed)
+    n = e["n"]
+    es, el, _, _ = O.cluster_lm(e["lcp"], e["bwt"], 16, 2)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    ctx.stage_reads(rs.reads, off)
+    for mcov in (5, 3, 8):
+        p, op = api.default_params(rs.nreads1, mcov_out=mcov), O.default_params(rs.nreads1, mcov_out=mcov)
+        ost = O.statistics(es, el, mcov, op.pval)
+        otext, ores = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+        sh = ctx.shard(n)
+        sh.load_soa(e["lcp"], e["text"], e["suff"], e["bwt"])
+        sh.seal()
+        res = sh.pipeline_resident(p, 16, 2)
+        assert sh.cluster_fetch_packed() == O.clusters_to_bytes(es, el)
+        assert (res.snp.n_analysed, res.snp.n_candidates, res.snp.n_events) == (ores.n_analysed, ores.n_candidates, ores.n_events), mcov
+        assert res.max_clust_length == ost.max_clust_length
+        assert api.events_format(sh.events(), p) == otext, mcov
+        # a different -m afterwards must not reuse the armed prefilter's list
+        p2 = api.default_params(rs.nreads1, mcov_out=mcov + 1)
+        st2 = sh.statistics(p2.mcov_out, p2.pval)
+        sh.find_events(p2, st2.max_clust_length)
+        op2 = O.default_params(rs.nreads1, mcov_out=mcov + 1)
+        ost2 = O.statistics(es, el, mcov + 1, op2.pval)
+        assert api.events_format(sh.events(), p2) == O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op2, ost2.max_clust_length, rs.reads, off)[0]
+        sh.close()
+    # sharded, fused: every record is prefiltered by the shard that wrote it or adopted by the shard that analyses it
+    p, op = api.default_params(rs.nreads1), O.default_params(rs.nreads1)
+    ost = O.statistics(es, el, 5, op.pval)
+    otext, ores = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+    cuts = [0, n // 3 + 7, 2 * n // 3 - 11, n]
+    shards, sums = [], []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        sh = ctx.shard(hi - lo, lo, n)
+        a, b = max(0, lo - 2), min(n, hi + 151)
+        sh.load_soa(e["lcp"][a:b], e["text"][a:b], e["suff"][a:b], e["bwt"][a:b], first=a)
+        sh.seal()
+        sh.cluster_prefilter(5)
+        sums.append(sh.cluster_run(16, 2))
+        shards.append(sh)
+    texts, first_id, ncand = [], 1, 0
+    for g, sh in enumerate(shards):
+        sh.cluster_finalize(api.cluster_merge(sums, g))
+        cnt = sh.find_events(p, ost.max_clust_length)
+        texts.append(api.events_format(sh.events(), p, first_id=first_id))
+        first_id += cnt.n_events
+        ncand += cnt.n_candidates
+        sh.close()
+    assert ncand == ores.n_candidates and b"".join(texts) == otext
