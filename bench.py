@@ -414,13 +414,16 @@ def main():
     # positions inside analysed clusters: from the (global) histogram, scaled to this shard for world > 1
     pos_analysed = sum(int(st.hist[l]) * l for l in range(lo, hi + 1)) / world
     # algorithmic bytes per launch (DESIGN.md "Kernels"): what the kernel has to move for this shard
+    fused = ktimes[api.KERNEL_SCAN][1] == 0             # K2 ran the BWT prefilter itself (e2s_cluster_prefilter): no K3a launch
     alg = {
         api.KERNEL_FLAGS: 4 * n + n / 4,                # LCP read once + 2 bit masks written
-        api.KERNEL_EMIT: n / 4 + 10 * m_own,            # bit masks read + 10-byte records written
+        api.KERNEL_EMIT: n / 4 + 10 * m_own + (pos_analysed if fused else 0),  # masks read + records written (+ BWT bytes in analysed clusters)
         api.KERNEL_SCAN: pos_analysed + 10 * m_own,     # BWT byte of positions in analysed clusters + record list
         api.KERNEL_EXACT: 0,
     }
     streamed = {api.KERNEL_SCAN: n + 10 * m_own}        # the tiles also carry the positions outside clusters
+    if fused:
+        streamed[api.KERNEL_EMIT] = n / 2 + 10 * m_own + n  # masks twice (count pass + write pass) + every BWT byte
     kern = {}
     ksum_ms = 0.0
     for kid, name in KERNELS.items():
@@ -445,7 +448,11 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
                     "frac": kern[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
                     "ms_per_launch": kern[dom]["ms"], "alg_bytes_per_launch": kern[dom]["alg_bytes"],
-                    "kernels": kern, "kernel_share_of_step": ksum_ms / ms if ms else None}
+                    "kernels": kern, "kernel_share_of_step": ksum_ms / ms if ms else None,
+                    "fused_prefilter": bool(fused),
+                    "pipeline": {"alg_bytes_per_step": sum(alg[k] for k in alg if ktimes[k][1]),
+                                 "GBps": sum(alg[k] for k in alg if ktimes[k][1]) / (ms / args.steps * 1e-3) / 1e9,
+                                 "frac_of_peak": sum(alg[k] for k in alg if ktimes[k][1]) / (ms / args.steps * 1e-3) / 1e9 / peak}}
 
     # ---- e2e: the C-ABI pipeline call from pinned host buffers, copies inside the timed region ----
     e2e = None

@@ -78,14 +78,20 @@ __device__ __forceinline__ void build_planes(const uint8_t* st, int n_chunks, ui
 // A cluster with at most one such code cannot pass find_variants (ref:clust2snp.cpp:402-429): counts[s][c] <= total[c].
 __device__ __forceinline__ uint32_t frequent_codes(const uint32_t* w0, const uint32_t* w1, uint32_t lo, uint32_t hi, uint32_t mcov) {
     uint32_t nC = 0, nG = 0, nT = 0;
-    for (uint32_t wi = lo >> 5; wi <= (hi - 1) >> 5; ++wi) {
-        uint32_t mask = 0xffffffffu;
-        if (wi == (lo >> 5)) mask &= 0xffffffffu << (lo & 31);
-        if (wi == ((hi - 1) >> 5)) mask &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+    auto add = [&](uint32_t wi, uint32_t mask) {
         const uint32_t x0 = w0[wi] & mask, x1 = w1[wi] & mask;
         nT += __popc(x0 & x1);
         nC += __popc(x0 & ~x1);
         nG += __popc(x1 & ~x0);
+    };
+    const uint32_t wlo = lo >> 5, whi = (hi - 1) >> 5;
+    const uint32_t m_first = 0xffffffffu << (lo & 31), m_last = 0xffffffffu >> (31 - ((hi - 1) & 31));
+    if (wlo == whi) {
+        add(wlo, m_first & m_last);
+    } else {
+        add(wlo, m_first);
+        for (uint32_t wi = wlo + 1; wi < whi; ++wi) add(wi, 0xffffffffu);
+        add(whi, m_last);
     }
     const uint32_t nA = (hi - lo) - nC - nG - nT;
     return uint32_t(nA >= mcov) + uint32_t(nC >= mcov) + uint32_t(nG >= mcov) + uint32_t(nT >= mcov);

@@ -319,3 +319,34 @@ def test_fused_prefilter_equals_two_phase(ctx, name, seed, monkeypatch):
         ncand += cnt.n_candidates
         sh.close()
     assert ncand == ores.n_candidates and b"".join(texts) == otext
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_non_acgt_bwt_bytes_use_exact_planes(ctx, fused):
+    """bytes outside the seal-time 'simple alphabet' ('#', 0xff, 'x'): K3a / fused K2 must fall back to per-byte equality
+    tests; every such byte counts as 'A' (ref:include.hpp:277)"""
+    rs, e = H.dataset("small", 3)
+    n = e["n"]
+    rng = np.random.default_rng(12)
+    bwt = e["bwt"].copy()
+    hit = rng.random(n) < 0.02
+    bwt[hit] = rng.choice(np.frombuffer(b"#\xffxE", dtype=np.uint8), size=int(hit.sum()))
+    es, el, _, _ = O.cluster_lm(e["lcp"], bwt, 16, 2)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    ctx.stage_reads(rs.reads, off)
+    p, op = api.default_params(rs.nreads1), O.default_params(rs.nreads1)
+    ost = O.statistics(es, el, op.mcov_out, op.pval)
+    otext, ores = O.find_events(e["lcp"], e["text"], e["suff"], bwt, es, el, op, ost.max_clust_length, rs.reads, off)
+    sh = ctx.shard(n)
+    sh.load_soa(e["lcp"], e["text"], e["suff"], bwt)
+    sh.seal()
+    if fused:
+        res = sh.pipeline_resident(p, 16, 2)
+        cnt = res.snp
+    else:
+        sh.cluster_lm(16, 2)
+        st = sh.statistics(p.mcov_out, p.pval)
+        cnt = sh.find_events(p, st.max_clust_length)
+    assert (cnt.n_analysed, cnt.n_candidates) == (ores.n_analysed, ores.n_candidates)
+    assert api.events_format(sh.events(), p) == otext and ores.n_candidates > 0
+    sh.close()
