@@ -301,6 +301,9 @@ def main():
     ap.add_argument("--cpu-positions", type=float, default=3e7, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tiles", type=int, default=1,
+                    help="resident-only study: tile the workload T times on the GPU (read ids shifted; every tile starts with "
+                         "lcp = 0), e.g. --tiles 8 = 4.46e9 positions, C3/C4-sized shards; implies --no-e2e --no-cpu-baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -324,7 +327,13 @@ def main():
 
     # ---- data: every rank owns one C2-size tile of a global eBWT of world * n positions (weak scaling) ----
     rs, eg = make_dataset(args.workload, args.seed + rank, args.scale, dev)
-    n = int(eg["n"])
+    T = max(1, args.tiles)
+    if T > 1:
+        args.no_e2e = args.no_cpu_baseline = True
+        if world > 1:
+            raise SystemExit("--tiles is a single-GPU study")
+    n_tile = int(eg["n"])
+    n = n_tile * T
     n_all = [n]
     if world > 1:
         t = torch.tensor([n], dtype=torch.int64, device=dev)
@@ -336,7 +345,9 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     ctx = api.Context(local, stream.cuda_stream)
     sh = ctx.shard(n, global_off, n_global)
-    sh.load_soa(eg["lcp"], eg["text"], eg["suff"], eg["bwt"], first=global_off, device=True)
+    R0 = rs.reads.shape[0]
+    for t in range(T):
+        sh.load_soa(eg["lcp"], eg["text"] + t * R0 if t else eg["text"], eg["suff"], eg["bwt"], first=global_off + t * n_tile, device=True)
     # halo exchange over NCCL: my left neighbour's last 2 records, my right neighbour's first 151
     left, right = sharding.exchange_halo(eg["lcp"], eg["text"], eg["suff"], eg["bwt"], dev)
     if left is not None:
@@ -344,8 +355,11 @@ def main():
     if right is not None:
         sh.load_soa(right["lcp"], right["text"], right["suff"], right["bwt"], first=global_off + n, device=True)
     sh.seal()
-    reads_dev = torch.from_numpy(rs.reads).to(dev).view(-1)
-    R, L = rs.reads.shape
+    reads_dev = torch.from_numpy(rs.reads).to(dev)
+    if T > 1:
+        reads_dev = reads_dev.repeat(T, 1)
+    reads_dev = reads_dev.contiguous().view(-1)
+    R, L = rs.reads.shape[0] * T, rs.reads.shape[1]
     off_dev = (torch.arange(R + 1, dtype=torch.int64, device=dev) * L)
     ctx.stage_reads(reads_dev, off_dev, device=True, n_bases=R * L)
     params = api.default_params(rs.nreads1)
@@ -497,7 +511,7 @@ def main():
             "config": {"workload": workload_name(args), "positions_per_gpu": n, "positions_total": n_global,
                        "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; NCCL all-gather of shard summaries",
                        "l2": "inputs (13 B/position, >= 7 GB per GPU at C2) exceed the 126 MB L2; no flush needed",
-                       "scale": args.scale},
+                       "scale": args.scale, "tiles": T},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "results": {"n_written": int(mg.total_written), "n_clust_out": int(mg.n_clust_out),
                         "max_clust_length": int(st.max_clust_length), "n_analysed_rank0": int(cnt.n_analysed),
