@@ -414,8 +414,18 @@ def main():
         ms = float(t.item())
         mg, st, cnt = out
         step.ids.resolve()
+        # what the host-synchronised exchange between the phases costs by itself (same message size, no compute around it)
+        torch.cuda.synchronize()
+        probe_words = np.zeros(api.SUMMARY_WORDS + C.sizeof(api.Stats) // 8, dtype=np.uint64)
+        for _ in range(3):
+            sharding.all_gather_words(probe_words, dev)
+        t_ex = time.perf_counter()
+        for _ in range(20):
+            sharding.all_gather_words(probe_words, dev)
+        exchange_us = (time.perf_counter() - t_ex) / 20 * 1e6
     else:  # the one-call step returns the pipeline result; the histogram is still on the shard
         import types
+        exchange_us = None
         mg = types.SimpleNamespace(total_written=out.n_written, n_clust_out=out.n_clust_out)
         cnt = out.snp
         st = sh.statistics(params.mcov_out, params.pval)
@@ -511,7 +521,7 @@ def main():
             "config": {"workload": workload_name(args), "positions_per_gpu": n, "positions_total": n_global,
                        "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; NCCL all-gather of shard summaries",
                        "l2": "inputs (13 B/position, >= 7 GB per GPU at C2) exceed the 126 MB L2; no flush needed",
-                       "scale": args.scale, "tiles": T},
+                       "scale": args.scale, "tiles": T, "exchange_us": exchange_us},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "results": {"n_written": int(mg.total_written), "n_clust_out": int(mg.n_clust_out),
                         "max_clust_length": int(st.max_clust_length), "n_analysed_rank0": int(cnt.n_analysed),
