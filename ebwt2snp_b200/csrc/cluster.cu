@@ -1,4 +1,4 @@
-// Phase 1 (ebwt2clust): K1 = streaming LCP boundary stencil, K2 = decoupled look-back scan + compaction.
+// Phase 1 (ebwt2clust): K1 = streaming LCP boundary stencil, K2 = chunked reduce-then-scan + compaction.
 //
 // Replaces the sequential state machine of cluster_lm / append_entry (ref:ebwt2clust.cpp:54-139)
 // by its local-stencil form:
@@ -16,14 +16,12 @@
 //     conflict free), STAGES tiles in flight per CTA behind mbarriers; every thread owns 32 consecutive
 //     positions in registers and writes one 32-bit word per mask (a warp writes 128 contiguous bytes).
 //     Traffic: 4 B/position read + 0.25 B/position written.  No inter-CTA dependency.
-// K2  k_cluster_emit: decoupled look-back over the bit masks (0.25 B/position read; 262144 positions per
-//     tile, so 32x fewer descriptors than K1's tile size would give).  Two chained scans:
-//       #1 "cluster still open, started at s" state (a tile containing any event publishes its inclusive
-//          state immediately, so chains stop at the nearest tile with an event);
-//       #2 exclusive sum of kept-record counts = output offset (classic aggregate/inclusive descriptors,
-//          warp-parallel windows of 64 predecessors).
-//     Records are written compacted in position order: 10 B per record; their length histogram
-//     (statistics(), ref:clust2snp.cpp:899-907) is accumulated on the way.
+// K2  k_cluster_emit: works on the bit masks only.  One contiguous chunk of 32768-position tiles per CTA:
+//     a bit-parallel count pass, ONE exchange of per-chunk values between the CTAs, then the write pass
+//     (see the comment above the kernel).  Records come out compacted in position order, 10 B each; their
+//     length histogram (statistics(), ref:clust2snp.cpp:899-907) is accumulated on the way.  In fused mode
+//     (e2s_cluster_prefilter) the write pass also streams the BWT bytes and applies clust2snp's BWT-only
+//     prefilter (planes.cuh) to every record it writes.
 
 #include <cuda.h>
 #include <cuda_runtime.h>

@@ -10,7 +10,7 @@
 //                    frequent codes (true variants, repeats) go on to the exact test.
 //   k_cluster_exact  K3x: per-cluster 2x4 nucleotide histogram (sample = gSA text id < nreads1),
 //                    first-argmax LCP and the find_variants filters        ref:clust2snp.cpp:377-429
-//   k_flag_*         ordered compaction of a cluster bit mask into an index list
+//   k_flag_compact   ordered compaction of a cluster bit mask into an index list (one launch)
 //   k_candidates     K3b: ordered (ballot/popc) selection of the first <= c supporting reads per
 //                    sample and allele pair                                ref:clust2snp.cpp:431-496
 //   k_compact_slots  candidates in reference order
@@ -19,8 +19,11 @@
 //
 // K3a is the only phase-2 kernel that touches every position: it streams 16384-byte BWT tiles (+150
 // byte overhang) into shared memory with the TMA engine (cp.async.bulk, STAGES tiles in flight per
-// CTA), turns them into two bit-planes of the 2-bit base code and answers every cluster of the tile
-// with a few range popcounts (one thread per cluster).  Traffic: 1 B/position + 10 B/cluster.
+// CTA), turns them into two bit-planes of the 2-bit base code (planes.cuh) and answers every cluster of
+// the tile with a few range popcounts (one thread per cluster).  Traffic: 1 B/position + 10 B/cluster.
+// It does not run when K2 already applied the same prefilter while writing the records (fused mode,
+// e2s_cluster_prefilter): snp_run then starts from K2's survivor list.
+// The whole phase is enqueued with device-resident counts and synchronises once (snp_run).
 
 #include <cuda_runtime.h>
 #include <stdint.h>
