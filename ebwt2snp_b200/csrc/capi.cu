@@ -516,7 +516,14 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
         p.pf_list = nullptr;
         p.pf_cap = 0;
         if (p.pf_mcov) {
-            const uint64_t want = s->rec_cap / 16 + 4096;
+            uint64_t want = s->rec_cap / 16 + 4096;
+            if (const char* dbg = getenv("E2S_PF_CAPACITY")) {  // test hook: a tiny list forces the overflow -> two-phase fallback
+                const uint64_t v = strtoull(dbg, nullptr, 10);
+                if (v) {
+                    want = v;
+                    if (s->pf_cap > v) s->pf_cap = v;  // also shrink the advertised capacity of an existing buffer
+                }
+            }
             if (want > s->pf_cap) {
                 cudaFree(s->d_pf_list);
                 s->d_pf_list = nullptr;

@@ -350,3 +350,35 @@ def test_non_acgt_bwt_bytes_use_exact_planes(ctx, fused):
     assert (cnt.n_analysed, cnt.n_candidates) == (ores.n_analysed, ores.n_candidates)
     assert api.events_format(sh.events(), p) == otext and ores.n_candidates > 0
     sh.close()
+
+
+def test_fused_prefilter_overflow_falls_back(ctx, monkeypatch):
+    """K2's survivor list is bounded; when it overflows, find_events must ignore it and run its own pass over the BWT"""
+    rs, e = H.dataset("small", 1)
+    n = e["n"]
+    es, el, _, _ = O.cluster_lm(e["lcp"], e["bwt"], 16, 2)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    ctx.stage_reads(rs.reads, off)
+    p, op = api.default_params(rs.nreads1), O.default_params(rs.nreads1)
+    ost = O.statistics(es, el, op.mcov_out, op.pval)
+    otext, ores = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+    monkeypatch.setenv("E2S_PF_CAPACITY", "3")
+    sh = ctx.shard(n)
+    sh.load_soa(e["lcp"], e["text"], e["suff"], e["bwt"])
+    sh.seal()
+    launches0 = ctx.launches
+    res = sh.pipeline_resident(p, 16, 2)
+    assert res.snp.n_candidates == ores.n_candidates and res.snp.n_analysed == ores.n_analysed
+    assert api.events_format(sh.events(), p) == otext
+    monkeypatch.delenv("E2S_PF_CAPACITY")
+    fused_launches = None
+    sh2 = ctx.shard(n)
+    sh2.load_soa(e["lcp"], e["text"], e["suff"], e["bwt"])
+    sh2.seal()
+    l0 = ctx.launches
+    sh2.pipeline_resident(p, 16, 2)
+    fused_launches = ctx.launches - l0
+    assert api.events_format(sh2.events(), p) == otext
+    sh.close()
+    sh2.close()
+    assert fused_launches >= 6
