@@ -547,8 +547,12 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
         // fused prefilter of find_variants on a record just written at index o (ref:clust2snp.cpp:402-429, planes.cuh)
         auto prefilter = [&](uint64_t st, uint32_t len, uint64_t o) {
             if (len < 2 * p.pf_mcov || len > uint32_t(MAX_C_LEN)) return;
-            const uint32_t lo = uint32_t(st + EM_PF_HALO - tile_gbase);  // window coordinates; st >= tile_gbase - 149
-            if (frequent_codes(reinterpret_cast<const uint32_t*>(pf_b0), reinterpret_cast<const uint32_t*>(pf_b1), lo, lo + len, p.pf_mcov) >= 2) {
+            // clust2snp analyses the positions [st, st + len) with the WRAPPED 16-bit length: for a cluster of 65536 + len
+            // positions that range lies far before this tile's window -- leave the decision to the exact test
+            const bool outside = st + EM_PF_HALO < tile_gbase;
+            const uint32_t lo = uint32_t(st + EM_PF_HALO - tile_gbase);  // window coordinates (st >= tile_gbase - 160 here)
+            if (outside ||
+                frequent_codes(reinterpret_cast<const uint32_t*>(pf_b0), reinterpret_cast<const uint32_t*>(pf_b1), lo, lo + len, p.pf_mcov) >= 2) {
                 const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
                 if (at < p.pf_cap) p.pf_list[at] = o;
             }

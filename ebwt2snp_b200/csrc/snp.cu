@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
         // (the gathers are issued EV_B reads at a time so that their latencies overlap; the updates stay in list order)
         for (int i = lane; i < kl; i += 32) {
             uint32_t cnt = 0;  // four 8-bit counters (<= 150 reads), one per base code
-            uint32_t cur = 'A';
+            uint32_t cur = 'A', cur_b = 0, cur_cnt = 0;  // the winner so far, its code and its count
             for (uint32_t j0 = 0; j0 < nr; j0 += EV_B) {
                 uint32_t ch[EV_B];
 #pragma unroll
@@ -602,7 +602,14 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
                         saw_n |= is_n(ch[u]);
                         const uint32_t b = base_code(ch[u]);
                         cnt += 1u << (8 * b);
-                        if (((cnt >> (8 * b)) & 0xffu) > ((cnt >> (8 * base_code(cur))) & 0xffu)) cur = ch[u];
+                        const uint32_t cb = (cnt >> (8 * b)) & 0xffu;
+                        if (b == cur_b) {
+                            cur_cnt = cb;  // (the stored char stays the first one that reached the lead)
+                        } else if (cb > cur_cnt) {  // strictly more than the current winner: first base to reach the final maximum wins
+                            cur = ch[u];
+                            cur_b = b;
+                            cur_cnt = cb;
+                        }
                     }
                 }
             }
@@ -623,8 +630,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
             }
 #pragma unroll
             for (int u = 0; u < EV_B; ++u) {
-                for (int o = 16; o > 0; o >>= 1) d[u] += __shfl_xor_sync(FULL, d[u], o);
-                sp += (j0 + u < nr && d[u] <= p.max_err);
+                sp += (j0 + u < nr && int(__reduce_add_sync(FULL, uint32_t(d[u]))) <= p.max_err);
             }
         }
         supp[s] = sp;

@@ -382,3 +382,44 @@ def test_fused_prefilter_overflow_falls_back(ctx, monkeypatch):
     sh.close()
     sh2.close()
     assert fused_launches >= 6
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_wrapped_length_cluster_in_phase2(ctx, fused):
+    """a cluster of 65536 + 24 positions is stored with length 24 and clust2snp analyses [start, start + 24): the fused
+    prefilter (which sees such a record far from where it starts) must hand it to the exact test"""
+    rng = np.random.default_rng(31)
+    n, R, L = 200_000, 400, 100
+    reads = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(R, L))]
+    lcp = np.zeros(n, dtype=np.uint32)
+    lcp[5000:5000 + 65536 + 24] = 40            # one giant run: wrapped length 24
+    lcp[150_000:150_030] = 35                    # and an ordinary cluster
+    text = rng.integers(0, R, size=n).astype(np.uint32)
+    suff = rng.integers(31, 60, size=n).astype(np.uint32)
+    bwt = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)].copy()
+    # make both analysed ranges look like SNP clusters: sample 0 (text < 200) all 'A', sample 1 all 'C'
+    for lo_, hi_ in ((5000, 5024), (150_000, 150_030)):
+        half = (hi_ - lo_) // 2
+        text[lo_:lo_ + half] = rng.integers(0, 200, size=half)
+        bwt[lo_:lo_ + half] = ord("A")
+        text[lo_ + half:hi_] = rng.integers(200, R, size=hi_ - lo_ - half)
+        bwt[lo_ + half:hi_] = ord("C")
+    es, el, _, _ = O.cluster_lm(lcp, bwt, 16, 2)
+    assert 24 in el.tolist()
+    off = O.uniform_read_offsets(R, L)
+    ctx.stage_reads(reads, off)
+    p, op = api.default_params(200), O.default_params(200)
+    ost = O.statistics(es, el, op.mcov_out, op.pval)
+    otext, ores = O.find_events(lcp, text, suff, bwt, es, el, op, ost.max_clust_length, reads, off)
+    assert ores.n_candidates >= 2
+    sh = ctx.shard(n)
+    sh.load_soa(lcp, text, suff, bwt)
+    sh.seal()
+    if fused:
+        cnt = sh.pipeline_resident(p, 16, 2).snp
+    else:
+        sh.cluster_lm(16, 2)
+        st = sh.statistics(p.mcov_out, p.pval)
+        cnt = sh.find_events(p, st.max_clust_length)
+    assert cnt.n_candidates == ores.n_candidates and api.events_format(sh.events(), p) == otext
+    sh.close()
