@@ -118,3 +118,19 @@ def test_cli_live_vs_reference(built, tmp_path):
         b = next(i for i, ln in enumerate(lines) if ln.startswith("Cluster sizes allowed"))
         return lines[a:b + 1]
     assert hist_block(o2.stdout) == hist_block(r2.stdout)
+
+
+def test_cli_multiline_fasta(built, tmp_path):
+    """the FASTA may wrap its sequences over several lines (ref:clust2snp.cpp:166-171,187-192); same .snp"""
+    g = GU.micro("micro_b")
+    fa = write_index(tmp_path, g, dict(x=4, y=4, z=4, bcr=False))
+    with open(fa, "w") as f:
+        for i, r in enumerate(g["reads"]):
+            seq = r.tobytes().decode()
+            f.write(f">read{i} some description\n")
+            for a in range(0, len(seq), 23):
+                f.write(seq[a:a + 23] + "\n")
+    assert run("ebwt2clust", "-i", fa, "-k", g["k"], "-m", g["m"], "-x", 4, "-y", 4, "-z", 4).returncode == 0
+    r = run("clust2snp", "-i", fa, "-n", g["nreads1"], "-x", 4, "-y", 4, "-z", 4)
+    assert r.returncode == 0, r.stderr
+    assert open(os.path.join(str(tmp_path), "micro_b.snp"), "rb").read() == g["variants"][0]["snp"]
