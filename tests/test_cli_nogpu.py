@@ -40,3 +40,30 @@ def test_missing_clusters_prints_help(built):
         r = run("clust2snp", "-i", fa, "-n", "5", "-x", "4", "-y", "4", "-z", "4")
         assert r.returncode == 0 and "ERROR: Could not find BWT clusters file" in r.stdout  # ref:clust2snp.cpp:1063-1068
         assert "Output events will be stored" not in r.stdout
+
+
+def test_fasta_reader_multiline_and_ragged(built, tmp_path):
+    """host_io.hpp's FASTA reader (get_reads, ref:clust2snp.cpp:147-212): wrapped sequences, ragged lengths, a first line
+    that is a header whatever it holds, no trailing newline"""
+    import textwrap
+    src = tmp_path / "t.cpp"
+    src.write_text(textwrap.dedent('''
+        #include <cstdio>
+        #include "host_io.hpp"
+        int main(int argc, char** argv) {
+            host::Reads r;
+            if (!r.load(argv[1])) return 1;
+            printf("%zu", size_t(r.n_reads()));
+            for (size_t i = 0; i < r.n_reads(); ++i)
+                printf(" %.*s", int(r.off[i + 1] - r.off[i]), reinterpret_cast<const char*>(r.bases.data() + r.off[i]));
+            printf("\\n");
+            return 0;
+        }'''))
+    exe = tmp_path / "t"
+    inc, host, lib = os.path.join(ROOT, "include"), os.path.join(ROOT, "ebwt2snp_b200", "host"), os.path.join(ROOT, "ebwt2snp_b200", "lib")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", inc, "-I", host, str(src), "-o", str(exe), "-L", lib, "-lebwt2snp_b200",
+                    f"-Wl,-rpath,{lib}", "-ldl", "-lpthread", "-lrt"], check=True)
+    fa = tmp_path / "r.fasta"
+    fa.write_text("first line is a header\nACGT\nAC\n>r2 desc\nGGGTTT\n>r3\nA\nC\nG\n>r4\nTTTT")
+    out = subprocess.run([str(exe), str(fa)], capture_output=True, text=True, check=True).stdout.split()
+    assert out == ["4", "ACGTAC", "GGGTTT", "ACG", "TTTT"]
