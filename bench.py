@@ -378,7 +378,7 @@ def main():
         if world == 1:  # the same sequence inside the library: one C call, no Python between the kernels
             return sh.pipeline_resident(params, K_DEF, M_DEF)
         mg, st, cnt, ids = sharding.hot_path_step(sh, params, K_DEF, M_DEF, dev)
-        step.ids = ids  # the id all-gather is enqueued; it is read (resolve) after the timed loop's last step
+        step.ids = ids  # global .snp ids are assigned when the text is formatted: resolved after the timed loop
         return mg, st, cnt
 
     def sync_all():

@@ -6,7 +6,7 @@ a few words per rank between the phases,
     1. halo records (2 left / 151 right) once, when the shards are loaded,
     2. the 14-word scan summary of every shard        -> e2s_cluster_merge (host integer logic),
     3. the 151-bin length histogram + 3 counters      -> e2s_statistics_finish (max_clust_length),
-    4. the kept-event count                            -> global id_nr offsets of the .snp records,
+    4. the kept-event count (when the text is written) -> global id_nr offsets of the .snp records,
 
 all done with `torch.distributed.all_gather` on small int64 tensors (NCCL over NVLink on the GPUs,
 gloo in the CPU tests).  The functions take ctypes structs of `api` in and out so that the same code
@@ -127,32 +127,18 @@ def event_id_offset(n_events, device, group=None):
 
 
 class EventIdOffset:
-    """Step 4 without a host synchronisation: the all-gather of the kept-event counts is enqueued on the stream and the
-    result is only read when the ids are needed (when the .snp text is formatted)."""
+    """Step 4, deferred: global id_nr offsets are only needed when the .snp text is formatted (ref:clust2snp.cpp:637,764),
+    so the all-gather of the kept-event counts runs when `resolve()` asks for them, not inside the hot path."""
 
     def __init__(self, n_events, device, group=None):
-        self.rank, self.world = _world(group)
-        self.n = int(n_events)
-        self._out = None
-        if self.world > 1:
-            h_send, h_recv, d_send, d_recv = _staging(1, self.world, device)
-            h_send[0] = self.n
-            d_send.copy_(h_send, non_blocking=True)
-            dist.all_gather_into_tensor(d_recv, d_send, group=group)
-            h_recv.copy_(d_recv, non_blocking=True)
-            self._out = (h_recv, torch.cuda.Event() if torch.device(device).type == "cuda" else None)
-            if self._out[1] is not None:
-                self._out[1].record()
+        self.n, self.device, self.group = int(n_events), device, group
+        self._res = None
 
     def resolve(self):
-        """-> (first id_nr of this rank's kept events, total kept events)"""
-        if self.world == 1:
-            return 1, self.n
-        h_recv, ev = self._out
-        if ev is not None:
-            ev.synchronize()
-        counts = [int(x) for x in h_recv.numpy()]
-        return 1 + sum(counts[:self.rank]), sum(counts)
+        """-> (first id_nr of this rank's kept events, total kept events); a collective: every rank must call it"""
+        if self._res is None:
+            self._res = event_id_offset(self.n, self.device, self.group)
+        return self._res
 
 
 def exchange_halo(lcp, text, suff, bwt, device, group=None):
@@ -215,5 +201,5 @@ def hot_path_step(shard: "api.Shard", params: api.SnpParams, k, min_len, device,
     mg, st = exchange_and_merge(s, own, params.mcov_out, params.pval, device, group)
     shard.cluster_finalize(mg)
     cnt = shard.find_events(params, st.max_clust_length)
-    ids = EventIdOffset(cnt.n_events, device, group)  # enqueued, not waited for
+    ids = EventIdOffset(cnt.n_events, device, group)  # resolved (one small all-gather) when the text is formatted
     return mg, st, cnt, ids
