@@ -434,13 +434,14 @@ def main():
     # ---- roofline of the two kernels that touch every position (this rank's shard) ----
     peak, peak_src = hbm_peak()
     m_own = sh.cluster_count()
+    lcp_bytes = sh.lcp_bytes_resident()
     lo, hi = 2 * params.mcov_out, st.max_clust_length
     # positions inside analysed clusters: from the (global) histogram, scaled to this shard for world > 1
     pos_analysed = sum(int(st.hist[l]) * l for l in range(lo, hi + 1)) / world
     # algorithmic bytes per launch (DESIGN.md "Kernels"): what the kernel has to move for this shard
     fused = ktimes[api.KERNEL_SCAN][1] == 0             # K2 ran the BWT prefilter itself (e2s_cluster_prefilter): no K3a launch
     alg = {
-        api.KERNEL_FLAGS: 4 * n + n / 4,                # LCP read once + 2 bit masks written
+        api.KERNEL_FLAGS: lcp_bytes * n + n / 4,        # resident LCP (1 B when every value <= 127, else 4 B) read once + 2 bit masks written
         api.KERNEL_EMIT: n / 4 + 10 * m_own + (pos_analysed if fused else 0),  # masks read + records written (+ BWT bytes in analysed clusters)
         api.KERNEL_SCAN: pos_analysed + 10 * m_own,     # BWT byte of positions in analysed clusters + record list
         api.KERNEL_EXACT: 0,
@@ -473,7 +474,7 @@ def main():
                     "frac": kern[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
                     "ms_per_launch": kern[dom]["ms"], "alg_bytes_per_launch": kern[dom]["alg_bytes"],
                     "kernels": kern, "kernel_share_of_step": ksum_ms / ms if ms else None,
-                    "fused_prefilter": bool(fused),
+                    "fused_prefilter": bool(fused), "resident_lcp_bytes": lcp_bytes,
                     "pipeline": {"alg_bytes_per_step": sum(alg[k] for k in alg if ktimes[k][1]),
                                  "GBps": sum(alg[k] for k in alg if ktimes[k][1]) / (ms / args.steps * 1e-3) / 1e9,
                                  "frac_of_peak": sum(alg[k] for k in alg if ktimes[k][1]) / (ms / args.steps * 1e-3) / 1e9 / peak}}
@@ -521,6 +522,7 @@ def main():
             "config": {"workload": workload_name(args), "positions_per_gpu": n, "positions_total": n_global,
                        "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; NCCL all-gather of shard summaries",
                        "l2": "inputs (13 B/position, >= 7 GB per GPU at C2) exceed the 126 MB L2; no flush needed",
+                       "resident_layout": f"SoA: lcp u32 + text u32 + suff u32 + bwt u8; K1 streams a {'one-byte LCP copy built at seal (every LCP value <= 127)' if lcp_bytes == 1 else 'the 4-byte LCP'}",
                        "scale": args.scale, "tiles": T, "exchange_us": exchange_us},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "results": {"n_written": int(mg.total_written), "n_clust_out": int(mg.n_clust_out),

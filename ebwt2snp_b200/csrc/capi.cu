@@ -47,6 +47,8 @@ struct e2s_shard {
     uint8_t* bwt_a = nullptr;
     uint32_t *lcp = nullptr, *text = nullptr, *suff = nullptr;  // local position 0
     uint8_t* bwt = nullptr;
+    uint8_t* lcp8_a = nullptr;   // byte copy of the LCP (same padding), built at seal when every value is <= 127
+    bool lcp8_ok = false;        // K1 streams the byte copy
     bool sealed = false;
     int lay_x = 4, lay_y = 4, lay_z = 4, lay_bcr = 0;  // layout of the index files (phantom record only)
     // record list
@@ -228,7 +230,7 @@ int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->bwt_a), ne);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_res), sizeof(ClusterDev));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_hist), (E2S_HIST_BINS + 1) * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_bwt_flag), 4);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_bwt_flag), 8);  // [0] BWT alphabet flag, [1] LCP-narrowing flag
     if (e != cudaSuccess) {
         e2s_shard_destroy(s);
         return fail(c, E2S_ERR_NOMEM, std::string("shard allocation: ") + cudaGetErrorString(e));
@@ -259,6 +261,7 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->text_a);
     cudaFree(s->suff_a);
     cudaFree(s->bwt_a);
+    cudaFree(s->lcp8_a);
     cudaFree(s->d_start);
     cudaFree(s->d_len);
     cudaFree(s->d_desc);
@@ -384,9 +387,39 @@ int e2s_shard_seal(e2s_shard* s) {
     // which plane builder K3a may use: one streaming look at the shard's BWT bytes (incl. the right halo / phantom)
     CU(c, launch_bwt_alphabet(s->bwt, s->n_local + HALO_R, s->d_bwt_flag, c->stream, c->sm_count));
     ++c->launches;
+    // narrow resident LCP for K1 (E2S_LCP_WIDE=1 keeps the 4-byte stream, for A/B measurements and the tests)
+    s->lcp8_ok = false;
+    const char* wide = getenv("E2S_LCP_WIDE");
+    if (!(wide && atoi(wide) != 0)) {
+        const size_t ne = size_t(PAD_L) + s->alloc_r;  // multiple of 16
+        if (!s->lcp8_a && cudaMalloc(reinterpret_cast<void**>(&s->lcp8_a), ne) != cudaSuccess) {
+            cudaGetLastError();
+            s->lcp8_a = nullptr;  // no room for the copy: stay on the 4-byte stream
+        }
+        if (s->lcp8_a) {
+            uint32_t* d_flag = s->d_bwt_flag + 1;
+            CU(c, cudaMemsetAsync(d_flag, 0, 4, c->stream));
+            // K1 looks at positions [-2, n_local] (on the last shard lcp[n_local] is the phantom, which only feeds END(n-1),
+            // left to the host tail rule); everything else in the copy just has to be a byte <= 127
+            const bool last_shard = s->global_off + s->n_local == s->n_global;
+            CU(c, launch_lcp_narrow(s->lcp_a, s->lcp8_a, ne, PAD_L - 2, uint64_t(PAD_L) + s->n_local + (last_shard ? 0 : 1), d_flag,
+                                    c->stream, c->sm_count));
+            ++c->launches;
+            uint32_t h_flag = 1;
+            CU(c, cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            s->lcp8_ok = h_flag == 0;
+            if (!s->lcp8_ok) {  // a value above 127: the copy is useless, give the memory back
+                cudaFree(s->lcp8_a);
+                s->lcp8_a = nullptr;
+            }
+        }
+    }
     s->sealed = true;
     return E2S_OK;
 }
+
+int e2s_shard_lcp_bytes_resident(const e2s_shard* s) { return s ? (s->sealed && s->lcp8_ok ? 1 : 4) : 0; }
 
 int e2s_reads_stage(e2s_ctx* c, const uint8_t* bases, const uint64_t* off, uint64_t n_reads) {
     if (!c || !bases || !off) return fail(c, E2S_ERR_ARG, "e2s_reads_stage: NULL argument");
@@ -489,7 +522,8 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
         fp.s_words = s->d_flags;
         fp.e_words = s->d_flags + s->flag_words;
         c->timer.begin(E2S_KERNEL_FLAGS, c->stream);
-        cudaError_t le = launch_flags(fp, s->alloc_r / 32, c->sm_count, c->stream, s->variant);
+        cudaError_t le = (s->sealed && s->lcp8_ok) ? launch_flags8(fp, s->lcp8_a + PAD_L, c->sm_count, c->stream)
+                                                   : launch_flags(fp, s->alloc_r / 32, c->sm_count, c->stream, s->variant);
         c->timer.end(c->stream);
         CU(c, le);
         ++c->launches;

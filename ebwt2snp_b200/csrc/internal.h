@@ -83,6 +83,11 @@ uint64_t emit_num_tiles(uint64_t n_local);
 uint64_t emit_desc_words();
 cudaError_t launch_flags(const FlagParams& p, uint64_t rows_alloc32, int sm_count, cudaStream_t stream, int variant);
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
+// narrow resident LCP: byte copy built at seal (values saturated at 127; *flag |= 1 if an element of [lo, hi) of the
+// padded array does not fit), and K1 on it (p.lcp unused)
+cudaError_t launch_lcp_narrow(const uint32_t* lcp_a, uint8_t* lcp8_a, uint64_t count, uint64_t lo, uint64_t hi,
+                              uint32_t* flag, cudaStream_t stream, int sm_count);
+cudaError_t launch_flags8(const FlagParams& p, const uint8_t* lcp8, int sm_count, cudaStream_t stream);
 // small helpers: append up to 3 records to the device list / pack the list into 10-byte file records
 cudaError_t launch_put_records(uint64_t* d_start, uint16_t* d_len, uint64_t at, const uint64_t* st, const uint64_t* ln,
                                int n, cudaStream_t stream);

@@ -101,6 +101,11 @@ int e2s_shard_set_layout(e2s_shard *sh, int x, int y, int z, int bcr);
  * reference's post-EOF phantom record (ref:clust2snp.cpp:827-833). */
 int e2s_shard_seal(e2s_shard *sh);
 
+/* Width in bytes of the LCP stream K1 reads for this shard: 1 when the seal found every LCP value <= 127 and
+ * built the one-byte resident copy (what egsa's default 1-byte LCP files hold, ref:pipeline.sh:30-32), else 4.
+ * Setting E2S_LCP_WIDE=1 in the environment before the seal keeps the 4-byte stream. */
+int e2s_shard_lcp_bytes_resident(const e2s_shard *sh);
+
 /* the read collection (FASTA bases), needed by e2s_find_events only: ref:clust2snp.cpp:147-212 */
 int e2s_reads_stage(e2s_ctx *ctx, const uint8_t *bases, const uint64_t *offsets /* n_reads+1 */, uint64_t n_reads);
 int e2s_reads_stage_dev(e2s_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,

@@ -69,6 +69,78 @@ def test_cluster_long_wrap(ctx):
             assert nc == enc and np.array_equal(s, es) and np.array_equal(l, el), (run, m)
 
 
+@pytest.mark.parametrize("wide", [0, 1])
+def test_cluster_narrow_lcp(ctx, wide, monkeypatch):
+    """K1 on the one-byte resident LCP (all values <= 127; built at seal) against the oracle, and the same inputs
+    forced onto the 4-byte stream (E2S_LCP_WIDE=1): sizes around the 16384-position tiles of the narrow kernel,
+    k on both sides of the byte range, single shards and shards cut at arbitrary positions."""
+    monkeypatch.setenv("E2S_LCP_WIDE", str(wide))
+    rng = np.random.default_rng(4242)
+    sizes = [2, 3, 5, 63, 64, 65, 127, 129, 16383, 16384, 16385, 16387, 32768, 49153, 100003, 262144 + 7]
+    for it, n in enumerate(sizes * 2):
+        k = int(rng.choice([1, 2, 16, 30, 100, 127, 128, 129, 300]))
+        m = int(rng.choice([1, 2, 3, 8, 34]))
+        mode = it % 4
+        if mode == 0:
+            lcp = rng.integers(0, 128, size=n)
+        elif mode == 1:
+            lcp = np.clip(np.cumsum(rng.integers(-3, 4, size=n)) + min(k, 120), 0, 127)
+        elif mode == 2:
+            lcp = rng.integers(max(0, min(k, 125) - 1), min(k, 125) + 3, size=n)
+        else:
+            lcp = rng.choice(np.array([0, 1, 126, 127]), size=n)
+        lcp = lcp.astype(np.uint32)
+        bwt = rng.choice(H.BWT_ALPHABET, size=n)
+        es, el, enc, _ = O.cluster_lm(lcp, bwt, k, m)
+        sh = ctx.shard(n)
+        sh.load_soa(lcp, None, None, bwt)
+        sh.seal()
+        assert sh.lcp_bytes_resident() == (4 if wide else 1)
+        nw, nc = sh.cluster_lm(k, m)
+        s, l = sh.cluster_fetch()
+        sh.close()
+        assert nc == enc and np.array_equal(s, es) and np.array_equal(l, el), (n, k, m, it)
+        if n < 200:
+            continue
+        nsh = int(rng.integers(2, 5))
+        cuts = sorted(set([0, n] + [int(c) for c in rng.integers(2, n - 2, size=nsh - 1)]))
+        cuts = [c for i, c in enumerate(cuts) if i == 0 or c - cuts[i - 1] >= 2 or c == n]
+        if n - cuts[-2] < 2:
+            cuts.pop(-2)
+        sums, recs = [], []
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            sh = ctx.shard(hi - lo, lo, n)
+            a, b = max(0, lo - 2), min(n, hi + 151)
+            sh.load_soa(lcp[a:b], None, None, bwt[a:b], first=a)
+            sh.seal()
+            assert sh.lcp_bytes_resident() == (4 if wide else 1)
+            sums.append(sh.cluster_run(k, m))
+            sh.cluster_finalize(api.ClusterMerged())
+            recs.append(sh.cluster_fetch())
+            sh.close()
+        S, L, mg = H.assemble(sums, recs)
+        assert mg.n_clust_out == enc and np.array_equal(S, es) and np.array_equal(L, el), (it, cuts)
+
+
+def test_lcp_above_127_stays_wide(ctx):
+    """one value of 128 anywhere in the shard (or its halo) keeps K1 on the 4-byte stream"""
+    n = 50000
+    lcp = np.full(n, 20, dtype=np.uint32)
+    bwt = np.full(n, ord("C"), dtype=np.uint8)
+    for pos in (0, 1, 16384, n - 1):
+        l2 = lcp.copy()
+        l2[pos] = 128
+        sh = ctx.shard(n)
+        sh.load_soa(l2, None, None, bwt)
+        sh.seal()
+        assert sh.lcp_bytes_resident() == 4
+        es, el, enc, _ = O.cluster_lm(l2, bwt, 16, 2)
+        nw, nc = sh.cluster_lm(16, 2)
+        s, l = sh.cluster_fetch()
+        sh.close()
+        assert nc == enc and np.array_equal(s, es) and np.array_equal(l, el)
+
+
 def test_cluster_sharded(ctx):
     """shards run one after the other on the same GPU + host merge == single pass"""
     rng = np.random.default_rng(7)
