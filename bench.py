@@ -442,13 +442,13 @@ def main():
     fused = ktimes[api.KERNEL_SCAN][1] == 0             # K2 ran the BWT prefilter itself (e2s_cluster_prefilter): no K3a launch
     alg = {
         api.KERNEL_FLAGS: lcp_bytes * n + n / 4,        # resident LCP (1 B when every value <= 127, else 4 B) read once + 2 bit masks written
-        api.KERNEL_EMIT: n / 4 + 10 * m_own + (pos_analysed if fused else 0),  # masks read + records written (+ BWT bytes in analysed clusters)
-        api.KERNEL_SCAN: pos_analysed + 10 * m_own,     # BWT byte of positions in analysed clusters + record list
+        api.KERNEL_EMIT: n / 4 + 10 * m_own + (pos_analysed / 4 if fused else 0),  # masks read + records written (+ the 2-bit base codes inside analysed clusters)
+        api.KERNEL_SCAN: pos_analysed / 4 + 10 * m_own,  # 2-bit base code (resident bit planes) of positions in analysed clusters + record list
         api.KERNEL_EXACT: 0,
     }
-    streamed = {api.KERNEL_SCAN: n + 10 * m_own}        # the tiles also carry the positions outside clusters
+    streamed = {api.KERNEL_SCAN: n / 4 + 10 * m_own}    # the 16-byte plane loads also carry the positions outside clusters
     if fused:
-        streamed[api.KERNEL_EMIT] = n / 2 + 10 * m_own + n  # masks twice (count pass + write pass) + every BWT byte
+        streamed[api.KERNEL_EMIT] = n / 2 + 10 * m_own + n / 4  # masks twice (count pass + write pass) + the bit planes
     kern = {}
     ksum_ms = 0.0
     for kid, name in KERNELS.items():
@@ -522,7 +522,7 @@ def main():
             "config": {"workload": workload_name(args), "positions_per_gpu": n, "positions_total": n_global,
                        "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; NCCL all-gather of shard summaries",
                        "l2": "inputs (13 B/position, >= 7 GB per GPU at C2) exceed the 126 MB L2; no flush needed",
-                       "resident_layout": f"SoA: lcp u32 + text u32 + suff u32 + bwt u8; K1 streams a {'one-byte LCP copy built at seal (every LCP value <= 127)' if lcp_bytes == 1 else 'the 4-byte LCP'}",
+                       "resident_layout": f"SoA: lcp u32 + text u32 + suff u32 + bwt u8 + 2-bit base-code planes of the BWT (built at seal); K1 streams a {'one-byte LCP copy built at seal (every LCP value <= 127)' if lcp_bytes == 1 else 'the 4-byte LCP'}",
                        "scale": args.scale, "tiles": T, "exchange_us": exchange_us},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "results": {"n_written": int(mg.total_written), "n_clust_out": int(mg.n_clust_out),

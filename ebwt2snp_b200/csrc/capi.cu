@@ -13,6 +13,8 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "planes.cuh"
+#include "planes.cuh"
 
 using namespace e2s;
 
@@ -77,7 +79,8 @@ struct e2s_shard {
     uint64_t* d_pf_list = nullptr;
     uint64_t pf_cap = 0, pf_count = 0;
     bool pf_ok = false;              // the list is complete (no overflow) and belongs to the current record list
-    uint32_t* d_bwt_flag = nullptr;  // != 0: the BWT holds bytes the bit-sliced base code does not cover (set at seal)
+    uint4* d_planes = nullptr;       // resident base-code bit planes of the BWT (planes.cuh), built at seal
+    uint32_t* d_seal_flag = nullptr; // != 0: an LCP value above 127 (set at seal)
     int variant = 0;
     // phase 2
     SnpWork* work = nullptr;
@@ -230,7 +233,8 @@ int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->bwt_a), ne);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_res), sizeof(ClusterDev));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_hist), (E2S_HIST_BINS + 1) * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_bwt_flag), 8);  // [0] BWT alphabet flag, [1] LCP-narrowing flag
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_seal_flag), 4);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_planes), plane_quads(s->alloc_r) * sizeof(uint4));
     if (e != cudaSuccess) {
         e2s_shard_destroy(s);
         return fail(c, E2S_ERR_NOMEM, std::string("shard allocation: ") + cudaGetErrorString(e));
@@ -270,7 +274,8 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFreeHost(s->h_pin);
     cudaFree(s->d_res);
     cudaFree(s->d_hist);
-    cudaFree(s->d_bwt_flag);
+    cudaFree(s->d_seal_flag);
+    cudaFree(s->d_planes);
     cudaFree(s->d_pf_list);
     snp_work_destroy(s->work);
     if (s->ctx->cached == s) s->ctx->cached = nullptr;
@@ -384,8 +389,8 @@ int e2s_shard_seal(e2s_shard* s) {
                                   s->lay_bcr, c->stream));
         ++c->launches;
     }
-    // which plane builder K3a may use: one streaming look at the shard's BWT bytes (incl. the right halo / phantom)
-    CU(c, launch_bwt_alphabet(s->bwt, s->n_local + HALO_R, s->d_bwt_flag, c->stream, c->sm_count));
+    // resident base-code bit planes of the BWT (incl. the right halo / phantom): what K3a and K2's fused prefilter read
+    CU(c, launch_bwt_planes(s->bwt_a, s->alloc_r, s->d_planes, c->stream, c->sm_count));
     ++c->launches;
     // narrow resident LCP for K1 (E2S_LCP_WIDE=1 keeps the 4-byte stream, for A/B measurements and the tests)
     s->lcp8_ok = false;
@@ -397,7 +402,7 @@ int e2s_shard_seal(e2s_shard* s) {
             s->lcp8_a = nullptr;  // no room for the copy: stay on the 4-byte stream
         }
         if (s->lcp8_a) {
-            uint32_t* d_flag = s->d_bwt_flag + 1;
+            uint32_t* d_flag = s->d_seal_flag;
             CU(c, cudaMemsetAsync(d_flag, 0, 4, c->stream));
             // K1 looks at positions [-2, n_local] (on the last shard lcp[n_local] is the phantom, which only feeds END(n-1),
             // left to the host tail rule); everything else in the copy just has to be a byte <= 127
@@ -544,8 +549,7 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
         p.out_len = s->d_len;
         p.cap = s->rec_cap - 4;  // room for adopted records
         p.desc = s->d_desc;
-        p.bwt = s->bwt;
-        p.bwt_not_simple = s->d_bwt_flag;
+        p.planes = s->d_planes;
         p.pf_mcov = (s->pf_arm && s->sealed) ? s->pf_arm : 0;
         p.pf_list = nullptr;
         p.pf_cap = 0;
@@ -1018,14 +1022,14 @@ int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length,
     a.text = s->text;
     a.suff = s->suff;
     a.bwt = s->bwt;
-    a.bwt_not_simple = s->d_bwt_flag;
+    a.planes = s->d_planes;
     a.n_local = s->n_local;
     a.global_off = s->global_off;
     a.cl_start = s->d_start;
     a.cl_len = s->d_len;
     a.m = s->m_list;
     // K2 already ran the BWT prefilter for this -m (fused mode): its survivors + the records adopted from the merge
-    // (which K2 did not see) replace k_tile_first + K3a
+    // (which K2 did not see) replace K3a
     const uint64_t* pre_list = nullptr;
     uint64_t pre_count = 0;
     if (!s->staged && s->pf_ok && s->pf_mcov == uint32_t(p->mcov_out) && max_clust_length <= E2S_MAX_C_LEN) {

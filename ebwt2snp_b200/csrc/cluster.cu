@@ -20,8 +20,8 @@
 //     a bit-parallel count pass, ONE exchange of per-chunk values between the CTAs, then the write pass
 //     (see the comment above the kernel).  Records come out compacted in position order, 10 B each; their
 //     length histogram (statistics(), ref:clust2snp.cpp:899-907) is accumulated on the way.  In fused mode
-//     (e2s_cluster_prefilter) the write pass also streams the BWT bytes and applies clust2snp's BWT-only
-//     prefilter (planes.cuh) to every record it writes.
+//     (e2s_cluster_prefilter) the write pass also applies clust2snp's BWT-only prefilter to every record it
+//     writes, with range popcounts on the shard's resident base-code bit planes (planes.cuh).
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_lcp_flags(const __grid_constant_
 constexpr int FL8_THREADS = 256;
 constexpr int FL8_V = 64;
 constexpr int FL8_T = FL8_THREADS * FL8_V;  // 16384 positions = 16 KB per tile
-constexpr int FL8_STAGES = 4;
+constexpr int FL8_STAGES = 3;
 
 __device__ __forceinline__ uint32_t gather_b7(uint32_t x) {  // bit 7 of bytes 0..3 -> bits 28..31
     return (x & 0x80808080u) * 0x00204081u;
@@ -225,6 +225,8 @@ __global__ void __launch_bounds__(FL8_THREADS) k_lcp_flags8(FlagParams p, const 
         const uint64_t tile_base = t * T;
         const uint64_t my_base = tile_base + uint64_t(tid) * V;
         const uint8_t* tile = smem8 + size_t(stage) * T;
+        const bool interior = p.global_off + tile_base != 0 && tile_base + T <= p.n_local &&
+                              p.global_off + tile_base + T < p.n_global;  // no special case applies inside this tile
 
         uint32_t g_prev = 0, g_next = 0;  // halo bytes outside the tile: issue the global loads early
         if (tid == 0) g_prev = *reinterpret_cast<const uint32_t*>(lcp8 + (int64_t(tile_base) - 4));
@@ -258,7 +260,10 @@ __global__ void __launch_bounds__(FL8_THREADS) k_lcp_flags8(FlagParams p, const 
         }
 
         // G_j = ge(j); A_j = lcp[j-1] > lcp[j]; words are consumed last to first so that each funnel shift
-        // pushes four more flags in at the bottom and position 0 ends up in bit 0
+        // pushes four more flags in at the bottom and position 0 ends up in bit 0.  With p = the word of the
+        // bytes before (p = cur << 8 | prev >> 24 = 256 cur + (prev >> 24) mod 2^32) the compare word
+        // (p | 0x80808080) - cur - 0x01010101 equals 255 cur + (prev >> 24) + 0x7f7f7f7f: multiply-adds, which
+        // run on the FMA pipe beside the logic ops of the ALU pipe (the ALU pipe is what bounds this kernel).
         uint32_t Gh[2], Ah[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -267,9 +272,9 @@ __global__ void __launch_bounds__(FL8_THREADS) k_lcp_flags8(FlagParams p, const 
             for (int i = 7; i >= 0; --i) {
                 const int q = 8 * h + i;
                 const uint32_t cur = w[q];
-                const uint32_t prv = __funnelshift_l(q == 0 ? pw : w[q - 1], cur, 8);  // bytes j-1 of this word's bytes j
+                const uint32_t carry = __umulhi(q == 0 ? pw : w[q - 1], 256u) + 0x7f7f7f7fu;  // (prev >> 24) + 0x7f7f7f7f
                 G = __funnelshift_l(gather_b7(cur + kadd), G, 4);
-                A = __funnelshift_l(gather_b7((prv | 0x80808080u) - cur - 0x01010101u), A, 4);
+                A = __funnelshift_l(gather_b7(cur * 255u + carry), A, 4);
             }
             Gh[h] = G;
             Ah[h] = A;
@@ -283,21 +288,20 @@ __global__ void __launch_bounds__(FL8_THREADS) k_lcp_flags8(FlagParams p, const 
         const uint64_t An = (A >> 1) | (a_V << (V - 1));   // lcp[j] > lcp[j+1]
         uint64_t E = G & ((A & ~An) | ~Gn);
         uint64_t e_prev = g_m1b & ((uint64_t(v_m2 > v_m1) & ((~A) & 1u)) | ((~G) & 1u));
-
-        const uint64_t gpos = p.global_off + my_base;
-        if (gpos == 0) {  // the init special cases of ref:ebwt2clust.cpp:83-86
-            E &= ~uint64_t(1);
-            e_prev = 0;
-            if ((G & 1u) && !(G & 2u)) E |= 2u;
-        }
-        uint64_t vm;
-        {
+        uint64_t vm = ~uint64_t(0);
+        if (!interior) {  // first tile of the eBWT, the tile holding position n_global - 1, tiles reaching past n_local
+            const uint64_t gpos = p.global_off + my_base;
+            if (gpos == 0) {  // the init special cases of ref:ebwt2clust.cpp:83-86
+                E &= ~uint64_t(1);
+                e_prev = 0;
+                if ((G & 1u) && !(G & 2u)) E |= 2u;
+            }
             const int64_t nvalid = int64_t(p.n_local) - int64_t(my_base);
             vm = nvalid >= V ? ~uint64_t(0) : (nvalid <= 0 ? 0 : ((uint64_t(1) << nvalid) - 1));
             const int64_t last = int64_t(p.n_global) - 1 - int64_t(gpos);  // END(n_global-1): host tail rule
             if (last >= 0 && last < V) E &= ~(uint64_t(1) << last);
+            E &= vm;
         }
-        E &= vm;
         const uint64_t Gp = (G << 1) | g_m1b;
         const uint64_t Ep = (E << 1) | e_prev;
         const uint64_t S = G & (~Gp | Ep) & vm;
@@ -382,10 +386,6 @@ constexpr int EM_WPT = 4;                               // 32-bit words per thre
 constexpr int EM_TILE_WORDS = EM_THREADS * EM_WPT;      // 1024 words = 32768 positions
 constexpr int EM_TILE_POS = EM_TILE_WORDS * 32;
 constexpr int EM_CAP = 2048;                            // ENDs per scatter window
-constexpr int EM_PF_HALO = 160;                         // BWT bytes before the tile (clusters <= 150 long that end in it), multiple of 16
-constexpr int EM_PF_BYTES = EM_TILE_POS + EM_PF_HALO;   // BWT window of one tile
-constexpr int EM_PF_CHUNKS = EM_PF_BYTES / 16;
-constexpr int EM_PF_SMEM = EM_PF_BYTES + 2 * EM_PF_CHUNKS * 2 + 16;  // window + two 16-bit plane arrays (dynamic shared memory)
 constexpr int EM_DESC_WORDS = 8;                        // u64 words per chunk descriptor
 constexpr int EM_MAX_CHUNKS = 148 * 8 * 2;              // upper bound of the grid (descriptor allocation)
 
@@ -456,21 +456,11 @@ __device__ __forceinline__ bool has_zero_byte(uint32_t x) { return ((x - 0x01010
 __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
     __shared__ EmitShared sh;
     __shared__ unsigned long long s_chunk;
-    __shared__ uint64_t pf_bar;
-    extern __shared__ __align__(128) uint8_t pf_smem[];  // fused prefilter only: BWT window, then the two planes
     const bool pf = p.pf_mcov != 0;
-    uint16_t* pf_b0 = reinterpret_cast<uint16_t*>(pf_smem + EM_PF_BYTES);
-    uint16_t* pf_b1 = pf_b0 + EM_PF_CHUNKS;
-    uint32_t pf_parity = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int spread = p.min_len >= 2 ? p.min_len - 2 : -1;  // extra positions a START shadows; -1: nothing is dropped
 
     for (int i = tid; i < E2S_HIST_BINS; i += EM_THREADS) sh.hist[i] = 0;
-    if (pf && tid == 0) {
-        mbar_init(&pf_bar, 1);
-        fence_mbar_init();
-    }
-    const bool pf_simple = pf && p.bwt_not_simple && *p.bwt_not_simple == 0;
     // Chunks are handed out by a ticket, so every chunk with a smaller id is owned by a CTA that is already
     // running: the spin-waits of the exchange cannot deadlock whatever else occupies the SMs.
     if (tid == 0) s_chunk = atomicAdd(&p.res->ticket, 1ull);
@@ -640,10 +630,6 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
         const uint32_t E[EM_WPT] = {e4.x, e4.y, e4.z, e4.w};
         const uint64_t tile_gbase = p.global_off + t * uint64_t(EM_TILE_POS);
         const bool pf_tile = pf && write;
-        if (pf_tile && tid == 0) {  // BWT bytes of the tile and of the 160 positions before it, by the bulk-copy engine
-            mbar_expect_tx(&pf_bar, EM_PF_BYTES);
-            bulk_g2s(pf_smem, p.bwt + (int64_t(t) * EM_TILE_POS - EM_PF_HALO), EM_PF_BYTES, &pf_bar);
-        }
         reinterpret_cast<uint4*>(sh.smask)[tid] = s4;
         reinterpret_cast<uint4*>(sh.emask)[tid] = e4;
         uint32_t D[EM_WPT] = {0, 0, 0, 0};
@@ -701,11 +687,6 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
                 sh.t_first_e = fe;
             }
         }
-        if (pf_tile) {  // bit planes of the base code for the prefilter (planes.cuh); read by the dense pass after barrier (2)
-            mbar_wait(&pf_bar, pf_parity);
-            pf_parity ^= 1u;
-            build_planes(pf_smem, EM_PF_CHUNKS, pf_b0, pf_b1, pf_simple, tid, EM_THREADS);
-        }
         uint32_t base = inc - pk, tot = 0;
 #pragma unroll
         for (int q = 0; q < EM_WARPS; ++q) {
@@ -732,12 +713,9 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
         // fused prefilter of find_variants on a record just written at index o (ref:clust2snp.cpp:402-429, planes.cuh)
         auto prefilter = [&](uint64_t st, uint32_t len, uint64_t o) {
             if (len < 2 * p.pf_mcov || len > uint32_t(MAX_C_LEN)) return;
-            // clust2snp analyses the positions [st, st + len) with the WRAPPED 16-bit length: for a cluster of 65536 + len
-            // positions that range lies far before this tile's window -- leave the decision to the exact test
-            const bool outside = st + EM_PF_HALO < tile_gbase;
-            const uint32_t lo = uint32_t(st + EM_PF_HALO - tile_gbase);  // window coordinates (st >= tile_gbase - 160 here)
-            if (outside ||
-                frequent_codes(reinterpret_cast<const uint32_t*>(pf_b0), reinterpret_cast<const uint32_t*>(pf_b1), lo, lo + len, p.pf_mcov) >= 2) {
+            // clust2snp analyses the positions [st, st + len) with the WRAPPED 16-bit length, wherever the END was seen;
+            // st >= global_off for every record a shard writes (a START before the shard makes it the head END)
+            if (frequent_codes(p.planes, int64_t(st - p.global_off), len, p.pf_mcov) >= 2) {
                 const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
                 if (at < p.pf_cap) p.pf_list[at] = o;
             }
@@ -1096,17 +1074,13 @@ uint64_t emit_desc_words() { return uint64_t(EM_MAX_CHUNKS) * EM_DESC_WORDS; }
 
 cudaError_t launch_emit(const EmitParams& p0, int sm_count, cudaStream_t stream) {
     EmitParams p = p0;
-    const int mode = p.pf_mcov ? 1 : 0;  // the fused prefilter needs the BWT window + planes in dynamic shared memory
-    const size_t smem = mode ? size_t(EM_PF_SMEM) : 0;
-    static int occ_dev[64][2] = {{0}};  // function attributes are per device
+    static int occ_dev[64] = {0};  // function attributes are per device
     int dev = 0;
     cudaGetDevice(&dev);
-    int& occ = occ_dev[dev & 63][mode];
+    int& occ = occ_dev[dev & 63];
     if (!occ) {
-        cudaError_t e = cudaFuncSetAttribute(k_cluster_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EM_PF_SMEM));
-        if (e != cudaSuccess) return e;
         int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_cluster_emit, EM_THREADS, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_cluster_emit, EM_THREADS, 0);
         if (e != cudaSuccess) return e;
         if (o < 1) return cudaErrorLaunchOutOfResources;
         occ = o;
@@ -1114,7 +1088,7 @@ cudaError_t launch_emit(const EmitParams& p0, int sm_count, cudaStream_t stream)
     uint64_t grid = uint64_t(sm_count) * occ;  // one chunk per CTA
     if (grid > p.num_tiles) grid = p.num_tiles;
     if (grid > EM_MAX_CHUNKS) grid = EM_MAX_CHUNKS;
-    k_cluster_emit<<<dim3(unsigned(grid)), dim3(EM_THREADS), smem, stream>>>(p);
+    k_cluster_emit<<<dim3(unsigned(grid)), dim3(EM_THREADS), 0, stream>>>(p);
     return cudaGetLastError();
 }
 

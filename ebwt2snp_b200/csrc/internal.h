@@ -67,8 +67,7 @@ struct EmitParams {  // K2
     uint64_t cap;
     uint64_t* desc;      // chunk descriptors (emit_desc_words() words, zeroed before the launch)
     // fused BWT prefilter of find_variants (pipeline mode: the caller already knows clust2snp's -m); pf_mcov = 0: off
-    const uint8_t* bwt;             // local position 0 (PAD_L readable bytes before it)
-    const uint32_t* bwt_not_simple; // seal-time alphabet flag (planes.cuh)
+    const uint4* planes;            // the shard's resident base-code bit planes (planes.cuh)
     uint32_t pf_mcov;
     uint64_t* pf_list;              // out: indices (in this shard's record list) of clusters that need the exact test, unordered
     uint64_t pf_cap;
@@ -121,7 +120,7 @@ struct SnpArrays {
     const uint32_t* text;
     const uint32_t* suff;
     const uint8_t* bwt;   // all: local position 0
-    const uint32_t* bwt_not_simple;  // device flag written at seal (k_bwt_alphabet): 0 = the bit-sliced base code is exact; may be null
+    const uint4* planes;  // resident base-code bit planes (planes.cuh), built at seal
     uint64_t n_local, global_off;
     const uint64_t* cl_start;  // global starts, sorted
     const uint16_t* cl_len;
@@ -137,7 +136,8 @@ struct CandSlot {  // one (flagged cluster, allele pair) slot written by K3b
     // followed in the slot arrays by idx/pos lists (see snp.cu)
 };
 
-cudaError_t launch_bwt_alphabet(const uint8_t* bwt, uint64_t count, uint32_t* flag, cudaStream_t stream, int sm_count);
+// seal-time: base-code bit planes of the padded BWT array (bwt_a = PAD_L bytes before local position 0, alloc_r after)
+cudaError_t launch_bwt_planes(const uint8_t* bwt_a, uint64_t alloc_r, uint4* planes, cudaStream_t stream, int sm_count);
 cudaError_t launch_len_hist(const uint16_t* len, uint64_t m, unsigned long long* hist /*151 + n_bases*/,
                             cudaStream_t stream, int sm_count);
 cudaError_t launch_check_sorted(const uint64_t* start, const uint16_t* len, uint64_t m, SnpDev* dev,

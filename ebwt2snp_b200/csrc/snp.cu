@@ -1,8 +1,8 @@
 // Phase 2 (clust2snp): per-cluster analysis and SNP/indel calling.
 //
 //   k_len_hist       statistics(): length histogram                      ref:clust2snp.cpp:889-909
-//   k_tile_first     merge-path style partition of the cluster list over position tiles
-//   k_code_scan      K3a: exact prefilter of find_variants on the BWT byte alone.  A cluster whose
+//   k_bwt_planes     seal-time: resident bit planes of the 2-bit base code of every BWT byte (planes.cuh)
+//   k_code_scan      K3a: exact prefilter of find_variants on the BWT base codes alone.  A cluster whose
 //                    records show at most ONE base code (base_to_int, ref:include.hpp:265-279) with
 //                    >= mcov_out occurrences over both samples cannot pass ref:clust2snp.cpp:402-429:
 //                    counts[s][c] <= total[c] < mcov_out for every other code, so both frequent sets are
@@ -17,10 +17,9 @@
 //   k_events         K4: gSA-driven gather of read contexts, consensus, support, distance()
 //                                                  ref:clust2snp.cpp:541-624, 254-302, include.hpp:334-371
 //
-// K3a is the only phase-2 kernel that touches every position: it streams 16384-byte BWT tiles (+150
-// byte overhang) into shared memory with the TMA engine (cp.async.bulk, STAGES tiles in flight per
-// CTA), turns them into two bit-planes of the 2-bit base code (planes.cuh) and answers every cluster of
-// the tile with a few range popcounts (one thread per cluster).  Traffic: 1 B/position + 10 B/cluster.
+// K3a is the only phase-2 kernel that touches every position: one thread per cluster record answers the record with
+// range popcounts on the shard's resident bit planes (16-byte loads of 64 positions x 2 planes, shared between
+// neighbouring threads through L1).  Traffic: 0.25 B/position + 10 B/cluster.
 // It does not run when K2 already applied the same prefilter while writing the records (fused mode,
 // e2s_cluster_prefilter): snp_run then starts from K2's survivor list.
 // The whole phase is enqueued with device-resident counts and synchronises once (snp_run).
@@ -90,19 +89,14 @@ cudaError_t launch_check_sorted(const uint64_t* start, const uint16_t* len, uint
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3a: base-code prefilter over the BWT
+// K3a: base-code prefilter on the resident bit planes
 // ---------------------------------------------------------------------------------------------
 constexpr int PS_THREADS = 256;
-constexpr int PS_T = 16384;                  // positions per tile
-constexpr int PS_SPAN = PS_T + HALO_R;       // bytes staged per tile (multiple of 16)
-constexpr int PS_STAGES = 3;
-constexpr int PS_CHUNKS = PS_SPAN / 16;      // 16-byte chunks per tile
-constexpr int PS_PLANE_WORDS = (PS_SPAN + 31) / 32 + 3;
+constexpr int PS_T = 16384;  // granularity of the analysed range: records starting before ceil(n_local / PS_T) * PS_T
 
 struct ScanParams {
     SnpArrays a;
-    const uint64_t* tile_first;  // num_tiles + 1
-    uint32_t num_tiles;
+    uint64_t limit;              // records with global_off <= start < global_off + limit are analysed
     uint32_t min_len, max_len;   // 2*mcov_out, max_clust_length
     uint32_t mcov;
     uint64_t* survivors;         // out: clusters that need the exact test (unordered; dev->n_survivors counts them)
@@ -110,126 +104,55 @@ struct ScanParams {
     SnpDev* dev;
 };
 
-__global__ void k_tile_first(const uint64_t* __restrict__ cl_start, uint64_t m, uint64_t global_off, uint32_t num_tiles,
-                             uint64_t* __restrict__ tile_first) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > num_tiles) return;
-    const uint64_t key = global_off + uint64_t(t) * PS_T;
-    uint64_t lo = 0, hi = m;
-    while (lo < hi) {
-        uint64_t mid = (lo + hi) >> 1;
-        if (cl_start[mid] < key) lo = mid + 1;
-        else hi = mid;
-    }
-    tile_first[t] = lo;
-}
-
-// Runs once when a shard is sealed: *flag != 0 iff some BWT byte's exact base code (base_code) differs from the
-// bit-sliced one above, in which case K3a keeps the per-byte equality tests.
-__global__ void __launch_bounds__(256) k_bwt_alphabet(const uint8_t* __restrict__ bwt, uint64_t count, uint32_t* flag) {
-    bool bad = false;
-    for (uint64_t i = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 16; i < count; i += uint64_t(gridDim.x) * blockDim.x * 16) {
-        const uint4 q = *reinterpret_cast<const uint4*>(bwt + i);  // the arrays are padded: a 16-byte read never leaves the allocation
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+// Runs once when a shard is sealed: the two bit planes of the base code of every byte of the padded BWT array
+// (layout in planes.cuh).  One thread per 64 positions; exact for every byte value (case-folded equality tests).
+__global__ void __launch_bounds__(256) k_bwt_planes(const uint8_t* __restrict__ bwt_a, uint64_t n_quads, uint4* __restrict__ planes) {
+    for (uint64_t q = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < n_quads; q += uint64_t(gridDim.x) * blockDim.x) {
+        // quad q = local positions [64 q - PL_PAD, +64) = bytes [64 q - (PL_PAD - PAD_L), +64) of bwt_a
+        const int64_t byte0 = int64_t(q) * 64 - (PL_PAD - PAD_L);
+        uint32_t w[4] = {0, 0, 0, 0};  // plane0 lo, plane0 hi, plane1 lo, plane1 hi
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t f0 = fast_b0(w[j]), f1 = fast_b1(w[j]);
+        for (int c = 0; c < 4; ++c) {
+            const int64_t b = byte0 + 16 * c;
+            if (b < 0) continue;  // before the allocation (the first PL_PAD - PAD_L positions): code 0
+            const uint4 v = *reinterpret_cast<const uint4*>(bwt_a + b);
+            const uint32_t x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                if (i + 4 * j + b < count) {
-                    const uint32_t code = base_code((w[j] >> (8 * b)) & 0xffu);
-                    bad |= code != (((f0 >> (8 * b)) & 1u) | (((f1 >> (8 * b)) & 1u) << 1));
-                }
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t code = base_code((x[j >> 2] >> (8 * (j & 3))) & 0xffu);
+                const int bit = 16 * c + j;
+                w[bit >> 5] |= (code & 1u) << (bit & 31);
+                w[2 + (bit >> 5)] |= (code >> 1) << (bit & 31);
             }
         }
+        planes[q] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    if (bad) *flag = 1u;
 }
 
-cudaError_t launch_bwt_alphabet(const uint8_t* bwt, uint64_t count, uint32_t* flag, cudaStream_t stream, int sm_count) {
-    cudaError_t e = cudaMemsetAsync(flag, 0, 4, stream);
-    if (e != cudaSuccess) return e;
-    k_bwt_alphabet<<<unsigned(sm_count) * 8, 256, 0, stream>>>(bwt, count, flag);
+cudaError_t launch_bwt_planes(const uint8_t* bwt_a, uint64_t alloc_r, uint4* planes, cudaStream_t stream, int sm_count) {
+    k_bwt_planes<<<unsigned(sm_count) * 8, 256, 0, stream>>>(bwt_a, plane_quads(alloc_r), planes);
     return cudaGetLastError();
 }
 
+// One thread per cluster record: total count of each base code by range popcounts on the planes (0.25 B/position,
+// 16-byte loads that neighbouring threads share through L1) + the 10-byte record.
 __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t full_bar[PS_STAGES];
-    __shared__ __align__(16) uint16_t s_b0[PS_PLANE_WORDS * 2];  // bit 0 of the base code (C, T)
-    __shared__ __align__(16) uint16_t s_b1[PS_PLANE_WORDS * 2];  // bit 1 of the base code (G, T)
-    const int tid = threadIdx.x, lane = tid & 31;
-
-    if (tid == 0) {
-        for (int s = 0; s < PS_STAGES; ++s) mbar_init(&full_bar[s], 1);
-        fence_mbar_init();
-    }
-    for (int i = tid; i < PS_PLANE_WORDS * 2; i += PS_THREADS) s_b0[i] = s_b1[i] = 0;
-    __syncthreads();
-    auto issue = [&](int s, uint64_t t) {
-        mbar_expect_tx(&full_bar[s], PS_SPAN);
-        bulk_g2s(smem + size_t(s) * PS_SPAN, p.a.bwt + t * PS_T, PS_SPAN, &full_bar[s]);
-    };
-    if (tid == 0) {
-        for (int s = 0; s < PS_STAGES; ++s) {
-            uint64_t t = uint64_t(blockIdx.x) + uint64_t(s) * gridDim.x;
-            if (t < p.num_tiles) issue(s, t);
-        }
-    }
-    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(s_b0);
-    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(s_b1);
-    const bool simple = p.a.bwt_not_simple && *p.a.bwt_not_simple == 0;  // block-uniform
-
     unsigned long long n_analysed = 0;
-    uint32_t it = 0;
-    for (uint64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-        const int stage = it % PS_STAGES;
-        const uint32_t parity = (it / PS_STAGES) & 1;
-        const uint8_t* st = smem + size_t(stage) * PS_SPAN;
-        const uint64_t c_lo = p.tile_first[t], c_hi = p.tile_first[t + 1];
-        const uint64_t tile_gbase = p.a.global_off + t * PS_T;
-        // my first cluster record: issue the loads before waiting for the tile
-        uint64_t c = c_lo + tid;
-        uint64_t c_start = 0;
-        uint32_t c_len = 0;
-        if (c < c_hi) {
-            c_start = p.a.cl_start[c];
-            c_len = p.a.cl_len[c];
-        }
-        mbar_wait(&full_bar[stage], parity);
-        // ---- bit planes of the base code: A=00 C=01 G=10 T=11, everything else 00 ----
-        build_planes(st, PS_CHUNKS, s_b0, s_b1, simple, tid, PS_THREADS);
-        __syncthreads();  // planes complete; the byte tile is no longer needed
-        if (tid == 0) {
-            uint64_t tn = t + uint64_t(PS_STAGES) * gridDim.x;
-            if (tn < p.num_tiles) issue(stage, tn);
-        }
-        // ---- one thread per cluster: total count of each base code by range popcounts ----
-        while (c < c_hi) {
-            const uint64_t cn = c + PS_THREADS;
-            uint64_t n_start = 0;
-            uint32_t n_len = 0;
-            if (cn < c_hi) {  // prefetch the next record
-                n_start = p.a.cl_start[cn];
-                n_len = p.a.cl_len[cn];
+    for (uint64_t c = uint64_t(blockIdx.x) * PS_THREADS + threadIdx.x; c < p.a.m; c += uint64_t(gridDim.x) * PS_THREADS) {
+        const uint64_t c_start = p.a.cl_start[c];
+        const uint32_t c_len = p.a.cl_len[c];
+        if (c_len >= p.min_len && c_len <= p.max_len && c_start - p.a.global_off < p.limit) {
+            ++n_analysed;
+            if (frequent_codes(p.a.planes, int64_t(c_start - p.a.global_off), c_len, p.mcov) >= 2) {
+                // rare (variants, repeats): plain atomic append, the exact test does not need an order
+                const unsigned long long at = atomicAdd(&p.dev->n_survivors, 1ull);
+                if (at < p.cap_surv) p.survivors[at] = c;
             }
-            if (c_len >= p.min_len && c_len <= p.max_len) {
-                ++n_analysed;
-                const uint32_t lo = uint32_t(c_start - tile_gbase);
-                if (frequent_codes(w0, w1, lo, lo + c_len, p.mcov) >= 2) {  // rare (variants, repeats): plain atomic append, the exact test does not need an order
-                    const unsigned long long at = atomicAdd(&p.dev->n_survivors, 1ull);
-                    if (at < p.cap_surv) p.survivors[at] = c;
-                }
-            }
-            c = cn;
-            c_start = n_start;
-            c_len = n_len;
         }
-        __syncthreads();  // planes are rebuilt by the next tile
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) n_analysed += __shfl_xor_sync(FULL, n_analysed, d);
-    if (lane == 0 && n_analysed) atomicAdd(&p.dev->n_analysed, n_analysed);
+    if ((threadIdx.x & 31) == 0 && n_analysed) atomicAdd(&p.dev->n_analysed, n_analysed);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -728,7 +651,6 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
 // host orchestration
 // ---------------------------------------------------------------------------------------------
 struct SnpWork {
-    uint64_t* tile_first = nullptr; size_t tile_first_cap = 0;
     uint8_t* zero_blk = nullptr; size_t zero_cap = 0;  // everything a pass needs zeroed, in one block: one memset
     unsigned long long* fc_sync = nullptr;              // (views into zero_blk)
     uint32_t* flag_words2 = nullptr;
@@ -753,7 +675,7 @@ SnpWork* snp_work_create() { return new SnpWork(); }
 void snp_work_destroy(SnpWork* w) {
     if (!w) return;
     cudaFree(w->zero_blk); cudaFree(w->survivors);
-    cudaFree(w->tile_first); cudaFree(w->flagged);
+    cudaFree(w->flagged);
     cudaFree(w->slots); cudaFree(w->slot_text); cudaFree(w->slot_pos); cudaFree(w->cand);
     cudaFreeHost(w->h_dev);
     cudaFreeHost(w->h_events);
@@ -792,7 +714,6 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     const uint32_t cap = uint32_t(p.consensus_reads < MAX_C_LEN ? p.consensus_reads : MAX_C_LEN);
     w->stride = uint32_t((sizeof(PackedEventHdr) + 2 * size_t(p.k_left) + size_t(p.k_right) + 15) & ~size_t(15));
 
-    CK(ensure(w->tile_first, w->tile_first_cap, size_t(num_tiles) + 1));
     // first guesses: clusters with two frequent base codes are variants and repeats, a small fraction of all
     if (!w->want_survivors) w->want_survivors = a.m / 64 + 4096;
     if (!w->want_flagged) w->want_flagged = a.m / 256 + 2048;
@@ -842,40 +763,23 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
         }
 
 
-        if (!pre_list) {
-        k_tile_first<<<(num_tiles + 1 + 255) / 256, 256, 0, stream>>>(a.cl_start, a.m, a.global_off, num_tiles, w->tile_first);
-        CK(cudaGetLastError());
-        ++*launches;
-        {   // K3a: base-code prefilter (BWT bytes only)
+        if (!pre_list) {   // K3a: base-code prefilter on the resident bit planes
             ScanParams sp;
             sp.a = a;
-            sp.tile_first = w->tile_first;
-            sp.num_tiles = num_tiles;
+            sp.limit = uint64_t(num_tiles) * PS_T;
             sp.min_len = uint32_t(2 * p.mcov_out);
             sp.max_len = uint32_t(max_clust_length);
             sp.mcov = uint32_t(p.mcov_out);
             sp.survivors = w->survivors;
             sp.cap_surv = cap_surv;
             sp.dev = w->dev;
-            const size_t smem = size_t(PS_STAGES) * PS_SPAN;
-            static int occ_dev[64] = {0};  // function attributes are per device
-            int dev = 0;
-            cudaGetDevice(&dev);
-            int& occ = occ_dev[dev & 63];
-            if (!occ) {
-                CK(cudaFuncSetAttribute(k_code_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-                int o = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_code_scan, PS_THREADS, smem));
-                occ = o < 1 ? 1 : o;
-            }
-            uint64_t grid = uint64_t(sm_count) * occ;
-            if (grid > num_tiles) grid = num_tiles;
+            uint64_t grid = (a.m + PS_THREADS - 1) / PS_THREADS;
+            if (grid > uint64_t(sm_count) * 32) grid = uint64_t(sm_count) * 32;
             if (timer) timer->begin(E2S_KERNEL_SCAN, stream);
-            k_code_scan<<<unsigned(grid), PS_THREADS, smem, stream>>>(sp);
+            k_code_scan<<<unsigned(grid), PS_THREADS, 0, stream>>>(sp);
             if (timer) timer->end(stream);
             CK(cudaGetLastError());
             ++*launches;
-        }
         }
         {   // K3x: exact filters on the survivors
             ExactParams ep;
