@@ -386,6 +386,7 @@ constexpr int EM_WPT = 4;                               // 32-bit words per thre
 constexpr int EM_TILE_WORDS = EM_THREADS * EM_WPT;      // 1024 words = 32768 positions
 constexpr int EM_TILE_POS = EM_TILE_WORDS * 32;
 constexpr int EM_CAP = 2048;                            // ENDs per scatter window
+constexpr int EM_PF_QUADS = EM_TILE_POS / 64 + PL_PAD / 64;  // plane quads of one tile and of the PL_PAD positions before it
 constexpr int EM_DESC_WORDS = 8;                        // u64 words per chunk descriptor
 constexpr int EM_MAX_CHUNKS = 148 * 8 * 2;              // upper bound of the grid (descriptor allocation)
 
@@ -456,11 +457,18 @@ __device__ __forceinline__ bool has_zero_byte(uint32_t x) { return ((x - 0x01010
 __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
     __shared__ EmitShared sh;
     __shared__ unsigned long long s_chunk;
+    __shared__ __align__(16) uint4 pf_win[EM_PF_QUADS];  // fused prefilter: the tile's window of the resident bit planes
+    __shared__ uint64_t pf_bar;
     const bool pf = p.pf_mcov != 0;
+    uint32_t pf_parity = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int spread = p.min_len >= 2 ? p.min_len - 2 : -1;  // extra positions a START shadows; -1: nothing is dropped
 
     for (int i = tid; i < E2S_HIST_BINS; i += EM_THREADS) sh.hist[i] = 0;
+    if (pf && tid == 0) {
+        mbar_init(&pf_bar, 1);
+        fence_mbar_init();
+    }
     // Chunks are handed out by a ticket, so every chunk with a smaller id is owned by a CTA that is already
     // running: the spin-waits of the exchange cannot deadlock whatever else occupies the SMs.
     if (tid == 0) s_chunk = atomicAdd(&p.res->ticket, 1ull);
@@ -630,6 +638,19 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
         const uint32_t E[EM_WPT] = {e4.x, e4.y, e4.z, e4.w};
         const uint64_t tile_gbase = p.global_off + t * uint64_t(EM_TILE_POS);
         const bool pf_tile = pf && write;
+        bool pf_pending = pf_tile;  // the window has been requested and not yet waited for (block-uniform)
+        if (pf_tile && tid == 0) {  // plane quads of the tile and of the 192 positions before it, by the bulk-copy engine
+            fence_proxy_async();    // the previous tile's window was read through the generic proxy
+            mbar_expect_tx(&pf_bar, EM_PF_QUADS * 16);
+            bulk_g2s(pf_win, p.planes + t * uint64_t(EM_TILE_POS / 64), EM_PF_QUADS * 16, &pf_bar);
+        }
+        auto pf_wait = [&]() {
+            if (pf_pending) {
+                mbar_wait(&pf_bar, pf_parity);
+                pf_parity ^= 1u;
+                pf_pending = false;
+            }
+        };
         reinterpret_cast<uint4*>(sh.smask)[tid] = s4;
         reinterpret_cast<uint4*>(sh.emask)[tid] = e4;
         uint32_t D[EM_WPT] = {0, 0, 0, 0};
@@ -713,9 +734,10 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
         // fused prefilter of find_variants on a record just written at index o (ref:clust2snp.cpp:402-429, planes.cuh)
         auto prefilter = [&](uint64_t st, uint32_t len, uint64_t o) {
             if (len < 2 * p.pf_mcov || len > uint32_t(MAX_C_LEN)) return;
-            // clust2snp analyses the positions [st, st + len) with the WRAPPED 16-bit length, wherever the END was seen;
-            // st >= global_off for every record a shard writes (a START before the shard makes it the head END)
-            if (frequent_codes(p.planes, int64_t(st - p.global_off), len, p.pf_mcov) >= 2) {
+            // clust2snp analyses the positions [st, st + len) with the WRAPPED 16-bit length: for a cluster of 65536 + len
+            // positions that range lies far before this tile's window -- leave the decision to the exact test
+            if (st + PL_PAD < tile_gbase ||
+                frequent_codes<false>(pf_win, int64_t(st) - int64_t(tile_gbase), len, p.pf_mcov) >= 2) {
                 const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
                 if (at < p.pf_cap) p.pf_list[at] = o;
             }
@@ -748,6 +770,7 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
                 }
             }
             __syncthreads();  // (2) list
+            pf_wait();
             const uint32_t cntw = nL - win < EM_CAP ? nL - win : EM_CAP;
             if (!exact) {
                 if (!write) continue;
@@ -827,6 +850,7 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
             }
         }
         if (exact || nL == 0) __syncthreads();  // row_kept / warp 0's tile summary (otherwise ordered by barrier (2))
+        pf_wait();  // a tile without ENDs: keep the barrier's phase in step with the requests
         const uint32_t tile_kept = exact ? sh.row_kept : nL - (carried_here ? adj : 0u);
         const int t_last_s = sh.t_last_s, t_last_e = sh.t_last_e;
         if (info) {

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
         const uint32_t c_len = p.a.cl_len[c];
         if (c_len >= p.min_len && c_len <= p.max_len && c_start - p.a.global_off < p.limit) {
             ++n_analysed;
-            if (frequent_codes(p.a.planes, int64_t(c_start - p.a.global_off), c_len, p.mcov) >= 2) {
+            if (frequent_codes<true>(p.a.planes, int64_t(c_start - p.a.global_off), c_len, p.mcov) >= 2) {
                 // rare (variants, repeats): plain atomic append, the exact test does not need an order
                 const unsigned long long at = atomicAdd(&p.dev->n_survivors, 1ull);
                 if (at < p.cap_surv) p.survivors[at] = c;
@@ -420,6 +420,10 @@ __global__ void __launch_bounds__(1024) k_compact_slots(const uint32_t* __restri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
+    {   // only the slots of the clusters K3x flagged can be valid: 4 slots per flagged cluster
+        const uint64_t used = (dev->n_flagged * 4 + 31) / 32;
+        if (used < n_words) n_words = used;
+    }
     for (uint64_t i0 = 0; i0 < n_words; i0 += 1024) {
         const uint64_t wi = i0 + threadIdx.x;
         uint32_t w = wi < n_words ? valid_words[wi] : 0u;
