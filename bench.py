@@ -301,6 +301,7 @@ def main():
     ap.add_argument("--cpu-positions", type=float, default=3e7, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--egsa-build", action="store_true", help="also time the library's EGSA builder on the workload's reads")
     ap.add_argument("--tiles", type=int, default=1,
                     help="resident-only study: tile the workload T times on the GPU (read ids shifted; every tile starts with "
                          "lcp = 0), e.g. --tiles 8 = 4.46e9 positions, C3/C4-sized shards; implies --no-e2e --no-cpu-baseline")
@@ -327,6 +328,27 @@ def main():
 
     # ---- data: every rank owns one C2-size tile of a global eBWT of world * n positions (weak scaling) ----
     rs, eg = make_dataset(args.workload, args.seed + rank, args.scale, dev)
+    # ---- EGSA construction on the GPU (data preparation, outside the timed step): the library's
+    # builder on the same reads, timed, and compared element by element with the arrays the step below runs on ----
+    egsa_build = None
+    if args.egsa_build and world == 1:
+        from ebwt2snp_b200 import api as _api
+        bctx = _api.Context(local)
+        try:
+            reads_t = torch.from_numpy(rs.reads).to(dev)
+            bctx.build_egsa(reads_t[: max(1, min(1000, reads_t.shape[0]))])  # warm-up (allocator, CUB kernels)
+            torch.cuda.synchronize()
+            tb = time.perf_counter()
+            mine = bctx.build_egsa(reads_t)
+            tb = time.perf_counter() - tb
+            same = all(bool(torch.equal(mine[k], eg[k])) for k in ("lcp", "text", "suff", "bwt"))
+            egsa_build = {"suffixes": int(mine["n"]), "seconds": tb, "suffixes_per_s": mine["n"] / tb,
+                          "equals_torch_builder": same, "api": "e2s_build_egsa_dev (2-bit keys, one cub radix pass per 64-bit key word)"}
+            log(f"[egsa] native builder: {mine['n']} suffixes in {tb:.3f}s, equal to the torch builder: {same}")
+            del mine, reads_t
+        finally:
+            bctx.close()
+        torch.cuda.empty_cache()
     T = max(1, args.tiles)
     if T > 1:
         args.no_e2e = args.no_cpu_baseline = True
@@ -524,7 +546,7 @@ def main():
                        "l2": "inputs (13 B/position, >= 7 GB per GPU at C2) exceed the 126 MB L2; no flush needed",
                        "resident_layout": f"SoA: lcp u32 + text u32 + suff u32 + bwt u8 + 2-bit base-code planes of the BWT (built at seal); K1 streams a {'one-byte LCP copy built at seal (every LCP value <= 127)' if lcp_bytes == 1 else 'the 4-byte LCP'}",
                        "scale": args.scale, "tiles": T, "exchange_us": exchange_us},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "egsa_build": egsa_build, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "results": {"n_written": int(mg.total_written), "n_clust_out": int(mg.n_clust_out),
                         "max_clust_length": int(st.max_clust_length), "n_analysed_rank0": int(cnt.n_analysed),
                         "n_candidates_rank0": int(cnt.n_candidates), "n_events_rank0": int(cnt.n_events),

@@ -80,7 +80,7 @@ class PipelineResult(C.Structure):
 SYMBOLS = [
     "e2s_version", "e2s_ctx_create", "e2s_ctx_destroy", "e2s_last_error", "e2s_ctx_set_stream",
     "e2s_ctx_synchronize", "e2s_ctx_launch_count", "e2s_ctx_timing", "e2s_ctx_kernel_time", "e2s_shard_create", "e2s_shard_destroy", "e2s_shard_load_gesa",
-    "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_shard_set_layout", "e2s_shard_seal", "e2s_shard_lcp_bytes_resident", "e2s_reads_stage", "e2s_reads_stage_dev",
+    "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_build_egsa_dev", "e2s_shard_set_layout", "e2s_shard_seal", "e2s_shard_lcp_bytes_resident", "e2s_reads_stage", "e2s_reads_stage_dev",
     "e2s_cluster_prefilter", "e2s_cluster_run", "e2s_cluster_merge", "e2s_cluster_finalize", "e2s_cluster_lm", "e2s_cluster_count",
     "e2s_cluster_fetch", "e2s_cluster_fetch_packed", "e2s_clusters_stage_packed", "e2s_clusters_stage",
     "e2s_statistics", "e2s_statistics_finish", "e2s_exchange_finish", "e2s_snp_default_params", "e2s_find_events", "e2s_events_fetch",
@@ -119,6 +119,7 @@ def load_library():
     lib.e2s_shard_load_soa.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64]
     lib.e2s_shard_load_soa_dev.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64]
     lib.e2s_shard_seal.argtypes = [C.c_void_p]
+    lib.e2s_build_egsa_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_void_p] * 4
     lib.e2s_shard_lcp_bytes_resident.argtypes = [C.c_void_p]
     lib.e2s_shard_set_layout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.e2s_reads_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
@@ -228,6 +229,7 @@ class Context:
         if rc:
             raise E2SError(rc, self.lib.e2s_last_error(None).decode())
         self.h = h
+        self.device = int(device)
         if stream is not None:
             self._ck(self.lib.e2s_ctx_set_stream(self.h, C.c_void_p(stream)))
 
@@ -272,6 +274,24 @@ class Context:
             offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
             self._ck(self.lib.e2s_reads_stage(self.h, _ptr(bases), _ptr(offsets), n_reads))
             self.synchronize()
+
+    def build_egsa(self, reads):
+        """EGSA construction on the GPU (e2s_build_egsa_dev): `reads` = (R, L) uint8 ASCII, a numpy array or a torch
+        tensor on this context's device.  Returns the same dict of torch tensors as synth.build_egsa (lcp / text /
+        suff as int32 holding u32, bwt uint8, n, L, R), resident on the device."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        reads_t = (torch.from_numpy(np.ascontiguousarray(reads, dtype=np.uint8)) if isinstance(reads, np.ndarray) else reads)
+        reads_t = reads_t.to(dev).contiguous()
+        R, L = int(reads_t.shape[0]), int(reads_t.shape[1])
+        n = R * (L + 1)
+        out = {k: torch.empty(n, dtype=torch.int32, device=dev) for k in ("lcp", "text", "suff")}
+        out["bwt"] = torch.empty(n, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)  # the library works on its own stream
+        self._ck(self.lib.e2s_build_egsa_dev(self.h, _ptr(reads_t), R, L, _ptr(out["lcp"]), _ptr(out["text"]),
+                                             _ptr(out["suff"]), _ptr(out["bwt"])))
+        out.update(n=n, L=L, R=R)
+        return out
 
     def shard(self, n_local, global_off=0, n_global=None):
         return Shard(self, n_local, global_off, n_local if n_global is None else n_global)

@@ -371,6 +371,22 @@ int e2s_shard_load_soa_dev(e2s_shard* s, const uint32_t* lcp, const uint32_t* te
     return load_soa(s, lcp, text, suff, bwt, first, count, cudaMemcpyDeviceToDevice);
 }
 
+int e2s_build_egsa_dev(e2s_ctx* c, const uint8_t* d_reads, uint64_t n_reads, uint32_t read_len, uint32_t* d_lcp, uint32_t* d_text,
+                       uint32_t* d_suff, uint8_t* d_bwt) {
+    if (!c || !d_reads || !d_lcp || !d_text || !d_suff || !d_bwt) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_dev: NULL argument");
+    if (n_reads == 0 || read_len == 0) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_dev: empty read collection");
+    if (n_reads > 0xffffffffull || n_reads * (uint64_t(read_len) + 1) > 0xffffffffull)
+        return fail(c, E2S_ERR_UNSUPPORTED, "e2s_build_egsa_dev: more than 2^32 - 1 suffixes in one call (build per shard)");
+    CU(c, cudaSetDevice(c->device));
+    cudaError_t e = build_egsa(d_reads, n_reads, read_len, d_lcp, d_text, d_suff, d_bwt, c->stream, &c->launches);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return fail(c, E2S_ERR_NOMEM, "e2s_build_egsa_dev: scratch buffers (about 24 bytes per suffix)");
+    }
+    if (e != cudaSuccess) return cuda_fail(c, e, "build_egsa");
+    return E2S_OK;
+}
+
 int e2s_shard_set_layout(e2s_shard* s, int x, int y, int z, int bcr) {
     if (!s) return fail(nullptr, E2S_ERR_ARG, "shard == NULL");
     auto ok = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8; };

@@ -101,6 +101,11 @@ cudaError_t launch_unpack_gesa(const uint8_t* d_rec, uint64_t count, int x, int 
 cudaError_t launch_fill_phantom(uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt, uint64_t n_local,
                                 uint64_t count, int x, int y, int z, int bcr, cudaStream_t stream);
 
+// ---- EGSA construction (build_egsa.cu) -----------------------------------------------------------
+// suffix sort of R reads of L bases (device pointer) -> lcp/text/suff/bwt device arrays of R (L + 1) elements; synchronises
+cudaError_t build_egsa(const uint8_t* d_reads, uint64_t R, uint32_t L, uint32_t* d_lcp, uint32_t* d_text, uint32_t* d_suff,
+                       uint8_t* d_bwt, cudaStream_t stream, uint64_t* launches);
+
 // ---- phase 2 -----------------------------------------------------------------------------------
 struct SnpDev {  // device counters of one e2s_find_events
     unsigned long long n_analysed;

@@ -92,6 +92,15 @@ int e2s_shard_load_soa(e2s_shard *sh, const uint32_t *lcp, const uint32_t *text,
 /* Same, from DEVICE pointers on the context's device (device-to-device copies). */
 int e2s_shard_load_soa_dev(e2s_shard *sh, const uint32_t *d_lcp, const uint32_t *d_text, const uint32_t *d_suff,
                            const uint8_t *d_bwt, uint64_t first, uint64_t count);
+/* EGSA construction on the GPU: what the reference expects an external egsa / BCR run to have
+ * produced before either tool starts (ref:README.md:46-60, ref:pipeline.sh:98-109).  Suffix-sorts a collection of
+ * n_reads reads of read_len ACGT bases each (DEVICE pointer, row-major ASCII, no separators) and writes the four arrays
+ * of n = n_reads * (read_len + 1) records to DEVICE memory, ready for e2s_shard_load_soa_dev: one record per suffix
+ * incl. the terminator suffix, `$` < A < C < G < T, equal suffixes by read id, lcp never extends over a terminator,
+ * bwt = preceding base or `$` (0x24).  n must be < 2^32 per call.  Synchronises the context's stream. */
+int e2s_build_egsa_dev(e2s_ctx *ctx, const uint8_t *d_reads, uint64_t n_reads, uint32_t read_len, uint32_t *d_lcp,
+                       uint32_t *d_text, uint32_t *d_suff, uint8_t *d_bwt);
+
 /* Layout of the index files the shard was loaded from: byte widths of lcp (x), text (y), suff (z) and whether it
  * was the BCR triple.  Only the reference's post-EOF phantom record depends on it.
  * e2s_shard_load_gesa sets (x, y, z, 0) itself; SoA loads default to (4, 4, 4, 0).  Call before e2s_shard_seal. */

@@ -468,3 +468,58 @@ int oracle_find_events_w(const uint32_t *lcp, const uint32_t *text, const uint32
     *snp_len = out.n;
     return 0;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+ * EGSA construction.  PARITY UNPINNED against the real thing: the reference delegates this step
+ * to the external `egsa` / BCR programs (ref:README.md:46-60, ref:pipeline.sh:98-109), which are neither vendored in
+ * /root/reference nor installed here, and nothing in the reference tree pins their terminator byte or tie order
+ * (last row).  This is the textbook definition -- sort all suffixes of all reads, `$` < A < C < G < T,
+ * equal suffixes by read id -- written as a comparison sort over (read, offset) pairs, with the conventions this
+ * repository's synthetic data has always used (ebwt2snp_b200/synth.py).  It checks the CUDA builder (e2s_build_egsa_dev).
+ * ------------------------------------------------------------------------------------------ */
+#include <stdlib.h>
+
+static const uint8_t *g_sort_reads;
+static uint32_t g_sort_L;
+
+static int suffix_cmp(const void *pa, const void *pb) {
+    const uint64_t a = *(const uint64_t *)pa, b = *(const uint64_t *)pb;
+    const uint64_t ra = a / (g_sort_L + 1), rb = b / (g_sort_L + 1);
+    const uint32_t oa = (uint32_t)(a % (g_sort_L + 1)), ob = (uint32_t)(b % (g_sort_L + 1));
+    const uint8_t *sa = g_sort_reads + ra * g_sort_L + oa, *sb = g_sort_reads + rb * g_sort_L + ob;
+    const uint32_t la = g_sort_L - oa, lb = g_sort_L - ob, lm = la < lb ? la : lb;
+    for (uint32_t i = 0; i < lm; ++i) {
+        if (sa[i] != sb[i]) return sa[i] < sb[i] ? -1 : 1; /* ASCII order of ACGT = code order */
+    }
+    if (la != lb) return la < lb ? -1 : 1; /* the terminator is smaller than every base */
+    return ra < rb ? -1 : (ra > rb ? 1 : 0);
+}
+
+int oracle_build_egsa(const uint8_t *reads, uint64_t n_reads, uint32_t read_len, uint32_t *lcp, uint32_t *text,
+                      uint32_t *suff, uint8_t *bwt) {
+    const uint64_t n = n_reads * ((uint64_t)read_len + 1);
+    uint64_t *idx = (uint64_t *)malloc(n * sizeof *idx);
+    if (!idx) return -1;
+    for (uint64_t i = 0; i < n; ++i) idx[i] = i;
+    g_sort_reads = reads;
+    g_sort_L = read_len;
+    qsort(idx, n, sizeof *idx, suffix_cmp);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t r = idx[i] / (read_len + 1);
+        const uint32_t o = (uint32_t)(idx[i] % (read_len + 1));
+        text[i] = (uint32_t)r;
+        suff[i] = o;
+        bwt[i] = o ? reads[r * read_len + o - 1] : (uint8_t)'$';
+        uint32_t l = 0;
+        if (i) {
+            const uint64_t r0 = idx[i - 1] / (read_len + 1);
+            const uint32_t o0 = (uint32_t)(idx[i - 1] % (read_len + 1));
+            const uint32_t lm = read_len - (o0 > o ? o0 : o);
+            while (l < lm && reads[r0 * read_len + o0 + l] == reads[r * read_len + o + l]) ++l;
+        }
+        lcp[i] = l;
+    }
+    free(idx);
+    return 0;
+}

@@ -104,6 +104,11 @@ uint64_t oracle_phantom_slot(uint32_t lcp_last, uint32_t text_last, uint32_t suf
 /* distance(), ref:clust2snp.cpp:254-302 (equal-length strings) */
 void oracle_distance(const char *a, const char *b, int len, int max_gap, int *D, int *gap);
 
+/* EGSA of n_reads reads of read_len ACGT bases (row-major): n = n_reads * (read_len + 1) records.  Checks
+ * e2s_build_egsa_dev; parity UNPINNED against the external egsa / BCR tools (absent; see oracle.c). */
+int oracle_build_egsa(const uint8_t *reads, uint64_t n_reads, uint32_t read_len, uint32_t *lcp, uint32_t *text,
+                      uint32_t *suff, uint8_t *bwt);
+
 void oracle_free(void *p);
 
 #ifdef __cplusplus

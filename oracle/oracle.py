@@ -188,3 +188,21 @@ def ref_clust2snp(fasta, nreads1, x=4, y=4, z=4, extra=(), timeout=3600):
         if line.startswith("Done. ") and "potential variants" in line:
             info["n_candidates"] = int(line.split()[1])
     return r, info
+
+
+def build_egsa(reads: np.ndarray):
+    """oracle_build_egsa: comparison sort of all suffixes (small inputs only).  Same dict as synth.build_egsa, numpy."""
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    R, L = reads.shape
+    n = R * (L + 1)
+    out = {k: np.empty(n, dtype=np.uint32) for k in ("lcp", "text", "suff")}
+    out["bwt"] = np.empty(n, dtype=np.uint8)
+    f = lib().oracle_build_egsa
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_void_p] * 4
+    rc = f(reads.ctypes.data, R, L, out["lcp"].ctypes.data, out["text"].ctypes.data, out["suff"].ctypes.data,
+           out["bwt"].ctypes.data)
+    if rc:
+        raise MemoryError("oracle_build_egsa")
+    out.update(n=n, L=L, R=R)
+    return out
