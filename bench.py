@@ -394,12 +394,15 @@ def main():
         eg[kk] = None
     torch.cuda.empty_cache()
 
+    # N > 1: the library's own NCCL communicator (one C call per step); E2S_PY_EXCHANGE=1 keeps the torch.distributed exchange
+    comm = sharding.make_comm(ctx, dev) if (world > 1 and not os.environ.get("E2S_PY_EXCHANGE")) else None
+
     def step():
         """one pass of the hot path over the resident shard(s): K1, K2, summaries all-gather + merge, statistics
         all-gather, K3a/K3x/K3b/K4, event-count all-gather (ebwt2snp_b200/sharding.py)"""
         if world == 1:  # the same sequence inside the library: one C call, no Python between the kernels
             return sh.pipeline_resident(params, K_DEF, M_DEF)
-        mg, st, cnt, ids = sharding.hot_path_step(sh, params, K_DEF, M_DEF, dev)
+        mg, st, cnt, ids = sharding.hot_path_step(sh, params, K_DEF, M_DEF, dev, comm=comm)
         step.ids = ids  # global .snp ids are assigned when the text is formatted: resolved after the timed loop
         return mg, st, cnt
 
@@ -542,7 +545,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(args), "positions_per_gpu": n, "positions_total": n_global,
-                       "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; NCCL all-gather of shard summaries",
+                       "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; " + ("one ncclAllGather of the shard summaries per step, issued by the library on its stream (e2s_pipeline_sharded)" if comm is not None else "NCCL all-gather of shard summaries"),
                        "l2": "inputs (13 B/position, >= 7 GB per GPU at C2) exceed the 126 MB L2; no flush needed",
                        "resident_layout": f"SoA: lcp u32 + text u32 + suff u32 + bwt u8 + 2-bit base-code planes of the BWT (built at seal); K1 streams a {'one-byte LCP copy built at seal (every LCP value <= 127)' if lcp_bytes == 1 else 'the 4-byte LCP'}",
                        "scale": args.scale, "tiles": T, "exchange_us": exchange_us},

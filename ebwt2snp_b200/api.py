@@ -85,6 +85,7 @@ SYMBOLS = [
     "e2s_cluster_fetch", "e2s_cluster_fetch_packed", "e2s_clusters_stage_packed", "e2s_clusters_stage",
     "e2s_statistics", "e2s_statistics_finish", "e2s_exchange_finish", "e2s_snp_default_params", "e2s_find_events", "e2s_events_fetch",
     "e2s_events_format", "e2s_free", "e2s_pipeline_resident", "e2s_pipeline_host",
+    "e2s_comm_unique_id", "e2s_comm_create", "e2s_comm_destroy", "e2s_pipeline_sharded",
 ]
 
 _lib = None
@@ -145,6 +146,12 @@ def load_library():
                                       C.POINTER(C.c_size_t)]
     lib.e2s_free.argtypes = [C.c_void_p]
     lib.e2s_pipeline_resident.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(SnpParams), C.POINTER(PipelineResult)]
+    lib.e2s_comm_unique_id.argtypes = [C.c_void_p]
+    lib.e2s_comm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.e2s_comm_destroy.argtypes = [C.c_void_p]
+    lib.e2s_comm_destroy.restype = None
+    lib.e2s_pipeline_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(SnpParams),
+                                         C.POINTER(ClusterMerged), C.POINTER(Stats), C.POINTER(SnpCounts)]
     lib.e2s_pipeline_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(SnpParams), C.c_void_p,
                                       C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PipelineResult)]
@@ -310,6 +317,28 @@ class Context:
         return res
 
 
+class Comm:
+    """The library's own NCCL communicator for the exchange between the phases (one process per GPU).  The 128-byte
+    unique id is created on rank 0 and broadcast by the caller's launcher plumbing (torch.distributed)."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, broadcast_bytes):
+        """broadcast_bytes(bytes | None) -> bytes: collective; returns on every rank what rank 0 passed in"""
+        self.ctx, self.lib = ctx, ctx.lib
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            ctx._ck(self.lib.e2s_comm_unique_id(buf))
+        got = broadcast_bytes(bytes(buf) if rank == 0 else None)
+        idb = (C.c_uint8 * 128).from_buffer_copy(got)
+        h = C.c_void_p()
+        ctx._ck(self.lib.e2s_comm_create(ctx.h, idb, rank, world, C.byref(h)))
+        self.h, self.rank, self.world = h, rank, world
+
+    def close(self):
+        if self.h:
+            self.lib.e2s_comm_destroy(self.h)
+            self.h = None
+
+
 class Shard:
     """A contiguous eBWT range resident on the GPU (see the header)."""
 
@@ -431,6 +460,13 @@ class Shard:
         res = PipelineResult()
         self.ctx._ck(self.lib.e2s_pipeline_resident(self.h, k, min_len, C.byref(params), C.byref(res)))
         return res
+
+    def pipeline_sharded(self, comm: "Comm", params: SnpParams, k=16, min_len=2):
+        """the sharded step in one C call (collective): -> (ClusterMerged of this shard, global Stats, SnpCounts)"""
+        mg, st, cnt = ClusterMerged(), Stats(), SnpCounts()
+        self.ctx._ck(self.lib.e2s_pipeline_sharded(self.h, comm.h, k, min_len, C.byref(params), C.byref(mg), C.byref(st),
+                                                   C.byref(cnt)))
+        return mg, st, cnt
 
     def events(self):
         n = C.c_uint64()

@@ -8,6 +8,8 @@
 #include <string.h>
 #include <time.h>
 
+#include <dlfcn.h>
+
 #include <string>
 #include <vector>
 
@@ -87,6 +89,52 @@ struct e2s_shard {
     std::vector<e2s_event> events;
     uint64_t n_variants = 0;
     bool have_events = false, events_expanded = false;
+};
+
+// ---- NCCL, bound at run time (no link dependency: under Python the process already holds torch's libnccl.so.2, a
+// stand-alone CLI gets the system one).  Only the five calls the inter-phase exchange needs; ABI as in nccl.h 2.x. ----
+typedef struct { char internal[128]; } e2s_nccl_id;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(e2s_nccl_id*) = nullptr;
+    int (*CommInitRank)(void**, int, e2s_nccl_id, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // already in the process (torch)?
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.lib = h;
+            api.GetUniqueId = reinterpret_cast<int (*)(e2s_nccl_id*)>(dlsym(h, "ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<int (*)(void**, int, e2s_nccl_id, int)>(dlsym(h, "ncclCommInitRank"));
+            api.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(h, "ncclAllGather"));
+            api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+            api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+            if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) api.lib = nullptr;
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+constexpr int NCCL_UINT64 = 5;  // ncclUint64 (nccl.h: ncclDataType_t)
+
+// one exchange row per shard: the scan's device accumulators + what the other ranks cannot know
+constexpr size_t XR_DEV_WORDS = sizeof(ClusterDev) / 8;
+constexpr size_t XR_WORDS = XR_DEV_WORDS + 4;  // + n_local, global_off, lcp_bytes, reserved
+
+struct e2s_comm {
+    e2s_ctx* ctx = nullptr;
+    void* nccl = nullptr;
+    int rank = 0, world = 1;
+    uint64_t* d_send = nullptr;  // XR_WORDS
+    uint64_t* d_recv = nullptr;  // world * XR_WORDS
+    uint64_t* h_recv = nullptr;  // pinned
 };
 
 static thread_local std::string g_err;
@@ -507,7 +555,41 @@ int e2s_cluster_prefilter(e2s_shard* s, int mcov_out) {
     return E2S_OK;
 }
 
-int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summary* sum) {
+__global__ void k_pack_exchange(const ClusterDev* res, uint64_t n_local, uint64_t global_off, uint64_t lcp_bytes, uint64_t* row) {
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(res);
+    for (uint32_t i = threadIdx.x; i < XR_DEV_WORDS; i += blockDim.x) row[i] = src[i];
+    if (threadIdx.x == 0) {
+        row[XR_DEV_WORDS + 0] = n_local;
+        row[XR_DEV_WORDS + 1] = global_off;
+        row[XR_DEV_WORDS + 2] = lcp_bytes;
+        row[XR_DEV_WORDS + 3] = 0;
+    }
+}
+
+static void summary_from_row(const uint64_t* row, uint64_t n_global, uint32_t k, int32_t min_len, e2s_cluster_summary* sum) {
+    const ClusterDev& h = *reinterpret_cast<const ClusterDev*>(row);
+    memset(sum, 0, sizeof *sum);
+    sum->n_local = row[XR_DEV_WORDS + 0];
+    sum->global_off = row[XR_DEV_WORDS + 1];
+    sum->n_global = n_global;
+    sum->n_end = h.n_end;
+    sum->n_written = h.n_written;
+    sum->head_end = h.head_end;
+    sum->any_event = h.any_event;
+    sum->open_start = h.any_event ? h.open_start : 0;
+    sum->end_nm2_start = h.end_nm2_start;
+    sum->k = k;
+    sum->min_len = uint64_t(int64_t(min_len));
+    sum->lcp_bytes = row[XR_DEV_WORDS + 2];
+    sum->tail_lcp_nm2 = h.tail_lcp_nm2;
+    sum->tail_lcp_nm1 = h.tail_lcp_nm1;
+    sum->tail_bwt_nm1 = h.tail_bwt_nm1;
+}
+
+// K1 + K2.  cm == NULL: this shard's accumulators come back with one device-to-host copy.  cm != NULL (one process per
+// GPU): the rows of ALL shards come back instead -- packed on the device, all-gathered by NCCL on the same stream, one
+// copy, one synchronisation -- and are left in cm->h_recv for the caller (e2s_pipeline_sharded).
+static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summary* sum, e2s_comm* cm) {
     if (!s || !sum) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_cluster_run: NULL argument");
     e2s_ctx* c = s->ctx;
     if (k == 0) return fail(c, E2S_ERR_ARG, "k must be >= 1 (the CLI maps 0 to the default 16)");
@@ -605,8 +687,29 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
         c->timer.end(c->stream);
         CU(c, le);
         ++c->launches;
-        CU(c, cudaMemcpyAsync(&h, s->d_res, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
+        bool any_overflow = false;
+        uint64_t max_written = 0;
+        if (cm) {
+            NcclApi* na = nccl_api();
+            k_pack_exchange<<<1, 256, 0, c->stream>>>(s->d_res, s->n_local, s->global_off, uint64_t(s->lay_x), cm->d_send);
+            CU(c, cudaGetLastError());
+            ++c->launches;
+            const int nr = na->AllGather(cm->d_send, cm->d_recv, XR_WORDS, NCCL_UINT64, cm->nccl, c->stream);
+            if (nr != 0) return fail(c, E2S_ERR_CUDA, std::string("ncclAllGather: ") + (na->GetErrorString ? na->GetErrorString(nr) : "error"));
+            CU(c, cudaMemcpyAsync(cm->h_recv, cm->d_recv, size_t(cm->world) * XR_WORDS * 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            memcpy(&h, cm->h_recv + size_t(cm->rank) * XR_WORDS, sizeof h);
+            for (int g = 0; g < cm->world; ++g) {  // every rank sees every overflow flag: all of them repeat the round together
+                const ClusterDev& hg = *reinterpret_cast<const ClusterDev*>(cm->h_recv + size_t(g) * XR_WORDS);
+                any_overflow |= hg.overflow != 0;
+                if (hg.n_written > max_written) max_written = hg.n_written;
+            }
+        } else {
+            CU(c, cudaMemcpyAsync(&h, s->d_res, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            any_overflow = h.overflow != 0;
+            max_written = h.n_written;
+        }
         if (d_dbg) {
             std::vector<uint64_t> hd(emit_desc_words() / 2);
             cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
@@ -618,10 +721,12 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
             }
             cudaFree(d_dbg);
         }
-        if (!h.overflow) break;
+        if (!any_overflow) break;
         if (attempt == 1) return fail(c, E2S_ERR_STATE, "record buffer overflow after resize");
-        int rc = ensure_records(s, h.n_written + 4096);
-        if (rc) return rc;
+        if (h.overflow || !cm) {
+            int rc = ensure_records(s, (cm ? h.n_written : max_written) + 4096);
+            if (rc) return rc;
+        }
     }
     memset(sum, 0, sizeof *sum);
     sum->n_local = s->n_local;
@@ -652,6 +757,10 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
     s->have_events = false;
     memset(&s->merged, 0, sizeof s->merged);
     return E2S_OK;
+}
+
+int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summary* sum) {
+    return cluster_run_impl(s, k, min_len, sum, nullptr);
 }
 
 // Host-only: chain the shards' open-cluster states, resolve head records, apply the tail rule with
@@ -1177,6 +1286,95 @@ int e2s_pipeline_resident(e2s_shard* s, uint32_t k, int32_t min_len, const e2s_s
     if ((rc = e2s_find_events(s, p, st.max_clust_length, &res->snp))) return rc;
     res->d2h_bytes += res->snp.n_candidates * 128;
     return E2S_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one process per GPU: the inter-phase exchange inside the library (NCCL on the context's stream)
+// ---------------------------------------------------------------------------------------------
+int e2s_comm_unique_id(uint8_t* id128) {
+    if (!id128) return fail(nullptr, E2S_ERR_ARG, "e2s_comm_unique_id: NULL argument");
+    NcclApi* na = nccl_api();
+    if (!na) return fail(nullptr, E2S_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+    e2s_nccl_id id;
+    const int r = na->GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, E2S_ERR_CUDA, std::string("ncclGetUniqueId: ") + (na->GetErrorString ? na->GetErrorString(r) : "error"));
+    memcpy(id128, id.internal, 128);
+    return E2S_OK;
+}
+
+int e2s_comm_create(e2s_ctx* c, const uint8_t* id128, int rank, int world, e2s_comm** out) {
+    if (!c || !id128 || !out || world < 1 || rank < 0 || rank >= world) return fail(c, E2S_ERR_ARG, "e2s_comm_create: bad argument");
+    *out = nullptr;
+    NcclApi* na = nccl_api();
+    if (!na) return fail(c, E2S_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+    CU(c, cudaSetDevice(c->device));
+    e2s_comm* cm = new e2s_comm();
+    cm->ctx = c;
+    cm->rank = rank;
+    cm->world = world;
+    e2s_nccl_id id;
+    memcpy(id.internal, id128, 128);
+    const int r = na->CommInitRank(&cm->nccl, world, id, rank);
+    if (r != 0) {
+        delete cm;
+        return fail(c, E2S_ERR_CUDA, std::string("ncclCommInitRank: ") + (na->GetErrorString ? na->GetErrorString(r) : "error"));
+    }
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&cm->d_send), XR_WORDS * 8);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&cm->d_recv), size_t(world) * XR_WORDS * 8);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&cm->h_recv), size_t(world) * XR_WORDS * 8, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        e2s_comm_destroy(cm);
+        return fail(c, E2S_ERR_NOMEM, "e2s_comm_create: exchange buffers");
+    }
+    *out = cm;
+    return E2S_OK;
+}
+
+void e2s_comm_destroy(e2s_comm* cm) {
+    if (!cm) return;
+    cudaSetDevice(cm->ctx->device);
+    if (cm->nccl) {
+        if (NcclApi* na = nccl_api()) na->CommDestroy(cm->nccl);
+    }
+    cudaFree(cm->d_send);
+    cudaFree(cm->d_recv);
+    cudaFreeHost(cm->h_recv);
+    delete cm;
+}
+
+// The sharded step in one call: K1, K2, ONE all-gather of the scan accumulators (summary + own length histogram) on
+// the stream, host merge of all shards + statistics, K3/K4 on local data.  Two host synchronisations, like the
+// single-shard e2s_pipeline_resident.
+int e2s_pipeline_sharded(e2s_shard* s, e2s_comm* cm, uint32_t k, int32_t min_len, const e2s_snp_params* p, e2s_cluster_merged* mg,
+                         e2s_stats* st, e2s_snp_counts* cnt) {
+    if (!s || !cm || !p || !mg || !st || !cnt) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_pipeline_sharded: NULL argument");
+    e2s_ctx* c = s->ctx;
+    if (cm->ctx != c) return fail(c, E2S_ERR_ARG, "e2s_pipeline_sharded: communicator belongs to another context");
+    const uint32_t arm_before = s->pf_arm;
+    s->pf_arm = (getenv("E2S_NO_FUSED_PREFILTER") || p->mcov_out < 1 || 2 * p->mcov_out > E2S_MAX_C_LEN) ? 0u : uint32_t(p->mcov_out);
+    e2s_cluster_summary own_sum;
+    int rc = cluster_run_impl(s, k, min_len, &own_sum, cm);
+    s->pf_arm = arm_before;
+    if (rc) return rc;
+    std::vector<e2s_cluster_summary> sums(size_t(cm->world));
+    std::vector<e2s_stats> own(size_t(cm->world));
+    for (int g = 0; g < cm->world; ++g) {
+        const uint64_t* row = cm->h_recv + size_t(g) * XR_WORDS;
+        summary_from_row(row, s->n_global, k, min_len, &sums[size_t(g)]);
+        const ClusterDev& h = *reinterpret_cast<const ClusterDev*>(row);
+        e2s_stats& o = own[size_t(g)];
+        memset(&o, 0, sizeof o);
+        for (int i = 0; i < E2S_HIST_BINS; ++i) o.hist[i] = h.hist[i];
+        o.n_bases = h.n_bases;
+        o.n_clust = h.n_written;
+        o.last_len = h.last_rec & 0xffff;
+    }
+    if ((rc = e2s_exchange_finish(sums.data(), own.data(), cm->world, cm->rank, p->mcov_out, p->pval, mg, st))) {
+        c->err = g_err;
+        return rc;
+    }
+    if ((rc = e2s_cluster_finalize(s, mg))) return rc;
+    return e2s_find_events(s, p, st->max_clust_length, cnt);
 }
 
 int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, int z, const uint8_t* read_bases,

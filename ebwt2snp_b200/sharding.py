@@ -185,10 +185,30 @@ def exchange_and_merge(summary: api.ClusterSummary, own: api.Stats, mcov_out, pv
     return api.exchange_finish(sum_rows, stat_rows, rank, mcov_out, pval)
 
 
-def hot_path_step(shard: "api.Shard", params: api.SnpParams, k, min_len, device, group=None):
-    """One pass of the hot path on this rank's resident shard, collectives included.
-    -> (ClusterMerged, Stats (global), SnpCounts (this shard), EventIdOffset: .resolve() gives the first id_nr of this shard)"""
+def make_comm(ctx: "api.Context", device, group=None) -> "api.Comm":
+    """The library's own NCCL communicator over the ranks of the process group (its unique id travels through one
+    torch.distributed broadcast).  With it, hot_path_step runs as ONE C call per step (e2s_pipeline_sharded): the
+    exchange between the phases is an ncclAllGather on the library's stream instead of Python-driven collectives."""
     rank, world = _world(group)
+
+    def bcast(data):
+        t = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+        dist.broadcast(t, src=0, group=group)
+        return bytes(t.cpu().numpy().tobytes())
+
+    return api.Comm(ctx, rank, world, bcast)
+
+
+def hot_path_step(shard: "api.Shard", params: api.SnpParams, k, min_len, device, group=None, comm=None):
+    """One pass of the hot path on this rank's resident shard, collectives included.
+    -> (ClusterMerged, Stats (global), SnpCounts (this shard), EventIdOffset: .resolve() gives the first id_nr of this shard)
+    comm (make_comm): the whole step is one library call, the exchange an ncclAllGather on the library's stream."""
+    rank, world = _world(group)
+    if comm is not None and world > 1:
+        mg, st, cnt = shard.pipeline_sharded(comm, params, k, min_len)
+        return mg, st, cnt, EventIdOffset(cnt.n_events, device, group)
     shard.cluster_prefilter(params.mcov_out)  # both phases run here: K2 applies the BWT prefilter while it writes the records
     s = shard.cluster_run(k, min_len)
     if world == 1:

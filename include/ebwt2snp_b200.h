@@ -270,6 +270,19 @@ typedef struct {
  * Records and events stay on the shard (e2s_cluster_fetch*, e2s_events_fetch). */
 int e2s_pipeline_resident(e2s_shard *sh, uint32_t k, int32_t min_len, const e2s_snp_params *p, e2s_pipeline_result *res);
 
+/* One process per GPU: the exchange between the phases inside the library.  A communicator wraps an
+ * NCCL communicator created from a 128-byte unique id (made on one rank with e2s_comm_unique_id and handed to the others
+ * by whatever launched the processes: torch.distributed in bench.py).  NCCL is bound at run time (libnccl.so.2).
+ * e2s_pipeline_sharded = e2s_pipeline_resident for a shard of a sharded eBWT: K1 + K2, ONE ncclAllGather of every shard's
+ * scan accumulators on the context's stream, e2s_exchange_finish on the host (identical on all ranks), K3/K4 on local
+ * data.  Collective: every rank of the communicator must call it. */
+typedef struct e2s_comm e2s_comm;
+int e2s_comm_unique_id(uint8_t *id128);
+int e2s_comm_create(e2s_ctx *ctx, const uint8_t *id128, int rank, int world, e2s_comm **out);
+void e2s_comm_destroy(e2s_comm *comm);
+int e2s_pipeline_sharded(e2s_shard *sh, e2s_comm *comm, uint32_t k, int32_t min_len, const e2s_snp_params *p,
+                         e2s_cluster_merged *merged, e2s_stats *stats, e2s_snp_counts *counts);
+
 /* ebwt2clust + clust2snp on one GPU from host buffers: .gesa records + reads in, .clusters
  * records (10-byte, into rec10 if non-NULL) and events out. */
 int e2s_pipeline_host(e2s_ctx *ctx, const void *gesa_records, uint64_t n, int x, int y, int z,

@@ -39,7 +39,12 @@ def main():
         off = O.uniform_read_offsets(*rs.reads.shape)
         ctx.stage_reads(rs.reads, off)
         p = api.default_params(rs.nreads1)
+        # once through the torch.distributed exchange, once through the library's own NCCL communicator: same result
         mg, st, cnt, ids = sharding.hot_path_step(sh, p, k, m, dev)
+        comm = sharding.make_comm(ctx, dev)
+        mg2, st2, cnt2, _ = sharding.hot_path_step(sh, p, k, m, dev, comm=comm)
+        assert bytes(mg2) == bytes(mg) and bytes(st2) == bytes(st) and bytes(cnt2) == bytes(cnt), "native exchange differs"
+        comm.close()
         first_id, total_events = ids.resolve()
         recs = sh.cluster_fetch_packed()
         text = api.events_format(sh.events(), p, first_id=first_id)
