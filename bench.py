@@ -301,7 +301,7 @@ def main():
     ap.add_argument("--cpu-positions", type=float, default=3e7, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--egsa-build", action="store_true", help="also time the library's EGSA builder on the workload's reads")
+    ap.add_argument("--no-egsa-build", action="store_true", help="skip timing the library's EGSA builder on the workload's reads (N = 1 only)")
     ap.add_argument("--tiles", type=int, default=1,
                     help="resident-only study: tile the workload T times on the GPU (read ids shifted; every tile starts with "
                          "lcp = 0), e.g. --tiles 8 = 4.46e9 positions, C3/C4-sized shards; implies --no-e2e --no-cpu-baseline")
@@ -331,7 +331,7 @@ def main():
     # ---- EGSA construction on the GPU (data preparation, outside the timed step): the library's
     # builder on the same reads, timed, and compared element by element with the arrays the step below runs on ----
     egsa_build = None
-    if args.egsa_build and world == 1:
+    if not args.no_egsa_build and world == 1:
         from ebwt2snp_b200 import api as _api
         bctx = _api.Context(local)
         try:

@@ -3,7 +3,7 @@ cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
 TAG=${TAG:-r1_v18}
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --egsa-build > gpurun_out/bench_${TAG}_c2.json 2> gpurun_out/bench_c2.err; echo "bench rc=$?"
+timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_${TAG}_c2.json 2> gpurun_out/bench_c2.err; echo "bench rc=$?"
 E2S_NO_FUSED_PREFILTER=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_${TAG}_c2_twophase.json 2>> gpurun_out/bench_c2.err; echo "bench two-phase rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 60 --csv --log-file gpurun_out/${TAG}_launches_c2.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "launches rc=$?"
 python - <<PY
