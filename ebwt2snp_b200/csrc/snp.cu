@@ -545,6 +545,18 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
         __syncwarp();
         // support: reads within max_err mismatches of the consensus, ref:clust2snp.cpp:556-567
         int sp = 0;
+        if (kl <= 32) {  // one context position per lane: a mismatch count is the popcount of a ballot
+            const bool act = lane < kl;
+            const uint32_t c = act ? uint32_t(uint8_t(s_cons[w][s][lane])) : 0u;
+            for (uint32_t j0 = 0; j0 < nr; j0 += EV_B) {
+                uint32_t ch[EV_B];
+#pragma unroll
+                for (int u = 0; u < EV_B; ++u) ch[u] = (act && j0 + u < nr) ? p.bases[s_base[w][j0 + u] + lane] : c;
+#pragma unroll
+                for (int u = 0; u < EV_B; ++u)
+                    if (j0 + u < nr) sp += int(__popc(__ballot_sync(FULL, ch[u] != c))) <= p.max_err;  // (warp-uniform condition)
+            }
+        } else
         for (uint32_t j0 = 0; j0 < nr; j0 += EV_B) {
             int d[EV_B];
 #pragma unroll
@@ -606,6 +618,23 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
     const char* b = s_cons[w][1];
     uint32_t best_ab = 0xffffffffu, best_ba = 0xffffffffu;  // (dist << 8) | g : min => smallest dist, then smallest g
     int d0 = 0;
+    if (kl <= 32) {
+        // lane t holds a[t] and b[t]: dH of the right-aligned strings with g characters dropped on the right of a
+        // (resp. b) = #{t >= g : a[t-g] != b[t]} (resp. a[t] != b[t-g]) = popcount of a ballot; every lane ends with the result
+        const uint32_t av = lane < kl ? uint32_t(uint8_t(a[lane])) : 0x100u, bv = lane < kl ? uint32_t(uint8_t(b[lane])) : 0x100u;
+        for (int g = 0; g <= p.max_gap; ++g) {
+            const uint32_t as = __shfl_up_sync(FULL, av, g), bs = __shfl_up_sync(FULL, bv, g);
+            const bool in = lane >= g && lane < kl;
+            const int dab = __popc(__ballot_sync(FULL, in && as != bv));
+            const int dba = __popc(__ballot_sync(FULL, in && av != bs));
+            if (g == 0) d0 = dab;
+            else {
+                const uint32_t kab = (uint32_t(dab + g) << 8) | uint32_t(g), kba = (uint32_t(dba + g) << 8) | uint32_t(g);
+                best_ab = kab < best_ab ? kab : best_ab;
+                best_ba = kba < best_ba ? kba : best_ba;
+            }
+        }
+    } else {
     for (int g = lane; g <= p.max_gap; g += 32) {
         int dab = 0, dba = 0;
         const int n = kl - g;  // compared length, right aligned
@@ -625,6 +654,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
         uint32_t x = __shfl_xor_sync(FULL, best_ab, o2), y = __shfl_xor_sync(FULL, best_ba, o2);
         best_ab = x < best_ab ? x : best_ab;
         best_ba = y < best_ba ? y : best_ba;
+    }
     }
     int D, gap;
     const int min_ab = int(best_ab >> 8), g_ab = int(best_ab & 0xff), min_ba = int(best_ba >> 8), g_ba = int(best_ba & 0xff);

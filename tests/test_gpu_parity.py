@@ -193,7 +193,9 @@ def test_pipeline_vs_oracle(ctx, name, seed):
     assert nc == enc and np.array_equal(s, es) and np.array_equal(l, el)
     assert sh.cluster_fetch_packed() == O.clusters_to_bytes(es, el)
 
-    for kw in ({}, {"mcov_out": 3}, {"consensus_reads": 3, "max_gap": 4}, {"k_left": 25, "k_right": 20, "max_err": 1}):
+    # (k_left <= 32 takes K4's one-position-per-lane ballot paths, k_left > 32 the strided ones; 32 is the boundary)
+    for kw in ({}, {"mcov_out": 3}, {"consensus_reads": 3, "max_gap": 4}, {"k_left": 25, "k_right": 20, "max_err": 1},
+               {"k_left": 32, "max_gap": 32}, {"k_left": 40, "k_right": 35, "max_gap": 12}, {"k_left": 33, "max_err": 0}):
         p = api.default_params(rs.nreads1, **kw)
         op = O.default_params(rs.nreads1, **kw)
         st = sh.statistics(p.mcov_out, p.pval)
