@@ -80,7 +80,7 @@ class PipelineResult(C.Structure):
 SYMBOLS = [
     "e2s_version", "e2s_ctx_create", "e2s_ctx_destroy", "e2s_last_error", "e2s_ctx_set_stream",
     "e2s_ctx_synchronize", "e2s_ctx_launch_count", "e2s_ctx_timing", "e2s_ctx_kernel_time", "e2s_shard_create", "e2s_shard_destroy", "e2s_shard_load_gesa",
-    "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_build_egsa_dev", "e2s_shard_set_layout", "e2s_shard_seal", "e2s_shard_lcp_bytes_resident", "e2s_reads_stage", "e2s_reads_stage_dev",
+    "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_build_egsa_dev", "e2s_build_egsa", "e2s_shard_set_layout", "e2s_shard_seal", "e2s_shard_lcp_bytes_resident", "e2s_reads_stage", "e2s_reads_stage_dev",
     "e2s_cluster_prefilter", "e2s_cluster_run", "e2s_cluster_merge", "e2s_cluster_finalize", "e2s_cluster_lm", "e2s_cluster_count",
     "e2s_cluster_fetch", "e2s_cluster_fetch_packed", "e2s_clusters_stage_packed", "e2s_clusters_stage",
     "e2s_statistics", "e2s_statistics_finish", "e2s_exchange_finish", "e2s_snp_default_params", "e2s_find_events", "e2s_events_fetch",
@@ -121,6 +121,7 @@ def load_library():
     lib.e2s_shard_load_soa_dev.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64]
     lib.e2s_shard_seal.argtypes = [C.c_void_p]
     lib.e2s_build_egsa_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_void_p] * 4
+    lib.e2s_build_egsa.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_void_p] * 4
     lib.e2s_shard_lcp_bytes_resident.argtypes = [C.c_void_p]
     lib.e2s_shard_set_layout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.e2s_reads_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]

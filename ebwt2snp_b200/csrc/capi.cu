@@ -435,6 +435,39 @@ int e2s_build_egsa_dev(e2s_ctx* c, const uint8_t* d_reads, uint64_t n_reads, uin
     return E2S_OK;
 }
 
+int e2s_build_egsa(e2s_ctx* c, const uint8_t* reads, uint64_t n_reads, uint32_t read_len, uint32_t* lcp, uint32_t* text, uint32_t* suff,
+                   uint8_t* bwt) {
+    if (!c || !reads || !lcp || !text || !suff || !bwt) return fail(c, E2S_ERR_ARG, "e2s_build_egsa: NULL argument");
+    if (n_reads == 0 || read_len == 0) return fail(c, E2S_ERR_ARG, "e2s_build_egsa: empty read collection");
+    CU(c, cudaSetDevice(c->device));
+    const uint64_t n = n_reads * (uint64_t(read_len) + 1);
+    uint8_t *d_reads = nullptr, *d_bwt = nullptr;
+    uint32_t *d_lcp = nullptr, *d_text = nullptr, *d_suff = nullptr;
+    auto release = [&]() { cudaFree(d_reads); cudaFree(d_bwt); cudaFree(d_lcp); cudaFree(d_text); cudaFree(d_suff); };
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_reads), n_reads * read_len);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_bwt), n);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_lcp), n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_text), n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_suff), n * 4);
+    if (e != cudaSuccess) {
+        release();
+        cudaGetLastError();
+        return fail(c, E2S_ERR_NOMEM, "e2s_build_egsa: device buffers");
+    }
+    e = cudaMemcpyAsync(d_reads, reads, n_reads * read_len, cudaMemcpyHostToDevice, c->stream);
+    int rc = e == cudaSuccess ? e2s_build_egsa_dev(c, d_reads, n_reads, read_len, d_lcp, d_text, d_suff, d_bwt) : cuda_fail(c, e, "H2D reads");
+    if (rc == E2S_OK) {
+        e = cudaMemcpyAsync(lcp, d_lcp, n * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(text, d_text, n * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(suff, d_suff, n * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(bwt, d_bwt, n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(c, e, "D2H index arrays");
+    }
+    release();
+    return rc;
+}
+
 int e2s_shard_set_layout(e2s_shard* s, int x, int y, int z, int bcr) {
     if (!s) return fail(nullptr, E2S_ERR_ARG, "shard == NULL");
     auto ok = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8; };

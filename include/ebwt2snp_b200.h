@@ -101,6 +101,10 @@ int e2s_shard_load_soa_dev(e2s_shard *sh, const uint32_t *d_lcp, const uint32_t 
 int e2s_build_egsa_dev(e2s_ctx *ctx, const uint8_t *d_reads, uint64_t n_reads, uint32_t read_len, uint32_t *d_lcp,
                        uint32_t *d_text, uint32_t *d_suff, uint8_t *d_bwt);
 
+/* Same from / to HOST memory (what ebwt2snp_b200/bin/build_gesa uses): device buffers are allocated and released inside. */
+int e2s_build_egsa(e2s_ctx *ctx, const uint8_t *reads, uint64_t n_reads, uint32_t read_len, uint32_t *lcp, uint32_t *text,
+                   uint32_t *suff, uint8_t *bwt);
+
 /* Layout of the index files the shard was loaded from: byte widths of lcp (x), text (y), suff (z) and whether it
  * was the BCR triple.  Only the reference's post-EOF phantom record depends on it.
  * e2s_shard_load_gesa sets (x, y, z, 0) itself; SoA loads default to (4, 4, 4, 0).  Call before e2s_shard_seal. */

@@ -134,3 +134,51 @@ def test_cli_multiline_fasta(built, tmp_path):
     r = run("clust2snp", "-i", fa, "-n", g["nreads1"], "-x", 4, "-y", 4, "-z", 4)
     assert r.returncode == 0, r.stderr
     assert open(os.path.join(str(tmp_path), "micro_b.snp"), "rb").read() == g["variants"][0]["snp"]
+
+
+def test_build_gesa_cli_feeds_both_tool_chains(built, tmp_path):
+    """build_gesa (index construction on the GPU) writes the files the tools look for: byte-identical
+    to the synthetic-data writer for the egsa default layout 4/1/1 (ref:pipeline.sh:30-32), 4/4/4 and the BCR triple; the
+    UNMODIFIED reference tools run on its output give the same .clusters / .snp as this repository's tools."""
+    rs = synth.make_config("tiny", seed=11)
+    e = synth.build_egsa(rs.reads)
+    for j, (x, y, z, bcr) in enumerate([(1, 4, 1, False), (4, 4, 4, False), (2, 4, 2, True)]):
+        d = tmp_path / f"b{j}"
+        want = synth.write_dataset(str(d / "want"), rs, e, x=x, y=y, z=z, bcr=bcr)
+        os.makedirs(d / "got")
+        fa = str(d / "got" / "ALL.fasta")
+        synth.write_fasta(fa, rs.reads)
+        r = run("build_gesa", "-i", fa, "-x", x, "-y", y, "-z", z, *(["-b"] if bcr else []))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert f"Done. {e['n']} suffixes of {rs.reads.shape[0]} reads indexed." in r.stdout
+        for ext in ((".out", ".out.lcp", ".out.pairSA") if bcr else (".gesa",)):
+            assert open(fa + ext, "rb").read() == open(want + ext, "rb").read(), (x, y, z, bcr, ext)
+    # the 4/1/1 index through both tool chains
+    fa = str(tmp_path / "b0" / "got" / "ALL.fasta")
+    w = ["-x", 1, "-y", 4, "-z", 1]
+    r = run("ebwt2clust", "-i", fa, *w)
+    assert r.returncode == 0, r.stderr
+    mine_cl = open(fa + ".clusters", "rb").read()
+    r = run("clust2snp", "-i", fa, "-n", rs.nreads1, *w)
+    assert r.returncode == 0, r.stderr
+    mine_snp = open(str(tmp_path / "b0" / "got" / "ALL.snp"), "rb").read()
+    assert len(mine_snp) > 0
+    if O.ref_available():
+        for f in (fa + ".clusters", str(tmp_path / "b0" / "got" / "ALL.snp")):
+            os.remove(f)
+        ref = os.path.join(ROOT, "oracle", "_ref")
+        r1 = subprocess.run([os.path.join(ref, "ebwt2clust"), "-i", fa, "-x", "1", "-y", "4", "-z", "1"], capture_output=True, text=True, timeout=600)
+        assert r1.returncode == 0
+        assert open(fa + ".clusters", "rb").read() == mine_cl
+        r2 = subprocess.run([os.path.join(ref, "clust2snp"), "-i", fa, "-n", str(rs.nreads1), "-x", "1", "-y", "4", "-z", "1"],
+                            capture_output=True, text=True, timeout=600)
+        assert r2.returncode == 0
+        assert open(str(tmp_path / "b0" / "got" / "ALL.snp"), "rb").read() == mine_snp
+
+
+def test_build_gesa_cli_rejects_ragged_reads(built, tmp_path):
+    fa = str(tmp_path / "r.fasta")
+    open(fa, "w").write(">a\nACGT\n>b\nACG\n")
+    r = run("build_gesa", "-i", fa)
+    assert r.returncode == 2 and "equal-length" in r.stdout
+    assert not os.path.exists(fa + ".gesa")

@@ -67,3 +67,21 @@ def test_fasta_reader_multiline_and_ragged(built, tmp_path):
     fa.write_text("first line is a header\nACGT\nAC\n>r2 desc\nGGGTTT\n>r3\nA\nC\nG\n>r4\nTTTT")
     out = subprocess.run([str(exe), str(fa)], capture_output=True, text=True, check=True).stdout.split()
     assert out == ["4", "ACGTAC", "GGGTTT", "ACG", "TTTT"]
+
+
+def test_build_gesa_decisions_before_gpu_work(built, tmp_path):
+    """build_gesa: help exits 0 like the reference's tools; unreadable input -> 1; ragged reads -> 2 (before any CUDA call);
+    without a GPU the library refuses loudly (exit 3, no index written) -- there is no CPU builder"""
+    for args in ([], ["-h"], ["-Q"], ["-x", "3", "-i", "x"]):
+        r = run("build_gesa", *args)
+        assert r.returncode == 0 and "build_gesa [options]" in r.stdout, args
+    assert run("build_gesa", "-i", str(tmp_path / "missing.fasta")).returncode == 1
+    fa = tmp_path / "r.fasta"
+    fa.write_text(">a\nACGT\n>b\nACG\n")
+    r = run("build_gesa", "-i", str(fa))
+    assert r.returncode == 2 and "equal-length" in r.stdout
+    import torch
+    if not torch.cuda.is_available():
+        fa.write_text(">a\nACGT\n>b\nACGA\n")
+        r = run("build_gesa", "-i", str(fa))
+        assert r.returncode == 3 and "no CPU fallback" in r.stdout and not os.path.exists(str(fa) + ".gesa")
