@@ -286,10 +286,115 @@ def snp_text_tools(d):
     print("snp_text:", len(inputs), "inputs")
 
 
+def snp_vs_vcf_inputs():
+    """Planted-truth inputs for snp_vs_vcf: the generator knows the SNPs it planted, so it can
+    write the VCF and the sample-1 reference; the calls are the .snp text of the oracle's ebwt2clust + clust2snp on the
+    same read set.  -> list of (name, {fasta, vcf, calls: bytes}, extra argv)"""
+    from ebwt2snp_b200 import synth
+    rs = synth.make_config("tiny", seed=21)
+    e = synth.build_egsa(rs.reads)
+    lcp, text, suff = (e[k].numpy().view(np.uint32) for k in ("lcp", "text", "suff"))
+    bwt = e["bwt"].numpy()
+    es, el, _, _ = O.cluster_lm(lcp, bwt, 16, 2)
+    op = O.default_params(rs.nreads1)
+    st = O.statistics(es, el, op.mcov_out, op.pval)
+    calls, _ = O.find_events(lcp, text, suff, bwt, es, el, op, st.max_clust_length, rs.reads, O.uniform_read_offsets(*rs.reads.shape))
+    g1 = rs.genome1.tobytes().decode()
+    g2 = rs.genome2.tobytes().decode()
+    rng = np.random.default_rng(5)
+
+    def fasta(contigs, width=60, lower_every=7):
+        out = []
+        for j, (name, seq) in enumerate(contigs):
+            out.append(">" + name)
+            for i in range(0, len(seq), width):
+                line = seq[i:i + width]
+                out.append(line.lower() if (i // width + j) % lower_every == 0 else line)
+        return ("\n".join(out) + "\n").encode()
+
+    def vcf(rows, extra=()):
+        lines = ["##fileformat=VCFv4.2", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO"]
+        lines += ["%s\t%d\t.\t%s\t%s\t.\tPASS\t." % r for r in rows]
+        lines += list(extra)
+        return ("\n".join(lines) + "\n").encode()
+
+    # sample 2 has no indels in genome coordinates before a SNP only if n_indels == 0; "tiny" plants 8 short indels, whose
+    # coordinates shift g2: the ALT base is read from the reads' point of view = g2 at the shifted position
+    shift = np.zeros(len(g1) + 1, dtype=np.int64)
+    for p, ln in rs.indels:
+        shift[p:] += ln
+    rows = []
+    for p in rs.snp_pos.tolist():
+        alt = g2[p + int(shift[p])] if 0 <= p + int(shift[p]) < len(g2) else "N"
+        rows.append(("chr1", p + 1, g1[p], alt))
+    indel_rows = [("chr1", p + 1, g1[p:p + 2], g1[p]) for p, ln in rs.indels if ln < 0][:3]
+    rows_all = sorted(rows + indel_rows, key=lambda r: r[1])
+    cases = []
+    cases.append(("planted", dict(fasta=fasta([("chr1", g1)]), vcf=vcf(rows_all), calls=calls), []))
+    cases.append(("k1000_l50", dict(fasta=fasta([("chr1", g1)]), vcf=vcf(rows_all), calls=calls), ["-k", "1000", "-l", "50"]))
+    # two contigs with descriptions, an unknown chromosome, a SNP too close to the start, one beyond the end, position 0
+    half = len(g1) // 2
+    rows2 = [("ctgA first half", p, r, a) if p <= half else ("ctgB", p - half, r, a) for (_, p, r, a) in rows]
+    rows2 = [(c.split()[0] if c.startswith("ctgB") else c, p, r, a) for (c, p, r, a) in rows2]
+    extra = ["chrUn\t77\t.\tA\tC\t.\tPASS\t.", "ctgB\t5\t.\tA\tG\t.\tPASS\t.", "ctgB\t%d\t.\tC\tT\t.\tPASS\t." % (len(g1) - half + 50),
+             "ctgB\t0\t.\tG\tT\t.\tPASS\t.", ""]
+    # (istream >> reads the contig name up to the first blank: "ctgA first half" in the VCF names contig "ctgA", which the
+    # FASTA calls "ctgA first half" -> not found, a WARNING per line: the reference's behaviour, kept)
+    cases.append(("two_contigs", dict(fasta=fasta([("ctgA first half", g1[:half]), ("ctgB", g1[half:])]),
+                                     vcf=vcf([r for r in rows2], extra), calls=calls), []))
+    # damaged calls: invented SNP records (false positives), a record with two mismatching columns, no trailing newline
+    recs = calls.decode().split("\n")
+    fake = []
+    for j in range(5):
+        a = "".join(rng.choice(list("ACGT"), size=61))
+        b = list(a)
+        b[30] = "ACGT"[("ACGT".index(a[30]) + 1) % 4]
+        if j == 4:
+            b[10] = "ACGT"[("ACGT".index(a[10]) + 2) % 4]
+        fake += [">SNP_higher_path_%d|P_1:30_%s/%s|5|nb_pol_1" % (900 + j, a[30], b[30]), a,
+                 ">SNP_lower_path_%d|P_1:30_%s/%s|6|nb_pol_1" % (900 + j, a[30], b[30]), "".join(b)]
+    damaged = "\n".join(recs[:40] + fake + recs[40:80])
+    cases.append(("damaged_calls", dict(fasta=fasta([("chr1", g1)]), vcf=vcf(rows_all), calls=damaged.rstrip("\n").encode()), []))
+    bad = "\n".join([">SNP_higher_path_1|P_1:30_A/C|5|nb_pol_1", "ACGTACGT", ">SNP_lower_path_1|P_1:30_A/C|5|nb_pol_1", "ACGTACG", ""])
+    cases.append(("unequal_lengths", dict(fasta=fasta([("chr1", g1)]), vcf=vcf(rows_all), calls=bad.encode()), []))
+    cases.append(("empty_calls", dict(fasta=fasta([("chr1", g1)]), vcf=vcf(rows_all), calls=b""), []))
+    return cases
+
+
+def snp_vs_vcf_golden(d):
+    """stdout + exit code of the reference's snp_vs_vcf on the planted-truth inputs"""
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref", "snp_vs_vcf")
+    out = {}
+    cases = snp_vs_vcf_inputs()
+    for j, (name, files, argv) in enumerate(cases):
+        paths = {}
+        for k, data in files.items():
+            paths[k] = os.path.join(d, f"svv{j}.{k}")
+            open(paths[k], "wb").write(data)
+            out[f"{j}_{k}"] = np.frombuffer(data, dtype=np.uint8)
+        r = subprocess.run([ref, "-v", paths["vcf"], "-c", paths["calls"], "-f", paths["fasta"], *argv], capture_output=True, timeout=120)
+        out[f"{j}_stdout"] = np.frombuffer(r.stdout, dtype=np.uint8)
+        out[f"{j}_rc"] = np.int64(r.returncode)
+        out[f"{j}_argv"] = np.array(argv, dtype="U16")
+        out[f"{j}_name"] = np.array(name)
+        print("snp_vs_vcf", name, "rc", r.returncode, r.stdout.decode().strip().splitlines()[-7:])
+    out["n"] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(HERE, "snp_vs_vcf.npz"), **out)
+
+
 if __name__ == "__main__":
     assert O.ref_available(), "oracle/_ref missing: run `make -C oracle ref` where /root/reference exists"
+    if len(sys.argv) > 1 and sys.argv[1] == "snp_vs_vcf":  # only this fixture
+        d = tempfile.mkdtemp(prefix="golden_")
+        try:
+            snp_vs_vcf_golden(d)
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+        sys.exit(0)
     d = tempfile.mkdtemp(prefix="golden_")
     try:
+        snp_vs_vcf_golden(d)
         phase1_fuzz(d)
         phantom_tail(d)
         phase1_fuzz_widths(d)

@@ -182,3 +182,26 @@ def test_build_gesa_cli_rejects_ragged_reads(built, tmp_path):
     r = run("build_gesa", "-i", fa)
     assert r.returncode == 2 and "equal-length" in r.stdout
     assert not os.path.exists(fa + ".gesa")
+
+
+def test_reads_to_scores_with_the_tools_alone(built, tmp_path):
+    """the reference's pipeline.sh end to end with this repository's tools only (ref:pipeline.sh:98-140): reads FASTA ->
+    build_gesa (4/1/1, egsa's default layout) -> ebwt2clust -> clust2snp -> snp_vs_vcf against the planted truth.  The .snp
+    equals the one the snp_vs_vcf golden fixture was made from (the oracle's), so the scores equal the reference tool's."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "snp_vs_vcf.npz"))
+    assert str(z["0_name"]) == "planted"
+    rs = synth.make_config("tiny", seed=21)  # the read set of tests/golden/make_golden.py:snp_vs_vcf_inputs
+    fa = str(tmp_path / "ALL.fasta")
+    synth.write_fasta(fa, rs.reads)
+    w = ["-x", 1, "-y", 4, "-z", 1]
+    assert run("build_gesa", "-i", fa, *w).returncode == 0
+    assert run("ebwt2clust", "-i", fa, *w).returncode == 0
+    assert run("clust2snp", "-i", fa, "-n", rs.nreads1, *w).returncode == 0
+    snp = str(tmp_path / "ALL.snp")
+    assert open(snp, "rb").read() == z["0_calls"].tobytes()
+    ref_fa, vcf = str(tmp_path / "ref.fasta"), str(tmp_path / "truth.vcf")
+    open(ref_fa, "wb").write(z["0_fasta"].tobytes())
+    open(vcf, "wb").write(z["0_vcf"].tobytes())
+    r = subprocess.run([os.path.join(BIN, "snp_vs_vcf"), "-v", vcf, "-c", snp, "-f", ref_fa], capture_output=True, timeout=120)
+    assert r.returncode == 0 and r.stdout == z["0_stdout"].tobytes()
+    assert b"TP = 39" in r.stdout and b"FP = 0" in r.stdout
