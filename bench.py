@@ -429,10 +429,18 @@ def main():
         ev1.record(stream)
         sync_all()
         ms = ev0.elapsed_time(ev1)
-        clocks = sampler.stop()
-        launches = ctx.launches - launches0
+        # the timed region lasts a few milliseconds, less than one nvidia-smi sampling period: the same steps continue
+        # untimed (~0.6 s) so that the clock / throttle samples are taken under the load that was timed
         ktimes = {kid: ctx.kernel_time(kid) for kid in KERNELS}
+        launches = ctx.launches - launches0
         ctx.timing(False)
+        n_soak = 1000 if T == 1 else 150  # a fixed count: every rank must run the same number of (collective) steps
+        for _ in range(n_soak):
+            step()
+        sync_all()
+        clocks = sampler.stop()
+        clocks["window"] = f"timed region + {n_soak} more of the same steps, untimed"
+
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
