@@ -22,8 +22,10 @@ __host__ __device__ inline uint64_t plane_quads(uint64_t alloc_r) { return (uint
 // `planes` holds the quads of the positions from -PL_PAD on (the shard's array: lo = local position; a staged window:
 // lo relative to the window's position 0).  GLOBAL: read through the read-only path, else plain (shared memory) loads.
 // A cluster with at most one such code cannot pass find_variants (ref:clust2snp.cpp:402-429): counts[s][c] <= total[c].
+// first: the quad holding position lo if the caller has already fetched it (it overlaps that load with others), else null.
 template <bool GLOBAL>
-__device__ __forceinline__ uint32_t frequent_codes(const uint4* __restrict__ planes, int64_t lo, uint32_t len, uint32_t mcov) {
+__device__ __forceinline__ uint32_t frequent_codes(const uint4* __restrict__ planes, int64_t lo, uint32_t len, uint32_t mcov,
+                                                   const uint4* first = nullptr) {
     const uint64_t b_lo = uint64_t(lo + PL_PAD), b_last = b_lo + len - 1;
     const uint64_t q_lo = b_lo >> 6, q_last = b_last >> 6;
     const unsigned long long m_first = ~0ull << (b_lo & 63), m_last = ~0ull >> (63 - (b_last & 63));
@@ -34,7 +36,7 @@ __device__ __forceinline__ uint32_t frequent_codes(const uint4* __restrict__ pla
         unsigned long long f0 = 0, f1 = 0;  // the first position's code bits, spread over a whole word
         uint32_t others = 0;
         for (uint64_t q = q_lo; q <= q_last; ++q) {
-            const uint4 v = GLOBAL ? __ldg(planes + q) : planes[q];
+            const uint4 v = (first && q == q_lo) ? *first : (GLOBAL ? __ldg(planes + q) : planes[q]);
             const unsigned long long x0 = (uint64_t(v.y) << 32) | v.x, x1 = (uint64_t(v.w) << 32) | v.z;
             unsigned long long mask = q == q_lo ? m_first : ~0ull;
             if (q == q_last) mask &= m_last;

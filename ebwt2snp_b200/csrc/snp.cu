@@ -10,10 +10,8 @@
 //                    frequent codes (true variants, repeats) go on to the exact test.
 //   k_cluster_exact  K3x: per-cluster 2x4 nucleotide histogram (sample = gSA text id < nreads1),
 //                    first-argmax LCP and the find_variants filters        ref:clust2snp.cpp:377-429
-//   k_flag_compact   ordered compaction of a cluster bit mask into an index list (one launch)
 //   k_candidates     K3b: ordered (ballot/popc) selection of the first <= c supporting reads per
 //                    sample and allele pair                                ref:clust2snp.cpp:431-496
-//   k_compact_slots  candidates in reference order
 //   k_events         K4: gSA-driven gather of read contexts, consensus, support, distance()
 //                                                  ref:clust2snp.cpp:541-624, 254-302, include.hpp:334-371
 //
@@ -25,6 +23,9 @@
 // The whole phase is enqueued with device-resident counts and synchronises once (snp_run).
 
 #include <cuda_runtime.h>
+
+#include <algorithm>
+#include <vector>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -136,17 +137,35 @@ cudaError_t launch_bwt_planes(const uint8_t* bwt_a, uint64_t alloc_r, uint4* pla
 
 // One thread per cluster record: total count of each base code by range popcounts on the planes (0.25 B/position,
 // 16-byte loads that neighbouring threads share through L1) + the 10-byte record.
+constexpr int PS_U = 4;  // records per thread in flight: the record loads, then the plane loads they address, overlap
+
 __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
     unsigned long long n_analysed = 0;
-    for (uint64_t c = uint64_t(blockIdx.x) * PS_THREADS + threadIdx.x; c < p.a.m; c += uint64_t(gridDim.x) * PS_THREADS) {
-        const uint64_t c_start = p.a.cl_start[c];
-        const uint32_t c_len = p.a.cl_len[c];
-        if (c_len >= p.min_len && c_len <= p.max_len && c_start - p.a.global_off < p.limit) {
+    const uint64_t stride = uint64_t(gridDim.x) * PS_THREADS * PS_U;
+    for (uint64_t c0 = uint64_t(blockIdx.x) * PS_THREADS * PS_U + threadIdx.x; c0 < p.a.m; c0 += stride) {
+        uint64_t st[PS_U];
+        uint32_t ln[PS_U];
+        uint4 q0[PS_U];  // first plane quad of each record (most clusters need one or two)
+#pragma unroll
+        for (int u = 0; u < PS_U; ++u) {
+            const uint64_t c = c0 + uint64_t(u) * PS_THREADS;
+            st[u] = c < p.a.m ? p.a.cl_start[c] : 0;
+            ln[u] = c < p.a.m ? p.a.cl_len[c] : 0;  // length 0 is never analysed
+        }
+        bool take[PS_U];
+#pragma unroll
+        for (int u = 0; u < PS_U; ++u) {
+            take[u] = ln[u] >= p.min_len && ln[u] <= p.max_len && st[u] - p.a.global_off < p.limit;
+            q0[u] = take[u] ? __ldg(p.a.planes + ((st[u] - p.a.global_off + PL_PAD) >> 6)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < PS_U; ++u) {
+            if (!take[u]) continue;
             ++n_analysed;
-            if (frequent_codes<true>(p.a.planes, int64_t(c_start - p.a.global_off), c_len, p.mcov) >= 2) {
+            if (frequent_codes<true>(p.a.planes, int64_t(st[u] - p.a.global_off), ln[u], p.mcov, &q0[u]) >= 2) {
                 // rare (variants, repeats): plain atomic append, the exact test does not need an order
                 const unsigned long long at = atomicAdd(&p.dev->n_survivors, 1ull);
-                if (at < p.cap_surv) p.survivors[at] = c;
+                if (at < p.cap_surv) p.survivors[at] = c0 + uint64_t(u) * PS_THREADS;
             }
         }
     }
@@ -170,7 +189,8 @@ struct ExactParams {
     uint32_t min_len, max_len; // 2 * mcov_out, max_clust_length (a fused prefilter only knew max_len <= 150)
     uint32_t mcov, k_right;
     uint32_t nr1_lo, nr1_big;
-    uint32_t* flag_words;      // out: bit per cluster = passes the find_variants filters
+    uint64_t* flagged;         // out: clusters that pass the find_variants filters, unordered (dev->n_flagged counts them)
+    uint64_t cap_flagged;
     SnpDev* dev;
 };
 
@@ -212,100 +232,13 @@ __global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
                 f1 |= uint32_t(((acc >> (8 * (b + 4))) & 0xff) >= p.mcov) << b;
             }
             const bool ok = f0 && f1 && __popc(f0) <= 2 && __popc(f1) <= 2 && f0 != f1 && __popc(f0 | f1) <= 3;
-            if (ok) atomicOr(&p.flag_words[ci >> 5], 1u << (ci & 31));
+            if (ok) {
+                const unsigned long long at = atomicAdd(&p.dev->n_flagged, 1ull);
+                if (at < p.cap_flagged) p.flagged[at] = ci;  // the host compares the count with the capacity and retries
+            }
         }
     }
     if (__any_sync(__activemask(), saw_n) && saw_n) atomicOr(&p.dev->saw_n, 1ull);
-}
-
-// ---------------------------------------------------------------------------------------------
-// ordered compaction of flagged clusters (bitmask -> ascending index list)
-// ---------------------------------------------------------------------------------------------
-constexpr int FC_THREADS = 256;
-constexpr int FC_WORDS = 4096;  // words per block
-
-// One launch: every block counts the set bits of its FC_WORDS words, publishes the count, sums the counts of the
-// blocks before it (they do not depend on anything, so there is no chain) and writes the indices of its set bits in
-// ascending order.  Block ids come from a ticket, so a block only ever waits for blocks that are already running.
-// sync[0] = ticket, sync[1 + b] = VALID | count of block b   (zeroed by the caller)
-constexpr unsigned long long FC_VALID = 1ull << 63;
-
-__global__ void __launch_bounds__(FC_THREADS) k_flag_compact(const uint32_t* __restrict__ words, uint64_t n_words,
-                                                             unsigned long long* sync, uint64_t* __restrict__ out_idx,
-                                                             uint64_t cap, unsigned long long* out_count) {
-    __shared__ unsigned long long s_bid, s_base;
-    __shared__ uint32_t s_w[FC_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        s_bid = atomicAdd(&sync[0], 1ull);
-        s_base = 0;
-    }
-    __syncthreads();
-    const uint64_t bid = s_bid, w0 = bid * FC_WORDS;
-    uint32_t wv[FC_WORDS / FC_THREADS];
-    uint32_t c = 0;
-#pragma unroll
-    for (int r = 0; r < FC_WORDS / FC_THREADS; ++r) {
-        const uint64_t wi = w0 + uint64_t(r) * FC_THREADS + threadIdx.x;
-        wv[r] = wi < n_words ? words[wi] : 0u;
-        c += __popc(wv[r]);
-    }
-    c = __reduce_add_sync(FULL, c);
-    if (lane == 0) s_w[warp] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int i = 0; i < FC_THREADS / 32; ++i) tot += s_w[i];
-        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&sync[1 + bid]), "l"(FC_VALID | tot) : "memory");
-    }
-    // counts of the blocks before mine
-    unsigned long long part = 0;
-    for (uint64_t i = threadIdx.x; i < bid; i += FC_THREADS) {
-        unsigned long long v;
-        do {
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&sync[1 + i]) : "memory");
-        } while (!(v & FC_VALID));
-        part += v & ~FC_VALID;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
-    if (lane == 0 && part) atomicAdd(&s_base, part);
-    __syncthreads();
-    uint64_t base = s_base;
-    if (bid == gridDim.x - 1 && threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int i = 0; i < FC_THREADS / 32; ++i) tot += s_w[i];
-        *out_count = base + tot;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < FC_WORDS / FC_THREADS; ++r) {
-        const uint64_t wi = w0 + uint64_t(r) * FC_THREADS + threadIdx.x;
-        uint32_t w = wv[r];
-        const uint32_t cw = __popc(w);
-        uint32_t inc = cw;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(FULL, inc, d);
-            if (lane >= d) inc += o;
-        }
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        uint32_t off = inc - cw, tot = 0;
-        for (int i = 0; i < FC_THREADS / 32; ++i) {
-            if (i < warp) off += s_w[i];
-            tot += s_w[i];
-        }
-        uint64_t o = base + off;
-        while (w) {
-            const int b = __ffs(w) - 1;
-            w &= w - 1;
-            if (o < cap) out_idx[o] = wi * 32 + b;  // the caller compares *out_count with cap and retries if it was too small
-            ++o;
-        }
-        base += tot;
-        __syncthreads();
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -320,7 +253,8 @@ struct CandParams {
     CandSlot* slots;       // 4 per flagged cluster
     uint32_t* slot_text;   // [slot][2][cap]
     uint32_t* slot_pos;    // [slot][2][cap]
-    uint32_t* valid_words; // bit per slot (zeroed by the caller)
+    uint64_t* cand;        // out: valid slots, unordered (dev->n_slots_valid counts them)
+    SnpDev* dev;
     uint64_t cap_flagged;  // capacity of the flagged list / slot arrays
 };
 
@@ -405,60 +339,18 @@ __global__ void __launch_bounds__(128) k_candidates(CandParams p) {
             }
             if (lane == 0) {
                 p.slots[slot] = hdr;
-                if (hdr.valid) atomicOr(&p.valid_words[slot >> 5], 1u << (slot & 31));
+                if (hdr.valid) p.cand[atomicAdd(&p.dev->n_slots_valid, 1ull)] = slot;  // at most 4 per flagged cluster: fits
             }
         }
     }
     }
 }
 
-// valid slots, in order: ordered compaction of the slot bit mask (single block: a few thousand words)
-__global__ void __launch_bounds__(1024) k_compact_slots(const uint32_t* __restrict__ valid_words, uint64_t n_words,
-                                                        uint64_t* __restrict__ cand, SnpDev* dev) {
-    __shared__ uint32_t s_w[32];
-    __shared__ uint64_t s_base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_base = 0;
-    __syncthreads();
-    {   // only the slots of the clusters K3x flagged can be valid: 4 slots per flagged cluster
-        const uint64_t used = (dev->n_flagged * 4 + 31) / 32;
-        if (used < n_words) n_words = used;
-    }
-    for (uint64_t i0 = 0; i0 < n_words; i0 += 1024) {
-        const uint64_t wi = i0 + threadIdx.x;
-        uint32_t w = wi < n_words ? valid_words[wi] : 0u;
-        const uint32_t c = __popc(w);
-        uint32_t inc = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(FULL, inc, d);
-            if (lane >= d) inc += o;
-        }
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        uint32_t off = inc - c, tot = 0;
-        for (int q = 0; q < 32; ++q) {
-            if (q < warp) off += s_w[q];
-            tot += s_w[q];
-        }
-        uint64_t o = s_base + off;
-        while (w) {
-            const int b = __ffs(w) - 1;
-            w &= w - 1;
-            cand[o++] = wi * 32 + b;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_base += tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) dev->n_slots_valid = s_base;
-}
-
 // ---------------------------------------------------------------------------------------------
 // K4: contexts, consensus, support, distance
 // ---------------------------------------------------------------------------------------------
 struct PackedEventHdr {  // followed by left0[k_left] left1[k_left] right[k_right]
-    int32_t D, gap, supp0, supp1, right_len, flags;  // flags bit0 = variant (supp0>0 && supp1>0), bit1 = keep
+    int32_t D, gap, supp0, supp1, right_len, flags;  // flags bit0 = variant (supp0>0 && supp1>0), bit1 = keep, bits 8-9 = allele pair of the cluster
     uint64_t cluster_start;
 };
 
@@ -667,7 +559,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
         oh->supp0 = supp[0];
         oh->supp1 = supp[1];
         oh->right_len = rl;
-        oh->flags = (variant ? 1 : 0) | ((variant && D <= p.max_snvs) ? 2 : 0);
+        oh->flags = (variant ? 1 : 0) | ((variant && D <= p.max_snvs) ? 2 : 0) | int32_t((slot & 3) << 8);  // bits 8-9: allele pair, for the output order
         oh->cluster_start = hdr.cluster_start;
         if (variant) atomicAdd(&p.dev->n_variants, 1ull);
         if (variant && D <= p.max_snvs) atomicAdd(&p.dev->n_events, 1ull);
@@ -686,13 +578,10 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
 // ---------------------------------------------------------------------------------------------
 struct SnpWork {
     uint8_t* zero_blk = nullptr; size_t zero_cap = 0;  // everything a pass needs zeroed, in one block: one memset
-    unsigned long long* fc_sync = nullptr;              // (views into zero_blk)
-    uint32_t* flag_words2 = nullptr;
     uint64_t* survivors = nullptr; size_t survivors_cap = 0;
     uint64_t* flagged = nullptr; size_t flagged_cap = 0;
     CandSlot* slots = nullptr; size_t slots_cap = 0;
     uint32_t* slot_text = nullptr; uint32_t* slot_pos = nullptr; size_t slot_list_cap = 0;
-    uint32_t* valid_words = nullptr;
     uint64_t* cand = nullptr; size_t cand_cap = 0;
     SnpDev* dev = nullptr;
     SnpDev* h_dev = nullptr;                                // pinned staging of the counters
@@ -743,8 +632,6 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     const uint32_t nr1_big = p.nr_reads1 > 0xffffffffull ? 1u : 0u;
     const uint32_t nr1_lo = nr1_big ? 0xffffffffu : uint32_t(p.nr_reads1);
     const uint32_t num_tiles = uint32_t((a.n_local + PS_T - 1) / PS_T);
-    const uint64_t n_words = (a.m + 31) / 32;
-    const uint32_t n_fblocks = uint32_t((n_words + FC_WORDS - 1) / FC_WORDS);
     const uint32_t cap = uint32_t(p.consensus_reads < MAX_C_LEN ? p.consensus_reads : MAX_C_LEN);
     w->stride = uint32_t((sizeof(PackedEventHdr) + 2 * size_t(p.k_left) + size_t(p.k_right) + 15) & ~size_t(15));
 
@@ -761,7 +648,6 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
         const uint64_t cap_surv = w->want_survivors < a.m ? w->want_survivors : a.m;
         const uint64_t cap_flag = w->want_flagged < cap_surv ? w->want_flagged : cap_surv;
         const uint64_t n_slots = cap_flag * 4;
-        const uint64_t n_vwords = (n_slots + 31) / 32;
         CK(ensure(w->survivors, w->survivors_cap, size_t(cap_surv)));
         CK(ensure(w->flagged, w->flagged_cap, size_t(cap_flag)));
         CK(ensure(w->slots, w->slots_cap, size_t(n_slots)));
@@ -774,17 +660,9 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_pos), n * 4));
             w->slot_list_cap = n;
         }
-        {   // SnpDev | fc_sync | flag_words2 | valid_words, 16-byte aligned pieces of one zeroed block
-            auto up16 = [](size_t v) { return (v + 15) & ~size_t(15); };
-            const size_t o_sync = up16(sizeof(SnpDev)), o_flag = o_sync + up16((size_t(n_fblocks) + 1) * 8);
-            const size_t o_valid = o_flag + up16(size_t(n_words) * 4), total = o_valid + up16(size_t(n_vwords) * 4);
-            CK(ensure(w->zero_blk, w->zero_cap, total));
-            w->dev = reinterpret_cast<SnpDev*>(w->zero_blk);
-            w->fc_sync = reinterpret_cast<unsigned long long*>(w->zero_blk + o_sync);
-            w->flag_words2 = reinterpret_cast<uint32_t*>(w->zero_blk + o_flag);
-            w->valid_words = reinterpret_cast<uint32_t*>(w->zero_blk + o_valid);
-            CK(cudaMemsetAsync(w->zero_blk, 0, total, stream));
-        }
+        CK(ensure(w->zero_blk, w->zero_cap, sizeof(SnpDev)));  // the device counters: the one thing a pass needs zeroed
+        w->dev = reinterpret_cast<SnpDev*>(w->zero_blk);
+        CK(cudaMemsetAsync(w->zero_blk, 0, sizeof(SnpDev), stream));
         CK(ensure(w->cand, w->cand_cap, size_t(n_slots)));
         if (size_t(n_slots) * w->stride > w->h_events_cap) {
             cudaFreeHost(w->h_events);
@@ -807,8 +685,8 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             sp.survivors = w->survivors;
             sp.cap_surv = cap_surv;
             sp.dev = w->dev;
-            uint64_t grid = (a.m + PS_THREADS - 1) / PS_THREADS;
-            if (grid > uint64_t(sm_count) * 32) grid = uint64_t(sm_count) * 32;
+            uint64_t grid = (a.m + PS_THREADS * PS_U - 1) / (PS_THREADS * PS_U);
+            if (grid > uint64_t(sm_count) * 16) grid = uint64_t(sm_count) * 16;
             if (timer) timer->begin(E2S_KERNEL_SCAN, stream);
             k_code_scan<<<unsigned(grid), PS_THREADS, 0, stream>>>(sp);
             if (timer) timer->end(stream);
@@ -828,7 +706,8 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             ep.k_right = uint32_t(p.k_right);
             ep.nr1_lo = nr1_lo;
             ep.nr1_big = nr1_big;
-            ep.flag_words = w->flag_words2;
+            ep.flagged = w->flagged;
+            ep.cap_flagged = cap_flag;
             ep.dev = w->dev;
             if (timer) timer->begin(E2S_KERNEL_EXACT, stream);
             k_cluster_exact<<<unsigned(sm_count) * 8, EX_THREADS, 0, stream>>>(ep);
@@ -836,11 +715,9 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             CK(cudaGetLastError());
             ++*launches;
         }
-        // clusters that pass the filters, in eBWT order (the candidate order of the reference)
-        k_flag_compact<<<n_fblocks, FC_THREADS, 0, stream>>>(w->flag_words2, n_words, w->fc_sync, w->flagged, cap_flag,
-                                                            &w->dev->n_flagged);
-        CK(cudaGetLastError());
-        ++*launches;
+        // Flagged clusters, their candidate slots and the events come out in whatever order the atomics give: the
+        // reference's order (eBWT position, then allele pair) is restored from (cluster_start, pair) when the events are
+        // fetched (snp_fetch_events), so the step needs no ordered compaction.
         {
             CandParams cp;
             cp.a = a;
@@ -856,12 +733,11 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             cp.slots = w->slots;
             cp.slot_text = w->slot_text;
             cp.slot_pos = w->slot_pos;
-            cp.valid_words = w->valid_words;
+            cp.cand = w->cand;
+            cp.dev = w->dev;
             uint64_t blocks = (cap_flag + 3) / 4;
             if (blocks > uint64_t(sm_count) * 16) blocks = uint64_t(sm_count) * 16;
             k_candidates<<<unsigned(blocks), 128, 0, stream>>>(cp);
-            CK(cudaGetLastError());
-            k_compact_slots<<<1, 1024, 0, stream>>>(w->valid_words, n_vwords, w->cand, w->dev);
             CK(cudaGetLastError());
             EventParams ep;
             ep.slots = w->slots;
@@ -885,7 +761,7 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
             if (eblocks > uint64_t(sm_count) * 16) eblocks = uint64_t(sm_count) * 16;
             k_events<<<unsigned(eblocks), EV_WARPS * 32, 0, stream>>>(ep);
             CK(cudaGetLastError());
-            *launches += 3;
+            *launches += 2;
         }
         CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));  // the only synchronisation of the pass
@@ -910,16 +786,24 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     return cudaSuccess;
 }
 
-// expands the host copy of the packed candidates, keeping the variants (supp0>0 && supp1>0) in order
+// expands the host copy of the packed candidates, keeping the variants (supp0>0 && supp1>0), in the reference's order:
+// clusters by eBWT position, the allele pairs of a cluster in the nested order of ref:clust2snp.cpp:431-435
 cudaError_t snp_fetch_events(SnpWork* w, e2s_event* host, uint64_t cap, uint64_t* n, cudaStream_t) {
     *n = 0;
     if (w->n_cand == 0) return cudaSuccess;
     const uint8_t* tmp = w->h_events;
-    uint64_t k = 0;
+    struct Key { uint64_t start; uint32_t pair; uint64_t c; };
+    std::vector<Key> order;
+    order.reserve(size_t(w->n_cand));
     for (uint64_t c = 0; c < w->n_cand; ++c) {
-        const uint8_t* o = tmp + c * w->stride;
+        const PackedEventHdr* h = reinterpret_cast<const PackedEventHdr*>(tmp + c * w->stride);
+        if (h->flags & 1) order.push_back(Key{h->cluster_start, uint32_t(h->flags >> 8) & 3u, c});
+    }
+    std::sort(order.begin(), order.end(), [](const Key& a, const Key& b) { return a.start != b.start ? a.start < b.start : a.pair < b.pair; });
+    uint64_t k = 0;
+    for (const Key& key : order) {
+        const uint8_t* o = tmp + key.c * w->stride;
         const PackedEventHdr* h = reinterpret_cast<const PackedEventHdr*>(o);
-        if (!(h->flags & 1)) continue;
         if (host && k < cap) {
             e2s_event* ev = &host[k];
             memset(ev, 0, sizeof *ev);
