@@ -148,14 +148,65 @@ def h2d_probe(torch, dev, mb=1024):
 # data
 # --------------------------------------------------------------------------------------------
 
-def make_dataset(workload, seed, scale, device):
+def make_dataset(workload, seed, scale, device, builder="torch"):
+    """builder: "torch" = synth.build_egsa (plain torch sorts, the independent check of the library's builder, needs
+    ~65 B of device memory per suffix); "native" = the library's e2s_build_egsa_dev (37 B per suffix incl. its outputs:
+    what makes a C3-size index, 3.9e9 suffixes, fit one GPU)."""
+    import torch
     from ebwt2snp_b200 import synth
     t0 = time.time()
     rs = synth.make_config(workload, seed=seed, scale=scale)
-    eg = synth.build_egsa(rs.reads, device=device)
-    log(f"[data] {workload} scale={scale} seed={seed}: reads={rs.reads.shape} n={eg['n']} built on {device} "
-        f"in {time.time() - t0:.1f}s")
+    t1 = time.time()
+    if builder == "native":
+        from ebwt2snp_b200 import api
+        torch.cuda.empty_cache()
+        bctx = api.Context(torch.device(device).index or 0)
+        try:
+            eg = bctx.build_egsa(rs.reads)
+        finally:
+            bctx.close()
+    else:
+        eg = synth.build_egsa(rs.reads, device=device)
+    log(f"[data] {workload} scale={scale} seed={seed}: reads={rs.reads.shape} in {t1 - t0:.1f}s, n={eg['n']} built on {device} "
+        f"by the {builder} builder in {time.time() - t1:.1f}s")
     return rs, eg
+
+
+def check_egsa_sample(rs, eg, samples=200000, seed=7):
+    """Size-independent property check of an index nobody else can build at this size: for sampled i, record i-1 sorts
+    before record i (`$` < A < C < G < T, equal suffixes by read id), lcp[i] is their common prefix (capped at the shorter
+    suffix) and bwt / text / suff agree with the reads.  Host-side numpy on the sample; -> (ok, records checked)."""
+    import torch
+    n, L = int(eg["n"]), int(eg["L"])
+    rng = np.random.default_rng(seed)
+    idx = np.unique(np.concatenate([rng.integers(1, n, size=samples), np.arange(1, min(n, 2000)), np.arange(max(1, n - 2000), n)]))
+    it = torch.from_numpy(idx).to(eg["text"].device)
+
+    def pick(k, off):
+        return eg[k][it - off].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+
+    t1, s1, t0, s0, lcp = pick("text", 0), pick("suff", 0), pick("text", 1), pick("suff", 1), pick("lcp", 0)
+    bwt = eg["bwt"][it].cpu().numpy()
+    reads = rs.reads
+    cols = np.arange(L + 1)[None, :]
+
+    def suffixes(t, sf):  # suffix strings, 0-padded (0 = the terminator, smaller than every base)
+        out = np.zeros((len(t), L + 1), dtype=np.uint8)
+        pos = sf[:, None] + cols
+        valid = pos < L
+        out[valid] = reads[np.broadcast_to(t[:, None], pos.shape)[valid], pos[valid]]
+        return out
+
+    a, b = suffixes(t0, s0), suffixes(t1, s1)
+    diff = a != b
+    differs = diff.any(axis=1)
+    first = np.where(differs, diff.argmax(axis=1), L + 1)
+    ok = bool(np.array_equal(np.minimum(first, np.minimum(L - s0, L - s1)), lcp))
+    rows, at = np.arange(len(idx)), np.minimum(first, L)
+    ok &= bool(np.where(differs, a[rows, at] < b[rows, at], t0 < t1).all())
+    ok &= bool(np.array_equal(np.where(s1 > 0, reads[t1, np.maximum(s1, 1) - 1], ord("$")).astype(np.uint8), bwt))
+    ok &= bool((s1 <= L).all() and (t1 < reads.shape[0]).all())
+    return ok, len(idx)
 
 
 def aos_records_pinned(eg, torch):
@@ -301,6 +352,9 @@ def main():
     ap.add_argument("--cpu-positions", type=float, default=3e7, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--builder", default="auto", choices=["auto", "torch", "native"],
+                    help="who builds the workload's index (data preparation): auto = torch for C1/C2 (and the library's builder is checked "
+                         "against it), the library's own builder for C3-size workloads")
     ap.add_argument("--no-egsa-build", action="store_true", help="skip timing the library's EGSA builder on the workload's reads (N = 1 only)")
     ap.add_argument("--tiles", type=int, default=1,
                     help="resident-only study: tile the workload T times on the GPU (read ids shifted; every tile starts with "
@@ -327,7 +381,19 @@ def main():
     warmup = max(args.warmup, 3)
 
     # ---- data: every rank owns one C2-size tile of a global eBWT of world * n positions (weak scaling) ----
-    rs, eg = make_dataset(args.workload, args.seed + rank, args.scale, dev)
+    big = args.workload not in ("C1", "C2") and args.scale >= 0.5  # beyond what the torch builder fits on one GPU
+    builder = args.builder if args.builder != "auto" else ("native" if big else "torch")
+    rs, eg = make_dataset(args.workload, args.seed + rank, args.scale, dev, builder=builder)
+    index_check = None
+    if builder == "native":
+        okc, nchk = check_egsa_sample(rs, eg)
+        index_check = {"builder": "e2s_build_egsa_dev", "sampled_records": nchk, "order_lcp_bwt_consistent": okc}
+        log(f"[data] index property check on {nchk} sampled records: {okc}")
+        if not okc:
+            raise SystemExit("the index built by the library fails the order / LCP / BWT property check")
+        args.no_egsa_build = True
+    if big:
+        args.no_e2e = True  # 13 B/position of pinned host records: not at this size
     # ---- EGSA construction on the GPU (data preparation, outside the timed step): the library's
     # builder on the same reads, timed, and compared element by element with the arrays the step below runs on ----
     egsa_build = None
@@ -557,7 +623,7 @@ def main():
                        "l2": "inputs (13 B/position, >= 7 GB per GPU at C2) exceed the 126 MB L2; no flush needed",
                        "resident_layout": f"SoA: lcp u32 + text u32 + suff u32 + bwt u8 + 2-bit base-code planes of the BWT (built at seal); K1 streams a {'one-byte LCP copy built at seal (every LCP value <= 127)' if lcp_bytes == 1 else 'the 4-byte LCP'}",
                        "scale": args.scale, "tiles": T, "exchange_us": exchange_us},
-            "clocks": clocks, "e2e": e2e, "egsa_build": egsa_build, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "egsa_build": egsa_build, "index_check": index_check, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "results": {"n_written": int(mg.total_written), "n_clust_out": int(mg.n_clust_out),
                         "max_clust_length": int(st.max_clust_length), "n_analysed_rank0": int(cnt.n_analysed),
                         "n_candidates_rank0": int(cnt.n_candidates), "n_events_rank0": int(cnt.n_events),
