@@ -352,6 +352,9 @@ def main():
     ap.add_argument("--cpu-positions", type=float, default=3e7, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one workload per GPU (the default, what the driver's scaling run uses); strong = one workload cut "
+                         "into N contiguous eBWT ranges (BASELINE config C5 with --workload C3)")
     ap.add_argument("--builder", default="auto", choices=["auto", "torch", "native"],
                     help="who builds the workload's index (data preparation): auto = torch for C1/C2 (and the library's builder is checked "
                          "against it), the library's own builder for C3-size workloads")
@@ -383,7 +386,11 @@ def main():
     # ---- data: every rank owns one C2-size tile of a global eBWT of world * n positions (weak scaling) ----
     big = args.workload not in ("C1", "C2") and args.scale >= 0.5  # beyond what the torch builder fits on one GPU
     builder = args.builder if args.builder != "auto" else ("native" if big else "torch")
-    rs, eg = make_dataset(args.workload, args.seed + rank, args.scale, dev, builder=builder)
+    # weak scaling (default): every rank owns its own workload-size tile of a global eBWT of world * n positions;
+    # strong scaling (--scaling strong; BASELINE config C5): ONE workload, every rank builds the same index and keeps its
+    # contiguous range of it
+    strong = args.scaling == "strong" and world > 1
+    rs, eg = make_dataset(args.workload, args.seed if strong else args.seed + rank, args.scale, dev, builder=builder)
     index_check = None
     if builder == "native":
         okc, nchk = check_egsa_sample(rs, eg)
@@ -423,7 +430,13 @@ def main():
     n_tile = int(eg["n"])
     n = n_tile * T
     n_all = [n]
-    if world > 1:
+    if strong:
+        if T > 1:
+            raise SystemExit("--tiles and --scaling strong do not combine")
+        cuts = sharding.shard_cuts(n_tile, world)
+        n_all = [cuts[g + 1] - cuts[g] for g in range(world)]
+        n = n_all[rank]
+    elif world > 1:
         t = torch.tensor([n], dtype=torch.int64, device=dev)
         g = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(g, t)
@@ -434,10 +447,15 @@ def main():
     ctx = api.Context(local, stream.cuda_stream)
     sh = ctx.shard(n, global_off, n_global)
     R0 = rs.reads.shape[0]
-    for t in range(T):
-        sh.load_soa(eg["lcp"], eg["text"] + t * R0 if t else eg["text"], eg["suff"], eg["bwt"], first=global_off + t * n_tile, device=True)
-    # halo exchange over NCCL: my left neighbour's last 2 records, my right neighbour's first 151
-    left, right = sharding.exchange_halo(eg["lcp"], eg["text"], eg["suff"], eg["bwt"], dev)
+    if strong:  # my range of the one index, halos included (2 left, 151 right): every rank holds the whole index here
+        a, b = max(0, global_off - sharding.HALO_L), min(n_global, global_off + n + sharding.HALO_R)
+        sh.load_soa(eg["lcp"][a:b], eg["text"][a:b], eg["suff"][a:b], eg["bwt"][a:b], first=a, device=True)
+        left = right = None
+    else:
+        for t in range(T):
+            sh.load_soa(eg["lcp"], eg["text"] + t * R0 if t else eg["text"], eg["suff"], eg["bwt"], first=global_off + t * n_tile, device=True)
+        # halo exchange over NCCL: my left neighbour's last 2 records, my right neighbour's first 151
+        left, right = sharding.exchange_halo(eg["lcp"], eg["text"], eg["suff"], eg["bwt"], dev)
     if left is not None:
         sh.load_soa(left["lcp"], left["text"], left["suff"], left["bwt"], first=global_off - sharding.HALO_L, device=True)
     if right is not None:
@@ -616,7 +634,7 @@ def main():
         c_ratio = m_own / n
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(args), "positions_per_gpu": n, "positions_total": n_global,
                        "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; " + ("one ncclAllGather of the shard summaries per step, issued by the library on its stream (e2s_pipeline_sharded)" if comm is not None else "NCCL all-gather of shard summaries"),
