@@ -66,7 +66,7 @@ uint64_t e2s_ctx_launch_count(const e2s_ctx *ctx);
  * the stream, returns the time and launch count accumulated since the last call and resets them. */
 #define E2S_KERNEL_FLAGS 0 /* K1: LCP boundary stencil -> START/END bit masks */
 #define E2S_KERNEL_EMIT 1  /* K2: look-back scan over the masks + record compaction */
-#define E2S_KERNEL_SCAN 2  /* K3a: per-cluster base-code prefilter over the BWT */
+#define E2S_KERNEL_SCAN 2  /* K3a: per-cluster base-code prefilter on the resident bit planes of the BWT */
 #define E2S_KERNEL_EXACT 3 /* K3x: exact 2x4 histogram / filters of the surviving clusters */
 #define E2S_KERNEL_COUNT 4
 int e2s_ctx_timing(e2s_ctx *ctx, int enable);

@@ -397,8 +397,8 @@ def test_fused_prefilter_equals_two_phase(ctx, name, seed, monkeypatch):
 
 @pytest.mark.parametrize("fused", [False, True])
 def test_non_acgt_bwt_bytes_use_exact_planes(ctx, fused):
-    """bytes outside the seal-time 'simple alphabet' ('#', 0xff, 'x'): K3a / fused K2 must fall back to per-byte equality
-    tests; every such byte counts as 'A' (ref:include.hpp:277)"""
+    """bytes that are neither ACGT nor acgt ('#', 0xff, 'x', 'E') in the BWT: the resident base-code planes built at seal
+    (k_bwt_planes) must give every such byte the code of 'A' (ref:include.hpp:277), for K3a and for the fused K2 alike"""
     rs, e = H.dataset("small", 3)
     n = e["n"]
     rng = np.random.default_rng(12)
