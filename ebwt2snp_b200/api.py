@@ -86,6 +86,7 @@ SYMBOLS = [
     "e2s_statistics", "e2s_statistics_finish", "e2s_exchange_finish", "e2s_snp_default_params", "e2s_find_events", "e2s_events_fetch",
     "e2s_events_format", "e2s_free", "e2s_pipeline_resident", "e2s_pipeline_host",
     "e2s_comm_unique_id", "e2s_comm_create", "e2s_comm_destroy", "e2s_pipeline_sharded",
+    "e2s_exchange_row_words", "e2s_exchange_rows_finish",
 ]
 
 _lib = None
@@ -148,6 +149,10 @@ def load_library():
     lib.e2s_free.argtypes = [C.c_void_p]
     lib.e2s_pipeline_resident.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(SnpParams), C.POINTER(PipelineResult)]
     lib.e2s_comm_unique_id.argtypes = [C.c_void_p]
+    lib.e2s_exchange_row_words.restype = C.c_uint64
+    lib.e2s_exchange_row_words.argtypes = []
+    lib.e2s_exchange_rows_finish.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_int32, C.c_int, C.c_double,
+                                             C.POINTER(ClusterMerged), C.POINTER(Stats)]
     lib.e2s_comm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.e2s_comm_destroy.argtypes = [C.c_void_p]
     lib.e2s_comm_destroy.restype = None
@@ -202,6 +207,29 @@ def exchange_finish(sum_rows, stat_rows, my, mcov_out=5, pval=0.99):
     rc = lib.e2s_exchange_finish(_ptr(sum_rows) if not isinstance(sum_rows, C.Array) else C.cast(sum_rows, C.c_void_p),
                                  _ptr(stat_rows) if not isinstance(stat_rows, C.Array) else C.cast(stat_rows, C.c_void_p),
                                  n, my, int(mcov_out), float(pval), C.byref(mg), C.byref(tot))
+    if rc:
+        raise E2SError(rc, lib.e2s_last_error(None).decode())
+    return mg, tot
+
+
+class ClusterDev(C.Structure):
+    """mirror of the scan's device accumulators (csrc/internal.h) = the leading words of one exchange row"""
+    _fields_ = [(n, C.c_uint64) for n in ("n_end", "n_written", "head_end", "any_event", "open_start", "end_nm2_start", "overflow",
+                                          "ticket", "n_pf", "last_rec", "tail_lcp_nm2", "tail_lcp_nm1", "tail_bwt_nm1", "n_bases")] + \
+               [("hist", C.c_uint64 * HIST_BINS)]
+
+
+def exchange_row_words() -> int:
+    return int(load_library().e2s_exchange_row_words())
+
+
+def exchange_rows_finish(rows, my, n_global, k, min_len, mcov_out=5, pval=0.99):
+    """e2s_exchange_rows_finish over the gathered (world, exchange_row_words()) uint64 rows -> (ClusterMerged, global Stats)"""
+    lib = load_library()
+    rows = np.ascontiguousarray(rows, dtype=np.uint64)
+    mg, tot = ClusterMerged(), Stats()
+    rc = lib.e2s_exchange_rows_finish(_ptr(rows), rows.shape[0], int(my), int(n_global), int(k), int(min_len), int(mcov_out),
+                                      float(pval), C.byref(mg), C.byref(tot))
     if rc:
         raise E2SError(rc, lib.e2s_last_error(None).decode())
     return mg, tot

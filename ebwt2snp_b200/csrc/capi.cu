@@ -1375,6 +1375,32 @@ void e2s_comm_destroy(e2s_comm* cm) {
     delete cm;
 }
 
+// Host-only: what every rank does with the all-gathered exchange rows (one per shard: the scan's device accumulators
+// + the shard's range) -- turn them into summaries and own-record statistics, then e2s_exchange_finish.
+uint64_t e2s_exchange_row_words(void) { return XR_WORDS; }
+
+int e2s_exchange_rows_finish(const uint64_t* rows, int n_shards, int my, uint64_t n_global, uint32_t k, int32_t min_len, int mcov_out,
+                             double pval, e2s_cluster_merged* mine, e2s_stats* total) {
+    if (!rows || !mine || !total || n_shards < 1 || my < 0 || my >= n_shards)
+        return fail(nullptr, E2S_ERR_ARG, "e2s_exchange_rows_finish: bad argument");
+    const size_t ns = static_cast<size_t>(n_shards);
+    std::vector<e2s_cluster_summary> sums(ns);
+    std::vector<e2s_stats> own(ns);
+    for (int g = 0; g < n_shards; ++g) {
+        const uint64_t* row = rows + size_t(g) * XR_WORDS;
+        summary_from_row(row, n_global, k, min_len, &sums[size_t(g)]);
+        ClusterDev h;
+        memcpy(&h, row, sizeof h);
+        e2s_stats& o = own[size_t(g)];
+        memset(&o, 0, sizeof o);
+        for (int i = 0; i < E2S_HIST_BINS; ++i) o.hist[i] = h.hist[i];
+        o.n_bases = h.n_bases;
+        o.n_clust = h.n_written;
+        o.last_len = h.last_rec & 0xffff;
+    }
+    return e2s_exchange_finish(sums.data(), own.data(), n_shards, my, mcov_out, pval, mine, total);
+}
+
 // The sharded step in one call: K1, K2, ONE all-gather of the scan accumulators (summary + own length histogram) on
 // the stream, host merge of all shards + statistics, K3/K4 on local data.  Two host synchronisations, like the
 // single-shard e2s_pipeline_resident.
@@ -1389,20 +1415,7 @@ int e2s_pipeline_sharded(e2s_shard* s, e2s_comm* cm, uint32_t k, int32_t min_len
     int rc = cluster_run_impl(s, k, min_len, &own_sum, cm);
     s->pf_arm = arm_before;
     if (rc) return rc;
-    std::vector<e2s_cluster_summary> sums(size_t(cm->world));
-    std::vector<e2s_stats> own(size_t(cm->world));
-    for (int g = 0; g < cm->world; ++g) {
-        const uint64_t* row = cm->h_recv + size_t(g) * XR_WORDS;
-        summary_from_row(row, s->n_global, k, min_len, &sums[size_t(g)]);
-        const ClusterDev& h = *reinterpret_cast<const ClusterDev*>(row);
-        e2s_stats& o = own[size_t(g)];
-        memset(&o, 0, sizeof o);
-        for (int i = 0; i < E2S_HIST_BINS; ++i) o.hist[i] = h.hist[i];
-        o.n_bases = h.n_bases;
-        o.n_clust = h.n_written;
-        o.last_len = h.last_rec & 0xffff;
-    }
-    if ((rc = e2s_exchange_finish(sums.data(), own.data(), cm->world, cm->rank, p->mcov_out, p->pval, mg, st))) {
+    if ((rc = e2s_exchange_rows_finish(cm->h_recv, cm->world, cm->rank, s->n_global, k, min_len, p->mcov_out, p->pval, mg, st))) {
         c->err = g_err;
         return rc;
     }

@@ -280,6 +280,13 @@ int e2s_pipeline_resident(e2s_shard *sh, uint32_t k, int32_t min_len, const e2s_
  * e2s_pipeline_sharded = e2s_pipeline_resident for a shard of a sharded eBWT: K1 + K2, ONE ncclAllGather of every shard's
  * scan accumulators on the context's stream, e2s_exchange_finish on the host (identical on all ranks), K3/K4 on local
  * data.  Collective: every rank of the communicator must call it. */
+/* Host-only (no CUDA), exposed for tests and for callers that move the rows themselves: e2s_exchange_row_words() u64 words per
+ * shard = the scan's device accumulators (ClusterDev: counters, open-cluster state, tail values, length histogram of the
+ * shard's own records) followed by n_local, global_off, lcp_bytes, 0.  e2s_exchange_rows_finish turns the gathered rows
+ * into summaries + own-record statistics and runs e2s_exchange_finish. */
+uint64_t e2s_exchange_row_words(void);
+int e2s_exchange_rows_finish(const uint64_t *rows, int n_shards, int my, uint64_t n_global, uint32_t k, int32_t min_len,
+                             int mcov_out, double pval, e2s_cluster_merged *mine, e2s_stats *total);
 typedef struct e2s_comm e2s_comm;
 int e2s_comm_unique_id(uint8_t *id128);
 int e2s_comm_create(e2s_ctx *ctx, const uint8_t *id128, int rank, int world, e2s_comm **out);

@@ -113,3 +113,52 @@ def test_statistics_finish(built):
         assert list(st.hist) == list(ost.hist)
         assert (st.n_clust, st.n_bases, st.max_len, st.max_clust_length) == (
             ost.n_clust, ost.n_bases, ost.max_len, ost.max_clust_length)
+
+
+def test_exchange_rows_equal_exchange_finish(built):
+    """the library-side exchange (e2s_pipeline_sharded) hands every rank the raw rows of all shards -- the scan's device
+    accumulators + the shard's range; e2s_exchange_rows_finish must turn them into the same merged view and global
+    statistics as e2s_exchange_finish gets from summaries + own-record statistics (the torch.distributed path)"""
+    import ctypes as C
+    W = api.exchange_row_words()
+    assert W == C.sizeof(api.ClusterDev) // 8 + 4
+    rng = np.random.default_rng(31)
+    for it in range(60):
+        n = int(rng.integers(200, 4000))
+        k = int(rng.choice([2, 5, 16]))
+        m = int(rng.choice([1, 2, 3]))
+        lcp = H.random_lcp(rng, n, k, it % 5)
+        bwt = rng.choice(H.BWT_ALPHABET, size=n)
+        cuts = random_cuts(rng, n, int(rng.integers(1, 6)))
+        G = len(cuts) - 1
+        sums = (api.ClusterSummary * G)()
+        stats = (api.Stats * G)()
+        rows = np.zeros((G, W), dtype=np.uint64)
+        for g, (lo, hi) in enumerate(zip(cuts[:-1], cuts[1:])):
+            s, rs, rl = H.emulate_shard(lcp, bwt, lo, hi, k, m)
+            sums[g] = s
+            st = stats[g]
+            d = api.ClusterDev()
+            for f in ("n_end", "n_written", "head_end", "any_event", "open_start", "end_nm2_start", "tail_lcp_nm2", "tail_lcp_nm1",
+                      "tail_bwt_nm1"):
+                setattr(d, f, getattr(s, f))
+            for l in rl.tolist():
+                if l <= api.MAX_C_LEN:
+                    d.hist[l] += 1
+                    st.hist[l] += 1
+            d.n_bases = st.n_bases = int(rl.astype(np.uint64).sum())
+            st.n_clust = len(rl)
+            st.last_len = int(rl[-1]) if len(rl) else 0
+            d.last_rec = (len(rl) << 16) | (int(rl[-1]) if len(rl) else 0)
+            d.ticket, d.n_pf = 12345, 7  # scratch values of the scan: must not matter
+            rows[g, :W - 4] = np.frombuffer(bytes(d), dtype=np.uint64)
+            rows[g, W - 4:] = (hi - lo, lo, 4, 0)
+        for my in range(G):
+            try:
+                want = api.exchange_finish(sums, stats, my)
+            except api.E2SError:
+                with pytest.raises(api.E2SError):
+                    api.exchange_rows_finish(rows, my, n, k, m)
+                continue
+            got = api.exchange_rows_finish(rows, my, n, k, m)
+            assert bytes(got[0]) == bytes(want[0]) and bytes(got[1]) == bytes(want[1]), (it, my, cuts)
