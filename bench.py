@@ -592,6 +592,8 @@ def main():
                     "ms_per_launch": kern[dom]["ms"], "alg_bytes_per_launch": kern[dom]["alg_bytes"],
                     "kernels": kern, "kernel_share_of_step": ksum_ms / ms if ms else None,
                     "fused_prefilter": bool(fused), "resident_lcp_bytes": lcp_bytes,
+                    "note": "k_lcp_flags is the HBM-bound streaming kernel (see kernels); k_cluster_emit is limited by issue slots, not DRAM "
+                            "(profiles/r1_v21_ncu_summary.md: 58 % issue-active, 171 M warp instructions)",
                     "pipeline": {"alg_bytes_per_step": sum(alg[k] for k in alg if ktimes[k][1]),
                                  "GBps": sum(alg[k] for k in alg if ktimes[k][1]) / (ms / args.steps * 1e-3) / 1e9,
                                  "frac_of_peak": sum(alg[k] for k in alg if ktimes[k][1]) / (ms / args.steps * 1e-3) / 1e9 / peak}}
@@ -637,8 +639,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(args), "positions_per_gpu": n, "positions_total": n_global,
-                       "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; " + ("one ncclAllGather of the shard summaries per step, issued by the library on its stream (e2s_pipeline_sharded)" if comm is not None else "NCCL all-gather of shard summaries"),
-                       "l2": "inputs (13 B/position, >= 7 GB per GPU at C2) exceed the 126 MB L2; no flush needed",
+                       "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; " + ("one ncclAllGather of the shard summaries per step, issued by the library on its stream (e2s_pipeline_sharded)" if comm is not None else ("no exchange (single shard: e2s_pipeline_resident)" if world == 1 else "torch.distributed all-gather of shard summaries")),
+                       "l2": "the resident inputs a step streams (1.25-4.25 B/position: >= 0.7 GB per GPU at C2) exceed the 126 MB L2; no flush needed",
                        "resident_layout": f"SoA: lcp u32 + text u32 + suff u32 + bwt u8 + 2-bit base-code planes of the BWT (built at seal); K1 streams a {'one-byte LCP copy built at seal (every LCP value <= 127)' if lcp_bytes == 1 else 'the 4-byte LCP'}",
                        "scale": args.scale, "tiles": T, "exchange_us": exchange_us},
             "clocks": clocks, "e2e": e2e, "egsa_build": egsa_build, "index_check": index_check, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
