@@ -79,3 +79,30 @@ def test_cuda_builder_matches_torch_builder_small(built):
         torch.cuda.synchronize()
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("case", CASES[:3] + [CASES[4]])
+def test_two_bit_zero_padded_keys_with_shortest_first_ties_give_the_terminated_order(case):
+    """the ordering argument of csrc/build_egsa.cu, restated in plain Python (no GPU): sort the suffixes by their 2-bit
+    packed, ZERO-padded keys with a STABLE sort whose initial order is (offset descending, read id ascending) -> exactly
+    the order of the `$`-terminated strings (`$` < A < C < G < T, equal suffixes by read id) the oracle's comparison sort gives"""
+    reads = _reads(case)
+    R, L = reads.shape
+    code = np.zeros(256, dtype=np.int64)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = i
+    c = code[reads]
+    ids = [(L - p) * R + r for p in range(L, -1, -1) for r in range(R)]  # ascending ids = the initial order
+    assert ids == sorted(ids)
+
+    def key(i):
+        p, r = L - i // R, i % R
+        v = 0
+        for s in range(p, L):
+            v = (v << 2) | int(c[r, s])
+        return v << (2 * p)  # zero padding up to L symbols
+
+    order = sorted(ids, key=key)  # Python's sort is stable
+    e = O.build_egsa(reads)
+    assert [i % R for i in order] == e["text"].tolist()
+    assert [L - i // R for i in order] == e["suff"].tolist()
