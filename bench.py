@@ -209,17 +209,22 @@ def check_egsa_sample(rs, eg, samples=200000, seed=7):
     return ok, len(idx)
 
 
-def aos_records_pinned(eg, torch):
-    """13-byte .gesa records (text suff lcp bwt) in pinned host memory, interleaved on the device."""
-    n = int(eg["n"])
+def aos_records_pinned(eg, torch, lo=0, hi=None, chunk=1 << 26):
+    """13-byte .gesa records (text suff lcp bwt) of positions [lo, hi) in pinned host memory, interleaved on the device
+    in bounded chunks (a C3-size index is 50 GB of records)."""
+    hi = int(eg["n"]) if hi is None else hi
+    n = hi - lo
     dev = eg["lcp"].device
-    rec = torch.empty((n, 13), dtype=torch.uint8, device=dev)
-    rec[:, 0:4] = eg["text"].view(torch.uint8).view(n, 4)
-    rec[:, 4:8] = eg["suff"].view(torch.uint8).view(n, 4)
-    rec[:, 8:12] = eg["lcp"].view(torch.uint8).view(n, 4)
-    rec[:, 12] = eg["bwt"]
     host = torch.empty(n * 13, dtype=torch.uint8, pin_memory=True)
-    host.copy_(rec.view(-1))
+    rec = torch.empty((min(chunk, n), 13), dtype=torch.uint8, device=dev)
+    for a in range(lo, hi, chunk):
+        b = min(hi, a + chunk)
+        r = rec[: b - a]
+        r[:, 0:4] = eg["text"][a:b].view(torch.uint8).view(b - a, 4)
+        r[:, 4:8] = eg["suff"][a:b].view(torch.uint8).view(b - a, 4)
+        r[:, 8:12] = eg["lcp"][a:b].view(torch.uint8).view(b - a, 4)
+        r[:, 12] = eg["bwt"][a:b]
+        host[(a - lo) * 13:(b - lo) * 13].copy_(r.view(-1))
     del rec
     return host
 
@@ -236,7 +241,7 @@ def reference_sample(workload, seed, target_positions, device):
     scale = min(1.0, target_positions / n_full)
     rs, eg = make_dataset(workload, seed, scale, device)
     d = tempfile.mkdtemp(prefix="e2s_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    fasta = synth.write_dataset(d, rs, eg)
+    fasta = synth.write_dataset(d, rs, eg, fixed_headers=True)
     return d, fasta, rs, eg, scale
 
 
@@ -294,11 +299,7 @@ def reference_arm(args):
     if not O.ref_available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binaries missing"}))
         return
-    try:
-        import torch
-        device = "cuda" if torch.cuda.is_available() else "cpu"
-    except Exception:
-        device = "cpu"
+    device = "cpu"  # the reference arm needs no GPU: its sample index is built by the torch sorts on the host
     d, fasta, rs, eg, scale = reference_sample(args.workload, args.seed + 1000, args.cpu_positions, device)
     try:
         n = int(eg["n"])
@@ -345,16 +346,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--workload", default="C3", help="C3 = the configuration BASELINE.json's metric is quoted on (config 5 = C3 at 1/2/4/8 GPUs)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-positions", type=float, default=3e7, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = one workload per GPU (the default, what the driver's scaling run uses); strong = one workload cut "
-                         "into N contiguous eBWT ranges (BASELINE config C5 with --workload C3)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong (default) = ONE workload cut into N contiguous eBWT ranges (BASELINE config 5 = C3 at 1/2/4/8 "
+                         "GPUs); weak = one workload per GPU, glued end to end")
     ap.add_argument("--builder", default="auto", choices=["auto", "torch", "native"],
                     help="who builds the workload's index (data preparation): auto = torch for C1/C2 (and the library's builder is checked "
                          "against it), the library's own builder for C3-size workloads")
@@ -399,8 +400,6 @@ def main():
         if not okc:
             raise SystemExit("the index built by the library fails the order / LCP / BWT property check")
         args.no_egsa_build = True
-    if big:
-        args.no_e2e = True  # 13 B/position of pinned host records: not at this size
     # ---- EGSA construction on the GPU (data preparation, outside the timed step): the library's
     # builder on the same reads, timed, and compared element by element with the arrays the step below runs on ----
     egsa_build = None
@@ -427,6 +426,8 @@ def main():
         args.no_e2e = args.no_cpu_baseline = True
         if world > 1:
             raise SystemExit("--tiles is a single-GPU study")
+    if strong:
+        args.no_e2e = True  # (every rank holds the whole index here; a sharded e2e stages only its range -- see e2e_sharded)
     n_tile = int(eg["n"])
     n = n_tile * T
     n_all = [n]

@@ -36,18 +36,26 @@ __device__ __forceinline__ uint32_t code2(uint32_t c) {  // ACGT / acgt -> 0..3 
 }
 
 // one thread per (read, word)
-__global__ void k_pack_reads(const uint8_t* __restrict__ reads, uint64_t R, uint32_t L, uint32_t W, uint64_t* __restrict__ packed) {
+// *bad is raised when a base is not one of ACGT / acgt: the 2-bit keys have no code for it (N would sort and compare as A)
+__global__ void k_pack_reads(const uint8_t* __restrict__ reads, uint64_t R, uint32_t L, uint32_t W, uint64_t* __restrict__ packed,
+                             uint32_t* __restrict__ bad) {
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= R * (W + 1)) return;
     const uint64_t r = i / (W + 1);
     const uint32_t w = uint32_t(i % (W + 1));
     uint64_t v = 0;
+    bool other = false;
     for (uint32_t j = 0; j < 32; ++j) {
         const uint32_t s = 32 * w + j;
         v <<= 2;
-        if (s < L) v |= code2(reads[r * L + s]);
+        if (s < L) {
+            const uint32_t c = reads[r * L + s], u = c & 0xDFu;
+            other |= !(u == 'A' || u == 'C' || u == 'G' || u == 'T');
+            v |= code2(c);
+        }
     }
     packed[i] = v;
+    if (other) *bad = 1u;
 }
 
 // symbols [p + 32 w, +32) of read r as one word (zero past the end of the read)
@@ -113,12 +121,15 @@ cudaError_t build_egsa(const uint8_t* d_reads, uint64_t R, uint32_t L, uint32_t*
     uint64_t *packed = nullptr, *k0 = nullptr, *k1 = nullptr;
     uint32_t *i0 = nullptr, *i1 = nullptr;
     void* tmp = nullptr;
+    uint32_t* d_bad = nullptr;
     size_t tmp_bytes = 0;
     cudaError_t e = cudaSuccess;
     auto done = [&](cudaError_t rc) {
-        cudaFree(packed); cudaFree(k0); cudaFree(k1); cudaFree(i0); cudaFree(i1); cudaFree(tmp);
+        cudaFree(packed); cudaFree(k0); cudaFree(k1); cudaFree(i0); cudaFree(i1); cudaFree(tmp); cudaFree(d_bad);
         return rc;
     };
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&d_bad), 4)) != cudaSuccess) return done(e);
+    if ((e = cudaMemsetAsync(d_bad, 0, 4, stream)) != cudaSuccess) return done(e);
     if ((e = cudaMalloc(reinterpret_cast<void**>(&packed), R * (W + 1) * 8)) != cudaSuccess) return done(e);
     if ((e = cudaMalloc(reinterpret_cast<void**>(&k0), n * 8)) != cudaSuccess) return done(e);
     if ((e = cudaMalloc(reinterpret_cast<void**>(&k1), n * 8)) != cudaSuccess) return done(e);
@@ -129,7 +140,13 @@ cudaError_t build_egsa(const uint8_t* d_reads, uint64_t R, uint32_t L, uint32_t*
     if ((e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, ids, n, 0, 64, stream)) != cudaSuccess) return done(e);
     if ((e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16)) != cudaSuccess) return done(e);
 
-    k_pack_reads<<<blocks_for(R * (W + 1), 256), 256, 0, stream>>>(d_reads, R, L, W, packed);
+    k_pack_reads<<<blocks_for(R * (W + 1), 256), 256, 0, stream>>>(d_reads, R, L, W, packed, d_bad);
+    {   // a base outside ACGT / acgt has no 2-bit code: refuse before sorting instead of building a wrong index
+        uint32_t h_bad = 0;
+        if ((e = cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return done(e);
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return done(e);
+        if (h_bad) return done(cudaErrorInvalidValue);
+    }
     k_iota32<<<blocks_for(n, 256), 256, 0, stream>>>(ids.Current(), n);
     *launches += 2;
     for (int w = int(W) - 1; w >= 0; --w) {

@@ -431,6 +431,12 @@ int e2s_build_egsa_dev(e2s_ctx* c, const uint8_t* d_reads, uint64_t n_reads, uin
         cudaGetLastError();
         return fail(c, E2S_ERR_NOMEM, "e2s_build_egsa_dev: scratch buffers (about 24 bytes per suffix)");
     }
+    if (e == cudaErrorInvalidValue) {
+        cudaGetLastError();
+        return fail(c, E2S_ERR_UNSUPPORTED,
+                    "e2s_build_egsa_dev: a read holds a base outside ACGT/acgt (N has no 2-bit code; the reference itself is "
+                    "non-deterministic on N, ref:include.hpp:273) -- filter such reads first");
+    }
     if (e != cudaSuccess) return cuda_fail(c, e, "build_egsa");
     return E2S_OK;
 }

@@ -645,10 +645,12 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
 
     SnpDev& hd = *w->h_dev;
     for (int attempt = 0;; ++attempt) {
-        const uint64_t cap_surv = w->want_survivors < a.m ? w->want_survivors : a.m;
+        // on the fused path (pre_list) the survivor list is the caller's: the flagged list is bounded by ITS length, not
+        // by the capacity guess of a K3a pass that does not run (the retry could otherwise never grow past that guess)
+        const uint64_t cap_surv = pre_list ? (pre_count ? pre_count : 1) : (w->want_survivors < a.m ? w->want_survivors : a.m);
         const uint64_t cap_flag = w->want_flagged < cap_surv ? w->want_flagged : cap_surv;
         const uint64_t n_slots = cap_flag * 4;
-        CK(ensure(w->survivors, w->survivors_cap, size_t(cap_surv)));
+        if (!pre_list) CK(ensure(w->survivors, w->survivors_cap, size_t(cap_surv)));
         CK(ensure(w->flagged, w->flagged_cap, size_t(cap_flag)));
         CK(ensure(w->slots, w->slots_cap, size_t(n_slots)));
         if (size_t(n_slots) * 2 * cap > w->slot_list_cap || !w->slot_text) {

@@ -249,10 +249,25 @@ def write_fasta(path, reads: np.ndarray):
         del nl
 
 
-def write_dataset(dirpath, rs: ReadSet, egsa, name="ALL.fasta", x=4, y=4, z=4, bcr=False):
+def write_fasta_fixed(path, reads: np.ndarray):
+    """Same reads, fixed-width headers (`>` + 9 digits): the whole file is one 2-D byte array, written without a Python
+    loop per read (C2 / C3-size read sets).  The tools only look at the first byte of a header line."""
+    R, L = reads.shape
+    out = np.empty((R, 11 + L + 1), dtype=np.uint8)
+    out[:, 0] = ord(">")
+    ids = np.arange(R, dtype=np.int64)
+    for j in range(9):
+        out[:, 9 - j] = (ids // 10 ** j % 10 + ord("0")).astype(np.uint8)
+    out[:, 10] = 10
+    out[:, 11:11 + L] = reads
+    out[:, 11 + L] = 10
+    out.tofile(path)
+
+
+def write_dataset(dirpath, rs: ReadSet, egsa, name="ALL.fasta", x=4, y=4, z=4, bcr=False, fixed_headers=False):
     os.makedirs(dirpath, exist_ok=True)
     fasta = os.path.join(dirpath, name)
-    write_fasta(fasta, rs.reads)
+    (write_fasta_fixed if fixed_headers else write_fasta)(fasta, rs.reads)
     if bcr:
         write_bcr(fasta, egsa, x, y, z)
     else:

@@ -56,6 +56,27 @@ def test_cuda_builder_matches_oracle(built, case):
 
 
 @pytest.mark.gpu
+def test_cuda_builder_rejects_bases_outside_acgt(built):
+    """an N (or any byte that is not ACGT / acgt) has no 2-bit code: the builder must refuse it, not index it as A"""
+    from ebwt2snp_b200 import api
+    reads = np.frombuffer(b"ACGTACGTACGTACGNACGTACGTacgtACGT", dtype=np.uint8).reshape(4, 8)
+    ctx = api.Context(0)
+    try:
+        with pytest.raises(api.E2SError) as ei:
+            ctx.build_egsa(reads)
+        assert ei.value.code == api.ERR_UNSUPPORTED and "ACGT" in str(ei.value)
+        ok = reads.copy()
+        ok[1, 7] = ord("a")  # lower case is a base
+        up = ok.copy()
+        up[1, 7] = ord("A")
+        a, b = ctx.build_egsa(ok), O.build_egsa(up)  # same order and LCP as the upper-case collection
+        for k in ("lcp", "text", "suff"):
+            assert np.array_equal(a[k].cpu().numpy().view(np.uint32), b[k]), k
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
 def test_cuda_builder_matches_torch_builder_small(built):
     """the 'small' configuration (8.1 M suffixes): CUDA builder == the torch sorts on the same GPU, and the hot path on
     arrays born on the device gives the oracle's clusters"""

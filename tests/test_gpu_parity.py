@@ -323,6 +323,27 @@ def test_phase2_capacity_retry(ctx, monkeypatch):
         sh.close()
 
 
+def test_phase2_capacity_retry_fused(ctx, monkeypatch):
+    """the same on the fused path (e2s_pipeline_resident: the survivor list comes from the scan, K3a does not run): the
+    flagged list must be able to grow up to the length of THAT list, whatever the capacity guess was"""
+    rs, e = H.dataset("small", 1)
+    n = e["n"]
+    es, el, _, _ = O.cluster_lm(e["lcp"], e["bwt"], 16, 2)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    ctx.stage_reads(rs.reads, off)
+    p, op = api.default_params(rs.nreads1), O.default_params(rs.nreads1)
+    ost = O.statistics(es, el, op.mcov_out, op.pval)
+    otext, ores = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+    for first_cap in ("1", "5"):
+        monkeypatch.setenv("E2S_SNP_FIRST_CAPACITY", first_cap)
+        sh = ctx.shard(n)
+        sh.load_soa(e["lcp"], e["text"], e["suff"], e["bwt"])
+        sh.seal()
+        res = sh.pipeline_resident(p, 16, 2)
+        assert res.snp.n_candidates == ores.n_candidates and api.events_format(sh.events(), p) == otext
+        sh.close()
+
+
 def test_rejects_unsorted_clusters(ctx):
     """the reference silently mis-joins unsorted / overlapping records (ref:clust2snp.cpp:818-833); here: E2S_ERR_UNSUPPORTED"""
     rs, e = H.dataset("tiny", 1)
