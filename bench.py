@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 METRIC = "ebwt_positions_per_s"
 UNIT = "positions/s"
 K_DEF, M_DEF = 16, 2  # ebwt2clust defaults (ref:ebwt2clust.cpp:18-19)
-KERNELS = {0: "k_lcp_flags", 1: "k_cluster_emit", 2: "k_code_scan", 3: "k_cluster_exact"}
+KERNELS = {0: "k_lcp_flags", 1: "k_cluster_emit", 2: "k_code_scan", 3: "k_cluster_exact", 4: "k_cluster_scan"}
 
 
 def log(*a):
@@ -563,10 +563,13 @@ def main():
         api.KERNEL_EMIT: n / 4 + 10 * m_own + (pos_analysed / 4 if fused else 0),  # masks read + records written (+ the 2-bit base codes inside analysed clusters)
         api.KERNEL_SCAN: pos_analysed / 4 + 10 * m_own,  # 2-bit base code (resident bit planes) of positions in analysed clusters + record list
         api.KERNEL_EXACT: 0,
+        # K1 + K2 in one pass: the byte LCP read once, the records written, the 2-bit base codes inside analysed clusters (fused prefilter)
+        api.KERNEL_SCAN1: n + 10 * m_own + (pos_analysed / 4 if fused else 0),
     }
     streamed = {api.KERNEL_SCAN: n / 4 + 10 * m_own}    # the 16-byte plane loads also carry the positions outside clusters
     if fused:
         streamed[api.KERNEL_EMIT] = n / 2 + 10 * m_own + n / 4  # masks twice (count pass + write pass) + the bit planes
+        streamed[api.KERNEL_SCAN1] = n + 10 * m_own + n / 4     # the whole plane array comes in with the tiles
     kern = {}
     ksum_ms = 0.0
     for kid, name in KERNELS.items():
@@ -593,8 +596,8 @@ def main():
                     "ms_per_launch": kern[dom]["ms"], "alg_bytes_per_launch": kern[dom]["alg_bytes"],
                     "kernels": kern, "kernel_share_of_step": ksum_ms / ms if ms else None,
                     "fused_prefilter": bool(fused), "resident_lcp_bytes": lcp_bytes,
-                    "note": "k_lcp_flags is the HBM-bound streaming kernel (see kernels); k_cluster_emit is limited by issue slots, not DRAM "
-                            "(profiles/r1_v21_ncu_summary.md: 58 % issue-active, 171 M warp instructions)",
+                    "note": "k_cluster_scan = LCP stencil + look-back scan + compaction + BWT prefilter in one pass over the byte LCP; "
+                            "k_lcp_flags / k_cluster_emit only run on shards whose LCP does not fit a byte or for -m > 33",
                     "pipeline": {"alg_bytes_per_step": sum(alg[k] for k in alg if ktimes[k][1]),
                                  "GBps": sum(alg[k] for k in alg if ktimes[k][1]) / (ms / args.steps * 1e-3) / 1e9,
                                  "frac_of_peak": sum(alg[k] for k in alg if ktimes[k][1]) / (ms / args.steps * 1e-3) / 1e9 / peak}}

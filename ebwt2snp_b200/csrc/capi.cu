@@ -68,6 +68,9 @@ struct e2s_shard {
     uint64_t flag_words = 0;
     uint64_t* d_desc = nullptr;
     size_t desc_cap = 0;
+    uint64_t* d_scan_desc = nullptr;  // k_cluster_scan: two look-back words per tile (A then B), validated by scan_epoch
+    uint64_t scan_tiles = 0;
+    uint32_t scan_epoch = 0;
     ClusterDev* d_res = nullptr;
     ClusterDev h_res;           // host copy of the last scan's accumulators (incl. length histogram)
     ClusterDev* h_pin = nullptr; // pinned staging for that copy
@@ -317,6 +320,7 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->d_start);
     cudaFree(s->d_len);
     cudaFree(s->d_desc);
+    cudaFree(s->d_scan_desc);
     cudaFree(s->d_flags);
     cudaFree(s->d_packed);
     cudaFreeHost(s->h_pin);
@@ -635,25 +639,39 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
     CU(c, cudaSetDevice(c->device));
     const char* env = getenv("E2S_CLUSTER_VARIANT");
     s->variant = env ? atoi(env) : 0;
+    // One pass over the byte LCP (k_cluster_scan) whenever the shard has it and min_len allows the bit-parallel length
+    // test; else the two-kernel path on the 4-byte LCP (k_lcp_flags + k_cluster_emit).  E2S_SCAN_LEGACY=1 forces the latter.
+    const bool one_pass = s->sealed && s->lcp8_ok && min_len <= 33 && !getenv("E2S_SCAN_LEGACY");
     const uint64_t num_tiles = emit_num_tiles(s->n_local);
-    if (!s->d_desc) {
-        if (cudaMalloc(reinterpret_cast<void**>(&s->d_desc), emit_desc_words() * 8) != cudaSuccess)
-            return fail(c, E2S_ERR_NOMEM, "chunk descriptors");
-        s->desc_cap = emit_desc_words();
-    }
-    if (!s->d_flags) {
-        s->flag_words = flags_words_needed(s->n_local);
-        if (cudaMalloc(reinterpret_cast<void**>(&s->d_flags), s->flag_words * 2 * 4) != cudaSuccess)
-            return fail(c, E2S_ERR_NOMEM, "flag masks");
-        // K1 overwrites the words of its tiles; the tail up to K2's tile size stays zero
-        CU(c, cudaMemsetAsync(s->d_flags, 0, s->flag_words * 2 * 4, c->stream));
+    if (one_pass) {
+        const uint64_t nt = scan_num_tiles(s->n_local);
+        if (!s->d_scan_desc || s->scan_tiles < nt) {
+            cudaFree(s->d_scan_desc);
+            s->d_scan_desc = nullptr;
+            if (cudaMalloc(reinterpret_cast<void**>(&s->d_scan_desc), nt * 2 * 8) != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "scan descriptors");
+            s->scan_tiles = nt;
+            s->scan_epoch = 0;
+        }
+    } else {
+        if (!s->d_desc) {
+            if (cudaMalloc(reinterpret_cast<void**>(&s->d_desc), emit_desc_words() * 8) != cudaSuccess)
+                return fail(c, E2S_ERR_NOMEM, "chunk descriptors");
+            s->desc_cap = emit_desc_words();
+        }
+        if (!s->d_flags) {
+            s->flag_words = flags_words_needed(s->n_local);
+            if (cudaMalloc(reinterpret_cast<void**>(&s->d_flags), s->flag_words * 2 * 4) != cudaSuccess)
+                return fail(c, E2S_ERR_NOMEM, "flag masks");
+            // K1 overwrites the words of its tiles; the tail up to K2's tile size stays zero
+            CU(c, cudaMemsetAsync(s->d_flags, 0, s->flag_words * 2 * 4, c->stream));
+        }
     }
     if (!s->d_start) {
         int rc = ensure_records(s, s->n_local / 8 + 4096);
         if (rc) return rc;
     }
-    // K1: LCP -> START/END masks
-    {
+    // K1: LCP -> START/END masks (two-kernel path only)
+    if (!one_pass) {
         FlagParams fp;
         fp.lcp = s->lcp;
         fp.n_local = s->n_local;
@@ -673,8 +691,8 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
     if (!s->h_pin) CU(c, cudaHostAlloc(reinterpret_cast<void**>(&s->h_pin), sizeof(ClusterDev), cudaHostAllocDefault));
     ClusterDev& h = *s->h_pin;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        CU(c, cudaMemsetAsync(s->d_desc, 0, s->desc_cap * 8, c->stream));
         CU(c, cudaMemsetAsync(s->d_res, 0, sizeof(ClusterDev), c->stream));
+        if (!one_pass) CU(c, cudaMemsetAsync(s->d_desc, 0, s->desc_cap * 8, c->stream));
         EmitParams p;
         p.s_words = s->d_flags;
         p.e_words = s->d_flags + s->flag_words;
@@ -721,10 +739,42 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
         const bool is_last = s->global_off + s->n_local == s->n_global;
         p.tail_lcp = is_last ? s->lcp + s->n_local - 2 : nullptr;
         p.tail_bwt = is_last ? s->bwt + s->n_local - 1 : nullptr;
-        c->timer.begin(E2S_KERNEL_EMIT, c->stream);
-        cudaError_t le = launch_emit(p, c->sm_count, c->stream);
-        c->timer.end(c->stream);
-        CU(c, le);
+        if (one_pass) {
+            if (++s->scan_epoch >= (1u << 20) || s->scan_epoch == 1) {  // a fresh buffer, or the epoch wrapped: stale words must not validate
+                CU(c, cudaMemsetAsync(s->d_scan_desc, 0, s->scan_tiles * 2 * 8, c->stream));
+                if (s->scan_epoch >= (1u << 20)) s->scan_epoch = 1;
+            }
+            Scan8Params sp;
+            sp.lcp8 = s->lcp8_a + PAD_L;
+            sp.planes = s->d_planes;
+            sp.n_local = s->n_local;
+            sp.global_off = s->global_off;
+            sp.n_global = s->n_global;
+            sp.k = k;
+            sp.min_len = min_len;
+            sp.num_tiles = 0;
+            sp.epoch = s->scan_epoch;
+            sp.descA = s->d_scan_desc;
+            sp.descB = s->d_scan_desc + s->scan_tiles;
+            sp.out_start = p.out_start;
+            sp.out_len = p.out_len;
+            sp.cap = p.cap;
+            sp.pf_mcov = p.pf_mcov;
+            sp.pf_list = p.pf_list;
+            sp.pf_cap = p.pf_cap;
+            sp.res = s->d_res;
+            sp.tail_lcp = p.tail_lcp;
+            sp.tail_bwt = p.tail_bwt;
+            c->timer.begin(E2S_KERNEL_SCAN1, c->stream);
+            cudaError_t le = launch_scan(sp, s->alloc_r, c->sm_count, c->stream);
+            c->timer.end(c->stream);
+            CU(c, le);
+        } else {
+            c->timer.begin(E2S_KERNEL_EMIT, c->stream);
+            cudaError_t le = launch_emit(p, c->sm_count, c->stream);
+            c->timer.end(c->stream);
+            CU(c, le);
+        }
         ++c->launches;
         bool any_overflow = false;
         uint64_t max_written = 0;

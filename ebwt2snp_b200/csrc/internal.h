@@ -77,6 +77,29 @@ struct EmitParams {  // K2
     const uint8_t* tail_bwt;   // &bwt[n_global-1]
 };
 
+struct Scan8Params {  // k_cluster_scan (scan.cu): K1 + K2 in one pass over the one-byte LCP
+    const uint8_t* lcp8;        // local position 0 of the byte LCP (PAD_L readable bytes before it)
+    const uint4* planes;        // resident base-code bit planes (fused prefilter), may be null when pf_mcov == 0
+    uint64_t n_local, global_off, n_global;
+    uint32_t k;
+    int32_t min_len;            // <= 33
+    uint32_t num_tiles;         // filled by the launcher
+    uint32_t epoch;             // 1 .. 2^20 - 1: validates the descriptor words of THIS launch
+    uint64_t* descA;            // per tile: state after the tile
+    uint64_t* descB;            // per tile: kept-record count (aggregate, then inclusive prefix)
+    uint64_t* out_start;
+    uint16_t* out_len;
+    uint64_t cap;
+    uint32_t pf_mcov;
+    uint64_t* pf_list;
+    uint64_t pf_cap;
+    ClusterDev* res;
+    const uint32_t* tail_lcp;   // &lcp[n_global-2] when this is the last shard, else null
+    const uint8_t* tail_bwt;    // &bwt[n_global-1]
+};
+uint64_t scan_num_tiles(uint64_t n_local);
+cudaError_t launch_scan(const Scan8Params& p, uint64_t alloc_r, int sm_count, cudaStream_t stream);
+
 uint64_t flags_words_needed(uint64_t n_local);
 uint64_t emit_num_tiles(uint64_t n_local);
 uint64_t emit_desc_words();

@@ -476,7 +476,7 @@ def test_fused_prefilter_overflow_falls_back(ctx, monkeypatch):
     assert api.events_format(sh2.events(), p) == otext
     sh.close()
     sh2.close()
-    assert fused_launches >= 6
+    assert fused_launches >= 5  # scan, k_put?/K3x, K3b, K4 (+ the adopted-record helper)
 
 
 @pytest.mark.parametrize("fused", [False, True])
