@@ -290,6 +290,14 @@ int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t
         e2s_shard_destroy(s);
         return fail(c, E2S_ERR_NOMEM, std::string("shard allocation: ") + cudaGetErrorString(e));
     }
+    // the byte copy of the LCP the one-pass scan streams (1 B/position); without room for it the shard stays on the 4-byte stream
+    if (cudaMalloc(reinterpret_cast<void**>(&s->lcp8_a), ne) != cudaSuccess) {
+        cudaGetLastError();
+        s->lcp8_a = nullptr;
+    }
+    if (s->lcp8_a) CU(c, cudaMemsetAsync(s->lcp8_a, 0, ne, c->stream));
+    CU(c, cudaMemsetAsync(s->d_planes, 0, plane_quads(s->alloc_r) * sizeof(uint4), c->stream));  // pads: code 0
+    CU(c, cudaMemsetAsync(s->d_seal_flag, 0, 4, c->stream));
     s->lcp = s->lcp_a + PAD_L;
     s->text = s->text_a + PAD_L;
     s->suff = s->suff_a + PAD_L;
@@ -341,6 +349,16 @@ static void keep_range(const e2s_shard* s, uint64_t* lo, uint64_t* hi) {
     *hi = h < s->n_global ? h : s->n_global;
 }
 
+// every load also writes the narrow resident copies of what it loaded (k_derive): byte LCP + base-code bit planes
+static cudaError_t derive_loaded(e2s_shard* s, int64_t l, uint64_t cnt, bool have_lcp, bool have_bwt) {
+    const bool last_shard = s->global_off + s->n_local == s->n_global;
+    // the scan looks at positions [-2, n_local] (on the last shard lcp[n_local] is the phantom, which only feeds END(n-1),
+    // left to the host tail rule): only those decide whether the byte copy is usable
+    return launch_derive(s->lcp, have_bwt ? s->bwt : nullptr, have_lcp ? (s->lcp8_a ? s->lcp8_a + PAD_L : nullptr) : nullptr, s->d_planes,
+                         l, l + int64_t(cnt), -2, int64_t(s->n_local) + (last_shard ? 0 : 1), s->d_seal_flag, s->ctx->stream,
+                         s->ctx->sm_count);
+}
+
 int e2s_shard_load_gesa(e2s_shard* s, const void* records, uint64_t first, uint64_t count, int x, int y, int z) {
     if (!s || !records) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_shard_load_gesa: NULL argument");
     e2s_ctx* c = s->ctx;
@@ -389,7 +407,8 @@ int e2s_shard_load_gesa(e2s_shard* s, const void* records, uint64_t first, uint6
         const int64_t l = int64_t(p) - int64_t(s->global_off);  // local index, may be -2 / -1
         CU(c, launch_unpack_gesa(c->d_raw[buf], cnt, x, y, z, s->lcp + l, s->text + l, s->suff + l, s->bwt + l, c->stream));
         CU(c, cudaEventRecord(c->ev_unpacked[buf], c->stream));
-        ++c->launches;
+        CU(c, derive_loaded(s, l, cnt, true, true));
+        c->launches += 2;
     }
     s->sealed = false;
     return E2S_OK;
@@ -410,6 +429,10 @@ static int load_soa(e2s_shard* s, const uint32_t* lcp, const uint32_t* text, con
     if (text) CU(c, cudaMemcpyAsync(s->text + l, text + so, cnt * 4, kind, c->stream));
     if (suff) CU(c, cudaMemcpyAsync(s->suff + l, suff + so, cnt * 4, kind, c->stream));
     if (bwt) CU(c, cudaMemcpyAsync(s->bwt + l, bwt + so, cnt, kind, c->stream));
+    if (lcp || bwt) {
+        CU(c, derive_loaded(s, l, cnt, lcp != nullptr, bwt != nullptr));
+        ++c->launches;
+    }
     s->sealed = false;
     return E2S_OK;
 }
@@ -491,41 +514,22 @@ int e2s_shard_seal(e2s_shard* s) {
     if (!s) return fail(nullptr, E2S_ERR_ARG, "shard == NULL");
     e2s_ctx* c = s->ctx;
     CU(c, cudaSetDevice(c->device));
-    if (s->global_off + s->n_local == s->n_global) {
+    if (s->global_off + s->n_local == s->n_global) {  // the records past EOF (a 1-block kernel) and their narrow copies
         CU(c, launch_fill_phantom(s->lcp, s->text, s->suff, s->bwt, s->n_local, HALO_R, s->lay_x, s->lay_y, s->lay_z,
                                   s->lay_bcr, c->stream));
-        ++c->launches;
+        CU(c, derive_loaded(s, int64_t(s->n_local), HALO_R, true, true));
+        c->launches += 2;
     }
-    // resident base-code bit planes of the BWT (incl. the right halo / phantom): what K3a and K2's fused prefilter read
-    CU(c, launch_bwt_planes(s->bwt_a, s->alloc_r, s->d_planes, c->stream, c->sm_count));
-    ++c->launches;
-    // narrow resident LCP for K1 (E2S_LCP_WIDE=1 keeps the 4-byte stream, for A/B measurements and the tests)
+    // The byte LCP and the bit planes were written by the loads themselves: sealing costs no pass over the data, only
+    // the verdict whether every LCP value the scan looks at fits the byte copy (E2S_LCP_WIDE=1 keeps the 4-byte stream,
+    // for A/B measurements and the tests)
     s->lcp8_ok = false;
     const char* wide = getenv("E2S_LCP_WIDE");
-    if (!(wide && atoi(wide) != 0)) {
-        const size_t ne = size_t(PAD_L) + s->alloc_r;  // multiple of 16
-        if (!s->lcp8_a && cudaMalloc(reinterpret_cast<void**>(&s->lcp8_a), ne) != cudaSuccess) {
-            cudaGetLastError();
-            s->lcp8_a = nullptr;  // no room for the copy: stay on the 4-byte stream
-        }
-        if (s->lcp8_a) {
-            uint32_t* d_flag = s->d_seal_flag;
-            CU(c, cudaMemsetAsync(d_flag, 0, 4, c->stream));
-            // K1 looks at positions [-2, n_local] (on the last shard lcp[n_local] is the phantom, which only feeds END(n-1),
-            // left to the host tail rule); everything else in the copy just has to be a byte <= 127
-            const bool last_shard = s->global_off + s->n_local == s->n_global;
-            CU(c, launch_lcp_narrow(s->lcp_a, s->lcp8_a, ne, PAD_L - 2, uint64_t(PAD_L) + s->n_local + (last_shard ? 0 : 1), d_flag,
-                                    c->stream, c->sm_count));
-            ++c->launches;
-            uint32_t h_flag = 1;
-            CU(c, cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
-            CU(c, cudaStreamSynchronize(c->stream));
-            s->lcp8_ok = h_flag == 0;
-            if (!s->lcp8_ok) {  // a value above 127: the copy is useless, give the memory back
-                cudaFree(s->lcp8_a);
-                s->lcp8_a = nullptr;
-            }
-        }
+    if (s->lcp8_a && !(wide && atoi(wide) != 0)) {
+        uint32_t h_flag = 1;
+        CU(c, cudaMemcpyAsync(&h_flag, s->d_seal_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        s->lcp8_ok = h_flag == 0;
     }
     s->sealed = true;
     return E2S_OK;
@@ -1507,6 +1511,7 @@ int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, in
     }
     lap("shard (cached after 1st call)");
     const int rs = x + y + z + 1;
+    CU(c, cudaMemsetAsync(s->d_seal_flag, 0, 4, c->stream));  // a cached shard is reloaded from its first position: forget the old verdict
     if ((rc = e2s_shard_load_gesa(s, gesa, 0, n, x, y, z))) return rc;
     if ((rc = e2s_shard_seal(s))) return rc;
     res->h2d_bytes += n * uint64_t(rs);

@@ -312,31 +312,6 @@ __global__ void __launch_bounds__(FL8_THREADS) k_lcp_flags8(FlagParams p, const 
     }
 }
 
-// seal-time: byte copy of the LCP (saturated at 127) + a flag if a value in [lo, hi) does not fit
-__global__ void k_lcp_narrow(const uint32_t* __restrict__ lcp_a, uint8_t* __restrict__ lcp8_a, uint64_t count4,
-                             uint64_t lo, uint64_t hi, uint32_t* flag) {
-    uint32_t bad = 0;
-    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count4; i += uint64_t(gridDim.x) * blockDim.x) {
-        const uint4 v = reinterpret_cast<const uint4*>(lcp_a)[i];
-        const uint32_t a[4] = {v.x, v.y, v.z, v.w};
-        uint32_t out = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint64_t e = 4 * i + j;
-            if (a[j] > 127u && e >= lo && e < hi) bad = 1;
-            out |= (a[j] > 127u ? 127u : a[j]) << (8 * j);
-        }
-        reinterpret_cast<uint32_t*>(lcp8_a)[i] = out;
-    }
-    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1u);
-}
-
-cudaError_t launch_lcp_narrow(const uint32_t* lcp_a, uint8_t* lcp8_a, uint64_t count, uint64_t lo, uint64_t hi,
-                              uint32_t* flag, cudaStream_t stream, int sm_count) {
-    k_lcp_narrow<<<dim3(unsigned(sm_count * 8)), dim3(256), 0, stream>>>(lcp_a, lcp8_a, count / 4, lo, hi, flag);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_flags8(const FlagParams& p0, const uint8_t* lcp8, int sm_count, cudaStream_t stream) {
     FlagParams p = p0;
     p.num_tiles = uint32_t((p.n_local + FL8_T - 1) / FL8_T);
@@ -739,7 +714,7 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
             if (st + PL_PAD < tile_gbase ||
                 frequent_codes<false>(pf_win, int64_t(st) - int64_t(tile_gbase), len, p.pf_mcov) >= 2) {
                 const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
-                if (at < p.pf_cap) p.pf_list[at] = o;
+                if (at < p.pf_cap) p.pf_list[at] = SurvEntry{st, st - p.global_off, len, 0u};
             }
         };
         // The list holds the ENDs that will be written: all of them in EXACT mode (D = 0), the kept ones otherwise

@@ -31,6 +31,16 @@ struct KernelTimer {
 };
 
 // ---- phase 1 ---------------------------------------------------------------------------------
+// One cluster handed to the exact test of phase 2 (find_variants, ref:clust2snp.cpp:367-500).  `base` is the index of the
+// cluster's first record in the arrays phase 2 reads: the shard's resident arrays (start - global_off) or, in streaming
+// mode, the compact payload the chunk's records were copied to before the chunk left the device.
+struct SurvEntry {
+    uint64_t start;  // global START (provenance; the events are put into eBWT order by it)
+    uint64_t base;
+    uint32_t len;    // wrapped 16-bit length, as in the .clusters record
+    uint32_t pad;
+};
+
 struct ClusterDev {  // device-resident accumulators of one e2s_cluster_run (zeroed before the launch)
     unsigned long long n_end;
     unsigned long long n_written;
@@ -69,7 +79,7 @@ struct EmitParams {  // K2
     // fused BWT prefilter of find_variants (pipeline mode: the caller already knows clust2snp's -m); pf_mcov = 0: off
     const uint4* planes;            // the shard's resident base-code bit planes (planes.cuh)
     uint32_t pf_mcov;
-    uint64_t* pf_list;              // out: indices (in this shard's record list) of clusters that need the exact test, unordered
+    SurvEntry* pf_list;             // out: clusters that need the exact test, unordered
     uint64_t pf_cap;
     uint64_t* dbg;       // optional: 4 globaltimer stamps per chunk (start, pass 1 done, exchange done, end); null = off
     ClusterDev* res;
@@ -91,7 +101,7 @@ struct Scan8Params {  // k_cluster_scan (scan.cu): K1 + K2 in one pass over the 
     uint16_t* out_len;
     uint64_t cap;
     uint32_t pf_mcov;
-    uint64_t* pf_list;
+    SurvEntry* pf_list;
     uint64_t pf_cap;
     ClusterDev* res;
     const uint32_t* tail_lcp;   // &lcp[n_global-2] when this is the last shard, else null
@@ -105,10 +115,7 @@ uint64_t emit_num_tiles(uint64_t n_local);
 uint64_t emit_desc_words();
 cudaError_t launch_flags(const FlagParams& p, uint64_t rows_alloc32, int sm_count, cudaStream_t stream, int variant);
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
-// narrow resident LCP: byte copy built at seal (values saturated at 127; *flag |= 1 if an element of [lo, hi) of the
-// padded array does not fit), and K1 on it (p.lcp unused)
-cudaError_t launch_lcp_narrow(const uint32_t* lcp_a, uint8_t* lcp8_a, uint64_t count, uint64_t lo, uint64_t hi,
-                              uint32_t* flag, cudaStream_t stream, int sm_count);
+// K1 on the byte LCP written by the loads (p.lcp unused)
 cudaError_t launch_flags8(const FlagParams& p, const uint8_t* lcp8, int sm_count, cudaStream_t stream);
 // small helpers: append up to 3 records to the device list / pack the list into 10-byte file records
 cudaError_t launch_put_records(uint64_t* d_start, uint16_t* d_len, uint64_t at, const uint64_t* st, const uint64_t* ln,
@@ -121,6 +128,10 @@ cudaError_t launch_pack_records(const uint64_t* d_start, const uint16_t* d_len, 
 // that receives record 0 (any may be null).
 cudaError_t launch_unpack_gesa(const uint8_t* d_rec, uint64_t count, int x, int y, int z, uint32_t* lcp, uint32_t* text,
                                uint32_t* suff, uint8_t* bwt, cudaStream_t stream);
+// narrow resident copies of the local positions [a, b) just loaded (byte LCP + base-code bit planes); *flag |= 1 when an
+// LCP value in [chk_lo, chk_hi) does not fit the byte copy
+cudaError_t launch_derive(const uint32_t* lcp, const uint8_t* bwt, uint8_t* lcp8, uint4* planes, int64_t a, int64_t b,
+                          int64_t chk_lo, int64_t chk_hi, uint32_t* flag, cudaStream_t stream, int sm_count);
 cudaError_t launch_fill_phantom(uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt, uint64_t n_local,
                                 uint64_t count, int x, int y, int z, int bcr, cudaStream_t stream);
 
@@ -164,8 +175,6 @@ struct CandSlot {  // one (flagged cluster, allele pair) slot written by K3b
     // followed in the slot arrays by idx/pos lists (see snp.cu)
 };
 
-// seal-time: base-code bit planes of the padded BWT array (bwt_a = PAD_L bytes before local position 0, alloc_r after)
-cudaError_t launch_bwt_planes(const uint8_t* bwt_a, uint64_t alloc_r, uint4* planes, cudaStream_t stream, int sm_count);
 cudaError_t launch_len_hist(const uint16_t* len, uint64_t m, unsigned long long* hist /*151 + n_bases*/,
                             cudaStream_t stream, int sm_count);
 cudaError_t launch_check_sorted(const uint64_t* start, const uint16_t* len, uint64_t m, SnpDev* dev,
@@ -177,11 +186,16 @@ void snp_work_destroy(SnpWork* w);
 // Runs K3a/K3x/K3b/K4 back to back on the stream with device-resident counts and synchronises ONCE at the
 // end; the packed events are written by K4 straight into pinned host memory.  If a capacity guess
 // (survivor / flagged lists) was too small the pass is repeated with larger buffers.
-// pre_list / pre_count: survivors of the prefilter when K2 already ran it (fused mode), else null / 0.
+// pre_list: survivors of the prefilter when the scan already ran it (fused mode), else null.  Their number is pre_count, or
+// -- d_pre_count != null -- a device-resident count (capped at pre_count = the list's capacity).  d_max_len != null: the
+// exact test reads max_clust_length from device memory (written by the merge kernel earlier on the stream).
 cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int max_clust_length,
                     const uint8_t* d_read_bases, const uint64_t* d_read_off, uint64_t n_reads, int sm_count,
                     cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err,
-                    KernelTimer* timer, const uint64_t* pre_list, uint64_t pre_count);
+                    KernelTimer* timer, const SurvEntry* pre_list, uint64_t pre_count,
+                    const unsigned long long* d_pre_count = nullptr, const int32_t* d_max_len = nullptr, bool sync = true);
+// the counters of the last snp_run (valid after the stream has been synchronised); false: a capacity guess was too small
+bool snp_collect(SnpWork* w, e2s_snp_counts* counts, const char** err, cudaError_t* rc);
 cudaError_t snp_fetch_events(SnpWork* w, e2s_event* host, uint64_t cap, uint64_t* n, cudaStream_t stream);
 
 }  // namespace e2s

@@ -49,11 +49,13 @@ constexpr int SC_WARPS = SC_THREADS / 32;
 constexpr int SC_V = 64;                       // positions per thread
 constexpr int SC_T = SC_THREADS * SC_V;        // 16384 positions per tile
 constexpr int SC_W = SC_V / 4;                 // 16 packed words per thread
-constexpr int SC_STAGES = 2;
-constexpr int SC_OCC = 4;                      // resident CTAs per SM the register / shared-memory budget is sized for
+constexpr int SC_STAGES = 2;                   // LCP tiles in flight / being read per CTA (a stage is free once its bytes are in registers)
+constexpr int SC_PSLOTS = 4;                   // plane windows: a tile's window lives until its records are written, one tile later
+constexpr int SC_OCC = 3;                      // resident CTAs per SM the register / shared-memory budget is sized for
 constexpr int SC_PF_QUADS = SC_T / 64 + PL_PAD / 64;  // plane quads of one tile and of the PL_PAD positions before it
 constexpr int SC_PF_BYTES = SC_PF_QUADS * 16;  // 4144
-constexpr int SC_STAGE_BYTES = SC_T + 5 * 1024;        // LCP tile (1024-aligned) + plane window, rounded up to keep the alignment
+constexpr int SC_PF_STRIDE = 4224;             // slot stride (128-byte multiple)
+constexpr int SC_DYN_SMEM = SC_STAGES * SC_T + SC_PSLOTS * SC_PF_STRIDE + 1024;  // + slack for the 1024-byte alignment of the TMA boxes
 constexpr int SC_CAP = 1024;                   // ENDs per list window (a typical tile lists ~300)
 
 // open-cluster state (as in cluster.cu)
@@ -94,26 +96,70 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
 }
 __device__ __forceinline__ uint64_t below(int b) { return (uint64_t(1) << b) - 1; }  // bits [0, b), b < 64
 
+// One look-back window: lane l polls desc[j0 - l] (tiles before tile 0 count as resolved) until the NEAREST resolved word
+// (status INC) is known and every word nearer than it is valid.  true: lane `first` holds that word; false: all 32 words are
+// valid aggregates (first = 32), go on with the next window.
+__device__ __forceinline__ bool poll_window(const uint64_t* desc, int64_t j0, int lane, uint32_t epoch, uint64_t& w, int& first) {
+    const int64_t j = j0 - lane;
+    w = 0;
+    bool ok = j < 0;
+    while (true) {
+        if (!ok) {
+            w = desc_load(desc + j);
+            ok = desc_valid(w, epoch);
+        }
+        const uint32_t okm = __ballot_sync(FULL, ok);
+        const uint32_t stopm = __ballot_sync(FULL, ok && (j < 0 || (w >> 62) == D_INC));
+        if (stopm) {
+            first = __ffs(stopm) - 1;
+            const uint32_t need = (1u << first) - 1u;
+            if ((okm & need) == need) return true;
+        } else if (okm == FULL) {
+            first = 32;
+            return false;
+        }
+        __nanosleep(20);
+    }
+}
+
+struct TileMeta {       // what P2 needs to know about a tile whose lists were filled by P1
+    uint64_t tile_gbase;
+    uint64_t x_in;      // open state entering the tile
+    uint64_t prefix;    // records kept before the tile (written by P2's look-back)
+    uint32_t tile;      // tile number
+    uint32_t nE;        // ENDs in the tile
+    uint32_t count;     // records it keeps
+    uint32_t adj;       // 1: the carried END is not written
+    uint32_t carried;   // the tile's first event is an END whose START lies before the tile
+    uint32_t pslot;     // plane-window slot
+};
+
 struct ScanShared {
     uint64_t full_bar[SC_STAGES];
     uint32_t tile_of[SC_STAGES];
     uint32_t wsum[2][SC_WARPS];   // per warp: #END | #dropped << 16 (double buffered by tile parity)
     int wls[2][SC_WARPS], wle[2][SC_WARPS], wfs[2][SC_WARPS], wfe[2][SC_WARPS];  // last / first START / END of the warp (tile-local)
     uint64_t wS[SC_WARPS];        // START word of the warp's last thread (min_len >= 3 only)
-    uint64_t x_in, prefix;        // open state entering the tile; records kept before it
-    uint32_t adj;                 // 1: the carried END is not written
+    TileMeta meta[2];
     unsigned int hist[E2S_HIST_BINS];
-    uint16_t s_pos[SC_CAP];       // [q] = tile-local position of the START that pairs with the window's q-th END
-    uint32_t e_ent[SC_CAP];       // [q] = END position | kept rank << 14 | kept << 28
+    uint16_t s_pos[2][SC_CAP];    // [slot][q] = tile-local position of the START that pairs with the window's q-th END
+    uint32_t e_ent[2][SC_CAP];    // [slot][q] = END position | kept rank << 14 | kept << 28
 };
 
 constexpr int NO_POS = 0x7fffffff;
 
 }  // namespace
 
+// The tile loop is software-pipelined so that no CTA ever blocks while it still owes the grid an aggregate:
+//   P1(tile)  wait for the tile, masks, ranks, lists; warp 0: publish A, resolve the state entering the tile, test the carried
+//             END, publish the kept count (B aggregate)
+//   P2(tile)  warp 0: look back over the B words -> records kept before the tile, publish B inclusive; all: write the records
+// run as P1(t0) P1(t1) P2(t0) P1(t2) P2(t1) ...: the aggregate of a CTA's NEXT tile is out before the CTA waits for the
+// prefix of its current one (with P1, P2 back to back a waiting CTA would hold up every tile after its next one).
 __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __grid_constant__ CUtensorMap tmap, Scan8Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* plane_slots = stages + size_t(SC_STAGES) * SC_T;  // SC_PSLOTS windows of SC_PF_STRIDE bytes
     __shared__ ScanShared sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -124,14 +170,16 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
     const uint32_t kadd = (128u - kk) * 0x01010101u;
 
     for (int i = tid; i < E2S_HIST_BINS; i += SC_THREADS) sh.hist[i] = 0;
-    auto issue = [&](int stage) {  // thread 0: next tile number from the ticket, its copies (or a bare arrival: no tile left)
+    // thread 0: the it-th tile of this CTA = next number from the ticket; its LCP box goes to stage it % SC_STAGES, its plane
+    // window to slot it % SC_PSLOTS, both signalling the stage's barrier (a bare arrival when no tile is left)
+    auto issue = [&](uint32_t it) {
+        const int stage = int(it % SC_STAGES);
         const uint32_t t = uint32_t(atomicAdd(&p.res->ticket, 1ull));
         sh.tile_of[stage] = t < num_tiles ? t : 0xffffffffu;
         if (t < num_tiles) {
-            uint8_t* dst = stages + size_t(stage) * SC_STAGE_BYTES;
             mbar_expect_tx(&sh.full_bar[stage], SC_T + (pf ? SC_PF_BYTES : 0));
-            tma_load_2d_u8(dst, &tmap, 0, int(t * (SC_T / 128)), &sh.full_bar[stage]);
-            if (pf) bulk_g2s(dst + SC_T, p.planes + uint64_t(t) * (SC_T / 64), SC_PF_BYTES, &sh.full_bar[stage]);
+            tma_load_2d_u8(stages + size_t(stage) * SC_T, &tmap, 0, int(t * (SC_T / 128)), &sh.full_bar[stage]);
+            if (pf) bulk_g2s(plane_slots + size_t(it % SC_PSLOTS) * SC_PF_STRIDE, p.planes + uint64_t(t) * (SC_T / 64), SC_PF_BYTES, &sh.full_bar[stage]);
         } else {
             mbar_arrive(&sh.full_bar[stage]);
         }
@@ -139,7 +187,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
     if (tid == 0) {
         for (int s = 0; s < SC_STAGES; ++s) mbar_init(&sh.full_bar[s], 1);
         fence_mbar_init();
-        for (int s = 0; s < SC_STAGES; ++s) issue(s);
+        for (uint32_t s = 0; s < uint32_t(SC_STAGES); ++s) issue(s);
     }
     __syncthreads();
 
@@ -147,16 +195,118 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
     unsigned long long cta_ends = 0;                // thread 0: ENDs of the tiles this CTA processed
     bool cta_any = false;                           // thread 0: one of them had an event
 
-    for (uint32_t it = 0;; ++it) {
+    // ---- P2: the records of one list window of the tile described by sh.meta[slot] (after a barrier that published lists + meta)
+    auto emit_window = [&](int slot, uint32_t win) {
+        const TileMeta& mt = sh.meta[slot];
+        const uint64_t X = mt.x_in, prefix = mt.prefix, tile_gbase = mt.tile_gbase;
+        const uint32_t adj = mt.adj, nE = mt.nE;
+        const bool carried = mt.carried != 0;
+        const uint4* pf_win = reinterpret_cast<const uint4*>(plane_slots + size_t(mt.pslot) * SC_PF_STRIDE);
+        const uint32_t cnt = nE - win < uint32_t(SC_CAP) ? nE - win : uint32_t(SC_CAP);
+        for (uint32_t i = tid; i < cnt; i += SC_THREADS) {
+            const uint32_t ent = sh.e_ent[slot][i];
+            const uint32_t e = ent & 0x3fffu, r = (ent >> 14) & 0x3fffu;
+            const uint64_t gend = tile_gbase + e;
+            const bool first_carried = carried && win + i == 0;
+            uint64_t st;
+            bool known = true;
+            if (first_carried) {
+                known = X >= OPEN_BIAS;
+                st = X - OPEN_BIAS;
+            } else {
+                st = tile_gbase + sh.s_pos[slot][i];
+            }
+            if (gend + 2 == p.n_global) p.res->end_nm2_start = known ? st + 1 : ~0ull;  // decides the post-EOF phantom
+            if (first_carried) {
+                if (!known) {  // the shard's head END: its START is in an earlier shard
+                    p.res->head_end = gend + 1;
+                    continue;
+                }
+                if (adj) continue;
+            } else if (!((ent >> 28) & 1u)) {
+                continue;
+            }
+            const uint32_t len = uint32_t(gend - st + 1) & 0xffffu;
+            const uint64_t o = prefix + r - ((carried && !first_carried) ? adj : 0u);
+            if (o < p.cap) {
+                p.out_start[o] = st;
+                p.out_len[o] = uint16_t(len);
+            } else {
+                p.res->overflow = 1;
+            }
+            acc_bases += len;
+            if (len <= uint32_t(MAX_C_LEN)) atomicAdd(&sh.hist[len], 1u);
+            const unsigned long long mark = ((o + 1) << 16) | len;
+            my_last = mark > my_last ? mark : my_last;
+            // fused BWT prefilter of find_variants (ref:clust2snp.cpp:402-429; planes.cuh): the one-popcount bound.  Fewer than
+            // mcov positions with a base code other than the first position's => at most one frequent code => the
+            // cluster cannot pass; everything else goes to the exact test (K3x).
+            if (pf && len >= 2 * p.pf_mcov && len <= uint32_t(MAX_C_LEN)) {
+                bool pass = st + PL_PAD < tile_gbase;  // the 16-bit length wrapped: the analysed range lies far before this window
+                if (!pass) {
+                    const uint64_t b_lo = st + PL_PAD - tile_gbase, b_last = b_lo + len - 1;
+                    const uint32_t q_lo = uint32_t(b_lo >> 6), q_last = uint32_t(b_last >> 6);
+                    unsigned long long f0 = 0, f1 = 0;
+                    uint32_t others = 0;
+                    for (uint32_t q = q_lo; q <= q_last; ++q) {
+                        const uint4 v = pf_win[q];
+                        const unsigned long long x0 = (uint64_t(v.y) << 32) | v.x, x1 = (uint64_t(v.w) << 32) | v.z;
+                        unsigned long long mask = ~0ull;
+                        if (q == q_lo) {
+                            mask = ~0ull << (b_lo & 63);
+                            f0 = 0ull - ((x0 >> (b_lo & 63)) & 1ull);
+                            f1 = 0ull - ((x1 >> (b_lo & 63)) & 1ull);
+                        }
+                        if (q == q_last) mask &= ~0ull >> (63 - (b_last & 63));
+                        others += __popcll(((x0 ^ f0) | (x1 ^ f1)) & mask);
+                    }
+                    pass = others >= p.pf_mcov;
+                }
+                if (pass) {
+                    const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
+                    if (at < p.pf_cap) p.pf_list[at] = SurvEntry{st, st - p.global_off, len, 0u};
+                }
+            }
+        }
+    };
+    // warp 0: records kept before the tile of sh.meta[slot] (decoupled look-back over the B words), B inclusive published
+    auto lookback_prefix = [&](int slot) {
+        __syncwarp();  // (lane 0 may have written the meta words just now)
+        TileMeta& mt = sh.meta[slot];
+        const uint32_t t = mt.tile;
+        uint64_t prefix = 0;
+        if (t > 0) {
+            int64_t j0 = int64_t(t) - 1;
+            while (true) {
+                uint64_t b;
+                int first;
+                const bool done = poll_window(p.descB, j0, lane, epoch, b, first);
+                uint64_t v = (lane <= first && j0 - lane >= 0) ? (b >> 20) & ((uint64_t(1) << 42) - 1) : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += shfl64(v, lane ^ o);
+                prefix += v;
+                if (done) break;
+                j0 -= 32;
+            }
+        }
+        if (lane == 0) {
+            desc_store_raw(p.descB + t, make_b(D_INC, prefix + mt.count, epoch));
+            mt.prefix = prefix;
+            if (t == num_tiles - 1) p.res->n_written = prefix + mt.count;  // total of kept records
+        }
+    };
+
+    bool pending = false;  // the previous tile's P2 is still to run (block-uniform)
+    uint32_t it = 0;
+    for (;; ++it) {
         const int stage = it % SC_STAGES;
         const uint32_t parity = (it / SC_STAGES) & 1;
-        const int pb = it & 1;  // buffer of the per-warp summaries
+        const int pb = it & 1;  // slot of the lists / meta / per-warp summaries
         const uint32_t t = sh.tile_of[stage];  // (written before a barrier every thread has passed since)
         if (t == 0xffffffffu) break;
         const uint64_t tile_base = uint64_t(t) * SC_T;
         const uint64_t tile_gbase = p.global_off + tile_base;
-        const uint8_t* tile = stages + size_t(stage) * SC_STAGE_BYTES;
-        const uint4* pf_win = reinterpret_cast<const uint4*>(tile + SC_T);
+        const uint8_t* tile = stages + size_t(stage) * SC_T;
         const bool interior = tile_gbase != 0 && tile_base + SC_T <= p.n_local && tile_gbase + SC_T < p.n_global;
 
         uint32_t g_prev = 0, g_next = 0;  // the bytes around the tile: issue the global loads before waiting for the tile
@@ -279,8 +429,9 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 sh.wfe[pb][warp] = fe;
             }
         }
-        __syncthreads();  // (A) per-warp summaries; every thread is done with the PREVIOUS tile (its plane window included):
-        if (tid == 0 && it > 0) issue(int((it - 1) % SC_STAGES));  // that tile's stage is refilled now
+        __syncthreads();  // (A) per-warp summaries.  Every thread has this tile's bytes in registers and is done with the tile
+        // before the previous one (its plane window included): the stage is refilled with the CTA's tile it + SC_STAGES
+        if (tid == 0) issue(it + SC_STAGES);
 
         uint32_t base = inc - pk, tot = 0;
 #pragma unroll
@@ -303,7 +454,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         const bool carried = t_fe != NO_POS && t_fe < t_fs;  // the tile's first event is an END: its START lies before the tile
         // (a START and an END at the same position: the START comes first, t_fe == t_fs is not carried)
 
-        // ---- look-back (warp 0): state entering the tile, the carried END's fate, records kept before the tile
+        // ---- warp 0: state entering the tile, the carried END's fate, B aggregate -- everything the tiles after this one wait for
         if (warp == 0) {
             // A: the state after this tile is local whenever the tile has an event
             if (lane == 0 && has_event)
@@ -314,22 +465,11 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             if (t > 0 && (carried || !has_event)) {
                 int64_t j0 = int64_t(t) - 1;
                 while (true) {
-                    const int64_t j = j0 - lane;
-                    uint64_t a = 0;
-                    bool ok = j < 0;
-                    while (true) {
-                        if (!ok) {
-                            a = desc_load(p.descA + j);
-                            ok = desc_valid(a, epoch);
-                        }
-                        if (__all_sync(FULL, ok)) break;
-                        __nanosleep(20);
-                    }
-                    const uint32_t bal = __ballot_sync(FULL, j < 0 || (a >> 62) == D_INC);
-                    if (bal) {
-                        const int src = __ffs(bal) - 1;
-                        const uint64_t av = shfl64(a, src);
-                        if (j0 - src >= 0) {
+                    uint64_t a;
+                    int first;
+                    if (poll_window(p.descA, j0, lane, epoch, a, first)) {
+                        const uint64_t av = shfl64(a, first);
+                        if (j0 - first >= 0) {
                             const uint64_t kind = (av >> 60) & 3u;
                             X = kind == A_OPEN ? OPEN_BIAS + p.global_off + ((av >> 20) & A_POS_MASK)
                                                : (kind == A_UNKNOWN ? OPEN_UNKNOWN : OPEN_NONE);
@@ -351,141 +491,75 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                     adj = int(len) >= p.min_len ? 0u : 1u;
                 }
             }
-            const uint64_t count = uint64_t(nE - nD - adj);
-            uint64_t prefix = 0;
-            if (t > 0) {
-                if (lane == 0) desc_store_raw(p.descB + t, make_b(D_AGG, count, epoch));
-                int64_t j0 = int64_t(t) - 1;
-                while (true) {
-                    const int64_t j = j0 - lane;
-                    uint64_t b = 0;
-                    bool ok = j < 0;
-                    while (true) {
-                        if (!ok) {
-                            b = desc_load(p.descB + j);
-                            ok = desc_valid(b, epoch);
-                        }
-                        if (__all_sync(FULL, ok)) break;
-                        __nanosleep(20);
-                    }
-                    const uint32_t bal = __ballot_sync(FULL, j < 0 || (b >> 62) == D_INC);
-                    const int first = bal ? __ffs(bal) - 1 : 32;
-                    uint64_t v = (lane <= first && j >= 0) ? (b >> 20) & ((uint64_t(1) << 42) - 1) : 0;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += shfl64(v, lane ^ o);
-                    prefix += v;
-                    if (bal) break;
-                    j0 -= 32;
-                }
-            }
             if (lane == 0) {
-                desc_store_raw(p.descB + t, make_b(D_INC, prefix + count, epoch));
-                sh.x_in = X;
-                sh.prefix = prefix;
-                sh.adj = adj;
+                const uint32_t count = nE - nD - adj;
+                if (t > 0) desc_store_raw(p.descB + t, make_b(D_AGG, count, epoch));
+                TileMeta& mt = sh.meta[pb];
+                mt.tile_gbase = tile_gbase;
+                mt.x_in = X;
+                mt.tile = t;
+                mt.nE = nE;
+                mt.count = count;
+                mt.adj = adj;
+                mt.carried = carried ? 1u : 0u;
+                mt.pslot = it % SC_PSLOTS;
                 cta_ends += nE;
                 cta_any |= has_event;
-                if (t == num_tiles - 1) {  // state after the whole shard, total of kept records
+                if (t == num_tiles - 1) {  // state after the whole shard
                     const uint64_t x_out = has_event ? (t_ls > t_le ? tile_gbase + uint64_t(t_ls) + OPEN_BIAS : OPEN_NONE) : X;
                     p.res->open_start = x_out >= OPEN_BIAS ? x_out - OPEN_BIAS + 1 : 0;
-                    p.res->n_written = prefix + count;
                 }
             }
         }
 
-        // ---- lists + records, one window of SC_CAP ENDs at a time (one iteration unless the tile is unusually dense)
-        for (uint32_t win = 0; win == 0 || win < nE; win += SC_CAP) {
-            if (win) __syncthreads();  // the previous window's lists are no longer read
-            if (nE) {
-                uint64_t m = S;
-                while (m) {  // a START goes to the slot of the END it pairs with: the one with as many ENDs before it
-                    const int b = __ffsll(m) - 1;
-                    m &= m - 1;
-                    const uint32_t q = baseE + __popcll(E & below(b)) - win;
-                    if (q < uint32_t(SC_CAP)) sh.s_pos[q] = uint16_t(tid * SC_V + b);
-                }
-                m = E;
-                while (m) {
-                    const int b = __ffsll(m) - 1;
-                    m &= m - 1;
-                    const uint32_t qa = baseE + __popcll(E & below(b));
-                    const uint32_t q = qa - win;
-                    if (q < uint32_t(SC_CAP)) {
-                        const uint32_t r = qa - (baseD + __popcll(D & below(b)));
-                        sh.e_ent[q] = uint32_t(tid * SC_V + b) | (r << 14) | ((uint32_t((D >> b) & 1u) ^ 1u) << 28);
-                    }
+        // ---- lists of the tile's first SC_CAP ENDs (all of them unless the tile is unusually dense)
+        auto scatter = [&](uint32_t win) {
+            uint64_t m = S;
+            while (m) {  // a START goes to the slot of the END it pairs with: the one with as many ENDs before it
+                const int b = __ffsll(m) - 1;
+                m &= m - 1;
+                const uint32_t q = baseE + __popcll(E & below(b)) - win;
+                if (q < uint32_t(SC_CAP)) sh.s_pos[pb][q] = uint16_t(tid * SC_V + b);
+            }
+            m = E;
+            while (m) {
+                const int b = __ffsll(m) - 1;
+                m &= m - 1;
+                const uint32_t qa = baseE + __popcll(E & below(b));
+                const uint32_t q = qa - win;
+                if (q < uint32_t(SC_CAP)) {
+                    const uint32_t r = qa - (baseD + __popcll(D & below(b)));
+                    sh.e_ent[pb][q] = uint32_t(tid * SC_V + b) | (r << 14) | ((uint32_t((D >> b) & 1u) ^ 1u) << 28);
                 }
             }
-            __syncthreads();  // (B) lists, x_in / prefix / adj
-            const uint64_t X = sh.x_in, prefix = sh.prefix;
-            const uint32_t adj = sh.adj;
-            const uint32_t cnt = nE - win < uint32_t(SC_CAP) ? nE - win : uint32_t(SC_CAP);
-            for (uint32_t i = tid; i < cnt; i += SC_THREADS) {
-                const uint32_t ent = sh.e_ent[i];
-                const uint32_t e = ent & 0x3fffu, r = (ent >> 14) & 0x3fffu;
-                const uint64_t gend = tile_gbase + e;
-                const bool first_carried = carried && win + i == 0;
-                uint64_t st;
-                bool known = true;
-                if (first_carried) {
-                    known = X >= OPEN_BIAS;
-                    st = X - OPEN_BIAS;
-                } else {
-                    st = tile_gbase + sh.s_pos[i];
-                }
-                if (gend + 2 == p.n_global) p.res->end_nm2_start = known ? st + 1 : ~0ull;  // decides the post-EOF phantom
-                if (first_carried) {
-                    if (!known) {  // the shard's head END: its START is in an earlier shard
-                        p.res->head_end = gend + 1;
-                        continue;
-                    }
-                    if (adj) continue;
-                } else if (!((ent >> 28) & 1u)) {
-                    continue;
-                }
-                const uint32_t len = uint32_t(gend - st + 1) & 0xffffu;
-                const uint64_t o = prefix + r - ((carried && !first_carried) ? adj : 0u);
-                if (o < p.cap) {
-                    p.out_start[o] = st;
-                    p.out_len[o] = uint16_t(len);
-                } else {
-                    p.res->overflow = 1;
-                }
-                acc_bases += len;
-                if (len <= uint32_t(MAX_C_LEN)) atomicAdd(&sh.hist[len], 1u);
-                const unsigned long long mark = ((o + 1) << 16) | len;
-                my_last = mark > my_last ? mark : my_last;
-                // fused BWT prefilter of find_variants (ref:clust2snp.cpp:402-429; planes.cuh): the one-popcount bound.  Fewer than
-                // mcov positions with a base code other than the first position's => at most one frequent code => the
-                // cluster cannot pass; everything else goes to the exact test (K3x).
-                if (pf && len >= 2 * p.pf_mcov && len <= uint32_t(MAX_C_LEN)) {
-                    bool pass = st + PL_PAD < tile_gbase;  // the 16-bit length wrapped: the analysed range lies far before this window
-                    if (!pass) {
-                        const uint64_t b_lo = st + PL_PAD - tile_gbase, b_last = b_lo + len - 1;
-                        const uint32_t q_lo = uint32_t(b_lo >> 6), q_last = uint32_t(b_last >> 6);
-                        unsigned long long f0 = 0, f1 = 0;
-                        uint32_t others = 0;
-                        for (uint32_t q = q_lo; q <= q_last; ++q) {
-                            const uint4 v = pf_win[q];
-                            const unsigned long long x0 = (uint64_t(v.y) << 32) | v.x, x1 = (uint64_t(v.w) << 32) | v.z;
-                            unsigned long long mask = ~0ull;
-                            if (q == q_lo) {
-                                mask = ~0ull << (b_lo & 63);
-                                f0 = 0ull - ((x0 >> (b_lo & 63)) & 1ull);
-                                f1 = 0ull - ((x1 >> (b_lo & 63)) & 1ull);
-                            }
-                            if (q == q_last) mask &= ~0ull >> (63 - (b_last & 63));
-                            others += __popcll(((x0 ^ f0) | (x1 ^ f1)) & mask);
-                        }
-                        pass = others >= p.pf_mcov;
-                    }
-                    if (pass) {
-                        const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
-                        if (at < p.pf_cap) p.pf_list[at] = o;
-                    }
-                }
-            }
+        };
+        scatter(0);
+
+        // ---- P2 of the previous tile: its aggregate and ours are out, now this CTA may wait
+        if (pending) {
+            if (warp == 0) lookback_prefix(pb ^ 1);
+            __syncthreads();  // (B) prefix of the previous tile (its lists and meta were published by barrier (A) above)
+            emit_window(pb ^ 1, 0);
         }
+        pending = true;
+        if (nE > uint32_t(SC_CAP)) {  // (block-uniform, rare) more ENDs than one list window holds: finish this tile here, window by window
+            if (warp == 0) lookback_prefix(pb);
+            __syncthreads();
+            emit_window(pb, 0);
+            for (uint32_t win = SC_CAP; win < nE; win += SC_CAP) {
+                __syncthreads();  // the previous window's lists are no longer read
+                scatter(win);
+                __syncthreads();
+                emit_window(pb, win);
+            }
+            pending = false;
+        }
+    }
+    if (pending) {  // P2 of the CTA's last tile (the loop left at iteration `it`: that tile's slot is the other one)
+        const int slot = int((it - 1) & 1);
+        if (warp == 0) lookback_prefix(slot);
+        __syncthreads();
+        emit_window(slot, 0);
     }
 
     // ---- per-CTA totals
@@ -549,7 +623,7 @@ cudaError_t launch_scan(const Scan8Params& p0, uint64_t alloc_r, int sm_count, c
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    const size_t smem = size_t(SC_STAGES) * SC_STAGE_BYTES + 1024;
+    const size_t smem = size_t(SC_DYN_SMEM);
     static int occ_dev[64] = {0};  // function attributes are per device
     int dev = 0;
     cudaGetDevice(&dev);

@@ -1,7 +1,6 @@
 // Phase 2 (clust2snp): per-cluster analysis and SNP/indel calling.
 //
 //   k_len_hist       statistics(): length histogram                      ref:clust2snp.cpp:889-909
-//   k_bwt_planes     seal-time: resident bit planes of the 2-bit base code of every BWT byte (planes.cuh)
 //   k_code_scan      K3a: exact prefilter of find_variants on the BWT base codes alone.  A cluster whose
 //                    records show at most ONE base code (base_to_int, ref:include.hpp:265-279) with
 //                    >= mcov_out occurrences over both samples cannot pass ref:clust2snp.cpp:402-429:
@@ -100,40 +99,10 @@ struct ScanParams {
     uint64_t limit;              // records with global_off <= start < global_off + limit are analysed
     uint32_t min_len, max_len;   // 2*mcov_out, max_clust_length
     uint32_t mcov;
-    uint64_t* survivors;         // out: clusters that need the exact test (unordered; dev->n_survivors counts them)
+    SurvEntry* survivors;        // out: clusters that need the exact test (unordered; dev->n_survivors counts them)
     uint64_t cap_surv;
     SnpDev* dev;
 };
-
-// Runs once when a shard is sealed: the two bit planes of the base code of every byte of the padded BWT array
-// (layout in planes.cuh).  One thread per 64 positions; exact for every byte value (case-folded equality tests).
-__global__ void __launch_bounds__(256) k_bwt_planes(const uint8_t* __restrict__ bwt_a, uint64_t n_quads, uint4* __restrict__ planes) {
-    for (uint64_t q = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < n_quads; q += uint64_t(gridDim.x) * blockDim.x) {
-        // quad q = local positions [64 q - PL_PAD, +64) = bytes [64 q - (PL_PAD - PAD_L), +64) of bwt_a
-        const int64_t byte0 = int64_t(q) * 64 - (PL_PAD - PAD_L);
-        uint32_t w[4] = {0, 0, 0, 0};  // plane0 lo, plane0 hi, plane1 lo, plane1 hi
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int64_t b = byte0 + 16 * c;
-            if (b < 0) continue;  // before the allocation (the first PL_PAD - PAD_L positions): code 0
-            const uint4 v = *reinterpret_cast<const uint4*>(bwt_a + b);
-            const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t code = base_code((x[j >> 2] >> (8 * (j & 3))) & 0xffu);
-                const int bit = 16 * c + j;
-                w[bit >> 5] |= (code & 1u) << (bit & 31);
-                w[2 + (bit >> 5)] |= (code >> 1) << (bit & 31);
-            }
-        }
-        planes[q] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-}
-
-cudaError_t launch_bwt_planes(const uint8_t* bwt_a, uint64_t alloc_r, uint4* planes, cudaStream_t stream, int sm_count) {
-    k_bwt_planes<<<unsigned(sm_count) * 8, 256, 0, stream>>>(bwt_a, plane_quads(alloc_r), planes);
-    return cudaGetLastError();
-}
 
 // One thread per cluster record: total count of each base code by range popcounts on the planes (0.25 B/position,
 // 16-byte loads that neighbouring threads share through L1) + the 10-byte record.
@@ -165,7 +134,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
             if (frequent_codes<true>(p.a.planes, int64_t(st[u] - p.a.global_off), ln[u], p.mcov, &q0[u]) >= 2) {
                 // rare (variants, repeats): plain atomic append, the exact test does not need an order
                 const unsigned long long at = atomicAdd(&p.dev->n_survivors, 1ull);
-                if (at < p.cap_surv) p.survivors[at] = c0 + uint64_t(u) * PS_THREADS;
+                if (at < p.cap_surv) p.survivors[at] = SurvEntry{st[u], st[u] - p.a.global_off, ln[u], 0u};
             }
         }
     }
@@ -182,14 +151,15 @@ constexpr int EX_G = 8;  // lanes per cluster
 
 struct ExactParams {
     SnpArrays a;
-    const uint64_t* list;      // cluster indices to test
+    const SurvEntry* list;     // clusters to test
     const unsigned long long* n_list;  // device-resident length of the list; null: n_list_host
     uint64_t n_list_host;
     uint64_t cap_list;         // capacity of the list (the pass is repeated when it was too small)
     uint32_t min_len, max_len; // 2 * mcov_out, max_clust_length (a fused prefilter only knew max_len <= 150)
+    const int32_t* d_max_len;  // != null: max_clust_length comes from device memory (the merge kernel wrote it)
     uint32_t mcov, k_right;
     uint32_t nr1_lo, nr1_big;
-    uint64_t* flagged;         // out: clusters that pass the find_variants filters, unordered (dev->n_flagged counts them)
+    SurvEntry* flagged;        // out: clusters that pass the find_variants filters, unordered (dev->n_flagged counts them)
     uint64_t cap_flagged;
     SnpDev* dev;
 };
@@ -201,12 +171,13 @@ __global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
     const uint64_t n_avail = p.n_list ? *p.n_list : p.n_list_host;
     const uint64_t n_list = n_avail < p.cap_list ? n_avail : p.cap_list;
     const uint64_t groups = uint64_t(gridDim.x) * (EX_THREADS / EX_G);
+    const uint32_t max_len = p.d_max_len ? uint32_t(*p.d_max_len) : p.max_len;
     uint32_t saw_n = 0;
     for (uint64_t i = (uint64_t(blockIdx.x) * EX_THREADS + threadIdx.x) / EX_G; i < n_list; i += groups) {
-        const uint64_t ci = p.list[i];
-        const uint64_t lp = p.a.cl_start[ci] - p.a.global_off;
-        const uint32_t len = p.a.cl_len[ci];
-        if (len < p.min_len || len > p.max_len) continue;  // group-uniform
+        const SurvEntry ent = p.list[i];
+        const uint64_t lp = ent.base;
+        const uint32_t len = ent.len;
+        if (len < p.min_len || len > max_len) continue;  // group-uniform
         unsigned long long acc = 0, best = 0;
         for (uint32_t j = gl; j < len; j += EX_G) {
             const uint32_t tx = p.a.text[lp + j];
@@ -234,7 +205,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
             const bool ok = f0 && f1 && __popc(f0) <= 2 && __popc(f1) <= 2 && f0 != f1 && __popc(f0 | f1) <= 3;
             if (ok) {
                 const unsigned long long at = atomicAdd(&p.dev->n_flagged, 1ull);
-                if (at < p.cap_flagged) p.flagged[at] = ci;  // the host compares the count with the capacity and retries
+                if (at < p.cap_flagged) p.flagged[at] = ent;  // the host compares the count with the capacity and retries
             }
         }
     }
@@ -246,7 +217,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
 // ---------------------------------------------------------------------------------------------
 struct CandParams {
     SnpArrays a;
-    const uint64_t* flagged;  // cluster indices, ascending
+    const SurvEntry* flagged;  // clusters that passed the exact test
     const unsigned long long* n_flagged;  // device-resident length of the list
     uint32_t mcov, k_left, k_right, cap;  // cap = min(consensus_reads, 150)
     uint32_t nr1_lo, nr1_big;
@@ -264,10 +235,10 @@ __global__ void __launch_bounds__(128) k_candidates(CandParams p) {
     if (n_f > p.cap_flagged) n_f = p.cap_flagged;  // overflow is reported by the host, which retries with more room
     const uint64_t warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
     for (uint64_t f = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; f < n_f; f += warps) {
-    const uint64_t ci = p.flagged[f];
-    const uint64_t start = p.a.cl_start[ci];
-    const uint32_t len = p.a.cl_len[ci];
-    const uint64_t lp = start - p.a.global_off;  // local position
+    const SurvEntry ent = p.flagged[f];
+    const uint64_t start = ent.start;
+    const uint32_t len = ent.len;
+    const uint64_t lp = ent.base;  // first record of the cluster in the arrays
     const uint32_t* text = p.a.text + lp;
     const uint32_t* lcp = p.a.lcp + lp;
     const uint32_t* suff = p.a.suff + lp;
@@ -578,8 +549,9 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
 // ---------------------------------------------------------------------------------------------
 struct SnpWork {
     uint8_t* zero_blk = nullptr; size_t zero_cap = 0;  // everything a pass needs zeroed, in one block: one memset
-    uint64_t* survivors = nullptr; size_t survivors_cap = 0;
-    uint64_t* flagged = nullptr; size_t flagged_cap = 0;
+    SurvEntry* survivors = nullptr; size_t survivors_cap = 0;
+    SurvEntry* flagged = nullptr; size_t flagged_cap = 0;
+    uint64_t cap_surv_used = 0, cap_flag_used = 0;          // capacities of the pass in flight (snp_collect compares the counters with them)
     CandSlot* slots = nullptr; size_t slots_cap = 0;
     uint32_t* slot_text = nullptr; uint32_t* slot_pos = nullptr; size_t slot_list_cap = 0;
     uint64_t* cand = nullptr; size_t cand_cap = 0;
@@ -618,164 +590,157 @@ static cudaError_t ensure(T*& ptr, size_t& cap, size_t need) {
 
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { *err = #x; return _e; } } while (0)
 
-cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int max_clust_length,
-                    const uint8_t* d_read_bases, const uint64_t* d_read_off, uint64_t n_reads, int sm_count,
-                    cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err,
-                    KernelTimer* timer, const uint64_t* pre_list, uint64_t pre_count) {
-    memset(counts, 0, sizeof *counts);
-    w->n_cand = 0;
-    w->k_left = p.k_left;
-    w->k_right = p.k_right;
-    if (!w->h_dev) CK(cudaHostAlloc(reinterpret_cast<void**>(&w->h_dev), sizeof(SnpDev), cudaHostAllocDefault));
-    if (a.m == 0 || a.n_local == 0) return cudaSuccess;
-
+// One pass of K3a / K3x / K3b / K4 with the current capacity guesses, enqueued on the stream together with the copy of the
+// device counters to pinned host memory.  No synchronisation.
+static cudaError_t snp_enqueue(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int max_clust_length,
+                               const uint8_t* d_read_bases, const uint64_t* d_read_off, uint64_t n_reads, int sm_count,
+                               cudaStream_t stream, uint64_t* launches, const char** err, KernelTimer* timer,
+                               const SurvEntry* pre_list, uint64_t pre_count, const unsigned long long* d_pre_count,
+                               const int32_t* d_max_len) {
     const uint32_t nr1_big = p.nr_reads1 > 0xffffffffull ? 1u : 0u;
     const uint32_t nr1_lo = nr1_big ? 0xffffffffu : uint32_t(p.nr_reads1);
     const uint32_t num_tiles = uint32_t((a.n_local + PS_T - 1) / PS_T);
     const uint32_t cap = uint32_t(p.consensus_reads < MAX_C_LEN ? p.consensus_reads : MAX_C_LEN);
     w->stride = uint32_t((sizeof(PackedEventHdr) + 2 * size_t(p.k_left) + size_t(p.k_right) + 15) & ~size_t(15));
-
-    // first guesses: clusters with two frequent base codes are variants and repeats, a small fraction of all
-    if (!w->want_survivors) w->want_survivors = a.m / 64 + 4096;
-    if (!w->want_flagged) w->want_flagged = a.m / 256 + 2048;
-    if (const char* dbg = getenv("E2S_SNP_FIRST_CAPACITY")) {  // test hook: start from a tiny guess to exercise the retry path
-        const uint64_t v = strtoull(dbg, nullptr, 10);
-        if (v) w->want_survivors = w->want_flagged = v;
+    // on the fused path (pre_list) the survivor list is the caller's: the flagged list is bounded by ITS capacity, not by the
+    // capacity guess of a K3a pass that does not run (the retry could otherwise never grow past that guess)
+    const uint64_t cap_surv = pre_list ? (pre_count ? pre_count : 1) : (w->want_survivors < a.m ? w->want_survivors : a.m);
+    const uint64_t cap_flag = w->want_flagged < cap_surv ? w->want_flagged : cap_surv;
+    w->cap_surv_used = cap_surv;
+    w->cap_flag_used = cap_flag;
+    const uint64_t n_slots = cap_flag * 4;
+    if (!pre_list) CK(ensure(w->survivors, w->survivors_cap, size_t(cap_surv)));
+    CK(ensure(w->flagged, w->flagged_cap, size_t(cap_flag)));
+    CK(ensure(w->slots, w->slots_cap, size_t(n_slots)));
+    if (size_t(n_slots) * 2 * cap > w->slot_list_cap || !w->slot_text) {
+        cudaFree(w->slot_text); cudaFree(w->slot_pos);
+        w->slot_text = w->slot_pos = nullptr;
+        w->slot_list_cap = 0;
+        const size_t n = size_t(n_slots) * 2 * cap;
+        CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_text), n * 4));
+        CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_pos), n * 4));
+        w->slot_list_cap = n;
+    }
+    CK(ensure(w->zero_blk, w->zero_cap, sizeof(SnpDev)));  // the device counters: the one thing a pass needs zeroed
+    w->dev = reinterpret_cast<SnpDev*>(w->zero_blk);
+    CK(cudaMemsetAsync(w->zero_blk, 0, sizeof(SnpDev), stream));
+    CK(ensure(w->cand, w->cand_cap, size_t(n_slots)));
+    if (size_t(n_slots) * w->stride > w->h_events_cap) {
+        cudaFreeHost(w->h_events);
+        w->h_events = nullptr;
+        w->h_events_cap = 0;
+        const size_t bytes = size_t(n_slots) * w->stride;
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&w->h_events), bytes, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&w->d_events), w->h_events, 0));
+        w->h_events_cap = bytes;
     }
 
-    SnpDev& hd = *w->h_dev;
-    for (int attempt = 0;; ++attempt) {
-        // on the fused path (pre_list) the survivor list is the caller's: the flagged list is bounded by ITS length, not
-        // by the capacity guess of a K3a pass that does not run (the retry could otherwise never grow past that guess)
-        const uint64_t cap_surv = pre_list ? (pre_count ? pre_count : 1) : (w->want_survivors < a.m ? w->want_survivors : a.m);
-        const uint64_t cap_flag = w->want_flagged < cap_surv ? w->want_flagged : cap_surv;
-        const uint64_t n_slots = cap_flag * 4;
-        if (!pre_list) CK(ensure(w->survivors, w->survivors_cap, size_t(cap_surv)));
-        CK(ensure(w->flagged, w->flagged_cap, size_t(cap_flag)));
-        CK(ensure(w->slots, w->slots_cap, size_t(n_slots)));
-        if (size_t(n_slots) * 2 * cap > w->slot_list_cap || !w->slot_text) {
-            cudaFree(w->slot_text); cudaFree(w->slot_pos);
-            w->slot_text = w->slot_pos = nullptr;
-            w->slot_list_cap = 0;
-            const size_t n = size_t(n_slots) * 2 * cap;
-            CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_text), n * 4));
-            CK(cudaMalloc(reinterpret_cast<void**>(&w->slot_pos), n * 4));
-            w->slot_list_cap = n;
-        }
-        CK(ensure(w->zero_blk, w->zero_cap, sizeof(SnpDev)));  // the device counters: the one thing a pass needs zeroed
-        w->dev = reinterpret_cast<SnpDev*>(w->zero_blk);
-        CK(cudaMemsetAsync(w->zero_blk, 0, sizeof(SnpDev), stream));
-        CK(ensure(w->cand, w->cand_cap, size_t(n_slots)));
-        if (size_t(n_slots) * w->stride > w->h_events_cap) {
-            cudaFreeHost(w->h_events);
-            w->h_events = nullptr;
-            w->h_events_cap = 0;
-            const size_t bytes = size_t(n_slots) * w->stride;
-            CK(cudaHostAlloc(reinterpret_cast<void**>(&w->h_events), bytes, cudaHostAllocMapped));
-            CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&w->d_events), w->h_events, 0));
-            w->h_events_cap = bytes;
-        }
+    if (!pre_list) {   // K3a: base-code prefilter on the resident bit planes
+        ScanParams sp;
+        sp.a = a;
+        sp.limit = uint64_t(num_tiles) * PS_T;
+        sp.min_len = uint32_t(2 * p.mcov_out);
+        sp.max_len = uint32_t(max_clust_length);
+        sp.mcov = uint32_t(p.mcov_out);
+        sp.survivors = w->survivors;
+        sp.cap_surv = cap_surv;
+        sp.dev = w->dev;
+        uint64_t grid = (a.m + PS_THREADS * PS_U - 1) / (PS_THREADS * PS_U);
+        if (grid > uint64_t(sm_count) * 16) grid = uint64_t(sm_count) * 16;
+        if (timer) timer->begin(E2S_KERNEL_SCAN, stream);
+        k_code_scan<<<unsigned(grid), PS_THREADS, 0, stream>>>(sp);
+        if (timer) timer->end(stream);
+        CK(cudaGetLastError());
+        ++*launches;
+    }
+    {   // K3x: exact filters on the survivors
+        ExactParams ep;
+        ep.a = a;
+        ep.list = pre_list ? pre_list : w->survivors;
+        ep.n_list = pre_list ? d_pre_count : &w->dev->n_survivors;
+        ep.n_list_host = pre_count;
+        ep.cap_list = pre_list ? pre_count : cap_surv;
+        ep.min_len = uint32_t(2 * p.mcov_out);
+        ep.max_len = uint32_t(max_clust_length);
+        ep.d_max_len = d_max_len;
+        ep.mcov = uint32_t(p.mcov_out);
+        ep.k_right = uint32_t(p.k_right);
+        ep.nr1_lo = nr1_lo;
+        ep.nr1_big = nr1_big;
+        ep.flagged = w->flagged;
+        ep.cap_flagged = cap_flag;
+        ep.dev = w->dev;
+        if (timer) timer->begin(E2S_KERNEL_EXACT, stream);
+        k_cluster_exact<<<unsigned(sm_count) * 8, EX_THREADS, 0, stream>>>(ep);
+        if (timer) timer->end(stream);
+        CK(cudaGetLastError());
+        ++*launches;
+    }
+    // Flagged clusters, their candidate slots and the events come out in whatever order the atomics give: the
+    // reference's order (eBWT position, then allele pair) is restored from (cluster_start, pair) when the events are
+    // fetched (snp_fetch_events), so the step needs no ordered compaction.
+    {
+        CandParams cp;
+        cp.a = a;
+        cp.flagged = w->flagged;
+        cp.n_flagged = &w->dev->n_flagged;
+        cp.cap_flagged = cap_flag;
+        cp.mcov = uint32_t(p.mcov_out);
+        cp.k_left = uint32_t(p.k_left);
+        cp.k_right = uint32_t(p.k_right);
+        cp.cap = cap;
+        cp.nr1_lo = nr1_lo;
+        cp.nr1_big = nr1_big;
+        cp.slots = w->slots;
+        cp.slot_text = w->slot_text;
+        cp.slot_pos = w->slot_pos;
+        cp.cand = w->cand;
+        cp.dev = w->dev;
+        uint64_t blocks = (cap_flag + 3) / 4;
+        if (blocks > uint64_t(sm_count) * 16) blocks = uint64_t(sm_count) * 16;
+        k_candidates<<<unsigned(blocks), 128, 0, stream>>>(cp);
+        CK(cudaGetLastError());
+        EventParams ep;
+        ep.slots = w->slots;
+        ep.slot_text = w->slot_text;
+        ep.slot_pos = w->slot_pos;
+        ep.cand = w->cand;
+        ep.n_cand = &w->dev->n_slots_valid;
+        ep.cap = cap;
+        ep.k_left = p.k_left;
+        ep.k_right = p.k_right;
+        ep.max_gap = p.max_gap;
+        ep.max_err = p.max_err;
+        ep.max_snvs = p.max_snvs;
+        ep.bases = d_read_bases;
+        ep.off = d_read_off;
+        ep.n_reads = n_reads;
+        ep.out = w->d_events;
+        ep.stride = w->stride;
+        ep.dev = w->dev;
+        uint64_t eblocks = (n_slots + EV_WARPS - 1) / EV_WARPS;
+        if (eblocks > uint64_t(sm_count) * 16) eblocks = uint64_t(sm_count) * 16;
+        k_events<<<unsigned(eblocks), EV_WARPS * 32, 0, stream>>>(ep);
+        CK(cudaGetLastError());
+        *launches += 2;
+    }
+    CK(cudaMemcpyAsync(w->h_dev, w->dev, sizeof(SnpDev), cudaMemcpyDeviceToHost, stream));
+    return cudaSuccess;
+}
 
-
-        if (!pre_list) {   // K3a: base-code prefilter on the resident bit planes
-            ScanParams sp;
-            sp.a = a;
-            sp.limit = uint64_t(num_tiles) * PS_T;
-            sp.min_len = uint32_t(2 * p.mcov_out);
-            sp.max_len = uint32_t(max_clust_length);
-            sp.mcov = uint32_t(p.mcov_out);
-            sp.survivors = w->survivors;
-            sp.cap_surv = cap_surv;
-            sp.dev = w->dev;
-            uint64_t grid = (a.m + PS_THREADS * PS_U - 1) / (PS_THREADS * PS_U);
-            if (grid > uint64_t(sm_count) * 16) grid = uint64_t(sm_count) * 16;
-            if (timer) timer->begin(E2S_KERNEL_SCAN, stream);
-            k_code_scan<<<unsigned(grid), PS_THREADS, 0, stream>>>(sp);
-            if (timer) timer->end(stream);
-            CK(cudaGetLastError());
-            ++*launches;
-        }
-        {   // K3x: exact filters on the survivors
-            ExactParams ep;
-            ep.a = a;
-            ep.list = pre_list ? pre_list : w->survivors;
-            ep.n_list = pre_list ? nullptr : &w->dev->n_survivors;
-            ep.n_list_host = pre_count;
-            ep.cap_list = pre_list ? pre_count : cap_surv;
-            ep.min_len = uint32_t(2 * p.mcov_out);
-            ep.max_len = uint32_t(max_clust_length);
-            ep.mcov = uint32_t(p.mcov_out);
-            ep.k_right = uint32_t(p.k_right);
-            ep.nr1_lo = nr1_lo;
-            ep.nr1_big = nr1_big;
-            ep.flagged = w->flagged;
-            ep.cap_flagged = cap_flag;
-            ep.dev = w->dev;
-            if (timer) timer->begin(E2S_KERNEL_EXACT, stream);
-            k_cluster_exact<<<unsigned(sm_count) * 8, EX_THREADS, 0, stream>>>(ep);
-            if (timer) timer->end(stream);
-            CK(cudaGetLastError());
-            ++*launches;
-        }
-        // Flagged clusters, their candidate slots and the events come out in whatever order the atomics give: the
-        // reference's order (eBWT position, then allele pair) is restored from (cluster_start, pair) when the events are
-        // fetched (snp_fetch_events), so the step needs no ordered compaction.
-        {
-            CandParams cp;
-            cp.a = a;
-            cp.flagged = w->flagged;
-            cp.n_flagged = &w->dev->n_flagged;
-            cp.cap_flagged = cap_flag;
-            cp.mcov = uint32_t(p.mcov_out);
-            cp.k_left = uint32_t(p.k_left);
-            cp.k_right = uint32_t(p.k_right);
-            cp.cap = cap;
-            cp.nr1_lo = nr1_lo;
-            cp.nr1_big = nr1_big;
-            cp.slots = w->slots;
-            cp.slot_text = w->slot_text;
-            cp.slot_pos = w->slot_pos;
-            cp.cand = w->cand;
-            cp.dev = w->dev;
-            uint64_t blocks = (cap_flag + 3) / 4;
-            if (blocks > uint64_t(sm_count) * 16) blocks = uint64_t(sm_count) * 16;
-            k_candidates<<<unsigned(blocks), 128, 0, stream>>>(cp);
-            CK(cudaGetLastError());
-            EventParams ep;
-            ep.slots = w->slots;
-            ep.slot_text = w->slot_text;
-            ep.slot_pos = w->slot_pos;
-            ep.cand = w->cand;
-            ep.n_cand = &w->dev->n_slots_valid;
-            ep.cap = cap;
-            ep.k_left = p.k_left;
-            ep.k_right = p.k_right;
-            ep.max_gap = p.max_gap;
-            ep.max_err = p.max_err;
-            ep.max_snvs = p.max_snvs;
-            ep.bases = d_read_bases;
-            ep.off = d_read_off;
-            ep.n_reads = n_reads;
-            ep.out = w->d_events;
-            ep.stride = w->stride;
-            ep.dev = w->dev;
-            uint64_t eblocks = (n_slots + EV_WARPS - 1) / EV_WARPS;
-            if (eblocks > uint64_t(sm_count) * 16) eblocks = uint64_t(sm_count) * 16;
-            k_events<<<unsigned(eblocks), EV_WARPS * 32, 0, stream>>>(ep);
-            CK(cudaGetLastError());
-            *launches += 2;
-        }
-        CK(cudaMemcpyAsync(&hd, w->dev, sizeof hd, cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));  // the only synchronisation of the pass
-        if (hd.n_survivors <= cap_surv && hd.n_flagged <= cap_flag) break;
-        if (attempt >= 2) { *err = "phase 2 capacity did not converge"; return cudaErrorUnknown; }
+// After the stream has been synchronised: the counters of the pass.  false + *rc == cudaSuccess: a capacity guess was too
+// small (the guesses have been raised: run the pass again); false + *rc != cudaSuccess: the pass failed.
+bool snp_collect(SnpWork* w, e2s_snp_counts* counts, const char** err, cudaError_t* rc) {
+    *rc = cudaSuccess;
+    const SnpDev& hd = *w->h_dev;
+    const uint64_t cap_surv = w->cap_surv_used, cap_flag = w->cap_flag_used;
+    if (hd.n_survivors > cap_surv || hd.n_flagged > cap_flag) {
         if (hd.n_survivors > cap_surv) w->want_survivors = hd.n_survivors + hd.n_survivors / 8 + 1024;
         // flagged clusters are a subset of the survivors; when the survivor list overflowed the flagged count is a lower bound
-        if (hd.n_flagged > cap_flag || hd.n_survivors > cap_surv) {
-            uint64_t guess = hd.n_flagged + hd.n_flagged / 8 + 1024;
-            if (hd.n_survivors > cap_surv) guess = guess * (hd.n_survivors / cap_surv + 1);
-            if (guess > w->want_flagged) w->want_flagged = guess;
-        }
+        uint64_t guess = hd.n_flagged + hd.n_flagged / 8 + 1024;
+        if (hd.n_survivors > cap_surv) guess = guess * (hd.n_survivors / cap_surv + 1);
+        if (guess > w->want_flagged) w->want_flagged = guess;
+        return false;
     }
     counts->n_analysed = hd.n_analysed;
     counts->n_flagged = hd.n_flagged;
@@ -783,9 +748,48 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
     counts->n_variants = hd.n_variants;
     counts->n_events = hd.n_events;
     counts->saw_n = hd.saw_n;
-    if (hd.bad_ref) { *err = "a candidate references a read/offset outside the staged reads"; return cudaErrorInvalidValue; }
+    if (hd.bad_ref) {
+        *err = "a candidate references a read/offset outside the staged reads";
+        *rc = cudaErrorInvalidValue;
+        return false;
+    }
     w->n_cand = hd.n_slots_valid;
-    return cudaSuccess;
+    return true;
+}
+
+cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int max_clust_length,
+                    const uint8_t* d_read_bases, const uint64_t* d_read_off, uint64_t n_reads, int sm_count,
+                    cudaStream_t stream, e2s_snp_counts* counts, uint64_t* launches, const char** err,
+                    KernelTimer* timer, const SurvEntry* pre_list, uint64_t pre_count, const unsigned long long* d_pre_count,
+                    const int32_t* d_max_len, bool sync) {
+    memset(counts, 0, sizeof *counts);
+    w->n_cand = 0;
+    w->k_left = p.k_left;
+    w->k_right = p.k_right;
+    if (!w->h_dev) CK(cudaHostAlloc(reinterpret_cast<void**>(&w->h_dev), sizeof(SnpDev), cudaHostAllocDefault));
+    memset(w->h_dev, 0, sizeof(SnpDev));
+    w->cap_surv_used = w->cap_flag_used = 0;
+    if (!pre_list && (a.m == 0 || a.n_local == 0)) return cudaSuccess;
+
+    // first guesses: clusters with two frequent base codes are variants and repeats, a small fraction of all
+    const uint64_t m_guess = a.m ? a.m : a.n_local / 32 + 1;
+    if (!w->want_survivors) w->want_survivors = m_guess / 64 + 4096;
+    if (!w->want_flagged) w->want_flagged = m_guess / 256 + 2048;
+    if (const char* dbg = getenv("E2S_SNP_FIRST_CAPACITY")) {  // test hook: start from a tiny guess to exercise the retry path
+        const uint64_t v = strtoull(dbg, nullptr, 10);
+        if (v) w->want_survivors = w->want_flagged = v;
+    }
+    for (int attempt = 0;; ++attempt) {
+        cudaError_t e = snp_enqueue(w, a, p, max_clust_length, d_read_bases, d_read_off, n_reads, sm_count, stream, launches, err, timer,
+                                    pre_list, pre_count, d_pre_count, d_max_len);
+        if (e != cudaSuccess) return e;
+        if (!sync) return cudaSuccess;  // the caller synchronises and calls snp_collect (and snp_run again if a guess was too small)
+        CK(cudaStreamSynchronize(stream));  // the only synchronisation of the pass
+        cudaError_t rc;
+        if (snp_collect(w, counts, err, &rc)) return cudaSuccess;
+        if (rc != cudaSuccess) return rc;
+        if (attempt >= 3) { *err = "phase 2 capacity did not converge"; return cudaErrorUnknown; }
+    }
 }
 
 // expands the host copy of the packed candidates, keeping the variants (supp0>0 && supp1>0), in the reference's order:

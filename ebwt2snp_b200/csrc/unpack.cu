@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "planes.cuh"
 
 namespace e2s {
 
@@ -55,6 +56,120 @@ cudaError_t launch_unpack_gesa(const uint8_t* d_rec, uint64_t count, int x, int 
     uint64_t n_tiles = (count + UP_RECS - 1) / UP_RECS;
     unsigned grid = unsigned(n_tiles < 148 * 8 ? n_tiles : 148 * 8);
     k_unpack_gesa<<<grid, UP_THREADS, smem, stream>>>(d_rec, count, x, y, z, lcp, text, suff, bwt);
+    return cudaGetLastError();
+}
+
+// ---- the narrow resident copies, written by every load ---------------------------------------------
+// The two kernels that touch every position do not need the inputs at file width: the scan reads a
+// one-byte LCP (values above 127 are saturated and raise *flag when they lie in the range the scan looks at: the shard
+// then stays on the 4-byte stream), the BWT-only prefilter reads the two bit planes of the 2-bit base code.  k_derive
+// writes both for the local positions [a, b) that a load has just put in place -- the unpack kernel's or the copies'
+// output is still in L2 -- so sealing a shard costs no pass over the data.  Work unit = 16 positions; the four lanes of a
+// 64-position plane quad combine their bits by shuffles; quads only partly inside [a, b) keep their other bits.
+__device__ __forceinline__ uint32_t code_of(uint32_t c) {  // base_to_int, ref:include.hpp:265-279: ACGT/acgt -> 0..3, anything else 0
+    const uint32_t u = c & 0xDFu;
+    return uint32_t(u == 'C') + 2u * uint32_t(u == 'G') + 3u * uint32_t(u == 'T');
+}
+
+__global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp, const uint8_t* __restrict__ bwt,
+                                                uint8_t* __restrict__ lcp8, uint4* __restrict__ planes, int64_t a, int64_t b,
+                                                int64_t chk_lo, int64_t chk_hi, uint32_t* __restrict__ flag) {
+    const int64_t q_first = (a + PL_PAD) >> 6, q_last = (b - 1 + PL_PAD) >> 6;
+    const int64_t n_units = (q_last - q_first + 1) * 4;
+    const int lane = threadIdx.x & 31;
+    uint32_t bad = 0;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t u0 = int64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31); u0 < n_units; u0 += stride) {  // warp-uniform trip count
+        const int64_t u = u0 + lane;
+        const bool act = u < n_units;
+        const int64_t q = q_first + (u >> 2);
+        const int64_t x0 = q * 64 - PL_PAD + (u & 3) * 16;  // my 16 positions: [x0, x0 + 16)
+        const int64_t lo = x0 > a ? x0 : a, hi = x0 + 16 < b ? x0 + 16 : b;
+        const uint32_t cov = (act && hi > lo) ? (((1u << (hi - lo)) - 1u) << (lo - x0)) : 0u;
+        uint32_t c0 = 0, c1 = 0;
+        if (cov == 0xffffu) {
+            if (bwt) {
+                const uint4 v = *reinterpret_cast<const uint4*>(bwt + x0);
+                const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t code = code_of((xs[j >> 2] >> (8 * (j & 3))) & 0xffu);
+                    c0 |= (code & 1u) << j;
+                    c1 |= (code >> 1) << j;
+                }
+            }
+            if (lcp8) {
+                uint32_t out[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(lcp + x0 + 4 * g);
+                    const uint32_t e4[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t o = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int64_t x = x0 + 4 * g + j;
+                        if (e4[j] > 127u && x >= chk_lo && x < chk_hi) bad = 1;
+                        o |= (e4[j] > 127u ? 127u : e4[j]) << (8 * j);
+                    }
+                    out[g] = o;
+                }
+                *reinterpret_cast<uint4*>(lcp8 + x0) = make_uint4(out[0], out[1], out[2], out[3]);
+            }
+        } else if (cov) {
+            for (int64_t x = lo; x < hi; ++x) {
+                if (bwt) {
+                    const uint32_t code = code_of(bwt[x]);
+                    c0 |= (code & 1u) << (x - x0);
+                    c1 |= (code >> 1) << (x - x0);
+                }
+                if (lcp8) {
+                    const uint32_t v = lcp[x];
+                    if (v > 127u && x >= chk_lo && x < chk_hi) bad = 1;
+                    lcp8[x] = uint8_t(v > 127u ? 127u : v);
+                }
+            }
+        }
+        if (planes) {  // (kernel-uniform) the quad's four lanes -> one 16-byte store by the first of them
+            const int l0 = lane & ~3;
+            uint32_t p0lo = 0, p0hi = 0, p1lo = 0, p1hi = 0, cvlo = 0, cvhi = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t b0 = __shfl_sync(0xffffffffu, c0, l0 + k), b1 = __shfl_sync(0xffffffffu, c1, l0 + k);
+                const uint32_t cv = __shfl_sync(0xffffffffu, cov, l0 + k);
+                if (k < 2) {
+                    p0lo |= b0 << (16 * k);
+                    p1lo |= b1 << (16 * k);
+                    cvlo |= cv << (16 * k);
+                } else {
+                    p0hi |= b0 << (16 * (k - 2));
+                    p1hi |= b1 << (16 * (k - 2));
+                    cvhi |= cv << (16 * (k - 2));
+                }
+            }
+            if (act && (lane & 3) == 0 && (cvlo | cvhi)) {
+                uint4 o = make_uint4(p0lo, p0hi, p1lo, p1hi);
+                if ((cvlo & cvhi) != 0xffffffffu) {  // partly covered: the other positions keep their bits
+                    const uint4 old = planes[q];
+                    o.x = (old.x & ~cvlo) | (o.x & cvlo);
+                    o.y = (old.y & ~cvhi) | (o.y & cvhi);
+                    o.z = (old.z & ~cvlo) | (o.z & cvlo);
+                    o.w = (old.w & ~cvhi) | (o.w & cvhi);
+                }
+                planes[q] = o;
+            }
+        }
+    }
+    if (__syncthreads_or(int(bad)) && threadIdx.x == 0 && flag) atomicOr(flag, 1u);
+}
+
+// lcp / bwt / lcp8: local position 0 of the padded arrays (a >= -PAD_L).  lcp8 == null: no byte LCP (bwt == null: no planes).
+cudaError_t launch_derive(const uint32_t* lcp, const uint8_t* bwt, uint8_t* lcp8, uint4* planes, int64_t a, int64_t b,
+                          int64_t chk_lo, int64_t chk_hi, uint32_t* flag, cudaStream_t stream, int sm_count) {
+    if (b <= a || (!lcp8 && !bwt)) return cudaSuccess;
+    const int64_t n_units = (((b - 1 + PL_PAD) >> 6) - ((a + PL_PAD) >> 6) + 1) * 4;
+    int64_t blocks = (n_units + 255) / 256;
+    if (blocks > int64_t(sm_count) * 16) blocks = int64_t(sm_count) * 16;
+    k_derive<<<unsigned(blocks), 256, 0, stream>>>(lcp8 ? lcp : nullptr, bwt, lcp8, bwt ? planes : nullptr, a, b, chk_lo, chk_hi, flag);
     return cudaGetLastError();
 }
 
