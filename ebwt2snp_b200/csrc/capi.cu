@@ -68,9 +68,15 @@ struct e2s_shard {
     uint64_t flag_words = 0;
     uint64_t* d_desc = nullptr;
     size_t desc_cap = 0;
-    uint64_t* d_scan_desc = nullptr;  // k_cluster_scan: two look-back words per tile (A then B), validated by scan_epoch
-    uint64_t scan_tiles = 0;
-    uint32_t scan_epoch = 0;
+    // one-pass scan (k_cluster_scan): one chunk of tiles per CTA, each with its own segment of the record arrays
+    uint64_t* d_seg_start = nullptr;
+    uint16_t* d_seg_len = nullptr;
+    uint64_t seg_cap = 0;            // records per segment
+    uint32_t n_chunks = 0, tiles_per_chunk = 0;
+    ChunkRec* d_chunks = nullptr;    // SCAN_MAX_CHUNKS chunk summaries
+    ChunkSeg* d_segs = nullptr;      // ... and where k_chunk_resolve put each segment in the position-ordered list
+    bool contiguous = true;          // d_start / d_len hold the record list (false: it still lies in the segments)
+    bool adopt_put = false;          // the records adopted from the merge have been appended to d_start / d_len
     ClusterDev* d_res = nullptr;
     ClusterDev h_res;           // host copy of the last scan's accumulators (incl. length histogram)
     ClusterDev* h_pin = nullptr; // pinned staging for that copy
@@ -81,7 +87,7 @@ struct e2s_shard {
     // fused prefilter (pipeline mode): armed by e2s_pipeline_resident with clust2snp's -m before the scan
     uint32_t pf_arm = 0;             // mcov to use in the next e2s_cluster_run, 0 = plain scan
     uint32_t pf_mcov = 0;            // what the last scan used
-    uint64_t* d_pf_list = nullptr;
+    SurvEntry* d_pf_list = nullptr;
     uint64_t pf_cap = 0, pf_count = 0;
     bool pf_ok = false;              // the list is complete (no overflow) and belongs to the current record list
     uint4* d_planes = nullptr;       // resident base-code bit planes of the BWT (planes.cuh), built at seal
@@ -328,7 +334,10 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->d_start);
     cudaFree(s->d_len);
     cudaFree(s->d_desc);
-    cudaFree(s->d_scan_desc);
+    cudaFree(s->d_seg_start);
+    cudaFree(s->d_seg_len);
+    cudaFree(s->d_chunks);
+    cudaFree(s->d_segs);
     cudaFree(s->d_flags);
     cudaFree(s->d_packed);
     cudaFreeHost(s->h_pin);
@@ -595,6 +604,33 @@ static int ensure_records(e2s_shard* s, uint64_t cap) {
     return E2S_OK;
 }
 
+static int ensure_segments(e2s_shard* s, uint64_t seg_cap) {
+    if (seg_cap <= s->seg_cap && s->d_seg_start) return E2S_OK;
+    cudaFree(s->d_seg_start);
+    cudaFree(s->d_seg_len);
+    s->d_seg_start = nullptr;
+    s->d_seg_len = nullptr;
+    s->seg_cap = 0;
+    const size_t total = size_t(seg_cap) * s->n_chunks;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->d_seg_start), total * 8);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_seg_len), total * 2 + 16);
+    if (e != cudaSuccess) return fail(s->ctx, E2S_ERR_NOMEM, "cluster record segments");
+    s->seg_cap = seg_cap;
+    return E2S_OK;
+}
+
+// the position-ordered record list in d_start / d_len (the one-pass scan leaves it in per-chunk segments: exported on demand)
+static int ensure_contiguous(e2s_shard* s) {
+    if (s->contiguous) return E2S_OK;
+    e2s_ctx* c = s->ctx;
+    int rc = ensure_records(s, s->m_own + 8);
+    if (rc) return rc;
+    CU(c, launch_export_records(s->d_segs, s->n_chunks, s->seg_cap, s->d_seg_start, s->d_seg_len, s->d_start, s->d_len, nullptr, c->stream));
+    ++c->launches;
+    s->contiguous = true;
+    return E2S_OK;
+}
+
 int e2s_cluster_prefilter(e2s_shard* s, int mcov_out) {
     if (!s) return fail(nullptr, E2S_ERR_ARG, "shard == NULL");
     if (mcov_out < 0 || 2 * mcov_out > E2S_MAX_C_LEN) return fail(s->ctx, E2S_ERR_ARG, "e2s_cluster_prefilter: need 0 <= 2 * mcov_out <= 150");
@@ -648,13 +684,15 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
     const bool one_pass = s->sealed && s->lcp8_ok && min_len <= 33 && !getenv("E2S_SCAN_LEGACY");
     const uint64_t num_tiles = emit_num_tiles(s->n_local);
     if (one_pass) {
-        const uint64_t nt = scan_num_tiles(s->n_local);
-        if (!s->d_scan_desc || s->scan_tiles < nt) {
-            cudaFree(s->d_scan_desc);
-            s->d_scan_desc = nullptr;
-            if (cudaMalloc(reinterpret_cast<void**>(&s->d_scan_desc), nt * 2 * 8) != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "scan descriptors");
-            s->scan_tiles = nt;
-            s->scan_epoch = 0;
+        if (!s->d_chunks) {
+            CU(c, scan_plan(s->n_local, c->sm_count, &s->n_chunks, &s->tiles_per_chunk));
+            if (cudaMalloc(reinterpret_cast<void**>(&s->d_chunks), SCAN_MAX_CHUNKS * sizeof(ChunkRec)) != cudaSuccess ||
+                cudaMalloc(reinterpret_cast<void**>(&s->d_segs), SCAN_MAX_CHUNKS * sizeof(ChunkSeg)) != cudaSuccess)
+                return fail(c, E2S_ERR_NOMEM, "chunk tables");
+        }
+        if (!s->d_seg_start) {
+            int rc = ensure_segments(s, (s->n_local / 8 + 4096) / s->n_chunks + 64);
+            if (rc) return rc;
         }
     } else {
         if (!s->d_desc) {
@@ -670,7 +708,7 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
             CU(c, cudaMemsetAsync(s->d_flags, 0, s->flag_words * 2 * 4, c->stream));
         }
     }
-    if (!s->d_start) {
+    if (!one_pass && !s->d_start) {
         int rc = ensure_records(s, s->n_local / 8 + 4096);
         if (rc) return rc;
     }
@@ -713,7 +751,7 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
         p.pf_list = nullptr;
         p.pf_cap = 0;
         if (p.pf_mcov) {
-            uint64_t want = s->rec_cap / 16 + 4096;
+            uint64_t want = (one_pass ? s->seg_cap * s->n_chunks : s->rec_cap) / 16 + 4096;
             if (const char* dbg = getenv("E2S_PF_CAPACITY")) {  // test hook: a tiny list forces the overflow -> two-phase fallback
                 const uint64_t v = strtoull(dbg, nullptr, 10);
                 if (v) {
@@ -725,7 +763,7 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
                 cudaFree(s->d_pf_list);
                 s->d_pf_list = nullptr;
                 s->pf_cap = 0;
-                if (cudaMalloc(reinterpret_cast<void**>(&s->d_pf_list), (want + 8) * 8) != cudaSuccess)
+                if (cudaMalloc(reinterpret_cast<void**>(&s->d_pf_list), (want + 8) * sizeof(SurvEntry)) != cudaSuccess)
                     return fail(c, E2S_ERR_NOMEM, "prefilter survivor list");
                 s->pf_cap = want;
             }
@@ -744,10 +782,7 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
         p.tail_lcp = is_last ? s->lcp + s->n_local - 2 : nullptr;
         p.tail_bwt = is_last ? s->bwt + s->n_local - 1 : nullptr;
         if (one_pass) {
-            if (++s->scan_epoch >= (1u << 20) || s->scan_epoch == 1) {  // a fresh buffer, or the epoch wrapped: stale words must not validate
-                CU(c, cudaMemsetAsync(s->d_scan_desc, 0, s->scan_tiles * 2 * 8, c->stream));
-                if (s->scan_epoch >= (1u << 20)) s->scan_epoch = 1;
-            }
+            CU(c, cudaMemsetAsync(s->d_chunks, 0, size_t(s->n_chunks) * sizeof(ChunkRec), c->stream));
             Scan8Params sp;
             sp.lcp8 = s->lcp8_a + PAD_L;
             sp.planes = s->d_planes;
@@ -757,12 +792,12 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
             sp.k = k;
             sp.min_len = min_len;
             sp.num_tiles = 0;
-            sp.epoch = s->scan_epoch;
-            sp.descA = s->d_scan_desc;
-            sp.descB = s->d_scan_desc + s->scan_tiles;
-            sp.out_start = p.out_start;
-            sp.out_len = p.out_len;
-            sp.cap = p.cap;
+            sp.n_chunks = s->n_chunks;
+            sp.tiles_per_chunk = s->tiles_per_chunk;
+            sp.seg_start = s->d_seg_start;
+            sp.seg_len = s->d_seg_len;
+            sp.seg_cap = s->seg_cap;
+            sp.chunks = s->d_chunks;
             sp.pf_mcov = p.pf_mcov;
             sp.pf_list = p.pf_list;
             sp.pf_cap = p.pf_cap;
@@ -770,9 +805,24 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
             sp.tail_lcp = p.tail_lcp;
             sp.tail_bwt = p.tail_bwt;
             c->timer.begin(E2S_KERNEL_SCAN1, c->stream);
-            cudaError_t le = launch_scan(sp, s->alloc_r, c->sm_count, c->stream);
+            cudaError_t le = launch_scan(sp, s->alloc_r, c->stream);
             c->timer.end(c->stream);
             CU(c, le);
+            ResolveParams rp;
+            rp.chunks = s->d_chunks;
+            rp.segs = s->d_segs;
+            rp.n_chunks = s->n_chunks;
+            rp.min_len = min_len;
+            rp.global_off = s->global_off;
+            rp.n_global = s->n_global;
+            rp.init_state = s->global_off == 0 ? 0 : 1;
+            rp.planes = s->d_planes;
+            rp.pf_mcov = p.pf_mcov;
+            rp.pf_list = p.pf_list;
+            rp.pf_cap = p.pf_cap;
+            rp.res = s->d_res;
+            CU(c, launch_chunk_resolve(rp, c->stream));
+            ++c->launches;
         } else {
             c->timer.begin(E2S_KERNEL_EMIT, c->stream);
             cudaError_t le = launch_emit(p, c->sm_count, c->stream);
@@ -817,7 +867,16 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
         if (!any_overflow) break;
         if (attempt == 1) return fail(c, E2S_ERR_STATE, "record buffer overflow after resize");
         if (h.overflow || !cm) {
-            int rc = ensure_records(s, (cm ? h.n_written : max_written) + 4096);
+            int rc;
+            if (one_pass) {  // the fullest segment decides (the chunks keep counting past their capacity)
+                std::vector<ChunkRec> hc(s->n_chunks);
+                CU(c, cudaMemcpy(hc.data(), s->d_chunks, hc.size() * sizeof(ChunkRec), cudaMemcpyDeviceToHost));
+                uint64_t mx = 0;
+                for (const ChunkRec& r : hc) mx = r.own_count > mx ? r.own_count : mx;
+                rc = ensure_segments(s, mx + 64);
+            } else {
+                rc = ensure_records(s, (cm ? h.n_written : max_written) + 4096);
+            }
             if (rc) return rc;
         }
     }
@@ -844,6 +903,7 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
     s->have_scan_stats = true;
     s->m_own = h.n_written;
     s->m_list = h.n_written;
+    s->contiguous = !one_pass;
     s->have_clusters = true;
     s->staged = false;
     s->finalized = false;
@@ -953,11 +1013,8 @@ int e2s_cluster_finalize(e2s_shard* s, const e2s_cluster_merged* mg) {
     if (!s->have_clusters || s->staged) return fail(c, E2S_ERR_STATE, "e2s_cluster_finalize: run e2s_cluster_run first");
     CU(c, cudaSetDevice(c->device));
     s->merged = *mg;
-    if (mg->n_adopt) {
-        CU(c, launch_put_records(s->d_start, s->d_len, s->m_own, mg->adopt_start, mg->adopt_len, int(mg->n_adopt), c->stream));
-        ++c->launches;
-    }
-    s->m_list = s->m_own + mg->n_adopt;
+    s->m_list = s->m_own + mg->n_adopt;  // the adopted records join the device list when a pass over it needs them (find_events)
+    s->adopt_put = false;
     s->finalized = true;
     return E2S_OK;
 }
@@ -1010,6 +1067,8 @@ int e2s_cluster_fetch(e2s_shard* s, uint64_t* start, uint16_t* len, uint64_t cap
         ++o;
     }
     if (s->m_own) {
+        int rc = ensure_contiguous(s);
+        if (rc) return rc;
         CU(c, cudaMemcpyAsync(start + o, s->d_start, s->m_own * 8, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaMemcpyAsync(len + o, s->d_len, s->m_own * 2, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
@@ -1049,7 +1108,10 @@ int e2s_cluster_fetch_packed(e2s_shard* s, void* rec10, uint64_t cap, uint64_t* 
                 return fail(c, E2S_ERR_NOMEM, "packed record buffer");
             s->packed_cap = s->m_own;
         }
-        CU(c, launch_pack_records(s->d_start, s->d_len, s->m_own, s->d_packed, c->stream, c->sm_count));
+        if (s->contiguous)
+            CU(c, launch_pack_records(s->d_start, s->d_len, s->m_own, s->d_packed, c->stream, c->sm_count));
+        else  // straight from the scan's segments
+            CU(c, launch_export_records(s->d_segs, s->n_chunks, s->seg_cap, s->d_seg_start, s->d_seg_len, nullptr, nullptr, s->d_packed, c->stream));
         ++c->launches;
         CU(c, cudaMemcpyAsync(o, s->d_packed, s->m_own * 10, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
@@ -1075,6 +1137,7 @@ int e2s_clusters_stage(e2s_shard* s, const uint64_t* start, const uint16_t* len,
         CU(c, cudaStreamSynchronize(c->stream));
     }
     s->m_own = s->m_list = m;
+    s->contiguous = true;
     s->pf_ok = false;
     s->have_clusters = true;
     s->staged = true;
@@ -1243,21 +1306,33 @@ int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length,
     a.planes = s->d_planes;
     a.n_local = s->n_local;
     a.global_off = s->global_off;
+    // K2 already ran the BWT prefilter for this -m (fused mode): its survivors + the records adopted from the merge
+    // (which K2 did not see) replace K3a
+    const SurvEntry* pre_list = nullptr;
+    uint64_t pre_count = 0;
+    if (!s->staged && s->pf_ok && s->pf_mcov == uint32_t(p->mcov_out) && max_clust_length <= E2S_MAX_C_LEN) {
+        SurvEntry extra[4];
+        const uint64_t n_extra = s->merged.n_adopt;  // <= 3 records the merge created and this shard analyses
+        for (uint64_t i = 0; i < n_extra && i < 4; ++i)
+            extra[i] = SurvEntry{s->merged.adopt_start[i], s->merged.adopt_start[i] - s->global_off, uint32_t(s->merged.adopt_len[i]), 0u};
+        if (n_extra) {
+            CU(c, cudaMemcpyAsync(s->d_pf_list + s->pf_count, extra, n_extra * sizeof(SurvEntry), cudaMemcpyHostToDevice, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));  // (extra[] lives on this stack frame)
+        }
+        pre_list = s->d_pf_list;
+        pre_count = s->pf_count + n_extra;
+    } else {
+        int rc = ensure_contiguous(s);  // the two-phase path walks the record list: own records, then the adopted ones
+        if (rc) return rc;
+        if (!s->staged && s->merged.n_adopt && !s->adopt_put) {
+            CU(c, launch_put_records(s->d_start, s->d_len, s->m_own, s->merged.adopt_start, s->merged.adopt_len, int(s->merged.n_adopt), c->stream));
+            ++c->launches;
+            s->adopt_put = true;
+        }
+    }
     a.cl_start = s->d_start;
     a.cl_len = s->d_len;
     a.m = s->m_list;
-    // K2 already ran the BWT prefilter for this -m (fused mode): its survivors + the records adopted from the merge
-    // (which K2 did not see) replace K3a
-    const uint64_t* pre_list = nullptr;
-    uint64_t pre_count = 0;
-    if (!s->staged && s->pf_ok && s->pf_mcov == uint32_t(p->mcov_out) && max_clust_length <= E2S_MAX_C_LEN) {
-        uint64_t extra[4];
-        const uint64_t n_extra = s->m_list - s->m_own;  // <= 3, appended behind the shard's own records
-        for (uint64_t i = 0; i < n_extra && i < 4; ++i) extra[i] = s->m_own + i;
-        if (n_extra) CU(c, cudaMemcpyAsync(s->d_pf_list + s->pf_count, extra, n_extra * 8, cudaMemcpyHostToDevice, c->stream));
-        pre_list = s->d_pf_list;
-        pre_count = s->pf_count + n_extra;
-    }
     const char* err = "";
     cudaError_t e = snp_run(s->work, a, *p, max_clust_length, c->d_bases, c->d_off, c->n_reads, c->sm_count, c->stream,
                             counts, &c->launches, &err, &c->timer, pre_list, pre_count);

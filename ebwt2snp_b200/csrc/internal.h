@@ -87,19 +87,35 @@ struct EmitParams {  // K2
     const uint8_t* tail_bwt;   // &bwt[n_global-1]
 };
 
-struct Scan8Params {  // k_cluster_scan (scan.cu): K1 + K2 in one pass over the one-byte LCP
+// k_cluster_scan (scan.cu): K1 + K2 in one pass over the one-byte LCP, one CTA per chunk of consecutive tiles
+constexpr uint32_t SCAN_MAX_CHUNKS = 1024;
+struct ChunkRec {  // what a chunk leaves behind (zeroed before the launch)
+    unsigned long long own_count;   // records in the chunk's segment (all ENDs with a START inside the chunk, minus the short ones)
+    unsigned long long head_end;    // 1 + global position of the chunk's first event if that is an END, 0 = none
+    unsigned long long last_state;  // 0: no event in the chunk; 1: closed after it; >= 2: 2 + global START left open
+    unsigned long long n_end;       // ENDs in the chunk, head included
+    unsigned long long n_bases;     // sum of the lengths in the segment
+    unsigned long long last_len;    // length of the segment's last record
+    unsigned long long pad[2];
+};
+struct ChunkSeg {  // written by k_chunk_resolve: where the chunk's records go in the position-ordered list
+    unsigned long long off;         // index of the chunk's first record (its head record if kept, else its segment's first)
+    unsigned long long own_count;
+    unsigned long long head_start;
+    uint32_t head_len, head_kept;
+};
+struct Scan8Params {
     const uint8_t* lcp8;        // local position 0 of the byte LCP (PAD_L readable bytes before it)
     const uint4* planes;        // resident base-code bit planes (fused prefilter), may be null when pf_mcov == 0
     uint64_t n_local, global_off, n_global;
     uint32_t k;
     int32_t min_len;            // <= 33
     uint32_t num_tiles;         // filled by the launcher
-    uint32_t epoch;             // 1 .. 2^20 - 1: validates the descriptor words of THIS launch
-    uint64_t* descA;            // per tile: state after the tile
-    uint64_t* descB;            // per tile: kept-record count (aggregate, then inclusive prefix)
-    uint64_t* out_start;
-    uint16_t* out_len;
-    uint64_t cap;
+    uint32_t n_chunks, tiles_per_chunk;  // scan_plan
+    uint64_t* seg_start;        // record segments: chunk c owns [c * seg_cap, (c + 1) * seg_cap)
+    uint16_t* seg_len;
+    uint64_t seg_cap;
+    ChunkRec* chunks;
     uint32_t pf_mcov;
     SurvEntry* pf_list;
     uint64_t pf_cap;
@@ -107,8 +123,27 @@ struct Scan8Params {  // k_cluster_scan (scan.cu): K1 + K2 in one pass over the 
     const uint32_t* tail_lcp;   // &lcp[n_global-2] when this is the last shard, else null
     const uint8_t* tail_bwt;    // &bwt[n_global-1]
 };
+struct ResolveParams {  // k_chunk_resolve
+    const ChunkRec* chunks;
+    ChunkSeg* segs;
+    uint32_t n_chunks;
+    int32_t min_len;
+    uint64_t global_off, n_global;
+    uint64_t init_state;        // open-cluster state before the shard: 0 closed (eBWT start), 1 unknown (an earlier shard decides)
+    const uint4* planes;
+    uint32_t pf_mcov;
+    SurvEntry* pf_list;
+    uint64_t pf_cap;
+    ClusterDev* res;
+};
 uint64_t scan_num_tiles(uint64_t n_local);
-cudaError_t launch_scan(const Scan8Params& p, uint64_t alloc_r, int sm_count, cudaStream_t stream);
+cudaError_t scan_plan(uint64_t n_local, int sm_count, uint32_t* n_chunks, uint32_t* tiles_per_chunk);
+cudaError_t launch_scan(const Scan8Params& p, uint64_t alloc_r, cudaStream_t stream);
+cudaError_t launch_chunk_resolve(const ResolveParams& p, cudaStream_t stream);
+// segments -> contiguous: SoA (out_start / out_len) or 10-byte file records (out_packed); the other output(s) null
+cudaError_t launch_export_records(const ChunkSeg* segs, uint32_t n_chunks, uint64_t seg_cap, const uint64_t* seg_start,
+                                  const uint16_t* seg_len, uint64_t* out_start, uint16_t* out_len, uint8_t* out_packed,
+                                  cudaStream_t stream);
 
 uint64_t flags_words_needed(uint64_t n_local);
 uint64_t emit_num_tiles(uint64_t n_local);

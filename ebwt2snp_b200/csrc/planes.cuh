@@ -62,4 +62,25 @@ __device__ __forceinline__ uint32_t frequent_codes(const uint4* __restrict__ pla
     return uint32_t(nA >= mcov) + uint32_t(nC >= mcov) + uint32_t(nG >= mcov) + uint32_t(nT >= mcov);
 }
 
+// The one-popcount bound alone, on the shard's plane array in global memory: true = the cluster MAY have two frequent base
+// codes (it goes to the exact test), false = fewer than mcov of its positions differ from the first one's code.
+__device__ __forceinline__ bool frequent_bound(const uint4* __restrict__ planes, int64_t lo, uint32_t len, uint32_t mcov) {
+    const uint64_t b_lo = uint64_t(lo + PL_PAD), b_last = b_lo + len - 1;
+    unsigned long long f0 = 0, f1 = 0;
+    uint32_t others = 0;
+    for (uint64_t q = b_lo >> 6; q <= (b_last >> 6); ++q) {
+        const uint4 v = __ldg(planes + q);
+        const unsigned long long x0 = (uint64_t(v.y) << 32) | v.x, x1 = (uint64_t(v.w) << 32) | v.z;
+        unsigned long long mask = ~0ull;
+        if (q == (b_lo >> 6)) {
+            mask = ~0ull << (b_lo & 63);
+            f0 = 0ull - ((x0 >> (b_lo & 63)) & 1ull);
+            f1 = 0ull - ((x1 >> (b_lo & 63)) & 1ull);
+        }
+        if (q == (b_last >> 6)) mask &= ~0ull >> (63 - (b_last & 63));
+        others += __popcll(((x0 ^ f0) | (x1 ^ f1)) & mask);
+    }
+    return others >= mcov;
+}
+
 }  // namespace e2s

@@ -50,8 +50,8 @@ constexpr int SC_V = 64;                       // positions per thread
 constexpr int SC_T = SC_THREADS * SC_V;        // 16384 positions per tile
 constexpr int SC_W = SC_V / 4;                 // 16 packed words per thread
 constexpr int SC_STAGES = 2;                   // LCP tiles in flight / being read per CTA (a stage is free once its bytes are in registers)
-constexpr int SC_PSLOTS = 4;                   // plane windows: a tile's window lives until its records are written, one tile later
-constexpr int SC_OCC = 3;                      // resident CTAs per SM the register / shared-memory budget is sized for
+constexpr int SC_PSLOTS = SC_STAGES + 1;       // plane windows: a window is read until its tile's records are written, after the stage was refilled
+constexpr int SC_OCC = 4;                      // resident CTAs per SM the register / shared-memory budget is sized for
 constexpr int SC_PF_QUADS = SC_T / 64 + PL_PAD / 64;  // plane quads of one tile and of the PL_PAD positions before it
 constexpr int SC_PF_BYTES = SC_PF_QUADS * 16;  // 4144
 constexpr int SC_PF_STRIDE = 4224;             // slot stride (128-byte multiple)
@@ -61,23 +61,6 @@ constexpr int SC_CAP = 1024;                   // ENDs per list window (a typica
 // open-cluster state (as in cluster.cu)
 constexpr uint64_t OPEN_NONE = 0, OPEN_UNKNOWN = 1, OPEN_BIAS = 2;
 
-// descriptor words: [63:62] status  [61:20] payload  [19:0] epoch
-constexpr uint64_t D_AGG = 1, D_INC = 2;
-constexpr uint64_t D_EPOCH_MASK = (uint64_t(1) << 20) - 1;
-constexpr uint64_t A_NONE = 0, A_CLOSED = 1, A_OPEN = 2, A_UNKNOWN = 3;  // payload bits [41:40] of A; [39:0] = local START
-constexpr uint64_t A_POS_MASK = (uint64_t(1) << 40) - 1;
-
-__device__ __forceinline__ uint64_t make_a(uint64_t status, uint64_t kind, uint64_t pos, uint32_t epoch) {
-    return (status << 62) | (kind << 60) | ((pos & A_POS_MASK) << 20) | epoch;
-}
-__device__ __forceinline__ uint64_t make_b(uint64_t status, uint64_t count, uint32_t epoch) {
-    return (status << 62) | (count << 20) | epoch;
-}
-__device__ __forceinline__ bool desc_valid(uint64_t v, uint32_t epoch) { return (v & D_EPOCH_MASK) == epoch && (v >> 62) != 0; }
-
-__device__ __forceinline__ void desc_store_raw(uint64_t* d, uint64_t v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(d), "l"(v) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -96,66 +79,26 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
 }
 __device__ __forceinline__ uint64_t below(int b) { return (uint64_t(1) << b) - 1; }  // bits [0, b), b < 64
 
-// One look-back window: lane l polls desc[j0 - l] (tiles before tile 0 count as resolved) until the NEAREST resolved word
-// (status INC) is known and every word nearer than it is valid.  true: lane `first` holds that word; false: all 32 words are
-// valid aggregates (first = 32), go on with the next window.
-__device__ __forceinline__ bool poll_window(const uint64_t* desc, int64_t j0, int lane, uint32_t epoch, uint64_t& w, int& first) {
-    const int64_t j = j0 - lane;
-    w = 0;
-    bool ok = j < 0;
-    while (true) {
-        if (!ok) {
-            w = desc_load(desc + j);
-            ok = desc_valid(w, epoch);
-        }
-        const uint32_t okm = __ballot_sync(FULL, ok);
-        const uint32_t stopm = __ballot_sync(FULL, ok && (j < 0 || (w >> 62) == D_INC));
-        if (stopm) {
-            first = __ffs(stopm) - 1;
-            const uint32_t need = (1u << first) - 1u;
-            if ((okm & need) == need) return true;
-        } else if (okm == FULL) {
-            first = 32;
-            return false;
-        }
-        __nanosleep(20);
-    }
-}
-
-struct TileMeta {       // what P2 needs to know about a tile whose lists were filled by P1
-    uint64_t tile_gbase;
-    uint64_t x_in;      // open state entering the tile
-    uint64_t prefix;    // records kept before the tile (written by P2's look-back)
-    uint32_t tile;      // tile number
-    uint32_t nE;        // ENDs in the tile
-    uint32_t count;     // records it keeps
-    uint32_t adj;       // 1: the carried END is not written
-    uint32_t carried;   // the tile's first event is an END whose START lies before the tile
-    uint32_t pslot;     // plane-window slot
-};
-
 struct ScanShared {
     uint64_t full_bar[SC_STAGES];
-    uint32_t tile_of[SC_STAGES];
-    uint32_t wsum[2][SC_WARPS];   // per warp: #END | #dropped << 16 (double buffered by tile parity)
+    uint32_t wsum[2][SC_WARPS];   // per warp: #END | #dropped << 16 (double buffered by tile parity: a tile without ENDs has no barrier (B))
     int wls[2][SC_WARPS], wle[2][SC_WARPS], wfs[2][SC_WARPS], wfe[2][SC_WARPS];  // last / first START / END of the warp (tile-local)
     uint64_t wS[SC_WARPS];        // START word of the warp's last thread (min_len >= 3 only)
-    TileMeta meta[2];
+    uint64_t prev_S[2];           // [it & 1] = START word of the last thread of the chunk's tile it - 1 (min_len >= 3 only)
     unsigned int hist[E2S_HIST_BINS];
-    uint16_t s_pos[2][SC_CAP];    // [slot][q] = tile-local position of the START that pairs with the window's q-th END
-    uint32_t e_ent[2][SC_CAP];    // [slot][q] = END position | kept rank << 14 | kept << 28
+    uint16_t s_pos[SC_CAP];       // [q] = tile-local position of the START that pairs with the window's q-th END
+    uint32_t e_ent[SC_CAP];       // [q] = END position | kept rank << 14 | kept << 28
 };
 
 constexpr int NO_POS = 0x7fffffff;
 
 }  // namespace
 
-// The tile loop is software-pipelined so that no CTA ever blocks while it still owes the grid an aggregate:
-//   P1(tile)  wait for the tile, masks, ranks, lists; warp 0: publish A, resolve the state entering the tile, test the carried
-//             END, publish the kept count (B aggregate)
-//   P2(tile)  warp 0: look back over the B words -> records kept before the tile, publish B inclusive; all: write the records
-// run as P1(t0) P1(t1) P2(t0) P1(t2) P2(t1) ...: the aggregate of a CTA's NEXT tile is out before the CTA waits for the
-// prefix of its current one (with P1, P2 back to back a waiting CTA would hold up every tile after its next one).
+// One CTA per CHUNK of consecutive tiles, no communication between CTAs: the open-cluster state and the record count are
+// carried from tile to tile in registers (every thread derives them from the same shared summaries), the records go to the
+// chunk's own segment of the record arrays.  What a chunk cannot know -- whether a cluster is open when it starts -- only
+// matters for its first event: if that is an END ("head" of the chunk) the record is left to k_chunk_resolve, which sees all
+// chunks' summaries (scan.cu, below).
 __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __grid_constant__ CUtensorMap tmap, Scan8Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -163,150 +106,53 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
     __shared__ ScanShared sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t num_tiles = p.num_tiles, epoch = p.epoch;
     const bool pf = p.pf_mcov != 0;
     const int spread = p.min_len >= 2 ? p.min_len - 2 : -1;  // extra positions a START shadows; -1: nothing is dropped
     const uint32_t kk = p.k > 128u ? 128u : p.k;             // bytes are <= 127: k >= 128 never matches
     const uint32_t kadd = (128u - kk) * 0x01010101u;
+    const uint32_t c = blockIdx.x;
+    const uint32_t t_lo = c * p.tiles_per_chunk < p.num_tiles ? c * p.tiles_per_chunk : p.num_tiles;
+    const uint32_t t_hi = t_lo + p.tiles_per_chunk < p.num_tiles ? t_lo + p.tiles_per_chunk : p.num_tiles;
+    const uint32_t n_my = t_hi - t_lo;
+    const uint64_t seg_base = uint64_t(c) * p.seg_cap;
 
     for (int i = tid; i < E2S_HIST_BINS; i += SC_THREADS) sh.hist[i] = 0;
-    // thread 0: the it-th tile of this CTA = next number from the ticket; its LCP box goes to stage it % SC_STAGES, its plane
-    // window to slot it % SC_PSLOTS, both signalling the stage's barrier (a bare arrival when no tile is left)
+    // thread 0: the it-th tile of the chunk -> LCP box to stage it % SC_STAGES, plane window to slot it % SC_PSLOTS
     auto issue = [&](uint32_t it) {
+        if (it >= n_my) return;
         const int stage = int(it % SC_STAGES);
-        const uint32_t t = uint32_t(atomicAdd(&p.res->ticket, 1ull));
-        sh.tile_of[stage] = t < num_tiles ? t : 0xffffffffu;
-        if (t < num_tiles) {
-            mbar_expect_tx(&sh.full_bar[stage], SC_T + (pf ? SC_PF_BYTES : 0));
-            tma_load_2d_u8(stages + size_t(stage) * SC_T, &tmap, 0, int(t * (SC_T / 128)), &sh.full_bar[stage]);
-            if (pf) bulk_g2s(plane_slots + size_t(it % SC_PSLOTS) * SC_PF_STRIDE, p.planes + uint64_t(t) * (SC_T / 64), SC_PF_BYTES, &sh.full_bar[stage]);
-        } else {
-            mbar_arrive(&sh.full_bar[stage]);
-        }
+        const uint32_t t = t_lo + it;
+        mbar_expect_tx(&sh.full_bar[stage], SC_T + (pf ? SC_PF_BYTES : 0));
+        tma_load_2d_u8(stages + size_t(stage) * SC_T, &tmap, 0, int(t * (SC_T / 128)), &sh.full_bar[stage]);
+        if (pf) bulk_g2s(plane_slots + size_t(it % SC_PSLOTS) * SC_PF_STRIDE, p.planes + uint64_t(t) * (SC_T / 64), SC_PF_BYTES, &sh.full_bar[stage]);
     };
     if (tid == 0) {
+        sh.prev_S[0] = 0;  // before the chunk: 0 (the chunk's head END is tested in k_chunk_resolve)
         for (int s = 0; s < SC_STAGES; ++s) mbar_init(&sh.full_bar[s], 1);
         fence_mbar_init();
         for (uint32_t s = 0; s < uint32_t(SC_STAGES); ++s) issue(s);
     }
     __syncthreads();
 
-    unsigned long long acc_bases = 0, my_last = 0;  // sum of kept lengths; (index of my last record + 1) << 16 | its length
-    unsigned long long cta_ends = 0;                // thread 0: ENDs of the tiles this CTA processed
-    bool cta_any = false;                           // thread 0: one of them had an event
+    // chunk state, identical in every thread
+    uint64_t X = OPEN_UNKNOWN;   // open-cluster state; unknown until the chunk's first event
+    uint64_t cnt = 0;            // records written to the segment so far
+    uint64_t n_end = 0;          // ENDs seen (head included)
+    uint64_t head_end = 0;       // 1 + global position of the chunk's head END, 0 = none
+    bool seen = false;           // the chunk has had an event
+    unsigned long long acc_bases = 0;  // (per thread) sum of the lengths I wrote
+    uint64_t my_last_o = ~0ull;        // (per thread) segment index and length of the last record I wrote
+    uint32_t my_last_len = 0;
 
-    // ---- P2: the records of one list window of the tile described by sh.meta[slot] (after a barrier that published lists + meta)
-    auto emit_window = [&](int slot, uint32_t win) {
-        const TileMeta& mt = sh.meta[slot];
-        const uint64_t X = mt.x_in, prefix = mt.prefix, tile_gbase = mt.tile_gbase;
-        const uint32_t adj = mt.adj, nE = mt.nE;
-        const bool carried = mt.carried != 0;
-        const uint4* pf_win = reinterpret_cast<const uint4*>(plane_slots + size_t(mt.pslot) * SC_PF_STRIDE);
-        const uint32_t cnt = nE - win < uint32_t(SC_CAP) ? nE - win : uint32_t(SC_CAP);
-        for (uint32_t i = tid; i < cnt; i += SC_THREADS) {
-            const uint32_t ent = sh.e_ent[slot][i];
-            const uint32_t e = ent & 0x3fffu, r = (ent >> 14) & 0x3fffu;
-            const uint64_t gend = tile_gbase + e;
-            const bool first_carried = carried && win + i == 0;
-            uint64_t st;
-            bool known = true;
-            if (first_carried) {
-                known = X >= OPEN_BIAS;
-                st = X - OPEN_BIAS;
-            } else {
-                st = tile_gbase + sh.s_pos[slot][i];
-            }
-            if (gend + 2 == p.n_global) p.res->end_nm2_start = known ? st + 1 : ~0ull;  // decides the post-EOF phantom
-            if (first_carried) {
-                if (!known) {  // the shard's head END: its START is in an earlier shard
-                    p.res->head_end = gend + 1;
-                    continue;
-                }
-                if (adj) continue;
-            } else if (!((ent >> 28) & 1u)) {
-                continue;
-            }
-            const uint32_t len = uint32_t(gend - st + 1) & 0xffffu;
-            const uint64_t o = prefix + r - ((carried && !first_carried) ? adj : 0u);
-            if (o < p.cap) {
-                p.out_start[o] = st;
-                p.out_len[o] = uint16_t(len);
-            } else {
-                p.res->overflow = 1;
-            }
-            acc_bases += len;
-            if (len <= uint32_t(MAX_C_LEN)) atomicAdd(&sh.hist[len], 1u);
-            const unsigned long long mark = ((o + 1) << 16) | len;
-            my_last = mark > my_last ? mark : my_last;
-            // fused BWT prefilter of find_variants (ref:clust2snp.cpp:402-429; planes.cuh): the one-popcount bound.  Fewer than
-            // mcov positions with a base code other than the first position's => at most one frequent code => the
-            // cluster cannot pass; everything else goes to the exact test (K3x).
-            if (pf && len >= 2 * p.pf_mcov && len <= uint32_t(MAX_C_LEN)) {
-                bool pass = st + PL_PAD < tile_gbase;  // the 16-bit length wrapped: the analysed range lies far before this window
-                if (!pass) {
-                    const uint64_t b_lo = st + PL_PAD - tile_gbase, b_last = b_lo + len - 1;
-                    const uint32_t q_lo = uint32_t(b_lo >> 6), q_last = uint32_t(b_last >> 6);
-                    unsigned long long f0 = 0, f1 = 0;
-                    uint32_t others = 0;
-                    for (uint32_t q = q_lo; q <= q_last; ++q) {
-                        const uint4 v = pf_win[q];
-                        const unsigned long long x0 = (uint64_t(v.y) << 32) | v.x, x1 = (uint64_t(v.w) << 32) | v.z;
-                        unsigned long long mask = ~0ull;
-                        if (q == q_lo) {
-                            mask = ~0ull << (b_lo & 63);
-                            f0 = 0ull - ((x0 >> (b_lo & 63)) & 1ull);
-                            f1 = 0ull - ((x1 >> (b_lo & 63)) & 1ull);
-                        }
-                        if (q == q_last) mask &= ~0ull >> (63 - (b_last & 63));
-                        others += __popcll(((x0 ^ f0) | (x1 ^ f1)) & mask);
-                    }
-                    pass = others >= p.pf_mcov;
-                }
-                if (pass) {
-                    const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
-                    if (at < p.pf_cap) p.pf_list[at] = SurvEntry{st, st - p.global_off, len, 0u};
-                }
-            }
-        }
-    };
-    // warp 0: records kept before the tile of sh.meta[slot] (decoupled look-back over the B words), B inclusive published
-    auto lookback_prefix = [&](int slot) {
-        __syncwarp();  // (lane 0 may have written the meta words just now)
-        TileMeta& mt = sh.meta[slot];
-        const uint32_t t = mt.tile;
-        uint64_t prefix = 0;
-        if (t > 0) {
-            int64_t j0 = int64_t(t) - 1;
-            while (true) {
-                uint64_t b;
-                int first;
-                const bool done = poll_window(p.descB, j0, lane, epoch, b, first);
-                uint64_t v = (lane <= first && j0 - lane >= 0) ? (b >> 20) & ((uint64_t(1) << 42) - 1) : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += shfl64(v, lane ^ o);
-                prefix += v;
-                if (done) break;
-                j0 -= 32;
-            }
-        }
-        if (lane == 0) {
-            desc_store_raw(p.descB + t, make_b(D_INC, prefix + mt.count, epoch));
-            mt.prefix = prefix;
-            if (t == num_tiles - 1) p.res->n_written = prefix + mt.count;  // total of kept records
-        }
-    };
-
-    bool pending = false;  // the previous tile's P2 is still to run (block-uniform)
-    uint32_t it = 0;
-    for (;; ++it) {
+    for (uint32_t it = 0; it < n_my; ++it) {
         const int stage = it % SC_STAGES;
         const uint32_t parity = (it / SC_STAGES) & 1;
-        const int pb = it & 1;  // slot of the lists / meta / per-warp summaries
-        const uint32_t t = sh.tile_of[stage];  // (written before a barrier every thread has passed since)
-        if (t == 0xffffffffu) break;
+        const int pb = it & 1;
+        const uint32_t t = t_lo + it;
         const uint64_t tile_base = uint64_t(t) * SC_T;
         const uint64_t tile_gbase = p.global_off + tile_base;
         const uint8_t* tile = stages + size_t(stage) * SC_T;
+        const uint4* pf_win = reinterpret_cast<const uint4*>(plane_slots + size_t(it % SC_PSLOTS) * SC_PF_STRIDE);
         const bool interior = tile_gbase != 0 && tile_base + SC_T <= p.n_local && tile_gbase + SC_T < p.n_global;
 
         uint32_t g_prev = 0, g_next = 0;  // the bytes around the tile: issue the global loads before waiting for the tile
@@ -322,11 +168,11 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             const uint8_t* row = tile + r * 128u;
 #pragma unroll
             for (uint32_t j = 0; j < 4; ++j) {
-                const uint4 c = lds128(row + (((c0 + j) ^ x) << 4));
-                w[4 * j + 0] = c.x;
-                w[4 * j + 1] = c.y;
-                w[4 * j + 2] = c.z;
-                w[4 * j + 3] = c.w;
+                const uint4 v = lds128(row + (((c0 + j) ^ x) << 4));
+                w[4 * j + 0] = v.x;
+                w[4 * j + 1] = v.y;
+                w[4 * j + 2] = v.z;
+                w[4 * j + 3] = v.w;
             }
             // the word before my bytes and the byte after them
             if (tid == 0) pw = g_prev;
@@ -390,9 +236,11 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             uint64_t sm = S;
             if (spread >= 1) {  // (kernel-uniform) the previous thread's START word: neighbours by shuffle, warps through shared memory
                 if (lane == 31) sh.wS[warp] = S;
+                if (tid == SC_THREADS - 1) sh.prev_S[pb ^ 1] = S;  // for the next tile
                 __syncthreads();
+                const uint64_t before_tile = sh.prev_S[pb];
                 uint64_t lo = shfl64(S, (lane + 31) & 31);
-                if (lane == 0) lo = warp ? sh.wS[warp - 1] : 0;  // before the tile: 0 (a carried END is tested exactly below)
+                if (lane == 0) lo = warp ? sh.wS[warp - 1] : before_tile;
                 uint64_t hi = S;
                 int width = 1;  // sm = OR of (S << d), d = 0 .. width - 1, over the 128 bits lo:hi
                 while (2 * width <= spread + 1) {
@@ -429,8 +277,8 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 sh.wfe[pb][warp] = fe;
             }
         }
-        __syncthreads();  // (A) per-warp summaries.  Every thread has this tile's bytes in registers and is done with the tile
-        // before the previous one (its plane window included): the stage is refilled with the CTA's tile it + SC_STAGES
+        __syncthreads();  // (A) per-warp summaries.  Every thread has this tile's bytes in registers and has written the records
+        // of the tile before: the stage is refilled with the chunk's tile it + SC_STAGES (plane slot: the previous tile's)
         if (tid == 0) issue(it + SC_STAGES);
 
         uint32_t base = inc - pk, tot = 0;
@@ -454,72 +302,36 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         const bool carried = t_fe != NO_POS && t_fe < t_fs;  // the tile's first event is an END: its START lies before the tile
         // (a START and an END at the same position: the START comes first, t_fe == t_fs is not carried)
 
-        // ---- warp 0: state entering the tile, the carried END's fate, B aggregate -- everything the tiles after this one wait for
-        if (warp == 0) {
-            // A: the state after this tile is local whenever the tile has an event
-            if (lane == 0 && has_event)
-                desc_store_raw(p.descA + t, t_ls > t_le ? make_a(D_INC, A_OPEN, tile_base + uint64_t(t_ls), epoch) : make_a(D_INC, A_CLOSED, 0, epoch));
-            else if (lane == 0)
-                desc_store_raw(p.descA + t, make_a(D_AGG, A_NONE, 0, epoch));
-            uint64_t X = p.global_off == 0 ? OPEN_NONE : OPEN_UNKNOWN;  // state before the shard
-            if (t > 0 && (carried || !has_event)) {
-                int64_t j0 = int64_t(t) - 1;
-                while (true) {
-                    uint64_t a;
-                    int first;
-                    if (poll_window(p.descA, j0, lane, epoch, a, first)) {
-                        const uint64_t av = shfl64(a, first);
-                        if (j0 - first >= 0) {
-                            const uint64_t kind = (av >> 60) & 3u;
-                            X = kind == A_OPEN ? OPEN_BIAS + p.global_off + ((av >> 20) & A_POS_MASK)
-                                               : (kind == A_UNKNOWN ? OPEN_UNKNOWN : OPEN_NONE);
-                        }
-                        break;
-                    }
-                    j0 -= 32;
-                }
+        // ---- the carried END: tested exactly on the wrapped length (ref:ebwt2clust.cpp:56,104) against the carried-in START --
+        // it is the only END of the tile that can be 65 536 or more positions from its START.  Before the chunk's first
+        // event the START is not known here: that END is the chunk's head, left to k_chunk_resolve.
+        uint32_t adj = 0;  // 1: the carried END is not written by this tile
+        const bool is_head = carried && !seen;
+        if (carried) {
+            adj = 1;
+            if (seen && X >= OPEN_BIAS) {
+                const uint32_t len = uint32_t(tile_gbase + uint64_t(t_fe) - (X - OPEN_BIAS) + 1) & 0xffffu;
+                adj = int(len) >= p.min_len ? 0u : 1u;
             }
-            if (lane == 0 && !has_event && t > 0)  // nothing happened here: pass the resolved state on
-                desc_store_raw(p.descA + t, X >= OPEN_BIAS ? make_a(D_INC, A_OPEN, X - OPEN_BIAS - p.global_off, epoch)
-                                                           : make_a(D_INC, X == OPEN_UNKNOWN ? A_UNKNOWN : A_CLOSED, 0, epoch));
-            uint32_t adj = 0;
-            if (carried) {  // exact test of append_entry on the wrapped length (ref:ebwt2clust.cpp:56,104); unknown START: the shard's head
-                const uint64_t gend = tile_gbase + uint64_t(t_fe);
-                adj = 1;
-                if (X >= OPEN_BIAS) {
-                    const uint32_t len = uint32_t(gend - (X - OPEN_BIAS) + 1) & 0xffffu;
-                    adj = int(len) >= p.min_len ? 0u : 1u;
-                }
-            }
-            if (lane == 0) {
-                const uint32_t count = nE - nD - adj;
-                if (t > 0) desc_store_raw(p.descB + t, make_b(D_AGG, count, epoch));
-                TileMeta& mt = sh.meta[pb];
-                mt.tile_gbase = tile_gbase;
-                mt.x_in = X;
-                mt.tile = t;
-                mt.nE = nE;
-                mt.count = count;
-                mt.adj = adj;
-                mt.carried = carried ? 1u : 0u;
-                mt.pslot = it % SC_PSLOTS;
-                cta_ends += nE;
-                cta_any |= has_event;
-                if (t == num_tiles - 1) {  // state after the whole shard
-                    const uint64_t x_out = has_event ? (t_ls > t_le ? tile_gbase + uint64_t(t_ls) + OPEN_BIAS : OPEN_NONE) : X;
-                    p.res->open_start = x_out >= OPEN_BIAS ? x_out - OPEN_BIAS + 1 : 0;
-                }
-            }
+            if (is_head) head_end = tile_gbase + uint64_t(t_fe) + 1;
+        }
+        const uint64_t x_in = X, prefix = seg_base + cnt;
+        cnt += nE - nD - adj;
+        n_end += nE;
+        if (has_event) {
+            X = t_ls > t_le ? tile_gbase + uint64_t(t_ls) + OPEN_BIAS : OPEN_NONE;
+            seen = true;
         }
 
-        // ---- lists of the tile's first SC_CAP ENDs (all of them unless the tile is unusually dense)
-        auto scatter = [&](uint32_t win) {
+        // ---- lists + records, one window of SC_CAP ENDs at a time (one iteration unless the tile is unusually dense)
+        for (uint32_t win = 0; win < nE; win += SC_CAP) {
+            if (win) __syncthreads();  // the previous window's lists are no longer read
             uint64_t m = S;
             while (m) {  // a START goes to the slot of the END it pairs with: the one with as many ENDs before it
                 const int b = __ffsll(m) - 1;
                 m &= m - 1;
                 const uint32_t q = baseE + __popcll(E & below(b)) - win;
-                if (q < uint32_t(SC_CAP)) sh.s_pos[pb][q] = uint16_t(tid * SC_V + b);
+                if (q < uint32_t(SC_CAP)) sh.s_pos[q] = uint16_t(tid * SC_V + b);
             }
             m = E;
             while (m) {
@@ -529,61 +341,224 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 const uint32_t q = qa - win;
                 if (q < uint32_t(SC_CAP)) {
                     const uint32_t r = qa - (baseD + __popcll(D & below(b)));
-                    sh.e_ent[pb][q] = uint32_t(tid * SC_V + b) | (r << 14) | ((uint32_t((D >> b) & 1u) ^ 1u) << 28);
+                    sh.e_ent[q] = uint32_t(tid * SC_V + b) | (r << 14) | ((uint32_t((D >> b) & 1u) ^ 1u) << 28);
                 }
             }
-        };
-        scatter(0);
-
-        // ---- P2 of the previous tile: its aggregate and ours are out, now this CTA may wait
-        if (pending) {
-            if (warp == 0) lookback_prefix(pb ^ 1);
-            __syncthreads();  // (B) prefix of the previous tile (its lists and meta were published by barrier (A) above)
-            emit_window(pb ^ 1, 0);
-        }
-        pending = true;
-        if (nE > uint32_t(SC_CAP)) {  // (block-uniform, rare) more ENDs than one list window holds: finish this tile here, window by window
-            if (warp == 0) lookback_prefix(pb);
-            __syncthreads();
-            emit_window(pb, 0);
-            for (uint32_t win = SC_CAP; win < nE; win += SC_CAP) {
-                __syncthreads();  // the previous window's lists are no longer read
-                scatter(win);
-                __syncthreads();
-                emit_window(pb, win);
+            __syncthreads();  // (B) lists
+            const uint32_t n_win = nE - win < uint32_t(SC_CAP) ? nE - win : uint32_t(SC_CAP);
+            for (uint32_t i = tid; i < n_win; i += SC_THREADS) {
+                const uint32_t ent = sh.e_ent[i];
+                const uint32_t e = ent & 0x3fffu, r = (ent >> 14) & 0x3fffu;
+                const uint64_t gend = tile_gbase + e;
+                const bool first_carried = carried && win + i == 0;
+                uint64_t st;
+                if (first_carried) {
+                    if (is_head) continue;       // k_chunk_resolve writes (or drops) it, and answers for position n_global - 2
+                    st = x_in - OPEN_BIAS;       // (x_in is an open state: START and END bits alternate)
+                } else {
+                    st = tile_gbase + sh.s_pos[i];
+                }
+                if (gend + 2 == p.n_global) p.res->end_nm2_start = st + 1;  // decides the post-EOF phantom, kept or not
+                if (first_carried ? adj != 0 : !((ent >> 28) & 1u)) continue;
+                const uint32_t len = uint32_t(gend - st + 1) & 0xffffu;
+                const uint64_t o = prefix + r - ((carried && !first_carried) ? adj : 0u);
+                if (o - seg_base < p.seg_cap) {
+                    p.seg_start[o] = st;
+                    p.seg_len[o] = uint16_t(len);
+                } else {
+                    p.res->overflow = 1;
+                }
+                acc_bases += len;
+                if (len <= uint32_t(MAX_C_LEN)) atomicAdd(&sh.hist[len], 1u);
+                my_last_o = o;
+                my_last_len = len;
+                // fused BWT prefilter of find_variants (ref:clust2snp.cpp:402-429; planes.cuh): the one-popcount bound.  Fewer than
+                // mcov positions with a base code other than the first position's => at most one frequent code => the
+                // cluster cannot pass; everything else goes to the exact test (K3x).
+                if (pf && len >= 2 * p.pf_mcov && len <= uint32_t(MAX_C_LEN)) {
+                    bool pass = st + PL_PAD < tile_gbase;  // the 16-bit length wrapped: the analysed range lies far before this window
+                    if (!pass) {
+                        const uint64_t b_lo = st + PL_PAD - tile_gbase, b_last = b_lo + len - 1;
+                        const uint32_t q_lo = uint32_t(b_lo >> 6), q_last = uint32_t(b_last >> 6);
+                        unsigned long long f0 = 0, f1 = 0;
+                        uint32_t others = 0;
+                        for (uint32_t q = q_lo; q <= q_last; ++q) {
+                            const uint4 v = pf_win[q];
+                            const unsigned long long x0 = (uint64_t(v.y) << 32) | v.x, x1 = (uint64_t(v.w) << 32) | v.z;
+                            unsigned long long mask = ~0ull;
+                            if (q == q_lo) {
+                                mask = ~0ull << (b_lo & 63);
+                                f0 = 0ull - ((x0 >> (b_lo & 63)) & 1ull);
+                                f1 = 0ull - ((x1 >> (b_lo & 63)) & 1ull);
+                            }
+                            if (q == q_last) mask &= ~0ull >> (63 - (b_last & 63));
+                            others += __popcll(((x0 ^ f0) | (x1 ^ f1)) & mask);
+                        }
+                        pass = others >= p.pf_mcov;
+                    }
+                    if (pass) {
+                        const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
+                        if (at < p.pf_cap) p.pf_list[at] = SurvEntry{st, st - p.global_off, len, 0u};
+                    }
+                }
             }
-            pending = false;
         }
     }
-    if (pending) {  // P2 of the CTA's last tile (the loop left at iteration `it`: that tile's slot is the other one)
-        const int slot = int((it - 1) & 1);
-        if (warp == 0) lookback_prefix(slot);
-        __syncthreads();
-        emit_window(slot, 0);
-    }
 
-    // ---- per-CTA totals
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        acc_bases += __shfl_xor_sync(FULL, acc_bases, d);
-        const unsigned long long o = __shfl_xor_sync(FULL, my_last, d);
-        my_last = o > my_last ? o : my_last;
-    }
-    if (lane == 0) {
-        if (acc_bases) atomicAdd(&p.res->n_bases, acc_bases);
-        if (my_last) atomicMax(&p.res->last_rec, my_last);
-    }
-    if (tid == 0) {
-        if (cta_ends) atomicAdd(&p.res->n_end, cta_ends);
-        if (cta_any) atomicOr(&p.res->any_event, 1ull);
-    }
+    // ---- what the chunk leaves for k_chunk_resolve
     __syncthreads();
     for (int i = tid; i < E2S_HIST_BINS; i += SC_THREADS)
         if (sh.hist[i]) atomicAdd(&p.res->hist[i], (unsigned long long)sh.hist[i]);
-    if (blockIdx.x == 0 && tid == 0 && p.tail_lcp) {
-        p.res->tail_lcp_nm2 = p.tail_lcp[0];
-        p.res->tail_lcp_nm1 = p.tail_lcp[1];
-        p.res->tail_bwt_nm1 = p.tail_bwt[0];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc_bases += __shfl_xor_sync(FULL, acc_bases, d);
+    ChunkRec* cr = p.chunks + c;
+    if (lane == 0 && acc_bases) atomicAdd(&cr->n_bases, acc_bases);
+    if (cnt && my_last_o + 1 == seg_base + cnt) cr->last_len = my_last_len;  // (one thread: the writer of the chunk's last record)
+    if (tid == 0) {
+        cr->own_count = cnt;
+        cr->head_end = head_end;
+        cr->last_state = seen ? (X >= OPEN_BIAS ? X : 1ull) : 0ull;  // 0: no event; 1: closed; >= 2: OPEN_BIAS + global START
+        cr->n_end = n_end;
+        if (c == 0 && p.tail_lcp) {
+            p.res->tail_lcp_nm2 = p.tail_lcp[0];
+            p.res->tail_lcp_nm1 = p.tail_lcp[1];
+            p.res->tail_bwt_nm1 = p.tail_bwt[0];
+        }
+    }
+}
+
+// =============================================================================================
+// k_chunk_resolve: what the chunks could not know (one CTA; a few hundred chunks)
+// =============================================================================================
+// state entering a chunk = state left by the nearest earlier chunk that had an event (else the state before the shard);
+// the chunk's head END closes the cluster that state holds open: exact length test, one record in front of the chunk's own;
+// an END without any START in the shard is the SHARD's head (resolved by e2s_cluster_merge across shards).  Then the
+// exclusive scan of the chunks' record counts (= where each segment goes in the position-ordered list) and the shard totals.
+constexpr int RS_THREADS = 1024;
+
+__global__ void __launch_bounds__(RS_THREADS) k_chunk_resolve(ResolveParams p) {
+    __shared__ unsigned long long s_state[RS_THREADS];
+    __shared__ unsigned long long s_cnt[RS_THREADS];
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_tot[4];  // records, ENDs, bases, (last chunk with records) + 1
+    const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
+    const bool act = uint32_t(c) < p.n_chunks;
+    ChunkRec rec;
+    rec.own_count = rec.head_end = rec.last_state = rec.n_end = rec.n_bases = rec.last_len = 0;
+    if (act) rec = p.chunks[c];
+    s_state[c] = rec.last_state;
+    if (c < 4) s_tot[c] = 0;
+    __syncthreads();
+    uint64_t X = p.init_state;
+    for (int j = c - 1; j >= 0; --j)
+        if (s_state[j]) {
+            X = s_state[j] >= OPEN_BIAS ? s_state[j] : OPEN_NONE;
+            break;
+        }
+    uint64_t h_start = 0;
+    uint32_t h_len = 0, h_kept = 0;
+    if (act && rec.head_end) {
+        const uint64_t e = rec.head_end - 1;
+        if (X >= OPEN_BIAS) {
+            h_start = X - OPEN_BIAS;
+            h_len = uint32_t(e - h_start + 1) & 0xffffu;  // append_entry's wrapped length (ref:ebwt2clust.cpp:56,104)
+            h_kept = int(h_len) >= p.min_len ? 1u : 0u;
+            if (e + 2 == p.n_global) p.res->end_nm2_start = h_start + 1;
+        } else {  // no START in this shard: the shard's head
+            p.res->head_end = e + 1;
+            if (e + 2 == p.n_global) p.res->end_nm2_start = ~0ull;
+        }
+    }
+    const unsigned long long mine = rec.own_count + h_kept;
+    unsigned long long inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = shfl64(inc, lane >= d ? lane - d : lane);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    s_cnt[c] = mine;
+    __syncthreads();
+    unsigned long long off = inc - mine;
+    for (int q = 0; q < warp; ++q) off += s_warp[q];
+    if (act) {
+        ChunkSeg sg;
+        sg.off = off;
+        sg.own_count = rec.own_count;
+        sg.head_start = h_start;
+        sg.head_len = h_len;
+        sg.head_kept = h_kept;
+        p.segs[c] = sg;
+        if (h_kept) {
+            if (h_len <= uint32_t(MAX_C_LEN)) atomicAdd(&p.res->hist[h_len], 1ull);
+            // the head record's turn at the fused BWT prefilter (its positions lie before the chunk: global planes)
+            if (p.pf_mcov && h_len >= 2 * p.pf_mcov && h_len <= uint32_t(MAX_C_LEN)) {
+                bool pass = h_start < p.global_off;  // (cannot happen for a record with a known START; kept for safety)
+                if (!pass) pass = frequent_bound(p.planes, int64_t(h_start - p.global_off), h_len, p.pf_mcov);
+                if (pass) {
+                    const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
+                    if (at < p.pf_cap) p.pf_list[at] = SurvEntry{h_start, h_start - p.global_off, h_len, 0u};
+                }
+            }
+        }
+        atomicAdd(&s_tot[0], mine);
+        atomicAdd(&s_tot[1], rec.n_end);
+        atomicAdd(&s_tot[2], rec.n_bases + (h_kept ? h_len : 0u));
+        if (mine) atomicMax(&s_tot[3], (unsigned long long)(c + 1));
+    }
+    __syncthreads();
+    if (act && mine && s_tot[3] == (unsigned long long)(c + 1))  // the list's last record is this chunk's last
+        p.res->last_rec = (s_tot[0] << 16) | (rec.own_count ? rec.last_len : h_len);
+    if (c == 0) {
+        p.res->n_written = s_tot[0];
+        p.res->n_end = s_tot[1];
+        p.res->n_bases = s_tot[2];
+        uint64_t x_out = p.init_state;
+        bool any = false;
+        for (int j = int(p.n_chunks) - 1; j >= 0; --j)
+            if (s_state[j]) {
+                x_out = s_state[j] >= OPEN_BIAS ? s_state[j] : OPEN_NONE;
+                any = true;
+                break;
+            }
+        p.res->any_event = any ? 1ull : 0ull;
+        p.res->open_start = x_out >= OPEN_BIAS ? x_out - OPEN_BIAS + 1 : 0;
+    }
+}
+
+// segments -> position-ordered contiguous list: as SoA (start u64, len u16) or as the 10-byte records of the .clusters
+// file (ref:ebwt2clust.cpp:58-59)
+__global__ void __launch_bounds__(256) k_export_records(const ChunkSeg* __restrict__ segs, uint32_t n_chunks, uint64_t seg_cap,
+                                                        const uint64_t* __restrict__ seg_start, const uint16_t* __restrict__ seg_len,
+                                                        uint64_t* __restrict__ out_start, uint16_t* __restrict__ out_len,
+                                                        uint16_t* __restrict__ out_packed) {
+    for (uint32_t c = blockIdx.y; c < n_chunks; c += gridDim.y) {
+        const ChunkSeg sg = segs[c];
+        const uint64_t total = sg.own_count + sg.head_kept;
+        const uint64_t src0 = uint64_t(c) * seg_cap;
+        for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x) {
+            uint64_t st;
+            uint16_t ln;
+            if (sg.head_kept && i == 0) {
+                st = sg.head_start;
+                ln = uint16_t(sg.head_len);
+            } else {
+                st = seg_start[src0 + i - sg.head_kept];
+                ln = seg_len[src0 + i - sg.head_kept];
+            }
+            const uint64_t o = sg.off + i;
+            if (out_packed) {
+                uint16_t* q = out_packed + o * 5;
+                q[0] = uint16_t(st);
+                q[1] = uint16_t(st >> 16);
+                q[2] = uint16_t(st >> 32);
+                q[3] = uint16_t(st >> 48);
+                q[4] = ln;
+            } else {
+                out_start[o] = st;
+                out_len[o] = ln;
+            }
+        }
     }
 }
 
@@ -608,12 +583,45 @@ static PFN_encodeTiled scan_encode_fn() {
 
 uint64_t scan_num_tiles(uint64_t n_local) { return (n_local + SC_T - 1) / SC_T; }
 
-cudaError_t launch_scan(const Scan8Params& p0, uint64_t alloc_r, int sm_count, cudaStream_t stream) {
+static int scan_occupancy(int* out) {
+    static int occ_dev[64] = {0};  // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& occ = occ_dev[dev & 63];
+    if (!occ) {
+        cudaError_t e = cudaFuncSetAttribute(k_cluster_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SC_DYN_SMEM));
+        if (e != cudaSuccess) return int(e);
+        int o = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_cluster_scan, SC_THREADS, SC_DYN_SMEM);
+        if (e != cudaSuccess) return int(e);
+        if (o < 1) return int(cudaErrorLaunchOutOfResources);
+        occ = o;
+    }
+    *out = occ;
+    return 0;
+}
+
+// chunks of a shard: one per CTA the device holds at once (at most SCAN_MAX_CHUNKS), at least one tile each
+cudaError_t scan_plan(uint64_t n_local, int sm_count, uint32_t* n_chunks, uint32_t* tiles_per_chunk) {
+    int occ = 0;
+    const int rc = scan_occupancy(&occ);
+    if (rc) return cudaError_t(rc);
+    const uint64_t nt = scan_num_tiles(n_local);
+    uint64_t g = uint64_t(sm_count) * occ;
+    if (g > SCAN_MAX_CHUNKS) g = SCAN_MAX_CHUNKS;
+    if (g > nt) g = nt;
+    if (g < 1) g = 1;
+    const uint64_t tpc = (nt + g - 1) / g;
+    *tiles_per_chunk = uint32_t(tpc < 1 ? 1 : tpc);
+    *n_chunks = uint32_t(nt ? (nt + *tiles_per_chunk - 1) / *tiles_per_chunk : 1);
+    return cudaSuccess;
+}
+
+cudaError_t launch_scan(const Scan8Params& p0, uint64_t alloc_r, cudaStream_t stream) {
     PFN_encodeTiled enc = scan_encode_fn();
     if (!enc) return cudaErrorNotSupported;
     Scan8Params p = p0;
     p.num_tiles = uint32_t(scan_num_tiles(p.n_local));
-    if (p.num_tiles == 0) return cudaSuccess;
     CUtensorMap tmap;
     cuuint64_t gdim[2] = {128, cuuint64_t(alloc_r / 128)};  // the padded byte array from local position 0 on, as rows of 128 bytes
     cuuint64_t gstride[1] = {128};
@@ -623,23 +631,28 @@ cudaError_t launch_scan(const Scan8Params& p0, uint64_t alloc_r, int sm_count, c
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    const size_t smem = size_t(SC_DYN_SMEM);
-    static int occ_dev[64] = {0};  // function attributes are per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    int& occ = occ_dev[dev & 63];
-    if (!occ) {
-        cudaError_t e = cudaFuncSetAttribute(k_cluster_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_cluster_scan, SC_THREADS, smem);
-        if (e != cudaSuccess) return e;
-        if (o < 1) return cudaErrorLaunchOutOfResources;
-        occ = o;
-    }
-    uint64_t grid = uint64_t(sm_count) * occ;
-    if (grid > p.num_tiles) grid = p.num_tiles;
-    k_cluster_scan<<<dim3(unsigned(grid)), dim3(SC_THREADS), smem, stream>>>(tmap, p);
+    int occ = 0;
+    const int rc = scan_occupancy(&occ);
+    if (rc) return cudaError_t(rc);
+    k_cluster_scan<<<dim3(p.n_chunks), dim3(SC_THREADS), SC_DYN_SMEM, stream>>>(tmap, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_chunk_resolve(const ResolveParams& p, cudaStream_t stream) {
+    if (p.n_chunks > uint32_t(RS_THREADS)) return cudaErrorInvalidValue;
+    k_chunk_resolve<<<1, RS_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export_records(const ChunkSeg* segs, uint32_t n_chunks, uint64_t seg_cap, const uint64_t* seg_start,
+                                  const uint16_t* seg_len, uint64_t* out_start, uint16_t* out_len, uint8_t* out_packed,
+                                  cudaStream_t stream) {
+    if (!n_chunks) return cudaSuccess;
+    uint64_t bx = (seg_cap + 255) / 256;
+    if (bx > 16) bx = 16;
+    if (bx < 1) bx = 1;
+    k_export_records<<<dim3(unsigned(bx), n_chunks > 1024 ? 1024 : n_chunks), 256, 0, stream>>>(
+        segs, n_chunks, seg_cap, seg_start, seg_len, out_start, out_len, reinterpret_cast<uint16_t*>(out_packed));
     return cudaGetLastError();
 }
 
