@@ -90,7 +90,8 @@ struct e2s_shard {
     SurvEntry* d_pf_list = nullptr;
     uint64_t pf_cap = 0, pf_count = 0;
     bool pf_ok = false;              // the list is complete (no overflow) and belongs to the current record list
-    uint4* d_planes = nullptr;       // resident base-code bit planes of the BWT (planes.cuh), built at seal
+    uint4* d_planes = nullptr;       // resident base-code bit planes of the BWT (planes.cuh), written by the loads
+    uint64_t* d_chg = nullptr;       // ... and the change plane: bit x = base code of x differs from that of x - 1
     uint32_t* d_seal_flag = nullptr; // != 0: an LCP value above 127 (set at seal)
     int variant = 0;
     // phase 2
@@ -292,6 +293,7 @@ int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_hist), (E2S_HIST_BINS + 1) * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_seal_flag), 4);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_planes), plane_quads(s->alloc_r) * sizeof(uint4));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_chg), (plane_quads(s->alloc_r) + 1) * 8);
     if (e != cudaSuccess) {
         e2s_shard_destroy(s);
         return fail(c, E2S_ERR_NOMEM, std::string("shard allocation: ") + cudaGetErrorString(e));
@@ -303,6 +305,7 @@ int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t
     }
     if (s->lcp8_a) CU(c, cudaMemsetAsync(s->lcp8_a, 0, ne, c->stream));
     CU(c, cudaMemsetAsync(s->d_planes, 0, plane_quads(s->alloc_r) * sizeof(uint4), c->stream));  // pads: code 0
+    CU(c, cudaMemsetAsync(s->d_chg, 0, (plane_quads(s->alloc_r) + 1) * 8, c->stream));
     CU(c, cudaMemsetAsync(s->d_seal_flag, 0, 4, c->stream));
     s->lcp = s->lcp_a + PAD_L;
     s->text = s->text_a + PAD_L;
@@ -345,6 +348,7 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->d_hist);
     cudaFree(s->d_seal_flag);
     cudaFree(s->d_planes);
+    cudaFree(s->d_chg);
     cudaFree(s->d_pf_list);
     snp_work_destroy(s->work);
     if (s->ctx->cached == s) s->ctx->cached = nullptr;
@@ -364,7 +368,7 @@ static cudaError_t derive_loaded(e2s_shard* s, int64_t l, uint64_t cnt, bool hav
     // the scan looks at positions [-2, n_local] (on the last shard lcp[n_local] is the phantom, which only feeds END(n-1),
     // left to the host tail rule): only those decide whether the byte copy is usable
     return launch_derive(s->lcp, have_bwt ? s->bwt : nullptr, have_lcp ? (s->lcp8_a ? s->lcp8_a + PAD_L : nullptr) : nullptr, s->d_planes,
-                         l, l + int64_t(cnt), -2, int64_t(s->n_local) + (last_shard ? 0 : 1), s->d_seal_flag, s->ctx->stream,
+                         s->d_chg, l, l + int64_t(cnt), -2, int64_t(s->n_local) + (last_shard ? 0 : 1), s->d_seal_flag, s->ctx->stream,
                          s->ctx->sm_count);
 }
 
@@ -786,6 +790,7 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
             Scan8Params sp;
             sp.lcp8 = s->lcp8_a + PAD_L;
             sp.planes = s->d_planes;
+            sp.chg = s->d_chg;
             sp.n_local = s->n_local;
             sp.global_off = s->global_off;
             sp.n_global = s->n_global;

@@ -57,6 +57,35 @@ struct ClusterDev {  // device-resident accumulators of one e2s_cluster_run (zer
     unsigned long long hist[E2S_HIST_BINS];  // their length histogram (lengths <= 150)
 };
 
+// ---- the exchange between the phases (merge.cu) -------------------------------------------------------
+// one exchange row per shard: the scan's device accumulators + what the other ranks cannot know
+constexpr size_t XR_DEV_WORDS = sizeof(ClusterDev) / 8;
+constexpr size_t XR_WORDS = XR_DEV_WORDS + 4;  // + n_local, global_off, lcp_bytes, reserved
+constexpr int MERGE_MAX_SHARDS = 64;
+struct MergeOut {  // written by k_merge_stats
+    e2s_cluster_merged mine;  // this shard's view of the merge
+    e2s_stats total;          // statistics() over all shards' records, max_clust_length included
+    int32_t status;           // merge.cuh: MERGE_OK ...
+    int32_t pad;
+};
+struct MergeParams {
+    const unsigned long long* rows;  // `world` rows of XR_WORDS words, in shard order (device memory)
+    int world, my;
+    uint64_t n_global;
+    uint32_t k;
+    int32_t min_len;
+    int32_t mcov;
+    double pval;
+    uint64_t own_global_off;
+    MergeOut* out;
+    SurvEntry* pf_list;              // the records this shard adopts are appended here (null: no fused prefilter)
+    uint64_t pf_cap;
+    ClusterDev* res;                 // ... and counted in res->n_pf
+};
+cudaError_t launch_pack_exchange(const ClusterDev* res, uint64_t n_local, uint64_t global_off, uint64_t lcp_bytes, uint64_t* row,
+                                 cudaStream_t stream);
+cudaError_t launch_merge_stats(const MergeParams& p, cudaStream_t stream);
+
 struct FlagParams {  // K1
     const uint32_t* lcp;  // local position 0 (PAD_L readable elements before it)
     uint64_t n_local, global_off, n_global;
@@ -106,7 +135,8 @@ struct ChunkSeg {  // written by k_chunk_resolve: where the chunk's records go i
 };
 struct Scan8Params {
     const uint8_t* lcp8;        // local position 0 of the byte LCP (PAD_L readable bytes before it)
-    const uint4* planes;        // resident base-code bit planes (fused prefilter), may be null when pf_mcov == 0
+    const uint4* planes;        // resident base-code bit planes (second level of the fused prefilter)
+    const uint64_t* chg;        // resident base-code CHANGE plane (fused prefilter): bit of position x = word (x + PL_PAD) >> 6, bit x & 63
     uint64_t n_local, global_off, n_global;
     uint32_t k;
     int32_t min_len;            // <= 33
@@ -165,7 +195,7 @@ cudaError_t launch_unpack_gesa(const uint8_t* d_rec, uint64_t count, int x, int 
                                uint32_t* suff, uint8_t* bwt, cudaStream_t stream);
 // narrow resident copies of the local positions [a, b) just loaded (byte LCP + base-code bit planes); *flag |= 1 when an
 // LCP value in [chk_lo, chk_hi) does not fit the byte copy
-cudaError_t launch_derive(const uint32_t* lcp, const uint8_t* bwt, uint8_t* lcp8, uint4* planes, int64_t a, int64_t b,
+cudaError_t launch_derive(const uint32_t* lcp, const uint8_t* bwt, uint8_t* lcp8, uint4* planes, uint64_t* chg, int64_t a, int64_t b,
                           int64_t chk_lo, int64_t chk_hi, uint32_t* flag, cudaStream_t stream, int sm_count);
 cudaError_t launch_fill_phantom(uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt, uint64_t n_local,
                                 uint64_t count, int x, int y, int z, int bcr, cudaStream_t stream);

@@ -50,13 +50,13 @@ constexpr int SC_V = 64;                       // positions per thread
 constexpr int SC_T = SC_THREADS * SC_V;        // 16384 positions per tile
 constexpr int SC_W = SC_V / 4;                 // 16 packed words per thread
 constexpr int SC_STAGES = 2;                   // LCP tiles in flight / being read per CTA (a stage is free once its bytes are in registers)
-constexpr int SC_PSLOTS = SC_STAGES + 1;       // plane windows: a window is read until its tile's records are written, after the stage was refilled
 constexpr int SC_OCC = 4;                      // resident CTAs per SM the register / shared-memory budget is sized for
+constexpr int SC_PSLOTS = SC_STAGES + 1;       // plane windows: a window is read until its tile's records are written, after the stage was refilled
 constexpr int SC_PF_QUADS = SC_T / 64 + PL_PAD / 64;  // plane quads of one tile and of the PL_PAD positions before it
 constexpr int SC_PF_BYTES = SC_PF_QUADS * 16;  // 4144
 constexpr int SC_PF_STRIDE = 4224;             // slot stride (128-byte multiple)
 constexpr int SC_DYN_SMEM = SC_STAGES * SC_T + SC_PSLOTS * SC_PF_STRIDE + 1024;  // + slack for the 1024-byte alignment of the TMA boxes
-constexpr int SC_CAP = 1024;                   // ENDs per list window (a typical tile lists ~300)
+constexpr int SC_CAP = 512;                    // kept ENDs per list window (a typical tile lists ~300)
 
 // open-cluster state (as in cluster.cu)
 constexpr uint64_t OPEN_NONE = 0, OPEN_UNKNOWN = 1, OPEN_BIAS = 2;
@@ -81,13 +81,23 @@ __device__ __forceinline__ uint64_t below(int b) { return (uint64_t(1) << b) - 1
 
 struct ScanShared {
     uint64_t full_bar[SC_STAGES];
-    uint32_t wsum[2][SC_WARPS];   // per warp: #END | #dropped << 16 (double buffered by tile parity: a tile without ENDs has no barrier (B))
-    int wls[2][SC_WARPS], wle[2][SC_WARPS], wfs[2][SC_WARPS], wfe[2][SC_WARPS];  // last / first START / END of the warp (tile-local)
+    // per warp, double buffered by tile parity (a tile without ENDs has no barrier (B)):
+    uint32_t wsum[2][SC_WARPS];   // #kept ENDs | #ENDs << 16
+    int wls[2][SC_WARPS], wlc[2][SC_WARPS];  // last START / last base-code change of the warp (tile-local position), -1 = none
+    int wle[2][SC_WARPS];                    // last END of the warp
+    int wfs[2][SC_WARPS], wfe[2][SC_WARPS];  // first START / END of the warp, NO_POS = none
     uint64_t wS[SC_WARPS];        // START word of the warp's last thread (min_len >= 3 only)
-    uint64_t prev_S[2];           // [it & 1] = START word of the last thread of the chunk's tile it - 1 (min_len >= 3 only)
+    // per tile, written by warp 0 between the barriers (A) and (B):
+    uint64_t x_in;                // open-cluster state entering the tile
+    uint64_t c_in;                // 1 + global position of the last base-code change before the tile (0: none in this chunk so far)
+    uint64_t prefix;              // segment index of the tile's first record
+    uint32_t adj;                 // 1: the carried END is not written by this tile
+    uint32_t carried;             // the tile's first event is an END
     unsigned int hist[E2S_HIST_BINS];
-    uint16_t s_pos[SC_CAP];       // [q] = tile-local position of the START that pairs with the window's q-th END
-    uint32_t e_ent[SC_CAP];       // [q] = END position | kept rank << 14 | kept << 28
+    uint64_t smask[SC_THREADS];   // START words of the tile (only in the tile that holds position n_global - 2)
+    uint32_t n2[2];               // entries of list2 (by tile parity: the other one is reset while this one is in use)
+    uint32_t list2[SC_CAP];       // records of the window with a base-code change inside: (start - tile start + PL_PAD) | len << 16 (counted after the records are out)
+    uint32_t e_ent[SC_CAP];       // [r] = kept END: position | len << 14 | survivor << 30, or position | change-seen << 30 | 1 << 31 (START before its warp)
 };
 
 constexpr int NO_POS = 0x7fffffff;
@@ -95,10 +105,18 @@ constexpr int NO_POS = 0x7fffffff;
 }  // namespace
 
 // One CTA per CHUNK of consecutive tiles, no communication between CTAs: the open-cluster state and the record count are
-// carried from tile to tile in registers (every thread derives them from the same shared summaries), the records go to the
-// chunk's own segment of the record arrays.  What a chunk cannot know -- whether a cluster is open when it starts -- only
-// matters for its first event: if that is an END ("head" of the chunk) the record is left to k_chunk_resolve, which sees all
-// chunks' summaries (scan.cu, below).
+// carried from tile to tile by warp 0, the records go to the chunk's own segment of the record arrays.  What a chunk
+// cannot know -- whether a cluster is open when it starts -- only matters for its first event: if that is an END ("head"
+// of the chunk) the record is left to k_chunk_resolve, which sees all chunks' summaries.
+//
+// Per tile: masks (S, E) and the change word C of my 64 positions; kept ENDs K = E minus the ENDs of clusters shorter than
+// min_len (bit-parallel: a START at most min_len - 2 positions before); one block scan ranks the kept ENDs.  A cluster is
+// [nearest START at or before its END, END]: each END finds that START in its own thread's word or, by one ballot + one
+// shuffle, in an earlier lane of its warp -- and the last base-code change before the END the same way; only ENDs whose
+// START lies before their warp (about one per warp) are resolved when the records are written, from the per-warp
+// summaries.  BWT prefilter (fused mode): a cluster without a base-code change inside it has ONE base code and can never
+// pass find_variants (ref:clust2snp.cpp:402-429: both samples' frequent sets would be that one letter): it is dropped
+// here for the price of a compare; the others go to the list K3x tests exactly.
 __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __grid_constant__ CUtensorMap tmap, Scan8Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -106,6 +124,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
     __shared__ ScanShared sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const bool pf = p.pf_mcov != 0;
     const int spread = p.min_len >= 2 ? p.min_len - 2 : -1;  // extra positions a START shadows; -1: nothing is dropped
     const uint32_t kk = p.k > 128u ? 128u : p.k;             // bytes are <= 127: k >= 128 never matches
@@ -117,25 +136,24 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
     const uint64_t seg_base = uint64_t(c) * p.seg_cap;
 
     for (int i = tid; i < E2S_HIST_BINS; i += SC_THREADS) sh.hist[i] = 0;
-    // thread 0: the it-th tile of the chunk -> LCP box to stage it % SC_STAGES, plane window to slot it % SC_PSLOTS
-    auto issue = [&](uint32_t it) {
+    auto issue = [&](uint32_t it) {  // thread 0: the it-th tile of the chunk -> stage it % SC_STAGES
         if (it >= n_my) return;
         const int stage = int(it % SC_STAGES);
-        const uint32_t t = t_lo + it;
         mbar_expect_tx(&sh.full_bar[stage], SC_T + (pf ? SC_PF_BYTES : 0));
-        tma_load_2d_u8(stages + size_t(stage) * SC_T, &tmap, 0, int(t * (SC_T / 128)), &sh.full_bar[stage]);
-        if (pf) bulk_g2s(plane_slots + size_t(it % SC_PSLOTS) * SC_PF_STRIDE, p.planes + uint64_t(t) * (SC_T / 64), SC_PF_BYTES, &sh.full_bar[stage]);
+        tma_load_2d_u8(stages + size_t(stage) * SC_T, &tmap, 0, int((t_lo + it) * (SC_T / 128)), &sh.full_bar[stage]);
+        if (pf) bulk_g2s(plane_slots + size_t(it % SC_PSLOTS) * SC_PF_STRIDE, p.planes + uint64_t(t_lo + it) * (SC_T / 64), SC_PF_BYTES, &sh.full_bar[stage]);
     };
     if (tid == 0) {
-        sh.prev_S[0] = 0;  // before the chunk: 0 (the chunk's head END is tested in k_chunk_resolve)
+        sh.n2[0] = sh.n2[1] = 0;
         for (int s = 0; s < SC_STAGES; ++s) mbar_init(&sh.full_bar[s], 1);
         fence_mbar_init();
         for (uint32_t s = 0; s < uint32_t(SC_STAGES); ++s) issue(s);
     }
     __syncthreads();
 
-    // chunk state, identical in every thread
+    // chunk state (warp 0; identical in its lanes)
     uint64_t X = OPEN_UNKNOWN;   // open-cluster state; unknown until the chunk's first event
+    uint64_t c_last = 0;         // 1 + global position of the chunk's last base-code change so far
     uint64_t cnt = 0;            // records written to the segment so far
     uint64_t n_end = 0;          // ENDs seen (head included)
     uint64_t head_end = 0;       // 1 + global position of the chunk's head END, 0 = none
@@ -155,9 +173,11 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         const uint4* pf_win = reinterpret_cast<const uint4*>(plane_slots + size_t(it % SC_PSLOTS) * SC_PF_STRIDE);
         const bool interior = tile_gbase != 0 && tile_base + SC_T <= p.n_local && tile_gbase + SC_T < p.n_global;
 
-        uint32_t g_prev = 0, g_next = 0;  // the bytes around the tile: issue the global loads before waiting for the tile
+        // issued before waiting for the tile: the bytes around it and my word of the change plane
+        uint32_t g_prev = 0, g_next = 0;
         if (tid == 0) g_prev = *reinterpret_cast<const uint32_t*>(p.lcp8 + (int64_t(tile_base) - 4));
         if (tid == SC_THREADS - 1) g_next = p.lcp8[tile_base + SC_T];
+        uint64_t C = pf ? __ldg(p.chg + ((tile_base + uint64_t(tid) * SC_V + PL_PAD) >> 6)) : 0;
 
         mbar_wait(&sh.full_bar[stage], parity);
 
@@ -224,23 +244,24 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 const int64_t last = int64_t(p.n_global) - 1 - int64_t(gpos);  // END(n_global-1): host tail rule
                 if (last >= 0 && last < SC_V) E &= ~(uint64_t(1) << last);
                 E &= vm;
+                C &= vm;
             }
             const uint64_t Gp = (G << 1) | g_m1b;
             const uint64_t Ep = (E << 1) | e_prev;
             S = G & (~Gp | Ep) & vm;
         }
 
-        // ---- D = ENDs of clusters shorter than min_len: a START at the same position or up to `spread` positions before
-        uint64_t D = 0;
+        // ---- K = kept ENDs: E minus the ENDs of clusters shorter than min_len (a START at the same position or up to `spread`
+        // positions before).  Before the tile: no START assumed -- the one END that can pair with a START of an earlier tile
+        // is the tile's first event, which warp 0 tests exactly below.
+        uint64_t K = E;
         if (spread >= 0) {
             uint64_t sm = S;
-            if (spread >= 1) {  // (kernel-uniform) the previous thread's START word: neighbours by shuffle, warps through shared memory
+            if (spread >= 1) {  // (kernel-uniform) the previous lane's START word; across warps through shared memory
                 if (lane == 31) sh.wS[warp] = S;
-                if (tid == SC_THREADS - 1) sh.prev_S[pb ^ 1] = S;  // for the next tile
                 __syncthreads();
-                const uint64_t before_tile = sh.prev_S[pb];
                 uint64_t lo = shfl64(S, (lane + 31) & 31);
-                if (lane == 0) lo = warp ? sh.wS[warp - 1] : before_tile;
+                if (lane == 0) lo = warp ? sh.wS[warp - 1] : 0;
                 uint64_t hi = S;
                 int width = 1;  // sm = OR of (S << d), d = 0 .. width - 1, over the 128 bits lo:hi
                 while (2 * width <= spread + 1) {
@@ -252,34 +273,46 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 if (rest) hi |= (hi << rest) | (lo >> (64 - rest));
                 sm = hi;
             }
-            D = E & sm;
+            K = E & ~sm;
         }
 
-        // ---- ranks: one block scan of #END | #dropped << 16; last / first events of the tile
-        const uint32_t cE = __popcll(E), cD = __popcll(D);
-        const uint32_t pk = cE | (cD << 16);
+        // ---- ranks of the kept ENDs (one block scan of #kept | #ENDs << 16) and the per-warp summaries
+        const uint32_t pk = uint32_t(__popcll(K)) | (uint32_t(__popcll(E)) << 16);
         uint32_t inc = pk;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(FULL, inc, d);
             if (lane >= d) inc += o;
         }
+        const int my_ls = S ? tid * SC_V + 63 - __clzll(S) : -1;  // my last START / base-code change (tile-local)
+        const int my_lc = C ? tid * SC_V + 63 - __clzll(C) : -1;
+        int prev_s = -1, prev_c = -1;  // the nearest one in an EARLIER lane of my warp
         {
-            const int ls = __reduce_max_sync(FULL, S ? tid * SC_V + 63 - __clzll(S) : -1);
+            const uint32_t ms = __ballot_sync(FULL, S != 0) & lt_mask, mc = __ballot_sync(FULL, C != 0) & lt_mask;
+            const int vs = __shfl_sync(FULL, my_ls, ms ? 31 - __clz(ms) : lane);
+            const int vc = __shfl_sync(FULL, my_lc, mc ? 31 - __clz(mc) : lane);
+            if (ms) prev_s = vs;
+            if (mc) prev_c = vc;
+        }
+        {
+            const int ls = __reduce_max_sync(FULL, my_ls), lc = __reduce_max_sync(FULL, my_lc);
             const int le = __reduce_max_sync(FULL, E ? tid * SC_V + 63 - __clzll(E) : -1);
             const int fs = __reduce_min_sync(FULL, S ? tid * SC_V + __ffsll(S) - 1 : NO_POS);
             const int fe = __reduce_min_sync(FULL, E ? tid * SC_V + __ffsll(E) - 1 : NO_POS);
             if (lane == 31) sh.wsum[pb][warp] = inc;
             if (lane == 0) {
                 sh.wls[pb][warp] = ls;
+                sh.wlc[pb][warp] = lc;
                 sh.wle[pb][warp] = le;
                 sh.wfs[pb][warp] = fs;
                 sh.wfe[pb][warp] = fe;
             }
         }
-        __syncthreads();  // (A) per-warp summaries.  Every thread has this tile's bytes in registers and has written the records
-        // of the tile before: the stage is refilled with the chunk's tile it + SC_STAGES (plane slot: the previous tile's)
-        if (tid == 0) issue(it + SC_STAGES);
+        __syncthreads();  // (A) per-warp summaries.  Every thread has this tile's bytes in registers: the stage is refilled
+        if (tid == 0) {
+            issue(it + SC_STAGES);
+            sh.n2[pb ^ 1] = 0;  // (the previous tile's count: every thread is done with it)
+        }
 
         uint32_t base = inc - pk, tot = 0;
 #pragma unroll
@@ -288,80 +321,128 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             if (q < warp) base += ws;
             tot += ws;
         }
-        const uint32_t nE = tot & 0xffffu, nD = tot >> 16;
-        const uint32_t baseE = base & 0xffffu, baseD = base >> 16;
-        int t_ls = -1, t_le = -1, t_fs = NO_POS, t_fe = NO_POS;
-#pragma unroll
-        for (int q = 0; q < SC_WARPS; ++q) {
-            t_ls = max(t_ls, sh.wls[pb][q]);
-            t_le = max(t_le, sh.wle[pb][q]);
-            t_fs = min(t_fs, sh.wfs[pb][q]);
-            t_fe = min(t_fe, sh.wfe[pb][q]);
-        }
-        const bool has_event = t_ls >= 0 || t_le >= 0;
-        const bool carried = t_fe != NO_POS && t_fe < t_fs;  // the tile's first event is an END: its START lies before the tile
-        // (a START and an END at the same position: the START comes first, t_fe == t_fs is not carried)
+        const uint32_t nK = tot & 0xffffu, nE = tot >> 16;
+        const uint32_t baseK = base & 0xffffu;
 
-        // ---- the carried END: tested exactly on the wrapped length (ref:ebwt2clust.cpp:56,104) against the carried-in START --
-        // it is the only END of the tile that can be 65 536 or more positions from its START.  Before the chunk's first
-        // event the START is not known here: that END is the chunk's head, left to k_chunk_resolve.
-        uint32_t adj = 0;  // 1: the carried END is not written by this tile
-        const bool is_head = carried && !seen;
-        if (carried) {
-            adj = 1;
-            if (seen && X >= OPEN_BIAS) {
-                const uint32_t len = uint32_t(tile_gbase + uint64_t(t_fe) - (X - OPEN_BIAS) + 1) & 0xffffu;
-                adj = int(len) >= p.min_len ? 0u : 1u;
+        // ---- warp 0: the tile's first / last events, the carried END, the chunk state
+        if (warp == 0) {
+            const int q8 = lane & (SC_WARPS - 1);
+            const int t_ls = __reduce_max_sync(FULL, sh.wls[pb][q8]), t_le = __reduce_max_sync(FULL, sh.wle[pb][q8]);
+            const int t_lc = __reduce_max_sync(FULL, sh.wlc[pb][q8]);
+            const int t_fs = __reduce_min_sync(FULL, sh.wfs[pb][q8]), t_fe = __reduce_min_sync(FULL, sh.wfe[pb][q8]);
+            const bool has_event = t_ls >= 0 || t_le >= 0;
+            // the tile's first event is an END: its START lies before the tile (a START and an END at the same position: the
+            // START comes first, t_fe == t_fs is not carried)
+            const bool carried = t_fe != NO_POS && t_fe < t_fs;
+            // The carried END is tested exactly on the wrapped length (ref:ebwt2clust.cpp:56,104) against the carried-in START: it is
+            // the only END of the tile that can be 65 536 or more positions from its START.  Before the chunk's first event that
+            // START is not known here: the END is the chunk's head, left to k_chunk_resolve.
+            uint32_t adj = 0;  // 1: the carried END is not written by this tile
+            const bool is_head = carried && !seen;
+            if (carried) {
+                adj = 1;
+                if (seen && X >= OPEN_BIAS) {
+                    const uint32_t len = uint32_t(tile_gbase + uint64_t(t_fe) - (X - OPEN_BIAS) + 1) & 0xffffu;
+                    adj = int(len) >= p.min_len ? 0u : 1u;
+                }
+                if (is_head) head_end = tile_gbase + uint64_t(t_fe) + 1;
             }
-            if (is_head) head_end = tile_gbase + uint64_t(t_fe) + 1;
-        }
-        const uint64_t x_in = X, prefix = seg_base + cnt;
-        cnt += nE - nD - adj;
-        n_end += nE;
-        if (has_event) {
-            X = t_ls > t_le ? tile_gbase + uint64_t(t_ls) + OPEN_BIAS : OPEN_NONE;
-            seen = true;
+            if (lane == 0) {
+                sh.x_in = X;
+                sh.c_in = c_last;
+                sh.prefix = seg_base + cnt;
+                sh.adj = adj | (is_head ? 2u : 0u);
+                sh.carried = carried ? 1u : 0u;
+            }
+            cnt += nK - adj;
+            n_end += nE;
+            if (has_event) {
+                X = t_ls > t_le ? tile_gbase + uint64_t(t_ls) + OPEN_BIAS : OPEN_NONE;
+                seen = true;
+            }
+            if (t_lc >= 0) c_last = tile_gbase + uint64_t(t_lc) + 1;
         }
 
-        // ---- lists + records, one window of SC_CAP ENDs at a time (one iteration unless the tile is unusually dense)
-        for (uint32_t win = 0; win < nE; win += SC_CAP) {
-            if (win) __syncthreads();  // the previous window's lists are no longer read
-            uint64_t m = S;
-            while (m) {  // a START goes to the slot of the END it pairs with: the one with as many ENDs before it
-                const int b = __ffsll(m) - 1;
-                m &= m - 1;
-                const uint32_t q = baseE + __popcll(E & below(b)) - win;
-                if (q < uint32_t(SC_CAP)) sh.s_pos[q] = uint16_t(tid * SC_V + b);
+        // ---- the tile that holds position n_global - 2 (one per eBWT): an END there decides the reference's post-EOF phantom
+        // value whether its record is kept or not -- its START, by a backward search in the tile's START words
+        if (!interior && p.n_global - 2 - tile_gbase < uint64_t(SC_T)) {
+            sh.smask[tid] = S;
+            __syncthreads();
+            const uint32_t e_loc = uint32_t(p.n_global - 2 - tile_gbase);
+            if (uint32_t(tid) == (e_loc >> 6) && ((E >> (e_loc & 63)) & 1u)) {
+                int wi = tid;
+                uint64_t m = S & ((uint64_t(2) << (e_loc & 63)) - 1);
+                while (!m && wi > 0) m = sh.smask[--wi];
+                if (m) p.res->end_nm2_start = tile_gbase + uint64_t(wi) * SC_V + uint64_t(63 - __clzll(m)) + 1;
+                else if (!(sh.adj & 2u)) p.res->end_nm2_start = sh.x_in >= OPEN_BIAS ? sh.x_in - OPEN_BIAS + 1 : ~0ull;
+                // (the chunk's head: k_chunk_resolve answers)
             }
-            m = E;
-            while (m) {
-                const int b = __ffsll(m) - 1;
-                m &= m - 1;
-                const uint32_t qa = baseE + __popcll(E & below(b));
-                const uint32_t q = qa - win;
-                if (q < uint32_t(SC_CAP)) {
-                    const uint32_t r = qa - (baseD + __popcll(D & below(b)));
-                    sh.e_ent[q] = uint32_t(tid * SC_V + b) | (r << 14) | ((uint32_t((D >> b) & 1u) ^ 1u) << 28);
+        }
+
+        // ---- list of the kept ENDs + records, one window of SC_CAP at a time (one iteration unless the tile is unusually dense)
+        for (uint32_t win = 0; win < nK; win += SC_CAP) {
+            if (win) {  // the previous window's lists are no longer read
+                __syncthreads();
+                if (tid == 0) sh.n2[pb] = 0;
+            }
+            {
+                uint64_t m = K;
+                uint32_t r = baseK - win;  // (mod 2^32: ranks below the window fail the bound check)
+                while (m) {
+                    const int b = __ffsll(m) - 1;
+                    m &= m - 1;
+                    if (r < uint32_t(SC_CAP)) {
+                        const uint64_t upto = (uint64_t(2) << b) - 1;  // bits 0 .. b
+                        const uint64_t sb = S & upto, cb = C & upto;
+                        const int s_loc = sb ? tid * SC_V + 63 - __clzll(sb) : prev_s;
+                        const uint32_t e_loc = uint32_t(tid * SC_V + b);
+                        uint32_t ent;
+                        if (s_loc >= 0) {  // the cluster is [s_loc, e_loc]: a base-code change at a position in (s_loc, e_loc]?
+                            const int c_loc = cb ? tid * SC_V + 63 - __clzll(cb) : prev_c;
+                            ent = e_loc | ((e_loc - uint32_t(s_loc) + 1u) << 14) | (uint32_t(c_loc > s_loc) << 30);
+                        } else {           // START before my warp: resolved when the record is written; a change seen here is inside
+                            ent = e_loc | (uint32_t(cb != 0 || prev_c >= 0) << 30) | (1u << 31);
+                        }
+                        sh.e_ent[r] = ent;
+                    }
+                    ++r;
                 }
             }
-            __syncthreads();  // (B) lists
-            const uint32_t n_win = nE - win < uint32_t(SC_CAP) ? nE - win : uint32_t(SC_CAP);
+            __syncthreads();  // (B) list; warp 0's tile words
+            const uint64_t x_in = sh.x_in, prefix = sh.prefix;
+            const uint32_t adj = sh.adj & 1u;
+            const bool carried = sh.carried != 0;
+            const uint32_t n_win = nK - win < uint32_t(SC_CAP) ? nK - win : uint32_t(SC_CAP);
             for (uint32_t i = tid; i < n_win; i += SC_THREADS) {
                 const uint32_t ent = sh.e_ent[i];
-                const uint32_t e = ent & 0x3fffu, r = (ent >> 14) & 0x3fffu;
+                const uint32_t e = ent & 0x3fffu;
                 const uint64_t gend = tile_gbase + e;
-                const bool first_carried = carried && win + i == 0;
                 uint64_t st;
-                if (first_carried) {
-                    if (is_head) continue;       // k_chunk_resolve writes (or drops) it, and answers for position n_global - 2
-                    st = x_in - OPEN_BIAS;       // (x_in is an open state: START and END bits alternate)
-                } else {
-                    st = tile_gbase + sh.s_pos[i];
+                uint32_t len;
+                bool chg = (ent >> 30) & 1u, carried_end = false;
+                if (!(ent >> 31)) {
+                    len = (ent >> 14) & 0xffffu;
+                    st = gend - len + 1;
+                } else {  // nearest START / change in the warps before the END's
+                    const int wq = int(e >> 11);
+                    int s_loc = -1, c_loc = -1;
+                    for (int q = wq - 1; q >= 0 && s_loc < 0; --q) s_loc = sh.wls[pb][q];
+                    for (int q = wq - 1; q >= 0 && c_loc < 0; --q) c_loc = sh.wlc[pb][q];
+                    if (s_loc >= 0) {
+                        st = tile_gbase + uint64_t(s_loc);
+                        len = e - uint32_t(s_loc) + 1u;
+                        chg = chg || c_loc > s_loc;
+                    } else {  // no START in the tile before it: the tile's carried END
+                        carried_end = true;
+                        if (sh.adj) continue;  // the chunk's head (k_chunk_resolve writes it) / dropped by the exact test
+                        st = x_in - OPEN_BIAS;
+                        len = uint32_t(gend - st + 1) & 0xffffu;
+                        // a change in the tile before it, or after the START in an earlier tile; a wrapped length: the analysed
+                        // range [st, st + len) is not this cluster's -- the exact test decides
+                        chg = chg || c_loc >= 0 || sh.c_in > st + 1 || gend - st + 1 != uint64_t(len);
+                    }
                 }
-                if (gend + 2 == p.n_global) p.res->end_nm2_start = st + 1;  // decides the post-EOF phantom, kept or not
-                if (first_carried ? adj != 0 : !((ent >> 28) & 1u)) continue;
-                const uint32_t len = uint32_t(gend - st + 1) & 0xffffu;
-                const uint64_t o = prefix + r - ((carried && !first_carried) ? adj : 0u);
+                const uint64_t o = prefix + win + i - ((carried && !carried_end) ? adj : 0u);
                 if (o - seg_base < p.seg_cap) {
                     p.seg_start[o] = st;
                     p.seg_len[o] = uint16_t(len);
@@ -372,31 +453,41 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 if (len <= uint32_t(MAX_C_LEN)) atomicAdd(&sh.hist[len], 1u);
                 my_last_o = o;
                 my_last_len = len;
-                // fused BWT prefilter of find_variants (ref:clust2snp.cpp:402-429; planes.cuh): the one-popcount bound.  Fewer than
-                // mcov positions with a base code other than the first position's => at most one frequent code => the
-                // cluster cannot pass; everything else goes to the exact test (K3x).
-                if (pf && len >= 2 * p.pf_mcov && len <= uint32_t(MAX_C_LEN)) {
-                    bool pass = st + PL_PAD < tile_gbase;  // the 16-bit length wrapped: the analysed range lies far before this window
-                    if (!pass) {
-                        const uint64_t b_lo = st + PL_PAD - tile_gbase, b_last = b_lo + len - 1;
-                        const uint32_t q_lo = uint32_t(b_lo >> 6), q_last = uint32_t(b_last >> 6);
-                        unsigned long long f0 = 0, f1 = 0;
-                        uint32_t others = 0;
-                        for (uint32_t q = q_lo; q <= q_last; ++q) {
-                            const uint4 v = pf_win[q];
-                            const unsigned long long x0 = (uint64_t(v.y) << 32) | v.x, x1 = (uint64_t(v.w) << 32) | v.z;
-                            unsigned long long mask = ~0ull;
-                            if (q == q_lo) {
-                                mask = ~0ull << (b_lo & 63);
-                                f0 = 0ull - ((x0 >> (b_lo & 63)) & 1ull);
-                                f1 = 0ull - ((x1 >> (b_lo & 63)) & 1ull);
-                            }
-                            if (q == q_last) mask &= ~0ull >> (63 - (b_last & 63));
-                            others += __popcll(((x0 ^ f0) | (x1 ^ f1)) & mask);
-                        }
-                        pass = others >= p.pf_mcov;
+                // BWT prefilter, first level: no base-code change inside the cluster = one base code = it cannot pass.  The others are
+                // counted below, densely; a record whose analysed range lies before the plane window (wrapped length) goes
+                // straight to the exact test.
+                if (pf && chg && len >= 2 * p.pf_mcov && len <= uint32_t(MAX_C_LEN)) {
+                    if (st + PL_PAD < tile_gbase) {
+                        const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
+                        if (at < p.pf_cap) p.pf_list[at] = SurvEntry{st, st - p.global_off, len, 0u};
+                    } else {
+                        sh.list2[atomicAdd(&sh.n2[pb], 1u)] = uint32_t(st + PL_PAD - tile_gbase) | (len << 16);
                     }
-                    if (pass) {
+                }
+            }
+            if (pf) {  // second level: the one-popcount bound (planes.cuh) on the records that have a change inside, one lane each
+                __syncthreads();
+                const uint32_t n2 = sh.n2[pb];
+                for (uint32_t j = tid; j < n2; j += SC_THREADS) {
+                    const uint32_t v = sh.list2[j];
+                    const uint32_t b_lo = v & 0xffffu, len = v >> 16, b_last = b_lo + len - 1;
+                    const uint32_t q_lo = b_lo >> 6, q_last = b_last >> 6;
+                    unsigned long long f0 = 0, f1 = 0;
+                    uint32_t others = 0;
+                    for (uint32_t q = q_lo; q <= q_last; ++q) {
+                        const uint4 pv = pf_win[q];
+                        const unsigned long long x0 = (uint64_t(pv.y) << 32) | pv.x, x1 = (uint64_t(pv.w) << 32) | pv.z;
+                        unsigned long long mask = ~0ull;
+                        if (q == q_lo) {
+                            mask = ~0ull << (b_lo & 63);
+                            f0 = 0ull - ((x0 >> (b_lo & 63)) & 1ull);
+                            f1 = 0ull - ((x1 >> (b_lo & 63)) & 1ull);
+                        }
+                        if (q == q_last) mask &= ~0ull >> (63 - (b_last & 63));
+                        others += __popcll(((x0 ^ f0) | (x1 ^ f1)) & mask);
+                    }
+                    if (others >= p.pf_mcov) {  // at least mcov records differ from the first one's base code: to the exact test
+                        const uint64_t st = tile_gbase + b_lo - PL_PAD;
                         const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
                         if (at < p.pf_cap) p.pf_list[at] = SurvEntry{st, st - p.global_off, len, 0u};
                     }
@@ -413,18 +504,20 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
     for (int d = 16; d > 0; d >>= 1) acc_bases += __shfl_xor_sync(FULL, acc_bases, d);
     ChunkRec* cr = p.chunks + c;
     if (lane == 0 && acc_bases) atomicAdd(&cr->n_bases, acc_bases);
-    if (cnt && my_last_o + 1 == seg_base + cnt) cr->last_len = my_last_len;  // (one thread: the writer of the chunk's last record)
     if (tid == 0) {
         cr->own_count = cnt;
         cr->head_end = head_end;
         cr->last_state = seen ? (X >= OPEN_BIAS ? X : 1ull) : 0ull;  // 0: no event; 1: closed; >= 2: OPEN_BIAS + global START
         cr->n_end = n_end;
+        sh.prefix = seg_base + cnt;  // (for the thread that wrote the chunk's last record)
         if (c == 0 && p.tail_lcp) {
             p.res->tail_lcp_nm2 = p.tail_lcp[0];
             p.res->tail_lcp_nm1 = p.tail_lcp[1];
             p.res->tail_bwt_nm1 = p.tail_bwt[0];
         }
     }
+    __syncthreads();
+    if (my_last_o + 1 == sh.prefix && sh.prefix != seg_base) cr->last_len = my_last_len;
 }
 
 // =============================================================================================

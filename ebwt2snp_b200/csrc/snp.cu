@@ -178,6 +178,9 @@ __global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
         const uint64_t lp = ent.base;
         const uint32_t len = ent.len;
         if (len < p.min_len || len > max_len) continue;  // group-uniform
+        // The scan's prefilter only dropped clusters without any base-code change; where the shard's bit planes are at hand the
+        // one-popcount bound (planes.cuh) drops those that cannot have two frequent codes before their records are read
+        if (p.a.planes && lp + len <= p.a.n_local + MAX_C_LEN + 1 && !frequent_bound(p.a.planes, int64_t(lp), len, p.mcov)) continue;
         unsigned long long acc = 0, best = 0;
         for (uint32_t j = gl; j < len; j += EX_G) {
             const uint32_t tx = p.a.text[lp + j];

@@ -71,10 +71,13 @@ __device__ __forceinline__ uint32_t code_of(uint32_t c) {  // base_to_int, ref:i
     return uint32_t(u == 'C') + 2u * uint32_t(u == 'G') + 3u * uint32_t(u == 'T');
 }
 
+// The CHANGE plane (what the one-pass scan's prefilter reads): bit x = base code of position x differs from that of x - 1.
+// A load of [a, b) also refreshes bit b (its left neighbour is new), so ranges may arrive in any order.
 __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp, const uint8_t* __restrict__ bwt,
-                                                uint8_t* __restrict__ lcp8, uint4* __restrict__ planes, int64_t a, int64_t b,
+                                                uint8_t* __restrict__ lcp8, uint4* __restrict__ planes,
+                                                unsigned long long* __restrict__ chg, int64_t a, int64_t b,
                                                 int64_t chk_lo, int64_t chk_hi, uint32_t* __restrict__ flag) {
-    const int64_t q_first = (a + PL_PAD) >> 6, q_last = (b - 1 + PL_PAD) >> 6;
+    const int64_t q_first = (a + PL_PAD) >> 6, q_last = (b + PL_PAD) >> 6;  // (position b included: its change bit)
     const int64_t n_units = (q_last - q_first + 1) * 4;
     const int lane = threadIdx.x & 31;
     uint32_t bad = 0;
@@ -86,7 +89,10 @@ __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp
         const int64_t x0 = q * 64 - PL_PAD + (u & 3) * 16;  // my 16 positions: [x0, x0 + 16)
         const int64_t lo = x0 > a ? x0 : a, hi = x0 + 16 < b ? x0 + 16 : b;
         const uint32_t cov = (act && hi > lo) ? (((1u << (hi - lo)) - 1u) << (lo - x0)) : 0u;
-        uint32_t c0 = 0, c1 = 0;
+        // change bits: my positions in [a, b]
+        const int64_t hic = x0 + 16 < b + 1 ? x0 + 16 : b + 1;
+        const uint32_t covc = (act && bwt && hic > lo) ? (((1u << (hic - lo)) - 1u) << (lo - x0)) : 0u;
+        uint32_t c0 = 0, c1 = 0, cc = 0;
         if (cov == 0xffffu) {
             if (bwt) {
                 const uint4 v = *reinterpret_cast<const uint4*>(bwt + x0);
@@ -97,6 +103,8 @@ __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp
                     c0 |= (code & 1u) << j;
                     c1 |= (code >> 1) << j;
                 }
+                const uint32_t pc = x0 > -int64_t(PAD_L) ? code_of(bwt[x0 - 1]) : 0u;  // the position before my 16
+                cc = ((c0 ^ ((c0 << 1) | (pc & 1u))) | (c1 ^ ((c1 << 1) | (pc >> 1)))) & 0xffffu;
             }
             if (lcp8) {
                 uint32_t out[4];
@@ -115,13 +123,20 @@ __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp
                 }
                 *reinterpret_cast<uint4*>(lcp8 + x0) = make_uint4(out[0], out[1], out[2], out[3]);
             }
-        } else if (cov) {
-            for (int64_t x = lo; x < hi; ++x) {
-                if (bwt) {
+        } else if (cov | covc) {
+            if (bwt) {
+                uint32_t pc = lo > -int64_t(PAD_L) ? code_of(bwt[lo - 1]) : 0u;
+                for (int64_t x = lo; x < hic; ++x) {  // (x == b: only the change bit, read from whatever position b holds now)
                     const uint32_t code = code_of(bwt[x]);
-                    c0 |= (code & 1u) << (x - x0);
-                    c1 |= (code >> 1) << (x - x0);
+                    if (x < hi) {
+                        c0 |= (code & 1u) << (x - x0);
+                        c1 |= (code >> 1) << (x - x0);
+                    }
+                    cc |= uint32_t(code != pc) << (x - x0);
+                    pc = code;
                 }
+            }
+            for (int64_t x = lo; x < hi; ++x) {
                 if (lcp8) {
                     const uint32_t v = lcp[x];
                     if (v > 127u && x >= chk_lo && x < chk_hi) bad = 1;
@@ -132,10 +147,13 @@ __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp
         if (planes) {  // (kernel-uniform) the quad's four lanes -> one 16-byte store by the first of them
             const int l0 = lane & ~3;
             uint32_t p0lo = 0, p0hi = 0, p1lo = 0, p1hi = 0, cvlo = 0, cvhi = 0;
+            unsigned long long cw = 0, cwcov = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t b0 = __shfl_sync(0xffffffffu, c0, l0 + k), b1 = __shfl_sync(0xffffffffu, c1, l0 + k);
                 const uint32_t cv = __shfl_sync(0xffffffffu, cov, l0 + k);
+                cw |= (unsigned long long)__shfl_sync(0xffffffffu, cc, l0 + k) << (16 * k);
+                cwcov |= (unsigned long long)__shfl_sync(0xffffffffu, covc, l0 + k) << (16 * k);
                 if (k < 2) {
                     p0lo |= b0 << (16 * k);
                     p1lo |= b1 << (16 * k);
@@ -145,6 +163,10 @@ __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp
                     p1hi |= b1 << (16 * (k - 2));
                     cvhi |= cv << (16 * (k - 2));
                 }
+            }
+            if (act && (lane & 3) == 0 && cwcov) {
+                if (cwcov != ~0ull) cw = (chg[q] & ~cwcov) | (cw & cwcov);
+                chg[q] = cw;
             }
             if (act && (lane & 3) == 0 && (cvlo | cvhi)) {
                 uint4 o = make_uint4(p0lo, p0hi, p1lo, p1hi);
@@ -163,13 +185,14 @@ __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp
 }
 
 // lcp / bwt / lcp8: local position 0 of the padded arrays (a >= -PAD_L).  lcp8 == null: no byte LCP (bwt == null: no planes).
-cudaError_t launch_derive(const uint32_t* lcp, const uint8_t* bwt, uint8_t* lcp8, uint4* planes, int64_t a, int64_t b,
+cudaError_t launch_derive(const uint32_t* lcp, const uint8_t* bwt, uint8_t* lcp8, uint4* planes, uint64_t* chg, int64_t a, int64_t b,
                           int64_t chk_lo, int64_t chk_hi, uint32_t* flag, cudaStream_t stream, int sm_count) {
     if (b <= a || (!lcp8 && !bwt)) return cudaSuccess;
-    const int64_t n_units = (((b - 1 + PL_PAD) >> 6) - ((a + PL_PAD) >> 6) + 1) * 4;
+    const int64_t n_units = (((b + PL_PAD) >> 6) - ((a + PL_PAD) >> 6) + 1) * 4;
     int64_t blocks = (n_units + 255) / 256;
     if (blocks > int64_t(sm_count) * 16) blocks = int64_t(sm_count) * 16;
-    k_derive<<<unsigned(blocks), 256, 0, stream>>>(lcp8 ? lcp : nullptr, bwt, lcp8, bwt ? planes : nullptr, a, b, chk_lo, chk_hi, flag);
+    k_derive<<<unsigned(blocks), 256, 0, stream>>>(lcp8 ? lcp : nullptr, bwt, lcp8, bwt ? planes : nullptr,
+                                                   reinterpret_cast<unsigned long long*>(bwt ? chg : nullptr), a, b, chk_lo, chk_hi, flag);
     return cudaGetLastError();
 }
 
