@@ -134,9 +134,6 @@ static NcclApi* nccl_api() {
 }
 constexpr int NCCL_UINT64 = 5;  // ncclUint64 (nccl.h: ncclDataType_t)
 
-// one exchange row per shard: the scan's device accumulators + what the other ranks cannot know
-constexpr size_t XR_DEV_WORDS = sizeof(ClusterDev) / 8;
-constexpr size_t XR_WORDS = XR_DEV_WORDS + 4;  // + n_local, global_off, lcp_bytes, reserved
 
 struct e2s_comm {
     e2s_ctx* ctx = nullptr;
