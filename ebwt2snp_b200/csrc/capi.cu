@@ -15,7 +15,7 @@
 
 #include "common.cuh"
 #include "internal.h"
-#include "planes.cuh"
+#include "merge.cuh"
 #include "planes.cuh"
 
 using namespace e2s;
@@ -77,6 +77,12 @@ struct e2s_shard {
     ChunkSeg* d_segs = nullptr;      // ... and where k_chunk_resolve put each segment in the position-ordered list
     bool contiguous = true;          // d_start / d_len hold the record list (false: it still lies in the segments)
     bool adopt_put = false;          // the records adopted from the merge have been appended to d_start / d_len
+    bool pf_has_adopted = false;     // ... and the survivor list already holds them (k_merge_stats appended them)
+    bool last_one_pass = false;      // what the last scan used
+    uint64_t pf_want = 0;            // survivor-list capacity asked for after an overflow
+    uint64_t* d_row = nullptr;       // this shard's exchange row (XR_WORDS) when there is no communicator
+    MergeOut* d_mout = nullptr;      // k_merge_stats output
+    MergeOut* h_mout = nullptr;      // ... its pinned host copy
     ClusterDev* d_res = nullptr;
     ClusterDev h_res;           // host copy of the last scan's accumulators (incl. length histogram)
     ClusterDev* h_pin = nullptr; // pinned staging for that copy
@@ -334,6 +340,9 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->d_start);
     cudaFree(s->d_len);
     cudaFree(s->d_desc);
+    cudaFree(s->d_row);
+    cudaFree(s->d_mout);
+    cudaFreeHost(s->h_mout);
     cudaFree(s->d_seg_start);
     cudaFree(s->d_seg_len);
     cudaFree(s->d_chunks);
@@ -639,17 +648,6 @@ int e2s_cluster_prefilter(e2s_shard* s, int mcov_out) {
     return E2S_OK;
 }
 
-__global__ void k_pack_exchange(const ClusterDev* res, uint64_t n_local, uint64_t global_off, uint64_t lcp_bytes, uint64_t* row) {
-    const uint64_t* src = reinterpret_cast<const uint64_t*>(res);
-    for (uint32_t i = threadIdx.x; i < XR_DEV_WORDS; i += blockDim.x) row[i] = src[i];
-    if (threadIdx.x == 0) {
-        row[XR_DEV_WORDS + 0] = n_local;
-        row[XR_DEV_WORDS + 1] = global_off;
-        row[XR_DEV_WORDS + 2] = lcp_bytes;
-        row[XR_DEV_WORDS + 3] = 0;
-    }
-}
-
 static void summary_from_row(const uint64_t* row, uint64_t n_global, uint32_t k, int32_t min_len, e2s_cluster_summary* sum) {
     const ClusterDev& h = *reinterpret_cast<const ClusterDev*>(row);
     memset(sum, 0, sizeof *sum);
@@ -673,16 +671,15 @@ static void summary_from_row(const uint64_t* row, uint64_t n_global, uint32_t k,
 // K1 + K2.  cm == NULL: this shard's accumulators come back with one device-to-host copy.  cm != NULL (one process per
 // GPU): the rows of ALL shards come back instead -- packed on the device, all-gathered by NCCL on the same stream, one
 // copy, one synchronisation -- and are left in cm->h_recv for the caller (e2s_pipeline_sharded).
-static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summary* sum, e2s_comm* cm) {
-    if (!s || !sum) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_cluster_run: NULL argument");
+// Everything the scan launches, enqueued on the context's stream without a synchronisation: accumulators zeroed, K1 + K2
+// (k_lcp_flags + k_cluster_emit) or the one-pass k_cluster_scan + k_chunk_resolve.  s->last_one_pass says which.
+static int scan_enqueue(e2s_shard* s, uint32_t k, int32_t min_len) {
     e2s_ctx* c = s->ctx;
-    if (k == 0) return fail(c, E2S_ERR_ARG, "k must be >= 1 (the CLI maps 0 to the default 16)");
-    CU(c, cudaSetDevice(c->device));
     const char* env = getenv("E2S_CLUSTER_VARIANT");
     s->variant = env ? atoi(env) : 0;
     // One pass over the byte LCP (k_cluster_scan) whenever the shard has it and min_len allows the bit-parallel length
     // test; else the two-kernel path on the 4-byte LCP (k_lcp_flags + k_cluster_emit).  E2S_SCAN_LEGACY=1 forces the latter.
-    const bool one_pass = s->sealed && s->lcp8_ok && min_len <= 33 && !getenv("E2S_SCAN_LEGACY");
+    const bool one_pass = s->last_one_pass = s->sealed && s->lcp8_ok && min_len <= 33 && !getenv("E2S_SCAN_LEGACY");
     const uint64_t num_tiles = emit_num_tiles(s->n_local);
     if (one_pass) {
         if (!s->d_chunks) {
@@ -731,113 +728,117 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
         CU(c, le);
         ++c->launches;
     }
+    CU(c, cudaMemsetAsync(s->d_res, 0, sizeof(ClusterDev), c->stream));
+    if (!one_pass) CU(c, cudaMemsetAsync(s->d_desc, 0, s->desc_cap * 8, c->stream));
+    EmitParams p;
+    p.s_words = s->d_flags;
+    p.e_words = s->d_flags + s->flag_words;
+    p.num_tiles = num_tiles;
+    p.global_off = s->global_off;
+    p.n_global = s->n_global;
+    p.min_len = min_len;
+    p.out_start = s->d_start;
+    p.out_len = s->d_len;
+    p.cap = s->rec_cap - 4;  // room for adopted records
+    p.desc = s->d_desc;
+    p.planes = s->d_planes;
+    p.pf_mcov = (s->pf_arm && s->sealed) ? s->pf_arm : 0;
+    p.pf_list = nullptr;
+    p.pf_cap = 0;
+    if (p.pf_mcov) {
+        uint64_t want = (one_pass ? s->seg_cap * s->n_chunks : s->rec_cap) / 16 + 4096;
+        if (const char* dbg = getenv("E2S_PF_CAPACITY")) {  // test hook: a tiny list forces the overflow -> two-phase fallback
+            const uint64_t v = strtoull(dbg, nullptr, 10);
+            if (v) {
+                want = v;
+                if (s->pf_cap > v) s->pf_cap = v;  // also shrink the advertised capacity of an existing buffer
+            }
+        }
+        if (want > s->pf_cap) {
+            cudaFree(s->d_pf_list);
+            s->d_pf_list = nullptr;
+            s->pf_cap = 0;
+            if (cudaMalloc(reinterpret_cast<void**>(&s->d_pf_list), (want + 8) * sizeof(SurvEntry)) != cudaSuccess)
+                return fail(c, E2S_ERR_NOMEM, "prefilter survivor list");
+            s->pf_cap = want;
+        }
+        p.pf_list = s->d_pf_list;
+        p.pf_cap = s->pf_cap > 4 ? s->pf_cap - 4 : 0;  // (room for the records k_merge_stats adopts)
+    }
+    p.dbg = nullptr;
+    p.res = s->d_res;
+    const bool is_last = s->global_off + s->n_local == s->n_global;
+    p.tail_lcp = is_last ? s->lcp + s->n_local - 2 : nullptr;
+    p.tail_bwt = is_last ? s->bwt + s->n_local - 1 : nullptr;
+    if (one_pass) {
+        CU(c, cudaMemsetAsync(s->d_chunks, 0, size_t(s->n_chunks) * sizeof(ChunkRec), c->stream));
+        Scan8Params sp;
+        sp.lcp8 = s->lcp8_a + PAD_L;
+        sp.planes = s->d_planes;
+        sp.chg = s->d_chg;
+        sp.n_local = s->n_local;
+        sp.global_off = s->global_off;
+        sp.n_global = s->n_global;
+        sp.k = k;
+        sp.min_len = min_len;
+        sp.num_tiles = 0;
+        sp.n_chunks = s->n_chunks;
+        sp.tiles_per_chunk = s->tiles_per_chunk;
+        sp.seg_start = s->d_seg_start;
+        sp.seg_len = s->d_seg_len;
+        sp.seg_cap = s->seg_cap;
+        sp.chunks = s->d_chunks;
+        sp.pf_mcov = p.pf_mcov;
+        sp.pf_list = p.pf_list;
+        sp.pf_cap = p.pf_cap;
+        sp.res = s->d_res;
+        sp.tail_lcp = p.tail_lcp;
+        sp.tail_bwt = p.tail_bwt;
+        c->timer.begin(E2S_KERNEL_SCAN1, c->stream);
+        cudaError_t le = launch_scan(sp, s->alloc_r, c->stream);
+        c->timer.end(c->stream);
+        CU(c, le);
+        ResolveParams rp;
+        rp.chunks = s->d_chunks;
+        rp.segs = s->d_segs;
+        rp.n_chunks = s->n_chunks;
+        rp.min_len = min_len;
+        rp.global_off = s->global_off;
+        rp.n_global = s->n_global;
+        rp.init_state = s->global_off == 0 ? 0 : 1;
+        rp.planes = s->d_planes;
+        rp.pf_mcov = p.pf_mcov;
+        rp.pf_list = p.pf_list;
+        rp.pf_cap = p.pf_cap;
+        rp.res = s->d_res;
+        CU(c, launch_chunk_resolve(rp, c->stream));
+        ++c->launches;
+    } else {
+        c->timer.begin(E2S_KERNEL_EMIT, c->stream);
+        cudaError_t le = launch_emit(p, c->sm_count, c->stream);
+        c->timer.end(c->stream);
+        CU(c, le);
+    }
+    ++c->launches;
+    return E2S_OK;
+}
+
+static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summary* sum, e2s_comm* cm) {
+    if (!s || !sum) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_cluster_run: NULL argument");
+    e2s_ctx* c = s->ctx;
+    if (k == 0) return fail(c, E2S_ERR_ARG, "k must be >= 1 (the CLI maps 0 to the default 16)");
+    CU(c, cudaSetDevice(c->device));
     if (!s->h_pin) CU(c, cudaHostAlloc(reinterpret_cast<void**>(&s->h_pin), sizeof(ClusterDev), cudaHostAllocDefault));
     ClusterDev& h = *s->h_pin;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        CU(c, cudaMemsetAsync(s->d_res, 0, sizeof(ClusterDev), c->stream));
-        if (!one_pass) CU(c, cudaMemsetAsync(s->d_desc, 0, s->desc_cap * 8, c->stream));
-        EmitParams p;
-        p.s_words = s->d_flags;
-        p.e_words = s->d_flags + s->flag_words;
-        p.num_tiles = num_tiles;
-        p.global_off = s->global_off;
-        p.n_global = s->n_global;
-        p.min_len = min_len;
-        p.out_start = s->d_start;
-        p.out_len = s->d_len;
-        p.cap = s->rec_cap - 4;  // room for adopted records
-        p.desc = s->d_desc;
-        p.planes = s->d_planes;
-        p.pf_mcov = (s->pf_arm && s->sealed) ? s->pf_arm : 0;
-        p.pf_list = nullptr;
-        p.pf_cap = 0;
-        if (p.pf_mcov) {
-            uint64_t want = (one_pass ? s->seg_cap * s->n_chunks : s->rec_cap) / 16 + 4096;
-            if (const char* dbg = getenv("E2S_PF_CAPACITY")) {  // test hook: a tiny list forces the overflow -> two-phase fallback
-                const uint64_t v = strtoull(dbg, nullptr, 10);
-                if (v) {
-                    want = v;
-                    if (s->pf_cap > v) s->pf_cap = v;  // also shrink the advertised capacity of an existing buffer
-                }
-            }
-            if (want > s->pf_cap) {
-                cudaFree(s->d_pf_list);
-                s->d_pf_list = nullptr;
-                s->pf_cap = 0;
-                if (cudaMalloc(reinterpret_cast<void**>(&s->d_pf_list), (want + 8) * sizeof(SurvEntry)) != cudaSuccess)
-                    return fail(c, E2S_ERR_NOMEM, "prefilter survivor list");
-                s->pf_cap = want;
-            }
-            p.pf_list = s->d_pf_list;
-            p.pf_cap = s->pf_cap;
-        }
-        p.dbg = nullptr;
-        uint64_t* d_dbg = nullptr;
-        const char* dbg_path = getenv("E2S_EMIT_DEBUG");  // developer aid: per-chunk phase time stamps of K2
-        if (dbg_path && cudaMalloc(reinterpret_cast<void**>(&d_dbg), emit_desc_words() * 4) == cudaSuccess) {
-            cudaMemsetAsync(d_dbg, 0, emit_desc_words() * 4, c->stream);
-            p.dbg = d_dbg;
-        }
-        p.res = s->d_res;
-        const bool is_last = s->global_off + s->n_local == s->n_global;
-        p.tail_lcp = is_last ? s->lcp + s->n_local - 2 : nullptr;
-        p.tail_bwt = is_last ? s->bwt + s->n_local - 1 : nullptr;
-        if (one_pass) {
-            CU(c, cudaMemsetAsync(s->d_chunks, 0, size_t(s->n_chunks) * sizeof(ChunkRec), c->stream));
-            Scan8Params sp;
-            sp.lcp8 = s->lcp8_a + PAD_L;
-            sp.planes = s->d_planes;
-            sp.chg = s->d_chg;
-            sp.n_local = s->n_local;
-            sp.global_off = s->global_off;
-            sp.n_global = s->n_global;
-            sp.k = k;
-            sp.min_len = min_len;
-            sp.num_tiles = 0;
-            sp.n_chunks = s->n_chunks;
-            sp.tiles_per_chunk = s->tiles_per_chunk;
-            sp.seg_start = s->d_seg_start;
-            sp.seg_len = s->d_seg_len;
-            sp.seg_cap = s->seg_cap;
-            sp.chunks = s->d_chunks;
-            sp.pf_mcov = p.pf_mcov;
-            sp.pf_list = p.pf_list;
-            sp.pf_cap = p.pf_cap;
-            sp.res = s->d_res;
-            sp.tail_lcp = p.tail_lcp;
-            sp.tail_bwt = p.tail_bwt;
-            c->timer.begin(E2S_KERNEL_SCAN1, c->stream);
-            cudaError_t le = launch_scan(sp, s->alloc_r, c->stream);
-            c->timer.end(c->stream);
-            CU(c, le);
-            ResolveParams rp;
-            rp.chunks = s->d_chunks;
-            rp.segs = s->d_segs;
-            rp.n_chunks = s->n_chunks;
-            rp.min_len = min_len;
-            rp.global_off = s->global_off;
-            rp.n_global = s->n_global;
-            rp.init_state = s->global_off == 0 ? 0 : 1;
-            rp.planes = s->d_planes;
-            rp.pf_mcov = p.pf_mcov;
-            rp.pf_list = p.pf_list;
-            rp.pf_cap = p.pf_cap;
-            rp.res = s->d_res;
-            CU(c, launch_chunk_resolve(rp, c->stream));
-            ++c->launches;
-        } else {
-            c->timer.begin(E2S_KERNEL_EMIT, c->stream);
-            cudaError_t le = launch_emit(p, c->sm_count, c->stream);
-            c->timer.end(c->stream);
-            CU(c, le);
-        }
-        ++c->launches;
+        int erc = scan_enqueue(s, k, min_len);
+        if (erc) return erc;
+        const bool one_pass = s->last_one_pass;
         bool any_overflow = false;
         uint64_t max_written = 0;
         if (cm) {
             NcclApi* na = nccl_api();
-            k_pack_exchange<<<1, 256, 0, c->stream>>>(s->d_res, s->n_local, s->global_off, uint64_t(s->lay_x), cm->d_send);
-            CU(c, cudaGetLastError());
+            CU(c, launch_pack_exchange(s->d_res, s->n_local, s->global_off, uint64_t(s->lay_x), cm->d_send, c->stream));
             ++c->launches;
             const int nr = na->AllGather(cm->d_send, cm->d_recv, XR_WORDS, NCCL_UINT64, cm->nccl, c->stream);
             if (nr != 0) return fail(c, E2S_ERR_CUDA, std::string("ncclAllGather: ") + (na->GetErrorString ? na->GetErrorString(nr) : "error"));
@@ -846,29 +847,18 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
             memcpy(&h, cm->h_recv + size_t(cm->rank) * XR_WORDS, sizeof h);
             for (int g = 0; g < cm->world; ++g) {  // every rank sees every overflow flag: all of them repeat the round together
                 const ClusterDev& hg = *reinterpret_cast<const ClusterDev*>(cm->h_recv + size_t(g) * XR_WORDS);
-                any_overflow |= hg.overflow != 0;
+                any_overflow |= (hg.overflow & 1) != 0;  // (bit 1 = survivor list: not fatal here, find_events then runs its own prefilter)
                 if (hg.n_written > max_written) max_written = hg.n_written;
             }
         } else {
             CU(c, cudaMemcpyAsync(&h, s->d_res, sizeof h, cudaMemcpyDeviceToHost, c->stream));
             CU(c, cudaStreamSynchronize(c->stream));
-            any_overflow = h.overflow != 0;
+            any_overflow = (h.overflow & 1) != 0;
             max_written = h.n_written;
-        }
-        if (d_dbg) {
-            std::vector<uint64_t> hd(emit_desc_words() / 2);
-            cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
-            if (FILE* f = fopen(dbg_path, "w")) {
-                for (size_t i = 0; i + 3 < hd.size(); i += 4)
-                    if (hd[i]) fprintf(f, "%zu %llu %llu %llu %llu\n", i / 4, (unsigned long long)hd[i], (unsigned long long)hd[i + 1],
-                                       (unsigned long long)hd[i + 2], (unsigned long long)hd[i + 3]);
-                fclose(f);
-            }
-            cudaFree(d_dbg);
         }
         if (!any_overflow) break;
         if (attempt == 1) return fail(c, E2S_ERR_STATE, "record buffer overflow after resize");
-        if (h.overflow || !cm) {
+        if ((h.overflow & 1) || !cm) {
             int rc;
             if (one_pass) {  // the fullest segment decides (the chunks keep counting past their capacity)
                 std::vector<ChunkRec> hc(s->n_chunks);
@@ -901,11 +891,12 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
     s->h_res = h;
     s->pf_mcov = (s->pf_arm && s->sealed) ? s->pf_arm : 0;
     s->pf_count = h.n_pf;
-    s->pf_ok = s->pf_mcov != 0 && h.n_pf <= s->pf_cap;
+    s->pf_ok = s->pf_mcov != 0 && !(h.overflow & 2) && h.n_pf + 4 <= s->pf_cap;
+    s->pf_has_adopted = false;
     s->have_scan_stats = true;
     s->m_own = h.n_written;
     s->m_list = h.n_written;
-    s->contiguous = !one_pass;
+    s->contiguous = !s->last_one_pass;
     s->have_clusters = true;
     s->staged = false;
     s->finalized = false;
@@ -920,92 +911,24 @@ int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summa
 
 // Host-only: chain the shards' open-cluster states, resolve head records, apply the tail rule with
 // the post-EOF phantom record (ref:ebwt2clust.cpp:90-135).
+static const char* merge_message(int rc) {
+    switch (rc) {
+        case MERGE_NOT_PARTITION: return "e2s_cluster_merge: shards are not a partition of [0, n_global)";
+        case MERGE_NOT_COVER: return "e2s_cluster_merge: shards do not cover n_global";
+        case MERGE_END_WITHOUT_START: return "e2s_cluster_merge: END without START (inconsistent summaries)";
+        case MERGE_EMPTY: return "empty .clusters (the reference divides by zero here)";
+        case MERGE_BAD_MCOV: return "2*mcov_out outside [0,150]";
+        default: return "merge failed";
+    }
+}
+static int merge_status(int rc) {
+    return rc == MERGE_END_WITHOUT_START ? E2S_ERR_STATE : ((rc == MERGE_EMPTY || rc == MERGE_BAD_MCOV) ? E2S_ERR_UNSUPPORTED : E2S_ERR_ARG);
+}
+
 int e2s_cluster_merge(const e2s_cluster_summary* all, int n_shards, int my, e2s_cluster_merged* out) {
     if (!all || !out || n_shards < 1 || my < 0 || my >= n_shards) return fail(nullptr, E2S_ERR_ARG, "e2s_cluster_merge: bad argument");
-    memset(out, 0, sizeof *out);
-    const uint64_t n = all[0].n_global;
-    const uint32_t k = uint32_t(all[0].k);
-    const int64_t min_len = int64_t(all[0].min_len);
-    uint64_t expect = 0;
-    for (int g = 0; g < n_shards; ++g) {
-        if (all[g].global_off != expect || all[g].n_global != n || all[g].k != all[0].k || all[g].min_len != all[0].min_len)
-            return fail(nullptr, E2S_ERR_ARG, "e2s_cluster_merge: shards are not a partition of [0, n_global)");
-        expect += all[g].n_local;
-    }
-    if (expect != n) return fail(nullptr, E2S_ERR_ARG, "e2s_cluster_merge: shards do not cover n_global");
-    auto owner = [&](uint64_t pos) {
-        for (int g = 0; g < n_shards; ++g)
-            if (pos < all[g].global_off + all[g].n_local) return g;
-        return n_shards - 1;  // position n (phantom-only cluster) stays with the last shard
-    };
-    auto adopt = [&](uint64_t st, uint64_t len) {
-        if (owner(st) == my && out->n_adopt < 3) {
-            out->adopt_start[out->n_adopt] = st;
-            out->adopt_len[out->n_adopt] = len;
-            out->n_adopt++;
-        }
-    };
-    uint64_t s_open = 0;  // 1 + global start of the open cluster, 0 = none
-    uint64_t offset = 0, closed = 0;
-    uint64_t last_head_start = 0;
-    for (int g = 0; g < n_shards; ++g) {
-        if (g == my) out->record_offset = offset;
-        if (all[g].head_end) {
-            if (!s_open) return fail(nullptr, E2S_ERR_STATE, "e2s_cluster_merge: END without START (inconsistent summaries)");
-            const uint64_t st = s_open - 1, en = all[g].head_end - 1;
-            const uint64_t len = (en - st + 1) & 0xffff;
-            const bool written = int64_t(len) >= min_len;
-            if (g == my) {
-                out->n_prepend = 1;
-                out->prepend_start = st;
-                out->prepend_len = len;
-                out->prepend_written = written;
-            }
-            if (written) {
-                offset += 1;
-                adopt(st, len);
-            }
-            last_head_start = st;
-            s_open = 0;
-        }
-        offset += all[g].n_written;
-        closed += all[g].n_end;
-        if (all[g].any_event) s_open = all[g].open_start;
-    }
-    // tail: position n-1 with the phantom record as its right neighbour, then position n
-    const e2s_cluster_summary& L = all[n_shards - 1];
-    const uint32_t e1 = uint32_t(L.tail_lcp_nm2), e2 = uint32_t(L.tail_lcp_nm1);
-    uint32_t P;
-    if (L.end_nm2_start == ~0ull) P = uint32_t(last_head_start);
-    else if (L.end_nm2_start) P = uint32_t(L.end_nm2_start - 1);
-    else P = (e2 & 0xFFFFFF00u) | uint32_t(L.tail_bwt_nm1 & 0xff);
-    // the failed read only touches a temporary of the LCP field's width (ref:include.hpp:126-155)
-    if (L.lcp_bytes == 1) P &= 0xFFu;
-    else if (L.lcp_bytes == 2) P &= 0xFFFFu;
-    out->phantom_lcp = P;
-    uint32_t na = 0;
-    auto tail_record = [&](uint64_t st, uint64_t en) {
-        const uint64_t len = (en - st + 1) & 0xffff;
-        ++closed;
-        if (int64_t(len) >= min_len) {
-            offset += 1;
-            if (my == n_shards - 1) {
-                out->append_start[na] = st;
-                out->append_len[na] = len;
-                ++na;
-            }
-            adopt(st, len);
-        }
-    };
-    if (s_open && ((e1 > e2 && e2 <= P) || P < k)) {
-        tail_record(s_open - 1, n - 1);
-        s_open = 0;
-    }
-    if (!s_open && P >= k) s_open = n + 1;
-    if (s_open) tail_record(s_open - 1, n);
-    out->n_append = na;
-    out->total_written = offset;
-    out->n_clust_out = closed;
+    const int rc = merge_core(all, n_shards, my, out);  // merge.cuh: the same code k_merge_stats runs on the device
+    if (rc != MERGE_OK) return fail(nullptr, merge_status(rc), merge_message(rc));
     return E2S_OK;
 }
 
@@ -1207,21 +1130,8 @@ int e2s_statistics(e2s_shard* s, e2s_stats* st) {
 // ref:clust2snp.cpp:889-946: the last record is counted twice; then the pval loop
 int e2s_statistics_finish(e2s_stats* st, uint64_t last_len, int mcov_out, double pval) {
     if (!st) return fail(nullptr, E2S_ERR_ARG, "NULL argument");
-    if (st->n_clust == 0) return fail(nullptr, E2S_ERR_UNSUPPORTED, "empty .clusters (the reference divides by zero here)");
-    if (last_len <= E2S_MAX_C_LEN) st->hist[last_len]++;
-    st->n_clust++;
-    st->n_bases += last_len;
-    st->max_len = 0;
-    for (int i = 0; i < E2S_HIST_BINS; ++i)
-        if (st->hist[i]) st->max_len = uint64_t(i);
-    int mcl = 2 * mcov_out;
-    if (mcl < 0 || mcl > E2S_MAX_C_LEN) return fail(nullptr, E2S_ERR_UNSUPPORTED, "2*mcov_out outside [0,150]");
-    uint64_t cumulative = st->hist[mcl] * uint64_t(mcl);
-    while (double(cumulative) / double(st->n_bases) < pval && mcl < E2S_MAX_C_LEN) {
-        mcl++;
-        cumulative += st->hist[mcl] * uint64_t(mcl);
-    }
-    st->max_clust_length = mcl;
+    const int rc = stats_finish_core(st, last_len, mcov_out, pval);  // merge.cuh
+    if (rc != MERGE_OK) return fail(nullptr, merge_status(rc), merge_message(rc));
     return E2S_OK;
 }
 
@@ -1273,15 +1183,18 @@ void e2s_snp_default_params(e2s_snp_params* p) {
     p->pval = 0.99;
 }
 
+static bool snp_params_ok(const e2s_snp_params* p) {
+    return !(p->k_left < 1 || p->k_left > E2S_MAX_K || p->k_right < 1 || p->k_right > E2S_MAX_K || p->max_gap < 1 ||
+             p->max_gap > p->k_left || p->max_gap > 255 || p->mcov_out < 1 || 2 * p->mcov_out > E2S_MAX_C_LEN || p->consensus_reads < 1);
+}
+
 int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length, e2s_snp_counts* counts) {
     if (!s || !p || !counts) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
     e2s_ctx* c = s->ctx;
     if (!s->have_clusters || !s->finalized) return fail(c, E2S_ERR_STATE, "clusters not computed / staged yet");
     if (!s->sealed) return fail(c, E2S_ERR_STATE, "call e2s_shard_seal after loading the shard");
     if (!c->d_bases) return fail(c, E2S_ERR_STATE, "stage the reads first (e2s_reads_stage)");
-    if (p->k_left < 1 || p->k_left > E2S_MAX_K || p->k_right < 1 || p->k_right > E2S_MAX_K || p->max_gap < 1 ||
-        p->max_gap > p->k_left || p->max_gap > 255 || p->mcov_out < 1 || 2 * p->mcov_out > E2S_MAX_C_LEN ||
-        p->consensus_reads < 1 || max_clust_length > E2S_MAX_C_LEN)
+    if (!snp_params_ok(p) || max_clust_length > E2S_MAX_C_LEN)
         return fail(c, E2S_ERR_UNSUPPORTED, "clust2snp parameters outside the supported range (DESIGN.md)");
     CU(c, cudaSetDevice(c->device));
     s->have_events = false;
@@ -1314,15 +1227,17 @@ int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length,
     uint64_t pre_count = 0;
     if (!s->staged && s->pf_ok && s->pf_mcov == uint32_t(p->mcov_out) && max_clust_length <= E2S_MAX_C_LEN) {
         SurvEntry extra[4];
-        const uint64_t n_extra = s->merged.n_adopt;  // <= 3 records the merge created and this shard analyses
+        const uint64_t n_extra = s->pf_has_adopted ? 0 : s->merged.n_adopt;  // <= 3 records the merge created and this shard analyses
         for (uint64_t i = 0; i < n_extra && i < 4; ++i)
             extra[i] = SurvEntry{s->merged.adopt_start[i], s->merged.adopt_start[i] - s->global_off, uint32_t(s->merged.adopt_len[i]), 0u};
         if (n_extra) {
             CU(c, cudaMemcpyAsync(s->d_pf_list + s->pf_count, extra, n_extra * sizeof(SurvEntry), cudaMemcpyHostToDevice, c->stream));
             CU(c, cudaStreamSynchronize(c->stream));  // (extra[] lives on this stack frame)
         }
+        s->pf_has_adopted = true;
+        s->pf_count += n_extra;
         pre_list = s->d_pf_list;
-        pre_count = s->pf_count + n_extra;
+        pre_count = s->pf_count;
     } else {
         int rc = ensure_contiguous(s);  // the two-phase path walks the record list: own records, then the adopted ones
         if (rc) return rc;
@@ -1430,6 +1345,183 @@ void e2s_free(void* p) { free(p); }
 // end to end over host buffers
 // ---------------------------------------------------------------------------------------------
 // ebwt2clust + clust2snp on a sealed shard that holds the whole eBWT (one GPU), reads already staged
+// Both phases on a sealed resident shard without leaving the stream in between: scan (+ the shard's exchange row, all-
+// gathered by NCCL when there is a communicator) -> k_merge_stats (merge of all shards, tail / phantom rule, statistics(),
+// max_clust_length: device memory) -> K3x / K3b / K4 on the scan's survivor list -> ONE copy of the results, ONE
+// synchronisation.  Needs the fused prefilter (valid -m); the caller falls back to the host-driven sequence otherwise.
+static int pipeline_step(e2s_shard* s, e2s_comm* cm, uint32_t k, int32_t min_len, const e2s_snp_params* p, e2s_cluster_merged* mg_out,
+                         e2s_stats* st_out, e2s_snp_counts* cnt_out) {
+    e2s_ctx* c = s->ctx;
+    if (k == 0) return fail(c, E2S_ERR_ARG, "k must be >= 1 (the CLI maps 0 to the default 16)");
+    if (!s->sealed) return fail(c, E2S_ERR_STATE, "call e2s_shard_seal after loading the shard");
+    if (!c->d_bases) return fail(c, E2S_ERR_STATE, "stage the reads first (e2s_reads_stage)");
+    if (!snp_params_ok(p)) return fail(c, E2S_ERR_UNSUPPORTED, "clust2snp parameters outside the supported range (DESIGN.md)");
+    CU(c, cudaSetDevice(c->device));
+    const int world = cm ? cm->world : 1, my = cm ? cm->rank : 0;
+    if (world > MERGE_MAX_SHARDS) return fail(c, E2S_ERR_UNSUPPORTED, "more shards than k_merge_stats handles");
+    if (!s->d_mout) {
+        CU(c, cudaMalloc(reinterpret_cast<void**>(&s->d_mout), sizeof(MergeOut)));
+        CU(c, cudaHostAlloc(reinterpret_cast<void**>(&s->h_mout), sizeof(MergeOut), cudaHostAllocDefault));
+        CU(c, cudaMalloc(reinterpret_cast<void**>(&s->d_row), XR_WORDS * 8));
+    }
+    if (!s->h_pin) CU(c, cudaHostAlloc(reinterpret_cast<void**>(&s->h_pin), sizeof(ClusterDev), cudaHostAllocDefault));
+    ClusterDev& h = *s->h_pin;
+    MergeOut& mo = *s->h_mout;
+    const uint32_t arm_before = s->pf_arm;
+    s->pf_arm = uint32_t(p->mcov_out);
+    s->have_events = false;
+    s->events.clear();
+    SnpArrays a;
+    a.lcp = s->lcp;
+    a.text = s->text;
+    a.suff = s->suff;
+    a.bwt = s->bwt;
+    a.planes = s->d_planes;
+    a.n_local = s->n_local;
+    a.global_off = s->global_off;
+    a.cl_start = nullptr;  // (phase 2 starts from the survivor list: the record list is not walked)
+    a.cl_len = nullptr;
+    a.m = 0;
+    const char* err = "";
+    int rc = E2S_OK;
+    for (int attempt = 0;; ++attempt) {
+        if ((rc = scan_enqueue(s, k, min_len))) break;
+        uint64_t* send = cm ? cm->d_send : s->d_row;
+        const uint64_t* rows = send;
+        if ((rc = launch_pack_exchange(s->d_res, s->n_local, s->global_off, uint64_t(s->lay_x), send, c->stream) == cudaSuccess ? 0 : 1)) {
+            rc = fail(c, E2S_ERR_CUDA, "k_pack_exchange");
+            break;
+        }
+        if (cm) {
+            NcclApi* na = nccl_api();
+            const int nr = na->AllGather(cm->d_send, cm->d_recv, XR_WORDS, NCCL_UINT64, cm->nccl, c->stream);
+            if (nr != 0) {
+                rc = fail(c, E2S_ERR_CUDA, std::string("ncclAllGather: ") + (na->GetErrorString ? na->GetErrorString(nr) : "error"));
+                break;
+            }
+            rows = cm->d_recv;
+        }
+        MergeParams mp;
+        mp.rows = reinterpret_cast<const unsigned long long*>(rows);
+        mp.world = world;
+        mp.my = my;
+        mp.n_global = s->n_global;
+        mp.k = k;
+        mp.min_len = min_len;
+        mp.mcov = p->mcov_out;
+        mp.pval = p->pval;
+        mp.own_global_off = s->global_off;
+        mp.out = s->d_mout;
+        mp.pf_list = s->d_pf_list;
+        mp.pf_cap = s->pf_cap;
+        mp.res = s->d_res;
+        const char* where = "k_merge_stats";
+        cudaError_t e = launch_merge_stats(mp, c->stream);
+        c->launches += 2;
+        // phase 2 from the survivor list, its length and max_clust_length read on the device
+        e2s_snp_counts counts;
+        if (e == cudaSuccess) {
+            where = "phase 2 kernels";
+            e = snp_run(s->work, a, *p, E2S_MAX_C_LEN, c->d_bases, c->d_off, c->n_reads, c->sm_count, c->stream, &counts, &c->launches, &err,
+                        &c->timer, s->d_pf_list, s->pf_cap, &s->d_res->n_pf, &s->d_mout->total.max_clust_length, false);
+        }
+        if (e == cudaSuccess) {
+            where = "copy of the scan accumulators";
+            e = cudaMemcpyAsync(&h, s->d_res, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+        }
+        if (e == cudaSuccess) {
+            where = "copy of the merge result";
+            e = cudaMemcpyAsync(&mo, s->d_mout, sizeof mo, cudaMemcpyDeviceToHost, c->stream);
+        }
+        if (e == cudaSuccess && cm) {
+            where = "copy of the exchange rows";
+            e = cudaMemcpyAsync(cm->h_recv, cm->d_recv, size_t(world) * XR_WORDS * 8, cudaMemcpyDeviceToHost, c->stream);
+        }
+        if (e == cudaSuccess) {
+            where = "synchronisation of the step";
+            e = cudaStreamSynchronize(c->stream);  // the only synchronisation of the step
+        }
+        if (e != cudaSuccess) {
+            rc = cuda_fail(c, e, err && err[0] ? err : where);
+            break;
+        }
+        // a full record segment (on any rank: every rank sees every row) or a full survivor list: more room, once more
+        bool any_overflow = h.overflow != 0;
+        if (cm)
+            for (int g = 0; g < world; ++g) any_overflow |= reinterpret_cast<const ClusterDev*>(cm->h_recv + size_t(g) * XR_WORDS)->overflow != 0;
+        const bool pf_overflow = h.n_pf > s->pf_cap || (h.overflow & 2);
+        if (any_overflow || pf_overflow) {
+            if (attempt >= 2) {
+                rc = fail(c, E2S_ERR_STATE, "record / survivor buffers still too small after two resizes");
+                break;
+            }
+            if (h.overflow & 1) {
+                if (s->last_one_pass) {
+                    std::vector<ChunkRec> hc(s->n_chunks);
+                    CU(c, cudaMemcpy(hc.data(), s->d_chunks, hc.size() * sizeof(ChunkRec), cudaMemcpyDeviceToHost));
+                    uint64_t mx = 0;
+                    for (const ChunkRec& r : hc) mx = r.own_count > mx ? r.own_count : mx;
+                    if ((rc = ensure_segments(s, mx + 64))) break;
+                } else if ((rc = ensure_records(s, h.n_written + 4096))) {
+                    break;
+                }
+            }
+            if (pf_overflow) s->pf_want = h.n_pf + h.n_pf / 8 + 4096;
+            continue;
+        }
+        if (mo.status != MERGE_OK) {
+            rc = fail(c, merge_status(mo.status), mo.status == MERGE_EMPTY ? "no clusters (the reference divides by zero here)" : merge_message(mo.status));
+            break;
+        }
+        cudaError_t src = cudaSuccess;
+        if (!snp_collect(s->work, &counts, &err, &src)) {
+            if (src == cudaSuccess)  // a capacity guess of phase 2 was too small: the lists it starts from are still on the device
+                src = snp_run(s->work, a, *p, mo.total.max_clust_length, c->d_bases, c->d_off, c->n_reads, c->sm_count, c->stream, &counts,
+                              &c->launches, &err, &c->timer, s->d_pf_list, s->pf_cap, &s->d_res->n_pf, nullptr, true);
+            if (src == cudaErrorInvalidValue && err && strstr(err, "outside the staged reads")) {
+                rc = fail(c, E2S_ERR_UNSUPPORTED, err);
+                break;
+            }
+            if (src != cudaSuccess) {
+                rc = cuda_fail(c, src, err);
+                break;
+            }
+        }
+        // K3a's count of length-passing clusters: from the scan's own histogram + the records this shard adopted
+        uint64_t na = 0;
+        for (int l = 2 * p->mcov_out; l <= mo.total.max_clust_length; ++l) na += h.hist[l];
+        for (uint32_t i = 0; i < mo.mine.n_adopt; ++i)
+            na += int64_t(mo.mine.adopt_len[i]) >= 2 * p->mcov_out && int64_t(mo.mine.adopt_len[i]) <= mo.total.max_clust_length;
+        counts.n_analysed = na;
+        *cnt_out = counts;
+        break;
+    }
+    s->pf_arm = arm_before;
+    if (rc) return rc;
+    // the shard's state, as e2s_cluster_run + e2s_cluster_finalize + e2s_find_events leave it
+    s->h_res = h;
+    s->pf_mcov = uint32_t(p->mcov_out);
+    s->pf_count = h.n_pf;
+    s->pf_ok = true;
+    s->pf_has_adopted = true;
+    s->have_scan_stats = true;
+    s->m_own = h.n_written;
+    s->merged = mo.mine;
+    s->m_list = s->m_own + mo.mine.n_adopt;
+    s->contiguous = !s->last_one_pass;
+    s->adopt_put = false;
+    s->have_clusters = true;
+    s->staged = false;
+    s->finalized = true;
+    s->n_variants = cnt_out->n_variants;
+    s->events_expanded = false;
+    s->have_events = true;
+    *mg_out = mo.mine;
+    *st_out = mo.total;
+    return E2S_OK;
+}
+
+// ebwt2clust + clust2snp on a sealed shard that holds the whole eBWT of one GPU, reads already staged
 int e2s_pipeline_resident(e2s_shard* s, uint32_t k, int32_t min_len, const e2s_snp_params* p, e2s_pipeline_result* res) {
     if (!s || !p || !res) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
     e2s_ctx* c = s->ctx;
@@ -1438,12 +1530,21 @@ int e2s_pipeline_resident(e2s_shard* s, uint32_t k, int32_t min_len, const e2s_s
     memset(res, 0, sizeof *res);
     res->h2d_bytes = h2d;
     res->d2h_bytes = d2h;
-    // both phases in one call: K2 can run clust2snp's BWT prefilter while it writes the records (set E2S_NO_FUSED_PREFILTER
-    // to keep the two phases apart as the CLIs have to)
-    const uint32_t arm_before = s->pf_arm;
-    s->pf_arm = (getenv("E2S_NO_FUSED_PREFILTER") || p->mcov_out < 1 || 2 * p->mcov_out > E2S_MAX_C_LEN) ? 0u : uint32_t(p->mcov_out);
+    if (s->global_off != 0 || s->n_local != s->n_global)
+        return fail(c, E2S_ERR_ARG, "e2s_pipeline_resident needs the whole eBWT in one shard; use e2s_pipeline_sharded");
+    // both phases in one call: the scan runs clust2snp's BWT prefilter while it writes the records and the step never leaves
+    // the stream (pipeline_step).  E2S_NO_FUSED_PREFILTER keeps the two phases apart as the CLIs have to.
+    if (!(getenv("E2S_NO_FUSED_PREFILTER") || p->mcov_out < 1 || 2 * p->mcov_out > E2S_MAX_C_LEN)) {
+        e2s_cluster_merged mg;
+        e2s_stats st;
+        if ((rc = pipeline_step(s, nullptr, k, min_len, p, &mg, &st, &res->snp))) return rc;
+        res->n_written = mg.total_written;
+        res->n_clust_out = mg.n_clust_out;
+        res->max_clust_length = st.max_clust_length;
+        res->d2h_bytes += res->snp.n_candidates * 128;
+        return E2S_OK;
+    }
     rc = e2s_cluster_lm(s, k, min_len, &res->n_written, &res->n_clust_out);
-    s->pf_arm = arm_before;
     if (rc) return rc;
     if (res->n_written == 0) return fail(c, E2S_ERR_UNSUPPORTED, "no clusters (the reference divides by zero here)");
     e2s_stats st;
@@ -1546,11 +1647,10 @@ int e2s_pipeline_sharded(e2s_shard* s, e2s_comm* cm, uint32_t k, int32_t min_len
     if (!s || !cm || !p || !mg || !st || !cnt) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_pipeline_sharded: NULL argument");
     e2s_ctx* c = s->ctx;
     if (cm->ctx != c) return fail(c, E2S_ERR_ARG, "e2s_pipeline_sharded: communicator belongs to another context");
-    const uint32_t arm_before = s->pf_arm;
-    s->pf_arm = (getenv("E2S_NO_FUSED_PREFILTER") || p->mcov_out < 1 || 2 * p->mcov_out > E2S_MAX_C_LEN) ? 0u : uint32_t(p->mcov_out);
+    // the exchange between the phases stays on the device: ncclAllGather of the rows, k_merge_stats on every rank (pipeline_step)
+    if (!(getenv("E2S_NO_FUSED_PREFILTER") || p->mcov_out < 1 || 2 * p->mcov_out > E2S_MAX_C_LEN)) return pipeline_step(s, cm, k, min_len, p, mg, st, cnt);
     e2s_cluster_summary own_sum;
     int rc = cluster_run_impl(s, k, min_len, &own_sum, cm);
-    s->pf_arm = arm_before;
     if (rc) return rc;
     if ((rc = e2s_exchange_rows_finish(cm->h_recv, cm->world, cm->rank, s->n_global, k, min_len, p->mcov_out, p->pval, mg, st))) {
         c->err = g_err;

@@ -715,6 +715,7 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
                 frequent_codes<false>(pf_win, int64_t(st) - int64_t(tile_gbase), len, p.pf_mcov) >= 2) {
                 const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
                 if (at < p.pf_cap) p.pf_list[at] = SurvEntry{st, st - p.global_off, len, 0u};
+                        else p.res->overflow |= 2;  // (seen by every rank in the exchange rows: all of them repeat the round)
             }
         };
         // The list holds the ENDs that will be written: all of them in EXACT mode (D = 0), the kept ones otherwise
@@ -773,7 +774,7 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
                         p.out_start[o] = st;
                         p.out_len[o] = uint16_t(len);
                     } else {
-                        p.res->overflow = 1;
+                        p.res->overflow |= 1;
                     }
                     acc_bases += len;
                     if (len <= MAX_C_LEN) atomicAdd(&sh.hist[len], 1u);
@@ -810,7 +811,7 @@ __global__ void __launch_bounds__(EM_THREADS, 4) k_cluster_emit(EmitParams p) {
                                     p.out_start[o] = st;
                                     p.out_len[o] = uint16_t(len);
                                 } else {
-                                    p.res->overflow = 1;
+                                    p.res->overflow |= 1;
                                 }
                                 acc_bases += len;
                                 if (len <= MAX_C_LEN) atomicAdd(&sh.hist[len], 1u);

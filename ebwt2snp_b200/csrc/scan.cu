@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                     p.seg_start[o] = st;
                     p.seg_len[o] = uint16_t(len);
                 } else {
-                    p.res->overflow = 1;
+                    p.res->overflow |= 1;
                 }
                 acc_bases += len;
                 if (len <= uint32_t(MAX_C_LEN)) atomicAdd(&sh.hist[len], 1u);
@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                     if (st + PL_PAD < tile_gbase) {
                         const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
                         if (at < p.pf_cap) p.pf_list[at] = SurvEntry{st, st - p.global_off, len, 0u};
+                        else p.res->overflow |= 2;  // (seen by every rank in the exchange rows: all of them repeat the round)
                     } else {
                         sh.list2[atomicAdd(&sh.n2[pb], 1u)] = uint32_t(st + PL_PAD - tile_gbase) | (len << 16);
                     }
@@ -490,6 +491,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                         const uint64_t st = tile_gbase + b_lo - PL_PAD;
                         const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
                         if (at < p.pf_cap) p.pf_list[at] = SurvEntry{st, st - p.global_off, len, 0u};
+                        else p.res->overflow |= 2;  // (seen by every rank in the exchange rows: all of them repeat the round)
                     }
                 }
             }
@@ -591,6 +593,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_chunk_resolve(ResolveParams p) {
                 if (pass) {
                     const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
                     if (at < p.pf_cap) p.pf_list[at] = SurvEntry{h_start, h_start - p.global_off, h_len, 0u};
+                    else p.res->overflow |= 2;
                 }
             }
         }
