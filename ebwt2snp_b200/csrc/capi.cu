@@ -751,9 +751,10 @@ static int scan_enqueue(e2s_shard* s, uint32_t k, int32_t min_len) {
             const uint64_t v = strtoull(dbg, nullptr, 10);
             if (v) {
                 want = v;
-                if (s->pf_cap > v) s->pf_cap = v;  // also shrink the advertised capacity of an existing buffer
+                if (s->pf_cap > v && !s->pf_want) s->pf_cap = v;  // also shrink the advertised capacity of an existing buffer
             }
         }
+        if (s->pf_want > want) want = s->pf_want;  // (an overflow of the last attempt asked for more)
         if (want > s->pf_cap) {
             cudaFree(s->d_pf_list);
             s->d_pf_list = nullptr;

@@ -46,49 +46,67 @@ __global__ void k_pack_exchange(const ClusterDev* res, uint64_t n_local, uint64_
     }
 }
 
-__global__ void k_merge_stats(MergeParams p) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    e2s_cluster_summary sums[MERGE_MAX_SHARDS];
-    for (int g = 0; g < p.world; ++g) summary_of_row(p.rows + size_t(g) * XR_WORDS, p.n_global, p.k, p.min_len, &sums[g]);
+__global__ void __launch_bounds__(128) k_merge_stats(MergeParams p) {
+    __shared__ e2s_cluster_summary sums[MERGE_MAX_SHARDS];
+    __shared__ e2s_stats tot;
+    const int tid = threadIdx.x;
+    // the rows -> summaries (one thread per shard) and the sum of the shards' own-record histograms (one thread per bin):
+    // everything the serial part below touches is then in shared memory
+    for (int g = tid; g < p.world; g += blockDim.x) summary_of_row(p.rows + size_t(g) * XR_WORDS, p.n_global, p.k, p.min_len, &sums[g]);
+    for (int i = tid; i < E2S_HIST_BINS; i += blockDim.x) {
+        unsigned long long v = 0;
+        for (int g = 0; g < p.world; ++g) v += reinterpret_cast<const ClusterDev*>(p.rows + size_t(g) * XR_WORDS)->hist[i];
+        tot.hist[i] = v;
+    }
+    if (tid == 0) {
+        tot.n_clust = tot.n_bases = tot.last_len = tot.max_len = 0;
+        tot.max_clust_length = tot.reserved = 0;
+    }
+    __syncthreads();
     MergeOut* out = p.out;
-    e2s_stats& tot = out->total;
-    tot = e2s_stats{};
-    uint64_t last_len = 0;
-    bool any = false;
-    int status = MERGE_OK;
-    for (int g = 0; g < p.world && status == MERGE_OK; ++g) {
-        e2s_cluster_merged mg;
-        status = merge_core(sums, p.world, g, &mg);
-        if (status != MERGE_OK) break;
-        if (g == p.my) out->mine = mg;
-        // records of shard g in file order: [head record] own records [tail records]
-        const ClusterDev& h = *reinterpret_cast<const ClusterDev*>(p.rows + size_t(g) * XR_WORDS);
-        uint64_t n_clust = h.n_written, n_bases = h.n_bases, ll = h.last_rec & 0xffff;
-        for (int i = 0; i < E2S_HIST_BINS; ++i) tot.hist[i] += h.hist[i];
-        auto add = [&](uint64_t l, bool is_last) {
-            if (l <= E2S_MAX_C_LEN) tot.hist[l]++;
-            n_bases += l;
-            n_clust++;
-            if (is_last) ll = l;
-        };
-        if (mg.n_prepend && mg.prepend_written) add(mg.prepend_len, h.n_written == 0);
-        for (uint32_t i = 0; i < mg.n_append; ++i) add(mg.append_len[i], true);
-        tot.n_clust += n_clust;
-        tot.n_bases += n_bases;
-        if (n_clust) {
-            last_len = ll;
-            any = true;
+    if (tid == 0) {
+        uint64_t last_len = 0;
+        bool any = false;
+        int status = MERGE_OK;
+        for (int g = 0; g < p.world && status == MERGE_OK; ++g) {
+            e2s_cluster_merged mg;
+            status = merge_core(sums, p.world, g, &mg);
+            if (status != MERGE_OK) break;
+            if (g == p.my) out->mine = mg;
+            // records of shard g in file order: [head record] own records [tail records]
+            const ClusterDev& h = *reinterpret_cast<const ClusterDev*>(p.rows + size_t(g) * XR_WORDS);
+            uint64_t n_clust = h.n_written, n_bases = h.n_bases, ll = h.last_rec & 0xffff;
+            auto add = [&](uint64_t l, bool is_last) {
+                if (l <= E2S_MAX_C_LEN) tot.hist[l]++;
+                n_bases += l;
+                n_clust++;
+                if (is_last) ll = l;
+            };
+            if (mg.n_prepend && mg.prepend_written) add(mg.prepend_len, h.n_written == 0);
+            for (uint32_t i = 0; i < mg.n_append; ++i) add(mg.append_len[i], true);
+            tot.n_clust += n_clust;
+            tot.n_bases += n_bases;
+            if (n_clust) {
+                last_len = ll;
+                any = true;
+            }
+        }
+        tot.last_len = last_len;
+        if (status == MERGE_OK) status = any ? stats_finish_core(&tot, last_len, p.mcov, p.pval) : MERGE_EMPTY;
+        out->status = status;
+        if (status == MERGE_OK && p.pf_list) {  // the records this shard adopts go to the exact test unconditionally
+            for (uint32_t i = 0; i < out->mine.n_adopt; ++i) {
+                const unsigned long long at = p.res->n_pf++;
+                if (at < p.pf_cap)
+                    p.pf_list[at] = SurvEntry{out->mine.adopt_start[i], out->mine.adopt_start[i] - p.own_global_off, uint32_t(out->mine.adopt_len[i]), 0u};
+            }
         }
     }
-    tot.last_len = last_len;
-    if (status == MERGE_OK) status = any ? stats_finish_core(&tot, last_len, p.mcov, p.pval) : MERGE_EMPTY;
-    out->status = status;
-    if (status == MERGE_OK && p.pf_list) {  // the records this shard adopts go to the exact test unconditionally
-        for (uint32_t i = 0; i < out->mine.n_adopt; ++i) {
-            const unsigned long long at = p.res->n_pf++;
-            if (at < p.pf_cap)
-                p.pf_list[at] = SurvEntry{out->mine.adopt_start[i], out->mine.adopt_start[i] - p.own_global_off, uint32_t(out->mine.adopt_len[i]), 0u};
-        }
+    __syncthreads();
+    {   // statistics() out, max_clust_length included (phase 2's exact test reads it from here)
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&tot);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&out->total);
+        for (uint32_t i = tid; i < sizeof(e2s_stats) / 8; i += blockDim.x) dst[i] = src[i];
     }
 }
 
@@ -100,7 +118,7 @@ cudaError_t launch_pack_exchange(const ClusterDev* res, uint64_t n_local, uint64
 
 cudaError_t launch_merge_stats(const MergeParams& p, cudaStream_t stream) {
     if (p.world < 1 || p.world > MERGE_MAX_SHARDS) return cudaErrorInvalidValue;
-    k_merge_stats<<<1, 32, 0, stream>>>(p);
+    k_merge_stats<<<1, 128, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -597,10 +597,24 @@ __global__ void __launch_bounds__(RS_THREADS) k_chunk_resolve(ResolveParams p) {
                 }
             }
         }
-        atomicAdd(&s_tot[0], mine);
-        atomicAdd(&s_tot[1], rec.n_end);
-        atomicAdd(&s_tot[2], rec.n_bases + (h_kept ? h_len : 0u));
-        if (mine) atomicMax(&s_tot[3], (unsigned long long)(c + 1));
+    }
+    {   // block totals: warp sums by shuffles, one shared atomic per warp
+        unsigned long long w0 = act ? mine : 0, w1 = act ? rec.n_end : 0, w2 = act ? rec.n_bases + (h_kept ? h_len : 0u) : 0;
+        unsigned long long w3 = (act && mine) ? (unsigned long long)(c + 1) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            w0 += shfl64(w0, lane ^ d);
+            w1 += shfl64(w1, lane ^ d);
+            w2 += shfl64(w2, lane ^ d);
+            const unsigned long long o = shfl64(w3, lane ^ d);
+            w3 = o > w3 ? o : w3;
+        }
+        if (lane == 0) {
+            if (w0) atomicAdd(&s_tot[0], w0);
+            if (w1) atomicAdd(&s_tot[1], w1);
+            if (w2) atomicAdd(&s_tot[2], w2);
+            if (w3) atomicMax(&s_tot[3], w3);
+        }
     }
     __syncthreads();
     if (act && mine && s_tot[3] == (unsigned long long)(c + 1))  // the list's last record is this chunk's last
