@@ -87,6 +87,7 @@ SYMBOLS = [
     "e2s_events_format", "e2s_free", "e2s_pipeline_resident", "e2s_pipeline_host",
     "e2s_comm_unique_id", "e2s_comm_create", "e2s_comm_destroy", "e2s_pipeline_sharded",
     "e2s_exchange_row_words", "e2s_exchange_rows_finish",
+    "e2s_shard_create_chunked", "e2s_shard_chunk_positions", "e2s_chunk_begin", "e2s_chunk_scan", "e2s_chunked_finish", "e2s_chunked_reset",
 ]
 
 _lib = None
@@ -158,6 +159,13 @@ def load_library():
     lib.e2s_comm_destroy.restype = None
     lib.e2s_pipeline_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(SnpParams),
                                          C.POINTER(ClusterMerged), C.POINTER(Stats), C.POINTER(SnpCounts)]
+    lib.e2s_shard_create_chunked.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.e2s_shard_chunk_positions.restype = C.c_uint64
+    lib.e2s_shard_chunk_positions.argtypes = [C.c_void_p]
+    lib.e2s_chunk_begin.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    lib.e2s_chunk_scan.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int, C.POINTER(C.c_uint64)]
+    lib.e2s_chunked_finish.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(ClusterSummary)]
+    lib.e2s_chunked_reset.argtypes = [C.c_void_p]
     lib.e2s_pipeline_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(SnpParams), C.c_void_p,
                                       C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PipelineResult)]
@@ -329,8 +337,9 @@ class Context:
         out.update(n=n, L=L, R=R)
         return out
 
-    def shard(self, n_local, global_off=0, n_global=None):
-        return Shard(self, n_local, global_off, n_local if n_global is None else n_global)
+    def shard(self, n_local, global_off=0, n_global=None, chunk_positions=None):
+        """chunk_positions: a CHUNKED shard -- the device buffers hold one chunk of the range at a time (streaming)"""
+        return Shard(self, n_local, global_off, n_local if n_global is None else n_global, chunk_positions)
 
     def pipeline_host(self, gesa_records, n, reads_bases, reads_off, params, k=16, min_len=2, x=4, y=4, z=4,
                       rec10=None, events=None):
@@ -371,12 +380,43 @@ class Comm:
 class Shard:
     """A contiguous eBWT range resident on the GPU (see the header)."""
 
-    def __init__(self, ctx: Context, n_local, global_off, n_global):
+    def __init__(self, ctx: Context, n_local, global_off, n_global, chunk_positions=None):
         self.ctx, self.lib = ctx, ctx.lib
         self.n_local, self.global_off, self.n_global = int(n_local), int(global_off), int(n_global)
         h = C.c_void_p()
-        ctx._ck(self.lib.e2s_shard_create(ctx.h, self.n_local, self.global_off, self.n_global, C.byref(h)))
+        if chunk_positions:
+            ctx._ck(self.lib.e2s_shard_create_chunked(ctx.h, self.n_local, self.global_off, self.n_global, int(chunk_positions), C.byref(h)))
+        else:
+            ctx._ck(self.lib.e2s_shard_create(ctx.h, self.n_local, self.global_off, self.n_global, C.byref(h)))
         self.h = h
+
+    # ---- chunked shards (streaming) ------------------------------------------------------
+    @property
+    def chunk_positions(self) -> int:
+        return int(self.lib.e2s_shard_chunk_positions(self.h))
+
+    def chunks(self):
+        """the (lo, n) of every chunk of the range, in order"""
+        cp, lo, end = self.chunk_positions, self.global_off, self.global_off + self.n_local
+        while lo < end:
+            yield lo, min(cp, end - lo)
+            lo += cp
+
+    def chunk_begin(self, lo, n):
+        self.ctx._ck(self.lib.e2s_chunk_begin(self.h, int(lo), int(n)))
+
+    def chunk_scan(self, k=16, min_len=2, mcov_out=0) -> int:
+        m = C.c_uint64()
+        self.ctx._ck(self.lib.e2s_chunk_scan(self.h, k, min_len, int(mcov_out), C.byref(m)))
+        return m.value
+
+    def chunked_finish(self, k=16, min_len=2) -> ClusterSummary:
+        s = ClusterSummary()
+        self.ctx._ck(self.lib.e2s_chunked_finish(self.h, k, min_len, C.byref(s)))
+        return s
+
+    def chunked_reset(self):
+        self.ctx._ck(self.lib.e2s_chunked_reset(self.h))
 
     def close(self):
         if self.h:

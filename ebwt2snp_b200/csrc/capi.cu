@@ -72,6 +72,7 @@ struct e2s_shard {
     uint64_t* d_seg_start = nullptr;
     uint16_t* d_seg_len = nullptr;
     uint64_t seg_cap = 0;            // records per segment
+    uint64_t seg_total = 0;          // records the segment arrays hold in all
     uint32_t n_chunks = 0, tiles_per_chunk = 0;
     ChunkRec* d_chunks = nullptr;    // SCAN_MAX_CHUNKS chunk summaries
     ChunkSeg* d_segs = nullptr;      // ... and where k_chunk_resolve put each segment in the position-ordered list
@@ -100,6 +101,22 @@ struct e2s_shard {
     uint64_t* d_chg = nullptr;       // ... and the change plane: bit x = base code of x differs from that of x - 1
     uint32_t* d_seal_flag = nullptr; // != 0: an LCP value above 127 (set at seal)
     int variant = 0;
+    // chunked mode (streaming): the device buffers hold one chunk [global_off, global_off + n_local) of the shard's range at a time
+    bool chunked = false;
+    uint64_t range_lo = 0, range_n = 0;   // the shard's own range of the eBWT
+    uint64_t chunk_cap = 0;               // positions the buffers hold
+    bool chunk_open = false;              // a chunk has been begun and not yet scanned
+    bool records_flushed = false;         // e2s_chunked_finish ran: the records were handed out chunk by chunk
+    ClusterDev acc;                       // the range's accumulators so far (host)
+    uint64_t carry_state = 0;             // open-cluster state after the chunks so far: 0 closed, 1 unknown (an earlier shard decides), >= 2: 2 + global START
+    uint32_t* p_lcp = nullptr;            // payload of the surviving clusters (see CaptureParams)
+    uint32_t* p_text = nullptr;
+    uint32_t* p_suff = nullptr;
+    uint8_t* p_bwt = nullptr;
+    uint64_t pay_cap = 0, pay_used = 0;
+    SurvEntry* d_surv = nullptr;
+    uint64_t surv_cap = 0, surv_count = 0;
+    unsigned long long* d_cap_counters = nullptr;  // payload cursor, survivor count, error bits
     // phase 2
     SnpWork* work = nullptr;
     std::vector<e2s_event> events;
@@ -273,7 +290,8 @@ int e2s_ctx_kernel_time(e2s_ctx* c, int kernel, double* total_ms, uint64_t* laun
 // ---------------------------------------------------------------------------------------------
 static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
-int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t n_global, e2s_shard** out) {
+// buf = positions the device buffers hold: the whole range (resident shard) or one chunk of it (chunked shard)
+static int shard_create_impl(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t n_global, uint64_t buf, e2s_shard** out) {
     if (!c || !out) return fail(c, E2S_ERR_ARG, "e2s_shard_create: NULL argument");
     *out = nullptr;
     if (n_local < 2 || global_off + n_local > n_global || (global_off != 0 && global_off < 2))
@@ -285,7 +303,7 @@ int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t
     s->n_local = n_local;
     s->global_off = global_off;
     s->n_global = n_global;
-    s->alloc_r = round_up(n_local, 32768) + 8192;  // whole K2 tiles (32768 positions) + one K1 tile of slack
+    s->alloc_r = round_up(buf, 32768) + 8192;  // whole K2 tiles (32768 positions) + one K1 tile of slack
     const size_t ne = size_t(PAD_L) + s->alloc_r;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->lcp_a), ne * 4);
@@ -319,15 +337,79 @@ int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t
     CU(c, cudaMemsetAsync(s->text_a, 0, PAD_L * 4, c->stream));
     CU(c, cudaMemsetAsync(s->suff_a, 0, PAD_L * 4, c->stream));
     CU(c, cudaMemsetAsync(s->bwt_a, 0, PAD_L, c->stream));
-    const size_t tail = size_t(s->alloc_r - n_local);
-    CU(c, cudaMemsetAsync(s->lcp + n_local, 0, tail * 4, c->stream));
-    CU(c, cudaMemsetAsync(s->text + n_local, 0, tail * 4, c->stream));
-    CU(c, cudaMemsetAsync(s->suff + n_local, 0, tail * 4, c->stream));
-    CU(c, cudaMemsetAsync(s->bwt + n_local, 0, tail, c->stream));
+    const size_t tail = size_t(s->alloc_r - buf);
+    CU(c, cudaMemsetAsync(s->lcp + buf, 0, tail * 4, c->stream));
+    CU(c, cudaMemsetAsync(s->text + buf, 0, tail * 4, c->stream));
+    CU(c, cudaMemsetAsync(s->suff + buf, 0, tail * 4, c->stream));
+    CU(c, cudaMemsetAsync(s->bwt + buf, 0, tail, c->stream));
     s->work = snp_work_create();
     *out = s;
     return E2S_OK;
 }
+
+int e2s_shard_create(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t n_global, e2s_shard** out) {
+    return shard_create_impl(c, n_local, global_off, n_global, n_local, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// chunked shards (streaming): a chunk is a shard in time
+// ---------------------------------------------------------------------------------------------
+int e2s_shard_create_chunked(e2s_ctx* c, uint64_t n_local, uint64_t global_off, uint64_t n_global, uint64_t chunk_positions,
+                             e2s_shard** out) {
+    if (chunk_positions < 16384) chunk_positions = 16384;
+    chunk_positions = round_up(chunk_positions, 16384);  // chunks start at whole scan tiles
+    const uint64_t cap = chunk_positions < round_up(n_local, 16384) ? chunk_positions : round_up(n_local, 16384);
+    int rc = shard_create_impl(c, n_local, global_off, n_global, cap, out);
+    if (rc) return rc;
+    e2s_shard* s = *out;
+    s->chunked = true;
+    s->range_lo = global_off;
+    s->range_n = n_local;
+    s->chunk_cap = cap;
+    memset(&s->acc, 0, sizeof s->acc);
+    s->carry_state = global_off == 0 ? 0 : 1;
+    if (cudaMalloc(reinterpret_cast<void**>(&s->d_cap_counters), 4 * 8) != cudaSuccess) {
+        e2s_shard_destroy(s);
+        *out = nullptr;
+        return fail(c, E2S_ERR_NOMEM, "chunked shard counters");
+    }
+    CU(c, cudaMemsetAsync(s->d_cap_counters, 0, 4 * 8, c->stream));
+    return E2S_OK;
+}
+
+uint64_t e2s_shard_chunk_positions(const e2s_shard* s) { return s && s->chunked ? s->chunk_cap : 0; }
+
+// The next chunk [chunk_lo, chunk_lo + chunk_n) of the shard's range: chunks follow each other without gaps, every chunk but
+// the last holds e2s_shard_chunk_positions() positions.  The loads that follow (e2s_shard_load_gesa / _soa / _soa_dev, global
+// positions as always) should cover [chunk_lo - 176, chunk_lo + chunk_n + 1) as far as the eBWT reaches -- on the shard's last
+// chunk + 151 as for every shard; what lies outside is ignored.
+int e2s_chunk_begin(e2s_shard* s, uint64_t chunk_lo, uint64_t chunk_n) {
+    if (!s || !s->chunked) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_chunk_begin: not a chunked shard");
+    e2s_ctx* c = s->ctx;
+    const uint64_t done = s->chunk_open || s->acc.ticket ? s->global_off + s->n_local : s->range_lo;  // (acc.ticket counts the chunks scanned)
+    if (s->chunk_open) return fail(c, E2S_ERR_STATE, "e2s_chunk_begin: the previous chunk has not been scanned");
+    if (chunk_lo != done || chunk_n < 1 || chunk_n > s->chunk_cap || chunk_lo + chunk_n > s->range_lo + s->range_n)
+        return fail(c, E2S_ERR_ARG, "e2s_chunk_begin: chunks must follow each other and fit the buffers");
+    if (chunk_lo + chunk_n < s->range_lo + s->range_n && chunk_n != s->chunk_cap)
+        return fail(c, E2S_ERR_ARG, "e2s_chunk_begin: only the last chunk may be shorter than e2s_shard_chunk_positions()");
+    CU(c, cudaSetDevice(c->device));
+    s->global_off = chunk_lo;
+    s->n_local = chunk_n;
+    s->sealed = false;
+    s->chunk_open = true;
+    CU(c, cudaMemsetAsync(s->d_seal_flag, 0, 4, c->stream));
+    if (chunk_lo < uint64_t(PAD_L)) {  // no (or a short) left context: the pad must read as zeros
+        CU(c, cudaMemsetAsync(s->lcp_a, 0, PAD_L * 4, c->stream));
+        CU(c, cudaMemsetAsync(s->text_a, 0, PAD_L * 4, c->stream));
+        CU(c, cudaMemsetAsync(s->suff_a, 0, PAD_L * 4, c->stream));
+        CU(c, cudaMemsetAsync(s->bwt_a, 0, PAD_L, c->stream));
+        if (s->lcp8_a) CU(c, cudaMemsetAsync(s->lcp8_a, 0, PAD_L, c->stream));
+        CU(c, cudaMemsetAsync(s->d_planes, 0, (PL_PAD / 64) * sizeof(uint4), c->stream));
+        CU(c, cudaMemsetAsync(s->d_chg, 0, (PL_PAD / 64) * 8, c->stream));
+    }
+    return E2S_OK;
+}
+
 
 void e2s_shard_destroy(e2s_shard* s) {
     if (!s) return;
@@ -343,6 +425,12 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->d_row);
     cudaFree(s->d_mout);
     cudaFreeHost(s->h_mout);
+    cudaFree(s->p_lcp);
+    cudaFree(s->p_text);
+    cudaFree(s->p_suff);
+    cudaFree(s->p_bwt);
+    cudaFree(s->d_surv);
+    cudaFree(s->d_cap_counters);
     cudaFree(s->d_seg_start);
     cudaFree(s->d_seg_len);
     cudaFree(s->d_chunks);
@@ -363,7 +451,9 @@ void e2s_shard_destroy(e2s_shard* s) {
 
 // the global range a shard keeps: 2 positions of left halo, MAX_C_LEN + 1 of right halo
 static void keep_range(const e2s_shard* s, uint64_t* lo, uint64_t* hi) {
-    *lo = s->global_off >= 2 ? s->global_off - 2 : 0;
+    // (a chunk keeps PAD_L positions of left context: clusters that end in it may start up to 150 positions before it)
+    const uint64_t left = s->chunked ? uint64_t(PAD_L) : 2;
+    *lo = s->global_off >= left ? s->global_off - left : 0;
     uint64_t h = s->global_off + s->n_local + MAX_C_LEN + 1;
     *hi = h < s->n_global ? h : s->n_global;
 }
@@ -615,7 +705,7 @@ static int ensure_records(e2s_shard* s, uint64_t cap) {
 }
 
 static int ensure_segments(e2s_shard* s, uint64_t seg_cap) {
-    if (seg_cap <= s->seg_cap && s->d_seg_start) return E2S_OK;
+    if (seg_cap <= s->seg_cap && s->d_seg_start && seg_cap * s->n_chunks <= s->seg_total) return E2S_OK;
     cudaFree(s->d_seg_start);
     cudaFree(s->d_seg_len);
     s->d_seg_start = nullptr;
@@ -626,6 +716,7 @@ static int ensure_segments(e2s_shard* s, uint64_t seg_cap) {
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_seg_len), total * 2 + 16);
     if (e != cudaSuccess) return fail(s->ctx, E2S_ERR_NOMEM, "cluster record segments");
     s->seg_cap = seg_cap;
+    s->seg_total = total;
     return E2S_OK;
 }
 
@@ -683,13 +774,14 @@ static int scan_enqueue(e2s_shard* s, uint32_t k, int32_t min_len) {
     const uint64_t num_tiles = emit_num_tiles(s->n_local);
     if (one_pass) {
         if (!s->d_chunks) {
-            CU(c, scan_plan(s->n_local, c->sm_count, &s->n_chunks, &s->tiles_per_chunk));
             if (cudaMalloc(reinterpret_cast<void**>(&s->d_chunks), SCAN_MAX_CHUNKS * sizeof(ChunkRec)) != cudaSuccess ||
                 cudaMalloc(reinterpret_cast<void**>(&s->d_segs), SCAN_MAX_CHUNKS * sizeof(ChunkSeg)) != cudaSuccess)
                 return fail(c, E2S_ERR_NOMEM, "chunk tables");
         }
-        if (!s->d_seg_start) {
-            int rc = ensure_segments(s, (s->n_local / 8 + 4096) / s->n_chunks + 64);
+        CU(c, scan_plan(s->n_local, c->sm_count, &s->n_chunks, &s->tiles_per_chunk));  // (n_local changes from chunk to chunk of a chunked shard)
+        {
+            const uint64_t want = (s->n_local / 8 + 4096) / s->n_chunks + 64;
+            int rc = ensure_segments(s, want > s->seg_cap ? want : s->seg_cap);
             if (rc) return rc;
         }
     } else {
@@ -806,7 +898,7 @@ static int scan_enqueue(e2s_shard* s, uint32_t k, int32_t min_len) {
         rp.min_len = min_len;
         rp.global_off = s->global_off;
         rp.n_global = s->n_global;
-        rp.init_state = s->global_off == 0 ? 0 : 1;
+        rp.init_state = s->chunked ? s->carry_state : (s->global_off == 0 ? 0 : 1);
         rp.planes = s->d_planes;
         rp.pf_mcov = p.pf_mcov;
         rp.pf_list = p.pf_list;
@@ -827,6 +919,7 @@ static int scan_enqueue(e2s_shard* s, uint32_t k, int32_t min_len) {
 static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summary* sum, e2s_comm* cm) {
     if (!s || !sum) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_cluster_run: NULL argument");
     e2s_ctx* c = s->ctx;
+    if (s->chunked) return fail(c, E2S_ERR_STATE, "chunked shard: use e2s_chunk_begin / e2s_chunk_scan / e2s_chunked_finish");
     if (k == 0) return fail(c, E2S_ERR_ARG, "k must be >= 1 (the CLI maps 0 to the default 16)");
     CU(c, cudaSetDevice(c->device));
     if (!s->h_pin) CU(c, cudaHostAlloc(reinterpret_cast<void**>(&s->h_pin), sizeof(ClusterDev), cudaHostAllocDefault));
@@ -906,6 +999,178 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
     return E2S_OK;
 }
 
+
+}  // extern "C"
+// capacity of the payload / survivor list of a chunked shard (grown between chunks, contents kept)
+template <typename T>
+static cudaError_t grow_keep(T*& ptr, uint64_t& cap, uint64_t used, uint64_t need, cudaStream_t stream) {
+    if (need <= cap && ptr) return cudaSuccess;
+    const uint64_t ncap = need + need / 2 + 4096;
+    T* np = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&np), ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (ptr && used) e = cudaMemcpyAsync(np, ptr, used * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(ptr);
+    ptr = np;
+    cap = ncap;
+    return e;
+}
+extern "C" {
+
+// copies the records of the survivors listed in d_pf_list[0, n) (base relative to the resident chunk) to the payload
+static int capture_survivors(e2s_shard* s, uint64_t n) {
+    e2s_ctx* c = s->ctx;
+    if (!n) return E2S_OK;
+    const uint64_t need_pay = s->pay_used + n * uint64_t(MAX_C_LEN);
+    uint64_t cap4 = s->pay_cap, cap1 = s->pay_cap, capt = s->pay_cap, caps = s->pay_cap;
+    CU(c, grow_keep(s->p_lcp, cap4, s->pay_used, need_pay, c->stream));
+    CU(c, grow_keep(s->p_text, capt, s->pay_used, need_pay, c->stream));
+    CU(c, grow_keep(s->p_suff, caps, s->pay_used, need_pay, c->stream));
+    CU(c, grow_keep(s->p_bwt, cap1, s->pay_used, need_pay, c->stream));
+    s->pay_cap = cap4;
+    CU(c, grow_keep(s->d_surv, s->surv_cap, s->surv_count, s->surv_count + n, c->stream));
+    CaptureParams cp;
+    cp.in = s->d_pf_list;
+    cp.n_in = &s->d_res->n_pf;
+    cp.n_in_cap = n;
+    cp.lcp = s->lcp;
+    cp.text = s->text;
+    cp.suff = s->suff;
+    cp.bwt = s->bwt;
+    cp.p_lcp = s->p_lcp;
+    cp.p_text = s->p_text;
+    cp.p_suff = s->p_suff;
+    cp.p_bwt = s->p_bwt;
+    cp.pay_cap = s->pay_cap;
+    cp.out = s->d_surv;
+    cp.out_cap = s->surv_cap;
+    cp.counters = s->d_cap_counters;
+    CU(c, launch_capture(cp, c->stream, c->sm_count));
+    ++c->launches;
+    unsigned long long hc[3] = {0, 0, 0};
+    CU(c, cudaMemcpyAsync(hc, s->d_cap_counters, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (hc[2] & 1)
+        return fail(c, E2S_ERR_UNSUPPORTED,
+                    "chunked shard: a cluster of 65 536 or more positions whose wrapped length passes the filters has left the device "
+                    "(use a resident shard for this input)");
+    if (hc[2]) return fail(c, E2S_ERR_STATE, "chunked shard: payload / survivor list capacity");
+    s->pay_used = hc[0];
+    s->surv_count = hc[1];
+    return E2S_OK;
+}
+
+// Scan of the chunk begun by e2s_chunk_begin, after its loads: seal, the one-pass scan with the state carried over from the
+// chunks before, and -- mcov_out > 0: both tools will run -- the fused BWT prefilter with the survivors' records captured
+// for phase 2.  *n_records = records of this chunk (e2s_cluster_fetch / _fetch_packed return exactly them until the next
+// e2s_chunk_begin).
+int e2s_chunk_scan(e2s_shard* s, uint32_t k, int32_t min_len, int mcov_out, uint64_t* n_records) {
+    if (!s || !s->chunked || !s->chunk_open) return fail(s ? s->ctx : nullptr, E2S_ERR_STATE, "e2s_chunk_scan: begin a chunk first");
+    e2s_ctx* c = s->ctx;
+    if (k == 0) return fail(c, E2S_ERR_ARG, "k must be >= 1 (the CLI maps 0 to the default 16)");
+    if (mcov_out < 0 || 2 * mcov_out > E2S_MAX_C_LEN) return fail(c, E2S_ERR_ARG, "e2s_chunk_scan: need 0 <= 2 * mcov_out <= 150");
+    int rc = e2s_shard_seal(s);
+    if (rc) return rc;
+    if (!s->lcp8_ok || min_len > 33)
+        return fail(c, E2S_ERR_UNSUPPORTED,
+                    "chunked shards need the one-pass scan: every LCP value <= 127 (reads shorter than 128 bases) and -m <= 33; "
+                    "use a resident shard for this input");
+    if (!s->h_pin) CU(c, cudaHostAlloc(reinterpret_cast<void**>(&s->h_pin), sizeof(ClusterDev), cudaHostAllocDefault));
+    ClusterDev& h = *s->h_pin;
+    const uint32_t arm_before = s->pf_arm;
+    s->pf_arm = uint32_t(mcov_out);
+    for (int attempt = 0;; ++attempt) {
+        if ((rc = scan_enqueue(s, k, min_len))) break;
+        cudaError_t e = cudaMemcpyAsync(&h, s->d_res, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            rc = cuda_fail(c, e, "chunk scan");
+            break;
+        }
+        if (!h.overflow) break;
+        if (attempt >= 2) {
+            rc = fail(c, E2S_ERR_STATE, "record / survivor buffers still too small after two resizes");
+            break;
+        }
+        if (h.overflow & 1) {
+            std::vector<ChunkRec> hc(s->n_chunks);
+            CU(c, cudaMemcpy(hc.data(), s->d_chunks, hc.size() * sizeof(ChunkRec), cudaMemcpyDeviceToHost));
+            uint64_t mx = 0;
+            for (const ChunkRec& r : hc) mx = r.own_count > mx ? r.own_count : mx;
+            if ((rc = ensure_segments(s, mx + 64))) break;
+        }
+        if (h.overflow & 2) s->pf_want = h.n_pf + h.n_pf / 8 + 4096;
+    }
+    s->pf_arm = arm_before;
+    if (rc) return rc;
+    if (mcov_out && h.n_pf && (rc = capture_survivors(s, h.n_pf))) return rc;
+    // the range's accumulators; the state the next chunk starts from
+    ClusterDev& a = s->acc;
+    a.n_end += h.n_end;
+    a.n_written += h.n_written;
+    if (!a.head_end) a.head_end = h.head_end;
+    a.any_event |= h.any_event;
+    a.open_start = h.open_start;
+    if (h.end_nm2_start) a.end_nm2_start = h.end_nm2_start;
+    if (h.n_written) a.last_rec = h.last_rec;
+    a.n_bases += h.n_bases;
+    for (int i = 0; i < E2S_HIST_BINS; ++i) a.hist[i] += h.hist[i];
+    if (s->global_off + s->n_local == s->n_global) {
+        a.tail_lcp_nm2 = h.tail_lcp_nm2;
+        a.tail_lcp_nm1 = h.tail_lcp_nm1;
+        a.tail_bwt_nm1 = h.tail_bwt_nm1;
+    }
+    a.ticket++;  // chunks scanned
+    if (a.any_event) s->carry_state = h.open_start ? h.open_start - 1 + 2 : 0;
+    s->chunk_open = false;
+    s->h_res = h;
+    s->pf_mcov = uint32_t(mcov_out);
+    s->m_own = s->m_list = h.n_written;
+    s->contiguous = false;
+    s->have_clusters = true;
+    s->staged = false;
+    s->finalized = false;
+    s->have_events = false;
+    s->have_scan_stats = true;
+    memset(&s->merged, 0, sizeof s->merged);
+    if (n_records) *n_records = h.n_written;
+    return E2S_OK;
+}
+
+// After the last chunk: the summary of the shard's whole range, as e2s_cluster_run returns it for a resident shard.  From
+// here on e2s_cluster_merge / e2s_cluster_finalize / e2s_statistics / e2s_find_events work as usual (the records themselves
+// were handed out chunk by chunk; phase 2 runs on the captured survivors).
+int e2s_chunked_finish(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summary* sum) {
+    if (!s || !s->chunked || !sum) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_chunked_finish: not a chunked shard");
+    e2s_ctx* c = s->ctx;
+    if (s->chunk_open || s->global_off + s->n_local != s->range_lo + s->range_n || !s->acc.ticket)
+        return fail(c, E2S_ERR_STATE, "e2s_chunked_finish: the last chunk of the range has not been scanned");
+    const ClusterDev& h = s->acc;
+    memset(sum, 0, sizeof *sum);
+    sum->n_local = s->range_n;
+    sum->global_off = s->range_lo;
+    sum->n_global = s->n_global;
+    sum->n_end = h.n_end;
+    sum->n_written = h.n_written;
+    sum->head_end = h.head_end;
+    sum->any_event = h.any_event;
+    sum->open_start = h.any_event ? h.open_start : 0;
+    sum->end_nm2_start = h.end_nm2_start;
+    sum->k = k;
+    sum->min_len = uint64_t(int64_t(min_len));
+    sum->lcp_bytes = uint64_t(s->lay_x);
+    sum->tail_lcp_nm2 = h.tail_lcp_nm2;
+    sum->tail_lcp_nm1 = h.tail_lcp_nm1;
+    sum->tail_bwt_nm1 = h.tail_bwt_nm1;
+    s->h_res = h;  // statistics() of the whole range
+    s->m_own = s->m_list = h.n_written;
+    s->records_flushed = true;
+    s->pf_ok = s->pf_mcov != 0;
+    s->pf_has_adopted = false;
+    return E2S_OK;
+}
+
 int e2s_cluster_run(e2s_shard* s, uint32_t k, int32_t min_len, e2s_cluster_summary* sum) {
     return cluster_run_impl(s, k, min_len, sum, nullptr);
 }
@@ -942,6 +1207,18 @@ int e2s_cluster_finalize(e2s_shard* s, const e2s_cluster_merged* mg) {
     s->m_list = s->m_own + mg->n_adopt;  // the adopted records join the device list when a pass over it needs them (find_events)
     s->adopt_put = false;
     s->finalized = true;
+    if (s->chunked && s->pf_mcov && mg->n_adopt) {  // their records are still on the device (the range's last chunk): to the payload
+        SurvEntry extra[4];
+        for (uint32_t i = 0; i < mg->n_adopt && i < 4; ++i)
+            extra[i] = SurvEntry{mg->adopt_start[i], mg->adopt_start[i] - s->global_off, uint32_t(mg->adopt_len[i]), 0u};
+        const unsigned long long n = mg->n_adopt;
+        CU(c, cudaMemcpyAsync(s->d_pf_list, extra, n * sizeof(SurvEntry), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(&s->d_res->n_pf, &n, 8, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        int rc = capture_survivors(s, n);
+        if (rc) return rc;
+        s->pf_has_adopted = true;
+    }
     return E2S_OK;
 }
 
@@ -982,6 +1259,7 @@ int e2s_cluster_fetch(e2s_shard* s, uint64_t* start, uint16_t* len, uint64_t cap
     if (!s || !start || !len || !m) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
     e2s_ctx* c = s->ctx;
     if (!s->have_clusters) return fail(c, E2S_ERR_STATE, "no clusters yet");
+    if (s->records_flushed) return fail(c, E2S_ERR_STATE, "chunked shard: the records were handed out chunk by chunk");
     const uint64_t total = out_count(s);
     *m = total;
     if (cap < total) return fail(c, E2S_ERR_ARG, "e2s_cluster_fetch: capacity too small");
@@ -1013,6 +1291,7 @@ int e2s_cluster_fetch_packed(e2s_shard* s, void* rec10, uint64_t cap, uint64_t* 
     if (!s || !rec10 || !m) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "NULL argument");
     e2s_ctx* c = s->ctx;
     if (!s->have_clusters) return fail(c, E2S_ERR_STATE, "no clusters yet");
+    if (s->records_flushed) return fail(c, E2S_ERR_STATE, "chunked shard: the records were handed out chunk by chunk");
     const uint64_t total = out_count(s);
     *m = total;
     if (cap < total) return fail(c, E2S_ERR_ARG, "e2s_cluster_fetch_packed: capacity too small");
@@ -1226,7 +1505,29 @@ int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length,
     // (which K2 did not see) replace K3a
     const SurvEntry* pre_list = nullptr;
     uint64_t pre_count = 0;
-    if (!s->staged && s->pf_ok && s->pf_mcov == uint32_t(p->mcov_out) && max_clust_length <= E2S_MAX_C_LEN) {
+    if (s->chunked) {
+        // the range went through the device chunk by chunk: phase 2 runs on the records e2s_chunk_scan captured for the
+        // clusters that survived its prefilter
+        if (!s->records_flushed || !s->pf_ok || s->pf_mcov != uint32_t(p->mcov_out))
+            return fail(c, E2S_ERR_STATE, "chunked shard: phase 2 needs e2s_chunk_scan(mcov_out = this -m) on every chunk and e2s_chunked_finish");
+        a.lcp = s->p_lcp;
+        a.text = s->p_text;
+        a.suff = s->p_suff;
+        a.bwt = s->p_bwt;
+        a.planes = nullptr;
+        pre_list = s->d_surv;
+        pre_count = s->surv_count;
+        if (!pre_count) {  // nothing survived: no candidates
+            memset(counts, 0, sizeof *counts);
+            uint64_t na0 = 0;
+            for (int l = 2 * p->mcov_out; l <= max_clust_length; ++l) na0 += s->h_res.hist[l];
+            counts->n_analysed = na0;
+            s->n_variants = 0;
+            s->events_expanded = false;
+            s->have_events = true;
+            return E2S_OK;
+        }
+    } else if (!s->staged && s->pf_ok && s->pf_mcov == uint32_t(p->mcov_out) && max_clust_length <= E2S_MAX_C_LEN) {
         SurvEntry extra[4];
         const uint64_t n_extra = s->pf_has_adopted ? 0 : s->merged.n_adopt;  // <= 3 records the merge created and this shard analyses
         for (uint64_t i = 0; i < n_extra && i < 4; ++i)
@@ -1661,57 +1962,149 @@ int e2s_pipeline_sharded(e2s_shard* s, e2s_comm* cm, uint32_t k, int32_t min_len
     return e2s_find_events(s, p, st->max_clust_length, cnt);
 }
 
-int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, int z, const uint8_t* read_bases,
-                      const uint64_t* read_off, uint64_t n_reads, uint32_t k, int32_t min_len, const e2s_snp_params* p,
-                      void* rec10, uint64_t cap_records, e2s_event* events, uint64_t cap_events, e2s_pipeline_result* res) {
-    if (!c || !gesa || !p || !res) return fail(c, E2S_ERR_ARG, "NULL argument");
-    memset(res, 0, sizeof *res);
-    // developer aid: E2S_PIPELINE_DEBUG=1 prints the wall time of every stage (with a stream sync after each)
-    const bool dbg = getenv("E2S_PIPELINE_DEBUG") != nullptr;
-    struct timespec t0;
-    clock_gettime(CLOCK_MONOTONIC, &t0);
-    auto lap = [&](const char* what) {
-        if (!dbg) return;
-        cudaStreamSynchronize(c->stream);
-        struct timespec t1;
-        clock_gettime(CLOCK_MONOTONIC, &t1);
-        fprintf(stderr, "[e2s_pipeline_host] %-28s %9.3f ms\n", what, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
-        t0 = t1;
-    };
+// forget the chunks scanned so far: the shard is about to stream its range again (or another data set of the same shape)
+int e2s_chunked_reset(e2s_shard* s) {
+    if (!s || !s->chunked) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_chunked_reset: not a chunked shard");
+    e2s_ctx* c = s->ctx;
+    CU(c, cudaSetDevice(c->device));
+    memset(&s->acc, 0, sizeof s->acc);
+    s->carry_state = s->range_lo == 0 ? 0 : 1;
+    s->pay_used = s->surv_count = 0;
+    s->chunk_open = s->records_flushed = false;
+    s->have_clusters = s->have_events = s->finalized = false;
+    s->pf_ok = false;
+    s->global_off = s->range_lo;
+    s->n_local = s->chunk_cap < s->range_n ? s->chunk_cap : s->range_n;
+    CU(c, cudaMemsetAsync(s->d_cap_counters, 0, 4 * 8, c->stream));
+    return E2S_OK;
+}
+
+static uint64_t chunk_positions_from_env() {
+    uint64_t chunk = uint64_t(1) << 28;  // 3.5 GB of 13-byte records per chunk, 3.9 GB of device buffers
+    if (const char* e = getenv("E2S_CHUNK_POSITIONS")) {
+        const uint64_t v = strtoull(e, nullptr, 10);
+        if (v) chunk = v;
+    }
+    return chunk;
+}
+
+// the same from a resident shard (inputs the one-pass scan does not take: an LCP value above 127, -m > 33)
+static int pipeline_host_resident(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, int z, uint32_t k, int32_t min_len,
+                                  const e2s_snp_params* p, void* rec10, uint64_t cap_records, e2s_event* events, uint64_t cap_events,
+                                  e2s_pipeline_result* res) {
     int rc;
     e2s_shard* s = c->cached;
-    if (!s || s->n_local != n || s->n_global != n) {
+    if (!s || s->chunked || s->n_local != n || s->n_global != n) {
         if (s) e2s_shard_destroy(s);
         c->cached = nullptr;
         rc = e2s_shard_create(c, n, 0, n, &s);
         if (rc) return rc;
         c->cached = s;
     }
-    lap("shard (cached after 1st call)");
     const int rs = x + y + z + 1;
     CU(c, cudaMemsetAsync(s->d_seal_flag, 0, 4, c->stream));  // a cached shard is reloaded from its first position: forget the old verdict
     if ((rc = e2s_shard_load_gesa(s, gesa, 0, n, x, y, z))) return rc;
     if ((rc = e2s_shard_seal(s))) return rc;
     res->h2d_bytes += n * uint64_t(rs);
-    lap("H2D records + de-interleave");
-    if (read_bases) {  // queued behind the records on the copy engine; the kernels below do not wait for it
-        if ((rc = e2s_reads_stage(c, read_bases, read_off, n_reads))) return rc;
-        res->h2d_bytes += read_off[n_reads] + (n_reads + 1) * 8;
-    }
-    lap("H2D reads");
     if ((rc = e2s_pipeline_resident(s, k, min_len, p, res))) return rc;
-    lap("K1 K2 merge statistics K3 K4");
     if (rec10) {
         uint64_t m = 0;
         if ((rc = e2s_cluster_fetch_packed(s, rec10, cap_records, &m))) return rc;
         res->d2h_bytes += m * 10;
     }
-    lap("pack + D2H .clusters records");
     if (events) {
         uint64_t nv = 0;
         if ((rc = e2s_events_fetch(s, events, cap_events, &nv))) return rc;
     }
-    lap("events to caller");
+    return E2S_OK;
+}
+
+// ebwt2clust + clust2snp from host buffers.  The records stream through a CHUNKED shard (a chunk is a shard in time): the
+// device holds one chunk of E2S_CHUNK_POSITIONS positions (default 2^28) whatever n is, the H2D copies of a chunk run on
+// their own stream ahead of its de-interleave kernels, each chunk's records go back as soon as it is scanned, the records
+// of the clusters that survive the fused prefilter are kept for phase 2, which runs once after the last chunk.
+int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, int z, const uint8_t* read_bases,
+                      const uint64_t* read_off, uint64_t n_reads, uint32_t k, int32_t min_len, const e2s_snp_params* p,
+                      void* rec10, uint64_t cap_records, e2s_event* events, uint64_t cap_events, e2s_pipeline_result* res) {
+    if (!c || !gesa || !p || !res) return fail(c, E2S_ERR_ARG, "NULL argument");
+    memset(res, 0, sizeof *res);
+    auto ok = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8; };
+    if (!ok(x) || !ok(y) || !ok(z)) return fail(c, E2S_ERR_ARG, "field byte sizes must be 1, 2, 4 or 8");
+    if (n < 2) return fail(c, E2S_ERR_ARG, "e2s_pipeline_host: need at least 2 records");
+    int rc;
+    const int rs = x + y + z + 1;
+    if (read_bases) {  // queued first on the stream; the scan kernels do not wait for it
+        if ((rc = e2s_reads_stage(c, read_bases, read_off, n_reads))) return rc;
+        res->h2d_bytes += read_off[n_reads] + (n_reads + 1) * 8;
+    }
+    const bool mcov_ok = p->mcov_out >= 1 && 2 * p->mcov_out <= E2S_MAX_C_LEN;
+    if (min_len > 33 || !mcov_ok || getenv("E2S_NO_FUSED_PREFILTER"))
+        return pipeline_host_resident(c, gesa, n, x, y, z, k, min_len, p, rec10, cap_records, events, cap_events, res);
+    const uint64_t chunk = chunk_positions_from_env();
+    e2s_shard* s = c->cached;
+    if (!s || !s->chunked || s->range_n != n || s->n_global != n || s->chunk_cap != (round_up(chunk < 16384 ? 16384 : chunk, 16384) < round_up(n, 16384) ? round_up(chunk < 16384 ? 16384 : chunk, 16384) : round_up(n, 16384))) {
+        if (s) e2s_shard_destroy(s);
+        c->cached = nullptr;
+        if ((rc = e2s_shard_create_chunked(c, n, 0, n, chunk, &s))) return rc;
+        c->cached = s;
+    } else if ((rc = e2s_chunked_reset(s))) {
+        return rc;
+    }
+    const uint8_t* src = static_cast<const uint8_t*>(gesa);
+    uint64_t off_rec = 0;
+    for (uint64_t lo = 0; lo < n; lo += s->chunk_cap) {
+        const uint64_t cn = n - lo < s->chunk_cap ? n - lo : s->chunk_cap;
+        if ((rc = e2s_chunk_begin(s, lo, cn))) return rc;
+        const uint64_t a = lo >= uint64_t(PAD_L) ? lo - PAD_L : 0;
+        const uint64_t b = lo + cn + MAX_C_LEN + 1 < n ? lo + cn + MAX_C_LEN + 1 : n;
+        if ((rc = e2s_shard_load_gesa(s, src + a * uint64_t(rs), a, b - a, x, y, z))) return rc;
+        res->h2d_bytes += (b - a) * uint64_t(rs);
+        uint64_t m = 0;
+        rc = e2s_chunk_scan(s, k, min_len, p->mcov_out, &m);
+        if (rc == E2S_ERR_UNSUPPORTED && lo == 0)  // e.g. an LCP value above 127: the resident two-kernel path takes it
+            return pipeline_host_resident(c, gesa, n, x, y, z, k, min_len, p, rec10, cap_records, events, cap_events, res);
+        if (rc) return rc;
+        if (rec10) {
+            if (off_rec + m > cap_records) return fail(c, E2S_ERR_ARG, "e2s_pipeline_host: record capacity too small");
+            uint64_t got = 0;
+            if (m && (rc = e2s_cluster_fetch_packed(s, static_cast<uint8_t*>(rec10) + off_rec * 10, cap_records - off_rec, &got))) return rc;
+            res->d2h_bytes += m * 10;
+        }
+        off_rec += m;
+    }
+    e2s_cluster_summary sum;
+    if ((rc = e2s_chunked_finish(s, k, min_len, &sum))) return rc;
+    e2s_cluster_merged mg;
+    if ((rc = e2s_cluster_merge(&sum, 1, 0, &mg))) {
+        c->err = g_err;
+        return rc;
+    }
+    if ((rc = e2s_cluster_finalize(s, &mg))) return rc;
+    if (rec10) {  // the records of the tail rule come last (ref:ebwt2clust.cpp:127-135)
+        if (off_rec + mg.n_append > cap_records) return fail(c, E2S_ERR_ARG, "e2s_pipeline_host: record capacity too small");
+        for (uint32_t i = 0; i < mg.n_append; ++i) {
+            uint8_t* o = static_cast<uint8_t*>(rec10) + (off_rec + i) * 10;
+            const uint16_t l16 = uint16_t(mg.append_len[i]);
+            memcpy(o, &mg.append_start[i], 8);
+            memcpy(o + 8, &l16, 2);
+        }
+    }
+    res->n_written = mg.total_written;
+    res->n_clust_out = mg.n_clust_out;
+    if (res->n_written == 0) return fail(c, E2S_ERR_UNSUPPORTED, "no clusters (the reference divides by zero here)");
+    e2s_stats st;
+    if ((rc = e2s_statistics(s, &st))) return rc;
+    if ((rc = e2s_statistics_finish(&st, st.last_len, p->mcov_out, p->pval))) {
+        c->err = g_err;
+        return rc;
+    }
+    res->max_clust_length = st.max_clust_length;
+    if ((rc = e2s_find_events(s, p, st.max_clust_length, &res->snp))) return rc;
+    res->d2h_bytes += res->snp.n_candidates * 128;
+    if (events) {
+        uint64_t nv = 0;
+        if ((rc = e2s_events_fetch(s, events, cap_events, &nv))) return rc;
+    }
     return E2S_OK;
 }
 

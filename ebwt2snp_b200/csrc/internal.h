@@ -245,6 +245,28 @@ cudaError_t launch_len_hist(const uint16_t* len, uint64_t m, unsigned long long*
 cudaError_t launch_check_sorted(const uint64_t* start, const uint16_t* len, uint64_t m, SnpDev* dev,
                                 cudaStream_t stream, int sm_count);
 
+// Streaming (a shard processed chunk by chunk): before a chunk leaves the device, the records of its surviving clusters
+// are copied to a compact payload (same four arrays, `base` of the entry = offset in them), so that phase 2 can run after
+// the last chunk -- when max_clust_length is known -- without a second pass over the input.
+struct CaptureParams {
+    const SurvEntry* in;               // the chunk's survivors (base = index relative to the chunk's local position 0, may be negative)
+    const unsigned long long* n_in;    // device-resident count (capped at n_in_cap)
+    uint64_t n_in_cap;
+    const uint32_t* lcp;
+    const uint32_t* text;
+    const uint32_t* suff;
+    const uint8_t* bwt;                // the chunk's arrays, local position 0
+    uint32_t* p_lcp;
+    uint32_t* p_text;
+    uint32_t* p_suff;
+    uint8_t* p_bwt;                    // payload arrays
+    uint64_t pay_cap;
+    SurvEntry* out;                    // the shard's survivor list (entries with payload offsets)
+    uint64_t out_cap;
+    unsigned long long* counters;      // [0] payload cursor, [1] entries in `out`, [2] error bits: 1 = cluster not resident, 2 = payload full, 4 = list full
+};
+cudaError_t launch_capture(const CaptureParams& p, cudaStream_t stream, int sm_count);
+
 struct SnpWork;  // opaque scratch owned by the shard (snp.cu)
 SnpWork* snp_work_create();
 void snp_work_destroy(SnpWork* w);

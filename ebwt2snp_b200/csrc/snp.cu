@@ -144,6 +144,47 @@ __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// streaming: the surviving clusters' records -> compact payload (one warp per cluster)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_capture(CaptureParams p) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_avail = *p.n_in;
+    const uint64_t n = n_avail < p.n_in_cap ? n_avail : p.n_in_cap;
+    const uint64_t warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t i = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const SurvEntry e = p.in[i];
+        const int64_t local = int64_t(e.base);  // (relative to the chunk's local position 0)
+        if (local < -int64_t(PAD_L)) {  // a cluster whose analysed range left the device with an earlier chunk (wrapped 16-bit length)
+            if (lane == 0) atomicOr(&p.counters[2], 1ull);
+            continue;
+        }
+        unsigned long long off = 0, slot = 0;
+        if (lane == 0) {
+            off = atomicAdd(&p.counters[0], (unsigned long long)e.len);
+            slot = atomicAdd(&p.counters[1], 1ull);
+        }
+        off = __shfl_sync(FULL, off, 0);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (off + e.len > p.pay_cap || slot >= p.out_cap) {
+            if (lane == 0) atomicOr(&p.counters[2], off + e.len > p.pay_cap ? 2ull : 4ull);
+            continue;
+        }
+        for (uint32_t j = lane; j < e.len; j += 32) {
+            p.p_lcp[off + j] = p.lcp[local + j];
+            p.p_text[off + j] = p.text[local + j];
+            p.p_suff[off + j] = p.suff[local + j];
+            p.p_bwt[off + j] = p.bwt[local + j];
+        }
+        if (lane == 0) p.out[slot] = SurvEntry{e.start, off, e.len, 0u};
+    }
+}
+
+cudaError_t launch_capture(const CaptureParams& p, cudaStream_t stream, int sm_count) {
+    k_capture<<<unsigned(sm_count) * 4, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3x: exact find_variants filters for the clusters that survived the prefilter
 // ---------------------------------------------------------------------------------------------
 constexpr int EX_THREADS = 256;

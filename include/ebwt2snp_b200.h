@@ -260,6 +260,34 @@ int e2s_events_format(const e2s_event *events, uint64_t n, uint64_t first_id, co
 void e2s_free(void *p);
 
 /* ---------------------------------------------------------------------------------------
+ * chunked shards: inputs larger than device memory (BASELINE config 4).  The reference streams: ebwt2clust holds three
+ * records at a time (ref:ebwt2clust.cpp:90-122), clust2snp one cluster and the candidates (ref:clust2snp.cpp:806-857).
+ * Here a CHUNK IS A SHARD IN TIME: the device buffers of a chunked shard hold one chunk of the shard's range; chunks are
+ * loaded and scanned one after the other with the open-cluster state carried over on the device side, each chunk's records
+ * are handed out as soon as it is scanned, and the records of the clusters that survive the fused BWT prefilter are copied
+ * to a compact payload, so that clust2snp's analysis runs once, after the last chunk, when statistics() has chosen
+ * max_clust_length -- without a second pass over the index.  Resident footprint: 14.6 bytes x chunk_positions + the
+ * payload (a few KB per candidate variant), whatever n is.
+ *
+ *   e2s_shard_create_chunked(ctx, n_local, global_off, n_global, chunk_positions, &sh);
+ *   for every chunk [lo, lo + cn) of the range, in order (cn = e2s_shard_chunk_positions(sh), the last one may be shorter):
+ *       e2s_chunk_begin(sh, lo, cn);
+ *       e2s_shard_load_gesa / _soa / _soa_dev(...)   records [lo - 176, lo + cn + 152) as far as the eBWT reaches
+ *       e2s_chunk_scan(sh, k, min_len, mcov_out, &m);  e2s_cluster_fetch_packed(sh, ...)  -> the chunk's m records
+ *   e2s_chunked_finish(sh, k, min_len, &summary);  then, exactly as for a resident shard:
+ *   e2s_cluster_merge -> e2s_cluster_finalize -> e2s_statistics (+ _finish) -> e2s_find_events -> e2s_events_fetch.
+ * Needs the one-pass scan: every LCP value <= 127 (reads shorter than 128 bases) and -m <= 33 (else E2S_ERR_UNSUPPORTED).
+ * ------------------------------------------------------------------------------------- */
+int e2s_shard_create_chunked(e2s_ctx *ctx, uint64_t n_local, uint64_t global_off, uint64_t n_global, uint64_t chunk_positions,
+                             e2s_shard **out);
+uint64_t e2s_shard_chunk_positions(const e2s_shard *sh); /* positions per chunk (rounded up to whole scan tiles); 0: not chunked */
+int e2s_chunk_begin(e2s_shard *sh, uint64_t chunk_lo, uint64_t chunk_n);
+/* mcov_out = clust2snp's -m when both tools run (fused prefilter + capture), 0 for ebwt2clust alone */
+int e2s_chunk_scan(e2s_shard *sh, uint32_t k, int32_t min_len, int mcov_out, uint64_t *n_records);
+int e2s_chunked_finish(e2s_shard *sh, uint32_t k, int32_t min_len, e2s_cluster_summary *summary);
+int e2s_chunked_reset(e2s_shard *sh); /* stream the range again from its first chunk */
+
+/* ---------------------------------------------------------------------------------------
  * end-to-end convenience over host buffers (what bench.py's `e2e` times)
  * ------------------------------------------------------------------------------------- */
 typedef struct {
@@ -296,7 +324,8 @@ int e2s_pipeline_sharded(e2s_shard *sh, e2s_comm *comm, uint32_t k, int32_t min_
                          e2s_cluster_merged *merged, e2s_stats *stats, e2s_snp_counts *counts);
 
 /* ebwt2clust + clust2snp on one GPU from host buffers: .gesa records + reads in, .clusters
- * records (10-byte, into rec10 if non-NULL) and events out. */
+ * records (10-byte, into rec10 if non-NULL) and events out.  The records stream through a chunked shard of
+ * E2S_CHUNK_POSITIONS positions (environment, default 2^28): device memory does not grow with n. */
 int e2s_pipeline_host(e2s_ctx *ctx, const void *gesa_records, uint64_t n, int x, int y, int z,
                       const uint8_t *read_bases, const uint64_t *read_off, uint64_t n_reads,
                       uint32_t k, int32_t min_len, const e2s_snp_params *p,

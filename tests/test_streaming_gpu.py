@@ -1,0 +1,139 @@
+"""-m gpu: chunked shards (streaming, BASELINE config 4's mode): a chunk is a shard in time.  Whatever the chunk size, the
+bytes of .clusters and .snp must be the ones of the single resident pass and of the oracle."""
+import numpy as np
+import pytest
+
+from ebwt2snp_b200 import api, synth
+from oracle import oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def stream_phase1(ctx, lcp, bwt, k, m, chunk, lo=0, hi=None, text=None, suff=None, mcov=0):
+    """the range [lo, hi) of the arrays through a chunked shard -> (summary, records of the range, shard)"""
+    n = len(lcp)
+    hi = n if hi is None else hi
+    sh = ctx.shard(hi - lo, lo, n, chunk_positions=chunk)
+    S, L = [], []
+    for clo, cn in sh.chunks():
+        sh.chunk_begin(clo, cn)
+        a, b = max(0, clo - 176), min(n, clo + cn + 152)
+        sh.load_soa(lcp[a:b], None if text is None else text[a:b], None if suff is None else suff[a:b], bwt[a:b], first=a)
+        cnt = sh.chunk_scan(k, m, mcov)
+        s, l = sh.cluster_fetch()
+        assert len(s) == cnt
+        S.append(s)
+        L.append(l)
+    return sh.chunked_finish(k, m), np.concatenate(S), np.concatenate(L), sh
+
+
+def test_chunked_cluster_fuzz(ctx):
+    """random LCP arrays (dense events, long runs, 16-bit wrap) cut into chunks of one, two and a few scan tiles"""
+    rng = np.random.default_rng(77)
+    for it, n in enumerate([16384, 16385, 40000, 100003, 262144 + 7, 300000]):
+        k = int(rng.choice([1, 2, 3, 16, 70]))
+        m = int(rng.choice([1, 2, 3, 8, 33]))
+        lcp = np.minimum(H.random_lcp(rng, n, k, it % 5), 127).astype(np.uint32)
+        if it == 5:
+            lcp[:] = 0
+            lcp[1000:71000] = 40  # one 70 000-long cluster across five chunks: length wraps mod 2^16
+            lcp[100000:100010] = 20
+        bwt = rng.choice(H.BWT_ALPHABET, size=n)
+        es, el, enc, _ = O.cluster_lm(lcp, bwt, k, m)
+        for chunk in (16384, 32768, 5 * 16384):
+            sm, s, l, sh = stream_phase1(ctx, lcp, bwt, k, m, chunk)
+            S, L, mg = H.assemble([sm], [(s, l)])
+            sh.close()
+            assert mg.n_clust_out == enc and np.array_equal(S, es) and np.array_equal(L, el), (n, k, m, chunk)
+
+
+def test_chunked_shards_merge(ctx):
+    """two chunked shards of one eBWT (multi-GPU streaming): summaries merge like those of resident shards"""
+    rng = np.random.default_rng(5)
+    n, k, m = 150_000, 16, 2
+    lcp = np.minimum(H.random_lcp(rng, n, k, 2), 127).astype(np.uint32)
+    bwt = rng.choice(H.BWT_ALPHABET, size=n)
+    es, el, enc, _ = O.cluster_lm(lcp, bwt, k, m)
+    cut = 70_001
+    sums, recs = [], []
+    for lo, hi in ((0, cut), (cut, n)):
+        sm, s, l, sh = stream_phase1(ctx, lcp, bwt, k, m, 32768, lo, hi)
+        sums.append(sm)
+        recs.append((s, l))
+        sh.close()
+    S, L, mg = H.assemble(sums, recs)
+    assert mg.n_clust_out == enc and np.array_equal(S, es) and np.array_equal(L, el)
+
+
+@pytest.mark.parametrize("name,seed", [("tiny", 4), ("small", 2)])
+def test_chunked_pipeline_equals_oracle(ctx, name, seed, monkeypatch):
+    """both tools through chunked shards: chunk = the whole range, a third of it, 100 003 positions (rounded up to scan
+    tiles), one scan tile -- through the chunk API and through e2s_pipeline_host (E2S_CHUNK_POSITIONS)"""
+    rs, e = H.dataset(name, seed)
+    n = e["n"]
+    k, m = 16, 2
+    es, el, enc, _ = O.cluster_lm(e["lcp"], e["bwt"], k, m)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    p, op = api.default_params(rs.nreads1), O.default_params(rs.nreads1)
+    ost = O.statistics(es, el, op.mcov_out, op.pval)
+    otext, ores = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+    assert ores.n_candidates > 0
+    want_clusters = O.clusters_to_bytes(es, el)
+    ctx.stage_reads(rs.reads, off)
+    for chunk in (n, n // 3, 100_003, 16384):
+        sm, s, l, sh = stream_phase1(ctx, e["lcp"], e["bwt"], k, m, chunk, text=e["text"], suff=e["suff"], mcov=p.mcov_out)
+        mg = api.cluster_merge([sm], 0)
+        sh.cluster_finalize(mg)
+        S, L, _ = H.assemble([sm], [(s, l)])
+        assert np.array_equal(S, es) and np.array_equal(L, el), chunk
+        st = sh.statistics(p.mcov_out, p.pval)
+        assert st.max_clust_length == ost.max_clust_length and list(st.hist) == list(ost.hist)
+        cnt = sh.find_events(p, st.max_clust_length)
+        assert (cnt.n_analysed, cnt.n_candidates, cnt.n_events) == (ores.n_analysed, ores.n_candidates, ores.n_events), chunk
+        assert api.events_format(sh.events(), p) == otext, chunk
+        sh.close()
+    # the one-call pipeline from host records
+    rec = synth.gesa_records(e).view(np.uint8).reshape(-1)
+    for chunk in (n, n // 3, 100_003):
+        monkeypatch.setenv("E2S_CHUNK_POSITIONS", str(chunk))
+        rec10 = np.empty((len(es) + 16) * 10, dtype=np.uint8)
+        evbuf = (api.Event * (ores.n_candidates + 16))()
+        res = ctx.pipeline_host(rec, n, rs.reads.reshape(-1), off, p, k, m, rec10=rec10, events=evbuf)
+        assert res.n_written == len(es) and rec10[: len(es) * 10].tobytes() == want_clusters, chunk
+        assert (res.n_clust_out, res.max_clust_length) == (enc, ost.max_clust_length)
+        assert res.snp.n_candidates == ores.n_candidates
+        assert api.events_format(list(evbuf)[: res.snp.n_variants], p) == otext, chunk
+
+
+def test_chunked_needs_byte_lcp(ctx):
+    """an LCP value above 127 keeps a shard off the one-pass scan: chunked shards say so, e2s_pipeline_host falls back"""
+    rs, e = H.dataset("tiny", 4)
+    n = e["n"]
+    lcp = e["lcp"].copy()
+    lcp[n // 2] = 200
+    sh = ctx.shard(n, 0, n, chunk_positions=65536)
+    clo, cn = next(iter(sh.chunks()))
+    sh.chunk_begin(clo, cn)
+    sh.load_soa(lcp[: cn + 152], e["text"][: cn + 152], e["suff"][: cn + 152], e["bwt"][: cn + 152], first=0)
+    if n // 2 < cn + 1:
+        with pytest.raises(api.E2SError) as ei:
+            sh.chunk_scan(16, 2, 5)
+        assert ei.value.code == api.ERR_UNSUPPORTED
+    sh.close()
+    es, el, enc, _ = O.cluster_lm(lcp, e["bwt"], 16, 2)
+    eg = dict(e)
+    eg["lcp"] = lcp
+    rec = synth.gesa_records(eg).view(np.uint8).reshape(-1)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    p = api.default_params(rs.nreads1)
+    rec10 = np.empty((len(es) + 16) * 10, dtype=np.uint8)
+    res = ctx.pipeline_host(rec, n, rs.reads.reshape(-1), off, p, 16, 2, rec10=rec10)
+    assert res.n_written == len(es) and rec10[: len(es) * 10].tobytes() == O.clusters_to_bytes(es, el)
