@@ -286,9 +286,32 @@ def cpu_baseline_leg(args, device, check_ctx=None):
             same_snp = snp == open(os.path.join(d, "ALL.snp"), "rb").read()
             out["parity_vs_reference_on_sample"] = bool(same_cl and same_snp)
             sh.close()
+        out["cli"] = cli_leg(fasta, d, rs.nreads1, n, tc, ts)
         return out
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def cli_leg(fasta, d, nreads1, n, ref_tc, ref_ts):
+    """The drop-in boundary itself: this repository's ebwt2clust + clust2snp as processes on the files the
+    reference just ran on (in /dev/shm), wall clock incl. process start and CUDA context creation; outputs compared."""
+    bin_dir = os.path.join(ROOT, "ebwt2snp_b200", "bin")
+    if not all(os.access(os.path.join(bin_dir, t), os.X_OK) for t in ("ebwt2clust", "clust2snp")):
+        return None
+    snp = os.path.join(d, "ALL.snp")
+    ref_cl, ref_snp = open(fasta + ".clusters", "rb").read(), open(snp, "rb").read()
+    os.remove(fasta + ".clusters")
+    os.remove(snp)
+    t0 = time.perf_counter()
+    r1 = subprocess.run([os.path.join(bin_dir, "ebwt2clust"), "-i", fasta, "-x", "4", "-y", "4", "-z", "4"], capture_output=True)
+    t1 = time.perf_counter()
+    r2 = subprocess.run([os.path.join(bin_dir, "clust2snp"), "-i", fasta, "-n", str(nreads1), "-x", "4", "-y", "4", "-z", "4"], capture_output=True)
+    t2 = time.perf_counter()
+    same = (r1.returncode == 0 and r2.returncode == 0 and open(fasta + ".clusters", "rb").read() == ref_cl and
+            open(snp, "rb").read() == ref_snp)
+    return {"positions": n, "ebwt2clust_s": t1 - t0, "clust2snp_s": t2 - t1, "positions_per_s": n / (t2 - t0),
+            "reference_ebwt2clust_s": ref_tc, "reference_clust2snp_s": ref_ts, "speedup_vs_reference": (ref_tc + ref_ts) / (t2 - t0),
+            "outputs_identical": bool(same), "note": "wall clock of the two processes, files in /dev/shm, process start + CUDA context included"}
 
 
 def reference_arm(args):
@@ -340,6 +363,151 @@ def workload_name(args):
 # the B200 arm
 # --------------------------------------------------------------------------------------------
 
+def bench_c4_streamed(args, torch, dist, api, sharding, rank, world, local, dev):
+    """BASELINE config 4 (1.21e11 positions: more than the HBM of the box holds as records) in the mode built for it: every
+    GPU STREAMS its contiguous range through a chunked shard -- a chunk is a shard in time -- and the ranks exchange their
+    summaries once at the end.  The eBWT is the C2 index tiled with shifted read ids; chunks are
+    produced on the device just before they are loaded (outside the timed regions: the 1.58 TB of records exist nowhere),
+    so the line measures the streaming machinery itself: chunk load (13 B/position copied + narrow copies derived), scan
+    with carried state, capture of the survivors, exchange, phase 2."""
+    rs, eg = make_dataset("C2", args.seed, args.scale, dev)
+    n_tile, R0 = int(eg["n"]), rs.reads.shape[0]
+    full = synth_positions("C4")
+    T_total = max(world, int(round(full * args.scale / n_tile))) if args.tiles <= 1 else args.tiles * world
+    n_global = T_total * n_tile
+    cuts = sharding.shard_cuts(n_global, world)
+    lo, hi = cuts[rank], cuts[rank + 1]
+    stream = torch.cuda.Stream(device=dev)
+    ctx = api.Context(local, stream.cuda_stream)
+    chunk_positions = int(os.environ.get("E2S_CHUNK_POSITIONS", 1 << 27))
+    params = api.default_params(rs.nreads1)
+    reads_dev = torch.from_numpy(rs.reads).to(dev).contiguous().view(-1)  # only tile 0 holds reads of sample 1: candidates come from it
+    L = rs.reads.shape[1]
+    off_dev = torch.arange(R0 + 1, dtype=torch.int64, device=dev) * L
+    ctx.stage_reads(reads_dev, off_dev, device=True, n_bases=R0 * L)
+    comm = sharding.make_comm(ctx, dev) if world > 1 else None
+    # what the totals must be: tiles repeat, so written(T) is linear in T -- from two small resident runs (rank 0's GPU)
+    expect = None
+    if rank == 0:
+        w = {}
+        for T in (2, 3):
+            s2 = ctx.shard(T * n_tile)
+            for t in range(T):
+                s2.load_soa(eg["lcp"], eg["text"] + t * R0 if t else eg["text"], eg["suff"], eg["bwt"], first=t * n_tile, device=True)
+            s2.seal()
+            w[T] = s2.cluster_lm(K_DEF, M_DEF)
+            s2.close()
+        expect = tuple(w[2][i] + (T_total - 2) * (w[3][i] - w[2][i]) for i in range(2))
+        torch.cuda.empty_cache()
+
+    def gen(a, b):
+        idx = torch.arange(a, b, dtype=torch.int64, device=dev)
+        t = idx // n_tile
+        i = idx - t * n_tile
+        text = (eg["text"][i].to(torch.int64) + t * R0).to(torch.int32)
+        return eg["lcp"][i], text, eg["suff"][i], eg["bwt"][i]
+
+    sh = ctx.shard(hi - lo, lo, n_global, chunk_positions=chunk_positions)
+
+    def one_pass():
+        """-> (device ms inside the library calls, merged, stats, counts)"""
+        sh.chunked_reset()
+        ms = 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for clo, cn in sh.chunks():
+            a, b = max(0, clo - 176), min(n_global, clo + cn + 152)
+            arrs = gen(a, b)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            sh.chunk_begin(clo, cn)
+            sh.load_soa(*arrs, first=a, device=True)
+            sh.chunk_scan(K_DEF, M_DEF, params.mcov_out)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+            del arrs
+        e0.record(stream)
+        if comm is not None:
+            mg, st = sh.chunked_exchange(comm, K_DEF, M_DEF, params.mcov_out, params.pval)
+        else:
+            sm = sh.chunked_finish(K_DEF, M_DEF)
+            mg = api.cluster_merge([sm], 0)
+            sh.cluster_finalize(mg)
+            st = sh.statistics(params.mcov_out, params.pval)
+        cnt = sh.find_events(params, st.max_clust_length)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+        return ms, mg, st, cnt
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(1, min(args.warmup, 1))):
+            one_pass()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = ctx.launches
+        t_wall = time.perf_counter()
+        tot_ms = 0.0
+        for _ in range(args.steps):
+            ms, mg, st, cnt = one_pass()
+            tot_ms += ms
+        wall = time.perf_counter() - t_wall
+        clocks = sampler.stop()
+    launches = ctx.launches - launches0
+    ncand = int(cnt.n_candidates)
+    if world > 1:
+        t = torch.tensor([tot_ms, float(ncand)], dtype=torch.float64, device=dev)
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tot_ms, ncand = float(tm[0].item()), int(t[1].item())
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        per_step = tot_ms / args.steps
+        ok = expect is not None and (int(mg.total_written), int(mg.n_clust_out)) == expect
+        print(json.dumps({
+            "metric": METRIC, "value": n_global / (per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": 1, "ms_per_step": per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": workload_name_of("C4") + f"; STREAMED as {T_total} tiles of the C2 index ({n_tile} positions each, read ids shifted) "
+                                   f"through chunked shards of {sh.chunk_positions} positions",
+                       "positions_total": n_global, "positions_per_gpu": hi - lo, "chunk_positions": sh.chunk_positions,
+                       "resident_bytes_per_gpu": int(sh.chunk_positions * 14.6),
+                       "timed": "CUDA events around the library calls of every chunk (begin, device-to-device load + narrow copies, scan, capture) "
+                                "and around the exchange + phase 2; producing the tile arrays on the device is outside (the 1.58 TB of records exist nowhere)",
+                       "wall_s_per_step_incl_tile_production": wall / args.steps,
+                       "l2": "every chunk (>= 1.9 GB of resident arrays) exceeds the 126 MB L2"},
+            "clocks": clocks, "e2e": None, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "chunk load + k_cluster_scan", "achieved": n_global / world * (2 * 13 + 1.375 + 1.25) / (per_step * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": n_global / world * (2 * 13 + 1.375 + 1.25) / (per_step * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src,
+                         "note": "per position: 13 B copied device to device (read + write) + 5 B re-read and 1.375 B written by k_derive "
+                                 "(counted as 1.375 here) + 1.25 B read by the scan"},
+            "cpu_baseline": None,
+            "results": {"n_written": int(mg.total_written), "n_clust_out": int(mg.n_clust_out), "max_clust_length": int(st.max_clust_length),
+                        "n_candidates": ncand, "totals_match_linear_extrapolation_of_resident_runs": bool(ok), "expected": expect},
+        }))
+    sh.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def synth_positions(name):
+    from ebwt2snp_b200 import synth
+    c = synth.CONFIGS[name]
+    return c["reads_per_sample"] * 2 * (2 if c["rc"] else 1) * (c["L"] + 1)
+
+
+def workload_name_of(name):
+    from ebwt2snp_b200 import synth
+    c = synth.CONFIGS[name]
+    return (f"{name}: synthetic {c['G']} bp genome, 2 samples x {c['reads_per_sample']} reads of {c['L']} bp"
+            f"{' + reverse complements' if c['rc'] else ''}, {c['n_snps']} SNPs, {c['n_indels']} indels; "
+            f"ebwt2clust -k 16 -m 2, clust2snp defaults, -x 4 -y 4 -z 4")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -383,6 +551,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
+    if args.workload == "C4":
+        return bench_c4_streamed(args, torch, dist, api, sharding, rank, world, local, dev)
 
     # ---- data: every rank owns one C2-size tile of a global eBWT of world * n positions (weak scaling) ----
     big = args.workload not in ("C1", "C2") and args.scale >= 0.5  # beyond what the torch builder fits on one GPU
@@ -426,8 +596,6 @@ def main():
         args.no_e2e = args.no_cpu_baseline = True
         if world > 1:
             raise SystemExit("--tiles is a single-GPU study")
-    if strong:
-        args.no_e2e = True  # (every rank holds the whole index here; a sharded e2e stages only its range -- see e2e_sharded)
     n_tile = int(eg["n"])
     n = n_tile * T
     n_all = [n]
@@ -461,7 +629,10 @@ def main():
         sh.load_soa(left["lcp"], left["text"], left["suff"], left["bwt"], first=global_off - sharding.HALO_L, device=True)
     if right is not None:
         sh.load_soa(right["lcp"], right["text"], right["suff"], right["bwt"], first=global_off + n, device=True)
-    sh.seal()
+    torch.cuda.synchronize()
+    t_seal = time.perf_counter()
+    sh.seal()  # (the loads wrote the byte LCP and the bit planes themselves: no kernel over the data here, see k_derive)
+    seal_ms = 1e3 * (time.perf_counter() - t_seal)
     reads_dev = torch.from_numpy(rs.reads).to(dev)
     if T > 1:
         reads_dev = reads_dev.repeat(T, 1)
@@ -472,8 +643,13 @@ def main():
     params = api.default_params(rs.nreads1)
 
     host_rec = None
+    rec_first = 0
     if not args.no_e2e:
-        host_rec = aos_records_pinned(eg, torch)
+        if strong:  # one eBWT from host buffers over the ranks: every rank stages ITS range + halos only
+            rec_first, rec_end = max(0, global_off - 176), min(n_global, global_off + n + 152)
+            host_rec = aos_records_pinned(eg, torch, rec_first, rec_end)
+        else:
+            host_rec = aos_records_pinned(eg, torch)
     # generator arrays are no longer needed on the device
     for kk in ("lcp", "text", "suff", "bwt"):
         eg[kk] = None
@@ -603,34 +779,58 @@ def main():
                                  "frac_of_peak": sum(alg[k] for k in alg if ktimes[k][1]) / (ms / args.steps * 1e-3) / 1e9 / peak}}
 
     # ---- e2e: the C-ABI pipeline call from pinned host buffers, copies inside the timed region ----
+    # N = 1: e2s_pipeline_host.  N > 1 (strong): ONE eBWT over the ranks, e2s_pipeline_host_sharded -- every rank streams its
+    # range of the records through a chunked shard, one ncclAllGather of the summaries, phase 2 per rank.
     e2e = None
     if host_rec is not None:
         reads_pin = torch.from_numpy(rs.reads).view(-1).pin_memory()
         off_pin = (torch.arange(R + 1, dtype=torch.int64) * L).pin_memory()
-        sh.close()  # free the resident shard: the pipeline call owns its own
+        sh.close()  # free the resident shard: the pipeline call owns its own (chunked) one
         torch.cuda.empty_cache()
-        rec10 = torch.empty((m_own + 16) * 10, dtype=torch.uint8, pin_memory=True)
+        rec10 = torch.empty((m_own + 64) * 10, dtype=torch.uint8, pin_memory=True)
         evbuf = (api.Event * (int(cnt.n_variants) + 16))()
         rec10_np = rec10.numpy()
-        for _ in range(1):
-            res = ctx.pipeline_host(host_rec, n, reads_pin, off_pin, params, K_DEF, M_DEF, rec10=rec10_np, events=evbuf)
+        sharded_e2e = strong and comm is not None
+
+        def e2e_call():
+            if sharded_e2e:
+                r3, _, _, _ = api.pipeline_host_sharded(ctx, comm, host_rec, rec_first, global_off, n, n_global, reads_pin, off_pin, params,
+                                                        K_DEF, M_DEF, rec10=rec10_np, events=evbuf)
+                return r3
+            return ctx.pipeline_host(host_rec, n, reads_pin, off_pin, params, K_DEF, M_DEF, rec10=rec10_np, events=evbuf)
+
+        res = e2e_call()
         sync_all()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            res = ctx.pipeline_host(host_rec, n, reads_pin, off_pin, params, K_DEF, M_DEF, rec10=rec10_np, events=evbuf)
+            res = e2e_call()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        h2d_b, d2h_b = int(res.h2d_bytes), int(res.d2h_bytes)
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            t = torch.tensor([dt, float(h2d_b), float(d2h_b)], dtype=torch.float64, device=dev)
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dt, h2d_b, d2h_b = float(tmax[0].item()), int(t[1].item()), int(t[2].item())
+        # what the box delivers right now: pinned H2D copies on ALL ranks at the same time (what the e2e number is read against)
+        sync_all()
         probe = h2d_probe(torch, dev)
-        e2e = {"value": n_global * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(res.h2d_bytes),
-               "h2d_probe_GBps": probe, "numa": numa,
-               "d2h_bytes_per_step": int(res.d2h_bytes), "ms_per_step": 1e3 * dt / args.e2e_steps,
-               "steps": args.e2e_steps, "api": "e2s_pipeline_host (13-byte .gesa records + reads in, .clusters records + events out)",
-               "h2d_GBps": res.h2d_bytes * args.e2e_steps / dt / 1e9,
-               "n_events": int(res.snp.n_events), "n_written": int(res.n_written)}
+        probe_sum = probe
+        if world > 1:
+            t = torch.tensor([probe], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            probe_sum = float(t.item())
+        e2e = {"value": n_global * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d_b,
+               "h2d_probe_GBps": probe, "h2d_probe_concurrent_sum_GBps": probe_sum, "numa": numa,
+               "d2h_bytes_per_step": d2h_b, "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "steps": args.e2e_steps,
+               "api": ("e2s_pipeline_host_sharded (one eBWT over the ranks: each streams its range of the 13-byte records through a chunked shard)"
+                       if sharded_e2e else "e2s_pipeline_host (13-byte .gesa records + reads in, .clusters records + events out; chunked shard)"),
+               "chunk_positions": int(os.environ.get("E2S_CHUNK_POSITIONS", 1 << 28)),
+               "h2d_GBps": h2d_b * args.e2e_steps / dt / 1e9,
+               "fraction_of_concurrent_probe": (h2d_b * args.e2e_steps / dt / 1e9) / probe_sum if probe_sum else None,
+               "n_events_rank0": int(res.snp.n_events), "n_written": int(res.n_written)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -646,7 +846,10 @@ def main():
                        "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; " + ("one ncclAllGather of the shard summaries per step, issued by the library on its stream (e2s_pipeline_sharded)" if comm is not None else ("no exchange (single shard: e2s_pipeline_resident)" if world == 1 else "torch.distributed all-gather of shard summaries")),
                        "l2": "the resident inputs a step streams (1.25-4.25 B/position: >= 0.7 GB per GPU at C2) exceed the 126 MB L2; no flush needed",
                        "resident_layout": f"SoA: lcp u32 + text u32 + suff u32 + bwt u8 + 2-bit base-code planes of the BWT (built at seal); K1 streams a {'one-byte LCP copy built at seal (every LCP value <= 127)' if lcp_bytes == 1 else 'the 4-byte LCP'}",
-                       "scale": args.scale, "tiles": T, "exchange_us": exchange_us},
+                       "scale": args.scale, "tiles": T, "exchange_us": exchange_us,
+                       "seal": {"ms": seal_ms, "kernels_over_the_data": 0,
+                                "note": "the byte LCP and the bit planes are written by the loads (k_derive): sealing is a 4-byte read-back"}},
+            "value_one_pass": n_global * args.steps / (ms * 1e-3 + args.steps * seal_ms * 1e-3),
             "clocks": clocks, "e2e": e2e, "egsa_build": egsa_build, "index_check": index_check, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "results": {"n_written": int(mg.total_written), "n_clust_out": int(mg.n_clust_out),
                         "max_clust_length": int(st.max_clust_length), "n_analysed_rank0": int(cnt.n_analysed),

@@ -87,7 +87,7 @@ SYMBOLS = [
     "e2s_events_format", "e2s_free", "e2s_pipeline_resident", "e2s_pipeline_host",
     "e2s_comm_unique_id", "e2s_comm_create", "e2s_comm_destroy", "e2s_pipeline_sharded",
     "e2s_exchange_row_words", "e2s_exchange_rows_finish",
-    "e2s_shard_create_chunked", "e2s_shard_chunk_positions", "e2s_chunk_begin", "e2s_chunk_scan", "e2s_chunked_finish", "e2s_chunked_reset",
+    "e2s_pipeline_host_sharded", "e2s_shard_create_chunked", "e2s_shard_chunk_positions", "e2s_chunk_begin", "e2s_chunk_scan", "e2s_chunked_finish", "e2s_chunked_reset", "e2s_chunked_exchange",
 ]
 
 _lib = None
@@ -166,9 +166,14 @@ def load_library():
     lib.e2s_chunk_scan.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int, C.POINTER(C.c_uint64)]
     lib.e2s_chunked_finish.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(ClusterSummary)]
     lib.e2s_chunked_reset.argtypes = [C.c_void_p]
+    lib.e2s_chunked_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int, C.c_double, C.POINTER(ClusterMerged), C.POINTER(Stats)]
     lib.e2s_pipeline_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(SnpParams), C.c_void_p,
                                       C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PipelineResult)]
+    lib.e2s_pipeline_host_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
+                                              C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(SnpParams),
+                                              C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64,
+                                              C.POINTER(ClusterMerged), C.POINTER(Stats), C.POINTER(PipelineResult)]
     _lib = lib
     return lib
 
@@ -355,6 +360,21 @@ class Context:
         return res
 
 
+def pipeline_host_sharded(ctx, comm, records, first, range_lo, range_n, n_global, reads_bases, reads_off, params, k=16, min_len=2,
+                          x=4, y=4, z=4, rec10=None, events=None):
+    """e2s_pipeline_host_sharded: this rank's range of ONE eBWT from host records -> (PipelineResult, ClusterMerged, Stats, records in rec10)"""
+    res, mg, st = PipelineResult(), ClusterMerged(), Stats()
+    n_reads = (len(reads_off) - 1) if reads_off is not None else 0
+    cap_r = (rec10.nbytes // 10) if rec10 is not None else 0
+    cap_e = len(events) if events is not None else 0
+    m = C.c_uint64()
+    ctx._ck(ctx.lib.e2s_pipeline_host_sharded(ctx.h, comm.h, _ptr(records), int(first), int(range_lo), int(range_n), int(n_global), x, y, z,
+                                              _ptr(reads_bases), _ptr(reads_off), n_reads, k, min_len, C.byref(params), _ptr(rec10), cap_r,
+                                              C.byref(m), C.cast(events, C.c_void_p) if events is not None else None, cap_e,
+                                              C.byref(mg), C.byref(st), C.byref(res)))
+    return res, mg, st, m.value
+
+
 class Comm:
     """The library's own NCCL communicator for the exchange between the phases (one process per GPU).  The 128-byte
     unique id is created on rank 0 and broadcast by the caller's launcher plumbing (torch.distributed)."""
@@ -414,6 +434,12 @@ class Shard:
         s = ClusterSummary()
         self.ctx._ck(self.lib.e2s_chunked_finish(self.h, k, min_len, C.byref(s)))
         return s
+
+    def chunked_exchange(self, comm, k=16, min_len=2, mcov_out=5, pval=0.99):
+        """multi-GPU: finish + all-gather of the ranks' accumulators + merge + statistics + finalize (collective)"""
+        mg, st = ClusterMerged(), Stats()
+        self.ctx._ck(self.lib.e2s_chunked_exchange(self.h, comm.h, k, min_len, int(mcov_out), float(pval), C.byref(mg), C.byref(st)))
+        return mg, st
 
     def chunked_reset(self):
         self.ctx._ck(self.lib.e2s_chunked_reset(self.h))

@@ -1000,6 +1000,7 @@ static int cluster_run_impl(e2s_shard* s, uint32_t k, int32_t min_len, e2s_clust
 }
 
 
+
 }  // extern "C"
 // capacity of the payload / survivor list of a chunked shard (grown between chunks, contents kept)
 template <typename T>
@@ -2019,6 +2020,39 @@ static int pipeline_host_resident(e2s_ctx* c, const void* gesa, uint64_t n, int 
     return E2S_OK;
 }
 
+// All chunks of a chunked shard's range from host records (`records` = the record of global position `first`; it must reach
+// from the range's left context to its right halo): load, scan, this chunk's records out (into rec10 from slot *off_rec on).
+static int stream_range(e2s_shard* s, const void* records, uint64_t first, int x, int y, int z, uint32_t k, int32_t min_len,
+                        int mcov_out, void* rec10, uint64_t cap_records, uint64_t* off_rec, e2s_pipeline_result* res,
+                        bool* unsupported_first) {
+    e2s_ctx* c = s->ctx;
+    const uint64_t n = s->n_global, end = s->range_lo + s->range_n;
+    const int rs = x + y + z + 1;
+    const uint8_t* src = static_cast<const uint8_t*>(records);
+    int rc;
+    for (uint64_t lo = s->range_lo; lo < end; lo += s->chunk_cap) {
+        const uint64_t cn = end - lo < s->chunk_cap ? end - lo : s->chunk_cap;
+        if ((rc = e2s_chunk_begin(s, lo, cn))) return rc;
+        const uint64_t a0 = lo >= uint64_t(PAD_L) ? lo - PAD_L : 0;
+        const uint64_t a = a0 > first ? a0 : first;
+        const uint64_t b = lo + cn + MAX_C_LEN + 1 < n ? lo + cn + MAX_C_LEN + 1 : n;
+        if ((rc = e2s_shard_load_gesa(s, src + (a - first) * uint64_t(rs), a, b - a, x, y, z))) return rc;
+        res->h2d_bytes += (b - a) * uint64_t(rs);
+        uint64_t m = 0;
+        rc = e2s_chunk_scan(s, k, min_len, mcov_out, &m);
+        if (rc == E2S_ERR_UNSUPPORTED && lo == s->range_lo && unsupported_first) *unsupported_first = true;
+        if (rc) return rc;
+        if (rec10) {
+            if (*off_rec + m > cap_records) return fail(c, E2S_ERR_ARG, "record capacity too small");
+            uint64_t got = 0;
+            if (m && (rc = e2s_cluster_fetch_packed(s, static_cast<uint8_t*>(rec10) + *off_rec * 10, cap_records - *off_rec, &got))) return rc;
+            res->d2h_bytes += m * 10;
+        }
+        *off_rec += m;
+    }
+    return E2S_OK;
+}
+
 // ebwt2clust + clust2snp from host buffers.  The records stream through a CHUNKED shard (a chunk is a shard in time): the
 // device holds one chunk of E2S_CHUNK_POSITIONS positions (default 2^28) whatever n is, the H2D copies of a chunk run on
 // their own stream ahead of its de-interleave kernels, each chunk's records go back as soon as it is scanned, the records
@@ -2050,28 +2084,12 @@ int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, in
     } else if ((rc = e2s_chunked_reset(s))) {
         return rc;
     }
-    const uint8_t* src = static_cast<const uint8_t*>(gesa);
     uint64_t off_rec = 0;
-    for (uint64_t lo = 0; lo < n; lo += s->chunk_cap) {
-        const uint64_t cn = n - lo < s->chunk_cap ? n - lo : s->chunk_cap;
-        if ((rc = e2s_chunk_begin(s, lo, cn))) return rc;
-        const uint64_t a = lo >= uint64_t(PAD_L) ? lo - PAD_L : 0;
-        const uint64_t b = lo + cn + MAX_C_LEN + 1 < n ? lo + cn + MAX_C_LEN + 1 : n;
-        if ((rc = e2s_shard_load_gesa(s, src + a * uint64_t(rs), a, b - a, x, y, z))) return rc;
-        res->h2d_bytes += (b - a) * uint64_t(rs);
-        uint64_t m = 0;
-        rc = e2s_chunk_scan(s, k, min_len, p->mcov_out, &m);
-        if (rc == E2S_ERR_UNSUPPORTED && lo == 0)  // e.g. an LCP value above 127: the resident two-kernel path takes it
-            return pipeline_host_resident(c, gesa, n, x, y, z, k, min_len, p, rec10, cap_records, events, cap_events, res);
-        if (rc) return rc;
-        if (rec10) {
-            if (off_rec + m > cap_records) return fail(c, E2S_ERR_ARG, "e2s_pipeline_host: record capacity too small");
-            uint64_t got = 0;
-            if (m && (rc = e2s_cluster_fetch_packed(s, static_cast<uint8_t*>(rec10) + off_rec * 10, cap_records - off_rec, &got))) return rc;
-            res->d2h_bytes += m * 10;
-        }
-        off_rec += m;
-    }
+    bool unsupported_first = false;
+    rc = stream_range(s, gesa, 0, x, y, z, k, min_len, p->mcov_out, rec10, cap_records, &off_rec, res, &unsupported_first);
+    if (unsupported_first)  // e.g. an LCP value above 127: the resident two-kernel path takes it
+        return pipeline_host_resident(c, gesa, n, x, y, z, k, min_len, p, rec10, cap_records, events, cap_events, res);
+    if (rc) return rc;
     e2s_cluster_summary sum;
     if ((rc = e2s_chunked_finish(s, k, min_len, &sum))) return rc;
     e2s_cluster_merged mg;
@@ -2100,6 +2118,105 @@ int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, in
     }
     res->max_clust_length = st.max_clust_length;
     if ((rc = e2s_find_events(s, p, st.max_clust_length, &res->snp))) return rc;
+    res->d2h_bytes += res->snp.n_candidates * 128;
+    if (events) {
+        uint64_t nv = 0;
+        if ((rc = e2s_events_fetch(s, events, cap_events, &nv))) return rc;
+    }
+    return E2S_OK;
+}
+
+
+// After the last chunk of every rank's chunked shard: e2s_chunked_finish, ONE ncclAllGather of the ranks' rows (accumulators +
+// range, the format of the resident sharded step), merge + statistics() on every rank, e2s_cluster_finalize.  Collective.
+int e2s_chunked_exchange(e2s_shard* s, e2s_comm* cm, uint32_t k, int32_t min_len, int mcov_out, double pval, e2s_cluster_merged* merged,
+                         e2s_stats* stats) {
+    if (!s || !cm || !merged || !stats) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_chunked_exchange: NULL argument");
+    e2s_ctx* c = s->ctx;
+    if (cm->ctx != c) return fail(c, E2S_ERR_ARG, "e2s_chunked_exchange: communicator belongs to another context");
+    int rc;
+    e2s_cluster_summary sum;
+    if ((rc = e2s_chunked_finish(s, k, min_len, &sum))) return rc;
+    uint64_t row[XR_WORDS];
+    memcpy(row, &s->acc, sizeof(ClusterDev));
+    reinterpret_cast<ClusterDev*>(row)->ticket = 0;
+    row[XR_DEV_WORDS + 0] = s->range_n;
+    row[XR_DEV_WORDS + 1] = s->range_lo;
+    row[XR_DEV_WORDS + 2] = uint64_t(s->lay_x);
+    row[XR_DEV_WORDS + 3] = 0;
+    NcclApi* na = nccl_api();
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(cm->d_send, row, sizeof row, cudaMemcpyHostToDevice, c->stream));
+    const int nr = na->AllGather(cm->d_send, cm->d_recv, XR_WORDS, NCCL_UINT64, cm->nccl, c->stream);
+    if (nr != 0) return fail(c, E2S_ERR_CUDA, std::string("ncclAllGather: ") + (na->GetErrorString ? na->GetErrorString(nr) : "error"));
+    CU(c, cudaMemcpyAsync(cm->h_recv, cm->d_recv, size_t(cm->world) * XR_WORDS * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if ((rc = e2s_exchange_rows_finish(cm->h_recv, cm->world, cm->rank, s->n_global, k, min_len, mcov_out, pval, merged, stats))) {
+        c->err = g_err;
+        return rc;
+    }
+    return e2s_cluster_finalize(s, merged);
+}
+
+// One eBWT over the GPUs of a box, from host buffers, one process (rank) per GPU: every rank streams ITS range of the records
+// through a chunked shard (staging nothing but its range + halo), the ranks' summaries and own-record histograms are
+// all-gathered (one ncclAllGather of a row per rank), every rank merges and finishes statistics(), then runs phase 2 on its
+// captured survivors.  `records` = the record of global position `first`; the buffer must reach from max(0, range_lo - 176)
+// to min(n_global, range_lo + range_n + 152).  rec10 receives this rank's slice of .clusters (head record, own records,
+// tail records, in file order): *n_records records that belong at index merged->record_offset of the file.
+int e2s_pipeline_host_sharded(e2s_ctx* c, e2s_comm* cm, const void* records, uint64_t first, uint64_t range_lo, uint64_t range_n,
+                              uint64_t n_global, int x, int y, int z, const uint8_t* read_bases, const uint64_t* read_off,
+                              uint64_t n_reads, uint32_t k, int32_t min_len, const e2s_snp_params* p, void* rec10,
+                              uint64_t cap_records, uint64_t* n_records, e2s_event* events, uint64_t cap_events,
+                              e2s_cluster_merged* merged, e2s_stats* stats, e2s_pipeline_result* res) {
+    if (!c || !cm || !records || !p || !res || !merged || !stats) return fail(c, E2S_ERR_ARG, "NULL argument");
+    if (cm->ctx != c) return fail(c, E2S_ERR_ARG, "e2s_pipeline_host_sharded: communicator belongs to another context");
+    memset(res, 0, sizeof *res);
+    auto ok = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8; };
+    if (!ok(x) || !ok(y) || !ok(z)) return fail(c, E2S_ERR_ARG, "field byte sizes must be 1, 2, 4 or 8");
+    if (!(p->mcov_out >= 1 && 2 * p->mcov_out <= E2S_MAX_C_LEN) || min_len > 33)
+        return fail(c, E2S_ERR_UNSUPPORTED, "e2s_pipeline_host_sharded needs a valid -m (clust2snp) and ebwt2clust -m <= 33");
+    int rc;
+    if (read_bases) {
+        if ((rc = e2s_reads_stage(c, read_bases, read_off, n_reads))) return rc;
+        res->h2d_bytes += read_off[n_reads] + (n_reads + 1) * 8;
+    }
+    const uint64_t chunk = chunk_positions_from_env();
+    e2s_shard* s = c->cached;
+    if (!s || !s->chunked || s->range_n != range_n || s->range_lo != range_lo || s->n_global != n_global) {
+        if (s) e2s_shard_destroy(s);
+        c->cached = nullptr;
+        if ((rc = e2s_shard_create_chunked(c, range_n, range_lo, n_global, chunk, &s))) return rc;
+        c->cached = s;
+    } else if ((rc = e2s_chunked_reset(s))) {
+        return rc;
+    }
+    uint8_t* out = static_cast<uint8_t*>(rec10);
+    uint64_t off_rec = rec10 ? 1 : 0;  // slot 0 is kept for the shard's head record
+    if ((rc = stream_range(s, records, first, x, y, z, k, min_len, p->mcov_out, rec10, cap_records, &off_rec, res, nullptr))) return rc;
+    if ((rc = e2s_chunked_exchange(s, cm, k, min_len, p->mcov_out, p->pval, merged, stats))) return rc;
+    uint64_t slice_first = 1, m_slice = off_rec ? off_rec - 1 : 0;
+    if (rec10) {
+        auto put = [&](uint64_t slot, uint64_t st, uint64_t ln) {
+            const uint16_t l16 = uint16_t(ln);
+            memcpy(out + slot * 10, &st, 8);
+            memcpy(out + slot * 10 + 8, &l16, 2);
+        };
+        if (merged->n_prepend && merged->prepend_written) {
+            put(0, merged->prepend_start, merged->prepend_len);
+            slice_first = 0;
+            ++m_slice;
+        }
+        if (off_rec + merged->n_append > cap_records) return fail(c, E2S_ERR_ARG, "record capacity too small");
+        for (uint32_t i = 0; i < merged->n_append; ++i) put(off_rec + i, merged->append_start[i], merged->append_len[i]);
+        m_slice += merged->n_append;
+        if (slice_first) memmove(out, out + 10, size_t(m_slice) * 10);  // no head record: the slice starts at slot 0 all the same
+    }
+    if (n_records) *n_records = m_slice;
+    res->n_written = merged->total_written;
+    res->n_clust_out = merged->n_clust_out;
+    res->max_clust_length = stats->max_clust_length;
+    if ((rc = e2s_find_events(s, p, stats->max_clust_length, &res->snp))) return rc;
     res->d2h_bytes += res->snp.n_candidates * 128;
     if (events) {
         uint64_t nv = 0;

@@ -49,6 +49,9 @@ CONFIGS = {
     "C1": dict(G=1_000_000, reads_per_sample=50_000, L=100, n_snps=1_000, n_indels=0, rc=False),
     "C2": dict(G=4_600_000, reads_per_sample=1_380_000, L=100, n_snps=4_600, n_indels=0, rc=True),
     "C3": dict(G=64_000_000, reads_per_sample=19_200_000, L=100, n_snps=64_000, n_indels=6_400, rc=False),
+    # C4 (3 Gbp, 2 x 20x: 1.21e11 positions, 1.58 TB of .gesa records) is never generated in one piece: bench.py streams it as
+    # tiles of the C2 index with shifted read ids (every tile starts with lcp = 0, no cluster spans tiles)
+    "C4": dict(G=3_000_000_000, reads_per_sample=600_000_000, L=100, n_snps=3_000_000, n_indels=0, rc=False),
 }
 
 

@@ -47,6 +47,7 @@ extern "C" {
 
 typedef struct e2s_ctx e2s_ctx;
 typedef struct e2s_shard e2s_shard;
+typedef struct e2s_comm e2s_comm; /* one process per GPU: wraps an NCCL communicator (e2s_comm_create) */
 
 /* ---------------------------------------------------------------------------------------
  * context
@@ -286,6 +287,10 @@ int e2s_chunk_begin(e2s_shard *sh, uint64_t chunk_lo, uint64_t chunk_n);
 int e2s_chunk_scan(e2s_shard *sh, uint32_t k, int32_t min_len, int mcov_out, uint64_t *n_records);
 int e2s_chunked_finish(e2s_shard *sh, uint32_t k, int32_t min_len, e2s_cluster_summary *summary);
 int e2s_chunked_reset(e2s_shard *sh); /* stream the range again from its first chunk */
+/* Chunked shards on several GPUs (one process per GPU): after every rank's last chunk, e2s_chunked_finish + ONE ncclAllGather
+ * of the ranks' accumulators + merge + statistics() + e2s_cluster_finalize.  Collective over the communicator. */
+int e2s_chunked_exchange(e2s_shard *sh, e2s_comm *comm, uint32_t k, int32_t min_len, int mcov_out, double pval,
+                         e2s_cluster_merged *merged, e2s_stats *stats);
 
 /* ---------------------------------------------------------------------------------------
  * end-to-end convenience over host buffers (what bench.py's `e2e` times)
@@ -316,7 +321,6 @@ int e2s_pipeline_resident(e2s_shard *sh, uint32_t k, int32_t min_len, const e2s_
 uint64_t e2s_exchange_row_words(void);
 int e2s_exchange_rows_finish(const uint64_t *rows, int n_shards, int my, uint64_t n_global, uint32_t k, int32_t min_len,
                              int mcov_out, double pval, e2s_cluster_merged *mine, e2s_stats *total);
-typedef struct e2s_comm e2s_comm;
 int e2s_comm_unique_id(uint8_t *id128);
 int e2s_comm_create(e2s_ctx *ctx, const uint8_t *id128, int rank, int world, e2s_comm **out);
 void e2s_comm_destroy(e2s_comm *comm);
@@ -331,6 +335,19 @@ int e2s_pipeline_host(e2s_ctx *ctx, const void *gesa_records, uint64_t n, int x,
                       uint32_t k, int32_t min_len, const e2s_snp_params *p,
                       void *rec10, uint64_t cap_records, e2s_event *events, uint64_t cap_events,
                       e2s_pipeline_result *res);
+
+/* The same for ONE eBWT over the GPUs of a box, one process (rank) per GPU: every rank streams its contiguous
+ * range [range_lo, range_lo + range_n) of the records through a chunked shard -- it stages nothing but its range and the
+ * halos -- then the ranks' summaries and own-record histograms are exchanged with one ncclAllGather, every rank merges,
+ * finishes statistics() and runs phase 2 on the clusters it owns.  `records` points at the record of global position `first`
+ * and must reach from max(0, range_lo - 176) to min(n_global, range_lo + range_n + 152).  rec10 (if non-NULL) receives this
+ * rank's slice of the .clusters file: *n_records records that belong at index merged->record_offset.  Event ids are an
+ * output-time matter: the caller numbers them from the ranks' n_events.  Collective: every rank of the communicator calls it. */
+int e2s_pipeline_host_sharded(e2s_ctx *ctx, e2s_comm *comm, const void *records, uint64_t first, uint64_t range_lo,
+                              uint64_t range_n, uint64_t n_global, int x, int y, int z, const uint8_t *read_bases,
+                              const uint64_t *read_off, uint64_t n_reads, uint32_t k, int32_t min_len, const e2s_snp_params *p,
+                              void *rec10, uint64_t cap_records, uint64_t *n_records, e2s_event *events, uint64_t cap_events,
+                              e2s_cluster_merged *merged, e2s_stats *stats, e2s_pipeline_result *res);
 
 #ifdef __cplusplus
 }

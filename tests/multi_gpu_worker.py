@@ -44,6 +44,24 @@ def main():
         comm = sharding.make_comm(ctx, dev)
         mg2, st2, cnt2, _ = sharding.hot_path_step(sh, p, k, m, dev, comm=comm)
         assert bytes(mg2) == bytes(mg) and bytes(st2) == bytes(st) and bytes(cnt2) == bytes(cnt), "native exchange differs"
+        # ... and end to end from host records: every rank streams its range through a chunked shard (e2s_pipeline_host_sharded)
+        a2, b2 = max(0, lo - 176), min(n, hi + 152)
+        sub = {kk: eg[kk][a2:b2] for kk in ("lcp", "text", "suff", "bwt")}
+        sub["n"] = b2 - a2
+        rec = synth.gesa_records(sub).view(np.uint8).reshape(-1)
+        os.environ["E2S_CHUNK_POSITIONS"] = str(32768 if name == "tiny" else 1 << 20)
+        ctx2 = api.Context(local)
+        comm2 = sharding.make_comm(ctx2, dev)
+        rec10 = np.empty((len(sh.cluster_fetch_packed()) // 10 + 16) * 10, dtype=np.uint8)
+        evbuf = (api.Event * (int(cnt.n_variants) + 16))()
+        res3, mg3, st3, m3 = api.pipeline_host_sharded(ctx2, comm2, rec, a2, lo, hi - lo, n, rs.reads.reshape(-1), off, p, k, m,
+                                                       rec10=rec10, events=evbuf)
+        assert bytes(mg3) == bytes(mg) and bytes(st3) == bytes(st), "chunked sharded pipeline: merge / statistics differ"
+        assert rec10[: m3 * 10].tobytes() == sh.cluster_fetch_packed(), "chunked sharded pipeline: records differ"
+        assert (res3.snp.n_candidates, res3.snp.n_events) == (cnt.n_candidates, cnt.n_events)
+        assert api.events_format(list(evbuf)[: res3.snp.n_variants], p) == api.events_format(sh.events(), p)
+        comm2.close()
+        ctx2.close()
         comm.close()
         first_id, total_events = ids.resolve()
         recs = sh.cluster_fetch_packed()
