@@ -67,23 +67,77 @@ int main(int argc, char** argv) {
         return 2;
     }
 
+    // One shard per GPU (E2S_GPUS), each STREAMED through the device chunk by chunk (a chunk is a shard in time: the device holds
+    // E2S_CHUNK_POSITIONS positions, default 2^28, whatever the size of the index); inputs the one-pass scan does not take
+    // (an LCP value above 127, -m > 33) go through a resident shard instead.
     const std::vector<uint64_t> cuts = host::shard_cuts(idx.n, host::gpu_count_from_env());
     const int G = int(cuts.size()) - 1;
+    uint64_t chunk = uint64_t(1) << 28;
+    if (const char* e = getenv("E2S_CHUNK_POSITIONS"))
+        if (strtoull(e, nullptr, 10)) chunk = strtoull(e, nullptr, 10);
     std::vector<e2s_ctx*> ctx(size_t(G), nullptr);
     std::vector<e2s_shard*> sh(size_t(G), nullptr);
     std::vector<e2s_cluster_summary> sums(static_cast<size_t>(G));
+    std::vector<std::vector<uint8_t>> recs(static_cast<size_t>(G));  // every shard's own records, 10 bytes each, in file order
     std::vector<int> rc(size_t(G), 0);
     std::vector<std::string> errs(static_cast<size_t>(G));
-    auto work = [&](int g) {
-        int r = e2s_ctx_create(g, &ctx[size_t(g)]);
-        if (r) { rc[size_t(g)] = r; errs[size_t(g)] = e2s_last_error(nullptr); return; }
+    auto resident = [&](int g) -> int {  // the whole range on the device at once
         const uint64_t lo = cuts[size_t(g)], hi = cuts[size_t(g) + 1];
-        r = e2s_shard_create(ctx[size_t(g)], hi - lo, lo, idx.n, &sh[size_t(g)]);
+        if (sh[size_t(g)]) e2s_shard_destroy(sh[size_t(g)]);
+        sh[size_t(g)] = nullptr;
+        int r = e2s_shard_create(ctx[size_t(g)], hi - lo, lo, idx.n, &sh[size_t(g)]);
         const uint64_t a = lo >= 2 ? lo - 2 : 0, b = hi + E2S_MAX_C_LEN + 1 < idx.n ? hi + E2S_MAX_C_LEN + 1 : idx.n;
         if (!r) r = idx.load(sh[size_t(g)], a, b - a);
         if (!r) r = e2s_shard_set_layout(sh[size_t(g)], idx.x, idx.y, idx.z, idx.bcr ? 1 : 0);
         if (!r) r = e2s_shard_seal(sh[size_t(g)]);
         if (!r) r = e2s_cluster_run(sh[size_t(g)], uint32_t(k), min_len, &sums[size_t(g)]);
+        uint64_t m = 0;
+        e2s_cluster_merged none;
+        memset(&none, 0, sizeof none);
+        if (!r) r = e2s_cluster_finalize(sh[size_t(g)], &none);  // own records only: head / tail records are written from the merge below
+        if (!r) r = e2s_cluster_count(sh[size_t(g)], &m);
+        if (!r) {
+            recs[size_t(g)].resize(size_t(m) * 10 + 16);
+            r = e2s_cluster_fetch_packed(sh[size_t(g)], recs[size_t(g)].data(), m, &m);
+            recs[size_t(g)].resize(size_t(m) * 10);
+        }
+        return r;
+    };
+    auto work = [&](int g) {
+        int r = e2s_ctx_create(g, &ctx[size_t(g)]);
+        if (r) { rc[size_t(g)] = r; errs[size_t(g)] = e2s_last_error(nullptr); return; }
+        const uint64_t lo = cuts[size_t(g)], hi = cuts[size_t(g) + 1];
+        bool fall_back = min_len > 33;
+        if (!fall_back) {
+            r = e2s_shard_create_chunked(ctx[size_t(g)], hi - lo, lo, idx.n, chunk, &sh[size_t(g)]);
+            if (!r) r = e2s_shard_set_layout(sh[size_t(g)], idx.x, idx.y, idx.z, idx.bcr ? 1 : 0);
+            const uint64_t cp = r ? 0 : e2s_shard_chunk_positions(sh[size_t(g)]);
+            for (uint64_t clo = lo; !r && clo < hi; clo += cp) {
+                const uint64_t cn = hi - clo < cp ? hi - clo : cp;
+                r = e2s_chunk_begin(sh[size_t(g)], clo, cn);
+                const uint64_t a = clo >= 176 ? clo - 176 : 0, b = clo + cn + E2S_MAX_C_LEN + 1 < idx.n ? clo + cn + E2S_MAX_C_LEN + 1 : idx.n;
+                if (!r) r = idx.load(sh[size_t(g)], a, b - a);
+                if (!r) r = e2s_shard_set_layout(sh[size_t(g)], idx.x, idx.y, idx.z, idx.bcr ? 1 : 0);
+                uint64_t m = 0;
+                if (!r) r = e2s_chunk_scan(sh[size_t(g)], uint32_t(k), min_len, 0, &m);
+                if (r == E2S_ERR_UNSUPPORTED && clo == lo) {  // not an input for the one-pass scan
+                    fall_back = true;
+                    r = 0;
+                    break;
+                }
+                if (!r && m) {
+                    const size_t at = recs[size_t(g)].size();
+                    recs[size_t(g)].resize(at + size_t(m) * 10 + 16);
+                    r = e2s_cluster_fetch_packed(sh[size_t(g)], recs[size_t(g)].data() + at, m, &m);
+                    recs[size_t(g)].resize(at + size_t(m) * 10);
+                }
+            }
+            if (!r && !fall_back) r = e2s_chunked_finish(sh[size_t(g)], uint32_t(k), min_len, &sums[size_t(g)]);
+        }
+        if (!r && fall_back) {
+            recs[size_t(g)].clear();
+            r = resident(g);
+        }
         if (r) { rc[size_t(g)] = r; errs[size_t(g)] = e2s_last_error(ctx[size_t(g)]); }
     };
     {
@@ -103,22 +157,25 @@ int main(int argc, char** argv) {
         return 2;
     }
     uint64_t n_clust_out = 0;
-    std::vector<uint8_t> buf;
-    for (int g = 0; g < G; ++g) {
+    auto put = [&](uint64_t st, uint64_t ln) {
+        uint8_t r10[10];
+        const uint16_t l16 = uint16_t(ln);
+        memcpy(r10, &st, 8);
+        memcpy(r10 + 8, &l16, 2);
+        return fwrite(r10, 10, 1, out) == 1;
+    };
+    for (int g = 0; g < G; ++g) {  // every shard's slice of the file: [head record] own records [tail records]
         e2s_cluster_merged mg;
-        int r = e2s_cluster_merge(sums.data(), G, g, &mg);
-        if (!r) r = e2s_cluster_finalize(sh[size_t(g)], &mg);
-        uint64_t m = 0;
-        if (!r) r = e2s_cluster_count(sh[size_t(g)], &m);
-        if (!r) {
-            buf.resize(size_t(m) * 10 + 16);
-            r = e2s_cluster_fetch_packed(sh[size_t(g)], buf.data(), m, &m);
-        }
-        if (r) {
-            std::cerr << "ebwt2clust: " << (e2s_last_error(ctx[size_t(g)])[0] ? e2s_last_error(ctx[size_t(g)]) : e2s_last_error(nullptr)) << std::endl;
+        if (e2s_cluster_merge(sums.data(), G, g, &mg)) {
+            std::cerr << "ebwt2clust: " << e2s_last_error(nullptr) << std::endl;
             return 2;
         }
-        if (m && fwrite(buf.data(), 10, size_t(m), out) != size_t(m)) {
+        bool okw = true;
+        if (mg.n_prepend && mg.prepend_written) okw = put(mg.prepend_start, mg.prepend_len);
+        const size_t m = recs[size_t(g)].size() / 10;
+        if (okw && m) okw = fwrite(recs[size_t(g)].data(), 10, m, out) == m;
+        for (uint32_t i = 0; okw && i < mg.n_append; ++i) okw = put(mg.append_start[i], mg.append_len[i]);
+        if (!okw) {
             std::cerr << "ebwt2clust: short write" << std::endl;
             return 2;
         }
