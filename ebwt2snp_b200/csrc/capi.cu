@@ -51,8 +51,8 @@ struct e2s_shard {
     uint8_t* bwt_a = nullptr;
     uint32_t *lcp = nullptr, *text = nullptr, *suff = nullptr;  // local position 0
     uint8_t* bwt = nullptr;
-    uint8_t* lcp8_a = nullptr;   // byte copy of the LCP (same padding), built at seal when every value is <= 127
-    bool lcp8_ok = false;        // K1 streams the byte copy
+    uint8_t* lcpt = nullptr;     // bit-sliced copy of the LCP (k_derive: 64-byte groups of 7 bit planes + the plane A), 1 B/position
+    bool lcpt_ok = false;        // every LCP value the scan looks at is <= 127: the one-pass scan may stream it
     bool sealed = false;
     int lay_x = 4, lay_y = 4, lay_z = 4, lay_bcr = 0;  // layout of the index files (phantom record only)
     // record list
@@ -98,7 +98,6 @@ struct e2s_shard {
     uint64_t pf_cap = 0, pf_count = 0;
     bool pf_ok = false;              // the list is complete (no overflow) and belongs to the current record list
     uint4* d_planes = nullptr;       // resident base-code bit planes of the BWT (planes.cuh), written by the loads
-    uint64_t* d_chg = nullptr;       // ... and the change plane: bit x = base code of x differs from that of x - 1
     uint32_t* d_seal_flag = nullptr; // != 0: an LCP value above 127 (set at seal)
     int variant = 0;
     // chunked mode (streaming): the device buffers hold one chunk [global_off, global_off + n_local) of the shard's range at a time
@@ -314,19 +313,17 @@ static int shard_create_impl(e2s_ctx* c, uint64_t n_local, uint64_t global_off, 
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_hist), (E2S_HIST_BINS + 1) * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_seal_flag), 4);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_planes), plane_quads(s->alloc_r) * sizeof(uint4));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_chg), (plane_quads(s->alloc_r) + 1) * 8);
     if (e != cudaSuccess) {
         e2s_shard_destroy(s);
         return fail(c, E2S_ERR_NOMEM, std::string("shard allocation: ") + cudaGetErrorString(e));
     }
-    // the byte copy of the LCP the one-pass scan streams (1 B/position); without room for it the shard stays on the 4-byte stream
-    if (cudaMalloc(reinterpret_cast<void**>(&s->lcp8_a), ne) != cudaSuccess) {
+    // the bit-sliced copy of the LCP the one-pass scan streams (1 B/position); without room for it the shard stays on the 4-byte stream
+    if (cudaMalloc(reinterpret_cast<void**>(&s->lcpt), lcpt_bytes(s->alloc_r)) != cudaSuccess) {
         cudaGetLastError();
-        s->lcp8_a = nullptr;
+        s->lcpt = nullptr;
     }
-    if (s->lcp8_a) CU(c, cudaMemsetAsync(s->lcp8_a, 0, ne, c->stream));
+    if (s->lcpt) CU(c, cudaMemsetAsync(s->lcpt, 0, lcpt_bytes(s->alloc_r), c->stream));
     CU(c, cudaMemsetAsync(s->d_planes, 0, plane_quads(s->alloc_r) * sizeof(uint4), c->stream));  // pads: code 0
-    CU(c, cudaMemsetAsync(s->d_chg, 0, (plane_quads(s->alloc_r) + 1) * 8, c->stream));
     CU(c, cudaMemsetAsync(s->d_seal_flag, 0, 4, c->stream));
     s->lcp = s->lcp_a + PAD_L;
     s->text = s->text_a + PAD_L;
@@ -403,9 +400,8 @@ int e2s_chunk_begin(e2s_shard* s, uint64_t chunk_lo, uint64_t chunk_n) {
         CU(c, cudaMemsetAsync(s->text_a, 0, PAD_L * 4, c->stream));
         CU(c, cudaMemsetAsync(s->suff_a, 0, PAD_L * 4, c->stream));
         CU(c, cudaMemsetAsync(s->bwt_a, 0, PAD_L, c->stream));
-        if (s->lcp8_a) CU(c, cudaMemsetAsync(s->lcp8_a, 0, PAD_L, c->stream));
+        if (s->lcpt) CU(c, cudaMemsetAsync(s->lcpt, 0, LCPT_BLOCK, c->stream));
         CU(c, cudaMemsetAsync(s->d_planes, 0, (PL_PAD / 64) * sizeof(uint4), c->stream));
-        CU(c, cudaMemsetAsync(s->d_chg, 0, (PL_PAD / 64) * 8, c->stream));
     }
     return E2S_OK;
 }
@@ -418,7 +414,7 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->text_a);
     cudaFree(s->suff_a);
     cudaFree(s->bwt_a);
-    cudaFree(s->lcp8_a);
+    cudaFree(s->lcpt);
     cudaFree(s->d_start);
     cudaFree(s->d_len);
     cudaFree(s->d_desc);
@@ -442,7 +438,6 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->d_hist);
     cudaFree(s->d_seal_flag);
     cudaFree(s->d_planes);
-    cudaFree(s->d_chg);
     cudaFree(s->d_pf_list);
     snp_work_destroy(s->work);
     if (s->ctx->cached == s) s->ctx->cached = nullptr;
@@ -463,8 +458,8 @@ static cudaError_t derive_loaded(e2s_shard* s, int64_t l, uint64_t cnt, bool hav
     const bool last_shard = s->global_off + s->n_local == s->n_global;
     // the scan looks at positions [-2, n_local] (on the last shard lcp[n_local] is the phantom, which only feeds END(n-1),
     // left to the host tail rule): only those decide whether the byte copy is usable
-    return launch_derive(s->lcp, have_bwt ? s->bwt : nullptr, have_lcp ? (s->lcp8_a ? s->lcp8_a + PAD_L : nullptr) : nullptr, s->d_planes,
-                         s->d_chg, l, l + int64_t(cnt), -2, int64_t(s->n_local) + (last_shard ? 0 : 1), s->d_seal_flag, s->ctx->stream,
+    return launch_derive(s->lcp, have_bwt ? s->bwt : nullptr, have_lcp ? s->lcpt : nullptr, s->d_planes,
+                         l, l + int64_t(cnt), -2, int64_t(s->n_local) + (last_shard ? 0 : 1), s->d_seal_flag, s->ctx->stream,
                          s->ctx->sm_count);
 }
 
@@ -632,19 +627,19 @@ int e2s_shard_seal(e2s_shard* s) {
     // The byte LCP and the bit planes were written by the loads themselves: sealing costs no pass over the data, only
     // the verdict whether every LCP value the scan looks at fits the byte copy (E2S_LCP_WIDE=1 keeps the 4-byte stream,
     // for A/B measurements and the tests)
-    s->lcp8_ok = false;
+    s->lcpt_ok = false;
     const char* wide = getenv("E2S_LCP_WIDE");
-    if (s->lcp8_a && !(wide && atoi(wide) != 0)) {
+    if (s->lcpt && !(wide && atoi(wide) != 0)) {
         uint32_t h_flag = 1;
         CU(c, cudaMemcpyAsync(&h_flag, s->d_seal_flag, 4, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
-        s->lcp8_ok = h_flag == 0;
+        s->lcpt_ok = h_flag == 0;
     }
     s->sealed = true;
     return E2S_OK;
 }
 
-int e2s_shard_lcp_bytes_resident(const e2s_shard* s) { return s ? (s->sealed && s->lcp8_ok ? 1 : 4) : 0; }
+int e2s_shard_lcp_bytes_resident(const e2s_shard* s) { return s ? (s->sealed && s->lcpt_ok ? 1 : 4) : 0; }
 
 int e2s_reads_stage(e2s_ctx* c, const uint8_t* bases, const uint64_t* off, uint64_t n_reads) {
     if (!c || !bases || !off) return fail(c, E2S_ERR_ARG, "e2s_reads_stage: NULL argument");
@@ -770,7 +765,7 @@ static int scan_enqueue(e2s_shard* s, uint32_t k, int32_t min_len) {
     s->variant = env ? atoi(env) : 0;
     // One pass over the byte LCP (k_cluster_scan) whenever the shard has it and min_len allows the bit-parallel length
     // test; else the two-kernel path on the 4-byte LCP (k_lcp_flags + k_cluster_emit).  E2S_SCAN_LEGACY=1 forces the latter.
-    const bool one_pass = s->last_one_pass = s->sealed && s->lcp8_ok && min_len <= 33 && !getenv("E2S_SCAN_LEGACY");
+    const bool one_pass = s->last_one_pass = s->sealed && s->lcpt_ok && min_len <= 33 && !getenv("E2S_SCAN_LEGACY");
     const uint64_t num_tiles = emit_num_tiles(s->n_local);
     if (one_pass) {
         if (!s->d_chunks) {
@@ -814,8 +809,7 @@ static int scan_enqueue(e2s_shard* s, uint32_t k, int32_t min_len) {
         fp.s_words = s->d_flags;
         fp.e_words = s->d_flags + s->flag_words;
         c->timer.begin(E2S_KERNEL_FLAGS, c->stream);
-        cudaError_t le = (s->sealed && s->lcp8_ok) ? launch_flags8(fp, s->lcp8_a + PAD_L, c->sm_count, c->stream)
-                                                   : launch_flags(fp, s->alloc_r / 32, c->sm_count, c->stream, s->variant);
+        cudaError_t le = launch_flags(fp, s->alloc_r / 32, c->sm_count, c->stream, s->variant);
         c->timer.end(c->stream);
         CU(c, le);
         ++c->launches;
@@ -866,9 +860,8 @@ static int scan_enqueue(e2s_shard* s, uint32_t k, int32_t min_len) {
     if (one_pass) {
         CU(c, cudaMemsetAsync(s->d_chunks, 0, size_t(s->n_chunks) * sizeof(ChunkRec), c->stream));
         Scan8Params sp;
-        sp.lcp8 = s->lcp8_a + PAD_L;
+        sp.lcpt = s->lcpt;
         sp.planes = s->d_planes;
-        sp.chg = s->d_chg;
         sp.n_local = s->n_local;
         sp.global_off = s->global_off;
         sp.n_global = s->n_global;
@@ -1073,7 +1066,7 @@ int e2s_chunk_scan(e2s_shard* s, uint32_t k, int32_t min_len, int mcov_out, uint
     if (mcov_out < 0 || 2 * mcov_out > E2S_MAX_C_LEN) return fail(c, E2S_ERR_ARG, "e2s_chunk_scan: need 0 <= 2 * mcov_out <= 150");
     int rc = e2s_shard_seal(s);
     if (rc) return rc;
-    if (!s->lcp8_ok || min_len > 33)
+    if (!s->lcpt_ok || min_len > 33)
         return fail(c, E2S_ERR_UNSUPPORTED,
                     "chunked shards need the one-pass scan: every LCP value <= 127 (reads shorter than 128 bases) and -m <= 33; "
                     "use a resident shard for this input");

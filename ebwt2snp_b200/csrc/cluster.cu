@@ -172,170 +172,6 @@ __global__ void __launch_bounds__(FL_THREADS) k_lcp_flags(const __grid_constant_
 }
 
 // =============================================================================================
-// K1 (narrow): the same stencil on a one-byte resident LCP
-// =============================================================================================
-// When every LCP value of the shard is <= 127 (proven at seal by k_lcp_narrow; always true for reads
-// shorter than 128 bases, and what egsa's default 1-byte LCP files hold anyway, ref:pipeline.sh:30-32)
-// the shard keeps a byte copy of the LCP and K1 streams 1 B/position instead of 4.  At that rate the
-// kernel would be bound by the integer pipes if it compared position by position, so the compares run
-// four positions per instruction on packed bytes (all bytes <= 127, so byte sums below never carry):
-//   ge(j)            bit 7 of  v_j + (128 - k)
-//   lcp[j-1]>lcp[j]  bit 7 of  (v_{j-1} | 128) - v_j - 1
-// and the four bit-7 flags of a word are gathered into the top nibble with one multiply.
-// Tiles of 16384 positions are brought to shared memory with the bulk-copy engine (cp.async.bulk),
-// FL8_STAGES tiles in flight per CTA; every thread owns 64 consecutive positions and writes two words per mask.
-constexpr int FL8_THREADS = 256;
-constexpr int FL8_V = 64;
-constexpr int FL8_T = FL8_THREADS * FL8_V;  // 16384 positions = 16 KB per tile
-constexpr int FL8_STAGES = 3;
-
-__device__ __forceinline__ uint32_t gather_b7(uint32_t x) {  // bit 7 of bytes 0..3 -> bits 28..31
-    return (x & 0x80808080u) * 0x00204081u;
-}
-
-__global__ void __launch_bounds__(FL8_THREADS) k_lcp_flags8(FlagParams p, const uint8_t* __restrict__ lcp8) {
-    constexpr int V = FL8_V, T = FL8_T, W = V / 4;
-    extern __shared__ __align__(128) uint8_t smem8[];
-    __shared__ uint64_t full_bar[FL8_STAGES];
-
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t kk = p.k > 128u ? 128u : p.k;      // bytes are <= 127: k >= 128 never matches
-    const uint32_t kadd = (128u - kk) * 0x01010101u;
-
-    if (tid == 0) {
-        for (int s = 0; s < FL8_STAGES; ++s) mbar_init(&full_bar[s], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    const uint32_t num_tiles = p.num_tiles;
-    if (tid == 0) {
-        for (int s = 0; s < FL8_STAGES; ++s) {
-            uint64_t t = uint64_t(blockIdx.x) + uint64_t(s) * gridDim.x;
-            if (t < num_tiles) {
-                mbar_expect_tx(&full_bar[s], T);
-                bulk_g2s(smem8 + size_t(s) * T, lcp8 + t * T, T, &full_bar[s]);
-            }
-        }
-    }
-
-    uint32_t it = 0;
-    for (uint64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int stage = it % FL8_STAGES;
-        const uint32_t parity = (it / FL8_STAGES) & 1;
-        const uint64_t tile_base = t * T;
-        const uint64_t my_base = tile_base + uint64_t(tid) * V;
-        const uint8_t* tile = smem8 + size_t(stage) * T;
-        const bool interior = p.global_off + tile_base != 0 && tile_base + T <= p.n_local &&
-                              p.global_off + tile_base + T < p.n_global;  // no special case applies inside this tile
-
-        uint32_t g_prev = 0, g_next = 0;  // halo bytes outside the tile: issue the global loads early
-        if (tid == 0) g_prev = *reinterpret_cast<const uint32_t*>(lcp8 + (int64_t(tile_base) - 4));
-        if (tid == FL8_THREADS - 1) g_next = lcp8[tile_base + T];
-
-        mbar_wait(&full_bar[stage], parity);
-
-        uint32_t w[W];
-        {
-            const uint8_t* row = tile + size_t(tid) * V;
-#pragma unroll
-            for (int j = 0; j < W / 4; ++j) {
-                uint4 c = lds128(row + 16 * j);
-                w[4 * j + 0] = c.x;
-                w[4 * j + 1] = c.y;
-                w[4 * j + 2] = c.z;
-                w[4 * j + 3] = c.w;
-            }
-        }
-        uint32_t pw = __shfl_up_sync(FULL, w[W - 1], 1);   // bytes -4..-1
-        uint32_t nw = __shfl_down_sync(FULL, w[0], 1);     // bytes V..V+3
-        if (lane == 0) pw = tid == 0 ? g_prev : *reinterpret_cast<const uint32_t*>(tile + size_t(tid) * V - 4);
-        if (lane == 31) nw = tid == FL8_THREADS - 1 ? g_next : *reinterpret_cast<const uint32_t*>(tile + size_t(tid + 1) * V);
-        __syncthreads();  // every thread has its tile data in registers: the stage can be refilled
-        if (tid == 0) {
-            uint64_t tn = t + uint64_t(FL8_STAGES) * gridDim.x;
-            if (tn < num_tiles) {
-                mbar_expect_tx(&full_bar[stage], T);
-                bulk_g2s(smem8 + size_t(stage) * T, lcp8 + tn * T, T, &full_bar[stage]);
-            }
-        }
-
-        // G_j = ge(j); A_j = lcp[j-1] > lcp[j]; words are consumed last to first so that each funnel shift
-        // pushes four more flags in at the bottom and position 0 ends up in bit 0.  With p = the word of the
-        // bytes before (p = cur << 8 | prev >> 24 = 256 cur + (prev >> 24) mod 2^32) the compare word
-        // (p | 0x80808080) - cur - 0x01010101 equals 255 cur + (prev >> 24) + 0x7f7f7f7f: multiply-adds, which
-        // run on the FMA pipe beside the logic ops of the ALU pipe (the ALU pipe is what bounds this kernel).
-        uint32_t Gh[2], Ah[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint32_t G = 0, A = 0;
-#pragma unroll
-            for (int i = 7; i >= 0; --i) {
-                const int q = 8 * h + i;
-                const uint32_t cur = w[q];
-                const uint32_t carry = __umulhi(q == 0 ? pw : w[q - 1], 256u) + 0x7f7f7f7fu;  // (prev >> 24) + 0x7f7f7f7f
-                G = __funnelshift_l(gather_b7(cur + kadd), G, 4);
-                A = __funnelshift_l(gather_b7(cur * 255u + carry), A, 4);
-            }
-            Gh[h] = G;
-            Ah[h] = A;
-        }
-        const uint64_t G = (uint64_t(Gh[1]) << 32) | Gh[0];
-        const uint64_t A = (uint64_t(Ah[1]) << 32) | Ah[0];
-        const uint32_t v_m2 = (pw >> 16) & 0xffu, v_m1 = pw >> 24, v_p = nw & 0xffu, v_last = w[W - 1] >> 24;
-        const uint64_t g_m1b = v_m1 >= p.k, g_pb = v_p >= p.k;
-        const uint64_t a_V = v_last > v_p;
-        const uint64_t Gn = (G >> 1) | (g_pb << (V - 1));  // ge(j+1)
-        const uint64_t An = (A >> 1) | (a_V << (V - 1));   // lcp[j] > lcp[j+1]
-        uint64_t E = G & ((A & ~An) | ~Gn);
-        uint64_t e_prev = g_m1b & ((uint64_t(v_m2 > v_m1) & ((~A) & 1u)) | ((~G) & 1u));
-        uint64_t vm = ~uint64_t(0);
-        if (!interior) {  // first tile of the eBWT, the tile holding position n_global - 1, tiles reaching past n_local
-            const uint64_t gpos = p.global_off + my_base;
-            if (gpos == 0) {  // the init special cases of ref:ebwt2clust.cpp:83-86
-                E &= ~uint64_t(1);
-                e_prev = 0;
-                if ((G & 1u) && !(G & 2u)) E |= 2u;
-            }
-            const int64_t nvalid = int64_t(p.n_local) - int64_t(my_base);
-            vm = nvalid >= V ? ~uint64_t(0) : (nvalid <= 0 ? 0 : ((uint64_t(1) << nvalid) - 1));
-            const int64_t last = int64_t(p.n_global) - 1 - int64_t(gpos);  // END(n_global-1): host tail rule
-            if (last >= 0 && last < V) E &= ~(uint64_t(1) << last);
-            E &= vm;
-        }
-        const uint64_t Gp = (G << 1) | g_m1b;
-        const uint64_t Ep = (E << 1) | e_prev;
-        const uint64_t S = G & (~Gp | Ep) & vm;
-
-        const uint64_t w2 = t * FL8_THREADS + tid;  // index in units of two mask words
-        reinterpret_cast<uint2*>(p.s_words)[w2] = make_uint2(uint32_t(S), uint32_t(S >> 32));
-        reinterpret_cast<uint2*>(p.e_words)[w2] = make_uint2(uint32_t(E), uint32_t(E >> 32));
-    }
-}
-
-cudaError_t launch_flags8(const FlagParams& p0, const uint8_t* lcp8, int sm_count, cudaStream_t stream) {
-    FlagParams p = p0;
-    p.num_tiles = uint32_t((p.n_local + FL8_T - 1) / FL8_T);
-    const size_t smem = size_t(FL8_STAGES) * FL8_T;
-    static int occ_dev[64] = {0};  // function attributes are per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    int& occ = occ_dev[dev & 63];
-    if (!occ) {
-        cudaError_t e = cudaFuncSetAttribute(k_lcp_flags8, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_lcp_flags8, FL8_THREADS, smem);
-        if (e != cudaSuccess) return e;
-        if (o < 1) return cudaErrorLaunchOutOfResources;
-        occ = o;
-    }
-    uint64_t grid = uint64_t(sm_count) * occ;
-    if (grid > p.num_tiles) grid = p.num_tiles;
-    k_lcp_flags8<<<dim3(unsigned(grid)), dim3(FL8_THREADS), smem, stream>>>(p, lcp8);
-    return cudaGetLastError();
-}
-
-// =============================================================================================
 // K2: chunked reduce-then-scan over the bit masks + compaction
 // =============================================================================================
 // START and END bits alternate (S <= E < S' <= E' ...): every END closes the cluster opened by the nearest

@@ -116,8 +116,10 @@ struct EmitParams {  // K2
     const uint8_t* tail_bwt;   // &bwt[n_global-1]
 };
 
-// k_cluster_scan (scan.cu): K1 + K2 in one pass over the one-byte LCP, one CTA per chunk of consecutive tiles
+// k_cluster_scan (scan.cu): K1 + K2 in one pass over the bit-sliced LCP, one CTA per chunk of consecutive tiles
 constexpr uint32_t SCAN_MAX_CHUNKS = 1024;
+constexpr int LCPT_BLOCK = 2048;  // positions (= bytes) per block of the bit-sliced LCP; one block of padding before local position 0
+inline size_t lcpt_bytes(uint64_t alloc_r) { return size_t(alloc_r) + 2 * LCPT_BLOCK; }  // ... and one after the last tile
 struct ChunkRec {  // what a chunk leaves behind (zeroed before the launch)
     unsigned long long own_count;   // records in the chunk's segment (all ENDs with a START inside the chunk, minus the short ones)
     unsigned long long head_end;    // 1 + global position of the chunk's first event if that is an END, 0 = none
@@ -134,9 +136,9 @@ struct ChunkSeg {  // written by k_chunk_resolve: where the chunk's records go i
     uint32_t head_len, head_kept;
 };
 struct Scan8Params {
-    const uint8_t* lcp8;        // local position 0 of the byte LCP (PAD_L readable bytes before it)
-    const uint4* planes;        // resident base-code bit planes (second level of the fused prefilter)
-    const uint64_t* chg;        // resident base-code CHANGE plane (fused prefilter): bit of position x = word (x + PL_PAD) >> 6, bit x & 63
+    const uint8_t* lcpt;        // the bit-sliced LCP (k_derive): blocks of LCPT_BLOCK positions = 8 runs (planes 0..6, A) of 32 words;
+                                // byte 0 = block of the local positions -LCPT_BLOCK .. -1, lcpt_bytes(alloc_r) bytes in all
+    const uint4* planes;        // resident base-code bit planes (fused prefilter)
     uint64_t n_local, global_off, n_global;
     uint32_t k;
     int32_t min_len;            // <= 33
@@ -180,8 +182,6 @@ uint64_t emit_num_tiles(uint64_t n_local);
 uint64_t emit_desc_words();
 cudaError_t launch_flags(const FlagParams& p, uint64_t rows_alloc32, int sm_count, cudaStream_t stream, int variant);
 cudaError_t launch_emit(const EmitParams& p, int sm_count, cudaStream_t stream);
-// K1 on the byte LCP written by the loads (p.lcp unused)
-cudaError_t launch_flags8(const FlagParams& p, const uint8_t* lcp8, int sm_count, cudaStream_t stream);
 // small helpers: append up to 3 records to the device list / pack the list into 10-byte file records
 cudaError_t launch_put_records(uint64_t* d_start, uint16_t* d_len, uint64_t at, const uint64_t* st, const uint64_t* ln,
                                int n, cudaStream_t stream);
@@ -195,7 +195,7 @@ cudaError_t launch_unpack_gesa(const uint8_t* d_rec, uint64_t count, int x, int 
                                uint32_t* suff, uint8_t* bwt, cudaStream_t stream);
 // narrow resident copies of the local positions [a, b) just loaded (byte LCP + base-code bit planes); *flag |= 1 when an
 // LCP value in [chk_lo, chk_hi) does not fit the byte copy
-cudaError_t launch_derive(const uint32_t* lcp, const uint8_t* bwt, uint8_t* lcp8, uint4* planes, uint64_t* chg, int64_t a, int64_t b,
+cudaError_t launch_derive(const uint32_t* lcp, const uint8_t* bwt, uint8_t* lcpt, uint4* planes, int64_t a, int64_t b,
                           int64_t chk_lo, int64_t chk_hi, uint32_t* flag, cudaStream_t stream, int sm_count);
 cudaError_t launch_fill_phantom(uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt, uint64_t n_local,
                                 uint64_t count, int x, int y, int z, int bcr, cudaStream_t stream);

@@ -1,35 +1,43 @@
-// Phase 1 (ebwt2clust) in ONE pass over the resident one-byte LCP: k_cluster_scan.
+// Phase 1 (ebwt2clust) in ONE pass over the resident bit-sliced LCP: k_cluster_scan.
 //
-// cluster_lm / append_entry (ref:ebwt2clust.cpp:54-139) in their stencil form (cluster.cu): the
-// kernel reads every LCP byte once, keeps the START / END bit masks of a tile in REGISTERS (they are never written to
-// memory), and goes straight on to the records:
+// cluster_lm / append_entry (ref:ebwt2clust.cpp:54-139) in their stencil form (cluster.cu).  The
+// kernel reads one byte per position once, keeps the START / END bit masks in REGISTERS (they are never written to
+// global memory), and goes straight on to the records.
 //
-//   tiles     16 384 positions; persistent CTAs take tile numbers from a ticket (so every tile with a smaller number is
-//             owned by a CTA that is already running) and keep SC_STAGES tiles in flight each: the LCP bytes come in as
-//             one TMA tensor box (128-byte rows, hardware 128B swizzle => each thread's four 16-byte reads of its 64
-//             bytes are bank-conflict free), the tile's window of the base-code bit planes (fused prefilter) as one
-//             bulk copy, both signalling the same mbarrier.
-//   masks     packed byte compares, four positions per instruction (k_lcp_flags8's arithmetic); each thread owns 64
-//             consecutive positions = one 64-bit word per mask.
-//   ranks     START and END bits alternate, so the START that pairs with the tile's q-th END is the START that has
-//             exactly q ENDs before it: ONE block scan of the per-thread END counts ranks both; every START writes its
-//             position to list slot [ENDs before it], every END writes (position, kept rank) to slot [its rank].
-//   min_len   ENDs of clusters shorter than min_len are a bit-parallel function of the masks (a START at most
-//             min_len - 2 positions before, min_len <= 33).  The only END whose START is not in its tile is the tile's
-//             first event ("carried" END): that one is tested exactly, wrapped 16-bit length included, against the
-//             carried-in START -- a tile is shorter than 65 503 positions, so no other END can wrap.
-//   look-back two 64-bit words per tile, each validated by an epoch (no memset between launches):
-//               A = state after the tile (closed / open at position p / nothing happened): local, published at once;
-//                   a tile without events re-publishes the resolved state once it knows it
-//               B = kept-record count: aggregate (after the carried END has been tested against A of the tiles before),
-//                   then inclusive prefix -- the classic decoupled look-back, 32 predecessors per poll.
-//   records   one lane per END of the tile: START from the list (or the carried-in START), length mod 2^16, stores
-//             (start u64, len u16) in position order, length histogram + n_bases of statistics()
-//             (ref:clust2snp.cpp:899-907), and -- fused mode -- the one-popcount bound of the BWT prefilter
-//             (planes.cuh) on the plane window in shared memory; survivors are appended to the list K3x reads.
+//   input     the LCP as the loads left it for this kernel (k_derive, unpack.cu): bit-sliced, plane-major in blocks of
+//             2048 positions -- block b = eight runs of 32 words, run p = bit plane p of the LCP value (<= 127) for
+//             p < 7 and the plane A (bit x = lcp[x-1] > lcp[x]) for p = 7, word g of a run = the 64 positions
+//             2048 b + 64 g ...  Nothing in it depends on an option of either tool.  "lcp >= k" is then a bit-sliced
+//             comparator: one LOP3 per plane word ((k_b ? ~x | lt : ~x & lt) as a single 3-input function), 14 logic
+//             instructions for 64 positions instead of the 64+ of a byte-wise compare; the local-minimum test of the
+//             stencil is A & ~(A >> 1).  A warp reads a run with one conflict-free 8-byte load per lane at a constant
+//             offset from its base: no address arithmetic.
+//   tiles     16 384 positions = 8 blocks = one per warp.  One CTA per CHUNK of consecutive tiles, no communication
+//             between CTAs; SC_STAGES tiles in flight per CTA: one bulk copy of the tile's 16 KB, two 128-byte tensor
+//             boxes with the plane words of the group before and of the group after the tile, and (fused prefilter) one
+//             bulk copy of the tile's window of the base-code bit planes, all signalling the same mbarrier.
+//   masks     each thread owns 64 consecutive positions = one 64-bit word per mask (G, A -> END, START); the G / A bits of
+//             the position before and after them come from the neighbouring words of the same runs.
+//   ranks     kept ENDs (K = E minus the ENDs of clusters shorter than min_len, a bit-parallel function of the masks: a
+//             START at most min_len - 2 positions before, min_len <= 33) are ranked by ONE block scan; each thread
+//             scatters the tile-local positions of its kept ENDs to a shared list -- nothing else happens at lane
+//             efficiency popcount / max popcount.
+//   records   one lane per list entry (dense): nearest START at or before the END from the tile's START words in shared
+//             memory (own word, else the per-warp ballots of non-empty words point at the word), length mod 2^16, stores
+//             (start u64, len u16) in position order into the chunk's segment, length histogram + n_bases of
+//             statistics() (ref:clust2snp.cpp:899-907), and -- fused mode -- the BWT prefilter of find_variants
+//             (ref:clust2snp.cpp:402-429) as the one-popcount bound of planes.cuh on the plane window; the survivors are
+//             appended to the list K3x reads.
+//   state     the open-cluster state and the record count are carried from tile to tile by warp 0.  What a chunk cannot
+//             know -- whether a cluster is open when it starts -- only matters for its first event: if that is an END
+//             ("head" of the chunk) the record is left to k_chunk_resolve, which sees all chunks' summaries.  The only
+//             END of a tile whose START is not in the tile is its first event ("carried" END): warp 0 tests it exactly,
+//             wrapped 16-bit length included (a tile is shorter than 65 503 positions, so no other END can wrap).
+//   barriers  two per tile: (A) after the masks, (B) after the scatter; the START words are double buffered by tile parity.
 //
-// Algorithmic bytes: 1 B/position read + 10 B per written record (+ 0.25 B/position of bit planes in fused mode).
-// Not handled here (callers fall back to k_lcp_flags + k_cluster_emit): min_len > 33, shards whose LCP does not fit a byte.
+// Algorithmic bytes: 1 B/position read + 10 B per written record (+ 0.25 B per position inside analysed clusters of
+// base-code planes in fused mode).
+// Not handled here (callers fall back to k_lcp_flags + k_cluster_emit): min_len > 33, shards with an LCP value > 127.
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -46,105 +54,150 @@ namespace {
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int SC_THREADS = 256;
 constexpr int SC_WARPS = SC_THREADS / 32;
-constexpr int SC_V = 64;                       // positions per thread
-constexpr int SC_T = SC_THREADS * SC_V;        // 16384 positions per tile
-constexpr int SC_W = SC_V / 4;                 // 16 packed words per thread
-constexpr int SC_STAGES = 2;                   // LCP tiles in flight / being read per CTA (a stage is free once its bytes are in registers)
+constexpr int SC_V = 64;                       // positions per thread = one word per plane
+constexpr int SC_T = SC_THREADS * SC_V;        // 16384 positions per tile = SC_WARPS blocks of LCPT_BLOCK positions
+constexpr int SC_EDGE = 128;                   // bytes of an edge box: 8 plane runs x 2 words
+constexpr int SC_STAGE_BYTES = SC_T + 2 * SC_EDGE;  // the tile, the box before it, the box after it
+constexpr int SC_STAGES = 2;                   // LCP tiles in flight / being read per CTA (a stage is free once its words are in registers)
 constexpr int SC_OCC = 4;                      // resident CTAs per SM the register / shared-memory budget is sized for
 constexpr int SC_PSLOTS = SC_STAGES + 1;       // plane windows: a window is read until its tile's records are written, after the stage was refilled
 constexpr int SC_PF_QUADS = SC_T / 64 + PL_PAD / 64;  // plane quads of one tile and of the PL_PAD positions before it
 constexpr int SC_PF_BYTES = SC_PF_QUADS * 16;  // 4144
 constexpr int SC_PF_STRIDE = 4224;             // slot stride (128-byte multiple)
-constexpr int SC_DYN_SMEM = SC_STAGES * SC_T + SC_PSLOTS * SC_PF_STRIDE + 1024;  // + slack for the 1024-byte alignment of the TMA boxes
+constexpr int SC_DYN_SMEM = SC_STAGES * SC_STAGE_BYTES + SC_PSLOTS * SC_PF_STRIDE;
 constexpr int SC_CAP = 512;                    // kept ENDs per list window (a typical tile lists ~300)
+static_assert(LCPT_BLOCK == 32 * SC_V && SC_T == SC_WARPS * LCPT_BLOCK, "one block of the bit-sliced LCP per warp");
+static_assert(SC_T <= (1 << 14), "tile-local positions fit 14 bits");
 
 // open-cluster state (as in cluster.cu)
 constexpr uint64_t OPEN_NONE = 0, OPEN_UNKNOWN = 1, OPEN_BIAS = 2;
+constexpr int NO_POS = 0x7fffffff;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_u8(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+struct ScanShared {
+    uint64_t full_bar[SC_STAGES];
+    uint64_t x_in;                // open-cluster state entering the tile            (warp 0, between the barriers (A) and (B))
+    uint64_t prefix;              // segment index of the tile's first record
+    uint32_t adj;                 // bit 0: the carried END is not written by this tile; bit 1: it is the chunk's head
+    uint32_t carried;             // the tile's first event is an END
+    uint32_t open_after;          // (interior tiles) a cluster is open after the tile's last position
+    uint32_t wsum[SC_WARPS];      // per warp: #kept ENDs | #ENDs << 16
+    uint32_t bS[2][SC_WARPS];     // per warp: lanes whose START word is not empty (by tile parity, like sS)
+    int wfe[SC_WARPS];            // first END of the warp (tile-local position), NO_POS = none
+    int wle[SC_WARPS];            // last END of the warp, -1 = none (tiles at the edges of the shard only)
+    unsigned int hist[E2S_HIST_BINS];
+    uint64_t sS[2][SC_THREADS];   // START words of the tile, by tile parity: read until the tile's records are out
+    uint16_t e_ent[SC_CAP];       // tile-local positions of the kept ENDs, by rank
+};
+
+__device__ __forceinline__ void tma_load_2d_u8(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
-__device__ __forceinline__ uint32_t gather_b7(uint32_t x) {  // bit 7 of bytes 0..3 -> bits 28..31
-    return (x & 0x80808080u) * 0x00204081u;
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// loads from the stages by 32-bit shared-window address (volatile: the data is written by the copy engine between two
+// visits of the same address)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
     return (uint64_t(__shfl_sync(FULL, uint32_t(v >> 32), src)) << 32) | __shfl_sync(FULL, uint32_t(v), src);
 }
-__device__ __forceinline__ uint64_t below(int b) { return (uint64_t(1) << b) - 1; }  // bits [0, b), b < 64
-
-struct ScanShared {
-    uint64_t full_bar[SC_STAGES];
-    // per warp, double buffered by tile parity (a tile without ENDs has no barrier (B)):
-    uint32_t wsum[2][SC_WARPS];   // #kept ENDs | #ENDs << 16
-    int wls[2][SC_WARPS], wlc[2][SC_WARPS];  // last START / last base-code change of the warp (tile-local position), -1 = none
-    int wle[2][SC_WARPS];                    // last END of the warp
-    int wfs[2][SC_WARPS], wfe[2][SC_WARPS];  // first START / END of the warp, NO_POS = none
-    uint64_t wS[SC_WARPS];        // START word of the warp's last thread (min_len >= 3 only)
-    // per tile, written by warp 0 between the barriers (A) and (B):
-    uint64_t x_in;                // open-cluster state entering the tile
-    uint64_t c_in;                // 1 + global position of the last base-code change before the tile (0: none in this chunk so far)
-    uint64_t prefix;              // segment index of the tile's first record
-    uint32_t adj;                 // 1: the carried END is not written by this tile
-    uint32_t carried;             // the tile's first event is an END
-    unsigned int hist[E2S_HIST_BINS];
-    uint64_t smask[SC_THREADS];   // START words of the tile (only in the tile that holds position n_global - 2)
-    uint32_t n2[2];               // entries of list2 (by tile parity: the other one is reset while this one is in use)
-    uint32_t list2[SC_CAP];       // records of the window with a base-code change inside: (start - tile start + PL_PAD) | len << 16 (counted after the records are out)
-    uint32_t e_ent[SC_CAP];       // [r] = kept END: position | len << 14 | survivor << 30, or position | change-seen << 30 | 1 << 31 (START before its warp)
-};
-
-constexpr int NO_POS = 0x7fffffff;
+// one step of the bit-sliced "value < k" from the least significant plane up: lt' = k_b ? (~x | lt) : (~x & lt), with
+// km = all ones / zero for k_b -- one 3-input logic function (a = x, b = km, c = lt: table 0x8E)
+__device__ __forceinline__ uint32_t lt_step(uint32_t x, uint32_t km, uint32_t lt) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x8E;" : "=r"(r) : "r"(x), "r"(km), "r"(lt));
+    return r;
+}
+// nearest set bit at or before tile-local position e of a 16 384-bit mask kept as one word per thread (words) plus, per
+// warp, the ballot of the lanes whose word is not empty (bal) and the warps that have any (any8); -1 = none
+__device__ __forceinline__ int find_prev(const uint64_t* words, const uint32_t* bal, uint32_t any8, uint32_t e) {
+    uint32_t t = e >> 6;
+    uint64_t m = words[t] & (~uint64_t(0) >> (63u - (e & 63u)));
+    if (!m) {
+        uint32_t w = t >> 5;
+        uint32_t bm = bal[w] & ((1u << (t & 31u)) - 1u);
+        if (!bm) {
+            const uint32_t a8 = any8 & ((1u << w) - 1u);
+            if (!a8) return -1;
+            w = 31u - uint32_t(__clz(a8));
+            bm = bal[w];
+        }
+        t = w * 32u + 31u - uint32_t(__clz(bm));
+        m = words[t];
+    }
+    return int(t * 64u) + 63 - __clzll(m);
+}
 
 }  // namespace
 
-// One CTA per CHUNK of consecutive tiles, no communication between CTAs: the open-cluster state and the record count are
-// carried from tile to tile by warp 0, the records go to the chunk's own segment of the record arrays.  What a chunk
-// cannot know -- whether a cluster is open when it starts -- only matters for its first event: if that is an END ("head"
-// of the chunk) the record is left to k_chunk_resolve, which sees all chunks' summaries.
-//
-// Per tile: masks (S, E) and the change word C of my 64 positions; kept ENDs K = E minus the ENDs of clusters shorter than
-// min_len (bit-parallel: a START at most min_len - 2 positions before); one block scan ranks the kept ENDs.  A cluster is
-// [nearest START at or before its END, END]: each END finds that START in its own thread's word or, by one ballot + one
-// shuffle, in an earlier lane of its warp -- and the last base-code change before the END the same way; only ENDs whose
-// START lies before their warp (about one per warp) are resolved when the records are written, from the per-warp
-// summaries.  BWT prefilter (fused mode): a cluster without a base-code change inside it has ONE base code and can never
-// pass find_variants (ref:clust2snp.cpp:402-429: both samples' frequent sets would be that one letter): it is dropped
-// here for the price of a compare; the others go to the list K3x tests exactly.
 __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __grid_constant__ CUtensorMap tmap, Scan8Params p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* plane_slots = stages + size_t(SC_STAGES) * SC_T;  // SC_PSLOTS windows of SC_PF_STRIDE bytes
+    extern __shared__ __align__(128) uint8_t smem_dyn[];  // SC_STAGES stages, then SC_PSLOTS plane windows
     __shared__ ScanShared sh;
+    const uint32_t stage0 = smem_u32(smem_dyn);
+    const uint32_t planes0 = stage0 + SC_STAGES * SC_STAGE_BYTES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const bool pf = p.pf_mcov != 0;
     const int spread = p.min_len >= 2 ? p.min_len - 2 : -1;  // extra positions a START shadows; -1: nothing is dropped
-    const uint32_t kk = p.k > 128u ? 128u : p.k;             // bytes are <= 127: k >= 128 never matches
-    const uint32_t kadd = (128u - kk) * 0x01010101u;
+    const uint32_t kk = p.k > 128u ? 128u : p.k;             // values are <= 127: k >= 128 never matches
+    uint32_t km[7];
+#pragma unroll
+    for (int b = 0; b < 7; ++b) km[b] = ((kk >> b) & 1u) ? FULL : 0u;
+    const uint32_t k_none = kk >= 128u ? FULL : 0u;          // "every value is below k"
     const uint32_t c = blockIdx.x;
     const uint32_t t_lo = c * p.tiles_per_chunk < p.num_tiles ? c * p.tiles_per_chunk : p.num_tiles;
     const uint32_t t_hi = t_lo + p.tiles_per_chunk < p.num_tiles ? t_lo + p.tiles_per_chunk : p.num_tiles;
     const uint32_t n_my = t_hi - t_lo;
     const uint64_t seg_base = uint64_t(c) * p.seg_cap;
+    const uint32_t seg_room = uint32_t(p.seg_cap < 0xffffffffull ? p.seg_cap : 0xffffffffull);
+    // tiles [t_int_lo, t_int_hi) need none of the edge rules: not the first tile of the eBWT, wholly inside n_local, not
+    // the tile that holds position n_global - 1
+    const uint32_t t_int_lo = p.global_off == 0 ? 1u : 0u;
+    const uint32_t t_int_hi = p.global_off + p.n_local == p.n_global ? (p.num_tiles ? p.num_tiles - 1 : 0) : uint32_t(p.n_local / SC_T);
+
+    // where my words are in a stage: run p of my warp's block at own + 256 p; the word before it in the same run (the last
+    // word of the previous block for lane 0, the edge box for thread 0: 8 rows of {word 30, word 31}) and the word after it
+    const uint32_t own = uint32_t(warp) * LCPT_BLOCK + uint32_t(lane) * 8u;
+    const uint32_t prev_off = tid == 0 ? uint32_t(SC_T) + 12u : own + (lane ? 0u - 8u : 0u - 1800u) + 4u;  // high half: bit 63
+    const uint32_t prev_str = tid == 0 ? 16u : 256u;
+    const uint32_t next_off = tid == SC_THREADS - 1 ? uint32_t(SC_T + SC_EDGE) : own + (lane < 31 ? 8u : 1800u);  // low half: bit 0
+    const uint32_t next_str = tid == SC_THREADS - 1 ? 16u : 256u;
 
     for (int i = tid; i < E2S_HIST_BINS; i += SC_THREADS) sh.hist[i] = 0;
     auto issue = [&](uint32_t it) {  // thread 0: the it-th tile of the chunk -> stage it % SC_STAGES
         if (it >= n_my) return;
         const int stage = int(it % SC_STAGES);
-        mbar_expect_tx(&sh.full_bar[stage], SC_T + (pf ? SC_PF_BYTES : 0));
-        tma_load_2d_u8(stages + size_t(stage) * SC_T, &tmap, 0, int((t_lo + it) * (SC_T / 128)), &sh.full_bar[stage]);
-        if (pf) bulk_g2s(plane_slots + size_t(it % SC_PSLOTS) * SC_PF_STRIDE, p.planes + uint64_t(t_lo + it) * (SC_T / 64), SC_PF_BYTES, &sh.full_bar[stage]);
+        const uint32_t dst = stage0 + uint32_t(stage) * SC_STAGE_BYTES;
+        const uint32_t t = t_lo + it;
+        mbar_expect_tx(&sh.full_bar[stage], SC_STAGE_BYTES + (pf ? SC_PF_BYTES : 0));
+        // (block 0 of the array = the LCPT_BLOCK positions before local position 0: tile t = blocks 8 t + 1 .. 8 t + 8)
+        bulk_g2s_a(dst, p.lcpt + (uint64_t(t) * SC_WARPS + 1) * LCPT_BLOCK, SC_T, &sh.full_bar[stage]);
+        // the tensor: rows of 256 bytes = one run; words 30, 31 of the 8 runs of the block before, words 0, 1 of the block after
+        tma_load_2d_u8(dst + SC_T, &tmap, 240, int(t * SC_WARPS * 8), &sh.full_bar[stage]);
+        tma_load_2d_u8(dst + SC_T + SC_EDGE, &tmap, 0, int((t * SC_WARPS + SC_WARPS + 1) * 8), &sh.full_bar[stage]);
+        if (pf) bulk_g2s_a(planes0 + (it % SC_PSLOTS) * SC_PF_STRIDE, p.planes + uint64_t(t) * (SC_T / 64), SC_PF_BYTES, &sh.full_bar[stage]);
     };
     if (tid == 0) {
-        sh.n2[0] = sh.n2[1] = 0;
         for (int s = 0; s < SC_STAGES; ++s) mbar_init(&sh.full_bar[s], 1);
         fence_mbar_init();
         for (uint32_t s = 0; s < uint32_t(SC_STAGES); ++s) issue(s);
@@ -153,13 +206,12 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
 
     // chunk state (warp 0; identical in its lanes)
     uint64_t X = OPEN_UNKNOWN;   // open-cluster state; unknown until the chunk's first event
-    uint64_t c_last = 0;         // 1 + global position of the chunk's last base-code change so far
-    uint64_t cnt = 0;            // records written to the segment so far
+    uint32_t cnt = 0;            // records written to the segment so far (a segment holds fewer than 2^32)
     uint64_t n_end = 0;          // ENDs seen (head included)
     uint64_t head_end = 0;       // 1 + global position of the chunk's head END, 0 = none
     bool seen = false;           // the chunk has had an event
     unsigned long long acc_bases = 0;  // (per thread) sum of the lengths I wrote
-    uint64_t my_last_o = ~0ull;        // (per thread) segment index and length of the last record I wrote
+    uint32_t my_last_o = 0xffffffffu;  // (per thread) segment-relative index and length of the last record I wrote
     uint32_t my_last_len = 0;
 
     for (uint32_t it = 0; it < n_my; ++it) {
@@ -169,67 +221,42 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         const uint32_t t = t_lo + it;
         const uint64_t tile_base = uint64_t(t) * SC_T;
         const uint64_t tile_gbase = p.global_off + tile_base;
-        const uint8_t* tile = stages + size_t(stage) * SC_T;
-        const uint4* pf_win = reinterpret_cast<const uint4*>(plane_slots + size_t(it % SC_PSLOTS) * SC_PF_STRIDE);
-        const bool interior = tile_gbase != 0 && tile_base + SC_T <= p.n_local && tile_gbase + SC_T < p.n_global;
-
-        // issued before waiting for the tile: the bytes around it and my word of the change plane
-        uint32_t g_prev = 0, g_next = 0;
-        if (tid == 0) g_prev = *reinterpret_cast<const uint32_t*>(p.lcp8 + (int64_t(tile_base) - 4));
-        if (tid == SC_THREADS - 1) g_next = p.lcp8[tile_base + SC_T];
-        uint64_t C = pf ? __ldg(p.chg + ((tile_base + uint64_t(tid) * SC_V + PL_PAD) >> 6)) : 0;
+        const uint32_t sa = stage0 + uint32_t(stage) * SC_STAGE_BYTES;
+        const uint32_t pf_win = planes0 + (it % SC_PSLOTS) * SC_PF_STRIDE;
+        const bool interior = t >= t_int_lo && t < t_int_hi;
 
         mbar_wait(&sh.full_bar[stage], parity);
 
-        // ---- my 64 bytes: row r = tid / 2 of 128 bytes, logical 16-byte chunks 4 (tid & 1) + j at physical chunk ^ (r & 7)
-        uint32_t w[SC_W], pw, nw;
+        // ---- G = (lcp >= k) and A of my 64 positions; G and A of the position before and of the position after them
+        uint64_t G, A;
+        uint32_t g_m1, a_m1, g_p, a_p;  // bit 0: position -1 / position 64 of my word
         {
-            const uint32_t r = uint32_t(tid) >> 1, c0 = (uint32_t(tid) & 1u) * 4u, x = r & 7u;
-            const uint8_t* row = tile + r * 128u;
+            uint32_t lt_lo = 0, lt_hi = 0, ltp = 0, ltn = 0;
 #pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) {
-                const uint4 v = lds128(row + (((c0 + j) ^ x) << 4));
-                w[4 * j + 0] = v.x;
-                w[4 * j + 1] = v.y;
-                w[4 * j + 2] = v.z;
-                w[4 * j + 3] = v.w;
+            for (int b = 0; b < 7; ++b) {
+                const uint2 v = lds_u64(sa + own + 256u * b);
+                lt_lo = lt_step(v.x, km[b], lt_lo);
+                lt_hi = lt_step(v.y, km[b], lt_hi);
+                ltp = lt_step(lds_u32(sa + prev_off + prev_str * b), km[b], ltp);
+                ltn = lt_step(lds_u32(sa + next_off + next_str * b), km[b], ltn);
             }
-            // the word before my bytes and the byte after them
-            if (tid == 0) pw = g_prev;
-            else if (c0) pw = *reinterpret_cast<const uint32_t*>(row + ((3u ^ x) << 4) + 12);
-            else pw = *reinterpret_cast<const uint32_t*>(row - 128 + ((7u ^ ((r - 1u) & 7u)) << 4) + 12);
-            if (tid == SC_THREADS - 1) nw = g_next;
-            else if (c0) nw = *reinterpret_cast<const uint32_t*>(row + 128 + ((0u ^ ((r + 1u) & 7u)) << 4));
-            else nw = *reinterpret_cast<const uint32_t*>(row + ((4u ^ x) << 4));
+            const uint2 av = lds_u64(sa + own + 256u * 7);
+            G = ~((uint64_t(lt_hi | k_none) << 32) | (lt_lo | k_none));
+            A = (uint64_t(av.y) << 32) | av.x;
+            g_m1 = (~(ltp | k_none)) >> 31;
+            a_m1 = lds_u32(sa + prev_off + prev_str * 7) >> 31;
+            g_p = (~(ltn | k_none)) & 1u;
+            a_p = lds_u32(sa + next_off + next_str * 7) & 1u;
         }
 
-        // ---- START / END masks of my 64 positions (k_lcp_flags8's packed compares)
+        // ---- START / END masks of my 64 positions
         uint64_t S, E;
         {
-            uint32_t Gh[2], Ah[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t G = 0, A = 0;
-#pragma unroll
-                for (int i = 7; i >= 0; --i) {
-                    const int q = 8 * h + i;
-                    const uint32_t cur = w[q];
-                    const uint32_t carry = __umulhi(q == 0 ? pw : w[q - 1], 256u) + 0x7f7f7f7fu;  // (prev >> 24) + 0x7f7f7f7f
-                    G = __funnelshift_l(gather_b7(cur + kadd), G, 4);
-                    A = __funnelshift_l(gather_b7(cur * 255u + carry), A, 4);
-                }
-                Gh[h] = G;
-                Ah[h] = A;
-            }
-            const uint64_t G = (uint64_t(Gh[1]) << 32) | Gh[0];
-            const uint64_t A = (uint64_t(Ah[1]) << 32) | Ah[0];
-            const uint32_t v_m2 = (pw >> 16) & 0xffu, v_m1 = pw >> 24, v_p = nw & 0xffu, v_last = w[SC_W - 1] >> 24;
-            const uint64_t g_m1b = v_m1 >= p.k, g_pb = v_p >= p.k;
-            const uint64_t a_V = v_last > v_p;
-            const uint64_t Gn = (G >> 1) | (g_pb << (SC_V - 1));  // ge(j+1)
-            const uint64_t An = (A >> 1) | (a_V << (SC_V - 1));   // lcp[j] > lcp[j+1]
+            const uint64_t Gn = (G >> 1) | (uint64_t(g_p) << (SC_V - 1));  // ge(j+1)
+            const uint64_t An = (A >> 1) | (uint64_t(a_p) << (SC_V - 1));  // lcp[j] > lcp[j+1]
             E = G & ((A & ~An) | ~Gn);
-            uint64_t e_prev = g_m1b & ((uint64_t(v_m2 > v_m1) & ((~A) & 1u)) | ((~G) & 1u));
+            // END of the position before mine: ge(-1) & ((A(-1) & ~A(0)) | ~ge(0))
+            uint64_t e_prev = uint64_t(g_m1 & ((a_m1 & ~uint32_t(A)) | ~uint32_t(G)) & 1u);
             uint64_t vm = ~uint64_t(0);
             if (!interior) {  // first tile of the eBWT, the tile holding position n_global - 1, tiles reaching past n_local
                 const uint64_t my_base = tile_base + uint64_t(tid) * SC_V;
@@ -244,12 +271,12 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 const int64_t last = int64_t(p.n_global) - 1 - int64_t(gpos);  // END(n_global-1): host tail rule
                 if (last >= 0 && last < SC_V) E &= ~(uint64_t(1) << last);
                 E &= vm;
-                C &= vm;
             }
-            const uint64_t Gp = (G << 1) | g_m1b;
+            const uint64_t Gp = (G << 1) | g_m1;
             const uint64_t Ep = (E << 1) | e_prev;
             S = G & (~Gp | Ep) & vm;
         }
+        sh.sS[pb][tid] = S;
 
         // ---- K = kept ENDs: E minus the ENDs of clusters shorter than min_len (a START at the same position or up to `spread`
         // positions before).  Before the tile: no START assumed -- the one END that can pair with a START of an earlier tile
@@ -257,11 +284,9 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         uint64_t K = E;
         if (spread >= 0) {
             uint64_t sm = S;
-            if (spread >= 1) {  // (kernel-uniform) the previous lane's START word; across warps through shared memory
-                if (lane == 31) sh.wS[warp] = S;
+            if (spread >= 1) {  // (kernel-uniform) the previous thread's START word
                 __syncthreads();
-                uint64_t lo = shfl64(S, (lane + 31) & 31);
-                if (lane == 0) lo = warp ? sh.wS[warp - 1] : 0;
+                uint64_t lo = tid ? sh.sS[pb][tid - 1] : 0;
                 uint64_t hi = S;
                 int width = 1;  // sm = OR of (S << d), d = 0 .. width - 1, over the 128 bits lo:hi
                 while (2 * width <= spread + 1) {
@@ -284,53 +309,72 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             const uint32_t o = __shfl_up_sync(FULL, inc, d);
             if (lane >= d) inc += o;
         }
-        const int my_ls = S ? tid * SC_V + 63 - __clzll(S) : -1;  // my last START / base-code change (tile-local)
-        const int my_lc = C ? tid * SC_V + 63 - __clzll(C) : -1;
-        int prev_s = -1, prev_c = -1;  // the nearest one in an EARLIER lane of my warp
         {
-            const uint32_t ms = __ballot_sync(FULL, S != 0) & lt_mask, mc = __ballot_sync(FULL, C != 0) & lt_mask;
-            const int vs = __shfl_sync(FULL, my_ls, ms ? 31 - __clz(ms) : lane);
-            const int vc = __shfl_sync(FULL, my_lc, mc ? 31 - __clz(mc) : lane);
-            if (ms) prev_s = vs;
-            if (mc) prev_c = vc;
-        }
-        {
-            const int ls = __reduce_max_sync(FULL, my_ls), lc = __reduce_max_sync(FULL, my_lc);
-            const int le = __reduce_max_sync(FULL, E ? tid * SC_V + 63 - __clzll(E) : -1);
-            const int fs = __reduce_min_sync(FULL, S ? tid * SC_V + __ffsll(S) - 1 : NO_POS);
-            const int fe = __reduce_min_sync(FULL, E ? tid * SC_V + __ffsll(E) - 1 : NO_POS);
-            if (lane == 31) sh.wsum[pb][warp] = inc;
+            const uint32_t bS = __ballot_sync(FULL, S != 0), bE = __ballot_sync(FULL, E != 0);
+            int fe = NO_POS;
+            if (bE) {  // (warp-uniform) the warp's first END: in the word of the first lane that has one
+                const int src = __ffs(bE) - 1;
+                const uint64_t Ef = shfl64(E, src);
+                fe = (warp * 32 + src) * SC_V + __ffsll(Ef) - 1;
+            }
+            if (lane == 31) sh.wsum[warp] = inc;
             if (lane == 0) {
-                sh.wls[pb][warp] = ls;
-                sh.wlc[pb][warp] = lc;
-                sh.wle[pb][warp] = le;
-                sh.wfs[pb][warp] = fs;
-                sh.wfe[pb][warp] = fe;
+                sh.bS[pb][warp] = bS;
+                sh.wfe[warp] = fe;
+            }
+            if (interior) {  // a cluster is open after the tile iff its last position is inside one and not its END
+                if (tid == SC_THREADS - 1) sh.open_after = uint32_t((G & ~E) >> 63);
+            } else {         // (positions past n_local, the cleared END(n_global - 1): by the tile's last START / END)
+                int le = -1;
+                if (bE) {
+                    const int src = 31 - __clz(bE);
+                    const uint64_t El = shfl64(E, src);
+                    le = (warp * 32 + src) * SC_V + 63 - __clzll(El);
+                }
+                if (lane == 0) sh.wle[warp] = le;
             }
         }
-        __syncthreads();  // (A) per-warp summaries.  Every thread has this tile's bytes in registers: the stage is refilled
-        if (tid == 0) {
-            issue(it + SC_STAGES);
-            sh.n2[pb ^ 1] = 0;  // (the previous tile's count: every thread is done with it)
-        }
+        __syncthreads();  // (A) per-warp summaries, START words.  Every thread has this tile's words in registers: the stage is refilled
+        if (tid == 0) issue(it + SC_STAGES);
 
-        uint32_t base = inc - pk, tot = 0;
-#pragma unroll
-        for (int q = 0; q < SC_WARPS; ++q) {
-            const uint32_t ws = sh.wsum[pb][q];
-            if (q < warp) base += ws;
-            tot += ws;
+        // my warp's rank offset, the tile's totals, the warps that have a START
+        uint32_t baseK, nK, nE, any8;
+        {
+            const uint32_t ws = sh.wsum[lane & (SC_WARPS - 1)], bq = sh.bS[pb][lane & (SC_WARPS - 1)];
+            const uint32_t tot = __reduce_add_sync(FULL, lane < SC_WARPS ? ws : 0u);
+            const uint32_t base = (inc - pk) + __reduce_add_sync(FULL, lane < warp ? ws : 0u);
+            any8 = __ballot_sync(FULL, bq != 0) & ((1u << SC_WARPS) - 1u);
+            nK = tot & 0xffffu;
+            nE = tot >> 16;
+            baseK = base & 0xffffu;
         }
-        const uint32_t nK = tot & 0xffffu, nE = tot >> 16;
-        const uint32_t baseK = base & 0xffffu;
+        const uint64_t* sS = sh.sS[pb];
+        const uint32_t* bSs = sh.bS[pb];
 
         // ---- warp 0: the tile's first / last events, the carried END, the chunk state
         if (warp == 0) {
-            const int q8 = lane & (SC_WARPS - 1);
-            const int t_ls = __reduce_max_sync(FULL, sh.wls[pb][q8]), t_le = __reduce_max_sync(FULL, sh.wle[pb][q8]);
-            const int t_lc = __reduce_max_sync(FULL, sh.wlc[pb][q8]);
-            const int t_fs = __reduce_min_sync(FULL, sh.wfs[pb][q8]), t_fe = __reduce_min_sync(FULL, sh.wfe[pb][q8]);
-            const bool has_event = t_ls >= 0 || t_le >= 0;
+            int t_fs = NO_POS;
+            if (any8) {
+                const uint32_t w = uint32_t(__ffs(any8) - 1);
+                const uint32_t t2 = w * 32u + uint32_t(__ffs(bSs[w]) - 1);
+                t_fs = int(t2 * 64u) + __ffsll(sS[t2]) - 1;
+            }
+            const int t_ls = find_prev(sS, bSs, any8, SC_T - 1);
+            int t_fe = NO_POS;
+#pragma unroll
+            for (int q = SC_WARPS - 1; q >= 0; --q)
+                if (sh.wfe[q] != NO_POS) t_fe = sh.wfe[q];
+            const bool has_event = t_ls >= 0 || t_fe != NO_POS;
+            bool open_after;
+            if (interior) {
+                open_after = sh.open_after != 0;
+            } else {
+                int t_le = -1;
+#pragma unroll
+                for (int q = 0; q < SC_WARPS; ++q)
+                    if (sh.wle[q] >= 0) t_le = sh.wle[q];
+                open_after = t_ls > t_le;
+            }
             // the tile's first event is an END: its START lies before the tile (a START and an END at the same position: the
             // START comes first, t_fe == t_fs is not carried)
             const bool carried = t_fe != NO_POS && t_fe < t_fs;
@@ -349,152 +393,116 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             }
             if (lane == 0) {
                 sh.x_in = X;
-                sh.c_in = c_last;
-                sh.prefix = seg_base + cnt;
+                sh.prefix = cnt;
                 sh.adj = adj | (is_head ? 2u : 0u);
                 sh.carried = carried ? 1u : 0u;
             }
             cnt += nK - adj;
             n_end += nE;
             if (has_event) {
-                X = t_ls > t_le ? tile_gbase + uint64_t(t_ls) + OPEN_BIAS : OPEN_NONE;
+                X = (open_after && t_ls >= 0) ? tile_gbase + uint64_t(t_ls) + OPEN_BIAS : (open_after ? X : OPEN_NONE);
                 seen = true;
             }
-            if (t_lc >= 0) c_last = tile_gbase + uint64_t(t_lc) + 1;
         }
 
-        // ---- the tile that holds position n_global - 2 (one per eBWT): an END there decides the reference's post-EOF phantom
-        // value whether its record is kept or not -- its START, by a backward search in the tile's START words
-        if (!interior && p.n_global - 2 - tile_gbase < uint64_t(SC_T)) {
-            sh.smask[tid] = S;
-            __syncthreads();
-            const uint32_t e_loc = uint32_t(p.n_global - 2 - tile_gbase);
-            if (uint32_t(tid) == (e_loc >> 6) && ((E >> (e_loc & 63)) & 1u)) {
-                int wi = tid;
-                uint64_t m = S & ((uint64_t(2) << (e_loc & 63)) - 1);
-                while (!m && wi > 0) m = sh.smask[--wi];
-                if (m) p.res->end_nm2_start = tile_gbase + uint64_t(wi) * SC_V + uint64_t(63 - __clzll(m)) + 1;
-                else if (!(sh.adj & 2u)) p.res->end_nm2_start = sh.x_in >= OPEN_BIAS ? sh.x_in - OPEN_BIAS + 1 : ~0ull;
-                // (the chunk's head: k_chunk_resolve answers)
-            }
-        }
-
-        // ---- list of the kept ENDs + records, one window of SC_CAP at a time (one iteration unless the tile is unusually dense)
-        for (uint32_t win = 0; win < nK; win += SC_CAP) {
-            if (win) {  // the previous window's lists are no longer read
-                __syncthreads();
-                if (tid == 0) sh.n2[pb] = 0;
-            }
+        // ---- scatter: the tile-local positions of my kept ENDs to their ranks (the list window by window of SC_CAP: one
+        // iteration unless the tile is unusually dense)
+        for (uint32_t win = 0; win == 0 || win < nK; win += SC_CAP) {
+            if (win) __syncthreads();  // the previous window's list is no longer read
             {
-                uint64_t m = K;
                 uint32_t r = baseK - win;  // (mod 2^32: ranks below the window fail the bound check)
+                uint32_t m = uint32_t(K);
+                const uint32_t p0 = uint32_t(tid) * SC_V;
                 while (m) {
-                    const int b = __ffsll(m) - 1;
+                    const uint32_t b = uint32_t(__ffs(m) - 1);
                     m &= m - 1;
-                    if (r < uint32_t(SC_CAP)) {
-                        const uint64_t upto = (uint64_t(2) << b) - 1;  // bits 0 .. b
-                        const uint64_t sb = S & upto, cb = C & upto;
-                        const int s_loc = sb ? tid * SC_V + 63 - __clzll(sb) : prev_s;
-                        const uint32_t e_loc = uint32_t(tid * SC_V + b);
-                        uint32_t ent;
-                        if (s_loc >= 0) {  // the cluster is [s_loc, e_loc]: a base-code change at a position in (s_loc, e_loc]?
-                            const int c_loc = cb ? tid * SC_V + 63 - __clzll(cb) : prev_c;
-                            ent = e_loc | ((e_loc - uint32_t(s_loc) + 1u) << 14) | (uint32_t(c_loc > s_loc) << 30);
-                        } else {           // START before my warp: resolved when the record is written; a change seen here is inside
-                            ent = e_loc | (uint32_t(cb != 0 || prev_c >= 0) << 30) | (1u << 31);
-                        }
-                        sh.e_ent[r] = ent;
-                    }
+                    if (r < uint32_t(SC_CAP)) sh.e_ent[r] = uint16_t(p0 + b);
+                    ++r;
+                }
+                m = uint32_t(K >> 32);
+                while (m) {
+                    const uint32_t b = uint32_t(__ffs(m) - 1);
+                    m &= m - 1;
+                    if (r < uint32_t(SC_CAP)) sh.e_ent[r] = uint16_t(p0 + 32u + b);
                     ++r;
                 }
             }
-            __syncthreads();  // (B) list; warp 0's tile words
-            const uint64_t x_in = sh.x_in, prefix = sh.prefix;
+            __syncthreads();  // (B) list; warp 0's tile words; warp 0 is done with the summaries
+
+            // ---- the tile that holds position n_global - 2 (one per eBWT): an END there decides the reference's post-EOF phantom
+            // value whether its record is kept or not
+            if (!interior && win == 0 && p.n_global - 2 - tile_gbase < uint64_t(SC_T)) {
+                const uint32_t e_loc = uint32_t(p.n_global - 2 - tile_gbase);
+                if (uint32_t(tid) == (e_loc >> 6) && ((E >> (e_loc & 63)) & 1u)) {
+                    const int s_loc = find_prev(sS, bSs, any8, e_loc);
+                    if (s_loc >= 0) p.res->end_nm2_start = tile_gbase + uint64_t(s_loc) + 1;
+                    else if (!(sh.adj & 2u)) p.res->end_nm2_start = sh.x_in >= OPEN_BIAS ? sh.x_in - OPEN_BIAS + 1 : ~0ull;
+                    // (the chunk's head: k_chunk_resolve answers)
+                }
+            }
+            if (nK == 0) break;
+
+            const uint64_t x_in = sh.x_in;
+            const uint32_t prefix = sh.prefix;
             const uint32_t adj = sh.adj & 1u;
             const bool carried = sh.carried != 0;
             const uint32_t n_win = nK - win < uint32_t(SC_CAP) ? nK - win : uint32_t(SC_CAP);
+            uint32_t bases32 = 0;
             for (uint32_t i = tid; i < n_win; i += SC_THREADS) {
-                const uint32_t ent = sh.e_ent[i];
-                const uint32_t e = ent & 0x3fffu;
-                const uint64_t gend = tile_gbase + e;
+                const uint32_t e = sh.e_ent[i];
+                const int s_loc = find_prev(sS, bSs, any8, e);
                 uint64_t st;
                 uint32_t len;
-                bool chg = (ent >> 30) & 1u, carried_end = false;
-                if (!(ent >> 31)) {
-                    len = (ent >> 14) & 0xffffu;
-                    st = gend - len + 1;
-                } else {  // nearest START / change in the warps before the END's
-                    const int wq = int(e >> 11);
-                    int s_loc = -1, c_loc = -1;
-                    for (int q = wq - 1; q >= 0 && s_loc < 0; --q) s_loc = sh.wls[pb][q];
-                    for (int q = wq - 1; q >= 0 && c_loc < 0; --q) c_loc = sh.wlc[pb][q];
-                    if (s_loc >= 0) {
-                        st = tile_gbase + uint64_t(s_loc);
-                        len = e - uint32_t(s_loc) + 1u;
-                        chg = chg || c_loc > s_loc;
-                    } else {  // no START in the tile before it: the tile's carried END
-                        carried_end = true;
-                        if (sh.adj) continue;  // the chunk's head (k_chunk_resolve writes it) / dropped by the exact test
-                        st = x_in - OPEN_BIAS;
-                        len = uint32_t(gend - st + 1) & 0xffffu;
-                        // a change in the tile before it, or after the START in an earlier tile; a wrapped length: the analysed
-                        // range [st, st + len) is not this cluster's -- the exact test decides
-                        chg = chg || c_loc >= 0 || sh.c_in > st + 1 || gend - st + 1 != uint64_t(len);
-                    }
+                if (s_loc >= 0) {
+                    len = e - uint32_t(s_loc) + 1u;
+                    st = tile_gbase + uint32_t(s_loc);
+                } else {  // no START in the tile before it: the tile's carried END
+                    if (sh.adj) continue;  // the chunk's head (k_chunk_resolve writes it) / dropped by the exact test
+                    st = x_in - OPEN_BIAS;
+                    len = uint32_t(tile_gbase + e - st + 1) & 0xffffu;
                 }
-                const uint64_t o = prefix + win + i - ((carried && !carried_end) ? adj : 0u);
-                if (o - seg_base < p.seg_cap) {
-                    p.seg_start[o] = st;
-                    p.seg_len[o] = uint16_t(len);
+                const uint32_t o = prefix + win + i - ((carried && s_loc >= 0) ? adj : 0u);
+                if (o < seg_room) {
+                    p.seg_start[seg_base + o] = st;
+                    p.seg_len[seg_base + o] = uint16_t(len);
                 } else {
                     p.res->overflow |= 1;
                 }
-                acc_bases += len;
+                bases32 += len;
                 if (len <= uint32_t(MAX_C_LEN)) atomicAdd(&sh.hist[len], 1u);
                 my_last_o = o;
                 my_last_len = len;
-                // BWT prefilter, first level: no base-code change inside the cluster = one base code = it cannot pass.  The others are
-                // counted below, densely; a record whose analysed range lies before the plane window (wrapped length) goes
-                // straight to the exact test.
-                if (pf && chg && len >= 2 * p.pf_mcov && len <= uint32_t(MAX_C_LEN)) {
-                    if (st + PL_PAD < tile_gbase) {
-                        const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
-                        if (at < p.pf_cap) p.pf_list[at] = SurvEntry{st, st - p.global_off, len, 0u};
-                        else p.res->overflow |= 2;  // (seen by every rank in the exchange rows: all of them repeat the round)
-                    } else {
-                        sh.list2[atomicAdd(&sh.n2[pb], 1u)] = uint32_t(st + PL_PAD - tile_gbase) | (len << 16);
-                    }
-                }
-            }
-            if (pf) {  // second level: the one-popcount bound (planes.cuh) on the records that have a change inside, one lane each
-                __syncthreads();
-                const uint32_t n2 = sh.n2[pb];
-                for (uint32_t j = tid; j < n2; j += SC_THREADS) {
-                    const uint32_t v = sh.list2[j];
-                    const uint32_t b_lo = v & 0xffffu, len = v >> 16, b_last = b_lo + len - 1;
-                    const uint32_t q_lo = b_lo >> 6, q_last = b_last >> 6;
-                    unsigned long long f0 = 0, f1 = 0;
-                    uint32_t others = 0;
-                    for (uint32_t q = q_lo; q <= q_last; ++q) {
-                        const uint4 pv = pf_win[q];
-                        const unsigned long long x0 = (uint64_t(pv.y) << 32) | pv.x, x1 = (uint64_t(pv.w) << 32) | pv.z;
-                        unsigned long long mask = ~0ull;
-                        if (q == q_lo) {
-                            mask = ~0ull << (b_lo & 63);
-                            f0 = 0ull - ((x0 >> (b_lo & 63)) & 1ull);
-                            f1 = 0ull - ((x1 >> (b_lo & 63)) & 1ull);
+                // BWT prefilter: the one-popcount bound (planes.cuh) on the analysed range [st, st + len) in the plane window; a
+                // record whose range starts before the window (a wrapped length) goes straight to the exact test
+                if (pf && len >= 2 * p.pf_mcov && len <= uint32_t(MAX_C_LEN)) {
+                    bool pass = true;
+                    if (st + PL_PAD >= tile_gbase) {
+                        const uint32_t b_lo = uint32_t(st + PL_PAD - tile_gbase), b_last = b_lo + len - 1;
+                        const uint32_t q_lo = b_lo >> 6, q_last = b_last >> 6;
+                        unsigned long long f0 = 0, f1 = 0;
+                        uint32_t others = 0;
+                        for (uint32_t q = q_lo; q <= q_last; ++q) {
+                            const uint4 pv = lds_u128(pf_win + q * 16u);
+                            const unsigned long long x0 = (uint64_t(pv.y) << 32) | pv.x, x1 = (uint64_t(pv.w) << 32) | pv.z;
+                            unsigned long long mask = ~0ull;
+                            if (q == q_lo) {
+                                mask = ~0ull << (b_lo & 63);
+                                f0 = 0ull - ((x0 >> (b_lo & 63)) & 1ull);
+                                f1 = 0ull - ((x1 >> (b_lo & 63)) & 1ull);
+                            }
+                            if (q == q_last) mask &= ~0ull >> (63 - (b_last & 63));
+                            others += __popcll(((x0 ^ f0) | (x1 ^ f1)) & mask);
                         }
-                        if (q == q_last) mask &= ~0ull >> (63 - (b_last & 63));
-                        others += __popcll(((x0 ^ f0) | (x1 ^ f1)) & mask);
+                        pass = others >= p.pf_mcov;  // at least mcov records differ from the first one's base code
                     }
-                    if (others >= p.pf_mcov) {  // at least mcov records differ from the first one's base code: to the exact test
-                        const uint64_t st = tile_gbase + b_lo - PL_PAD;
+                    if (pass) {
                         const unsigned long long at = atomicAdd(&p.res->n_pf, 1ull);
                         if (at < p.pf_cap) p.pf_list[at] = SurvEntry{st, st - p.global_off, len, 0u};
                         else p.res->overflow |= 2;  // (seen by every rank in the exchange rows: all of them repeat the round)
                     }
                 }
             }
+            acc_bases += bases32;
         }
     }
 
@@ -511,7 +519,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         cr->head_end = head_end;
         cr->last_state = seen ? (X >= OPEN_BIAS ? X : 1ull) : 0ull;  // 0: no event; 1: closed; >= 2: OPEN_BIAS + global START
         cr->n_end = n_end;
-        sh.prefix = seg_base + cnt;  // (for the thread that wrote the chunk's last record)
+        sh.prefix = cnt;  // (for the thread that wrote the chunk's last record)
         if (c == 0 && p.tail_lcp) {
             p.res->tail_lcp_nm2 = p.tail_lcp[0];
             p.res->tail_lcp_nm1 = p.tail_lcp[1];
@@ -519,7 +527,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         }
     }
     __syncthreads();
-    if (my_last_o + 1 == sh.prefix && sh.prefix != seg_base) cr->last_len = my_last_len;
+    if (my_last_o + 1 == sh.prefix && sh.prefix != 0) cr->last_len = my_last_len;
 }
 
 // =============================================================================================
@@ -732,13 +740,15 @@ cudaError_t launch_scan(const Scan8Params& p0, uint64_t alloc_r, cudaStream_t st
     if (!enc) return cudaErrorNotSupported;
     Scan8Params p = p0;
     p.num_tiles = uint32_t(scan_num_tiles(p.n_local));
+    // the bit-sliced LCP as rows of 256 bytes = one run of 32 words (8 rows per block of LCPT_BLOCK positions); the boxes
+    // the kernel takes from it are 2 words x 8 runs: the plane words of the group before / after a tile
     CUtensorMap tmap;
-    cuuint64_t gdim[2] = {128, cuuint64_t(alloc_r / 128)};  // the padded byte array from local position 0 on, as rows of 128 bytes
-    cuuint64_t gstride[1] = {128};
-    cuuint32_t box[2] = {128, cuuint32_t(SC_T / 128)};
+    cuuint64_t gdim[2] = {256, cuuint64_t(lcpt_bytes(alloc_r) / 256)};
+    cuuint64_t gstride[1] = {256};
+    cuuint32_t box[2] = {16, 8};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(p.lcp8), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(p.lcpt), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     int occ = 0;

@@ -60,24 +60,28 @@ cudaError_t launch_unpack_gesa(const uint8_t* d_rec, uint64_t count, int x, int 
 }
 
 // ---- the narrow resident copies, written by every load ---------------------------------------------
-// The two kernels that touch every position do not need the inputs at file width: the scan reads a
-// one-byte LCP (values above 127 are saturated and raise *flag when they lie in the range the scan looks at: the shard
-// then stays on the 4-byte stream), the BWT-only prefilter reads the two bit planes of the 2-bit base code.  k_derive
-// writes both for the local positions [a, b) that a load has just put in place -- the unpack kernel's or the copies'
-// output is still in L2 -- so sealing a shard costs no pass over the data.  Work unit = 16 positions; the four lanes of a
-// 64-position plane quad combine their bits by shuffles; quads only partly inside [a, b) keep their other bits.
+// The two kernels that touch every position do not need the inputs at file width:
+//  * the scan reads the LCP BIT-SLICED and plane-major: blocks of LCPT_BLOCK = 2048 positions, each eight runs of 32
+//    64-bit words -- run p < 7 = bit plane p of the value, run 7 = the plane A, bit x = lcp[x-1] > lcp[x]; word g of a run
+//    = positions 64 g .. 64 g + 63 of the block.  Values above 127 are saturated and raise *flag when they lie in the
+//    range the scan looks at: the shard then stays on the 4-byte stream.  Nothing here depends on k: "lcp >= k" is a
+//    7-step bit-sliced compare in the scan (scan.cu), the local-minimum test is A & ~(A >> 1);
+//  * the BWT-only prefilter reads the two bit planes of the 2-bit base code.
+// k_derive writes both for the local positions [a, b) that a load has just put in place -- the unpack kernel's or the
+// copies' output is still in L2 -- so sealing a shard costs no pass over the data.  A load of [a, b) also refreshes bit b
+// of A (its left neighbour is new), so ranges may arrive in any order.  Work unit = 16 positions; the four lanes of a
+// 64-position quad combine their bits by shuffles; quads only partly inside [a, b) keep their other bits.
 __device__ __forceinline__ uint32_t code_of(uint32_t c) {  // base_to_int, ref:include.hpp:265-279: ACGT/acgt -> 0..3, anything else 0
     const uint32_t u = c & 0xDFu;
     return uint32_t(u == 'C') + 2u * uint32_t(u == 'G') + 3u * uint32_t(u == 'T');
 }
+// bit b of the four bytes of w -> bits 0..3
+__device__ __forceinline__ uint32_t gather_bit(uint32_t w, int b) { return (((w >> b) & 0x01010101u) * 0x01020408u) >> 24; }
 
-// The CHANGE plane (what the one-pass scan's prefilter reads): bit x = base code of position x differs from that of x - 1.
-// A load of [a, b) also refreshes bit b (its left neighbour is new), so ranges may arrive in any order.
 __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp, const uint8_t* __restrict__ bwt,
-                                                uint8_t* __restrict__ lcp8, uint4* __restrict__ planes,
-                                                unsigned long long* __restrict__ chg, int64_t a, int64_t b,
-                                                int64_t chk_lo, int64_t chk_hi, uint32_t* __restrict__ flag) {
-    const int64_t q_first = (a + PL_PAD) >> 6, q_last = (b + PL_PAD) >> 6;  // (position b included: its change bit)
+                                                unsigned long long* __restrict__ lcpt, uint4* __restrict__ planes,
+                                                int64_t a, int64_t b, int64_t chk_lo, int64_t chk_hi, uint32_t* __restrict__ flag) {
+    const int64_t q_first = (a + PL_PAD) >> 6, q_last = (b + PL_PAD) >> 6;  // (position b included: its A bit)
     const int64_t n_units = (q_last - q_first + 1) * 4;
     const int lane = threadIdx.x & 31;
     uint32_t bad = 0;
@@ -89,10 +93,11 @@ __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp
         const int64_t x0 = q * 64 - PL_PAD + (u & 3) * 16;  // my 16 positions: [x0, x0 + 16)
         const int64_t lo = x0 > a ? x0 : a, hi = x0 + 16 < b ? x0 + 16 : b;
         const uint32_t cov = (act && hi > lo) ? (((1u << (hi - lo)) - 1u) << (lo - x0)) : 0u;
-        // change bits: my positions in [a, b]
+        // A bits: my positions in [a, b]
         const int64_t hic = x0 + 16 < b + 1 ? x0 + 16 : b + 1;
-        const uint32_t covc = (act && bwt && hic > lo) ? (((1u << (hic - lo)) - 1u) << (lo - x0)) : 0u;
-        uint32_t c0 = 0, c1 = 0, cc = 0;
+        const uint32_t covc = (act && lcpt && hic > lo) ? (((1u << (hic - lo)) - 1u) << (lo - x0)) : 0u;
+        uint32_t c0 = 0, c1 = 0;
+        uint32_t pl[4] = {0, 0, 0, 0};  // my 16 bits of LCP planes 2i | 2i + 1 << 16; [3] = plane 6 | A << 16
         if (cov == 0xffffu) {
             if (bwt) {
                 const uint4 v = *reinterpret_cast<const uint4*>(bwt + x0);
@@ -103,11 +108,10 @@ __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp
                     c0 |= (code & 1u) << j;
                     c1 |= (code >> 1) << j;
                 }
-                const uint32_t pc = x0 > -int64_t(PAD_L) ? code_of(bwt[x0 - 1]) : 0u;  // the position before my 16
-                cc = ((c0 ^ ((c0 << 1) | (pc & 1u))) | (c1 ^ ((c1 << 1) | (pc >> 1)))) & 0xffffu;
             }
-            if (lcp8) {
-                uint32_t out[4];
+            if (lcpt) {
+                uint32_t prev = x0 > -int64_t(PAD_L) ? lcp[x0 - 1] : 0u;
+                uint32_t abits = 0;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const uint4 v = *reinterpret_cast<const uint4*>(lcp + x0 + 4 * g);
@@ -118,57 +122,72 @@ __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp
                         const int64_t x = x0 + 4 * g + j;
                         if (e4[j] > 127u && x >= chk_lo && x < chk_hi) bad = 1;
                         o |= (e4[j] > 127u ? 127u : e4[j]) << (8 * j);
+                        abits |= uint32_t(prev > e4[j]) << (4 * g + j);
+                        prev = e4[j];
                     }
-                    out[g] = o;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        pl[i] |= gather_bit(o, 2 * i) << (4 * g);
+                        if (i < 3) pl[i] |= gather_bit(o, 2 * i + 1) << (16 + 4 * g);
+                    }
                 }
-                *reinterpret_cast<uint4*>(lcp8 + x0) = make_uint4(out[0], out[1], out[2], out[3]);
+                pl[3] |= abits << 16;
             }
         } else if (cov | covc) {
             if (bwt) {
-                uint32_t pc = lo > -int64_t(PAD_L) ? code_of(bwt[lo - 1]) : 0u;
-                for (int64_t x = lo; x < hic; ++x) {  // (x == b: only the change bit, read from whatever position b holds now)
+                for (int64_t x = lo; x < hi; ++x) {
                     const uint32_t code = code_of(bwt[x]);
-                    if (x < hi) {
-                        c0 |= (code & 1u) << (x - x0);
-                        c1 |= (code >> 1) << (x - x0);
-                    }
-                    cc |= uint32_t(code != pc) << (x - x0);
-                    pc = code;
+                    c0 |= (code & 1u) << (x - x0);
+                    c1 |= (code >> 1) << (x - x0);
                 }
             }
-            for (int64_t x = lo; x < hi; ++x) {
-                if (lcp8) {
+            if (lcpt) {
+                uint32_t prev = lo > -int64_t(PAD_L) ? lcp[lo - 1] : 0u;
+                for (int64_t x = lo; x < hic; ++x) {  // (x == b: only the A bit, from whatever position b holds now)
                     const uint32_t v = lcp[x];
-                    if (v > 127u && x >= chk_lo && x < chk_hi) bad = 1;
-                    lcp8[x] = uint8_t(v > 127u ? 127u : v);
+                    if (x < hi) {
+                        if (v > 127u && x >= chk_lo && x < chk_hi) bad = 1;
+                        const uint32_t vs = v > 127u ? 127u : v;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            pl[i] |= ((vs >> (2 * i)) & 1u) << (x - x0);
+                            if (i < 3) pl[i] |= ((vs >> (2 * i + 1)) & 1u) << (16 + (x - x0));
+                        }
+                    }
+                    pl[3] |= uint32_t(prev > v) << (16 + (x - x0));
+                    prev = v;
                 }
             }
         }
-        if (planes) {  // (kernel-uniform) the quad's four lanes -> one 16-byte store by the first of them
-            const int l0 = lane & ~3;
-            uint32_t p0lo = 0, p0hi = 0, p1lo = 0, p1hi = 0, cvlo = 0, cvhi = 0;
-            unsigned long long cw = 0, cwcov = 0;
+        // the quad's four lanes -> stores by the first of them
+        const int l0 = lane & ~3;
+        const bool writer = act && (lane & 3) == 0;
+        uint32_t cvlo = 0, cvhi = 0, cclo = 0, cchi = 0;  // coverage of the quad: positions [a, b) / [a, b]
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t cv = __shfl_sync(0xffffffffu, cov | (covc << 16), l0 + k);
+            if (k < 2) {
+                cvlo |= (cv & 0xffffu) << (16 * k);
+                cclo |= (cv >> 16) << (16 * k);
+            } else {
+                cvhi |= (cv & 0xffffu) << (16 * (k - 2));
+                cchi |= (cv >> 16) << (16 * (k - 2));
+            }
+        }
+        if (planes) {  // (kernel-uniform)
+            uint32_t p0lo = 0, p0hi = 0, p1lo = 0, p1hi = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t b0 = __shfl_sync(0xffffffffu, c0, l0 + k), b1 = __shfl_sync(0xffffffffu, c1, l0 + k);
-                const uint32_t cv = __shfl_sync(0xffffffffu, cov, l0 + k);
-                cw |= (unsigned long long)__shfl_sync(0xffffffffu, cc, l0 + k) << (16 * k);
-                cwcov |= (unsigned long long)__shfl_sync(0xffffffffu, covc, l0 + k) << (16 * k);
+                const uint32_t b01 = __shfl_sync(0xffffffffu, c0 | (c1 << 16), l0 + k);
                 if (k < 2) {
-                    p0lo |= b0 << (16 * k);
-                    p1lo |= b1 << (16 * k);
-                    cvlo |= cv << (16 * k);
+                    p0lo |= (b01 & 0xffffu) << (16 * k);
+                    p1lo |= (b01 >> 16) << (16 * k);
                 } else {
-                    p0hi |= b0 << (16 * (k - 2));
-                    p1hi |= b1 << (16 * (k - 2));
-                    cvhi |= cv << (16 * (k - 2));
+                    p0hi |= (b01 & 0xffffu) << (16 * (k - 2));
+                    p1hi |= (b01 >> 16) << (16 * (k - 2));
                 }
             }
-            if (act && (lane & 3) == 0 && cwcov) {
-                if (cwcov != ~0ull) cw = (chg[q] & ~cwcov) | (cw & cwcov);
-                chg[q] = cw;
-            }
-            if (act && (lane & 3) == 0 && (cvlo | cvhi)) {
+            if (writer && (cvlo | cvhi)) {
                 uint4 o = make_uint4(p0lo, p0hi, p1lo, p1hi);
                 if ((cvlo & cvhi) != 0xffffffffu) {  // partly covered: the other positions keep their bits
                     const uint4 old = planes[q];
@@ -180,19 +199,51 @@ __global__ void __launch_bounds__(256) k_derive(const uint32_t* __restrict__ lcp
                 planes[q] = o;
             }
         }
+        if (lcpt) {  // (kernel-uniform) the eight words of my quad: word g of the runs of block blk
+            uint32_t wlo[8] = {0, 0, 0, 0, 0, 0, 0, 0}, whi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, pl[i], l0 + k);
+                    if (k < 2) {
+                        wlo[2 * i] |= (v & 0xffffu) << (16 * k);
+                        wlo[2 * i + 1] |= (v >> 16) << (16 * k);
+                    } else {
+                        whi[2 * i] |= (v & 0xffffu) << (16 * (k - 2));
+                        whi[2 * i + 1] |= (v >> 16) << (16 * (k - 2));
+                    }
+                }
+            }
+            const int64_t gi = q - PL_PAD / 64 + LCPT_BLOCK / 64;  // group index from the first group of the array (position -LCPT_BLOCK)
+            if (writer && gi >= 0 && (cclo | cchi)) {
+                unsigned long long* run0 = lcpt + (gi >> 5) * (LCPT_BLOCK / 8) + (gi & 31);
+                const bool full = (cvlo & cvhi) == 0xffffffffu;  // (then [a, b] covers the quad as well)
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    unsigned long long o = (uint64_t(whi[w]) << 32) | wlo[w];
+                    if (!full) {
+                        const unsigned long long m = w == 7 ? ((uint64_t(cchi) << 32) | cclo) : ((uint64_t(cvhi) << 32) | cvlo);  // run 7 = A: [a, b]
+                        o = (run0[w * 32] & ~m) | (o & m);
+                    }
+                    run0[w * 32] = o;
+                }
+            }
+        }
     }
     if (__syncthreads_or(int(bad)) && threadIdx.x == 0 && flag) atomicOr(flag, 1u);
 }
 
-// lcp / bwt / lcp8: local position 0 of the padded arrays (a >= -PAD_L).  lcp8 == null: no byte LCP (bwt == null: no planes).
-cudaError_t launch_derive(const uint32_t* lcp, const uint8_t* bwt, uint8_t* lcp8, uint4* planes, uint64_t* chg, int64_t a, int64_t b,
+// lcp / bwt: local position 0 of the padded arrays (a >= -PAD_L); lcpt: first byte of the bit-sliced array (the block of
+// the local positions -LCPT_BLOCK .. -1).  lcpt == null: no bit-sliced LCP (bwt == null: no planes).
+cudaError_t launch_derive(const uint32_t* lcp, const uint8_t* bwt, uint8_t* lcpt, uint4* planes, int64_t a, int64_t b,
                           int64_t chk_lo, int64_t chk_hi, uint32_t* flag, cudaStream_t stream, int sm_count) {
-    if (b <= a || (!lcp8 && !bwt)) return cudaSuccess;
+    if (b <= a || (!lcpt && !bwt)) return cudaSuccess;
     const int64_t n_units = (((b + PL_PAD) >> 6) - ((a + PL_PAD) >> 6) + 1) * 4;
     int64_t blocks = (n_units + 255) / 256;
     if (blocks > int64_t(sm_count) * 16) blocks = int64_t(sm_count) * 16;
-    k_derive<<<unsigned(blocks), 256, 0, stream>>>(lcp8 ? lcp : nullptr, bwt, lcp8, bwt ? planes : nullptr,
-                                                   reinterpret_cast<unsigned long long*>(bwt ? chg : nullptr), a, b, chk_lo, chk_hi, flag);
+    k_derive<<<unsigned(blocks), 256, 0, stream>>>(lcpt ? lcp : nullptr, bwt, reinterpret_cast<unsigned long long*>(lcpt),
+                                                   bwt ? planes : nullptr, a, b, chk_lo, chk_hi, flag);
     return cudaGetLastError();
 }
 
