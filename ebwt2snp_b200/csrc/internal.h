@@ -143,6 +143,8 @@ struct Scan8Params {
     uint32_t k;
     int32_t min_len;            // <= 33
     uint32_t num_tiles;         // filled by the launcher
+    uint32_t km[8];             // (launcher) bit b of min(k, 128) as an all-ones / zero word, b < 7; [7]: k >= 128
+    uint32_t t_int_lo, t_int_hi;  // (launcher) tiles that need none of the edge rules
     uint32_t n_chunks, tiles_per_chunk;  // scan_plan
     uint64_t* seg_start;        // record segments: chunk c owns [c * seg_cap, (c + 1) * seg_cap)
     uint16_t* seg_len;

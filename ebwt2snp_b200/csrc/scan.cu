@@ -76,9 +76,8 @@ constexpr int NO_POS = 0x7fffffff;
 struct ScanShared {
     uint64_t full_bar[SC_STAGES];
     uint64_t x_in;                // open-cluster state entering the tile            (warp 0, between the barriers (A) and (B))
-    uint64_t prefix;              // segment index of the tile's first record
+    uint32_t prefix;              // segment index of the record of the tile's kept END of rank 0 (one less when the carried END is not written)
     uint32_t adj;                 // bit 0: the carried END is not written by this tile; bit 1: it is the chunk's head
-    uint32_t carried;             // the tile's first event is an END
     uint32_t open_after;          // (interior tiles) a cluster is open after the tile's last position
     uint32_t wsum[SC_WARPS];      // per warp: #kept ENDs | #ENDs << 16
     uint32_t bS[2][SC_WARPS];     // per warp: lanes whose START word is not empty (by tile parity, like sS)
@@ -122,18 +121,25 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
     return (uint64_t(__shfl_sync(FULL, uint32_t(v >> 32), src)) << 32) | __shfl_sync(FULL, uint32_t(v), src);
 }
 // one step of the bit-sliced "value < k" from the least significant plane up: lt' = k_b ? (~x | lt) : (~x & lt), with
-// km = all ones / zero for k_b -- one 3-input logic function (a = x, b = km, c = lt: table 0x8E)
+// km = all ones / zero for k_b -- one 3-input logic function (LOP3, table 0x8E), km read from the kernel parameters
 __device__ __forceinline__ uint32_t lt_step(uint32_t x, uint32_t km, uint32_t lt) {
-    uint32_t r;
+    uint32_t r;  // (written as C++ the compiler emits three instructions for it)
     asm("lop3.b32 %0, %1, %2, %3, 0x8E;" : "=r"(r) : "r"(x), "r"(km), "r"(lt));
     return r;
 }
-// nearest set bit at or before tile-local position e of a 16 384-bit mask kept as one word per thread (words) plus, per
-// warp, the ballot of the lanes whose word is not empty (bal) and the warps that have any (any8); -1 = none
-__device__ __forceinline__ int find_prev(const uint64_t* words, const uint32_t* bal, uint32_t any8, uint32_t e) {
+// nearest set bit at or before tile-local position e of a 16 384-bit mask kept as one 64-bit word per thread (words, as
+// 32-bit halves) plus, per warp, the ballot of the lanes whose word is not empty (bal) and the warps that have any (any8);
+// -1 = none
+__device__ __forceinline__ int find_prev(const uint2* words, const uint32_t* bal, uint32_t any8, uint32_t e) {
     uint32_t t = e >> 6;
-    uint64_t m = words[t] & (~uint64_t(0) >> (63u - (e & 63u)));
-    if (!m) {
+    uint2 v = words[t];
+    const uint32_t keep = FULL >> (31u - (e & 31u));
+    if (e & 32u) v.y &= keep;
+    else {
+        v.x &= keep;
+        v.y = 0;
+    }
+    if (!(v.x | v.y)) {
         uint32_t w = t >> 5;
         uint32_t bm = bal[w] & ((1u << (t & 31u)) - 1u);
         if (!bm) {
@@ -143,14 +149,14 @@ __device__ __forceinline__ int find_prev(const uint64_t* words, const uint32_t* 
             bm = bal[w];
         }
         t = w * 32u + 31u - uint32_t(__clz(bm));
-        m = words[t];
+        v = words[t];
     }
-    return int(t * 64u) + 63 - __clzll(m);
+    return int(t * 64u) + (v.y ? 63 - __clz(v.y) : 31 - __clz(v.x));
 }
 
 }  // namespace
 
-__global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __grid_constant__ CUtensorMap tmap, Scan8Params p) {
+__global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Scan8Params p) {
     extern __shared__ __align__(128) uint8_t smem_dyn[];  // SC_STAGES stages, then SC_PSLOTS plane windows
     __shared__ ScanShared sh;
     const uint32_t stage0 = smem_u32(smem_dyn);
@@ -159,29 +165,20 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool pf = p.pf_mcov != 0;
     const int spread = p.min_len >= 2 ? p.min_len - 2 : -1;  // extra positions a START shadows; -1: nothing is dropped
-    const uint32_t kk = p.k > 128u ? 128u : p.k;             // values are <= 127: k >= 128 never matches
-    uint32_t km[7];
-#pragma unroll
-    for (int b = 0; b < 7; ++b) km[b] = ((kk >> b) & 1u) ? FULL : 0u;
-    const uint32_t k_none = kk >= 128u ? FULL : 0u;          // "every value is below k"
     const uint32_t c = blockIdx.x;
     const uint32_t t_lo = c * p.tiles_per_chunk < p.num_tiles ? c * p.tiles_per_chunk : p.num_tiles;
     const uint32_t t_hi = t_lo + p.tiles_per_chunk < p.num_tiles ? t_lo + p.tiles_per_chunk : p.num_tiles;
     const uint32_t n_my = t_hi - t_lo;
-    const uint64_t seg_base = uint64_t(c) * p.seg_cap;
+    uint64_t* const seg_start = p.seg_start + uint64_t(c) * p.seg_cap;  // my chunk's segment
+    uint16_t* const seg_len = p.seg_len + uint64_t(c) * p.seg_cap;
     const uint32_t seg_room = uint32_t(p.seg_cap < 0xffffffffull ? p.seg_cap : 0xffffffffull);
-    // tiles [t_int_lo, t_int_hi) need none of the edge rules: not the first tile of the eBWT, wholly inside n_local, not
-    // the tile that holds position n_global - 1
-    const uint32_t t_int_lo = p.global_off == 0 ? 1u : 0u;
-    const uint32_t t_int_hi = p.global_off + p.n_local == p.n_global ? (p.num_tiles ? p.num_tiles - 1 : 0) : uint32_t(p.n_local / SC_T);
 
-    // where my words are in a stage: run p of my warp's block at own + 256 p; the word before it in the same run (the last
-    // word of the previous block for lane 0, the edge box for thread 0: 8 rows of {word 30, word 31}) and the word after it
+    // where my words are in a stage: run b of my warp's block at own + 256 b; the word before it in the same run (lane 0:
+    // the last word of the previous block) and the word after it, at the same constant offsets from their bases.  Thread 0
+    // and the last thread read next to the stage there and take their neighbours from the edge boxes afterwards.
     const uint32_t own = uint32_t(warp) * LCPT_BLOCK + uint32_t(lane) * 8u;
-    const uint32_t prev_off = tid == 0 ? uint32_t(SC_T) + 12u : own + (lane ? 0u - 8u : 0u - 1800u) + 4u;  // high half: bit 63
-    const uint32_t prev_str = tid == 0 ? 16u : 256u;
-    const uint32_t next_off = tid == SC_THREADS - 1 ? uint32_t(SC_T + SC_EDGE) : own + (lane < 31 ? 8u : 1800u);  // low half: bit 0
-    const uint32_t next_str = tid == SC_THREADS - 1 ? 16u : 256u;
+    const uint32_t prev_off = own + (lane ? 0u - 8u : 0u - 1800u) + 4u;  // high half: bit 63
+    const uint32_t next_off = own + (lane < 31 ? 8u : 1800u);            // low half: bit 0
 
     for (int i = tid; i < E2S_HIST_BINS; i += SC_THREADS) sh.hist[i] = 0;
     auto issue = [&](uint32_t it) {  // thread 0: the it-th tile of the chunk -> stage it % SC_STAGES
@@ -191,10 +188,10 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         const uint32_t t = t_lo + it;
         mbar_expect_tx(&sh.full_bar[stage], SC_STAGE_BYTES + (pf ? SC_PF_BYTES : 0));
         // (block 0 of the array = the LCPT_BLOCK positions before local position 0: tile t = blocks 8 t + 1 .. 8 t + 8)
-        bulk_g2s_a(dst, p.lcpt + (uint64_t(t) * SC_WARPS + 1) * LCPT_BLOCK, SC_T, &sh.full_bar[stage]);
+        bulk_g2s_a(dst + SC_EDGE, p.lcpt + (uint64_t(t) * SC_WARPS + 1) * LCPT_BLOCK, SC_T, &sh.full_bar[stage]);
         // the tensor: rows of 256 bytes = one run; words 30, 31 of the 8 runs of the block before, words 0, 1 of the block after
-        tma_load_2d_u8(dst + SC_T, &tmap, 240, int(t * SC_WARPS * 8), &sh.full_bar[stage]);
-        tma_load_2d_u8(dst + SC_T + SC_EDGE, &tmap, 0, int((t * SC_WARPS + SC_WARPS + 1) * 8), &sh.full_bar[stage]);
+        tma_load_2d_u8(dst, &tmap, 240, int(t * SC_WARPS * 8), &sh.full_bar[stage]);
+        tma_load_2d_u8(dst + SC_EDGE + SC_T, &tmap, 0, int((t * SC_WARPS + SC_WARPS + 1) * 8), &sh.full_bar[stage]);
         if (pf) bulk_g2s_a(planes0 + (it % SC_PSLOTS) * SC_PF_STRIDE, p.planes + uint64_t(t) * (SC_T / 64), SC_PF_BYTES, &sh.full_bar[stage]);
     };
     if (tid == 0) {
@@ -219,11 +216,11 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         const uint32_t parity = (it / SC_STAGES) & 1;
         const int pb = it & 1;
         const uint32_t t = t_lo + it;
-        const uint64_t tile_base = uint64_t(t) * SC_T;
-        const uint64_t tile_gbase = p.global_off + tile_base;
-        const uint32_t sa = stage0 + uint32_t(stage) * SC_STAGE_BYTES;
+        const uint32_t sa = stage0 + uint32_t(stage) * SC_STAGE_BYTES + SC_EDGE;  // the tile's first byte; the edge boxes at sa - SC_EDGE and sa + SC_T
         const uint32_t pf_win = planes0 + (it % SC_PSLOTS) * SC_PF_STRIDE;
-        const bool interior = t >= t_int_lo && t < t_int_hi;
+        const bool interior = t >= p.t_int_lo && t < p.t_int_hi;
+        uint2* const sS = reinterpret_cast<uint2*>(sh.sS[pb]);
+        uint32_t* const bSs = sh.bS[pb];
 
         mbar_wait(&sh.full_bar[stage], parity);
 
@@ -235,18 +232,31 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
 #pragma unroll
             for (int b = 0; b < 7; ++b) {
                 const uint2 v = lds_u64(sa + own + 256u * b);
-                lt_lo = lt_step(v.x, km[b], lt_lo);
-                lt_hi = lt_step(v.y, km[b], lt_hi);
-                ltp = lt_step(lds_u32(sa + prev_off + prev_str * b), km[b], ltp);
-                ltn = lt_step(lds_u32(sa + next_off + next_str * b), km[b], ltn);
+                lt_lo = lt_step(v.x, p.km[b], lt_lo);
+                lt_hi = lt_step(v.y, p.km[b], lt_hi);
+                ltp = lt_step(lds_u32(sa + prev_off + 256u * b), p.km[b], ltp);
+                ltn = lt_step(lds_u32(sa + next_off + 256u * b), p.km[b], ltn);
             }
             const uint2 av = lds_u64(sa + own + 256u * 7);
-            G = ~((uint64_t(lt_hi | k_none) << 32) | (lt_lo | k_none));
+            uint32_t ap = lds_u32(sa + prev_off + 256u * 7), an = lds_u32(sa + next_off + 256u * 7);
+            if (tid == 0) {  // the group before the tile: word 31 of the runs of the block before it (edge box: rows of {word 30, word 31})
+                ltp = 0;
+#pragma unroll
+                for (int b = 0; b < 7; ++b) ltp = lt_step(lds_u32(sa - SC_EDGE + 12u + 16u * b), p.km[b], ltp);
+                ap = lds_u32(sa - SC_EDGE + 12u + 16u * 7);
+            }
+            if (tid == SC_THREADS - 1) {  // the group after the tile: word 0 of the runs of the block after it
+                ltn = 0;
+#pragma unroll
+                for (int b = 0; b < 7; ++b) ltn = lt_step(lds_u32(sa + SC_T + 16u * b), p.km[b], ltn);
+                an = lds_u32(sa + SC_T + 16u * 7);
+            }
+            G = ~((uint64_t(lt_hi | p.km[7]) << 32) | (lt_lo | p.km[7]));  // km[7]: "every value is below k" (k >= 128)
             A = (uint64_t(av.y) << 32) | av.x;
-            g_m1 = (~(ltp | k_none)) >> 31;
-            a_m1 = lds_u32(sa + prev_off + prev_str * 7) >> 31;
-            g_p = (~(ltn | k_none)) & 1u;
-            a_p = lds_u32(sa + next_off + next_str * 7) & 1u;
+            g_m1 = (~(ltp | p.km[7])) >> 31;
+            a_m1 = ap >> 31;
+            g_p = (~(ltn | p.km[7])) & 1u;
+            a_p = an & 1u;
         }
 
         // ---- START / END masks of my 64 positions
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             uint64_t e_prev = uint64_t(g_m1 & ((a_m1 & ~uint32_t(A)) | ~uint32_t(G)) & 1u);
             uint64_t vm = ~uint64_t(0);
             if (!interior) {  // first tile of the eBWT, the tile holding position n_global - 1, tiles reaching past n_local
-                const uint64_t my_base = tile_base + uint64_t(tid) * SC_V;
+                const uint64_t my_base = uint64_t(t) * SC_T + uint64_t(tid) * SC_V;
                 const uint64_t gpos = p.global_off + my_base;
                 if (gpos == 0) {  // the init special cases of ref:ebwt2clust.cpp:83-86
                     E &= ~uint64_t(1);
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             const uint64_t Ep = (E << 1) | e_prev;
             S = G & (~Gp | Ep) & vm;
         }
-        sh.sS[pb][tid] = S;
+        sS[tid] = make_uint2(uint32_t(S), uint32_t(S >> 32));
 
         // ---- K = kept ENDs: E minus the ENDs of clusters shorter than min_len (a START at the same position or up to `spread`
         // positions before).  Before the tile: no START assumed -- the one END that can pair with a START of an earlier tile
@@ -300,9 +310,10 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             }
             K = E & ~sm;
         }
+        uint32_t k_lo = uint32_t(K), k_hi = uint32_t(K >> 32);
 
         // ---- ranks of the kept ENDs (one block scan of #kept | #ENDs << 16) and the per-warp summaries
-        const uint32_t pk = uint32_t(__popcll(K)) | (uint32_t(__popcll(E)) << 16);
+        const uint32_t pk = uint32_t(__popc(k_lo) + __popc(k_hi)) | (uint32_t(__popcll(E)) << 16);
         uint32_t inc = pk;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -314,12 +325,12 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             int fe = NO_POS;
             if (bE) {  // (warp-uniform) the warp's first END: in the word of the first lane that has one
                 const int src = __ffs(bE) - 1;
-                const uint64_t Ef = shfl64(E, src);
-                fe = (warp * 32 + src) * SC_V + __ffsll(Ef) - 1;
+                const uint32_t e_lo = __shfl_sync(FULL, uint32_t(E), src), e_hi = __shfl_sync(FULL, uint32_t(E >> 32), src);
+                fe = (warp * 32 + src) * SC_V + (e_lo ? __ffs(e_lo) - 1 : 31 + __ffs(e_hi));
             }
             if (lane == 31) sh.wsum[warp] = inc;
             if (lane == 0) {
-                sh.bS[pb][warp] = bS;
+                bSs[warp] = bS;
                 sh.wfe[warp] = fe;
             }
             if (interior) {  // a cluster is open after the tile iff its last position is inside one and not its END
@@ -340,7 +351,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         // my warp's rank offset, the tile's totals, the warps that have a START
         uint32_t baseK, nK, nE, any8;
         {
-            const uint32_t ws = sh.wsum[lane & (SC_WARPS - 1)], bq = sh.bS[pb][lane & (SC_WARPS - 1)];
+            const uint32_t ws = sh.wsum[lane & (SC_WARPS - 1)], bq = bSs[lane & (SC_WARPS - 1)];
             const uint32_t tot = __reduce_add_sync(FULL, lane < SC_WARPS ? ws : 0u);
             const uint32_t base = (inc - pk) + __reduce_add_sync(FULL, lane < warp ? ws : 0u);
             any8 = __ballot_sync(FULL, bq != 0) & ((1u << SC_WARPS) - 1u);
@@ -348,16 +359,15 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             nE = tot >> 16;
             baseK = base & 0xffffu;
         }
-        const uint64_t* sS = sh.sS[pb];
-        const uint32_t* bSs = sh.bS[pb];
 
         // ---- warp 0: the tile's first / last events, the carried END, the chunk state
         if (warp == 0) {
+            const uint64_t tile_gbase = p.global_off + uint64_t(t) * SC_T;
             int t_fs = NO_POS;
             if (any8) {
                 const uint32_t w = uint32_t(__ffs(any8) - 1);
                 const uint32_t t2 = w * 32u + uint32_t(__ffs(bSs[w]) - 1);
-                t_fs = int(t2 * 64u) + __ffsll(sS[t2]) - 1;
+                t_fs = int(t2 * 64u) + __ffsll(sh.sS[pb][t2]) - 1;
             }
             const int t_ls = find_prev(sS, bSs, any8, SC_T - 1);
             int t_fe = NO_POS;
@@ -393,9 +403,8 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             }
             if (lane == 0) {
                 sh.x_in = X;
-                sh.prefix = cnt;
+                sh.prefix = cnt - ((carried && adj) ? 1u : 0u);  // (the records after a carried END that is not written move up one)
                 sh.adj = adj | (is_head ? 2u : 0u);
-                sh.carried = carried ? 1u : 0u;
             }
             cnt += nK - adj;
             n_end += nE;
@@ -411,60 +420,70 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             if (win) __syncthreads();  // the previous window's list is no longer read
             {
                 uint32_t r = baseK - win;  // (mod 2^32: ranks below the window fail the bound check)
-                uint32_t m = uint32_t(K);
+                uint32_t mlo = k_lo, mhi = k_hi;
                 const uint32_t p0 = uint32_t(tid) * SC_V;
-                while (m) {
-                    const uint32_t b = uint32_t(__ffs(m) - 1);
-                    m &= m - 1;
-                    if (r < uint32_t(SC_CAP)) sh.e_ent[r] = uint16_t(p0 + b);
-                    ++r;
-                }
-                m = uint32_t(K >> 32);
-                while (m) {
-                    const uint32_t b = uint32_t(__ffs(m) - 1);
-                    m &= m - 1;
-                    if (r < uint32_t(SC_CAP)) sh.e_ent[r] = uint16_t(p0 + 32u + b);
-                    ++r;
+                if (nK <= uint32_t(SC_CAP)) {  // (the usual case: every rank is inside the window)
+                    while (mlo | mhi) {
+                        const uint32_t x = mlo ? mlo : mhi;
+                        const uint32_t b = uint32_t(__ffs(x) - 1) + (mlo ? 0u : 32u);
+                        if (mlo) mlo &= mlo - 1;
+                        else mhi &= mhi - 1;
+                        sh.e_ent[r++] = uint16_t(p0 + b);
+                    }
+                } else {
+                    while (mlo | mhi) {
+                        const uint32_t x = mlo ? mlo : mhi;
+                        const uint32_t b = uint32_t(__ffs(x) - 1) + (mlo ? 0u : 32u);
+                        if (mlo) mlo &= mlo - 1;
+                        else mhi &= mhi - 1;
+                        if (r < uint32_t(SC_CAP)) sh.e_ent[r] = uint16_t(p0 + b);
+                        ++r;
+                    }
                 }
             }
             __syncthreads();  // (B) list; warp 0's tile words; warp 0 is done with the summaries
 
             // ---- the tile that holds position n_global - 2 (one per eBWT): an END there decides the reference's post-EOF phantom
             // value whether its record is kept or not
-            if (!interior && win == 0 && p.n_global - 2 - tile_gbase < uint64_t(SC_T)) {
-                const uint32_t e_loc = uint32_t(p.n_global - 2 - tile_gbase);
-                if (uint32_t(tid) == (e_loc >> 6) && ((E >> (e_loc & 63)) & 1u)) {
-                    const int s_loc = find_prev(sS, bSs, any8, e_loc);
-                    if (s_loc >= 0) p.res->end_nm2_start = tile_gbase + uint64_t(s_loc) + 1;
-                    else if (!(sh.adj & 2u)) p.res->end_nm2_start = sh.x_in >= OPEN_BIAS ? sh.x_in - OPEN_BIAS + 1 : ~0ull;
-                    // (the chunk's head: k_chunk_resolve answers)
+            if (!interior && win == 0) {
+                const uint64_t tile_gbase = p.global_off + uint64_t(t) * SC_T;
+                if (p.n_global - 2 - tile_gbase < uint64_t(SC_T)) {
+                    const uint32_t e_loc = uint32_t(p.n_global - 2 - tile_gbase);
+                    if (uint32_t(tid) == (e_loc >> 6) && ((E >> (e_loc & 63)) & 1u)) {
+                        const int s_loc = find_prev(sS, bSs, any8, e_loc);
+                        if (s_loc >= 0) p.res->end_nm2_start = tile_gbase + uint64_t(s_loc) + 1;
+                        else if (!(sh.adj & 2u)) p.res->end_nm2_start = sh.x_in >= OPEN_BIAS ? sh.x_in - OPEN_BIAS + 1 : ~0ull;
+                        // (the chunk's head: k_chunk_resolve answers)
+                    }
                 }
             }
             if (nK == 0) break;
 
-            const uint64_t x_in = sh.x_in;
-            const uint32_t prefix = sh.prefix;
-            const uint32_t adj = sh.adj & 1u;
-            const bool carried = sh.carried != 0;
+            const uint32_t prefix = sh.prefix + win;
             const uint32_t n_win = nK - win < uint32_t(SC_CAP) ? nK - win : uint32_t(SC_CAP);
             uint32_t bases32 = 0;
             for (uint32_t i = tid; i < n_win; i += SC_THREADS) {
                 const uint32_t e = sh.e_ent[i];
                 const int s_loc = find_prev(sS, bSs, any8, e);
+                uint32_t len, o = prefix + i;
+                uint32_t b_lo;          // first position of the analysed range, from the plane window's first position (tile start - PL_PAD)
+                bool in_window = true;  // ... unless the range starts before it (a wrapped length)
                 uint64_t st;
-                uint32_t len;
                 if (s_loc >= 0) {
                     len = e - uint32_t(s_loc) + 1u;
-                    st = tile_gbase + uint32_t(s_loc);
-                } else {  // no START in the tile before it: the tile's carried END
+                    b_lo = uint32_t(s_loc) + PL_PAD;
+                    st = (p.global_off + uint64_t(t) * SC_T) + uint32_t(s_loc);
+                } else {  // no START in the tile before it: the tile's carried END (rank 0)
                     if (sh.adj) continue;  // the chunk's head (k_chunk_resolve writes it) / dropped by the exact test
-                    st = x_in - OPEN_BIAS;
+                    const uint64_t tile_gbase = p.global_off + uint64_t(t) * SC_T;
+                    st = sh.x_in - OPEN_BIAS;
                     len = uint32_t(tile_gbase + e - st + 1) & 0xffffu;
+                    in_window = st + PL_PAD >= tile_gbase;
+                    b_lo = uint32_t(st + PL_PAD - tile_gbase);
                 }
-                const uint32_t o = prefix + win + i - ((carried && s_loc >= 0) ? adj : 0u);
                 if (o < seg_room) {
-                    p.seg_start[seg_base + o] = st;
-                    p.seg_len[seg_base + o] = uint16_t(len);
+                    seg_start[o] = st;
+                    seg_len[o] = uint16_t(len);
                 } else {
                     p.res->overflow |= 1;
                 }
@@ -472,27 +491,30 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 if (len <= uint32_t(MAX_C_LEN)) atomicAdd(&sh.hist[len], 1u);
                 my_last_o = o;
                 my_last_len = len;
-                // BWT prefilter: the one-popcount bound (planes.cuh) on the analysed range [st, st + len) in the plane window; a
-                // record whose range starts before the window (a wrapped length) goes straight to the exact test
+                // BWT prefilter: the one-popcount bound (planes.cuh) on the analysed range [st, st + len) in the plane window, on
+                // 32-bit halves of the quads {plane 0 lo, hi, plane 1 lo, hi}; a record whose range starts before the window goes
+                // straight to the exact test
                 if (pf && len >= 2 * p.pf_mcov && len <= uint32_t(MAX_C_LEN)) {
                     bool pass = true;
-                    if (st + PL_PAD >= tile_gbase) {
-                        const uint32_t b_lo = uint32_t(st + PL_PAD - tile_gbase), b_last = b_lo + len - 1;
-                        const uint32_t q_lo = b_lo >> 6, q_last = b_last >> 6;
-                        unsigned long long f0 = 0, f1 = 0;
+                    if (in_window) {
+                        const uint32_t b_last = b_lo + len - 1;
+                        uint32_t h = b_lo >> 5;
+                        const uint32_t h_last = b_last >> 5;
+                        uint32_t addr = pf_win + (h >> 1) * 16u + (h & 1u) * 4u;
+                        uint32_t x0 = lds_u32(addr), x1 = lds_u32(addr + 8u);
+                        const uint32_t f0 = 0u - ((x0 >> (b_lo & 31u)) & 1u), f1 = 0u - ((x1 >> (b_lo & 31u)) & 1u);  // the first record's code
+                        uint32_t mask = FULL << (b_lo & 31u);
                         uint32_t others = 0;
-                        for (uint32_t q = q_lo; q <= q_last; ++q) {
-                            const uint4 pv = lds_u128(pf_win + q * 16u);
-                            const unsigned long long x0 = (uint64_t(pv.y) << 32) | pv.x, x1 = (uint64_t(pv.w) << 32) | pv.z;
-                            unsigned long long mask = ~0ull;
-                            if (q == q_lo) {
-                                mask = ~0ull << (b_lo & 63);
-                                f0 = 0ull - ((x0 >> (b_lo & 63)) & 1ull);
-                                f1 = 0ull - ((x1 >> (b_lo & 63)) & 1ull);
-                            }
-                            if (q == q_last) mask &= ~0ull >> (63 - (b_last & 63));
-                            others += __popcll(((x0 ^ f0) | (x1 ^ f1)) & mask);
+                        while (h < h_last) {
+                            others += __popc(((x0 ^ f0) | (x1 ^ f1)) & mask);
+                            ++h;
+                            addr += (h & 1u) ? 4u : 12u;
+                            x0 = lds_u32(addr);
+                            x1 = lds_u32(addr + 8u);
+                            mask = FULL;
                         }
+                        mask &= FULL >> (31u - (b_last & 31u));
+                        others += __popc(((x0 ^ f0) | (x1 ^ f1)) & mask);
                         pass = others >= p.pf_mcov;  // at least mcov records differ from the first one's base code
                     }
                     if (pass) {
@@ -740,6 +762,13 @@ cudaError_t launch_scan(const Scan8Params& p0, uint64_t alloc_r, cudaStream_t st
     if (!enc) return cudaErrorNotSupported;
     Scan8Params p = p0;
     p.num_tiles = uint32_t(scan_num_tiles(p.n_local));
+    const uint32_t kk = p.k > 128u ? 128u : p.k;  // values are <= 127: k >= 128 never matches
+    for (int b = 0; b < 7; ++b) p.km[b] = ((kk >> b) & 1u) ? 0xffffffffu : 0u;
+    p.km[7] = kk >= 128u ? 0xffffffffu : 0u;
+    // tiles [t_int_lo, t_int_hi) need none of the edge rules: not the first tile of the eBWT, wholly inside n_local, not
+    // the tile that holds position n_global - 1
+    p.t_int_lo = p.global_off == 0 ? 1u : 0u;
+    p.t_int_hi = p.global_off + p.n_local == p.n_global ? (p.num_tiles ? p.num_tiles - 1 : 0) : uint32_t(p.n_local / SC_T);
     // the bit-sliced LCP as rows of 256 bytes = one run of 32 words (8 rows per block of LCPT_BLOCK positions); the boxes
     // the kernel takes from it are 2 words x 8 runs: the plane words of the group before / after a tile
     CUtensorMap tmap;
