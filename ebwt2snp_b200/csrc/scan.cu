@@ -66,6 +66,7 @@ constexpr int SC_PF_BYTES = SC_PF_QUADS * 16;  // 4144
 constexpr int SC_PF_STRIDE = 4224;             // slot stride (128-byte multiple)
 constexpr int SC_DYN_SMEM = SC_STAGES * SC_STAGE_BYTES + SC_PSLOTS * SC_PF_STRIDE;
 constexpr int SC_CAP = 512;                    // kept ENDs per list window (a typical tile lists ~300)
+static_assert(SC_STAGES == 2, "stage = tile parity");
 static_assert(LCPT_BLOCK == 32 * SC_V && SC_T == SC_WARPS * LCPT_BLOCK, "one block of the bit-sliced LCP per warp");
 static_assert(SC_T <= (1 << 14), "tile-local positions fit 14 bits");
 
@@ -78,11 +79,11 @@ struct ScanShared {
     uint64_t x_in;                // open-cluster state entering the tile            (warp 0, between the barriers (A) and (B))
     uint32_t prefix;              // segment index of the record of the tile's kept END of rank 0 (one less when the carried END is not written)
     uint32_t adj;                 // bit 0: the carried END is not written by this tile; bit 1: it is the chunk's head
-    uint32_t open_after;          // (interior tiles) a cluster is open after the tile's last position
+    uint32_t open_after[2];       // (interior tiles) a cluster is open after the tile's last position; by tile parity (read after (B))
     uint32_t wsum[SC_WARPS];      // per warp: #kept ENDs | #ENDs << 16
     uint32_t bS[2][SC_WARPS];     // per warp: lanes whose START word is not empty (by tile parity, like sS)
     int wfe[SC_WARPS];            // first END of the warp (tile-local position), NO_POS = none
-    int wle[SC_WARPS];            // last END of the warp, -1 = none (tiles at the edges of the shard only)
+    int wle[2][SC_WARPS];         // last END of the warp, -1 = none (tiles at the edges of the shard only); by tile parity
     unsigned int hist[E2S_HIST_BINS];
     uint64_t sS[2][SC_THREADS];   // START words of the tile, by tile parity: read until the tile's records are out
     uint16_t e_ent[SC_CAP];       // tile-local positions of the kept ENDs, by rank
@@ -117,6 +118,10 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t lo, uint32_t hi) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
     return (uint64_t(__shfl_sync(FULL, uint32_t(v >> 32), src)) << 32) | __shfl_sync(FULL, uint32_t(v), src);
 }
@@ -127,12 +132,12 @@ __device__ __forceinline__ uint32_t lt_step(uint32_t x, uint32_t km, uint32_t lt
     asm("lop3.b32 %0, %1, %2, %3, 0x8E;" : "=r"(r) : "r"(x), "r"(km), "r"(lt));
     return r;
 }
-// nearest set bit at or before tile-local position e of a 16 384-bit mask kept as one 64-bit word per thread (words, as
-// 32-bit halves) plus, per warp, the ballot of the lanes whose word is not empty (bal) and the warps that have any (any8);
-// -1 = none
-__device__ __forceinline__ int find_prev(const uint2* words, const uint32_t* bal, uint32_t any8, uint32_t e) {
+// nearest set bit at or before tile-local position e of a 16 384-bit mask kept as one 64-bit word per thread (at the
+// shared-window address words) plus, per warp, the ballot of the lanes whose word is not empty (at bal) and the warps that
+// have any (any8); -1 = none
+__device__ __forceinline__ int find_prev(uint32_t words, uint32_t bal, uint32_t any8, uint32_t e) {
     uint32_t t = e >> 6;
-    uint2 v = words[t];
+    uint2 v = lds_u64(words + t * 8u);
     const uint32_t keep = FULL >> (31u - (e & 31u));
     if (e & 32u) v.y &= keep;
     else {
@@ -141,15 +146,15 @@ __device__ __forceinline__ int find_prev(const uint2* words, const uint32_t* bal
     }
     if (!(v.x | v.y)) {
         uint32_t w = t >> 5;
-        uint32_t bm = bal[w] & ((1u << (t & 31u)) - 1u);
+        uint32_t bm = lds_u32(bal + w * 4u) & ((1u << (t & 31u)) - 1u);
         if (!bm) {
             const uint32_t a8 = any8 & ((1u << w) - 1u);
             if (!a8) return -1;
             w = 31u - uint32_t(__clz(a8));
-            bm = bal[w];
+            bm = lds_u32(bal + w * 4u);
         }
         t = w * 32u + 31u - uint32_t(__clz(bm));
-        v = words[t];
+        v = lds_u64(words + t * 8u);
     }
     return int(t * 64u) + (v.y ? 63 - __clz(v.y) : 31 - __clz(v.x));
 }
@@ -161,6 +166,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
     __shared__ ScanShared sh;
     const uint32_t stage0 = smem_u32(smem_dyn);
     const uint32_t planes0 = stage0 + SC_STAGES * SC_STAGE_BYTES;
+    const uint32_t sS0 = smem_u32(&sh.sS[0][0]), bS0 = smem_u32(&sh.bS[0][0]);  // shared-window addresses of the double-buffered arrays
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool pf = p.pf_mcov != 0;
@@ -211,16 +217,15 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
     uint32_t my_last_o = 0xffffffffu;  // (per thread) segment-relative index and length of the last record I wrote
     uint32_t my_last_len = 0;
 
-    for (uint32_t it = 0; it < n_my; ++it) {
-        const int stage = it % SC_STAGES;
-        const uint32_t parity = (it / SC_STAGES) & 1;
-        const int pb = it & 1;
+    uint32_t pf_win = planes0;  // the tile's plane window: slot it % SC_PSLOTS
+    for (uint32_t it = 0; it < n_my; ++it, pf_win = pf_win == planes0 + (SC_PSLOTS - 1) * SC_PF_STRIDE ? planes0 : pf_win + SC_PF_STRIDE) {
+        const uint32_t pb = it & 1u;  // = stage (SC_STAGES == 2)
+        const uint32_t parity = (it >> 1) & 1u;
         const uint32_t t = t_lo + it;
-        const uint32_t sa = stage0 + uint32_t(stage) * SC_STAGE_BYTES + SC_EDGE;  // the tile's first byte; the edge boxes at sa - SC_EDGE and sa + SC_T
-        const uint32_t pf_win = planes0 + (it % SC_PSLOTS) * SC_PF_STRIDE;
+        const uint32_t sa = stage0 + pb * SC_STAGE_BYTES + SC_EDGE;  // the tile's first byte; the edge boxes at sa - SC_EDGE and sa + SC_T
         const bool interior = t >= p.t_int_lo && t < p.t_int_hi;
-        uint2* const sS = reinterpret_cast<uint2*>(sh.sS[pb]);
-        uint32_t* const bSs = sh.bS[pb];
+        const uint32_t sS_a = sS0 + pb * (SC_THREADS * 8u), bS_a = bS0 + pb * (SC_WARPS * 4u);
+        const int stage = int(pb);
 
         mbar_wait(&sh.full_bar[stage], parity);
 
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             const uint64_t Ep = (E << 1) | e_prev;
             S = G & (~Gp | Ep) & vm;
         }
-        sS[tid] = make_uint2(uint32_t(S), uint32_t(S >> 32));
+        sts_u64(sS_a + uint32_t(tid) * 8u, uint32_t(S), uint32_t(S >> 32));
 
         // ---- K = kept ENDs: E minus the ENDs of clusters shorter than min_len (a START at the same position or up to `spread`
         // positions before).  Before the tile: no START assumed -- the one END that can pair with a START of an earlier tile
@@ -330,11 +335,11 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             }
             if (lane == 31) sh.wsum[warp] = inc;
             if (lane == 0) {
-                bSs[warp] = bS;
+                sts_u32(bS_a + uint32_t(warp) * 4u, bS);
                 sh.wfe[warp] = fe;
             }
             if (interior) {  // a cluster is open after the tile iff its last position is inside one and not its END
-                if (tid == SC_THREADS - 1) sh.open_after = uint32_t((G & ~E) >> 63);
+                if (tid == SC_THREADS - 1) sh.open_after[pb] = uint32_t((G & ~E) >> 63);
             } else {         // (positions past n_local, the cleared END(n_global - 1): by the tile's last START / END)
                 int le = -1;
                 if (bE) {
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                     const uint64_t El = shfl64(E, src);
                     le = (warp * 32 + src) * SC_V + 63 - __clzll(El);
                 }
-                if (lane == 0) sh.wle[warp] = le;
+                if (lane == 0) sh.wle[pb][warp] = le;
             }
         }
         __syncthreads();  // (A) per-warp summaries, START words.  Every thread has this tile's words in registers: the stage is refilled
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         // my warp's rank offset, the tile's totals, the warps that have a START
         uint32_t baseK, nK, nE, any8;
         {
-            const uint32_t ws = sh.wsum[lane & (SC_WARPS - 1)], bq = bSs[lane & (SC_WARPS - 1)];
+            const uint32_t ws = sh.wsum[lane & (SC_WARPS - 1)], bq = lds_u32(bS_a + uint32_t(lane & (SC_WARPS - 1)) * 4u);
             const uint32_t tot = __reduce_add_sync(FULL, lane < SC_WARPS ? ws : 0u);
             const uint32_t base = (inc - pk) + __reduce_add_sync(FULL, lane < warp ? ws : 0u);
             any8 = __ballot_sync(FULL, bq != 0) & ((1u << SC_WARPS) - 1u);
@@ -360,31 +365,20 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             baseK = base & 0xffffu;
         }
 
-        // ---- warp 0: the tile's first / last events, the carried END, the chunk state
+        // ---- warp 0, before the barrier (B): the carried END and where the tile's records go
+        int t_fe = NO_POS;
         if (warp == 0) {
             const uint64_t tile_gbase = p.global_off + uint64_t(t) * SC_T;
             int t_fs = NO_POS;
             if (any8) {
                 const uint32_t w = uint32_t(__ffs(any8) - 1);
-                const uint32_t t2 = w * 32u + uint32_t(__ffs(bSs[w]) - 1);
-                t_fs = int(t2 * 64u) + __ffsll(sh.sS[pb][t2]) - 1;
+                const uint32_t t2 = w * 32u + uint32_t(__ffs(lds_u32(bS_a + w * 4u)) - 1);
+                const uint2 v = lds_u64(sS_a + t2 * 8u);
+                t_fs = int(t2 * 64u) + (v.x ? __ffs(v.x) - 1 : 31 + __ffs(v.y));
             }
-            const int t_ls = find_prev(sS, bSs, any8, SC_T - 1);
-            int t_fe = NO_POS;
 #pragma unroll
             for (int q = SC_WARPS - 1; q >= 0; --q)
                 if (sh.wfe[q] != NO_POS) t_fe = sh.wfe[q];
-            const bool has_event = t_ls >= 0 || t_fe != NO_POS;
-            bool open_after;
-            if (interior) {
-                open_after = sh.open_after != 0;
-            } else {
-                int t_le = -1;
-#pragma unroll
-                for (int q = 0; q < SC_WARPS; ++q)
-                    if (sh.wle[q] >= 0) t_le = sh.wle[q];
-                open_after = t_ls > t_le;
-            }
             // the tile's first event is an END: its START lies before the tile (a START and an END at the same position: the
             // START comes first, t_fe == t_fs is not carried)
             const bool carried = t_fe != NO_POS && t_fe < t_fs;
@@ -408,10 +402,6 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             }
             cnt += nK - adj;
             n_end += nE;
-            if (has_event) {
-                X = (open_after && t_ls >= 0) ? tile_gbase + uint64_t(t_ls) + OPEN_BIAS : (open_after ? X : OPEN_NONE);
-                seen = true;
-            }
         }
 
         // ---- scatter: the tile-local positions of my kept ENDs to their ranks (the list window by window of SC_CAP: one
@@ -450,11 +440,29 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 if (p.n_global - 2 - tile_gbase < uint64_t(SC_T)) {
                     const uint32_t e_loc = uint32_t(p.n_global - 2 - tile_gbase);
                     if (uint32_t(tid) == (e_loc >> 6) && ((E >> (e_loc & 63)) & 1u)) {
-                        const int s_loc = find_prev(sS, bSs, any8, e_loc);
+                        const int s_loc = find_prev(sS_a, bS_a, any8, e_loc);
                         if (s_loc >= 0) p.res->end_nm2_start = tile_gbase + uint64_t(s_loc) + 1;
                         else if (!(sh.adj & 2u)) p.res->end_nm2_start = sh.x_in >= OPEN_BIAS ? sh.x_in - OPEN_BIAS + 1 : ~0ull;
                         // (the chunk's head: k_chunk_resolve answers)
                     }
+                }
+            }
+            if (warp == 0 && win == 0) {  // the chunk state after this tile (off the other warps' path to the records)
+                const int t_ls = find_prev(sS_a, bS_a, any8, SC_T - 1);
+                bool open_after;
+                if (interior) {
+                    open_after = sh.open_after[pb] != 0;
+                } else {
+                    int t_le = -1;
+#pragma unroll
+                    for (int q = 0; q < SC_WARPS; ++q)
+                        if (sh.wle[pb][q] >= 0) t_le = sh.wle[pb][q];
+                    open_after = t_ls > t_le;
+                }
+                if (t_ls >= 0 || t_fe != NO_POS) {
+                    const uint64_t tile_gbase = p.global_off + uint64_t(t) * SC_T;
+                    X = (open_after && t_ls >= 0) ? tile_gbase + uint64_t(t_ls) + OPEN_BIAS : (open_after ? X : OPEN_NONE);
+                    seen = true;
                 }
             }
             if (nK == 0) break;
@@ -462,9 +470,11 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             const uint32_t prefix = sh.prefix + win;
             const uint32_t n_win = nK - win < uint32_t(SC_CAP) ? nK - win : uint32_t(SC_CAP);
             uint32_t bases32 = 0;
-            for (uint32_t i = tid; i < n_win; i += SC_THREADS) {
+            // entry -> lane: the first SC_THREADS entries in order, later rounds from the last thread down (warp 0 carries the chunk
+            // state: the extra rounds land on the warps that are ahead)
+            for (uint32_t i = uint32_t(tid), nxt = 2u * SC_THREADS - 1u - uint32_t(tid); i < n_win; i = nxt, nxt += SC_THREADS) {
                 const uint32_t e = sh.e_ent[i];
-                const int s_loc = find_prev(sS, bSs, any8, e);
+                const int s_loc = find_prev(sS_a, bS_a, any8, e);
                 uint32_t len, o = prefix + i;
                 uint32_t b_lo;          // first position of the analysed range, from the plane window's first position (tile start - PL_PAD)
                 bool in_window = true;  // ... unless the range starts before it (a wrapped length)
