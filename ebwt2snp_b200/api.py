@@ -79,7 +79,7 @@ class PipelineResult(C.Structure):
 # every symbol include/ebwt2snp_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
     "e2s_version", "e2s_ctx_create", "e2s_ctx_destroy", "e2s_last_error", "e2s_ctx_set_stream",
-    "e2s_ctx_synchronize", "e2s_ctx_launch_count", "e2s_ctx_timing", "e2s_ctx_kernel_time", "e2s_shard_create", "e2s_shard_destroy", "e2s_shard_load_gesa",
+    "e2s_ctx_synchronize", "e2s_ctx_launch_count", "e2s_ctx_timing", "e2s_ctx_kernel_time", "e2s_shard_create", "e2s_shard_destroy", "e2s_shard_load_gesa", "e2s_shard_load_gesa_fd",
     "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_build_egsa_dev", "e2s_build_egsa", "e2s_shard_set_layout", "e2s_shard_seal", "e2s_shard_lcp_bytes_resident", "e2s_reads_stage", "e2s_reads_stage_dev",
     "e2s_cluster_prefilter", "e2s_cluster_run", "e2s_cluster_merge", "e2s_cluster_finalize", "e2s_cluster_lm", "e2s_cluster_count",
     "e2s_cluster_fetch", "e2s_cluster_fetch_packed", "e2s_clusters_stage_packed", "e2s_clusters_stage",
@@ -119,6 +119,7 @@ def load_library():
     lib.e2s_shard_create.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
     lib.e2s_shard_destroy.argtypes = [C.c_void_p]
     lib.e2s_shard_load_gesa.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
+    lib.e2s_shard_load_gesa_fd.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
     lib.e2s_shard_load_soa.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64]
     lib.e2s_shard_load_soa_dev.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64]
     lib.e2s_shard_seal.argtypes = [C.c_void_p]
@@ -462,6 +463,10 @@ class Shard:
             count = records.nbytes // rs if isinstance(records, np.ndarray) else records.numel() * records.element_size() // rs
         self.ctx._ck(self.lib.e2s_shard_load_gesa(self.h, _ptr(records), int(first), int(count), x, y, z))
         self.ctx.synchronize()
+
+    def load_gesa_fd(self, fd, first, count, x=4, y=4, z=4):
+        """records [first, first + count) of the X.gesa file open at the descriptor fd (pinned ring + reader threads)"""
+        self.ctx._ck(self.lib.e2s_shard_load_gesa_fd(self.h, int(fd), int(first), int(count), x, y, z))
 
     def load_soa(self, lcp, text, suff, bwt, first=0, device=False):
         count = len(lcp) if lcp is not None else len(bwt)

@@ -9,8 +9,11 @@
 #include <time.h>
 
 #include <dlfcn.h>
+#include <unistd.h>
 
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -38,6 +41,10 @@ struct e2s_ctx {
     size_t raw_cap = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_unpacked[2] = {nullptr, nullptr}, ev_start = nullptr;
+    // e2s_shard_load_gesa_fd: ring of pinned pieces the reader threads fill from the file
+    uint8_t* pin_ring = nullptr;
+    size_t pin_piece = 0;  // bytes per slot
+    cudaEvent_t ev_slot[4] = {nullptr, nullptr, nullptr, nullptr};
     // cached shard for e2s_pipeline_host
     e2s_shard* cached = nullptr;
     KernelTimer timer;
@@ -230,6 +237,9 @@ void e2s_ctx_destroy(e2s_ctx* c) {
         if (c->ev_unpacked[i]) cudaEventDestroy(c->ev_unpacked[i]);
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
+    for (int i = 0; i < 4; ++i)
+        if (c->ev_slot[i]) cudaEventDestroy(c->ev_slot[i]);
+    if (c->pin_ring) cudaFreeHost(c->pin_ring);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -515,6 +525,128 @@ int e2s_shard_load_gesa(e2s_shard* s, const void* records, uint64_t first, uint6
         c->launches += 2;
     }
     s->sealed = false;
+    return E2S_OK;
+}
+
+// The same straight from the file (what egsa_stream does, ref:include.hpp:42-81,120-155, instead of one istream::read per
+// field): reader threads pread() pieces of the file into a ring of pinned buffers while the copy engine moves the pieces
+// before them and the de-interleave kernel unpacks the ones before those.  Record i of the file = global position i.
+int e2s_shard_load_gesa_fd(e2s_shard* s, int fd, uint64_t first, uint64_t count, int x, int y, int z) {
+    if (!s || fd < 0) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_shard_load_gesa_fd: bad argument");
+    e2s_ctx* c = s->ctx;
+    auto ok = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8; };
+    if (!ok(x) || !ok(y) || !ok(z)) return fail(c, E2S_ERR_ARG, "field byte sizes must be 1, 2, 4 or 8");
+    CU(c, cudaSetDevice(c->device));
+    uint64_t lo, hi;
+    keep_range(s, &lo, &hi);
+    const uint64_t a = first > lo ? first : lo, b = first + count < hi ? first + count : hi;
+    if (a >= b) return E2S_OK;
+    s->lay_x = x; s->lay_y = y; s->lay_z = z; s->lay_bcr = 0;
+    const int rs = x + y + z + 1;
+    constexpr int R = 4;                          // pinned slots
+    const uint64_t piece = uint64_t(1) << 20;     // records per piece (multiple of 16)
+    const size_t piece_bytes = size_t(piece) * rs + 64;
+    if (c->pin_piece < piece_bytes) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        if (c->pin_ring) cudaFreeHost(c->pin_ring);
+        c->pin_ring = nullptr;
+        c->pin_piece = 0;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&c->pin_ring), piece_bytes * R, cudaHostAllocDefault) != cudaSuccess)
+            return fail(c, E2S_ERR_NOMEM, "pinned read ring");
+        c->pin_piece = piece_bytes;
+    }
+    if (piece_bytes > c->raw_cap) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(c->d_raw[i]);
+            c->d_raw[i] = nullptr;
+        }
+        c->raw_cap = 0;
+        for (int i = 0; i < 2; ++i)
+            if (cudaMalloc(reinterpret_cast<void**>(&c->d_raw[i]), piece_bytes) != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "raw staging buffer");
+        c->raw_cap = piece_bytes;
+    }
+    if (!c->copy_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&c->ev_unpacked[i], cudaEventDisableTiming));
+        }
+        CU(c, cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+    }
+    for (int i = 0; i < R; ++i)
+        if (!c->ev_slot[i]) CU(c, cudaEventCreateWithFlags(&c->ev_slot[i], cudaEventDisableTiming));
+    CU(c, cudaEventRecord(c->ev_start, c->stream));
+    CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
+
+    const uint64_t n_pieces = (b - a + piece - 1) / piece;
+    std::atomic<int64_t> filled(-1), recorded(-1);  // last piece read from the file / last piece whose copy has been enqueued
+    std::atomic<int> stop(0), read_err(0);
+    int env_threads = 6;
+    if (const char* e = getenv("E2S_READ_THREADS")) env_threads = atoi(e) > 0 ? atoi(e) : 6;
+    const int T = env_threads > 16 ? 16 : env_threads;
+    const int device = c->device;
+    std::thread filler([&]() {
+        cudaSetDevice(device);
+        for (uint64_t p = 0; p < n_pieces && !stop.load(); ++p) {
+            const int slot = int(p % R);
+            if (p >= uint64_t(R)) {  // the copy that last read this slot must be over
+                while (recorded.load(std::memory_order_acquire) < int64_t(p) - R && !stop.load()) std::this_thread::yield();
+                if (stop.load()) break;
+                cudaEventSynchronize(c->ev_slot[slot]);
+            }
+            const uint64_t p0 = a + p * piece, cnt = b - p0 < piece ? b - p0 : piece;
+            uint8_t* dst = c->pin_ring + size_t(slot) * c->pin_piece;
+            const size_t bytes = size_t(cnt) * rs;
+            const off_t off0 = off_t(p0) * rs;
+            auto part = [&](int t) {  // thread t of T: its share of the piece, 4 KB granules
+                size_t lo_b = (bytes * size_t(t) / size_t(T)) & ~size_t(4095), hi_b = t + 1 == T ? bytes : (bytes * size_t(t + 1) / size_t(T)) & ~size_t(4095);
+                while (lo_b < hi_b) {
+                    const ssize_t got = pread(fd, dst + lo_b, hi_b - lo_b, off0 + off_t(lo_b));
+                    if (got <= 0) {
+                        read_err.store(1);
+                        return;
+                    }
+                    lo_b += size_t(got);
+                }
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < T; ++t) th.emplace_back(part, t);
+            part(0);
+            for (auto& w : th) w.join();
+            filled.store(int64_t(p), std::memory_order_release);
+            if (read_err.load()) break;
+        }
+    });
+    int rc = E2S_OK;
+    cudaError_t ce = cudaSuccess;
+    for (uint64_t p = 0; p < n_pieces && ce == cudaSuccess; ++p) {
+        while (filled.load(std::memory_order_acquire) < int64_t(p) && !read_err.load()) std::this_thread::yield();
+        if (read_err.load()) {
+            rc = E2S_ERR_ARG;
+            break;
+        }
+        const int slot = int(p % R), buf = int(p & 1);
+        const uint64_t p0 = a + p * piece, cnt = b - p0 < piece ? b - p0 : piece;
+        if (p >= 2) ce = cudaStreamWaitEvent(c->copy_stream, c->ev_unpacked[buf], 0);  // the kernel that read this device buffer is done
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(c->d_raw[buf], c->pin_ring + size_t(slot) * c->pin_piece, size_t(cnt) * rs, cudaMemcpyHostToDevice, c->copy_stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(c->ev_copied[buf], c->copy_stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(c->ev_slot[slot], c->copy_stream);
+        recorded.store(int64_t(p), std::memory_order_release);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0);
+        const int64_t l = int64_t(p0) - int64_t(s->global_off);  // local index, may be negative (left context)
+        if (ce == cudaSuccess) ce = launch_unpack_gesa(c->d_raw[buf], cnt, x, y, z, s->lcp + l, s->text + l, s->suff + l, s->bwt + l, c->stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(c->ev_unpacked[buf], c->stream);
+        if (ce == cudaSuccess) ce = derive_loaded(s, l, cnt, true, true);
+        c->launches += 2;
+    }
+    stop.store(1);
+    filler.join();
+    // the ring is reused by the next call: its last copies must have left it
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->copy_stream);
+    s->sealed = false;
+    if (ce != cudaSuccess) return cuda_fail(c, ce, "e2s_shard_load_gesa_fd");
+    if (rc) return fail(c, rc, "e2s_shard_load_gesa_fd: short read from the index file");
     return E2S_OK;
 }
 

@@ -501,30 +501,34 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 if (len <= uint32_t(MAX_C_LEN)) atomicAdd(&sh.hist[len], 1u);
                 my_last_o = o;
                 my_last_len = len;
-                // BWT prefilter: the one-popcount bound (planes.cuh) on the analysed range [st, st + len) in the plane window, on
-                // 32-bit halves of the quads {plane 0 lo, hi, plane 1 lo, hi}; a record whose range starts before the window goes
+                // BWT prefilter: the one-popcount bound (planes.cuh) on the analysed range [st, st + len) in the plane window, one
+                // quad {plane 0 lo, hi, plane 1 lo, hi} = 64 positions per step; a record whose range starts before the window goes
                 // straight to the exact test
                 if (pf && len >= 2 * p.pf_mcov && len <= uint32_t(MAX_C_LEN)) {
                     bool pass = true;
                     if (in_window) {
                         const uint32_t b_last = b_lo + len - 1;
-                        uint32_t h = b_lo >> 5;
-                        const uint32_t h_last = b_last >> 5;
-                        uint32_t addr = pf_win + (h >> 1) * 16u + (h & 1u) * 4u;
-                        uint32_t x0 = lds_u32(addr), x1 = lds_u32(addr + 8u);
-                        const uint32_t f0 = 0u - ((x0 >> (b_lo & 31u)) & 1u), f1 = 0u - ((x1 >> (b_lo & 31u)) & 1u);  // the first record's code
-                        uint32_t mask = FULL << (b_lo & 31u);
+                        uint32_t q = b_lo >> 6;
+                        const uint32_t q_last = b_last >> 6;
+                        uint32_t addr = pf_win + q * 16u;
+                        uint4 pv = lds_u128(addr);  // {plane 0 lo, hi, plane 1 lo, hi} of 64 positions
+                        const uint32_t s5 = b_lo & 31u;
+                        const bool s_hi = (b_lo & 32u) != 0;
+                        const uint32_t f0 = 0u - (((s_hi ? pv.y : pv.x) >> s5) & 1u), f1 = 0u - (((s_hi ? pv.w : pv.z) >> s5) & 1u);  // the first record's code
+                        uint32_t mlo = s_hi ? 0u : FULL << s5, mhi = s_hi ? FULL << s5 : FULL;
                         uint32_t others = 0;
-                        while (h < h_last) {
-                            others += __popc(((x0 ^ f0) | (x1 ^ f1)) & mask);
-                            ++h;
-                            addr += (h & 1u) ? 4u : 12u;
-                            x0 = lds_u32(addr);
-                            x1 = lds_u32(addr + 8u);
-                            mask = FULL;
+                        while (q < q_last) {
+                            others += __popc(((pv.x ^ f0) | (pv.z ^ f1)) & mlo) + __popc(((pv.y ^ f0) | (pv.w ^ f1)) & mhi);
+                            ++q;
+                            addr += 16u;
+                            pv = lds_u128(addr);
+                            mlo = mhi = FULL;
                         }
-                        mask &= FULL >> (31u - (b_last & 31u));
-                        others += __popc(((x0 ^ f0) | (x1 ^ f1)) & mask);
+                        const uint32_t e5 = 31u - (b_last & 31u);
+                        const bool e_hi = (b_last & 32u) != 0;
+                        mlo &= e_hi ? FULL : FULL >> e5;
+                        mhi &= e_hi ? FULL >> e5 : 0u;
+                        others += __popc(((pv.x ^ f0) | (pv.z ^ f1)) & mlo) + __popc(((pv.y ^ f0) | (pv.w ^ f1)) & mhi);
                         pass = others >= p.pf_mcov;  // at least mcov records differ from the first one's base code
                     }
                     if (pass) {

@@ -115,12 +115,14 @@ int main(int argc, char** argv) {
         }
         rcut[size_t(g)] = lo;
     }
+    host::stamp("index + .clusters opened");
     host::Reads reads;
     if (!reads.load(input)) {
         std::cerr << "clust2snp: cannot read " << input << std::endl;
         return 2;
     }
 
+    host::stamp("FASTA parsed");
     std::vector<e2s_ctx*> ctx(size_t(G), nullptr);
     std::vector<e2s_shard*> sh(size_t(G), nullptr);
     std::vector<e2s_stats> stats(static_cast<size_t>(G));
@@ -134,12 +136,14 @@ int main(int argc, char** argv) {
     auto stage = [&](int g) {
         int r = e2s_ctx_create(g, &ctx[size_t(g)]);
         if (r) return fail_of(g, r);
+        if (g == 0) host::stamp("context created");
         const uint64_t lo = cuts[size_t(g)], hi = cuts[size_t(g) + 1];
         r = e2s_shard_create(ctx[size_t(g)], hi - lo, lo, idx.n, &sh[size_t(g)]);
         const uint64_t a = lo >= 2 ? lo - 2 : 0, b = hi + E2S_MAX_C_LEN + 1 < idx.n ? hi + E2S_MAX_C_LEN + 1 : idx.n;
         if (!r) r = idx.load(sh[size_t(g)], a, b - a);
         if (!r) r = e2s_shard_set_layout(sh[size_t(g)], idx.x, idx.y, idx.z, idx.bcr ? 1 : 0);
         if (!r) r = e2s_shard_seal(sh[size_t(g)]);
+        if (g == 0) host::stamp("index loaded + sealed");
         if (!r) r = e2s_clusters_stage_packed(sh[size_t(g)], cl.data + rcut[size_t(g)] * 10, rcut[size_t(g) + 1] - rcut[size_t(g)]);
         if (!r) r = e2s_statistics(sh[size_t(g)], &stats[size_t(g)]);
         if (!r) r = e2s_reads_stage(ctx[size_t(g)], reads.bases.data(), reads.off.data(), reads.n_reads());
@@ -150,6 +154,7 @@ int main(int argc, char** argv) {
         for (int g = 0; g < G; ++g) th.emplace_back(stage, g);
         for (auto& t : th) t.join();
     }
+    host::stamp(".clusters + reads staged, statistics");
     for (int g = 0; g < G; ++g)
         if (rc[size_t(g)]) {
             std::cerr << "clust2snp: GPU " << g << ": " << errs[size_t(g)] << std::endl;
@@ -209,6 +214,7 @@ int main(int argc, char** argv) {
         n_cand += counts[size_t(g)].n_candidates;
         saw_n |= counts[size_t(g)].saw_n != 0;
     }
+    host::stamp("find_events done");
     std::cout << " 100% done." << std::endl;
     std::cout << "Done. " << n_cand << " potential variants detected (some might be detected twice: on fw and rev strands)" << std::endl;
     if (saw_n)
@@ -247,11 +253,14 @@ int main(int argc, char** argv) {
         next_id += counts[size_t(g)].n_events;
     }
     fclose(out);
+    host::stamp(".snp written");
     std::cout << " 100% done." << std::endl;
+    std::cout << "Done. " << std::endl;
+    host::quick_exit_unless_asked(0);  // (everything is on disk: skip the teardown of the CUDA contexts unless E2S_CLI_CLEAN_EXIT is set)
     for (int g = 0; g < G; ++g) {
         e2s_shard_destroy(sh[size_t(g)]);
         e2s_ctx_destroy(ctx[size_t(g)]);
     }
-    std::cout << "Done. " << std::endl;
+    host::stamp("contexts destroyed");
     return 0;
 }

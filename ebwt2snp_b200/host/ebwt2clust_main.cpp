@@ -27,6 +27,7 @@ static void help() {
 }
 
 int main(int argc, char** argv) {
+    host::stamp("start");
     if (argc < 2) help();
     int k = 0, min_len = 0, lcp = 0, da = 0, pos = 0;
     std::string input;
@@ -57,6 +58,7 @@ int main(int argc, char** argv) {
         return 1;
     }
     std::cout << "This is ebwt2clust. Input file: " << input << std::endl;
+    host::stamp("index opened");
     auto ok = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8; };
     if (!ok(lcp) || !ok(da) || !ok(pos)) {
         std::cerr << "ebwt2clust: -x/-y/-z must be 1, 2, 4 or 8" << std::endl;
@@ -106,6 +108,7 @@ int main(int argc, char** argv) {
     auto work = [&](int g) {
         int r = e2s_ctx_create(g, &ctx[size_t(g)]);
         if (r) { rc[size_t(g)] = r; errs[size_t(g)] = e2s_last_error(nullptr); return; }
+        if (g == 0) host::stamp("context created");
         const uint64_t lo = cuts[size_t(g)], hi = cuts[size_t(g) + 1];
         bool fall_back = min_len > 33;
         if (!fall_back) {
@@ -145,6 +148,7 @@ int main(int argc, char** argv) {
         for (int g = 0; g < G; ++g) th.emplace_back(work, g);
         for (auto& t : th) t.join();
     }
+    host::stamp("loaded + scanned, records on the host");
     for (int g = 0; g < G; ++g)
         if (rc[size_t(g)]) {
             std::cerr << "ebwt2clust: GPU " << g << ": " << errs[size_t(g)] << std::endl;
@@ -182,11 +186,14 @@ int main(int argc, char** argv) {
         n_clust_out = mg.n_clust_out;
     }
     fclose(out);
+    host::stamp(".clusters written");
+    // the reference counts closures in an unsigned int (ref:ebwt2clust.cpp:88,137)
+    std::cout << "Done. " << static_cast<unsigned int>(n_clust_out) << " clusters saved to output file." << std::endl;
+    host::quick_exit_unless_asked(0);  // (everything is on disk: skip the teardown of the CUDA contexts unless E2S_CLI_CLEAN_EXIT is set)
     for (int g = 0; g < G; ++g) {
         e2s_shard_destroy(sh[size_t(g)]);
         e2s_ctx_destroy(ctx[size_t(g)]);
     }
-    // the reference counts closures in an unsigned int (ref:ebwt2clust.cpp:88,137)
-    std::cout << "Done. " << static_cast<unsigned int>(n_clust_out) << " clusters saved to output file." << std::endl;
+    host::stamp("contexts destroyed");
     return 0;
 }

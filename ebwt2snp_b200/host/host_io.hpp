@@ -13,6 +13,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -78,6 +79,9 @@ struct Index {
     int load(e2s_shard* sh, uint64_t first, uint64_t count) const {
         if (count == 0) return E2S_OK;
         if (egsa) {
+            // straight from the file through the library's pinned ring (E2S_CLI_MMAP=1: hand the mapping over instead -- pageable copies)
+            static const bool use_map = getenv("E2S_CLI_MMAP") != nullptr;
+            if (!use_map) return e2s_shard_load_gesa_fd(sh, gesa.fd, first, count, x, y, z);
             const size_t rs = size_t(x + y + z + 1);
             return e2s_shard_load_gesa(sh, gesa.data + first * rs, first, count, x, y, z);
         }
@@ -99,6 +103,24 @@ struct Index {
         return E2S_OK;
     }
 };
+
+// E2S_CLI_TIMING=1: wall-clock stamps of the CLI's phases on stderr (seconds since the first stamp)
+inline void stamp(const char* what) {
+    static const bool on = getenv("E2S_CLI_TIMING") != nullptr;
+    if (!on) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    const double t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[e2s timing] %8.3f s  %s\n", t, what);
+}
+
+// A CLI whose outputs are on disk has nothing left to do: tearing the CUDA contexts down costs 50-200 ms of wall time per process.
+inline void quick_exit_unless_asked(int code) {
+    if (getenv("E2S_CLI_CLEAN_EXIT")) return;
+    stamp("exit");
+    fflush(stdout);
+    fflush(stderr);
+    _exit(code);
+}
 
 // contiguous, nearly equal shards; every shard has >= 2 positions
 inline std::vector<uint64_t> shard_cuts(uint64_t n, int parts) {

@@ -87,6 +87,10 @@ void e2s_shard_destroy(e2s_shard *sh);
  * [global_off - 2, global_off + n_local + E2S_MAX_C_LEN + 1) and ignores the rest.
  * The copy is H2D of the raw bytes followed by a de-interleave kernel. */
 int e2s_shard_load_gesa(e2s_shard *sh, const void *records, uint64_t first, uint64_t count, int x, int y, int z);
+/* The same straight from an open X.gesa file (record i at byte i * (x + y + z + 1) = global position i): what egsa_stream does
+ * with one istream::read per field (ref:include.hpp:42-81,120-155).  Reader threads (E2S_READ_THREADS, default 6) pread()
+ * pieces into a pinned ring while earlier pieces are copied and de-interleaved. */
+int e2s_shard_load_gesa_fd(e2s_shard *sh, int fd, uint64_t first, uint64_t count, int x, int y, int z);
 
 /* Host structure-of-arrays (BCR-like: ref:include.hpp:157-188).  Arrays may be NULL to skip a field. */
 int e2s_shard_load_soa(e2s_shard *sh, const uint32_t *lcp, const uint32_t *text, const uint32_t *suff,

@@ -137,3 +137,37 @@ def test_chunked_needs_byte_lcp(ctx):
     rec10 = np.empty((len(es) + 16) * 10, dtype=np.uint8)
     res = ctx.pipeline_host(rec, n, rs.reads.reshape(-1), off, p, 16, 2, rec10=rec10)
     assert res.n_written == len(es) and rec10[: len(es) * 10].tobytes() == O.clusters_to_bytes(es, el)
+
+
+def test_load_gesa_from_file_descriptor(ctx, tmp_path, monkeypatch):
+    """e2s_shard_load_gesa_fd: the index straight from the file through the pinned ring (several pieces, 3 reader threads), whole
+    range and a sub-range with halos, against the oracle"""
+    import os
+    rs, e = H.dataset("small", 2)
+    n = e["n"]
+    rec = synth.gesa_records(e).view(np.uint8).reshape(-1)
+    path = tmp_path / "x.gesa"
+    rec.tofile(path)
+    monkeypatch.setenv("E2S_READ_THREADS", "3")
+    k, m = 16, 2
+    es, el, enc, _ = O.cluster_lm(e["lcp"], e["bwt"], k, m)
+    fd = os.open(path, os.O_RDONLY)
+    try:
+        sh = ctx.shard(n, 0, n)
+        sh.load_gesa_fd(fd, 0, n)
+        sh.seal()
+        nw, nc = sh.cluster_lm(k, m)
+        s, l = sh.cluster_fetch()
+        assert nc & 0xFFFFFFFF == enc and nw == len(es) and np.array_equal(s, es) and np.array_equal(l, el)
+        sh.close()
+        lo, hi = n // 3 + 5, 2 * n // 3 + 11
+        sh = ctx.shard(hi - lo, lo, n)
+        sh.load_gesa_fd(fd, 0, n)  # (the shard keeps its range + halos)
+        sh.seal()
+        sm = sh.cluster_run(k, m)
+        s2, l2 = sh.cluster_fetch()
+        want, ws, wl = H.emulate_shard(e["lcp"], e["bwt"], lo, hi, k, m)
+        assert np.array_equal(s2, ws) and np.array_equal(l2, wl) and sm.n_end == want.n_end
+        sh.close()
+    finally:
+        os.close(fd)
