@@ -36,6 +36,7 @@ struct e2s_ctx {
     uint64_t n_reads = 0, n_bases = 0;
     uint64_t reads_cap_bases = 0, reads_cap_off = 0;
     bool reads_owned = false;
+    uint32_t* d_reads_flag = nullptr;  // != 0: the staged reads hold a byte outside ACGTacgt (launch_reads_check)
     // staging: two raw-record buffers, the H2D copies run on their own stream ahead of the de-interleave kernels
     uint8_t* d_raw[2] = {nullptr, nullptr};
     size_t raw_cap = 0;
@@ -232,6 +233,7 @@ void e2s_ctx_destroy(e2s_ctx* c) {
     }
     cudaFree(c->d_raw[0]);
     cudaFree(c->d_raw[1]);
+    cudaFree(c->d_reads_flag);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_unpacked[i]) cudaEventDestroy(c->ev_unpacked[i]);
@@ -773,6 +775,15 @@ int e2s_shard_seal(e2s_shard* s) {
 
 int e2s_shard_lcp_bytes_resident(const e2s_shard* s) { return s ? (s->sealed && s->lcpt_ok ? 1 : 4) : 0; }
 
+// one pass over the staged reads: does any byte fall outside ACGTacgt?  (K4's consensus then needs base_to_int's general rule)
+static int reads_check(e2s_ctx* c) {
+    if (!c->d_reads_flag && cudaMalloc(reinterpret_cast<void**>(&c->d_reads_flag), 4) != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "reads flag");
+    CU(c, cudaMemsetAsync(c->d_reads_flag, 0, 4, c->stream));
+    CU(c, launch_reads_check(c->d_bases, c->n_bases, c->d_reads_flag, c->stream, c->sm_count));
+    ++c->launches;
+    return E2S_OK;
+}
+
 int e2s_reads_stage(e2s_ctx* c, const uint8_t* bases, const uint64_t* off, uint64_t n_reads) {
     if (!c || !bases || !off) return fail(c, E2S_ERR_ARG, "e2s_reads_stage: NULL argument");
     CU(c, cudaSetDevice(c->device));
@@ -796,7 +807,7 @@ int e2s_reads_stage(e2s_ctx* c, const uint8_t* bases, const uint64_t* off, uint6
     CU(c, cudaMemcpyAsync(c->d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     c->n_reads = n_reads;
     c->n_bases = nb;
-    return E2S_OK;
+    return reads_check(c);
 }
 
 int e2s_reads_stage_dev(e2s_ctx* c, const uint8_t* d_bases, const uint64_t* d_off, uint64_t n_reads, uint64_t n_bases) {
@@ -811,7 +822,7 @@ int e2s_reads_stage_dev(e2s_ctx* c, const uint8_t* d_bases, const uint64_t* d_of
     c->d_off = const_cast<uint64_t*>(d_off);
     c->n_reads = n_reads;
     c->n_bases = n_bases;
-    return E2S_OK;
+    return reads_check(c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1627,6 +1638,7 @@ int e2s_find_events(e2s_shard* s, const e2s_snp_params* p, int max_clust_length,
     a.planes = s->d_planes;
     a.n_local = s->n_local;
     a.global_off = s->global_off;
+    a.reads_flag = s->ctx->d_reads_flag;
     // K2 already ran the BWT prefilter for this -m (fused mode): its survivors + the records adopted from the merge
     // (which K2 did not see) replace K3a
     const SurvEntry* pre_list = nullptr;
@@ -1807,6 +1819,7 @@ static int pipeline_step(e2s_shard* s, e2s_comm* cm, uint32_t k, int32_t min_len
     a.planes = s->d_planes;
     a.n_local = s->n_local;
     a.global_off = s->global_off;
+    a.reads_flag = s->ctx->d_reads_flag;
     a.cl_start = nullptr;  // (phase 2 starts from the survivor list: the record list is not walked)
     a.cl_len = nullptr;
     a.m = 0;
@@ -1969,7 +1982,7 @@ int e2s_pipeline_resident(e2s_shard* s, uint32_t k, int32_t min_len, const e2s_s
         res->n_written = mg.total_written;
         res->n_clust_out = mg.n_clust_out;
         res->max_clust_length = st.max_clust_length;
-        res->d2h_bytes += res->snp.n_candidates * 128;
+        res->d2h_bytes += res->snp.n_candidates * snp_event_stride(s->work);
         return E2S_OK;
     }
     rc = e2s_cluster_lm(s, k, min_len, &res->n_written, &res->n_clust_out);
@@ -1983,7 +1996,7 @@ int e2s_pipeline_resident(e2s_shard* s, uint32_t k, int32_t min_len, const e2s_s
     }
     res->max_clust_length = st.max_clust_length;
     if ((rc = e2s_find_events(s, p, st.max_clust_length, &res->snp))) return rc;
-    res->d2h_bytes += res->snp.n_candidates * 128;
+    res->d2h_bytes += res->snp.n_candidates * snp_event_stride(s->work);
     return E2S_OK;
 }
 
@@ -2243,7 +2256,7 @@ int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, in
     }
     res->max_clust_length = st.max_clust_length;
     if ((rc = e2s_find_events(s, p, st.max_clust_length, &res->snp))) return rc;
-    res->d2h_bytes += res->snp.n_candidates * 128;
+    res->d2h_bytes += res->snp.n_candidates * snp_event_stride(s->work);
     if (events) {
         uint64_t nv = 0;
         if ((rc = e2s_events_fetch(s, events, cap_events, &nv))) return rc;
@@ -2342,7 +2355,7 @@ int e2s_pipeline_host_sharded(e2s_ctx* c, e2s_comm* cm, const void* records, uin
     res->n_clust_out = merged->n_clust_out;
     res->max_clust_length = stats->max_clust_length;
     if ((rc = e2s_find_events(s, p, stats->max_clust_length, &res->snp))) return rc;
-    res->d2h_bytes += res->snp.n_candidates * 128;
+    res->d2h_bytes += res->snp.n_candidates * snp_event_stride(s->work);
     if (events) {
         uint64_t nv = 0;
         if ((rc = e2s_events_fetch(s, events, cap_events, &nv))) return rc;

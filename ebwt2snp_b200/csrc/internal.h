@@ -218,7 +218,7 @@ struct SnpDev {  // device counters of one e2s_find_events
     unsigned long long unsorted;
     unsigned long long n_variants;   // candidates with supp0 > 0 and supp1 > 0
     unsigned long long n_events;     // of those, D <= max_snvs
-    unsigned long long pad[1];
+    unsigned long long compact;      // K4 wrote the compact event records (reads hold nothing but upper-case ACGT, k_left / k_right <= 32)
 };
 
 struct SnpArrays {
@@ -231,6 +231,7 @@ struct SnpArrays {
     const uint64_t* cl_start;  // global starts, sorted
     const uint16_t* cl_len;
     uint64_t m;
+    const uint32_t* reads_flag = nullptr;  // device word written when the reads were staged: != 0 = a base outside ACGTacgt (null: unknown)
 };
 
 struct CandSlot {  // one (flagged cluster, allele pair) slot written by K3b
@@ -269,6 +270,9 @@ struct CaptureParams {
 };
 cudaError_t launch_capture(const CaptureParams& p, cudaStream_t stream, int sm_count);
 
+// *flag |= 1 when one of the n bytes is not in ACGTacgt (K4 then keeps base_to_int's "anything else counts as A" path)
+cudaError_t launch_reads_check(const uint8_t* d_bases, uint64_t n, uint32_t* flag, cudaStream_t stream, int sm_count);
+
 struct SnpWork;  // opaque scratch owned by the shard (snp.cu)
 SnpWork* snp_work_create();
 void snp_work_destroy(SnpWork* w);
@@ -286,5 +290,6 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
 // the counters of the last snp_run (valid after the stream has been synchronised); false: a capacity guess was too small
 bool snp_collect(SnpWork* w, e2s_snp_counts* counts, const char** err, cudaError_t* rc);
 cudaError_t snp_fetch_events(SnpWork* w, e2s_event* host, uint64_t cap, uint64_t* n, cudaStream_t stream);
+uint32_t snp_event_stride(const SnpWork* w);  // bytes per candidate K4 wrote to pinned host memory in the last pass
 
 }  // namespace e2s

@@ -206,7 +206,11 @@ struct ExactParams {
 };
 
 __global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
-    const int lane = threadIdx.x & 31;
+    // Appending to the flagged list: ONE atomic per block and round (tens of thousands of same-address atomics, one per
+    // cluster, were what the kernel's time consisted of: ~2 ns each, serialised in L2)
+    __shared__ uint32_t s_wcnt[EX_THREADS / 32];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane & (EX_G - 1);
     const uint32_t gmask = ((1u << EX_G) - 1u) << (lane & ~(EX_G - 1));
     const uint64_t n_avail = p.n_list ? *p.n_list : p.n_list_host;
@@ -214,44 +218,67 @@ __global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
     const uint64_t groups = uint64_t(gridDim.x) * (EX_THREADS / EX_G);
     const uint32_t max_len = p.d_max_len ? uint32_t(*p.d_max_len) : p.max_len;
     uint32_t saw_n = 0;
-    for (uint64_t i = (uint64_t(blockIdx.x) * EX_THREADS + threadIdx.x) / EX_G; i < n_list; i += groups) {
-        const SurvEntry ent = p.list[i];
-        const uint64_t lp = ent.base;
-        const uint32_t len = ent.len;
-        if (len < p.min_len || len > max_len) continue;  // group-uniform
-        // The scan's prefilter only dropped clusters without any base-code change; where the shard's bit planes are at hand the
-        // one-popcount bound (planes.cuh) drops those that cannot have two frequent codes before their records are read
-        if (p.a.planes && lp + len <= p.a.n_local + MAX_C_LEN + 1 && !frequent_bound(p.a.planes, int64_t(lp), len, p.mcov)) continue;
-        unsigned long long acc = 0, best = 0;
-        for (uint32_t j = gl; j < len; j += EX_G) {
-            const uint32_t tx = p.a.text[lp + j];
-            const uint32_t lc = p.a.lcp[lp + j];
-            const uint32_t b = p.a.bwt[lp + j];
-            const uint32_t sample = (tx >= p.nr1_lo) & (p.nr1_big ^ 1u);
-            saw_n |= is_n(b);
-            acc += 1ull << (8 * (sample * 4 + base_code(b)));
-            const unsigned long long key = (uint64_t(lc) << 8) | (255u - j);
-            best = key > best ? key : best;
-        }
+    for (uint64_t i0 = uint64_t(blockIdx.x) * (EX_THREADS / EX_G); i0 < n_list; i0 += groups) {  // block-uniform trip count
+        const uint64_t i = i0 + uint64_t(threadIdx.x / EX_G);
+        bool ok = false;
+        SurvEntry fe;
+        fe.start = fe.base = 0;
+        fe.len = fe.pad = 0;
+        if (i < n_list) {
+            const SurvEntry ent = p.list[i];
+            const uint64_t lp = ent.base;
+            const uint32_t len = ent.len;
+            // (group-uniform conditions) the analysed lengths; where the shard's bit planes are at hand the one-popcount bound
+            // (planes.cuh) once more for the records the scan could not test (adopted ones, ranges before a plane window)
+            if (len >= p.min_len && len <= max_len &&
+                !(p.a.planes && lp + len <= p.a.n_local + MAX_C_LEN + 1 && !frequent_bound(p.a.planes, int64_t(lp), len, p.mcov))) {
+                unsigned long long acc = 0, best = 0;
+                for (uint32_t j = gl; j < len; j += EX_G) {
+                    const uint32_t tx = p.a.text[lp + j];
+                    const uint32_t lc = p.a.lcp[lp + j];
+                    const uint32_t b = p.a.bwt[lp + j];
+                    const uint32_t sample = (tx >= p.nr1_lo) & (p.nr1_big ^ 1u);
+                    saw_n |= is_n(b);
+                    acc += 1ull << (8 * (sample * 4 + base_code(b)));
+                    const unsigned long long key = (uint64_t(lc) << 8) | (255u - j);
+                    best = key > best ? key : best;
+                }
 #pragma unroll
-        for (int d = EX_G / 2; d > 0; d >>= 1) {
-            acc += __shfl_xor_sync(gmask, acc, d);
-            unsigned long long o = __shfl_xor_sync(gmask, best, d);
-            best = o > best ? o : best;
-        }
-        if (gl == 0 && (best >> 8) >= p.k_right) {
-            uint32_t f0 = 0, f1 = 0;
+                for (int d = EX_G / 2; d > 0; d >>= 1) {
+                    acc += __shfl_xor_sync(gmask, acc, d);
+                    unsigned long long o = __shfl_xor_sync(gmask, best, d);
+                    best = o > best ? o : best;
+                }
+                if (gl == 0 && (best >> 8) >= p.k_right) {
+                    uint32_t f0 = 0, f1 = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                f0 |= uint32_t(((acc >> (8 * b)) & 0xff) >= p.mcov) << b;
-                f1 |= uint32_t(((acc >> (8 * (b + 4))) & 0xff) >= p.mcov) << b;
-            }
-            const bool ok = f0 && f1 && __popc(f0) <= 2 && __popc(f1) <= 2 && f0 != f1 && __popc(f0 | f1) <= 3;
-            if (ok) {
-                const unsigned long long at = atomicAdd(&p.dev->n_flagged, 1ull);
-                if (at < p.cap_flagged) p.flagged[at] = ent;  // the host compares the count with the capacity and retries
+                    for (int b = 0; b < 4; ++b) {
+                        f0 |= uint32_t(((acc >> (8 * b)) & 0xff) >= p.mcov) << b;
+                        f1 |= uint32_t(((acc >> (8 * (b + 4))) & 0xff) >= p.mcov) << b;
+                    }
+                    ok = f0 && f1 && __popc(f0) <= 2 && __popc(f1) <= 2 && f0 != f1 && __popc(f0 | f1) <= 3;
+                    fe = ent;
+                    // what K3b would otherwise recompute: the frequent codes of both samples and the first strict LCP maximum
+                    fe.pad = f0 | (f1 << 4) | ((255u - uint32_t(best & 0xff)) << 8) | (1u << 31);
+                }
             }
         }
+        const uint32_t okm = __ballot_sync(FULL, ok);
+        if (lane == 0) s_wcnt[warp] = uint32_t(__popc(okm));
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int q = 0; q < EX_THREADS / 32; ++q) tot += s_wcnt[q];
+            s_base = tot ? atomicAdd(&p.dev->n_flagged, (unsigned long long)tot) : 0ull;
+        }
+        __syncthreads();
+        if (ok) {
+            unsigned long long at = s_base + uint32_t(__popc(okm & ((1u << lane) - 1u)));
+            for (int q = 0; q < warp; ++q) at += s_wcnt[q];
+            if (at < p.cap_flagged) p.flagged[at] = fe;  // the host compares the count with the capacity and retries
+        }
+        __syncthreads();  // (s_wcnt / s_base are rewritten by the next round)
     }
     if (__any_sync(__activemask(), saw_n) && saw_n) atomicOr(&p.dev->saw_n, 1ull);
 }
@@ -273,12 +300,19 @@ struct CandParams {
     uint64_t cap_flagged;  // capacity of the flagged list / slot arrays
 };
 
-__global__ void __launch_bounds__(128) k_candidates(CandParams p) {
-    const int lane = threadIdx.x & 31;
+constexpr int CA_WARPS = 8;
+
+__global__ void __launch_bounds__(CA_WARPS * 32) k_candidates(CandParams p) {
+    __shared__ uint32_t s_wcnt[CA_WARPS];  // valid slots per warp: one atomic per block and round appends them all
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t n_f = *p.n_flagged;
     if (n_f > p.cap_flagged) n_f = p.cap_flagged;  // overflow is reported by the host, which retries with more room
-    const uint64_t warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
-    for (uint64_t f = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; f < n_f; f += warps) {
+    const uint64_t warps = uint64_t(gridDim.x) * CA_WARPS;
+    for (uint64_t f0 = uint64_t(blockIdx.x) * CA_WARPS; f0 < n_f; f0 += warps) {  // block-uniform trip count
+    const uint64_t f = f0 + uint64_t(warp);
+    uint32_t vmask = 0;  // valid slots of my cluster
+    if (f < n_f) {
     const SurvEntry ent = p.flagged[f];
     const uint64_t start = ent.start;
     const uint32_t len = ent.len;
@@ -288,23 +322,35 @@ __global__ void __launch_bounds__(128) k_candidates(CandParams p) {
     const uint32_t* suff = p.a.suff + lp;
     const uint8_t* bwt = p.a.bwt + lp;
 
-    unsigned long long acc = 0, best = 0;
-    for (uint32_t j = lane; j < len; j += 32) {
-        const uint32_t sample = (text[j] >= p.nr1_lo) & (p.nr1_big ^ 1u);
-        acc += 1ull << (8 * (sample * 4 + base_code(bwt[j])));
-        const unsigned long long key = (uint64_t(lcp[j]) << 8) | (255u - j);
-        best = key > best ? key : best;
-    }
-    for (int d = 16; d > 0; d >>= 1) {
-        acc += __shfl_xor_sync(FULL, acc, d);
-        unsigned long long o = __shfl_xor_sync(FULL, best, d);
-        best = o > best ? o : best;
-    }
     uint32_t fr[2][2], nf[2] = {0, 0};
-    for (int s = 0; s < 2; ++s)
-        for (int b = 0; b < 4; ++b)
-            if (((acc >> (8 * (s * 4 + b))) & 0xff) >= p.mcov && nf[s] < 2) fr[s][nf[s]++] = b;
-    const uint32_t jbest = 255u - uint32_t(best & 0xff);
+    uint32_t jbest;
+    if (ent.pad >> 31) {  // K3x left the frequent codes (ascending, at most two per sample) and the position of the LCP maximum
+        for (int s = 0; s < 2; ++s) {
+            uint32_t f = (ent.pad >> (4 * s)) & 0xfu;
+            while (f && nf[s] < 2) {
+                fr[s][nf[s]++] = uint32_t(__ffs(f) - 1);
+                f &= f - 1;
+            }
+        }
+        jbest = (ent.pad >> 8) & 0xffu;
+    } else {
+        unsigned long long acc = 0, best = 0;
+        for (uint32_t j = lane; j < len; j += 32) {
+            const uint32_t sample = (text[j] >= p.nr1_lo) & (p.nr1_big ^ 1u);
+            acc += 1ull << (8 * (sample * 4 + base_code(bwt[j])));
+            const unsigned long long key = (uint64_t(lcp[j]) << 8) | (255u - j);
+            best = key > best ? key : best;
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            acc += __shfl_xor_sync(FULL, acc, d);
+            unsigned long long o = __shfl_xor_sync(FULL, best, d);
+            best = o > best ? o : best;
+        }
+        for (int s = 0; s < 2; ++s)
+            for (int b = 0; b < 4; ++b)
+                if (((acc >> (8 * (s * 4 + b))) & 0xff) >= p.mcov && nf[s] < 2) fr[s][nf[s]++] = b;
+        jbest = 255u - uint32_t(best & 0xff);
+    }
     const uint64_t right_idx = text[jbest], right_pos = suff[jbest];
 
     for (uint32_t i0 = 0; i0 < 2; ++i0) {
@@ -352,12 +398,28 @@ __global__ void __launch_bounds__(128) k_candidates(CandParams p) {
                 hdr.n1 = n1 < p.cap ? n1 : p.cap;
                 hdr.valid = (n0 > 0 && n1 > 0) ? 1u : 0u;
             }
-            if (lane == 0) {
-                p.slots[slot] = hdr;
-                if (hdr.valid) p.cand[atomicAdd(&p.dev->n_slots_valid, 1ull)] = slot;  // at most 4 per flagged cluster: fits
-            }
+            if (lane == 0) p.slots[slot] = hdr;
+            if (hdr.valid) vmask |= 1u << (i0 * 2 + i1);
         }
     }
+    }
+    // the valid slots of the block's clusters -> candidate list (at most 4 per flagged cluster: fits)
+    if (lane == 0) s_wcnt[warp] = uint32_t(__popc(vmask));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int q = 0; q < CA_WARPS; ++q) tot += s_wcnt[q];
+        s_base = tot ? atomicAdd(&p.dev->n_slots_valid, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (lane == 0 && vmask) {
+        unsigned long long at = s_base;
+        for (int q = 0; q < warp; ++q) at += s_wcnt[q];
+        for (uint32_t b = 0; b < 4; ++b)
+            if ((vmask >> b) & 1u) p.cand[at++] = f * 4 + b;
+    }
+    __syncthreads();  // (s_wcnt / s_base are rewritten by the next round)
     }
 }
 
@@ -368,6 +430,20 @@ struct PackedEventHdr {  // followed by left0[k_left] left1[k_left] right[k_righ
     int32_t D, gap, supp0, supp1, right_len, flags;  // flags bit0 = variant (supp0>0 && supp1>0), bit1 = keep, bits 8-9 = allele pair of the cluster
     uint64_t cluster_start;
 };
+
+// The same when the staged reads hold nothing but upper-case ACGT and both context lengths are <= 32: the three strings as two
+// bit planes each (bit i of plane p = bit p of the code (char >> 1) & 3 of character i; the host maps the codes back through
+// "ACTG").  48 bytes instead of 128 for the default -L 31 -R 30: K4's stores cross PCIe to pinned host memory.
+struct CompactEvent {
+    uint64_t cluster_start;
+    uint8_t D, supp0, supp1, right_len;
+    int8_t gap;
+    uint8_t flags;  // bit0 = variant, bit1 = keep, bits 2-3 = allele pair of the cluster
+    uint16_t pad;
+    uint32_t l0[2], l1[2], r[2];
+    uint32_t pad2[2];
+};
+static_assert(sizeof(CompactEvent) == 48, "compact event record");
 
 struct EventParams {
     const CandSlot* slots;
@@ -383,9 +459,11 @@ struct EventParams {
     uint8_t* out;
     uint32_t stride;
     SnpDev* dev;
+    const uint32_t* reads_flag;  // device word: bit 0 = the staged reads hold a byte outside ACGTacgt, bit 1 = a lower-case base (null: unknown)
 };
 
 constexpr int EV_WARPS = 4;
+constexpr int EV_MAXR = 32;  // reads per sample the fast path caches in shared memory
 constexpr int EV_B = 8;  // reads gathered per batch
 constexpr int EV_REC_MAX = 32 + 3 * E2S_MAX_K;  // packed record: header + left0 + left1 + right, stride is a multiple of 16
 
@@ -393,8 +471,14 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
     __shared__ uint64_t s_base[EV_WARPS][MAX_C_LEN];
     __shared__ char s_cons[EV_WARPS][2][E2S_MAX_K];
     __shared__ __align__(16) uint8_t s_rec[EV_WARPS][EV_REC_MAX];
+    __shared__ uint8_t s_ch[EV_WARPS][EV_MAXR][32];  // (fast path) the left contexts of one sample's reads, one byte per lane
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t n_cand = *p.n_cand;
+    const uint32_t rflag = p.reads_flag ? *p.reads_flag : 1u;
+    unsigned long long nv_local = 0, ne_local = 0;  // (lane 0) variants / kept events of my candidates: one atomic per warp at the end
+    const bool fast = p.k_left <= 32 && !(rflag & 1u);
+    const bool compact = fast && rflag == 0 && p.k_right <= 32;  // (kernel-uniform: every record of the launch has the same format)
+    if (compact && blockIdx.x == 0 && threadIdx.x == 0) p.dev->compact = 1;
     for (uint64_t c = uint64_t(blockIdx.x) * EV_WARPS + w; c < n_cand; c += uint64_t(gridDim.x) * EV_WARPS) {
     __syncwarp();
     const uint64_t slot = p.cand[c];
@@ -404,6 +488,58 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
     uint32_t saw_n = 0;
     int supp[2];
 
+    if (fast && hdr.n0 <= uint32_t(EV_MAXR) && hdr.n1 <= uint32_t(EV_MAXR)) {
+        // k_left <= 32 (one context position per lane), reads known to be ACGTacgt only, at most EV_MAXR reads per sample:
+        // both samples' read addresses in one go, every read's context gathered ONCE into shared memory (all loads in flight
+        // together), consensus and support from there.  The counter slot of a base is (char >> 1) & 3 -- a bijection on ACGT in
+        // either case, which is all cons::increment needs (ref:include.hpp:349-358); the stored winner is the raw char.
+        {
+            const uint32_t n0 = hdr.n0, nt = hdr.n0 + hdr.n1;
+            for (uint32_t j = lane; j < nt; j += 32) {
+                const uint32_t s = j >= n0, jj = s ? j - n0 : j;
+                const uint64_t r = p.slot_text[(slot * 2 + s) * p.cap + jj];
+                uint64_t b = 0;
+                if (r >= p.n_reads) bad = true;
+                else {
+                    b = p.off[r] + p.slot_pos[(slot * 2 + s) * p.cap + jj];
+                    if (b + uint64_t(kl) > p.off[r + 1]) bad = true;
+                }
+                s_base[w][s * EV_MAXR + jj] = b;
+            }
+            bad = __any_sync(FULL, bad);
+            __syncwarp();
+        }
+        if (!bad) {
+            const bool act = lane < kl;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const uint32_t nr = s ? hdr.n1 : hdr.n0;
+                for (uint32_t j = 0; j < nr; ++j)  // (independent loads: all in flight)
+                    s_ch[w][j][lane] = act ? p.bases[s_base[w][s * EV_MAXR + j] + lane] : uint8_t(0);
+                __syncwarp();
+                uint32_t cnt = 0, cur = 'A', cur_b = 0, cur_cnt = 0;  // four 8-bit counters; the winner so far, its slot and its count
+                for (uint32_t j = 0; j < nr; ++j) {
+                    const uint32_t ch = s_ch[w][j][lane];
+                    const uint32_t b8 = (ch << 2) & 24u;  // 8 * ((ch >> 1) & 3)
+                    cnt += 1u << b8;
+                    const uint32_t cb = (cnt >> b8) & 0xffu;
+                    const bool same = b8 == cur_b, lead = cb > cur_cnt;
+                    if (!same && lead) {  // strictly more than the current winner: first base to reach the final maximum wins
+                        cur = ch;
+                        cur_b = b8;
+                    }
+                    if (same || lead) cur_cnt = cb;  // (the stored char stays the first one that reached the lead)
+                }
+                if (act) s_cons[w][s][lane] = char(cur);
+                // support: reads within max_err mismatches of the consensus, ref:clust2snp.cpp:556-567
+                const uint32_t c = act ? cur : 0u;
+                int sp = 0;
+                for (uint32_t j = 0; j < nr; ++j) sp += int(__popc(__ballot_sync(FULL, uint32_t(s_ch[w][j][lane]) != c))) <= p.max_err;
+                supp[s] = sp;
+                __syncwarp();
+            }
+        }
+    } else
     for (int s = 0; s < 2; ++s) {
         const uint32_t nr = s ? hdr.n1 : hdr.n0;
         const uint32_t* lt = p.slot_text + (slot * 2 + s) * p.cap;
@@ -499,6 +635,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
 
     // right context = reads[idx].substr(pos, k_right), ref:clust2snp.cpp:604
     int rl = 0;
+    uint32_t r_ch = 0;  // (compact) my character of the right context
     if (variant) {
         if (hdr.right_idx >= p.n_reads) bad = true;
         else {
@@ -507,7 +644,11 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
             else {
                 uint64_t avail = re - rb - hdr.right_pos;
                 rl = int(avail < uint64_t(p.k_right) ? avail : uint64_t(p.k_right));
-                for (int i = lane; i < rl; i += 32) o_r[i] = char(p.bases[rb + hdr.right_pos + i]);
+                if (compact) {
+                    if (lane < rl) r_ch = p.bases[rb + hdr.right_pos + lane];
+                } else {
+                    for (int i = lane; i < rl; i += 32) o_r[i] = char(p.bases[rb + hdr.right_pos + i]);
+                }
             }
         }
         if (bad) {
@@ -515,9 +656,20 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
             return;
         }
     }
-    for (int i = lane; i < kl; i += 32) {
-        o_l0[i] = s_cons[w][0][i];
-        o_l1[i] = s_cons[w][1][i];
+    uint32_t cm[6] = {0, 0, 0, 0, 0, 0};  // (compact) bit planes of left0, left1, right
+    if (compact) {
+        const uint32_t a_ch = lane < kl ? uint32_t(uint8_t(s_cons[w][0][lane])) : 0u, b_ch = lane < kl ? uint32_t(uint8_t(s_cons[w][1][lane])) : 0u;
+        cm[0] = __ballot_sync(FULL, lane < kl && (a_ch & 2u));
+        cm[1] = __ballot_sync(FULL, lane < kl && (a_ch & 4u));
+        cm[2] = __ballot_sync(FULL, lane < kl && (b_ch & 2u));
+        cm[3] = __ballot_sync(FULL, lane < kl && (b_ch & 4u));
+        cm[4] = __ballot_sync(FULL, lane < rl && (r_ch & 2u));
+        cm[5] = __ballot_sync(FULL, lane < rl && (r_ch & 4u));
+    } else {
+        for (int i = lane; i < kl; i += 32) {
+            o_l0[i] = s_cons[w][0][i];
+            o_l1[i] = s_cons[w][1][i];
+        }
     }
 
     // distance(), ref:clust2snp.cpp:254-302.  g = 0: plain Hamming; g >= 1: drop g chars on the right of a / of b
@@ -568,24 +720,88 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
     if (d0 < min_ab && d0 < min_ba) { D = d0; gap = 0; }
     else if (min_ab < min_ba) { D = min_ab - g_ab; gap = g_ab; }
     else { D = min_ba - g_ba; gap = -g_ba; }
+    const bool keep = variant && D <= p.max_snvs;
     if (lane == 0) {
-        oh->D = D;
-        oh->gap = gap;
-        oh->supp0 = supp[0];
-        oh->supp1 = supp[1];
-        oh->right_len = rl;
-        oh->flags = (variant ? 1 : 0) | ((variant && D <= p.max_snvs) ? 2 : 0) | int32_t((slot & 3) << 8);  // bits 8-9: allele pair, for the output order
-        oh->cluster_start = hdr.cluster_start;
-        if (variant) atomicAdd(&p.dev->n_variants, 1ull);
-        if (variant && D <= p.max_snvs) atomicAdd(&p.dev->n_events, 1ull);
+        if (compact) {
+            CompactEvent* ce = reinterpret_cast<CompactEvent*>(o);
+            ce->cluster_start = hdr.cluster_start;
+            ce->D = uint8_t(D);
+            ce->supp0 = uint8_t(supp[0]);
+            ce->supp1 = uint8_t(supp[1]);
+            ce->right_len = uint8_t(rl);
+            ce->gap = int8_t(gap);
+            ce->flags = uint8_t((variant ? 1 : 0) | (keep ? 2 : 0) | int(slot & 3) << 2);
+            ce->pad = 0;
+            ce->l0[0] = cm[0]; ce->l0[1] = cm[1];
+            ce->l1[0] = cm[2]; ce->l1[1] = cm[3];
+            ce->r[0] = cm[4]; ce->r[1] = cm[5];
+            ce->pad2[0] = ce->pad2[1] = 0;
+        } else {
+            oh->D = D;
+            oh->gap = gap;
+            oh->supp0 = supp[0];
+            oh->supp1 = supp[1];
+            oh->right_len = rl;
+            oh->flags = (variant ? 1 : 0) | (keep ? 2 : 0) | int32_t((slot & 3) << 8);  // bits 8-9: allele pair, for the output order
+            oh->cluster_start = hdr.cluster_start;
+        }
+        nv_local += variant ? 1u : 0u;
+        ne_local += keep ? 1u : 0u;
     }
     __syncwarp();
     {
+        const uint32_t stride = compact ? uint32_t(sizeof(CompactEvent)) : p.stride;
         const uint4* src = reinterpret_cast<const uint4*>(s_rec[w]);
-        uint4* dst = reinterpret_cast<uint4*>(p.out + c * p.stride);
-        for (uint32_t i = lane; i < p.stride / 16; i += 32) dst[i] = src[i];
+        uint4* dst = reinterpret_cast<uint4*>(p.out + c * stride);
+        for (uint32_t i = lane; i < stride / 16; i += 32) dst[i] = src[i];
     }
     }
+    if (lane == 0) {
+        if (nv_local) atomicAdd(&p.dev->n_variants, nv_local);
+        if (ne_local) atomicAdd(&p.dev->n_events, ne_local);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// staged reads: any byte outside ACGTacgt (bit 0), any lower-case base (bit 1)?  One pass when the reads are staged; K4's fast
+// path and its compact event records depend on the answer
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reads_check(const uint8_t* __restrict__ bases, uint64_t n, uint32_t* flag) {
+    uint32_t bad = 0, lower = 0;
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    const uint64_t head = (16 - (reinterpret_cast<uintptr_t>(bases) & 15)) & 15;  // bytes before the first 16-byte boundary
+    const uint64_t nv = n > head ? (n - head) / 16 : 0;
+    const uint4* v = reinterpret_cast<const uint4*>(bases + head);
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const uint4 q = v[i];
+        const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t u = ws[k] & 0xDFDFDFDFu;
+            const uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+            bad |= ~ok ? 1u : 0u;
+            lower |= ws[k] & 0x20202020u;
+        }
+    }
+    if (blockIdx.x == 0) {  // the unaligned head and the tail, byte by byte
+        auto one = [&](uint64_t x) {
+            const uint32_t u = bases[x] & 0xDFu;
+            if (!(u == 'A' || u == 'C' || u == 'G' || u == 'T')) bad = 1;
+            lower |= bases[x] & 0x20u;
+        };
+        for (uint64_t x = threadIdx.x; x < (head < n ? head : n); x += blockDim.x) one(x);
+        for (uint64_t x = head + nv * 16 + threadIdx.x; x < n; x += blockDim.x) one(x);
+    }
+    const int any_bad = __syncthreads_or(int(bad != 0)), any_lower = __syncthreads_or(int(lower != 0));
+    if (threadIdx.x == 0 && (any_bad || any_lower)) atomicOr(flag, (any_bad ? 1u : 0u) | (any_lower ? 2u : 0u));
+}
+
+cudaError_t launch_reads_check(const uint8_t* d_bases, uint64_t n, uint32_t* flag, cudaStream_t stream, int sm_count) {
+    if (!n) return cudaSuccess;
+    uint64_t blocks = (n / 16 + 255) / 256 + 1;
+    if (blocks > uint64_t(sm_count) * 8) blocks = uint64_t(sm_count) * 8;
+    k_reads_check<<<unsigned(blocks), 256, 0, stream>>>(d_bases, n, flag);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -715,7 +931,7 @@ static cudaError_t snp_enqueue(SnpWork* w, const SnpArrays& a, const e2s_snp_par
         ep.cap_flagged = cap_flag;
         ep.dev = w->dev;
         if (timer) timer->begin(E2S_KERNEL_EXACT, stream);
-        k_cluster_exact<<<unsigned(sm_count) * 8, EX_THREADS, 0, stream>>>(ep);
+        k_cluster_exact<<<unsigned(sm_count) * 16, EX_THREADS, 0, stream>>>(ep);
         if (timer) timer->end(stream);
         CK(cudaGetLastError());
         ++*launches;
@@ -740,9 +956,9 @@ static cudaError_t snp_enqueue(SnpWork* w, const SnpArrays& a, const e2s_snp_par
         cp.slot_pos = w->slot_pos;
         cp.cand = w->cand;
         cp.dev = w->dev;
-        uint64_t blocks = (cap_flag + 3) / 4;
-        if (blocks > uint64_t(sm_count) * 16) blocks = uint64_t(sm_count) * 16;
-        k_candidates<<<unsigned(blocks), 128, 0, stream>>>(cp);
+        uint64_t blocks = (cap_flag + CA_WARPS - 1) / CA_WARPS;
+        if (blocks > uint64_t(sm_count) * 8) blocks = uint64_t(sm_count) * 8;
+        k_candidates<<<unsigned(blocks), CA_WARPS * 32, 0, stream>>>(cp);
         CK(cudaGetLastError());
         EventParams ep;
         ep.slots = w->slots;
@@ -762,6 +978,7 @@ static cudaError_t snp_enqueue(SnpWork* w, const SnpArrays& a, const e2s_snp_par
         ep.out = w->d_events;
         ep.stride = w->stride;
         ep.dev = w->dev;
+        ep.reads_flag = getenv("E2S_K4_GENERIC") ? nullptr : a.reads_flag;  // (test hook: keep K4 on the general path)
         uint64_t eblocks = (n_slots + EV_WARPS - 1) / EV_WARPS;
         if (eblocks > uint64_t(sm_count) * 16) eblocks = uint64_t(sm_count) * 16;
         k_events<<<unsigned(eblocks), EV_WARPS * 32, 0, stream>>>(ep);
@@ -838,36 +1055,62 @@ cudaError_t snp_run(SnpWork* w, const SnpArrays& a, const e2s_snp_params& p, int
 
 // expands the host copy of the packed candidates, keeping the variants (supp0>0 && supp1>0), in the reference's order:
 // clusters by eBWT position, the allele pairs of a cluster in the nested order of ref:clust2snp.cpp:431-435
+uint32_t snp_event_stride(const SnpWork* w) { return (w->h_dev && w->h_dev->compact) ? uint32_t(sizeof(CompactEvent)) : w->stride; }
+
 cudaError_t snp_fetch_events(SnpWork* w, e2s_event* host, uint64_t cap, uint64_t* n, cudaStream_t) {
     *n = 0;
     if (w->n_cand == 0) return cudaSuccess;
     const uint8_t* tmp = w->h_events;
+    const bool compact = w->h_dev->compact != 0;
+    const size_t stride = compact ? sizeof(CompactEvent) : size_t(w->stride);
     struct Key { uint64_t start; uint32_t pair; uint64_t c; };
     std::vector<Key> order;
     order.reserve(size_t(w->n_cand));
     for (uint64_t c = 0; c < w->n_cand; ++c) {
-        const PackedEventHdr* h = reinterpret_cast<const PackedEventHdr*>(tmp + c * w->stride);
-        if (h->flags & 1) order.push_back(Key{h->cluster_start, uint32_t(h->flags >> 8) & 3u, c});
+        if (compact) {
+            const CompactEvent* h = reinterpret_cast<const CompactEvent*>(tmp + c * stride);
+            if (h->flags & 1) order.push_back(Key{h->cluster_start, uint32_t(h->flags >> 2) & 3u, c});
+        } else {
+            const PackedEventHdr* h = reinterpret_cast<const PackedEventHdr*>(tmp + c * stride);
+            if (h->flags & 1) order.push_back(Key{h->cluster_start, uint32_t(h->flags >> 8) & 3u, c});
+        }
     }
     std::sort(order.begin(), order.end(), [](const Key& a, const Key& b) { return a.start != b.start ? a.start < b.start : a.pair < b.pair; });
     uint64_t k = 0;
     for (const Key& key : order) {
-        const uint8_t* o = tmp + key.c * w->stride;
-        const PackedEventHdr* h = reinterpret_cast<const PackedEventHdr*>(o);
+        const uint8_t* o = tmp + key.c * stride;
         if (host && k < cap) {
             e2s_event* ev = &host[k];
             memset(ev, 0, sizeof *ev);
-            ev->D = h->D;
-            ev->gap = h->gap;
-            ev->supp0 = h->supp0;
-            ev->supp1 = h->supp1;
-            ev->right_len = h->right_len;
-            ev->keep = (h->flags & 2) ? 1 : 0;
-            ev->cluster_start = h->cluster_start;
-            const char* s = reinterpret_cast<const char*>(o + sizeof(PackedEventHdr));
-            memcpy(ev->left0, s, size_t(w->k_left));
-            memcpy(ev->left1, s + w->k_left, size_t(w->k_left));
-            memcpy(ev->right, s + 2 * w->k_left, size_t(h->right_len));
+            if (compact) {
+                const CompactEvent* h = reinterpret_cast<const CompactEvent*>(o);
+                ev->D = h->D;
+                ev->gap = h->gap;
+                ev->supp0 = h->supp0;
+                ev->supp1 = h->supp1;
+                ev->right_len = h->right_len;
+                ev->keep = (h->flags & 2) ? 1 : 0;
+                ev->cluster_start = h->cluster_start;
+                auto expand = [](char* dst, const uint32_t* m, int len) {  // code (char >> 1) & 3: A 0, C 1, T 2, G 3
+                    for (int i = 0; i < len; ++i) dst[i] = "ACTG"[((m[0] >> i) & 1u) | (((m[1] >> i) & 1u) << 1)];
+                };
+                expand(ev->left0, h->l0, w->k_left);
+                expand(ev->left1, h->l1, w->k_left);
+                expand(ev->right, h->r, h->right_len);
+            } else {
+                const PackedEventHdr* h = reinterpret_cast<const PackedEventHdr*>(o);
+                ev->D = h->D;
+                ev->gap = h->gap;
+                ev->supp0 = h->supp0;
+                ev->supp1 = h->supp1;
+                ev->right_len = h->right_len;
+                ev->keep = (h->flags & 2) ? 1 : 0;
+                ev->cluster_start = h->cluster_start;
+                const char* s = reinterpret_cast<const char*>(o + sizeof(PackedEventHdr));
+                memcpy(ev->left0, s, size_t(w->k_left));
+                memcpy(ev->left1, s + w->k_left, size_t(w->k_left));
+                memcpy(ev->right, s + 2 * w->k_left, size_t(h->right_len));
+            }
         }
         ++k;
     }

@@ -518,3 +518,40 @@ def test_wrapped_length_cluster_in_phase2(ctx, fused):
         cnt = sh.find_events(p, st.max_clust_length)
     assert cnt.n_candidates == ores.n_candidates and api.events_format(sh.events(), p) == otext
     sh.close()
+
+
+def test_events_fast_and_general_path_agree(ctx, monkeypatch):
+    """K4 takes a short cut when the staged reads hold nothing but ACGT (k_reads_check) and k_left <= 32: same events as the
+    general path (E2S_K4_GENERIC), and reads with an N keep it off by themselves"""
+    rs, e = H.dataset("small", 2)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    p = api.default_params(rs.nreads1)
+
+    def events(reads):
+        ctx.stage_reads(reads, off)
+        sh = ctx.shard(e["n"])
+        sh.load_soa(e["lcp"], e["text"], e["suff"], e["bwt"])
+        sh.seal()
+        sh.cluster_lm(16, 2)
+        st = sh.statistics(p.mcov_out, p.pval)
+        cnt = sh.find_events(p, st.max_clust_length)
+        text = api.events_format(sh.events(), p)
+        sh.close()
+        return cnt, text
+
+    c1, t1 = events(rs.reads)
+    monkeypatch.setenv("E2S_K4_GENERIC", "1")
+    c2, t2 = events(rs.reads)
+    monkeypatch.delenv("E2S_K4_GENERIC")
+    assert c1.n_events > 0 and (c1.n_candidates, c1.n_events) == (c2.n_candidates, c2.n_events) and t1 == t2
+    es, el, _, _ = O.cluster_lm(e["lcp"], e["bwt"], 16, 2)
+    op = O.default_params(rs.nreads1)
+    ost = O.statistics(es, el, op.mcov_out, op.pval)
+    otext, _ = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+    assert t1 == otext
+    # a read that is never used as a context gets an N: the flag keeps K4 on the general path, the events stay the same
+    dirty = rs.reads.copy()
+    dirty[-1, -1] = ord("N")
+    c3, t3 = events(dirty)
+    if c3.saw_n == 0:
+        assert t3 == t1
