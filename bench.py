@@ -31,7 +31,8 @@ sys.path.insert(0, ROOT)
 METRIC = "ebwt_positions_per_s"
 UNIT = "positions/s"
 K_DEF, M_DEF = 16, 2  # ebwt2clust defaults (ref:ebwt2clust.cpp:18-19)
-KERNELS = {0: "k_lcp_flags", 1: "k_cluster_emit", 2: "k_code_scan", 3: "k_cluster_exact", 4: "k_cluster_scan"}
+KERNELS = {0: "k_lcp_flags", 1: "k_cluster_emit", 2: "k_code_scan", 3: "k_cluster_exact", 4: "k_cluster_scan",
+           5: "k_chunk_resolve", 6: "k_candidates", 7: "k_events", 8: "exchange (k_pack_exchange [+ ncclAllGather] + k_merge_stats)"}
 
 
 def log(*a):
@@ -752,6 +753,7 @@ def main():
         api.KERNEL_EXACT: 0,
         # K1 + K2 in one pass: the bit-sliced LCP (1 B/position) read once, the records written, the 2-bit base codes inside analysed clusters (fused prefilter)
         api.KERNEL_SCAN1: n + 10 * m_own + (pos_analysed / 4 if fused else 0),
+        api.KERNEL_RESOLVE: 0, api.KERNEL_CAND: 0, api.KERNEL_EVENTS: 0, api.KERNEL_MERGE: 0,  # (latency-bound small kernels: times only)
     }
     streamed = {api.KERNEL_SCAN: n / 4 + 10 * m_own}    # the 16-byte plane loads also carry the positions outside clusters
     if fused:

@@ -20,7 +20,7 @@ MAX_C_LEN = 150
 MAX_K = 128
 HIST_BINS = MAX_C_LEN + 1
 
-KERNEL_FLAGS, KERNEL_EMIT, KERNEL_SCAN, KERNEL_EXACT, KERNEL_SCAN1 = 0, 1, 2, 3, 4
+KERNEL_FLAGS, KERNEL_EMIT, KERNEL_SCAN, KERNEL_EXACT, KERNEL_SCAN1, KERNEL_RESOLVE, KERNEL_CAND, KERNEL_EVENTS, KERNEL_MERGE = 0, 1, 2, 3, 4, 5, 6, 7, 8
 OK, ERR_CUDA, ERR_ARG, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = range(6)
 
 

@@ -36,7 +36,7 @@ struct e2s_ctx {
     uint64_t n_reads = 0, n_bases = 0;
     uint64_t reads_cap_bases = 0, reads_cap_off = 0;
     bool reads_owned = false;
-    uint32_t* d_reads_flag = nullptr;  // != 0: the staged reads hold a byte outside ACGTacgt (launch_reads_check)
+    uint32_t* d_reads_flag = nullptr;  // [0] bit 0: a staged base outside ACGTacgt, bit 1: a lower-case base; [1] != 0: reads of different lengths
     // staging: two raw-record buffers, the H2D copies run on their own stream ahead of the de-interleave kernels
     uint8_t* d_raw[2] = {nullptr, nullptr};
     size_t raw_cap = 0;
@@ -267,6 +267,14 @@ uint64_t e2s_ctx_launch_count(const e2s_ctx* c) { return c ? c->launches : 0; }
 int e2s_ctx_timing(e2s_ctx* c, int enable) {
     if (!c) return fail(nullptr, E2S_ERR_ARG, "ctx == NULL");
     c->timer.enabled = enable != 0;
+    if (enable) {  // events for a few dozen steps up front: none is created inside a timed region
+        CU(c, cudaSetDevice(c->device));
+        while (c->timer.pool.size() < 512) {
+            cudaEvent_t e;
+            CU(c, cudaEventCreate(&e));
+            c->timer.pool.push_back(e);
+        }
+    }
     return E2S_OK;
 }
 
@@ -287,8 +295,8 @@ int e2s_ctx_kernel_time(e2s_ctx* c, int kernel, double* total_ms, uint64_t* laun
             ms += t;
             ++cnt;
         }
-        cudaEventDestroy(r.a);
-        cudaEventDestroy(r.b);
+        c->timer.give(r.a);
+        c->timer.give(r.b);
     }
     c->timer.recs.swap(keep);
     *total_ms = ms;
@@ -777,10 +785,10 @@ int e2s_shard_lcp_bytes_resident(const e2s_shard* s) { return s ? (s->sealed && 
 
 // one pass over the staged reads: does any byte fall outside ACGTacgt?  (K4's consensus then needs base_to_int's general rule)
 static int reads_check(e2s_ctx* c) {
-    if (!c->d_reads_flag && cudaMalloc(reinterpret_cast<void**>(&c->d_reads_flag), 4) != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "reads flag");
-    CU(c, cudaMemsetAsync(c->d_reads_flag, 0, 4, c->stream));
-    CU(c, launch_reads_check(c->d_bases, c->n_bases, c->d_reads_flag, c->stream, c->sm_count));
-    ++c->launches;
+    if (!c->d_reads_flag && cudaMalloc(reinterpret_cast<void**>(&c->d_reads_flag), 8) != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "reads flag");
+    CU(c, cudaMemsetAsync(c->d_reads_flag, 0, 8, c->stream));
+    CU(c, launch_reads_check(c->d_bases, c->n_bases, c->d_off, c->n_reads, c->d_reads_flag, c->stream, c->sm_count));
+    c->launches += 2;
     return E2S_OK;
 }
 
@@ -1040,7 +1048,10 @@ static int scan_enqueue(e2s_shard* s, uint32_t k, int32_t min_len) {
         rp.pf_list = p.pf_list;
         rp.pf_cap = p.pf_cap;
         rp.res = s->d_res;
-        CU(c, launch_chunk_resolve(rp, c->stream));
+        c->timer.begin(E2S_KERNEL_RESOLVE, c->stream);
+        cudaError_t re = launch_chunk_resolve(rp, c->stream);
+        c->timer.end(c->stream);
+        CU(c, re);
         ++c->launches;
     } else {
         c->timer.begin(E2S_KERNEL_EMIT, c->stream);
@@ -1829,7 +1840,9 @@ static int pipeline_step(e2s_shard* s, e2s_comm* cm, uint32_t k, int32_t min_len
         if ((rc = scan_enqueue(s, k, min_len))) break;
         uint64_t* send = cm ? cm->d_send : s->d_row;
         const uint64_t* rows = send;
+        c->timer.begin(E2S_KERNEL_MERGE, c->stream);
         if ((rc = launch_pack_exchange(s->d_res, s->n_local, s->global_off, uint64_t(s->lay_x), send, c->stream) == cudaSuccess ? 0 : 1)) {
+            c->timer.end(c->stream);
             rc = fail(c, E2S_ERR_CUDA, "k_pack_exchange");
             break;
         }
@@ -1837,6 +1850,7 @@ static int pipeline_step(e2s_shard* s, e2s_comm* cm, uint32_t k, int32_t min_len
             NcclApi* na = nccl_api();
             const int nr = na->AllGather(cm->d_send, cm->d_recv, XR_WORDS, NCCL_UINT64, cm->nccl, c->stream);
             if (nr != 0) {
+                c->timer.end(c->stream);
                 rc = fail(c, E2S_ERR_CUDA, std::string("ncclAllGather: ") + (na->GetErrorString ? na->GetErrorString(nr) : "error"));
                 break;
             }
@@ -1858,6 +1872,7 @@ static int pipeline_step(e2s_shard* s, e2s_comm* cm, uint32_t k, int32_t min_len
         mp.res = s->d_res;
         const char* where = "k_merge_stats";
         cudaError_t e = launch_merge_stats(mp, c->stream);
+        c->timer.end(c->stream);
         c->launches += 2;
         // phase 2 from the survivor list, its length and max_clust_length read on the device
         e2s_snp_counts counts;

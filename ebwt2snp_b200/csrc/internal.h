@@ -15,12 +15,24 @@ struct KernelTimer {
     bool enabled = false;
     struct Rec { int id; cudaEvent_t a, b; };
     std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;  // events are reused: creating one costs microseconds on the launching thread
+    cudaEvent_t take() {
+        cudaEvent_t e;
+        if (!pool.empty()) {
+            e = pool.back();
+            pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    }
+    void give(cudaEvent_t e) { pool.push_back(e); }
     void begin(int id, cudaStream_t s) {
         if (!enabled) return;
         Rec r;
         r.id = id;
-        cudaEventCreate(&r.a);
-        cudaEventCreate(&r.b);
+        r.a = take();
+        r.b = take();
         cudaEventRecord(r.a, s);
         recs.push_back(r);
     }
@@ -231,7 +243,7 @@ struct SnpArrays {
     const uint64_t* cl_start;  // global starts, sorted
     const uint16_t* cl_len;
     uint64_t m;
-    const uint32_t* reads_flag = nullptr;  // device word written when the reads were staged: != 0 = a base outside ACGTacgt (null: unknown)
+    const uint32_t* reads_flag = nullptr;  // two device words written when the reads were staged (launch_reads_check); null: unknown
 };
 
 struct CandSlot {  // one (flagged cluster, allele pair) slot written by K3b
@@ -271,7 +283,9 @@ struct CaptureParams {
 cudaError_t launch_capture(const CaptureParams& p, cudaStream_t stream, int sm_count);
 
 // *flag |= 1 when one of the n bytes is not in ACGTacgt (K4 then keeps base_to_int's "anything else counts as A" path)
-cudaError_t launch_reads_check(const uint8_t* d_bases, uint64_t n, uint32_t* flag, cudaStream_t stream, int sm_count);
+// flag[1] |= 1 unless all n_reads reads (offsets d_off[0 .. n_reads]) have the same length
+cudaError_t launch_reads_check(const uint8_t* d_bases, uint64_t n, const uint64_t* d_off, uint64_t n_reads, uint32_t* flag, cudaStream_t stream,
+                               int sm_count);
 
 struct SnpWork;  // opaque scratch owned by the shard (snp.cu)
 SnpWork* snp_work_create();

@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(EX_THREADS) k_cluster_exact(ExactParams p) {
             if (len >= p.min_len && len <= max_len &&
                 !(p.a.planes && lp + len <= p.a.n_local + MAX_C_LEN + 1 && !frequent_bound(p.a.planes, int64_t(lp), len, p.mcov))) {
                 unsigned long long acc = 0, best = 0;
-                for (uint32_t j = gl; j < len; j += EX_G) {
+#pragma unroll 4
+                for (uint32_t j = gl; j < len; j += EX_G) {  // (unrolled: the loads of four rounds are in flight together)
                     const uint32_t tx = p.a.text[lp + j];
                     const uint32_t lc = p.a.lcp[lp + j];
                     const uint32_t b = p.a.bwt[lp + j];
@@ -352,6 +353,25 @@ __global__ void __launch_bounds__(CA_WARPS * 32) k_candidates(CandParams p) {
         jbest = 255u - uint32_t(best & 0xff);
     }
     const uint64_t right_idx = text[jbest], right_pos = suff[jbest];
+    // the cluster's records, once, all loads in flight together (a flagged cluster is at most MAX_C_LEN = 150 long: 5 rounds of 32)
+    constexpr int CA_R = (MAX_C_LEN + 31) / 32;
+    uint32_t rtx[CA_R], rsf[CA_R], rch[CA_R];
+    bool rcommon[CA_R];
+    {
+        uint32_t rlc[CA_R];
+#pragma unroll
+        for (int it = 0; it < CA_R; ++it) {
+            const uint32_t j = uint32_t(it) * 32u + uint32_t(lane);
+            const bool in = j < len;
+            rtx[it] = in ? text[j] : 0u;
+            rsf[it] = in ? suff[j] : 0u;
+            rch[it] = in ? uint32_t(bwt[j]) : 0u;
+            rlc[it] = in ? lcp[j] : 0u;
+        }
+#pragma unroll
+        for (int it = 0; it < CA_R; ++it)
+            rcommon[it] = uint32_t(it) * 32u + uint32_t(lane) < len && rsf[it] >= p.k_left && rlc[it] >= p.k_right;
+    }
 
     for (uint32_t i0 = 0; i0 < 2; ++i0) {
         for (uint32_t i1 = 0; i1 < 2; ++i1) {
@@ -368,19 +388,13 @@ __global__ void __launch_bounds__(CA_WARPS * 32) k_candidates(CandParams p) {
                 uint32_t* t1 = p.slot_text + (slot * 2 + 1) * p.cap;
                 uint32_t* p0 = p.slot_pos + (slot * 2 + 0) * p.cap;
                 uint32_t* p1 = p.slot_pos + (slot * 2 + 1) * p.cap;
-                for (uint32_t j0 = 0; j0 < len; j0 += 32) {
-                    const uint32_t j = j0 + lane;
-                    bool q0 = false, q1 = false;
-                    uint32_t tx = 0, sf = 0;
-                    if (j < len) {
-                        tx = text[j];
-                        sf = suff[j];
-                        const uint32_t ch = bwt[j];
-                        const uint32_t sample = (tx >= p.nr1_lo) & (p.nr1_big ^ 1u);
-                        const bool common = sf >= p.k_left && lcp[j] >= p.k_right;
-                        q0 = common && ch == c0 && sample == 0;  // raw byte compare, ref:clust2snp.cpp:455,466
-                        q1 = common && ch == c1 && sample == 1;
-                    }
+#pragma unroll
+                for (int it = 0; it < CA_R; ++it) {
+                    if (uint32_t(it) * 32u >= len) break;  // (warp-uniform)
+                    const uint32_t tx = rtx[it], sf = rsf[it];
+                    const uint32_t sample = (tx >= p.nr1_lo) & (p.nr1_big ^ 1u);
+                    const bool q0 = rcommon[it] && rch[it] == c0 && sample == 0;  // raw byte compare, ref:clust2snp.cpp:455,466
+                    const bool q1 = rcommon[it] && rch[it] == c1 && sample == 1;
                     const uint32_t b0 = __ballot_sync(FULL, q0), b1 = __ballot_sync(FULL, q1);
                     const uint32_t lt = (1u << lane) - 1u;
                     if (q0) {
@@ -464,17 +478,21 @@ struct EventParams {
 
 constexpr int EV_WARPS = 4;
 constexpr int EV_MAXR = 32;  // reads per sample the fast path caches in shared memory
-constexpr int EV_B = 8;  // reads gathered per batch
+constexpr int EV_B = 8;   // reads gathered per batch (general path)
+constexpr int EV_FB = 8;  // ... (fast path)
 constexpr int EV_REC_MAX = 32 + 3 * E2S_MAX_K;  // packed record: header + left0 + left1 + right, stride is a multiple of 16
 
-__global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
+__global__ void __launch_bounds__(EV_WARPS * 32, 12) k_events(EventParams p) {
     __shared__ uint64_t s_base[EV_WARPS][MAX_C_LEN];
     __shared__ char s_cons[EV_WARPS][2][E2S_MAX_K];
     __shared__ __align__(16) uint8_t s_rec[EV_WARPS][EV_REC_MAX];
     __shared__ uint8_t s_ch[EV_WARPS][EV_MAXR][32];  // (fast path) the left contexts of one sample's reads, one byte per lane
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t n_cand = *p.n_cand;
-    const uint32_t rflag = p.reads_flag ? *p.reads_flag : 1u;
+    const uint32_t rflag = p.reads_flag ? p.reads_flag[0] : 1u;
+    // every read as long as the first one (k_offsets_check): offsets by arithmetic (UL = 0: look them up)
+    const uint64_t UL = (p.reads_flag && p.reads_flag[1] == 0 && p.n_reads) ? p.off[1] - p.off[0] : 0, U0 = UL ? p.off[0] : 0;
+    auto off_of = [&](uint64_t r) { return UL ? U0 + r * UL : p.off[r]; };
     unsigned long long nv_local = 0, ne_local = 0;  // (lane 0) variants / kept events of my candidates: one atomic per warp at the end
     const bool fast = p.k_left <= 32 && !(rflag & 1u);
     const bool compact = fast && rflag == 0 && p.k_right <= 32;  // (kernel-uniform: every record of the launch has the same format)
@@ -501,8 +519,8 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
                 uint64_t b = 0;
                 if (r >= p.n_reads) bad = true;
                 else {
-                    b = p.off[r] + p.slot_pos[(slot * 2 + s) * p.cap + jj];
-                    if (b + uint64_t(kl) > p.off[r + 1]) bad = true;
+                    b = off_of(r) + p.slot_pos[(slot * 2 + s) * p.cap + jj];
+                    if (b + uint64_t(kl) > off_of(r + 1)) bad = true;
                 }
                 s_base[w][s * EV_MAXR + jj] = b;
             }
@@ -514,8 +532,14 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const uint32_t nr = s ? hdr.n1 : hdr.n0;
-                for (uint32_t j = 0; j < nr; ++j)  // (independent loads: all in flight)
-                    s_ch[w][j][lane] = act ? p.bases[s_base[w][s * EV_MAXR + j] + lane] : uint8_t(0);
+                for (uint32_t j0 = 0; j0 < nr; j0 += EV_FB) {  // EV_FB independent loads in flight, then their stores
+                    uint8_t v[EV_FB];
+#pragma unroll
+                    for (int u = 0; u < EV_FB; ++u) v[u] = (act && j0 + u < nr) ? p.bases[s_base[w][s * EV_MAXR + j0 + u] + lane] : uint8_t(0);
+#pragma unroll
+                    for (int u = 0; u < EV_FB; ++u)
+                        if (j0 + u < nr) s_ch[w][j0 + u][lane] = v[u];
+                }
                 __syncwarp();
                 uint32_t cnt = 0, cur = 'A', cur_b = 0, cur_cnt = 0;  // four 8-bit counters; the winner so far, its slot and its count
                 for (uint32_t j = 0; j < nr; ++j) {
@@ -549,8 +573,8 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
             uint64_t b = 0;
             if (r >= p.n_reads) bad = true;
             else {
-                b = p.off[r] + lp[j];
-                if (b + uint64_t(kl) > p.off[r + 1]) bad = true;
+                b = off_of(r) + lp[j];
+                if (b + uint64_t(kl) > off_of(r + 1)) bad = true;
             }
             s_base[w][j] = b;
         }
@@ -639,7 +663,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) k_events(EventParams p) {
     if (variant) {
         if (hdr.right_idx >= p.n_reads) bad = true;
         else {
-            const uint64_t rb = p.off[hdr.right_idx], re = p.off[hdr.right_idx + 1];
+            const uint64_t rb = off_of(hdr.right_idx), re = off_of(hdr.right_idx + 1);
             if (hdr.right_pos > re - rb) bad = true;
             else {
                 uint64_t avail = re - rb - hdr.right_pos;
@@ -796,11 +820,25 @@ __global__ void __launch_bounds__(256) k_reads_check(const uint8_t* __restrict__
     if (threadIdx.x == 0 && (any_bad || any_lower)) atomicOr(flag, (any_bad ? 1u : 0u) | (any_lower ? 2u : 0u));
 }
 
-cudaError_t launch_reads_check(const uint8_t* d_bases, uint64_t n, uint32_t* flag, cudaStream_t stream, int sm_count) {
-    if (!n) return cudaSuccess;
+// flag[1] |= 1 unless every read has the length of the first one (K4 then computes read offsets instead of looking them up: one
+// dependent DRAM access less per gathered context)
+__global__ void __launch_bounds__(256) k_offsets_check(const uint64_t* __restrict__ off, uint64_t n_reads, uint32_t* flag) {
+    const uint64_t L = off[1] - off[0];
+    uint32_t bad = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_reads; i += uint64_t(gridDim.x) * blockDim.x)
+        bad |= uint32_t(off[i + 1] - off[i] != L);
+    if (__syncthreads_or(int(bad)) && threadIdx.x == 0) atomicOr(flag + 1, 1u);
+}
+
+cudaError_t launch_reads_check(const uint8_t* d_bases, uint64_t n, const uint64_t* d_off, uint64_t n_reads, uint32_t* flag, cudaStream_t stream,
+                               int sm_count) {
+    if (!n || !n_reads) return cudaSuccess;
     uint64_t blocks = (n / 16 + 255) / 256 + 1;
     if (blocks > uint64_t(sm_count) * 8) blocks = uint64_t(sm_count) * 8;
     k_reads_check<<<unsigned(blocks), 256, 0, stream>>>(d_bases, n, flag);
+    blocks = (n_reads + 255) / 256;
+    if (blocks > uint64_t(sm_count) * 8) blocks = uint64_t(sm_count) * 8;
+    k_offsets_check<<<unsigned(blocks), 256, 0, stream>>>(d_off, n_reads, flag);
     return cudaGetLastError();
 }
 
@@ -958,7 +996,9 @@ static cudaError_t snp_enqueue(SnpWork* w, const SnpArrays& a, const e2s_snp_par
         cp.dev = w->dev;
         uint64_t blocks = (cap_flag + CA_WARPS - 1) / CA_WARPS;
         if (blocks > uint64_t(sm_count) * 8) blocks = uint64_t(sm_count) * 8;
+        if (timer) timer->begin(E2S_KERNEL_CAND, stream);
         k_candidates<<<unsigned(blocks), CA_WARPS * 32, 0, stream>>>(cp);
+        if (timer) timer->end(stream);
         CK(cudaGetLastError());
         EventParams ep;
         ep.slots = w->slots;
@@ -981,7 +1021,9 @@ static cudaError_t snp_enqueue(SnpWork* w, const SnpArrays& a, const e2s_snp_par
         ep.reads_flag = getenv("E2S_K4_GENERIC") ? nullptr : a.reads_flag;  // (test hook: keep K4 on the general path)
         uint64_t eblocks = (n_slots + EV_WARPS - 1) / EV_WARPS;
         if (eblocks > uint64_t(sm_count) * 16) eblocks = uint64_t(sm_count) * 16;
+        if (timer) timer->begin(E2S_KERNEL_EVENTS, stream);
         k_events<<<unsigned(eblocks), EV_WARPS * 32, 0, stream>>>(ep);
+        if (timer) timer->end(stream);
         CK(cudaGetLastError());
         *launches += 2;
     }

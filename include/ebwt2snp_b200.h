@@ -69,8 +69,12 @@ uint64_t e2s_ctx_launch_count(const e2s_ctx *ctx);
 #define E2S_KERNEL_EMIT 1  /* K2: look-back scan over the masks + record compaction */
 #define E2S_KERNEL_SCAN 2  /* K3a: per-cluster base-code prefilter on the resident bit planes of the BWT */
 #define E2S_KERNEL_EXACT 3 /* K3x: exact 2x4 histogram / filters of the surviving clusters */
-#define E2S_KERNEL_SCAN1 4 /* K1 + K2 in one pass over the one-byte LCP (k_cluster_scan): what runs whenever the shard has it */
-#define E2S_KERNEL_COUNT 5
+#define E2S_KERNEL_SCAN1 4 /* K1 + K2 in one pass over the bit-sliced LCP (k_cluster_scan): what runs whenever the shard has it */
+#define E2S_KERNEL_RESOLVE 5 /* k_chunk_resolve: chunk heads, segment offsets, shard totals */
+#define E2S_KERNEL_CAND 6   /* K3b: candidate slots of the flagged clusters */
+#define E2S_KERNEL_EVENTS 7 /* K4: contexts, consensus, support, distance, event records to pinned host memory */
+#define E2S_KERNEL_MERGE 8  /* k_pack_exchange [+ ncclAllGather] + k_merge_stats: the exchange between the phases (pipelines only) */
+#define E2S_KERNEL_COUNT 9
 int e2s_ctx_timing(e2s_ctx *ctx, int enable);
 int e2s_ctx_kernel_time(e2s_ctx *ctx, int kernel, double *total_ms, uint64_t *launches);
 
