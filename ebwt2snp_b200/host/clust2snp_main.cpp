@@ -9,25 +9,38 @@
 
 #include "host_io.hpp"
 
-static void help(const e2s_snp_params& d) {
-    std::cout << "clust2snp [options]\nOptions:\n"
-              << "-h          Print this help.\n"
-              << "-i <arg>    Input fasta file containing the samples' reads (REQUIRED).\n"
-              << "-n <arg>    Number of reads in the first sample (REQUIRED).\n"
-              << "-L <arg>    Length of left-context, SNP included (default: " << d.k_left << ").\n"
-              << "-R <arg>    Length of right context, SNP excluded (default: " << d.k_right << ").\n"
-              << "-g <arg>    Maximum allowed gap length in indel (default: " << d.max_gap << "). 0 selects the default.\n"
-              << "-v <arg>    Maximum number of non-isolated SNPs in left-contexts (default: " << d.max_snvs << "; accepted, not used).\n"
-              << "-c <arg>    Reads per individual used for the consensus of the left-context (default: " << d.consensus_reads << ").\n"
-              << "-e <arg>    Mismatches allowed between a read and the consensus (default: " << d.max_err << ").\n"
-              << "-m <arg>    Minimum cluster length per individual (default: " << d.mcov_out << "); clusters shorter than 2*<arg> are skipped.\n"
-              << "-p <arg>    Choose the max cluster length so that this fraction of bases is analyzed (default: " << d.pval << ").\n"
-              << "-x <arg>    Byte size of LCP integers in input EGSA/BCR file (default: 1).\n"
-              << "-y <arg>    Byte size of DA integers (read number) in input EGSA/BCR file (default: 4).\n"
-              << "-z <arg>    Byte size of pos integers (position in read) in input EGSA/BCR file (default: 1).\n\n"
-              << "Needs the EGSA/BCR index of the reads and the cluster file written by ebwt2clust. Events are stored\n"
-              << "in KisSNP2-style fasta in <input up to .fast*>.snp; most events appear on both strands.\n"
-              << "B200 build: set E2S_GPUS=N to shard the eBWT over N GPUs." << std::endl;
+// the reference's help text, byte for byte (ref:clust2snp.cpp:64-94 as its binary prints it with the default values;
+// tests/golden/help_clust2snp.txt is that output)
+static const char* const HELP_TEXT = R"HELP(clust2snp [options]
+Options:
+-h          Print this help.
+-i <arg>    Input fasta file containing the samples' reads (REQUIRED).
+-n <arg>    Number of reads in the first sample (REQUIRED).
+-L <arg>    Length of left-context, SNP included (default: 31).
+-R <arg>    Length of right context, SNP excluded (default: 30).
+-g <arg>    Maximum allowed gap length in indel (default: 10). If 0, indels are disabled.
+-v <arg>    Maximum number of non-isolated SNPs in left-contexts. The central SNP/indel is excluded from this count (default: 3).
+-c <arg>    Extract this maximum number of reads per individual to compute consensus of left-context (default: 20).
+-e <arg>    Mismatches allowed between DNA fragments forming consensus of left-context (default: 2).
+-m <arg>    Minimum cluster length per individual (default: 5). The minimum cluster length (for the 2 individuals) is 2*<arg>.
+-p <arg>    Automatically choose max cluster length so that this fraction of bases is analyzed (default: 
+            0.99). In any case, the maximum cluster length will not exceed the value specified with -M.
+-M <arg>    Maximum cluster length. Read the description of option -p.
+-x <arg>    Byte size of LCP integers in input EGSA/BCR file (default: 1).
+-y <arg>    Byte size of DA integers (read number) in input EGSA/BCR file (default: 4).
+-z <arg>    Byte size of pos integers (position in read) in input EGSA/BCR file (default: 1).
+
+
+To run clust2snp, you must first build (1) the Enhanced Generalized Suffix Array of the input sequences
+and the  cluster file built with ebwt2snp. Output is stored in reads.snp (this  is actually a fasta
+file), where reads.fasta is the input fasta file.
+
+Output:  SNPs are output in KisSNP2 format as a fasta file. IMPORTANT: in many cases, each SNP/indel is
+reported twice: one time on the forward strand and one on the reverse strand. 
+)HELP";
+
+static void help(const e2s_snp_params&) {
+    std::cout << HELP_TEXT << std::flush;
     exit(0);  // ref:clust2snp.cpp:93
 }
 

@@ -10,19 +10,28 @@
 
 static const int min_def = 2, K_def = 16, lcp_def = 1, da_def = 4, pos_def = 1;
 
+// the reference's help text, byte for byte (ref:ebwt2clust.cpp:34-52 as its binary prints it with the default values;
+// tests/golden/help_ebwt2clust.txt is that output)
+static const char* const HELP_TEXT = R"HELP(ebwt2clust [options]
+Options:
+-h         Print this help
+-i <arg>   Input fasta file (REQUIRED)
+-k <arg>   Minimum LCP required in clusters (default: 16)
+-m <arg>   Discard clusters smaller than this value (default: 2)
+-x <arg>   Byte size of LCP integers in input EGSA/BCR file (default: 1).
+-y <arg>   Byte size of DA integers (read number) in input EGSA/BCR file (default: 4).
+-z <arg>   Byte size of pos integers (position in read) in input EGSA/BCR file (default: 1).
+
+
+To run ebwt2clust, you must  first build the Enhanced Generalized  Suffix Array of the input
+sequences. The EGSA must be stored in the input file's folder adding extension .gesa to the
+name of the input file (github.com/felipelouza/egsa), or in three files with extensions
+.out, .out.lcp, .out.pairSA computed using the BCR algorithm 
+(https://github.com/giovannarosone/BCR_LCP_GSA). Output is stored in reads.fasta.clusters.
+)HELP";
+
 static void help() {
-    std::cout << "ebwt2clust [options]\nOptions:\n"
-              << "-h         Print this help\n"
-              << "-i <arg>   Input fasta file (REQUIRED)\n"
-              << "-k <arg>   Minimum LCP required in clusters (default: " << K_def << ")\n"
-              << "-m <arg>   Discard clusters smaller than this value (default: " << min_def << ")\n"
-              << "-x <arg>   Byte size of LCP integers in input EGSA/BCR file (default: " << lcp_def << ").\n"
-              << "-y <arg>   Byte size of DA integers (read number) in input EGSA/BCR file (default: " << da_def << ").\n"
-              << "-z <arg>   Byte size of pos integers (position in read) in input EGSA/BCR file (default: " << pos_def << ").\n\n"
-              << "The Enhanced Generalized Suffix Array of the reads must exist next to the input file, either as\n"
-              << "<input>.gesa (github.com/felipelouza/egsa) or as the BCR triple <input>.out, .out.lcp, .out.pairSA\n"
-              << "(github.com/giovannarosone/BCR_LCP_GSA). Output goes to <input>.clusters.\n"
-              << "B200 build: set E2S_GPUS=N to shard the eBWT over N GPUs." << std::endl;
+    std::cout << HELP_TEXT << std::flush;
     exit(0);  // the reference exits 0 from help(), also on errors (ref:ebwt2clust.cpp:51)
 }
 

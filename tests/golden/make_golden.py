@@ -383,8 +383,19 @@ def snp_vs_vcf_golden(d):
     np.savez_compressed(os.path.join(HERE, "snp_vs_vcf.npz"), **out)
 
 
+def help_texts():
+    """what the reference binaries print for -h (the drop-in CLIs print the same bytes)"""
+    import subprocess
+    for tool in ("ebwt2clust", "clust2snp"):
+        r = subprocess.run([os.path.join(os.path.dirname(HERE), "..", "oracle", "_ref", tool), "-h"], capture_output=True)
+        open(os.path.join(HERE, "help_" + tool + ".txt"), "wb").write(r.stdout)
+
+
 if __name__ == "__main__":
     assert O.ref_available(), "oracle/_ref missing: run `make -C oracle ref` where /root/reference exists"
+    if len(sys.argv) > 1 and sys.argv[1] == "help":  # only these fixtures
+        help_texts()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "snp_vs_vcf":  # only this fixture
         d = tempfile.mkdtemp(prefix="golden_")
         try:
@@ -401,6 +412,7 @@ if __name__ == "__main__":
         for name, cfg in MICRO.items():
             micro(name, cfg, d)
         snp_text_tools(d)
+        help_texts()
     finally:
         shutil.rmtree(d, ignore_errors=True)
     print("golden vectors written to", HERE)

@@ -25,6 +25,17 @@ def test_help_exits_zero(built):
     assert "clust2snp [options]" in run("clust2snp", "-i", "x", "-n", "3", "-b").stdout
 
 
+def test_help_text_is_the_reference_s(built):
+    """tests/golden/help_*.txt = what the reference binaries print for -h (tests/golden/make_golden.py); live against
+    oracle/_ref when it is there"""
+    for tool in ("ebwt2clust", "clust2snp"):
+        want = open(os.path.join(ROOT, "tests", "golden", "help_" + tool + ".txt")).read()
+        assert run(tool, "-h").stdout == want
+        ref = os.path.join(ROOT, "oracle", "_ref", tool)
+        if os.access(ref, os.X_OK):
+            assert subprocess.run([ref, "-h"], capture_output=True, text=True).stdout == want
+
+
 def test_missing_index_exits_one(built):
     with tempfile.TemporaryDirectory() as d:
         fa = os.path.join(d, "none.fasta")
