@@ -230,6 +230,30 @@ def aos_records_pinned(eg, torch, lo=0, hi=None, chunk=1 << 26):
     return host
 
 
+def lcp_fits_byte(eg, torch):
+    return int(eg["lcp"].max().item()) <= 127 if int(eg["n"]) else False
+
+
+def soa_triple_host(eg, torch, chunk=1 << 26):
+    """the index as the BCR triple: (lcp u8 pinned, bwt u8 pinned, pairSA bytes = suff(1) text(4) per position, pageable)"""
+    n = int(eg["n"])
+    dev = eg["lcp"].device
+    lcp = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    bwt = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    pair = torch.empty(n * 5, dtype=torch.uint8)
+    rec = torch.empty((min(chunk, n), 5), dtype=torch.uint8, device=dev)
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        r = rec[: b - a]
+        r[:, 0] = eg["suff"][a:b].to(torch.uint8)
+        r[:, 1:5] = eg["text"][a:b].view(torch.uint8).view(b - a, 4)
+        pair[a * 5:b * 5].copy_(r.view(-1))
+        lcp[a:b].copy_(eg["lcp"][a:b].to(torch.uint8))
+        bwt[a:b].copy_(eg["bwt"][a:b])
+    del rec
+    return lcp, bwt, pair
+
+
 # --------------------------------------------------------------------------------------------
 # the reference arm / CPU baseline: oracle/_ref binaries on a bounded sample
 # --------------------------------------------------------------------------------------------
@@ -662,6 +686,11 @@ def main():
             host_rec = aos_records_pinned(eg, torch, rec_first, rec_end)
         else:
             host_rec = aos_records_pinned(eg, torch)
+    # the same index as the BCR triple (ref:include.hpp:157-188) at BCR's usual widths: X.out.lcp 1 byte, X.out 1 byte (both pinned:
+    # they cross PCIe), X.out.pairSA = suff(1) + text(4) in ordinary host memory (only the host reads it)
+    host_soa = None
+    if not args.no_e2e and world == 1 and lcp_fits_byte(eg, torch):
+        host_soa = soa_triple_host(eg, torch)
     # generator arrays are no longer needed on the device
     for kk in ("lcp", "text", "suff", "bwt"):
         eg[kk] = None
@@ -847,6 +876,37 @@ def main():
                "h2d_GBps": h2d_b * args.e2e_steps / dt / 1e9,
                "fraction_of_concurrent_probe": (h2d_b * args.e2e_steps / dt / 1e9) / probe_sum if probe_sum else None,
                "n_events_rank0": int(res.snp.n_events), "n_written": int(res.n_written)}
+
+    # ---- e2e_soa: the same job from the BCR triple, lean (e2s_pipeline_host_soa): lcp + bwt cross PCIe, text / suff of the
+    # survivors only are fetched from the host's pairSA.  Same outputs as the e2e call above (compared).
+    if host_soa is not None and e2e is not None:
+        host_rec = None
+        l8, b8, pair = host_soa
+        want_rec = rec10[: int(res.n_written) * 10].clone()
+        want_counts = (int(res.n_written), int(res.n_clust_out), int(res.max_clust_length), int(res.snp.n_candidates), int(res.snp.n_events))
+        want_ev = api.events_format(list(evbuf)[: int(res.snp.n_variants)], params)
+
+        def soa_call():
+            return ctx.pipeline_host_soa(l8, b8, pair, n, reads_pin, off_pin, params, K_DEF, M_DEF, 1, 4, 1, rec10=rec10_np, events=evbuf)
+
+        r2 = soa_call()
+        same = (want_counts == (int(r2.n_written), int(r2.n_clust_out), int(r2.max_clust_length), int(r2.snp.n_candidates), int(r2.snp.n_events))
+                and bool(torch.equal(want_rec, rec10[: int(r2.n_written) * 10]))
+                and want_ev == api.events_format(list(evbuf)[: int(r2.snp.n_variants)], params))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            r2 = soa_call()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e["soa"] = {"value": n_global * args.e2e_steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / args.e2e_steps,
+                      "h2d_bytes_per_step": int(r2.h2d_bytes), "d2h_bytes_per_step": int(r2.d2h_bytes),
+                      "h2d_GBps": int(r2.h2d_bytes) * args.e2e_steps / dt / 1e9,
+                      "api": "e2s_pipeline_host_soa (BCR triple: X.out.lcp 1 byte + X.out cross PCIe in full; X.out.pairSA (suff 1 + text 4 bytes) stays "
+                             "on the host, only the prefilter survivors' records are fetched from it)",
+                      "outputs_equal_e2e": bool(same)}
+        del want_rec, l8, b8, pair
+        host_soa = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -87,6 +87,7 @@ SYMBOLS = [
     "e2s_events_format", "e2s_free", "e2s_pipeline_resident", "e2s_pipeline_host",
     "e2s_comm_unique_id", "e2s_comm_create", "e2s_comm_destroy", "e2s_pipeline_sharded",
     "e2s_exchange_row_words", "e2s_exchange_rows_finish",
+    "e2s_pipeline_host_soa", "e2s_shard_host_gsa", "e2s_shard_load_lcp_bwt",
     "e2s_pipeline_host_sharded", "e2s_shard_create_chunked", "e2s_shard_chunk_positions", "e2s_chunk_begin", "e2s_chunk_scan", "e2s_chunked_finish", "e2s_chunked_reset", "e2s_chunked_exchange",
 ]
 
@@ -171,6 +172,11 @@ def load_library():
     lib.e2s_pipeline_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(SnpParams), C.c_void_p,
                                       C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PipelineResult)]
+    lib.e2s_pipeline_host_soa.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p,
+                                          C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(SnpParams), C.c_void_p,
+                                          C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PipelineResult)]
+    lib.e2s_shard_host_gsa.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.e2s_shard_load_lcp_bwt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64]
     lib.e2s_pipeline_host_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                               C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(SnpParams),
                                               C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64,
@@ -358,6 +364,20 @@ class Context:
                                             n_reads, k, min_len, C.byref(params), _ptr(rec10), cap_r,
                                             C.cast(events, C.c_void_p) if events is not None else None, cap_e,
                                             C.byref(res)))
+        return res
+
+    def pipeline_host_soa(self, lcp, bwt, pair_sa, n, reads_bases, reads_off, params, k=16, min_len=2, x=4, y=4, z=4,
+                          rec10=None, events=None):
+        """The same from the BCR triple (X.out.lcp, X.out, X.out.pairSA as byte buffers): only lcp + bwt cross PCIe in full,
+        the survivors' text / suff are fetched from the host's pairSA (e2s_pipeline_host_soa)."""
+        res = PipelineResult()
+        n_reads = (len(reads_off) - 1) if reads_off is not None else 0
+        cap_r = (rec10.nbytes // 10) if rec10 is not None else 0
+        cap_e = len(events) if events is not None else 0
+        self._ck(self.lib.e2s_pipeline_host_soa(self.h, _ptr(lcp), x, _ptr(bwt), _ptr(pair_sa), y, z, n, _ptr(reads_bases),
+                                                _ptr(reads_off), n_reads, k, min_len, C.byref(params), _ptr(rec10), cap_r,
+                                                C.cast(events, C.c_void_p) if events is not None else None, cap_e,
+                                                C.byref(res)))
         return res
 
 

@@ -42,6 +42,9 @@ struct e2s_ctx {
     size_t raw_cap = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_unpacked[2] = {nullptr, nullptr}, ev_start = nullptr;
+    uint8_t* d_soa_stage[2] = {nullptr, nullptr};  // e2s_pipeline_host_soa: lcp + BWT bytes of a chunk as they crossed PCIe
+    size_t soa_stage_cap = 0;
+    cudaEvent_t ev_soa_staged[2] = {nullptr, nullptr}, ev_soa_free[2] = {nullptr, nullptr};
     // e2s_shard_load_gesa_fd: ring of pinned pieces the reader threads fill from the file
     uint8_t* pin_ring = nullptr;
     size_t pin_piece = 0;  // bytes per slot
@@ -50,6 +53,8 @@ struct e2s_ctx {
     e2s_shard* cached = nullptr;
     KernelTimer timer;
 };
+
+constexpr uint64_t GSA_TAIL = 512;  // lean SoA mode: text / suff of the last positions of the eBWT are loaded like the rest (phantom records, tail clusters)
 
 struct e2s_shard {
     e2s_ctx* ctx = nullptr;
@@ -60,7 +65,10 @@ struct e2s_shard {
     uint32_t *lcp = nullptr, *text = nullptr, *suff = nullptr;  // local position 0
     uint8_t* bwt = nullptr;
     uint8_t* lcpt = nullptr;     // bit-sliced copy of the LCP (k_derive: 64-byte groups of 7 bit planes + the plane A), 1 B/position
-    bool lcpt_ok = false;        // every LCP value the scan looks at is <= 127: the one-pass scan may stream it
+    bool lcpt_ok = false;        // the bit-sliced copy is there for the one-pass scan to stream (E2S_LCP_WIDE=1 switches it off)
+    bool lcpt_sat = false;       // an LCP value the scan looks at is > 127 and was saturated to 127 in the copy: "lcp >= k" is
+                                 // still exact for k <= 127 (the plane A is derived from the exact values), so only -k > 127 needs
+                                 // the 4-byte stream then
     bool sealed = false;
     int lay_x = 4, lay_y = 4, lay_z = 4, lay_bcr = 0;  // layout of the index files (phantom record only)
     // record list
@@ -110,6 +118,13 @@ struct e2s_shard {
     int variant = 0;
     // chunked mode (streaming): the device buffers hold one chunk [global_off, global_off + n_local) of the shard's range at a time
     bool chunked = false;
+    // lean SoA mode (e2s_shard_host_gsa): text / suff stay on the host in the BCR pairSA layout; only the records of the clusters
+    // that reach phase 2 are fetched from there (capture_survivors), the last GSA_TAIL positions of the eBWT excepted
+    const uint8_t* host_gsa = nullptr;
+    int gsa_y = 4, gsa_z = 4;
+    uint64_t lean_h2d = 0, lean_d2h = 0;                    // bytes of the survivor fetches (for the callers' accounting)
+    SurvEntry* h_surv = nullptr; size_t h_surv_cap = 0;     // pinned
+    uint32_t* h_gather = nullptr; size_t h_gather_cap = 0;  // pinned: text values then suff values of one capture
     uint64_t range_lo = 0, range_n = 0;   // the shard's own range of the eBWT
     uint64_t chunk_cap = 0;               // positions the buffers hold
     bool chunk_open = false;              // a chunk has been begun and not yet scanned
@@ -236,6 +251,9 @@ void e2s_ctx_destroy(e2s_ctx* c) {
     cudaFree(c->d_reads_flag);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_soa_staged[i]) cudaEventDestroy(c->ev_soa_staged[i]);
+        if (c->ev_soa_free[i]) cudaEventDestroy(c->ev_soa_free[i]);
+        cudaFree(c->d_soa_stage[i]);
         if (c->ev_unpacked[i]) cudaEventDestroy(c->ev_unpacked[i]);
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
@@ -435,6 +453,8 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->suff_a);
     cudaFree(s->bwt_a);
     cudaFree(s->lcpt);
+    if (s->h_surv) cudaFreeHost(s->h_surv);
+    if (s->h_gather) cudaFreeHost(s->h_gather);
     cudaFree(s->d_start);
     cudaFree(s->d_len);
     cudaFree(s->d_desc);
@@ -692,6 +712,99 @@ int e2s_shard_load_soa_dev(e2s_shard* s, const uint32_t* lcp, const uint32_t* te
     return load_soa(s, lcp, text, suff, bwt, first, count, cudaMemcpyDeviceToDevice);
 }
 
+// ---- lean SoA inputs (the BCR triple: X.out.lcp, X.out, X.out.pairSA; ref:include.hpp:157-188) -----------------------------
+// Phase 1 and the prefilter need the LCP and the BWT only: 1 + x bytes per position cross PCIe instead of the 13 of an EGSA
+// record.  text / suff (the pairSA file) stay on the host; the records of the ~0.1 % of the clusters that reach phase 2 are
+// fetched from there when a chunk's survivors are captured.
+int e2s_shard_host_gsa(e2s_shard* s, const void* pair_sa, int y, int z) {
+    if (!s) return fail(nullptr, E2S_ERR_ARG, "shard == NULL");
+    auto ok = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8; };
+    if (!s->chunked) return fail(s->ctx, E2S_ERR_STATE, "e2s_shard_host_gsa: chunked shards only (the survivors' records are captured per chunk)");
+    if (pair_sa && (!ok(y) || !ok(z))) return fail(s->ctx, E2S_ERR_ARG, "field byte sizes must be 1, 2, 4 or 8");
+    s->host_gsa = static_cast<const uint8_t*>(pair_sa);
+    s->gsa_y = y;
+    s->gsa_z = z;
+    return E2S_OK;
+}
+
+// the text / suff of the last GSA_TAIL positions of the eBWT, as far as [a, b) holds them: the phantom records past EOF are made
+// of them, and clusters that start there are captured from the device
+static int lean_load_tail(e2s_shard* s, uint64_t a, uint64_t b) {
+    e2s_ctx* c = s->ctx;
+    if (!s->host_gsa) return E2S_OK;
+    const uint64_t tail_lo = s->n_global > GSA_TAIL ? s->n_global - GSA_TAIL : 0;
+    const uint64_t ta = a > tail_lo ? a : tail_lo;
+    if (ta >= b) return E2S_OK;
+    std::vector<uint32_t> t(size_t(b - ta)), sf(size_t(b - ta));
+    const int rs = s->gsa_y + s->gsa_z;
+    for (uint64_t p = ta; p < b; ++p) {
+        const uint8_t* g = s->host_gsa + p * uint64_t(rs);
+        uint32_t vs = 0, vt = 0;
+        for (int q = 0; q < (s->gsa_z < 4 ? s->gsa_z : 4); ++q) vs |= uint32_t(g[q]) << (8 * q);
+        for (int q = 0; q < (s->gsa_y < 4 ? s->gsa_y : 4); ++q) vt |= uint32_t(g[s->gsa_z + q]) << (8 * q);
+        sf[size_t(p - ta)] = vs;
+        t[size_t(p - ta)] = vt;
+    }
+    const int64_t lt = int64_t(ta) - int64_t(s->global_off);
+    CU(c, cudaMemcpyAsync(s->text + lt, t.data(), (b - ta) * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(s->suff + lt, sf.data(), (b - ta) * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));  // (the vectors go out of scope)
+    return E2S_OK;
+}
+
+// lcp (x bytes per position) + BWT bytes of the global positions [first, first + count) -> the shard's resident arrays and their
+// narrow copies.  dev: the sources are device memory (a staging buffer the caller filled), else host memory.
+static int load_lcp_bwt(e2s_shard* s, const void* lcp, int x, const uint8_t* bwt, uint64_t first, uint64_t count, bool dev) {
+    e2s_ctx* c = s->ctx;
+    uint64_t lo, hi;
+    keep_range(s, &lo, &hi);
+    const uint64_t a = first > lo ? first : lo, b = first + count < hi ? first + count : hi;
+    if (a >= b) return E2S_OK;
+    s->lay_x = x;
+    const uint8_t* src = static_cast<const uint8_t*>(lcp);
+    const int64_t l0 = int64_t(a) - int64_t(s->global_off);
+    const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (x == 4) {  // already at the resident width
+        CU(c, cudaMemcpyAsync(s->lcp + l0, src + (a - first) * 4, (b - a) * 4, kind, c->stream));
+    } else if (dev) {
+        CU(c, launch_widen(src + (a - first) * uint64_t(x), x, s->lcp + l0, b - a, c->stream, c->sm_count));
+        ++c->launches;
+    } else {
+        const uint64_t piece = uint64_t(1) << 24;
+        const size_t need = size_t(piece) * x + 64;
+        if (need > c->raw_cap) {
+            CU(c, cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < 2; ++i) {
+                cudaFree(c->d_raw[i]);
+                c->d_raw[i] = nullptr;
+            }
+            c->raw_cap = 0;
+            for (int i = 0; i < 2; ++i)
+                if (cudaMalloc(reinterpret_cast<void**>(&c->d_raw[i]), need) != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "raw staging buffer");
+            c->raw_cap = need;
+        }
+        for (uint64_t p = a; p < b; p += piece) {  // (one stream: the staging buffer is free again when the widening kernel has run)
+            const uint64_t cnt = b - p < piece ? b - p : piece;
+            CU(c, cudaMemcpyAsync(c->d_raw[0], src + (p - first) * uint64_t(x), cnt * uint64_t(x), cudaMemcpyHostToDevice, c->stream));
+            CU(c, launch_widen(c->d_raw[0], x, s->lcp + (int64_t(p) - int64_t(s->global_off)), cnt, c->stream, c->sm_count));
+            ++c->launches;
+        }
+    }
+    CU(c, cudaMemcpyAsync(s->bwt + l0, bwt + (a - first), b - a, kind, c->stream));
+    CU(c, derive_loaded(s, l0, b - a, true, true));
+    ++c->launches;
+    s->sealed = false;
+    return lean_load_tail(s, a, b);
+}
+
+int e2s_shard_load_lcp_bwt(e2s_shard* s, const void* lcp, int x, const uint8_t* bwt, uint64_t first, uint64_t count) {
+    if (!s || !lcp || !bwt) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_shard_load_lcp_bwt: NULL argument");
+    e2s_ctx* c = s->ctx;
+    if (!(x == 1 || x == 2 || x == 4 || x == 8)) return fail(c, E2S_ERR_ARG, "field byte sizes must be 1, 2, 4 or 8");
+    CU(c, cudaSetDevice(c->device));
+    return load_lcp_bwt(s, lcp, x, bwt, first, count, false);
+}
+
 int e2s_build_egsa_dev(e2s_ctx* c, const uint8_t* d_reads, uint64_t n_reads, uint32_t read_len, uint32_t* d_lcp, uint32_t* d_text,
                        uint32_t* d_suff, uint8_t* d_bwt) {
     if (!c || !d_reads || !d_lcp || !d_text || !d_suff || !d_bwt) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_dev: NULL argument");
@@ -769,19 +882,26 @@ int e2s_shard_seal(e2s_shard* s) {
     // The byte LCP and the bit planes were written by the loads themselves: sealing costs no pass over the data, only
     // the verdict whether every LCP value the scan looks at fits the byte copy (E2S_LCP_WIDE=1 keeps the 4-byte stream,
     // for A/B measurements and the tests)
-    s->lcpt_ok = false;
+    s->lcpt_ok = s->lcpt_sat = false;
     const char* wide = getenv("E2S_LCP_WIDE");
     if (s->lcpt && !(wide && atoi(wide) != 0)) {
         uint32_t h_flag = 1;
         CU(c, cudaMemcpyAsync(&h_flag, s->d_seal_flag, 4, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
-        s->lcpt_ok = h_flag == 0;
+        s->lcpt_ok = true;
+        s->lcpt_sat = h_flag != 0;
     }
     s->sealed = true;
     return E2S_OK;
 }
 
 int e2s_shard_lcp_bytes_resident(const e2s_shard* s) { return s ? (s->sealed && s->lcpt_ok ? 1 : 4) : 0; }
+
+// may k_cluster_scan run on this shard with these options?  (min_len <= 33: the bit-parallel length test; the saturated
+// bit-sliced LCP compares exactly against k <= 127 whatever the values, against any k when nothing was saturated)
+static bool one_pass_ok(const e2s_shard* s, uint32_t k, int32_t min_len) {
+    return s->sealed && s->lcpt_ok && (!s->lcpt_sat || k <= 127u) && min_len <= 33;
+}
 
 // one pass over the staged reads: does any byte fall outside ACGTacgt?  (K4's consensus then needs base_to_int's general rule)
 static int reads_check(e2s_ctx* c) {
@@ -916,7 +1036,7 @@ static int scan_enqueue(e2s_shard* s, uint32_t k, int32_t min_len) {
     s->variant = env ? atoi(env) : 0;
     // One pass over the byte LCP (k_cluster_scan) whenever the shard has it and min_len allows the bit-parallel length
     // test; else the two-kernel path on the 4-byte LCP (k_lcp_flags + k_cluster_emit).  E2S_SCAN_LEGACY=1 forces the latter.
-    const bool one_pass = s->last_one_pass = s->sealed && s->lcpt_ok && min_len <= 33 && !getenv("E2S_SCAN_LEGACY");
+    const bool one_pass = s->last_one_pass = one_pass_ok(s, k, min_len) && !getenv("E2S_SCAN_LEGACY");
     const uint64_t num_tiles = emit_num_tiles(s->n_local);
     if (one_pass) {
         if (!s->d_chunks) {
@@ -1167,6 +1287,7 @@ static cudaError_t grow_keep(T*& ptr, uint64_t& cap, uint64_t used, uint64_t nee
 extern "C" {
 
 // copies the records of the survivors listed in d_pf_list[0, n) (base relative to the resident chunk) to the payload
+
 static int capture_survivors(e2s_shard* s, uint64_t n) {
     e2s_ctx* c = s->ctx;
     if (!n) return E2S_OK;
@@ -1204,8 +1325,67 @@ static int capture_survivors(e2s_shard* s, uint64_t n) {
                     "chunked shard: a cluster of 65 536 or more positions whose wrapped length passes the filters has left the device "
                     "(use a resident shard for this input)");
     if (hc[2]) return fail(c, E2S_ERR_STATE, "chunked shard: payload / survivor list capacity");
+    const uint64_t pay0 = s->pay_used, surv0 = s->surv_count;
     s->pay_used = hc[0];
     s->surv_count = hc[1];
+    if (s->host_gsa && hc[1] > surv0) {  // lean SoA mode: text / suff of the captured records come from the host's pairSA
+        const uint64_t n_new = hc[1] - surv0, n_pay = hc[0] - pay0;
+        if (n_new > s->h_surv_cap) {
+            if (s->h_surv) cudaFreeHost(s->h_surv);
+            s->h_surv = nullptr;
+            s->h_surv_cap = 0;
+            CU(c, cudaHostAlloc(reinterpret_cast<void**>(&s->h_surv), (n_new + n_new / 4 + 1024) * sizeof(SurvEntry), cudaHostAllocDefault));
+            s->h_surv_cap = n_new + n_new / 4 + 1024;
+        }
+        if (2 * n_pay > s->h_gather_cap) {
+            if (s->h_gather) cudaFreeHost(s->h_gather);
+            s->h_gather = nullptr;
+            s->h_gather_cap = 0;
+            CU(c, cudaHostAlloc(reinterpret_cast<void**>(&s->h_gather), (2 * n_pay + n_pay / 2 + 4096) * 4, cudaHostAllocDefault));
+            s->h_gather_cap = 2 * n_pay + n_pay / 2 + 4096;
+        }
+        CU(c, cudaMemcpyAsync(s->h_surv, s->d_surv + surv0, n_new * sizeof(SurvEntry), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        uint32_t* g_text = s->h_gather;
+        uint32_t* g_suff = s->h_gather + n_pay;
+        const uint64_t tail_lo = s->n_global > GSA_TAIL ? s->n_global - GSA_TAIL : 0;
+        const int y = s->gsa_y, z = s->gsa_z, rs = y + z;
+        auto le = [](const uint8_t* q, int nb) {
+            uint32_t v = 0;
+            for (int b = 0; b < (nb < 4 ? nb : 4); ++b) v |= uint32_t(q[b]) << (8 * b);
+            return v;
+        };
+        bool any_tail = false;
+        for (uint64_t i = 0; i < n_new; ++i) {
+            const SurvEntry& e = s->h_surv[i];
+            const uint64_t o = e.base - pay0;
+            if (e.start >= tail_lo) {  // the device holds text / suff of these positions (and of the phantom records behind them)
+                any_tail = true;
+                continue;
+            }
+            const uint8_t* g = s->host_gsa + e.start * uint64_t(rs);  // suff(z) then text(y): ref:include.hpp:159-175
+            // (an adopted record may run past the end of the eBWT: far longer than any analysed cluster, its records are never read)
+            const uint64_t have = e.start + e.len <= s->n_global ? e.len : s->n_global - e.start;
+            for (uint32_t j = 0; j < e.len; ++j, g += rs) {
+                g_suff[o + j] = j < have ? le(g, z) : 0u;
+                g_text[o + j] = j < have ? le(g + z, y) : 0u;
+            }
+        }
+        if (any_tail) {  // their captured values come back first so that one copy can overwrite the whole range
+            for (uint64_t i = 0; i < n_new; ++i) {
+                const SurvEntry& e = s->h_surv[i];
+                if (e.start < tail_lo) continue;
+                CU(c, cudaMemcpyAsync(g_text + (e.base - pay0), s->p_text + e.base, size_t(e.len) * 4, cudaMemcpyDeviceToHost, c->stream));
+                CU(c, cudaMemcpyAsync(g_suff + (e.base - pay0), s->p_suff + e.base, size_t(e.len) * 4, cudaMemcpyDeviceToHost, c->stream));
+            }
+            CU(c, cudaStreamSynchronize(c->stream));
+        }
+        CU(c, cudaMemcpyAsync(s->p_text + pay0, g_text, n_pay * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(s->p_suff + pay0, g_suff, n_pay * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));  // (the staging is reused by the next chunk)
+        s->lean_h2d += n_pay * 8;
+        s->lean_d2h += n_new * sizeof(SurvEntry);
+    }
     return E2S_OK;
 }
 
@@ -1220,9 +1400,9 @@ int e2s_chunk_scan(e2s_shard* s, uint32_t k, int32_t min_len, int mcov_out, uint
     if (mcov_out < 0 || 2 * mcov_out > E2S_MAX_C_LEN) return fail(c, E2S_ERR_ARG, "e2s_chunk_scan: need 0 <= 2 * mcov_out <= 150");
     int rc = e2s_shard_seal(s);
     if (rc) return rc;
-    if (!s->lcpt_ok || min_len > 33)
+    if (!one_pass_ok(s, k, min_len))
         return fail(c, E2S_ERR_UNSUPPORTED,
-                    "chunked shards need the one-pass scan: every LCP value <= 127 (reads shorter than 128 bases) and -m <= 33; "
+                    "chunked shards need the one-pass scan: -m <= 33, and -k <= 127 when an LCP value exceeds 127; "
                     "use a resident shard for this input");
     if (!s->h_pin) CU(c, cudaHostAlloc(reinterpret_cast<void**>(&s->h_pin), sizeof(ClusterDev), cudaHostAllocDefault));
     ClusterDev& h = *s->h_pin;
@@ -2240,7 +2420,7 @@ int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, in
     uint64_t off_rec = 0;
     bool unsupported_first = false;
     rc = stream_range(s, gesa, 0, x, y, z, k, min_len, p->mcov_out, rec10, cap_records, &off_rec, res, &unsupported_first);
-    if (unsupported_first)  // e.g. an LCP value above 127: the resident two-kernel path takes it
+    if (unsupported_first)  // e.g. -m > 33: the resident two-kernel path takes it
         return pipeline_host_resident(c, gesa, n, x, y, z, k, min_len, p, rec10, cap_records, events, cap_events, res);
     if (rc) return rc;
     e2s_cluster_summary sum;
@@ -2279,6 +2459,150 @@ int e2s_pipeline_host(e2s_ctx* c, const void* gesa, uint64_t n, int x, int y, in
     return E2S_OK;
 }
 
+
+// ebwt2clust + clust2snp from the BCR triple in host memory, lean: only X.out.lcp (x bytes per position) and X.out (1 byte) are
+// copied to the device in full; X.out.pairSA stays on the host and only the survivors' records are fetched from it.  Same
+// outputs as e2s_pipeline_host on the same index.  Needs the one-pass scan (-m <= 33; -k <= 127 when an LCP value exceeds 127) and 2 <= 2 mcov <= 150.
+int e2s_pipeline_host_soa(e2s_ctx* c, const void* lcp, int x, const uint8_t* bwt, const void* pair_sa, int y, int z, uint64_t n,
+                          const uint8_t* read_bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k, int32_t min_len,
+                          const e2s_snp_params* p, void* rec10, uint64_t cap_records, e2s_event* events, uint64_t cap_events,
+                          e2s_pipeline_result* res) {
+    if (!c || !lcp || !bwt || !pair_sa || !p || !res) return fail(c, E2S_ERR_ARG, "NULL argument");
+    memset(res, 0, sizeof *res);
+    if (n < 2) return fail(c, E2S_ERR_ARG, "e2s_pipeline_host_soa: need at least 2 records");
+    const bool mcov_ok = p->mcov_out >= 1 && 2 * p->mcov_out <= E2S_MAX_C_LEN;
+    if (min_len > 33 || !mcov_ok) return fail(c, E2S_ERR_UNSUPPORTED, "e2s_pipeline_host_soa: needs -m <= 33 and 1 <= mcov_out <= 75");
+    int rc;
+    if (read_bases) {
+        if ((rc = e2s_reads_stage(c, read_bases, read_off, n_reads))) return rc;
+        res->h2d_bytes += read_off[n_reads] + (n_reads + 1) * 8;
+    }
+    const uint64_t chunk = chunk_positions_from_env();
+    e2s_shard* s = c->cached;
+    const uint64_t want_cap = round_up(chunk < 16384 ? 16384 : chunk, 16384) < round_up(n, 16384) ? round_up(chunk < 16384 ? 16384 : chunk, 16384) : round_up(n, 16384);
+    if (!s || !s->chunked || s->range_n != n || s->n_global != n || s->chunk_cap != want_cap) {
+        if (s) e2s_shard_destroy(s);
+        c->cached = nullptr;
+        if ((rc = e2s_shard_create_chunked(c, n, 0, n, chunk, &s))) return rc;
+        c->cached = s;
+    } else if ((rc = e2s_chunked_reset(s))) {
+        return rc;
+    }
+    if ((rc = e2s_shard_host_gsa(s, pair_sa, y, z))) return rc;
+    if ((rc = e2s_shard_set_layout(s, x, y, z, 1))) return rc;
+    s->lean_h2d = s->lean_d2h = 0;
+    uint64_t off_rec = 0;
+    const uint8_t* lsrc = static_cast<const uint8_t*>(lcp);
+    // The lcp + BWT bytes of chunk i + 1 cross PCIe on the copy stream, into one of two staging buffers, while chunk i is widened
+    // (from its staging buffer), scanned, its records fetched and its survivors' records gathered from the host's pairSA.
+    const uint64_t span = s->chunk_cap + PAD_L + MAX_C_LEN + 1;  // positions a chunk loads at most
+    const size_t stage_bytes = size_t(span) * size_t(x + 1) + 256;
+    if (c->soa_stage_cap < stage_bytes) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(c->d_soa_stage[i]);
+            c->d_soa_stage[i] = nullptr;
+        }
+        c->soa_stage_cap = 0;
+        for (int i = 0; i < 2; ++i)
+            if (cudaMalloc(reinterpret_cast<void**>(&c->d_soa_stage[i]), stage_bytes) != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "SoA staging buffers");
+        c->soa_stage_cap = stage_bytes;
+    }
+    if (!c->copy_stream) CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        if (!c->ev_soa_staged[i]) CU(c, cudaEventCreateWithFlags(&c->ev_soa_staged[i], cudaEventDisableTiming));
+        if (!c->ev_soa_free[i]) CU(c, cudaEventCreateWithFlags(&c->ev_soa_free[i], cudaEventDisableTiming));
+    }
+    auto bounds = [&](uint64_t lo, uint64_t* a, uint64_t* b) {
+        const uint64_t cn = n - lo < s->chunk_cap ? n - lo : s->chunk_cap;
+        *a = lo >= uint64_t(PAD_L) ? lo - PAD_L : 0;
+        *b = lo + cn + MAX_C_LEN + 1 < n ? lo + cn + MAX_C_LEN + 1 : n;
+    };
+    auto stage = [&](uint64_t lo, int buf, bool reused) -> cudaError_t {  // lcp bytes, then (64-byte aligned) the BWT bytes
+        uint64_t a, b;
+        bounds(lo, &a, &b);
+        cudaError_t e = cudaSuccess;
+        if (reused) e = cudaStreamWaitEvent(c->copy_stream, c->ev_soa_free[buf], 0);
+        uint8_t* d = c->d_soa_stage[buf];
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, lsrc + a * uint64_t(x), (b - a) * uint64_t(x), cudaMemcpyHostToDevice, c->copy_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d + round_up((b - a) * uint64_t(x), 64), bwt + a, b - a, cudaMemcpyHostToDevice, c->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev_soa_staged[buf], c->copy_stream);
+        return e;
+    };
+    CU(c, stage(0, 0, false));
+    uint64_t ci = 0;
+    for (uint64_t lo = 0; lo < n; lo += s->chunk_cap, ++ci) {
+        const uint64_t cn = n - lo < s->chunk_cap ? n - lo : s->chunk_cap;
+        const int buf = int(ci & 1);
+        if (lo + s->chunk_cap < n) {
+            const cudaError_t e = stage(lo + s->chunk_cap, buf ^ 1, ci >= 1);
+            if (e != cudaSuccess) {
+                rc = cuda_fail(c, e, "e2s_pipeline_host_soa: staging");
+                break;
+            }
+        }
+        if ((rc = e2s_chunk_begin(s, lo, cn))) break;
+        uint64_t a, b;
+        bounds(lo, &a, &b);
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_soa_staged[buf], 0));
+        const uint8_t* d = c->d_soa_stage[buf];
+        if ((rc = load_lcp_bwt(s, d, x, d + round_up((b - a) * uint64_t(x), 64), a, b - a, true))) break;
+        CU(c, cudaEventRecord(c->ev_soa_free[buf], c->stream));
+        if ((rc = e2s_shard_set_layout(s, x, y, z, 1))) break;
+        res->h2d_bytes += (b - a) * uint64_t(x + 1);
+        uint64_t m = 0;
+        if ((rc = e2s_chunk_scan(s, k, min_len, p->mcov_out, &m))) break;
+        if (rec10) {
+            if (off_rec + m > cap_records) {
+                rc = fail(c, E2S_ERR_ARG, "record capacity too small");
+                break;
+            }
+            uint64_t got = 0;
+            if (m && (rc = e2s_cluster_fetch_packed(s, static_cast<uint8_t*>(rec10) + off_rec * 10, cap_records - off_rec, &got))) break;
+            res->d2h_bytes += m * 10;
+        }
+        off_rec += m;
+    }
+    if (rc) cudaStreamSynchronize(c->copy_stream);  // (a staged copy may still be reading the caller's buffers)
+    e2s_shard_host_gsa(s, nullptr, 4, 4);  // (the caller's buffer is not ours to keep)
+    if (rc) return rc;
+    res->h2d_bytes += s->lean_h2d;
+    res->d2h_bytes += s->lean_d2h;
+    e2s_cluster_summary sum;
+    if ((rc = e2s_chunked_finish(s, k, min_len, &sum))) return rc;
+    e2s_cluster_merged mg;
+    if ((rc = e2s_cluster_merge(&sum, 1, 0, &mg))) {
+        c->err = g_err;
+        return rc;
+    }
+    if ((rc = e2s_cluster_finalize(s, &mg))) return rc;
+    if (rec10) {  // the records of the tail rule come last (ref:ebwt2clust.cpp:127-135)
+        if (off_rec + mg.n_append > cap_records) return fail(c, E2S_ERR_ARG, "e2s_pipeline_host_soa: record capacity too small");
+        for (uint32_t i = 0; i < mg.n_append; ++i) {
+            uint8_t* o = static_cast<uint8_t*>(rec10) + (off_rec + i) * 10;
+            const uint16_t l16 = uint16_t(mg.append_len[i]);
+            memcpy(o, &mg.append_start[i], 8);
+            memcpy(o + 8, &l16, 2);
+        }
+    }
+    res->n_written = mg.total_written;
+    res->n_clust_out = mg.n_clust_out;
+    if (res->n_written == 0) return fail(c, E2S_ERR_UNSUPPORTED, "no clusters (the reference divides by zero here)");
+    e2s_stats st;
+    if ((rc = e2s_statistics(s, &st))) return rc;
+    if ((rc = e2s_statistics_finish(&st, st.last_len, p->mcov_out, p->pval))) {
+        c->err = g_err;
+        return rc;
+    }
+    res->max_clust_length = st.max_clust_length;
+    if ((rc = e2s_find_events(s, p, st.max_clust_length, &res->snp))) return rc;
+    res->d2h_bytes += res->snp.n_candidates * snp_event_stride(s->work);
+    if (events) {
+        uint64_t nv = 0;
+        if ((rc = e2s_events_fetch(s, events, cap_events, &nv))) return rc;
+    }
+    return E2S_OK;
+}
 
 // After the last chunk of every rank's chunked shard: e2s_chunked_finish, ONE ncclAllGather of the ranks' rows (accumulators +
 // range, the format of the resident sharded step), merge + statistics() on every rank, e2s_cluster_finalize.  Collective.

@@ -295,6 +295,12 @@ int e2s_chunk_begin(e2s_shard *sh, uint64_t chunk_lo, uint64_t chunk_n);
 int e2s_chunk_scan(e2s_shard *sh, uint32_t k, int32_t min_len, int mcov_out, uint64_t *n_records);
 int e2s_chunked_finish(e2s_shard *sh, uint32_t k, int32_t min_len, e2s_cluster_summary *summary);
 int e2s_chunked_reset(e2s_shard *sh); /* stream the range again from its first chunk */
+/* Lean SoA inputs for a chunked shard: text / suff stay in the caller's pairSA buffer (suff(z) then text(y) per position, index =
+ * global position; it must stay valid until the last e2s_chunk_scan), chunks are loaded with e2s_shard_load_lcp_bwt (lcp at x
+ * bytes per position + BWT bytes: `lcp` / `bwt` point at the element of global position `first`), and e2s_chunk_scan fetches the
+ * records of the clusters that survive the prefilter from the host.  pair_sa == NULL switches the mode off. */
+int e2s_shard_host_gsa(e2s_shard *sh, const void *pair_sa, int y, int z);
+int e2s_shard_load_lcp_bwt(e2s_shard *sh, const void *lcp, int x, const uint8_t *bwt, uint64_t first, uint64_t count);
 /* Chunked shards on several GPUs (one process per GPU): after every rank's last chunk, e2s_chunked_finish + ONE ncclAllGather
  * of the ranks' accumulators + merge + statistics() + e2s_cluster_finalize.  Collective over the communicator. */
 int e2s_chunked_exchange(e2s_shard *sh, e2s_comm *comm, uint32_t k, int32_t min_len, int mcov_out, double pval,
@@ -343,6 +349,16 @@ int e2s_pipeline_host(e2s_ctx *ctx, const void *gesa_records, uint64_t n, int x,
                       uint32_t k, int32_t min_len, const e2s_snp_params *p,
                       void *rec10, uint64_t cap_records, e2s_event *events, uint64_t cap_events,
                       e2s_pipeline_result *res);
+
+/* The same from the BCR triple (ref:include.hpp:157-188: X.out.lcp = lcp(x) per position, X.out = BWT bytes, X.out.pairSA =
+ * suff(z) then text(y) per position), LEAN: phase 1 and the BWT prefilter need the LCP and the BWT only, so 1 + x bytes per
+ * position cross PCIe instead of the 13 of an EGSA record; the pairSA buffer stays on the host and only the records of the
+ * clusters that reach phase 2 (~0.1 %) are fetched from it.  Same outputs as e2s_pipeline_host on the same index.  Needs the
+ * one-pass scan (every LCP value <= 127, -m <= 33). */
+int e2s_pipeline_host_soa(e2s_ctx *ctx, const void *lcp, int x, const uint8_t *bwt, const void *pair_sa, int y, int z, uint64_t n,
+                          const uint8_t *read_bases, const uint64_t *read_off, uint64_t n_reads, uint32_t k, int32_t min_len,
+                          const e2s_snp_params *p, void *rec10, uint64_t cap_records, e2s_event *events, uint64_t cap_events,
+                          e2s_pipeline_result *res);
 
 /* The same for ONE eBWT over the GPUs of a box, one process (rank) per GPU: every rank streams its contiguous
  * range [range_lo, range_lo + range_n) of the records through a chunked shard -- it stages nothing but its range and the

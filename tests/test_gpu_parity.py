@@ -122,8 +122,9 @@ def test_cluster_narrow_lcp(ctx, wide, monkeypatch):
         assert mg.n_clust_out == enc and np.array_equal(S, es) and np.array_equal(L, el), (it, cuts)
 
 
-def test_lcp_above_127_stays_wide(ctx):
-    """one value of 128 anywhere in the shard (or its halo) keeps K1 on the 4-byte stream"""
+def test_lcp_above_127(ctx):
+    """LCP values above 127 (reads of 128 bases and more) are saturated in the bit-sliced copy: the one-pass scan stays exact
+    for -k <= 127 (the descent plane comes from the exact values); -k > 127 goes to the 4-byte kernels.  Both against the oracle."""
     n = 50000
     lcp = np.full(n, 20, dtype=np.uint32)
     bwt = np.full(n, ord("C"), dtype=np.uint8)
@@ -133,12 +134,34 @@ def test_lcp_above_127_stays_wide(ctx):
         sh = ctx.shard(n)
         sh.load_soa(l2, None, None, bwt)
         sh.seal()
-        assert sh.lcp_bytes_resident() == 4
-        es, el, enc, _ = O.cluster_lm(l2, bwt, 16, 2)
-        nw, nc = sh.cluster_lm(16, 2)
-        s, l = sh.cluster_fetch()
+        assert sh.lcp_bytes_resident() == 1
+        for k in (16, 128):
+            es, el, enc, _ = O.cluster_lm(l2, bwt, k, 2)
+            if len(es) == 0:
+                continue
+            nw, nc = sh.cluster_lm(k, 2)
+            s, l = sh.cluster_fetch()
+            assert nc == enc and np.array_equal(s, es) and np.array_equal(l, el), (pos, k)
         sh.close()
-        assert nc == enc and np.array_equal(s, es) and np.array_equal(l, el)
+    rng = np.random.default_rng(128)
+    for it, n in enumerate([16385, 100003, 262144 + 7, 300001]):
+        for k in (1, 16, 100, 127, 128, 150, 260):
+            m = int(rng.choice([1, 2, 3, 8, 33]))
+            if it % 2:  # random walks around 127 / around k: runs above and below both thresholds, local minima among saturated values
+                lcp = np.clip(np.cumsum(rng.integers(-3, 4, size=n)) + (125 if it == 1 else k), 0, 255).astype(np.uint32)
+            else:
+                lcp = rng.choice(np.array([0, 1, k - 1 if k > 1 else 0, k, k + 1, 126, 127, 128, 129, 200, 255, 70000], dtype=np.uint32), size=n)
+            bwt = rng.choice(H.BWT_ALPHABET, size=n)
+            es, el, enc, _ = O.cluster_lm(lcp, bwt, k, m)
+            if len(es) == 0:
+                continue
+            sh = ctx.shard(n)
+            sh.load_soa(lcp, None, None, bwt)
+            sh.seal()
+            nw, nc = sh.cluster_lm(k, m)
+            s, l = sh.cluster_fetch()
+            sh.close()
+            assert nc == enc and np.array_equal(s, es) and np.array_equal(l, el), (it, n, k, m)
 
 
 def test_cluster_sharded(ctx):

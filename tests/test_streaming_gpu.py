@@ -113,61 +113,75 @@ def test_chunked_pipeline_equals_oracle(ctx, name, seed, monkeypatch):
         assert api.events_format(list(evbuf)[: res.snp.n_variants], p) == otext, chunk
 
 
-def test_chunked_needs_byte_lcp(ctx):
-    """an LCP value above 127 keeps a shard off the one-pass scan: chunked shards say so, e2s_pipeline_host falls back"""
+def test_chunked_lcp_above_127(ctx):
+    """LCP values above 127 (saturated in the bit-sliced copy) stream through chunked shards for -k <= 127; -k > 127 on such a
+    shard is refused by the chunk API (e2s_pipeline_host falls back to a resident shard)"""
     rs, e = H.dataset("tiny", 4)
     n = e["n"]
     lcp = e["lcp"].copy()
-    lcp[n // 2] = 200
+    rng = np.random.default_rng(9)
+    at = rng.integers(0, n, size=n // 50)
+    lcp[at] = rng.integers(128, 256, size=len(at))
+    for k, m in ((16, 2), (127, 2)):
+        es, el, enc, _ = O.cluster_lm(lcp, e["bwt"], k, m)
+        for chunk in (n // 3, 16384):
+            sm, s, l, sh = stream_phase1(ctx, lcp, e["bwt"], k, m, chunk)
+            S, L, mg = H.assemble([sm], [(s, l)])
+            sh.close()
+            assert mg.n_clust_out == enc and np.array_equal(S, es) and np.array_equal(L, el), (k, chunk)
     sh = ctx.shard(n, 0, n, chunk_positions=65536)
     clo, cn = next(iter(sh.chunks()))
     sh.chunk_begin(clo, cn)
-    sh.load_soa(lcp[: cn + 152], e["text"][: cn + 152], e["suff"][: cn + 152], e["bwt"][: cn + 152], first=0)
-    if n // 2 < cn + 1:
-        with pytest.raises(api.E2SError) as ei:
-            sh.chunk_scan(16, 2, 5)
-        assert ei.value.code == api.ERR_UNSUPPORTED
+    hi = min(n, cn + 152)
+    sh.load_soa(lcp[:hi], e["text"][:hi], e["suff"][:hi], e["bwt"][:hi], first=0)
+    with pytest.raises(api.E2SError) as ei:
+        sh.chunk_scan(128, 2, 5)
+    assert ei.value.code == api.ERR_UNSUPPORTED
     sh.close()
-    es, el, enc, _ = O.cluster_lm(lcp, e["bwt"], 16, 2)
     eg = dict(e)
     eg["lcp"] = lcp
     rec = synth.gesa_records(eg).view(np.uint8).reshape(-1)
     off = O.uniform_read_offsets(*rs.reads.shape)
-    p = api.default_params(rs.nreads1)
-    rec10 = np.empty((len(es) + 16) * 10, dtype=np.uint8)
-    res = ctx.pipeline_host(rec, n, rs.reads.reshape(-1), off, p, 16, 2, rec10=rec10)
-    assert res.n_written == len(es) and rec10[: len(es) * 10].tobytes() == O.clusters_to_bytes(es, el)
+    p, op = api.default_params(rs.nreads1), O.default_params(rs.nreads1)
+    for k in (16, 128):
+        es, el, enc, _ = O.cluster_lm(lcp, e["bwt"], k, 2)
+        rec10 = np.empty((len(es) + 16) * 10, dtype=np.uint8)
+        res = ctx.pipeline_host(rec, n, rs.reads.reshape(-1), off, p, k, 2, rec10=rec10)
+        assert res.n_written == len(es) and rec10[: len(es) * 10].tobytes() == O.clusters_to_bytes(es, el), k
+        ost = O.statistics(es, el, op.mcov_out, op.pval)
+        _, ores = O.find_events(lcp, e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+        assert (res.snp.n_candidates, res.snp.n_events) == (ores.n_candidates, ores.n_events), k
 
 
-def test_load_gesa_from_file_descriptor(ctx, tmp_path, monkeypatch):
-    """e2s_shard_load_gesa_fd: the index straight from the file through the pinned ring (several pieces, 3 reader threads), whole
-    range and a sub-range with halos, against the oracle"""
-    import os
-    rs, e = H.dataset("small", 2)
+@pytest.mark.parametrize("name,seed", [("tiny", 4), ("small", 2)])
+@pytest.mark.parametrize("xyz", [(4, 4, 4), (1, 4, 1), (2, 8, 2)])
+def test_lean_soa_pipeline_equals_oracle(ctx, name, seed, xyz, monkeypatch):
+    """e2s_pipeline_host_soa: the BCR triple with only lcp + bwt sent to the device in full and the survivors' text / suff
+    fetched from the host's pairSA -- same .clusters / .snp bytes as the oracle, whatever the chunk size and field widths"""
+    x, y, z = xyz
+    rs, e = H.dataset(name, seed)
     n = e["n"]
-    rec = synth.gesa_records(e).view(np.uint8).reshape(-1)
-    path = tmp_path / "x.gesa"
-    rec.tofile(path)
-    monkeypatch.setenv("E2S_READ_THREADS", "3")
     k, m = 16, 2
     es, el, enc, _ = O.cluster_lm(e["lcp"], e["bwt"], k, m)
-    fd = os.open(path, os.O_RDONLY)
-    try:
-        sh = ctx.shard(n, 0, n)
-        sh.load_gesa_fd(fd, 0, n)
-        sh.seal()
-        nw, nc = sh.cluster_lm(k, m)
-        s, l = sh.cluster_fetch()
-        assert nc & 0xFFFFFFFF == enc and nw == len(es) and np.array_equal(s, es) and np.array_equal(l, el)
-        sh.close()
-        lo, hi = n // 3 + 5, 2 * n // 3 + 11
-        sh = ctx.shard(hi - lo, lo, n)
-        sh.load_gesa_fd(fd, 0, n)  # (the shard keeps its range + halos)
-        sh.seal()
-        sm = sh.cluster_run(k, m)
-        s2, l2 = sh.cluster_fetch()
-        want, ws, wl = H.emulate_shard(e["lcp"], e["bwt"], lo, hi, k, m)
-        assert np.array_equal(s2, ws) and np.array_equal(l2, wl) and sm.n_end == want.n_end
-        sh.close()
-    finally:
-        os.close(fd)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    p, op = api.default_params(rs.nreads1), O.default_params(rs.nreads1)
+    ost = O.statistics(es, el, op.mcov_out, op.pval)
+    otext, ores = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+    assert ores.n_candidates > 0
+    want_clusters = O.clusters_to_bytes(es, el)
+    lcp = np.ascontiguousarray(e["lcp"].astype(f"<u{x}")).view(np.uint8)
+    pair = np.empty(n, dtype=np.dtype([("suff", f"<u{z}"), ("text", f"<u{y}")]))
+    pair["suff"], pair["text"] = e["suff"], e["text"]
+    pair = pair.view(np.uint8)
+    bwt = np.ascontiguousarray(e["bwt"])
+    for chunk in (n, n // 3, 100_003, 16384):
+        monkeypatch.setenv("E2S_CHUNK_POSITIONS", str(chunk))
+        rec10 = np.empty((len(es) + 16) * 10, dtype=np.uint8)
+        evbuf = (api.Event * (ores.n_candidates + 16))()
+        res = ctx.pipeline_host_soa(lcp, bwt, pair, n, rs.reads.reshape(-1), off, p, k, m, x, y, z, rec10=rec10, events=evbuf)
+        assert res.n_written == len(es) and rec10[: len(es) * 10].tobytes() == want_clusters, chunk
+        assert (res.n_clust_out, res.max_clust_length) == (enc, ost.max_clust_length)
+        assert res.snp.n_candidates == ores.n_candidates
+        assert api.events_format(list(evbuf)[: res.snp.n_variants], p) == otext, chunk
+        if x == 1 and chunk == n:  # lcp + bwt in full, the survivors' records only: far from the 13 B/position of EGSA records
+            assert res.h2d_bytes - rs.reads.size - 8 * len(off) < 6 * n, (res.h2d_bytes, n)
