@@ -87,7 +87,7 @@ SYMBOLS = [
     "e2s_events_format", "e2s_free", "e2s_pipeline_resident", "e2s_pipeline_host",
     "e2s_comm_unique_id", "e2s_comm_create", "e2s_comm_destroy", "e2s_pipeline_sharded",
     "e2s_exchange_row_words", "e2s_exchange_rows_finish",
-    "e2s_pipeline_host_soa", "e2s_shard_host_gsa", "e2s_shard_load_lcp_bwt",
+    "e2s_pipeline_host_soa", "e2s_shard_host_gsa", "e2s_shard_load_lcp_bwt", "e2s_shard_load_bcr",
     "e2s_pipeline_host_sharded", "e2s_shard_create_chunked", "e2s_shard_chunk_positions", "e2s_chunk_begin", "e2s_chunk_scan", "e2s_chunked_finish", "e2s_chunked_reset", "e2s_chunked_exchange",
 ]
 
@@ -177,6 +177,7 @@ def load_library():
                                           C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PipelineResult)]
     lib.e2s_shard_host_gsa.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.e2s_shard_load_lcp_bwt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64]
+    lib.e2s_shard_load_bcr.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
     lib.e2s_pipeline_host_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                               C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(SnpParams),
                                               C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64,
@@ -498,6 +499,17 @@ class Shard:
             self.ctx._ck(self.lib.e2s_shard_load_soa(self.h, *[_ptr(a) for a in arrs], int(first), count))
         self.ctx.synchronize()
 
+    def load_bcr(self, lcp, bwt, pair_sa, x, y, z, first=0):
+        """the BCR triple as byte buffers (lcp at x bytes, BWT, pairSA = suff(z) text(y)); pair_sa=None: lcp + BWT only"""
+        count = len(bwt)
+        lcp, bwt = np.ascontiguousarray(lcp).view(np.uint8), np.ascontiguousarray(bwt, dtype=np.uint8)
+        if pair_sa is None:
+            self.ctx._ck(self.lib.e2s_shard_load_lcp_bwt(self.h, _ptr(lcp), x, _ptr(bwt), int(first), count))
+        else:
+            pair_sa = np.ascontiguousarray(pair_sa).view(np.uint8)
+            self.ctx._ck(self.lib.e2s_shard_load_bcr(self.h, _ptr(lcp), x, _ptr(bwt), _ptr(pair_sa), y, z, int(first), count))
+        self.ctx.synchronize()
+
     def set_layout(self, x=4, y=4, z=4, bcr=False):
         """byte widths / format of the index files the arrays came from (the reference's phantom record depends on it)"""
         self.ctx._ck(self.lib.e2s_shard_set_layout(self.h, x, y, z, int(bcr)))
@@ -506,7 +518,7 @@ class Shard:
         self.ctx._ck(self.lib.e2s_shard_seal(self.h))
 
     def lcp_bytes_resident(self) -> int:
-        """1 when K1 streams the one-byte LCP copy built at seal (all values <= 127), else 4"""
+        """1 when the scan streams the bit-sliced LCP copy the loads wrote (values above 127 saturated: exact for -k <= 127), else 4"""
         return int(self.lib.e2s_shard_lcp_bytes_resident(self.h))
 
     # ---- phase 1 -----------------------------------------------------------------------

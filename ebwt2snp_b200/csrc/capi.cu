@@ -797,6 +797,48 @@ static int load_lcp_bwt(e2s_shard* s, const void* lcp, int x, const uint8_t* bwt
     return lean_load_tail(s, a, b);
 }
 
+// The whole BCR triple of [first, first + count): lcp + BWT as above, and X.out.pairSA (suff(z) then text(y) per position,
+// ref:include.hpp:157-188) copied as it is in the file and split / widened on the device.
+int e2s_shard_load_bcr(e2s_shard* s, const void* lcp, int x, const uint8_t* bwt, const void* pair_sa, int y, int z, uint64_t first,
+                       uint64_t count) {
+    if (!s || !lcp || !bwt || !pair_sa) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_shard_load_bcr: NULL argument");
+    e2s_ctx* c = s->ctx;
+    auto ok = [](int v) { return v == 1 || v == 2 || v == 4 || v == 8; };
+    if (!ok(x) || !ok(y) || !ok(z)) return fail(c, E2S_ERR_ARG, "field byte sizes must be 1, 2, 4 or 8");
+    CU(c, cudaSetDevice(c->device));
+    int rc = load_lcp_bwt(s, lcp, x, bwt, first, count, false);
+    if (rc) return rc;
+    uint64_t lo, hi;
+    keep_range(s, &lo, &hi);
+    const uint64_t a = first > lo ? first : lo, b = first + count < hi ? first + count : hi;
+    if (a >= b) return E2S_OK;
+    s->lay_y = y; s->lay_z = z; s->lay_bcr = 1;
+    const int rs = y + z;
+    const uint64_t piece = uint64_t(1) << 22;
+    const size_t need = size_t(piece) * size_t(rs) + 64;
+    if (need > c->raw_cap) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(c->d_raw[i]);
+            c->d_raw[i] = nullptr;
+        }
+        c->raw_cap = 0;
+        for (int i = 0; i < 2; ++i)
+            if (cudaMalloc(reinterpret_cast<void**>(&c->d_raw[i]), need) != cudaSuccess) return fail(c, E2S_ERR_NOMEM, "raw staging buffer");
+        c->raw_cap = need;
+    }
+    const uint8_t* src = static_cast<const uint8_t*>(pair_sa);
+    uint64_t i = 0;
+    for (uint64_t p = a; p < b; p += piece, ++i) {  // (one stream: a staging buffer is free again when the kernel that read it has run)
+        const uint64_t cnt = b - p < piece ? b - p : piece;
+        const int64_t l = int64_t(p) - int64_t(s->global_off);
+        CU(c, cudaMemcpyAsync(c->d_raw[i & 1], src + (p - first) * uint64_t(rs), cnt * uint64_t(rs), cudaMemcpyHostToDevice, c->stream));
+        CU(c, launch_widen_pairs(c->d_raw[i & 1], z, y, s->suff + l, s->text + l, cnt, c->stream, c->sm_count));
+        ++c->launches;
+    }
+    return E2S_OK;
+}
+
 int e2s_shard_load_lcp_bwt(e2s_shard* s, const void* lcp, int x, const uint8_t* bwt, uint64_t first, uint64_t count) {
     if (!s || !lcp || !bwt) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_shard_load_lcp_bwt: NULL argument");
     e2s_ctx* c = s->ctx;

@@ -266,6 +266,31 @@ cudaError_t launch_widen(const uint8_t* d_src, int w, uint32_t* d_dst, uint64_t 
     return cudaGetLastError();
 }
 
+// records of two little-endian fields (wa bytes, then wb bytes) -> two u32 arrays (the BCR pairSA file: suff then text)
+__global__ void __launch_bounds__(256) k_widen_pairs(const uint8_t* __restrict__ src, int wa, int wb, uint32_t* __restrict__ da,
+                                                     uint32_t* __restrict__ db, uint64_t cnt) {
+    auto le = [](const uint8_t* q, int w) {
+        uint32_t v = q[0];
+        if (w >= 2) v |= uint32_t(q[1]) << 8;
+        if (w >= 4) v |= (uint32_t(q[2]) << 16) | (uint32_t(q[3]) << 24);
+        return v;
+    };
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < cnt; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint8_t* q = src + i * uint64_t(wa + wb);
+        da[i] = le(q, wa);
+        db[i] = le(q + wa, wb);
+    }
+}
+
+cudaError_t launch_widen_pairs(const uint8_t* d_src, int wa, int wb, uint32_t* d_a, uint32_t* d_b, uint64_t cnt, cudaStream_t stream,
+                               int sm_count) {
+    if (!cnt) return cudaSuccess;
+    uint64_t blocks = (cnt + 255) / 256;
+    if (blocks > uint64_t(sm_count) * 16) blocks = uint64_t(sm_count) * 16;
+    k_widen_pairs<<<unsigned(blocks), 256, 0, stream>>>(d_src, wa, wb, d_a, d_b, cnt);
+    return cudaGetLastError();
+}
+
 // The record "read" after EOF.  read_el's temporaries share one 8-byte stack slot and a
 // failed read leaves it as the last valid record left it: byte 0 = bwt[n-1] (read last); byte b >= 1 = byte b of
 // the last-read field wider than b: lcp, then suff, then text for the EGSA record order (text suff lcp), lcp, then

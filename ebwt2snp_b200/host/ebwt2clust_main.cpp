@@ -98,7 +98,7 @@ int main(int argc, char** argv) {
         sh[size_t(g)] = nullptr;
         int r = e2s_shard_create(ctx[size_t(g)], hi - lo, lo, idx.n, &sh[size_t(g)]);
         const uint64_t a = lo >= 2 ? lo - 2 : 0, b = hi + E2S_MAX_C_LEN + 1 < idx.n ? hi + E2S_MAX_C_LEN + 1 : idx.n;
-        if (!r) r = idx.load(sh[size_t(g)], a, b - a);
+        if (!r) r = idx.load(sh[size_t(g)], a, b - a, false);
         if (!r) r = e2s_shard_set_layout(sh[size_t(g)], idx.x, idx.y, idx.z, idx.bcr ? 1 : 0);
         if (!r) r = e2s_shard_seal(sh[size_t(g)]);
         if (!r) r = e2s_cluster_run(sh[size_t(g)], uint32_t(k), min_len, &sums[size_t(g)]);
@@ -128,7 +128,7 @@ int main(int argc, char** argv) {
                 const uint64_t cn = hi - clo < cp ? hi - clo : cp;
                 r = e2s_chunk_begin(sh[size_t(g)], clo, cn);
                 const uint64_t a = clo >= 176 ? clo - 176 : 0, b = clo + cn + E2S_MAX_C_LEN + 1 < idx.n ? clo + cn + E2S_MAX_C_LEN + 1 : idx.n;
-                if (!r) r = idx.load(sh[size_t(g)], a, b - a);
+                if (!r) r = idx.load(sh[size_t(g)], a, b - a, false);
                 if (!r) r = e2s_shard_set_layout(sh[size_t(g)], idx.x, idx.y, idx.z, idx.bcr ? 1 : 0);
                 uint64_t m = 0;
                 if (!r) r = e2s_chunk_scan(sh[size_t(g)], uint32_t(k), min_len, 0, &m);

@@ -75,8 +75,9 @@ struct Index {
         return v;
     }
 
-    // Loads the global range [first, first+count) into the shard (which keeps what it needs).
-    int load(e2s_shard* sh, uint64_t first, uint64_t count) const {
+    // Loads the global range [first, first+count) into the shard (which keeps what it needs).  need_gsa = false (ebwt2clust: the
+    // cluster scan reads the LCP and the BWT only) leaves X.out.pairSA of a BCR triple on the disk.
+    int load(e2s_shard* sh, uint64_t first, uint64_t count, bool need_gsa = true) const {
         if (count == 0) return E2S_OK;
         if (egsa) {
             // straight from the file through the library's pinned ring (E2S_CLI_MMAP=1: hand the mapping over instead -- pageable copies)
@@ -85,22 +86,9 @@ struct Index {
             const size_t rs = size_t(x + y + z + 1);
             return e2s_shard_load_gesa(sh, gesa.data + first * rs, first, count, x, y, z);
         }
-        // BCR triple is already structure-of-arrays; widen to u32 on the host in bounded chunks
-        const uint64_t chunk = uint64_t(1) << 24;
-        std::vector<uint32_t> l, t, s;
-        for (uint64_t p = first; p < first + count; p += chunk) {
-            const uint64_t c = first + count - p < chunk ? first + count - p : chunk;
-            l.resize(c); t.resize(c); s.resize(c);
-            for (uint64_t i = 0; i < c; ++i) {
-                l[i] = le(lcp.data + (p + i) * x, x);
-                const uint8_t* g = gsa.data + (p + i) * (z + y);  // suff(z) then text(y): ref:include.hpp:159-175
-                s[i] = le(g, z);
-                t[i] = le(g + z, y);
-            }
-            int rc = e2s_shard_load_soa(sh, l.data(), t.data(), s.data(), bwt.data + p, p, c);
-            if (rc) return rc;
-        }
-        return E2S_OK;
+        // the BCR triple is already structure-of-arrays: the bytes go to the device as they are in the files and are widened there
+        if (!need_gsa) return e2s_shard_load_lcp_bwt(sh, lcp.data + first * uint64_t(x), x, bwt.data + first, first, count);
+        return e2s_shard_load_bcr(sh, lcp.data + first * uint64_t(x), x, bwt.data + first, gsa.data + first * uint64_t(y + z), y, z, first, count);
     }
 };
 

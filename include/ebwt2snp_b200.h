@@ -301,6 +301,11 @@ int e2s_chunked_reset(e2s_shard *sh); /* stream the range again from its first c
  * records of the clusters that survive the prefilter from the host.  pair_sa == NULL switches the mode off. */
 int e2s_shard_host_gsa(e2s_shard *sh, const void *pair_sa, int y, int z);
 int e2s_shard_load_lcp_bwt(e2s_shard *sh, const void *lcp, int x, const uint8_t *bwt, uint64_t first, uint64_t count);
+/* The BCR triple as it is in the files (egsa_stream's second input format, ref:include.hpp:157-188): lcp at x bytes, BWT bytes,
+ * pairSA = suff(z) then text(y) per position; every pointer at the element of global position `first`.  Split and widened on
+ * the device.  Any shard; ebwt2clust needs e2s_shard_load_lcp_bwt only (the cluster scan never reads text / suff). */
+int e2s_shard_load_bcr(e2s_shard *sh, const void *lcp, int x, const uint8_t *bwt, const void *pair_sa, int y, int z,
+                       uint64_t first, uint64_t count);
 /* Chunked shards on several GPUs (one process per GPU): after every rank's last chunk, e2s_chunked_finish + ONE ncclAllGather
  * of the ranks' accumulators + merge + statistics() + e2s_cluster_finalize.  Collective over the communicator. */
 int e2s_chunked_exchange(e2s_shard *sh, e2s_comm *comm, uint32_t k, int32_t min_len, int mcov_out, double pval,

@@ -185,3 +185,39 @@ def test_lean_soa_pipeline_equals_oracle(ctx, name, seed, xyz, monkeypatch):
         assert api.events_format(list(evbuf)[: res.snp.n_variants], p) == otext, chunk
         if x == 1 and chunk == n:  # lcp + bwt in full, the survivors' records only: far from the 13 B/position of EGSA records
             assert res.h2d_bytes - rs.reads.size - 8 * len(off) < 6 * n, (res.h2d_bytes, n)
+
+
+@pytest.mark.parametrize("xyz", [(4, 4, 4), (1, 4, 1), (2, 8, 2), (8, 2, 1)])
+def test_load_bcr_equals_load_soa(ctx, xyz):
+    """e2s_shard_load_bcr (the triple's bytes widened on the device) leaves the shard as e2s_shard_load_soa of the widened arrays
+    does: both tools' outputs equal the oracle's, resident and with lcp + BWT only for ebwt2clust"""
+    x, y, z = xyz
+    rs, e = H.dataset("tiny", 4)
+    n = e["n"]
+    k, m = 16, 2
+    text = e["text"] & (0xFFFF if y == 2 else 0xFFFFFFFF)  # (what a 2-byte field keeps)
+    es, el, enc, _ = O.cluster_lm(e["lcp"], e["bwt"], k, m)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    p, op = api.default_params(rs.nreads1), O.default_params(rs.nreads1)
+    ost = O.statistics(es, el, op.mcov_out, op.pval)
+    otext, ores = O.find_events(e["lcp"], text, e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+    lcp = np.ascontiguousarray(e["lcp"].astype(f"<u{x}")).view(np.uint8)
+    pair = np.empty(n, dtype=np.dtype([("suff", f"<u{z}"), ("text", f"<u{y}")]))
+    pair["suff"], pair["text"] = e["suff"], e["text"]
+    pair = pair.view(np.uint8)
+    ctx.stage_reads(rs.reads, off)
+    for with_gsa in (True, False):
+        sh = ctx.shard(n)
+        # in two pieces that do not meet at a multiple of anything
+        cut = n // 2 + 13
+        for a, b in ((cut, n), (0, cut)):
+            sh.load_bcr(lcp[a * x:b * x], e["bwt"][a:b], pair[a * (y + z):b * (y + z)] if with_gsa else None, x, y, z, first=a)
+        sh.set_layout(x, y, z, True)
+        sh.seal()
+        nw, nc = sh.cluster_lm(k, m)
+        assert nc == enc and sh.cluster_fetch_packed() == O.clusters_to_bytes(es, el)
+        if with_gsa:
+            st = sh.statistics(p.mcov_out, p.pval)
+            cnt = sh.find_events(p, st.max_clust_length)
+            assert cnt.n_candidates == ores.n_candidates and api.events_format(sh.events(), p) == otext
+        sh.close()
