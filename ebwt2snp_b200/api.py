@@ -79,7 +79,7 @@ class PipelineResult(C.Structure):
 # every symbol include/ebwt2snp_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
     "e2s_version", "e2s_ctx_create", "e2s_ctx_destroy", "e2s_last_error", "e2s_ctx_set_stream",
-    "e2s_ctx_synchronize", "e2s_ctx_launch_count", "e2s_ctx_timing", "e2s_ctx_kernel_time", "e2s_shard_create", "e2s_shard_destroy", "e2s_shard_load_gesa", "e2s_shard_load_gesa_fd",
+    "e2s_ctx_synchronize", "e2s_ctx_mem_info", "e2s_ctx_launch_count", "e2s_ctx_timing", "e2s_ctx_kernel_time", "e2s_shard_create", "e2s_shard_destroy", "e2s_shard_load_gesa", "e2s_shard_load_gesa_fd",
     "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_build_egsa_dev", "e2s_build_egsa", "e2s_shard_set_layout", "e2s_shard_seal", "e2s_shard_lcp_bytes_resident", "e2s_reads_stage", "e2s_reads_stage_dev",
     "e2s_cluster_prefilter", "e2s_cluster_run", "e2s_cluster_merge", "e2s_cluster_finalize", "e2s_cluster_lm", "e2s_cluster_count",
     "e2s_cluster_fetch", "e2s_cluster_fetch_packed", "e2s_clusters_stage_packed", "e2s_clusters_stage",
@@ -87,7 +87,7 @@ SYMBOLS = [
     "e2s_events_format", "e2s_free", "e2s_pipeline_resident", "e2s_pipeline_host",
     "e2s_comm_unique_id", "e2s_comm_create", "e2s_comm_destroy", "e2s_pipeline_sharded",
     "e2s_exchange_row_words", "e2s_exchange_rows_finish",
-    "e2s_pipeline_host_soa", "e2s_shard_host_gsa", "e2s_shard_load_lcp_bwt", "e2s_shard_load_bcr",
+    "e2s_pipeline_host_soa", "e2s_shard_host_gsa", "e2s_shard_load_lcp_bwt", "e2s_shard_load_bcr", "e2s_chunk_stage_clusters", "e2s_chunked_clusters_finish",
     "e2s_pipeline_host_sharded", "e2s_shard_create_chunked", "e2s_shard_chunk_positions", "e2s_chunk_begin", "e2s_chunk_scan", "e2s_chunked_finish", "e2s_chunked_reset", "e2s_chunked_exchange",
 ]
 
@@ -115,6 +115,7 @@ def load_library():
     lib.e2s_ctx_destroy.argtypes = [C.c_void_p]
     lib.e2s_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.e2s_ctx_synchronize.argtypes = [C.c_void_p]
+    lib.e2s_ctx_mem_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.e2s_ctx_timing.argtypes = [C.c_void_p, C.c_int]
     lib.e2s_ctx_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.e2s_shard_create.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
@@ -176,6 +177,8 @@ def load_library():
                                           C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(SnpParams), C.c_void_p,
                                           C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(PipelineResult)]
     lib.e2s_shard_host_gsa.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.e2s_chunk_stage_clusters.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    lib.e2s_chunked_clusters_finish.argtypes = [C.c_void_p]
     lib.e2s_shard_load_lcp_bwt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64]
     lib.e2s_shard_load_bcr.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
     lib.e2s_pipeline_host_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
@@ -451,6 +454,21 @@ class Shard:
         m = C.c_uint64()
         self.ctx._ck(self.lib.e2s_chunk_scan(self.h, k, min_len, int(mcov_out), C.byref(m)))
         return m.value
+
+    def chunk_stage_clusters(self, rec10, mcov_out, max_clust_length) -> int:
+        """clust2snp on a chunked shard: the .clusters records (10-byte, uint8 array) that start in the open chunk -> #survivors"""
+        rec10 = np.ascontiguousarray(rec10, dtype=np.uint8)
+        ns = C.c_uint64()
+        self.ctx._ck(self.lib.e2s_chunk_stage_clusters(self.h, _ptr(rec10) if len(rec10) else None, len(rec10) // 10, int(mcov_out),
+                                                       int(max_clust_length), C.byref(ns)))
+        return ns.value
+
+    def chunked_clusters_finish(self):
+        self.ctx._ck(self.lib.e2s_chunked_clusters_finish(self.h))
+
+    def host_gsa(self, pair_sa, y, z):
+        """lean SoA mode of a chunked shard: text / suff of the captured records come from this host buffer (kept alive by the caller)"""
+        self.ctx._ck(self.lib.e2s_shard_host_gsa(self.h, _ptr(pair_sa), y, z))
 
     def chunked_finish(self, k=16, min_len=2) -> ClusterSummary:
         s = ClusterSummary()

@@ -123,6 +123,7 @@ struct e2s_shard {
     const uint8_t* host_gsa = nullptr;
     int gsa_y = 4, gsa_z = 4;
     uint64_t lean_h2d = 0, lean_d2h = 0;                    // bytes of the survivor fetches (for the callers' accounting)
+    SnpDev* d_stage_dev = nullptr;                           // e2s_chunk_stage_clusters: K3a's counters
     SurvEntry* h_surv = nullptr; size_t h_surv_cap = 0;     // pinned
     uint32_t* h_gather = nullptr; size_t h_gather_cap = 0;  // pinned: text values then suff values of one capture
     uint64_t range_lo = 0, range_n = 0;   // the shard's own range of the eBWT
@@ -412,6 +413,16 @@ int e2s_shard_create_chunked(e2s_ctx* c, uint64_t n_local, uint64_t global_off, 
     return E2S_OK;
 }
 
+int e2s_ctx_mem_info(e2s_ctx* c, uint64_t* free_bytes, uint64_t* total_bytes) {
+    if (!c) return fail(nullptr, E2S_ERR_ARG, "ctx == NULL");
+    CU(c, cudaSetDevice(c->device));
+    size_t f = 0, t = 0;
+    CU(c, cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return E2S_OK;
+}
+
 uint64_t e2s_shard_chunk_positions(const e2s_shard* s) { return s && s->chunked ? s->chunk_cap : 0; }
 
 // The next chunk [chunk_lo, chunk_lo + chunk_n) of the shard's range: chunks follow each other without gaps, every chunk but
@@ -453,6 +464,7 @@ void e2s_shard_destroy(e2s_shard* s) {
     cudaFree(s->suff_a);
     cudaFree(s->bwt_a);
     cudaFree(s->lcpt);
+    cudaFree(s->d_stage_dev);
     if (s->h_surv) cudaFreeHost(s->h_surv);
     if (s->h_gather) cudaFreeHost(s->h_gather);
     cudaFree(s->d_start);
@@ -1330,7 +1342,7 @@ extern "C" {
 
 // copies the records of the survivors listed in d_pf_list[0, n) (base relative to the resident chunk) to the payload
 
-static int capture_survivors(e2s_shard* s, uint64_t n) {
+static int capture_survivors(e2s_shard* s, uint64_t n, const unsigned long long* d_count = nullptr) {
     e2s_ctx* c = s->ctx;
     if (!n) return E2S_OK;
     const uint64_t need_pay = s->pay_used + n * uint64_t(MAX_C_LEN);
@@ -1343,7 +1355,7 @@ static int capture_survivors(e2s_shard* s, uint64_t n) {
     CU(c, grow_keep(s->d_surv, s->surv_cap, s->surv_count, s->surv_count + n, c->stream));
     CaptureParams cp;
     cp.in = s->d_pf_list;
-    cp.n_in = &s->d_res->n_pf;
+    cp.n_in = d_count ? d_count : &s->d_res->n_pf;
     cp.n_in_cap = n;
     cp.lcp = s->lcp;
     cp.text = s->text;
@@ -1505,6 +1517,90 @@ int e2s_chunk_scan(e2s_shard* s, uint32_t k, int32_t min_len, int mcov_out, uint
     s->have_scan_stats = true;
     memset(&s->merged, 0, sizeof s->merged);
     if (n_records) *n_records = h.n_written;
+    return E2S_OK;
+}
+
+// clust2snp on a chunked shard (an index larger than device memory): instead of scanning the chunk for clusters, take them from
+// the .clusters file -- the m records whose START lies in the open chunk, 10 bytes each, in file order -- run the BWT prefilter of
+// find_variants on them (K3a, ref:clust2snp.cpp:402-429) and keep the EGSA records of the survivors for phase 2.
+// max_clust_length comes from statistics() over the whole file (ref:clust2snp.cpp:877-966), which needs no index.
+int e2s_chunk_stage_clusters(e2s_shard* s, const void* rec10, uint64_t m, int mcov_out, int max_clust_length, uint64_t* n_survivors) {
+    if (!s || !s->chunked || !s->chunk_open) return fail(s ? s->ctx : nullptr, E2S_ERR_STATE, "e2s_chunk_stage_clusters: begin a chunk first");
+    e2s_ctx* c = s->ctx;
+    if (m && !rec10) return fail(c, E2S_ERR_ARG, "e2s_chunk_stage_clusters: NULL records");
+    if (mcov_out < 1 || 2 * mcov_out > E2S_MAX_C_LEN || max_clust_length > E2S_MAX_C_LEN)
+        return fail(c, E2S_ERR_UNSUPPORTED, "e2s_chunk_stage_clusters: need 2 <= 2 * mcov_out <= 150 and max_clust_length <= 150");
+    if (s->acc.ticket && s->pf_mcov != uint32_t(mcov_out)) return fail(c, E2S_ERR_ARG, "e2s_chunk_stage_clusters: one -m for all the chunks of a range");
+    int rc = e2s_shard_seal(s);
+    if (rc) return rc;
+    if (n_survivors) *n_survivors = 0;
+    if (m) {
+        if ((rc = ensure_records(s, m + 8))) return rc;
+        std::vector<uint64_t> st(m);
+        std::vector<uint16_t> ln(m);
+        const uint8_t* r = static_cast<const uint8_t*>(rec10);
+        for (uint64_t i = 0; i < m; ++i) {
+            memcpy(&st[i], r + i * 10, 8);
+            memcpy(&ln[i], r + i * 10 + 8, 2);
+            if (st[i] - s->global_off >= s->n_local) return fail(c, E2S_ERR_ARG, "e2s_chunk_stage_clusters: a record does not start in the open chunk");
+            if (ln[i] <= E2S_MAX_C_LEN) s->acc.hist[ln[i]]++;
+        }
+        if (m + 8 > s->pf_cap) {  // every record may survive
+            cudaFree(s->d_pf_list);
+            s->d_pf_list = nullptr;
+            s->pf_cap = 0;
+            const uint64_t want = m + m / 4 + 4096;
+            if (cudaMalloc(reinterpret_cast<void**>(&s->d_pf_list), (want + 8) * sizeof(SurvEntry)) != cudaSuccess)
+                return fail(c, E2S_ERR_NOMEM, "survivor list");
+            s->pf_cap = want;
+        }
+        if (!s->d_stage_dev) CU(c, cudaMalloc(reinterpret_cast<void**>(&s->d_stage_dev), sizeof(SnpDev)));
+        CU(c, cudaMemsetAsync(s->d_stage_dev, 0, sizeof(SnpDev), c->stream));
+        CU(c, cudaMemcpyAsync(s->d_start, st.data(), m * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(s->d_len, ln.data(), m * 2, cudaMemcpyHostToDevice, c->stream));
+        SnpArrays a;
+        a.lcp = s->lcp;
+        a.text = s->text;
+        a.suff = s->suff;
+        a.bwt = s->bwt;
+        a.planes = s->d_planes;
+        a.n_local = s->n_local;
+        a.global_off = s->global_off;
+        a.cl_start = s->d_start;
+        a.cl_len = s->d_len;
+        a.m = m;
+        CU(c, launch_code_scan(a, uint32_t(mcov_out), uint32_t(max_clust_length), s->d_pf_list, s->pf_cap, s->d_stage_dev, c->stream, c->sm_count));
+        ++c->launches;
+        SnpDev h;
+        CU(c, cudaMemcpyAsync(&h, s->d_stage_dev, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));  // (also: st / ln leave this frame)
+        if (h.n_survivors && (rc = capture_survivors(s, h.n_survivors, &s->d_stage_dev->n_survivors))) return rc;
+        if (n_survivors) *n_survivors = h.n_survivors;
+    }
+    s->acc.ticket++;  // chunks done
+    s->acc.n_written += m;
+    s->chunk_open = false;
+    s->pf_mcov = uint32_t(mcov_out);
+    return E2S_OK;
+}
+
+// After the last chunk of the range went through e2s_chunk_stage_clusters: e2s_find_events runs on the captured records.
+int e2s_chunked_clusters_finish(e2s_shard* s) {
+    if (!s || !s->chunked) return fail(s ? s->ctx : nullptr, E2S_ERR_ARG, "e2s_chunked_clusters_finish: not a chunked shard");
+    e2s_ctx* c = s->ctx;
+    if (s->chunk_open || s->global_off + s->n_local != s->range_lo + s->range_n || !s->acc.ticket)
+        return fail(c, E2S_ERR_STATE, "e2s_chunked_clusters_finish: the last chunk of the range has not been staged");
+    s->h_res = s->acc;  // (the length histogram of the staged records: n_analysed of e2s_find_events)
+    s->m_own = s->m_list = s->acc.n_written;
+    s->records_flushed = true;
+    s->have_clusters = true;
+    s->staged = false;
+    s->finalized = true;
+    s->have_events = false;
+    s->have_scan_stats = false;
+    s->pf_ok = true;
+    s->pf_has_adopted = true;
+    memset(&s->merged, 0, sizeof s->merged);
     return E2S_OK;
 }
 

@@ -284,6 +284,8 @@ struct CaptureParams {
     unsigned long long* counters;      // [0] payload cursor, [1] entries in `out`, [2] error bits: 1 = cluster not resident, 2 = payload full, 4 = list full
 };
 cudaError_t launch_capture(const CaptureParams& p, cudaStream_t stream, int sm_count);
+cudaError_t launch_code_scan(const SnpArrays& a, uint32_t mcov, uint32_t max_len, SurvEntry* out, uint64_t cap, SnpDev* dev,
+                             cudaStream_t stream, int sm_count);
 
 // *flag |= 1 when one of the n bytes is not in ACGTacgt (K4 then keeps base_to_int's "anything else counts as A" path)
 // flag[1] |= 1 unless all n_reads reads (offsets d_off[0 .. n_reads]) have the same length

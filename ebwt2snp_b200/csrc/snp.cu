@@ -143,6 +143,25 @@ __global__ void __launch_bounds__(PS_THREADS) k_code_scan(ScanParams p) {
     if ((threadIdx.x & 31) == 0 && n_analysed) atomicAdd(&p.dev->n_analysed, n_analysed);
 }
 
+// K3a alone (streaming clust2snp: the staged records of one chunk -> the list k_capture reads); dev->n_survivors / n_analysed count
+cudaError_t launch_code_scan(const SnpArrays& a, uint32_t mcov, uint32_t max_len, SurvEntry* out, uint64_t cap, SnpDev* dev,
+                             cudaStream_t stream, int sm_count) {
+    if (!a.m) return cudaSuccess;
+    ScanParams sp;
+    sp.a = a;
+    sp.limit = (a.n_local + PS_T - 1) / PS_T * PS_T;
+    sp.min_len = 2 * mcov;
+    sp.max_len = max_len;
+    sp.mcov = mcov;
+    sp.survivors = out;
+    sp.cap_surv = cap;
+    sp.dev = dev;
+    uint64_t grid = (a.m + PS_THREADS * PS_U - 1) / (PS_THREADS * PS_U);
+    if (grid > uint64_t(sm_count) * 16) grid = uint64_t(sm_count) * 16;
+    k_code_scan<<<unsigned(grid), PS_THREADS, 0, stream>>>(sp);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // streaming: the surviving clusters' records -> compact payload (one warp per cluster)
 // ---------------------------------------------------------------------------------------------

@@ -146,11 +146,39 @@ int main(int argc, char** argv) {
         const char* e = ctx[size_t(g)] ? e2s_last_error(ctx[size_t(g)]) : "";
         errs[size_t(g)] = e[0] ? e : e2s_last_error(nullptr);
     };
+    // A shard that does not fit the device (or E2S_CLI_STREAM=1) is STREAMED through a chunked shard of E2S_CHUNK_POSITIONS
+    // positions (default 2^28), as the reference streams the index past the records (ref:clust2snp.cpp:806-857): statistics()
+    // needs the .clusters file only, each chunk's records are staged with it, the prefilter runs per chunk and phase 2 on the
+    // records of its survivors.  A BCR triple then sends X.out.lcp + X.out only; X.out.pairSA is read for the survivors.
+    std::vector<char> streamed(size_t(G), 0);
+    uint64_t chunk = uint64_t(1) << 28;
+    if (const char* e = getenv("E2S_CHUNK_POSITIONS"))
+        if (strtoull(e, nullptr, 10)) chunk = strtoull(e, nullptr, 10);
     auto stage = [&](int g) {
         int r = e2s_ctx_create(g, &ctx[size_t(g)]);
         if (r) return fail_of(g, r);
         if (g == 0) host::stamp("context created");
         const uint64_t lo = cuts[size_t(g)], hi = cuts[size_t(g) + 1];
+        {
+            uint64_t free_b = 0, total_b = 0;
+            e2s_ctx_mem_info(ctx[size_t(g)], &free_b, &total_b);
+            const uint64_t need = (hi - lo) * 15 + (rcut[size_t(g) + 1] - rcut[size_t(g)]) * 12 + reads.bases.size() + (uint64_t(1) << 30);
+            const char* fs = getenv("E2S_CLI_STREAM");
+            streamed[size_t(g)] = (fs && atoi(fs) != 0) || need > free_b / 10 * 9;
+        }
+        if (streamed[size_t(g)]) {  // statistics() of this shard's records on the host; the index is streamed in analyse()
+            e2s_stats& s_g = stats[size_t(g)];
+            memset(&s_g, 0, sizeof s_g);
+            for (uint64_t i = rcut[size_t(g)]; i < rcut[size_t(g) + 1]; ++i) {
+                const uint16_t l = rec_len(i);
+                if (l <= E2S_MAX_C_LEN) s_g.hist[l]++;
+                s_g.n_bases += l;
+                s_g.n_clust++;
+            }
+            r = e2s_reads_stage(ctx[size_t(g)], reads.bases.data(), reads.off.data(), reads.n_reads());
+            if (r) fail_of(g, r);
+            return;
+        }
         r = e2s_shard_create(ctx[size_t(g)], hi - lo, lo, idx.n, &sh[size_t(g)]);
         const uint64_t a = lo >= 2 ? lo - 2 : 0, b = hi + E2S_MAX_C_LEN + 1 < idx.n ? hi + E2S_MAX_C_LEN + 1 : idx.n;
         if (!r) r = idx.load(sh[size_t(g)], a, b - a);
@@ -209,7 +237,34 @@ int main(int argc, char** argv) {
     std::cout << "(1/4) Filtering relevant clusters ... " << std::endl;
     std::vector<e2s_snp_counts> counts(static_cast<size_t>(G));
     auto analyse = [&](int g) {
-        int r = e2s_find_events(sh[size_t(g)], &p, st.max_clust_length, &counts[size_t(g)]);
+        int r = 0;
+        if (streamed[size_t(g)]) {
+            const uint64_t lo = cuts[size_t(g)], hi = cuts[size_t(g) + 1];
+            e2s_shard*& s_g = sh[size_t(g)];
+            r = e2s_shard_create_chunked(ctx[size_t(g)], hi - lo, lo, idx.n, chunk, &s_g);
+            if (!r) r = e2s_shard_set_layout(s_g, idx.x, idx.y, idx.z, idx.bcr ? 1 : 0);
+            if (!r && idx.bcr) r = e2s_shard_host_gsa(s_g, idx.gsa.data, idx.y, idx.z);
+            const uint64_t cp = r ? 0 : e2s_shard_chunk_positions(s_g);
+            uint64_t r0 = rcut[size_t(g)];
+            for (uint64_t clo = lo; !r && clo < hi; clo += cp) {
+                const uint64_t cn = hi - clo < cp ? hi - clo : cp;
+                r = e2s_chunk_begin(s_g, clo, cn);
+                const uint64_t a = clo >= 176 ? clo - 176 : 0, b = clo + cn + E2S_MAX_C_LEN + 1 < idx.n ? clo + cn + E2S_MAX_C_LEN + 1 : idx.n;
+                if (!r) r = idx.load(s_g, a, b - a, !idx.bcr);
+                if (!r) r = e2s_shard_set_layout(s_g, idx.x, idx.y, idx.z, idx.bcr ? 1 : 0);
+                uint64_t r1 = r0, top = rcut[size_t(g) + 1];  // first record of the shard that starts at or after the chunk's end
+                while (r1 < top) {
+                    const uint64_t mid = (r1 + top) / 2;
+                    if (rec_start(mid) < clo + cn) r1 = mid + 1;
+                    else top = mid;
+                }
+                if (!r) r = e2s_chunk_stage_clusters(s_g, cl.data + r0 * 10, r1 - r0, p.mcov_out, st.max_clust_length, nullptr);
+                r0 = r1;
+            }
+            if (!r) r = e2s_chunked_clusters_finish(s_g);
+            if (g == 0) host::stamp("index streamed, survivors captured");
+        }
+        if (!r) r = e2s_find_events(sh[size_t(g)], &p, st.max_clust_length, &counts[size_t(g)]);
         if (r) fail_of(g, r);
     };
     {

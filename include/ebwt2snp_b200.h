@@ -60,6 +60,8 @@ const char *e2s_last_error(const e2s_ctx *ctx);
 /* use an existing CUDA stream (cudaStream_t passed as void*) instead of the context's own */
 int e2s_ctx_set_stream(e2s_ctx *ctx, void *cuda_stream);
 int e2s_ctx_synchronize(e2s_ctx *ctx);
+/* free / total device memory of the context's GPU right now (the CLIs choose between a resident and a chunked shard with it) */
+int e2s_ctx_mem_info(e2s_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 uint64_t e2s_ctx_launch_count(const e2s_ctx *ctx);
 /* Per-kernel device time, measured with CUDA events recorded on the context's stream around the
@@ -295,6 +297,14 @@ int e2s_chunk_begin(e2s_shard *sh, uint64_t chunk_lo, uint64_t chunk_n);
 int e2s_chunk_scan(e2s_shard *sh, uint32_t k, int32_t min_len, int mcov_out, uint64_t *n_records);
 int e2s_chunked_finish(e2s_shard *sh, uint32_t k, int32_t min_len, e2s_cluster_summary *summary);
 int e2s_chunked_reset(e2s_shard *sh); /* stream the range again from its first chunk */
+/* clust2snp on a chunked shard (ref:clust2snp.cpp:788-872 streams the index past the .clusters records in the same way): after
+ * the loads of a chunk, hand over the `m` records of the .clusters file whose START lies in the chunk (10 bytes each, file
+ * order) instead of scanning for clusters; the BWT prefilter runs on them and the EGSA records of its survivors are kept.
+ * max_clust_length = the result of statistics() over the whole file (e2s_statistics_finish).  After the last chunk
+ * e2s_chunked_clusters_finish, then e2s_find_events / e2s_events_fetch as for any shard. */
+int e2s_chunk_stage_clusters(e2s_shard *sh, const void *rec10, uint64_t m, int mcov_out, int max_clust_length,
+                             uint64_t *n_survivors);
+int e2s_chunked_clusters_finish(e2s_shard *sh);
 /* Lean SoA inputs for a chunked shard: text / suff stay in the caller's pairSA buffer (suff(z) then text(y) per position, index =
  * global position; it must stay valid until the last e2s_chunk_scan), chunks are loaded with e2s_shard_load_lcp_bwt (lcp at x
  * bytes per position + BWT bytes: `lcp` / `bwt` point at the element of global position `first`), and e2s_chunk_scan fetches the

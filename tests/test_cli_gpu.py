@@ -77,6 +77,39 @@ def test_cli_other_layouts(built, tmp_path, name):
         assert open(os.path.join(str(d), name + ".snp"), "rb").read() == lay["snp"], lay
 
 
+@pytest.mark.parametrize("name", ["micro_a", "micro_b"])
+def test_cli_clust2snp_streamed(built, tmp_path, name):
+    """clust2snp with the index STREAMED through a chunked shard (what it does for an index larger than device memory;
+    E2S_CLI_STREAM=1 forces it): every option set and layout -- EGSA and the BCR triple, whose pairSA is then only read for the
+    prefilter's survivors -- gives the reference's .snp"""
+    g = GU.micro(name)
+    env = {"E2S_CLI_STREAM": "1", "E2S_CHUNK_POSITIONS": "20000"}
+    fa = write_index(tmp_path / "d", g, dict(x=4, y=4, z=4, bcr=False))
+    assert run("ebwt2clust", "-i", fa, "-k", g["k"], "-m", g["m"], "-x", 4, "-y", 4, "-z", 4).returncode == 0
+    snp = os.path.join(str(tmp_path / "d"), name + ".snp")
+    for v in g["variants"]:
+        if os.path.exists(snp):
+            os.remove(snp)
+        r = run("clust2snp", "-i", fa, "-n", g["nreads1"], "-x", 4, "-y", 4, "-z", 4, *v["args"], env=env)
+        assert f"Cluster sizes allowed: [{v['allowed'][0]},{v['allowed'][1]}]" in r.stdout, v["args"]
+        if v["rc"] == 0:
+            assert r.returncode == 0, r.stderr
+            assert stdout_value(r.stdout, "Done. ") == v["ncand"]
+            assert open(snp, "rb").read() == v["snp"], v["args"]
+        else:
+            assert r.returncode == 3 and not os.path.exists(snp)
+    for j, lay in enumerate(g["layouts"]):
+        d = tmp_path / f"lay{j}"
+        fa = write_index(d, g, lay)
+        w = ["-x", lay["x"], "-y", lay["y"], "-z", lay["z"]]
+        assert run("ebwt2clust", "-i", fa, "-k", g["k"], "-m", g["m"], *w, env=env).returncode == 0
+        assert open(fa + ".clusters", "rb").read() == lay["clusters"], lay
+        r = run("clust2snp", "-i", fa, "-n", g["nreads1"], *w, env=env)
+        assert r.returncode == 0, (lay, r.stderr)
+        assert stdout_value(r.stdout, "Done. ") == lay["ncand"]
+        assert open(os.path.join(str(d), name + ".snp"), "rb").read() == lay["snp"], lay
+
+
 def test_cli_sharded_on_one_box(built, tmp_path):
     """E2S_GPUS=N shards the eBWT over N devices; outputs must not depend on N (runs with every N the box offers)"""
     import torch

@@ -221,3 +221,43 @@ def test_load_bcr_equals_load_soa(ctx, xyz):
             cnt = sh.find_events(p, st.max_clust_length)
             assert cnt.n_candidates == ores.n_candidates and api.events_format(sh.events(), p) == otext
         sh.close()
+
+
+@pytest.mark.parametrize("name,seed", [("tiny", 4), ("small", 2)])
+@pytest.mark.parametrize("lean", [False, True])
+def test_chunked_clust2snp_equals_oracle(ctx, name, seed, lean):
+    """clust2snp alone on a chunked shard (an index larger than device memory): the .clusters records of each chunk are staged,
+    the prefilter runs per chunk, phase 2 on the captured records -- same .snp as the oracle; lean = text / suff from the host"""
+    rs, e = H.dataset(name, seed)
+    n = e["n"]
+    k, m = 16, 2
+    es, el, enc, _ = O.cluster_lm(e["lcp"], e["bwt"], k, m)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    p, op = api.default_params(rs.nreads1), O.default_params(rs.nreads1)
+    ost = O.statistics(es, el, op.mcov_out, op.pval)
+    otext, ores = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+    rec10 = np.frombuffer(O.clusters_to_bytes(es, el), dtype=np.uint8)
+    ctx.stage_reads(rs.reads, off)
+    pair = np.empty(n, dtype=np.dtype([("suff", "<u1"), ("text", "<u4")]))
+    pair["suff"], pair["text"] = e["suff"], e["text"]
+    pair = pair.view(np.uint8)
+    lcp1 = e["lcp"].astype(np.uint8)
+    for chunk in (n, n // 3, 100_003, 16384):
+        sh = ctx.shard(n, 0, n, chunk_positions=chunk)
+        if lean:
+            sh.host_gsa(pair, 4, 1)
+        for clo, cn in sh.chunks():
+            sh.chunk_begin(clo, cn)
+            a, b = max(0, clo - 176), min(n, clo + cn + 152)
+            if lean:
+                sh.load_bcr(lcp1[a:b], e["bwt"][a:b], None, 1, 4, 1, first=a)
+                sh.set_layout(1, 4, 1, True)
+            else:
+                sh.load_soa(e["lcp"][a:b], e["text"][a:b], e["suff"][a:b], e["bwt"][a:b], first=a)
+            r0, r1 = np.searchsorted(es, clo), np.searchsorted(es, clo + cn)
+            sh.chunk_stage_clusters(rec10[r0 * 10:r1 * 10], p.mcov_out, ost.max_clust_length)
+        sh.chunked_clusters_finish()
+        cnt = sh.find_events(p, ost.max_clust_length)
+        assert (cnt.n_analysed, cnt.n_candidates, cnt.n_events) == (ores.n_analysed, ores.n_candidates, ores.n_events), chunk
+        assert api.events_format(sh.events(), p) == otext, chunk
+        sh.close()
