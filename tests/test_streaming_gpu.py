@@ -261,3 +261,44 @@ def test_chunked_clust2snp_equals_oracle(ctx, name, seed, lean):
         assert (cnt.n_analysed, cnt.n_candidates, cnt.n_events) == (ores.n_analysed, ores.n_candidates, ores.n_events), chunk
         assert api.events_format(sh.events(), p) == otext, chunk
         sh.close()
+
+
+def test_reads_150bp_stream_like_any_other(ctx, monkeypatch):
+    """150-base reads (LCP values up to 150: saturated in the bit-sliced copy) through the streaming pipelines and the lean
+    SoA pipeline: .clusters / .snp equal the oracle's, and the index is the library builder's"""
+    rs = synth.make_read_set(G=40_000, reads_per_sample=5_000, L=150, n_snps=80, n_indels=8, rc=True, seed=150)
+    e = synth.build_egsa(rs.reads)
+    eg = {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in e.items()}
+    for f in ("lcp", "text", "suff"):
+        eg[f] = eg[f].view(np.uint32)
+    n = int(eg["n"])
+    assert int(eg["lcp"].max()) > 127
+    mine = ctx.build_egsa(rs.reads)
+    for key in ("lcp", "text", "suff", "bwt"):
+        got = mine[key].cpu().numpy()
+        assert np.array_equal(got.view(np.uint32) if key != "bwt" else got, eg[key]), key
+    k, m = 16, 2
+    es, el, enc, _ = O.cluster_lm(eg["lcp"], eg["bwt"], k, m)
+    off = O.uniform_read_offsets(*rs.reads.shape)
+    p, op = api.default_params(rs.nreads1), O.default_params(rs.nreads1)
+    ost = O.statistics(es, el, op.mcov_out, op.pval)
+    otext, ores = O.find_events(eg["lcp"], eg["text"], eg["suff"], eg["bwt"], es, el, op, ost.max_clust_length, rs.reads, off)
+    assert ores.n_events > 0
+    want = O.clusters_to_bytes(es, el)
+    rec = synth.gesa_records(eg).view(np.uint8).reshape(-1)
+    lcp1 = eg["lcp"].astype(np.uint8)
+    pair = np.empty(n, dtype=np.dtype([("suff", "<u1"), ("text", "<u4")]))
+    pair["suff"], pair["text"] = eg["suff"], eg["text"]
+    pair = pair.view(np.uint8)
+    for chunk in (n, 100_003):
+        monkeypatch.setenv("E2S_CHUNK_POSITIONS", str(chunk))
+        for lean in (False, True):
+            rec10 = np.empty((len(es) + 16) * 10, dtype=np.uint8)
+            evbuf = (api.Event * (ores.n_candidates + 16))()
+            if lean:
+                res = ctx.pipeline_host_soa(lcp1, eg["bwt"], pair, n, rs.reads.reshape(-1), off, p, k, m, 1, 4, 1, rec10=rec10, events=evbuf)
+            else:
+                res = ctx.pipeline_host(rec, n, rs.reads.reshape(-1), off, p, k, m, rec10=rec10, events=evbuf)
+            assert res.n_written == len(es) and rec10[: len(es) * 10].tobytes() == want, (chunk, lean)
+            assert (res.n_clust_out, res.max_clust_length, res.snp.n_candidates) == (enc, ost.max_clust_length, ores.n_candidates)
+            assert api.events_format(list(evbuf)[: res.snp.n_variants], p) == otext, (chunk, lean)
