@@ -22,9 +22,8 @@
 //             START at most min_len - 2 positions before, min_len <= 33) are ranked by ONE block scan; each thread
 //             scatters the tile-local positions of its kept ENDs to a shared list -- nothing else happens at lane
 //             efficiency popcount / max popcount.
-//   records   one lane per list entry (dense): nearest START at or before the END = the last START in the word of the END's
-//             owner, else the owner's carry c_prev (the tile's last START before its word: nearest earlier lane of the warp
-//             by ballot + one shuffle, else the last START of the earlier warps -- no search), length mod 2^16, stores
+//   records   one lane per list entry (dense): nearest START at or before the END from the tile's START words in shared
+//             memory (own word, else the per-warp ballots of non-empty words point at the word), length mod 2^16, stores
 //             (start u64, len u16) in position order into the chunk's segment, length histogram + n_bases of
 //             statistics() (ref:clust2snp.cpp:899-907), and -- fused mode -- the BWT prefilter of find_variants
 //             (ref:clust2snp.cpp:402-429) as the one-popcount bound of planes.cuh on the plane window; the survivors are
@@ -88,8 +87,6 @@ struct ScanShared {
     unsigned int hist[E2S_HIST_BINS];
     uint64_t sS[2][SC_THREADS];   // START words of the tile, by tile parity: read until the tile's records are out
     uint16_t e_ent[SC_CAP];       // tile-local positions of the kept ENDs, by rank
-    int wls[2][SC_WARPS];         // per warp: tile-local position of its last START, -1 = none; by tile parity
-    int c_prev[SC_THREADS];       // per thread: the tile's last START before the thread's word, -1 = none (written after (A), read after (B))
 };
 
 __device__ __forceinline__ void tma_load_2d_u8(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -336,12 +333,10 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 const uint32_t e_lo = __shfl_sync(FULL, uint32_t(E), src), e_hi = __shfl_sync(FULL, uint32_t(E >> 32), src);
                 fe = (warp * 32 + src) * SC_V + (e_lo ? __ffs(e_lo) - 1 : 31 + __ffs(e_hi));
             }
-            const uint64_t shfl_last_S = shfl64(S, bS ? 31 - __clz(bS) : 0);  // the START word of the warp's last lane that has one
             if (lane == 31) sh.wsum[warp] = inc;
             if (lane == 0) {
                 sts_u32(bS_a + uint32_t(warp) * 4u, bS);
                 sh.wfe[warp] = fe;
-                sh.wls[pb][warp] = bS ? (warp * 32 + (31 - __clz(bS))) * SC_V + 63 - __clzll(shfl_last_S) : -1;
             }
             if (interior) {  // a cluster is open after the tile iff its last position is inside one and not its END
                 if (tid == SC_THREADS - 1) sh.open_after[pb] = uint32_t((G & ~E) >> 63);
@@ -368,18 +363,6 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             nK = tot & 0xffffu;
             nE = tot >> 16;
             baseK = base & 0xffffu;
-        }
-
-        // ---- the tile's last START before my word: in my warp (the nearest earlier lane with a START: from the ballot) or in
-        // an earlier warp.  The record loop then finds the START of an END with its owner's word and this value: no search.
-        {
-            const uint32_t bS_mine = __ballot_sync(FULL, S != 0);
-            const uint32_t before = bS_mine & ((1u << lane) - 1u);
-            const int src = before ? 31 - __clz(before) : 0;
-            const uint64_t Sp = shfl64(S, src);
-            const int wl = sh.wls[pb][lane & (SC_WARPS - 1)];
-            const int prev_warps = __reduce_max_sync(FULL, lane < warp ? wl : -1);
-            sh.c_prev[tid] = before ? (warp * 32 + src) * SC_V + 63 - __clzll(Sp) : prev_warps;
         }
 
         // ---- warp 0, before the barrier (B): the carried END and where the tile's records go
@@ -465,7 +448,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 }
             }
             if (warp == 0 && win == 0) {  // the chunk state after this tile (off the other warps' path to the records)
-                const int t_ls = __reduce_max_sync(FULL, sh.wls[pb][lane & (SC_WARPS - 1)]);  // the tile's last START
+                const int t_ls = find_prev(sS_a, bS_a, any8, SC_T - 1);
                 bool open_after;
                 if (interior) {
                     open_after = sh.open_after[pb] != 0;
@@ -491,18 +474,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             // state: the extra rounds land on the warps that are ahead)
             for (uint32_t i = uint32_t(tid), nxt = 2u * SC_THREADS - 1u - uint32_t(tid); i < n_win; i = nxt, nxt += SC_THREADS) {
                 const uint32_t e = sh.e_ent[i];
-                int s_loc;
-                {   // nearest START at or before e: in the word of e's owner, else the owner's carry
-                    const uint32_t t_own = e >> 6;
-                    uint2 v = lds_u64(sS_a + t_own * 8u);
-                    const uint32_t keep = FULL >> (31u - (e & 31u));
-                    if (e & 32u) v.y &= keep;
-                    else {
-                        v.x &= keep;
-                        v.y = 0;
-                    }
-                    s_loc = (v.x | v.y) ? int(t_own * 64u) + (v.y ? 63 - __clz(v.y) : 31 - __clz(v.x)) : sh.c_prev[t_own];
-                }
+                const int s_loc = find_prev(sS_a, bS_a, any8, e);
                 uint32_t len, o = prefix + i;
                 uint32_t b_lo;          // first position of the analysed range, from the plane window's first position (tile start - PL_PAD)
                 bool in_window = true;  // ... unless the range starts before it (a wrapped length)
