@@ -42,6 +42,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -87,6 +88,12 @@ struct ScanShared {
     unsigned int hist[E2S_HIST_BINS];
     uint64_t sS[2][SC_THREADS];   // START words of the tile, by tile parity: read until the tile's records are out
     uint16_t e_ent[SC_CAP];       // tile-local positions of the kept ENDs, by rank
+    // chunk state that lives here instead of in (every thread's) registers: the kernel runs at its 64-register cap
+    uint64_t x_state;             // warp 0: open-cluster state after the last tile; unknown until the chunk's first event
+    uint64_t n_end_acc;           // warp 0: ENDs seen (head included)
+    uint64_t head_end;            // warp 0: 1 + global position of the chunk's head END, 0 = none
+    unsigned long long big_bases; // sum of the written lengths above MAX_C_LEN (the others are in hist)
+    uint32_t seen;                // warp 0: the chunk has had an event
 };
 
 __device__ __forceinline__ void tma_load_2d_u8(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -161,7 +168,12 @@ __device__ __forceinline__ int find_prev(uint32_t words, uint32_t bal, uint32_t 
 
 }  // namespace
 
-__global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Scan8Params p) {
+// OCC = the resident CTAs per SM ptxas is asked to make room for.  Its register allocation is erratic around the 64-register
+// line (the same source has come out at 56 / 62 registers for OCC = 4 and 62 / 72 / 80 for OCC = 3, and the 56-register
+// build re-materialises per-thread constants every tile: C2 253.5 vs 247.7 us), so both builds are compiled and
+// scan_kernel() picks at run time: most resident CTAs first, then most registers.
+template <int OCC>
+__global__ void __launch_bounds__(SC_THREADS, OCC) k_cluster_scan(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Scan8Params p) {
     extern __shared__ __align__(128) uint8_t smem_dyn[];  // SC_STAGES stages, then SC_PSLOTS plane windows
     __shared__ ScanShared sh;
     const uint32_t stage0 = smem_u32(smem_dyn);
@@ -201,21 +213,19 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
         if (pf) bulk_g2s_a(planes0 + (it % SC_PSLOTS) * SC_PF_STRIDE, p.planes + uint64_t(t) * (SC_T / 64), SC_PF_BYTES, &sh.full_bar[stage]);
     };
     if (tid == 0) {
+        sh.x_state = OPEN_UNKNOWN;
+        sh.n_end_acc = 0;
+        sh.head_end = 0;
+        sh.big_bases = 0;
+        sh.seen = 0;
         for (int s = 0; s < SC_STAGES; ++s) mbar_init(&sh.full_bar[s], 1);
         fence_mbar_init();
         for (uint32_t s = 0; s < uint32_t(SC_STAGES); ++s) issue(s);
     }
     __syncthreads();
 
-    // chunk state (warp 0; identical in its lanes)
-    uint64_t X = OPEN_UNKNOWN;   // open-cluster state; unknown until the chunk's first event
+    // chunk state (warp 0; identical in its lanes); the rest of it is in shared memory (ScanShared)
     uint32_t cnt = 0;            // records written to the segment so far (a segment holds fewer than 2^32)
-    uint64_t n_end = 0;          // ENDs seen (head included)
-    uint64_t head_end = 0;       // 1 + global position of the chunk's head END, 0 = none
-    bool seen = false;           // the chunk has had an event
-    unsigned long long acc_bases = 0;  // (per thread) sum of the lengths I wrote
-    uint32_t my_last_o = 0xffffffffu;  // (per thread) segment-relative index and length of the last record I wrote
-    uint32_t my_last_len = 0;
 
     uint32_t pf_win = planes0;  // the tile's plane window: slot it % SC_PSLOTS
     for (uint32_t it = 0; it < n_my; ++it, pf_win = pf_win == planes0 + (SC_PSLOTS - 1) * SC_PF_STRIDE ? planes0 : pf_win + SC_PF_STRIDE) {
@@ -386,6 +396,8 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
             // the only END of the tile that can be 65 536 or more positions from its START.  Before the chunk's first event that
             // START is not known here: the END is the chunk's head, left to k_chunk_resolve.
             uint32_t adj = 0;  // 1: the carried END is not written by this tile
+            const uint64_t X = sh.x_state;
+            const bool seen = sh.seen != 0;
             const bool is_head = carried && !seen;
             if (carried) {
                 adj = 1;
@@ -393,15 +405,15 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                     const uint32_t len = uint32_t(tile_gbase + uint64_t(t_fe) - (X - OPEN_BIAS) + 1) & 0xffffu;
                     adj = int(len) >= p.min_len ? 0u : 1u;
                 }
-                if (is_head) head_end = tile_gbase + uint64_t(t_fe) + 1;
+                if (is_head && lane == 0) sh.head_end = tile_gbase + uint64_t(t_fe) + 1;
             }
             if (lane == 0) {
+                sh.n_end_acc += nE;
                 sh.x_in = X;
                 sh.prefix = cnt - ((carried && adj) ? 1u : 0u);  // (the records after a carried END that is not written move up one)
                 sh.adj = adj | (is_head ? 2u : 0u);
             }
             cnt += nK - adj;
-            n_end += nE;
         }
 
         // ---- scatter: the tile-local positions of my kept ENDs to their ranks (the list window by window of SC_CAP: one
@@ -459,17 +471,16 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                         if (sh.wle[pb][q] >= 0) t_le = sh.wle[pb][q];
                     open_after = t_ls > t_le;
                 }
-                if (t_ls >= 0 || t_fe != NO_POS) {
+                if ((t_ls >= 0 || t_fe != NO_POS) && lane == 0) {  // (read again by warp 0 after the next tile's barrier (A))
                     const uint64_t tile_gbase = p.global_off + uint64_t(t) * SC_T;
-                    X = (open_after && t_ls >= 0) ? tile_gbase + uint64_t(t_ls) + OPEN_BIAS : (open_after ? X : OPEN_NONE);
-                    seen = true;
+                    sh.x_state = (open_after && t_ls >= 0) ? tile_gbase + uint64_t(t_ls) + OPEN_BIAS : (open_after ? sh.x_in : OPEN_NONE);
+                    sh.seen = 1;
                 }
             }
             if (nK == 0) break;
 
             const uint32_t prefix = sh.prefix + win;
             const uint32_t n_win = nK - win < uint32_t(SC_CAP) ? nK - win : uint32_t(SC_CAP);
-            uint32_t bases32 = 0;
             // entry -> lane: the first SC_THREADS entries in order, later rounds from the last thread down (warp 0 carries the chunk
             // state: the extra rounds land on the warps that are ahead)
             for (uint32_t i = uint32_t(tid), nxt = 2u * SC_THREADS - 1u - uint32_t(tid); i < n_win; i = nxt, nxt += SC_THREADS) {
@@ -497,10 +508,8 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                 } else {
                     p.res->overflow |= 1;
                 }
-                bases32 += len;
                 if (len <= uint32_t(MAX_C_LEN)) atomicAdd(&sh.hist[len], 1u);
-                my_last_o = o;
-                my_last_len = len;
+                else atomicAdd(&sh.big_bases, (unsigned long long)len);
                 // BWT prefilter: the one-popcount bound (planes.cuh) on the analysed range [st, st + len) in the plane window, one
                 // quad {plane 0 lo, hi, plane 1 lo, hi} = 64 positions per step; a record whose range starts before the window goes
                 // straight to the exact test
@@ -538,32 +547,35 @@ __global__ void __launch_bounds__(SC_THREADS, SC_OCC) k_cluster_scan(const __gri
                     }
                 }
             }
-            acc_bases += bases32;
         }
     }
 
     // ---- what the chunk leaves for k_chunk_resolve
     __syncthreads();
+    unsigned long long acc_bases = tid == 0 ? sh.big_bases : 0ull;  // sum of the written lengths: from the histogram
     for (int i = tid; i < E2S_HIST_BINS; i += SC_THREADS)
-        if (sh.hist[i]) atomicAdd(&p.res->hist[i], (unsigned long long)sh.hist[i]);
+        if (sh.hist[i]) {
+            atomicAdd(&p.res->hist[i], (unsigned long long)sh.hist[i]);
+            acc_bases += (unsigned long long)sh.hist[i] * uint32_t(i);
+        }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc_bases += __shfl_xor_sync(FULL, acc_bases, d);
     ChunkRec* cr = p.chunks + c;
     if (lane == 0 && acc_bases) atomicAdd(&cr->n_bases, acc_bases);
     if (tid == 0) {
+        const uint64_t X = sh.x_state;
         cr->own_count = cnt;
-        cr->head_end = head_end;
-        cr->last_state = seen ? (X >= OPEN_BIAS ? X : 1ull) : 0ull;  // 0: no event; 1: closed; >= 2: OPEN_BIAS + global START
-        cr->n_end = n_end;
-        sh.prefix = cnt;  // (for the thread that wrote the chunk's last record)
+        cr->head_end = sh.head_end;
+        cr->last_state = sh.seen ? (X >= OPEN_BIAS ? X : 1ull) : 0ull;  // 0: no event; 1: closed; >= 2: OPEN_BIAS + global START
+        cr->n_end = sh.n_end_acc;
+        // the chunk's last record (written by some thread of this CTA before the barrier above)
+        if (cnt && cnt - 1 < seg_room) cr->last_len = seg_len[cnt - 1];
         if (c == 0 && p.tail_lcp) {
             p.res->tail_lcp_nm2 = p.tail_lcp[0];
             p.res->tail_lcp_nm1 = p.tail_lcp[1];
             p.res->tail_bwt_nm1 = p.tail_bwt[0];
         }
     }
-    __syncthreads();
-    if (my_last_o + 1 == sh.prefix && sh.prefix != 0) cr->last_len = my_last_len;
 }
 
 // =============================================================================================
@@ -737,16 +749,40 @@ static PFN_encodeTiled scan_encode_fn() {
 
 uint64_t scan_num_tiles(uint64_t n_local) { return (n_local + SC_T - 1) / SC_T; }
 
+using ScanKernel = void (*)(const CUtensorMap, const Scan8Params);
+// the build that keeps the most CTAs resident, among equals the one ptxas gave more registers (E2S_SCAN_OCC=3|4 forces one)
+static ScanKernel scan_kernel() {
+    static const ScanKernel chosen = [] {
+        const ScanKernel k3 = static_cast<ScanKernel>(k_cluster_scan<3>), k4 = static_cast<ScanKernel>(k_cluster_scan<SC_OCC>);
+        if (const char* e = getenv("E2S_SCAN_OCC")) {
+            if (atoi(e) == 3) return k3;
+            if (atoi(e) == SC_OCC) return k4;
+        }
+        int o3 = 0, o4 = 0;
+        cudaFuncAttributes a3{}, a4{};
+        cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SC_DYN_SMEM));
+        cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SC_DYN_SMEM));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k3, SC_THREADS, SC_DYN_SMEM) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o4, k4, SC_THREADS, SC_DYN_SMEM) != cudaSuccess ||
+            cudaFuncGetAttributes(&a3, k3) != cudaSuccess || cudaFuncGetAttributes(&a4, k4) != cudaSuccess) {
+            cudaGetLastError();
+            return k4;
+        }
+        return (o3 > o4 || (o3 == o4 && a3.numRegs > a4.numRegs)) ? k3 : k4;
+    }();
+    return chosen;
+}
+
 static int scan_occupancy(int* out) {
     static int occ_dev[64] = {0};  // function attributes are per device
     int dev = 0;
     cudaGetDevice(&dev);
     int& occ = occ_dev[dev & 63];
     if (!occ) {
-        cudaError_t e = cudaFuncSetAttribute(k_cluster_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SC_DYN_SMEM));
+        cudaError_t e = cudaFuncSetAttribute(scan_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, int(SC_DYN_SMEM));
         if (e != cudaSuccess) return int(e);
         int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_cluster_scan, SC_THREADS, SC_DYN_SMEM);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, scan_kernel(), SC_THREADS, SC_DYN_SMEM);
         if (e != cudaSuccess) return int(e);
         if (o < 1) return int(cudaErrorLaunchOutOfResources);
         occ = o;
@@ -797,7 +833,7 @@ cudaError_t launch_scan(const Scan8Params& p0, uint64_t alloc_r, cudaStream_t st
     int occ = 0;
     const int rc = scan_occupancy(&occ);
     if (rc) return cudaError_t(rc);
-    k_cluster_scan<<<dim3(p.n_chunks), dim3(SC_THREADS), SC_DYN_SMEM, stream>>>(tmap, p);
+    scan_kernel()<<<dim3(p.n_chunks), dim3(SC_THREADS), SC_DYN_SMEM, stream>>>(tmap, p);
     return cudaGetLastError();
 }
 
