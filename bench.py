@@ -776,7 +776,7 @@ def main():
     # algorithmic bytes per launch (DESIGN.md "Kernels"): what the kernel has to move for this shard
     fused = ktimes[api.KERNEL_SCAN][1] == 0             # K2 ran the BWT prefilter itself (e2s_cluster_prefilter): no K3a launch
     alg = {
-        api.KERNEL_FLAGS: lcp_bytes * n + n / 4,        # resident LCP (1 B when every value <= 127, else 4 B) read once + 2 bit masks written
+        api.KERNEL_FLAGS: lcp_bytes * n + n / 4,        # resident LCP (1 B bit-sliced, else 4 B) read once + 2 bit masks written
         api.KERNEL_EMIT: n / 4 + 10 * m_own + (pos_analysed / 4 if fused else 0),  # masks read + records written (+ the 2-bit base codes inside analysed clusters)
         api.KERNEL_SCAN: pos_analysed / 4 + 10 * m_own,  # 2-bit base code (resident bit planes) of positions in analysed clusters + record list
         api.KERNEL_EXACT: 0,
@@ -818,7 +818,7 @@ def main():
                     "fused_prefilter": bool(fused), "resident_lcp_bytes": lcp_bytes,
                     "note": "k_cluster_scan = LCP stencil (bit-sliced compare) + ranks + compaction + length histogram + BWT prefilter in one pass over the "
                             "bit-sliced LCP (1 B/position), one CTA per chunk of tiles; bound by instruction issue, not DRAM (DESIGN.md 3.1); "
-                            "k_lcp_flags / k_cluster_emit only run on shards with an LCP value > 127 or for -m > 33",
+                            "k_lcp_flags / k_cluster_emit only run for -m > 33 and for -k > 127 on shards with an LCP value > 127",
                     "pipeline": {"alg_bytes_per_step": sum(alg[k] for k in alg if ktimes[k][1]),
                                  "GBps": sum(alg[k] for k in alg if ktimes[k][1]) / (ms / args.steps * 1e-3) / 1e9,
                                  "frac_of_peak": sum(alg[k] for k in alg if ktimes[k][1]) / (ms / args.steps * 1e-3) / 1e9 / peak}}
@@ -928,7 +928,7 @@ def main():
             "config": {"workload": workload_name(args), "positions_per_gpu": n, "positions_total": n_global,
                        "parallelism": f"{world} contiguous eBWT shard(s), one per GPU; " + ("one ncclAllGather of the shard summaries per step, issued by the library on its stream (e2s_pipeline_sharded)" if comm is not None else ("no exchange (single shard: e2s_pipeline_resident)" if world == 1 else "torch.distributed all-gather of shard summaries")),
                        "l2": "the resident inputs a step streams (1.25 B/position, 4.25 on the 4-byte path: >= 0.7 GB per GPU at C2, 4.8 GB at C3) exceed the 126 MB L2; no flush needed",
-                       "resident_layout": f"SoA: lcp u32 + text u32 + suff u32 + bwt u8; written by the loads: 2-bit base-code planes of the BWT + a bit-sliced LCP (7 bit planes + the descent plane, 1 B/position); the scan streams {'the bit-sliced copy (every LCP value <= 127)' if lcp_bytes == 1 else 'the 4-byte LCP'}",
+                       "resident_layout": f"SoA: lcp u32 + text u32 + suff u32 + bwt u8; written by the loads: 2-bit base-code planes of the BWT + a bit-sliced LCP (7 bit planes + the descent plane, 1 B/position); the scan streams {'the bit-sliced copy (values above 127 saturated: exact for -k <= 127)' if lcp_bytes == 1 else 'the 4-byte LCP'}",
                        "scale": args.scale, "tiles": T, "exchange_us": exchange_us,
                        "seal": {"ms": seal_ms, "kernels_over_the_data": 0,
                                 "note": "the bit-sliced LCP and the base-code planes are written by the loads (k_derive): sealing is a 4-byte read-back"}},
