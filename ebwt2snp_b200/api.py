@@ -80,7 +80,7 @@ class PipelineResult(C.Structure):
 SYMBOLS = [
     "e2s_version", "e2s_ctx_create", "e2s_ctx_destroy", "e2s_last_error", "e2s_ctx_set_stream",
     "e2s_ctx_synchronize", "e2s_ctx_mem_info", "e2s_ctx_launch_count", "e2s_ctx_timing", "e2s_ctx_kernel_time", "e2s_shard_create", "e2s_shard_destroy", "e2s_shard_load_gesa", "e2s_shard_load_gesa_fd",
-    "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_build_egsa_dev", "e2s_build_egsa", "e2s_shard_set_layout", "e2s_shard_seal", "e2s_shard_lcp_bytes_resident", "e2s_reads_stage", "e2s_reads_stage_dev",
+    "e2s_shard_load_soa", "e2s_shard_load_soa_dev", "e2s_build_egsa_dev", "e2s_build_egsa", "e2s_build_egsa_ragged_dev", "e2s_build_egsa_ragged", "e2s_shard_set_layout", "e2s_shard_seal", "e2s_shard_lcp_bytes_resident", "e2s_reads_stage", "e2s_reads_stage_dev",
     "e2s_cluster_prefilter", "e2s_cluster_run", "e2s_cluster_merge", "e2s_cluster_finalize", "e2s_cluster_lm", "e2s_cluster_count",
     "e2s_cluster_fetch", "e2s_cluster_fetch_packed", "e2s_clusters_stage_packed", "e2s_clusters_stage",
     "e2s_statistics", "e2s_statistics_finish", "e2s_exchange_finish", "e2s_snp_default_params", "e2s_find_events", "e2s_events_fetch",
@@ -127,6 +127,8 @@ def load_library():
     lib.e2s_shard_seal.argtypes = [C.c_void_p]
     lib.e2s_build_egsa_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_void_p] * 4
     lib.e2s_build_egsa.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_void_p] * 4
+    lib.e2s_build_egsa_ragged_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 4
+    lib.e2s_build_egsa_ragged.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 4
     lib.e2s_shard_lcp_bytes_resident.argtypes = [C.c_void_p]
     lib.e2s_shard_set_layout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.e2s_reads_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
@@ -351,6 +353,26 @@ class Context:
         self._ck(self.lib.e2s_build_egsa_dev(self.h, _ptr(reads_t), R, L, _ptr(out["lcp"]), _ptr(out["text"]),
                                              _ptr(out["suff"]), _ptr(out["bwt"])))
         out.update(n=n, L=L, R=R)
+        return out
+
+    def build_egsa_ragged(self, bases, off):
+        """The same for reads of any lengths (e2s_build_egsa_ragged_dev): `bases` = all reads back to back (numpy uint8 or a
+        torch tensor on this context's device), `off` = R + 1 offsets (host).  n = off[R] + R records."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        R = len(off) - 1
+        n = int(off[R]) + R
+        bases_t = (torch.from_numpy(np.ascontiguousarray(bases, dtype=np.uint8).reshape(-1)) if isinstance(bases, np.ndarray) else bases)
+        if bases_t.numel() == 0:
+            bases_t = torch.zeros(1, dtype=torch.uint8)
+        bases_t = bases_t.to(dev).contiguous()
+        out = {k: torch.empty(n, dtype=torch.int32, device=dev) for k in ("lcp", "text", "suff")}
+        out["bwt"] = torch.empty(n, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)
+        self._ck(self.lib.e2s_build_egsa_ragged_dev(self.h, _ptr(bases_t), off.ctypes.data, R, _ptr(out["lcp"]), _ptr(out["text"]),
+                                                    _ptr(out["suff"]), _ptr(out["bwt"])))
+        out.update(n=n, R=R)
         return out
 
     def shard(self, n_local, global_off=0, n_global=None, chunk_positions=None):

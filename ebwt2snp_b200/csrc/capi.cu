@@ -859,38 +859,83 @@ int e2s_shard_load_lcp_bwt(e2s_shard* s, const void* lcp, int x, const uint8_t* 
     return load_lcp_bwt(s, lcp, x, bwt, first, count, false);
 }
 
-int e2s_build_egsa_dev(e2s_ctx* c, const uint8_t* d_reads, uint64_t n_reads, uint32_t read_len, uint32_t* d_lcp, uint32_t* d_text,
-                       uint32_t* d_suff, uint8_t* d_bwt) {
-    if (!c || !d_reads || !d_lcp || !d_text || !d_suff || !d_bwt) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_dev: NULL argument");
-    if (n_reads == 0 || read_len == 0) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_dev: empty read collection");
-    if (n_reads > 0xffffffffull || n_reads * (uint64_t(read_len) + 1) > 0xffffffffull)
-        return fail(c, E2S_ERR_UNSUPPORTED, "e2s_build_egsa_dev: more than 2^32 - 1 suffixes in one call (build per shard)");
-    CU(c, cudaSetDevice(c->device));
-    cudaError_t e = build_egsa(d_reads, n_reads, read_len, d_lcp, d_text, d_suff, d_bwt, c->stream, &c->launches);
+// shared by the four builder entry points.  off = nullptr: n_reads reads of read_len bases; else n_reads + 1 HOST offsets.
+static int build_egsa_common(e2s_ctx* c, const char* who, const uint8_t* d_reads, const uint64_t* off, uint64_t n_reads, uint32_t read_len,
+                             uint32_t* d_lcp, uint32_t* d_text, uint32_t* d_suff, uint8_t* d_bwt) {
+    if (n_reads > 0xffffffffull) return fail(c, E2S_ERR_UNSUPPORTED, std::string(who) + ": more than 2^32 - 1 reads (text is a 32-bit field)");
+    uint64_t total = n_reads * uint64_t(read_len);
+    uint32_t longest = read_len;
+    uint64_t* d_off = nullptr;
+    if (off) {
+        if (off[0] != 0) return fail(c, E2S_ERR_ARG, std::string(who) + ": off[0] must be 0");
+        longest = 0;
+        for (uint64_t r = 0; r < n_reads; ++r) {
+            if (off[r + 1] < off[r]) return fail(c, E2S_ERR_ARG, std::string(who) + ": read offsets must not decrease");
+            const uint64_t l = off[r + 1] - off[r];
+            if (l >= 65536) return fail(c, E2S_ERR_UNSUPPORTED, std::string(who) + ": a read of 65536 bases or more (the keys are fixed-width: short reads only)");
+            longest = l > longest ? uint32_t(l) : longest;
+        }
+        total = off[n_reads];
+        if (longest == 0) return fail(c, E2S_ERR_ARG, std::string(who) + ": every read is empty");
+        if (cudaMalloc(reinterpret_cast<void**>(&d_off), (n_reads + 1) * 8) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(c, E2S_ERR_NOMEM, std::string(who) + ": read offsets on the device");
+        }
+        cudaError_t eo = cudaMemcpyAsync(d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+        if (eo != cudaSuccess) {
+            cudaFree(d_off);
+            return cuda_fail(c, eo, "H2D read offsets");
+        }
+    }
+    cudaError_t e = build_egsa(d_reads, d_off, n_reads, longest, total, d_lcp, d_text, d_suff, d_bwt, c->stream, &c->launches);
+    if (d_off) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(d_off);
+    }
     if (e == cudaErrorMemoryAllocation) {
         cudaGetLastError();
-        return fail(c, E2S_ERR_NOMEM, "e2s_build_egsa_dev: scratch buffers (about 24 bytes per suffix)");
+        return fail(c, E2S_ERR_NOMEM, std::string(who) + ": scratch buffers (24.5 bytes per suffix with 32-bit suffix ids, 32.5 with 64-bit ids)");
     }
     if (e == cudaErrorInvalidValue) {
         cudaGetLastError();
         return fail(c, E2S_ERR_UNSUPPORTED,
-                    "e2s_build_egsa_dev: a read holds a base outside ACGT/acgt (N has no 2-bit code; the reference itself is "
+                    std::string(who) + ": a read holds a base outside ACGT/acgt (N has no 2-bit code; the reference itself is "
                     "non-deterministic on N, ref:include.hpp:273) -- filter such reads first");
+    }
+    if (e == cudaErrorInvalidConfiguration) {
+        cudaGetLastError();
+        return fail(c, E2S_ERR_UNSUPPORTED, std::string(who) + ": the collection is outside what one call sorts (read length < 65536, < 2^43 suffixes)");
     }
     if (e != cudaSuccess) return cuda_fail(c, e, "build_egsa");
     return E2S_OK;
 }
 
-int e2s_build_egsa(e2s_ctx* c, const uint8_t* reads, uint64_t n_reads, uint32_t read_len, uint32_t* lcp, uint32_t* text, uint32_t* suff,
-                   uint8_t* bwt) {
-    if (!c || !reads || !lcp || !text || !suff || !bwt) return fail(c, E2S_ERR_ARG, "e2s_build_egsa: NULL argument");
-    if (n_reads == 0 || read_len == 0) return fail(c, E2S_ERR_ARG, "e2s_build_egsa: empty read collection");
+int e2s_build_egsa_dev(e2s_ctx* c, const uint8_t* d_reads, uint64_t n_reads, uint32_t read_len, uint32_t* d_lcp, uint32_t* d_text,
+                       uint32_t* d_suff, uint8_t* d_bwt) {
+    if (!c || !d_reads || !d_lcp || !d_text || !d_suff || !d_bwt) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_dev: NULL argument");
+    if (n_reads == 0 || read_len == 0) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_dev: empty read collection");
     CU(c, cudaSetDevice(c->device));
-    const uint64_t n = n_reads * (uint64_t(read_len) + 1);
+    return build_egsa_common(c, "e2s_build_egsa_dev", d_reads, nullptr, n_reads, read_len, d_lcp, d_text, d_suff, d_bwt);
+}
+
+int e2s_build_egsa_ragged_dev(e2s_ctx* c, const uint8_t* d_bases, const uint64_t* off, uint64_t n_reads, uint32_t* d_lcp, uint32_t* d_text,
+                              uint32_t* d_suff, uint8_t* d_bwt) {
+    if (!c || !d_bases || !off || !d_lcp || !d_text || !d_suff || !d_bwt) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_ragged_dev: NULL argument");
+    if (n_reads == 0) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_ragged_dev: empty read collection");
+    CU(c, cudaSetDevice(c->device));
+    return build_egsa_common(c, "e2s_build_egsa_ragged_dev", d_bases, off, n_reads, 0, d_lcp, d_text, d_suff, d_bwt);
+}
+
+// host buffers in and out: device buffers allocated and released here
+static int build_egsa_host(e2s_ctx* c, const char* who, const uint8_t* reads, const uint64_t* off, uint64_t n_reads, uint32_t read_len,
+                           uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt) {
+    CU(c, cudaSetDevice(c->device));
+    const uint64_t total = off ? off[n_reads] : n_reads * uint64_t(read_len);
+    const uint64_t n = total + n_reads;
     uint8_t *d_reads = nullptr, *d_bwt = nullptr;
     uint32_t *d_lcp = nullptr, *d_text = nullptr, *d_suff = nullptr;
     auto release = [&]() { cudaFree(d_reads); cudaFree(d_bwt); cudaFree(d_lcp); cudaFree(d_text); cudaFree(d_suff); };
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_reads), n_reads * read_len);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_reads), total ? total : 1);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_bwt), n);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_lcp), n * 4);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_text), n * 4);
@@ -898,10 +943,10 @@ int e2s_build_egsa(e2s_ctx* c, const uint8_t* reads, uint64_t n_reads, uint32_t 
     if (e != cudaSuccess) {
         release();
         cudaGetLastError();
-        return fail(c, E2S_ERR_NOMEM, "e2s_build_egsa: device buffers");
+        return fail(c, E2S_ERR_NOMEM, std::string(who) + ": device buffers");
     }
-    e = cudaMemcpyAsync(d_reads, reads, n_reads * read_len, cudaMemcpyHostToDevice, c->stream);
-    int rc = e == cudaSuccess ? e2s_build_egsa_dev(c, d_reads, n_reads, read_len, d_lcp, d_text, d_suff, d_bwt) : cuda_fail(c, e, "H2D reads");
+    e = cudaMemcpyAsync(d_reads, reads, total, cudaMemcpyHostToDevice, c->stream);
+    int rc = e == cudaSuccess ? build_egsa_common(c, who, d_reads, off, n_reads, read_len, d_lcp, d_text, d_suff, d_bwt) : cuda_fail(c, e, "H2D reads");
     if (rc == E2S_OK) {
         e = cudaMemcpyAsync(lcp, d_lcp, n * 4, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(text, d_text, n * 4, cudaMemcpyDeviceToHost, c->stream);
@@ -912,6 +957,20 @@ int e2s_build_egsa(e2s_ctx* c, const uint8_t* reads, uint64_t n_reads, uint32_t 
     }
     release();
     return rc;
+}
+
+int e2s_build_egsa(e2s_ctx* c, const uint8_t* reads, uint64_t n_reads, uint32_t read_len, uint32_t* lcp, uint32_t* text, uint32_t* suff,
+                   uint8_t* bwt) {
+    if (!c || !reads || !lcp || !text || !suff || !bwt) return fail(c, E2S_ERR_ARG, "e2s_build_egsa: NULL argument");
+    if (n_reads == 0 || read_len == 0) return fail(c, E2S_ERR_ARG, "e2s_build_egsa: empty read collection");
+    return build_egsa_host(c, "e2s_build_egsa", reads, nullptr, n_reads, read_len, lcp, text, suff, bwt);
+}
+
+int e2s_build_egsa_ragged(e2s_ctx* c, const uint8_t* bases, const uint64_t* off, uint64_t n_reads, uint32_t* lcp, uint32_t* text,
+                          uint32_t* suff, uint8_t* bwt) {
+    if (!c || !bases || !off || !lcp || !text || !suff || !bwt) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_ragged: NULL argument");
+    if (n_reads == 0) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_ragged: empty read collection");
+    return build_egsa_host(c, "e2s_build_egsa_ragged", bases, off, n_reads, 0, lcp, text, suff, bwt);
 }
 
 int e2s_shard_set_layout(e2s_shard* s, int x, int y, int z, int bcr) {

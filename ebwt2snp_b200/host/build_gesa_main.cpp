@@ -3,8 +3,8 @@
 // (ref:include.hpp:42-81).  Stands in for the external `egsa` / BCR run of ref:pipeline.sh:98-109 and
 // ref:README.md:46-60; record layout as egsa_stream reads it: text(y) suff(z) lcp(x) bwt(1), little endian
 // (ref:include.hpp:126-155).  -x / -y / -z have the meaning and the defaults (1 / 4 / 1) of the two tools, so the same
-// flags can be passed to all three.  This version needs equal-length reads (what the reference's read simulators and
-// this repository's workloads produce) and fewer than 2^32 suffixes.
+// flags can be passed to all three.  Reads may have any lengths below 65536 (empty ones included, as the reference's
+// FASTA parser keeps them, ref:clust2snp.cpp:147-212); bases must be ACGT / acgt.
 #include <getopt.h>
 
 #include <string>
@@ -54,17 +54,22 @@ int main(int argc, char** argv) {
         printf("Error: could not read %s\n", input.c_str());
         return 1;
     }
-    const uint64_t R = reads.n_reads(), L = reads.off[1] - reads.off[0];
-    for (uint64_t r = 0; r < R; ++r)
-        if (reads.off[r + 1] - reads.off[r] != L || L == 0) {
-            printf("Error: read %llu has %llu bases, the first one %llu: this version needs equal-length, non-empty reads.\n",
-                   (unsigned long long)r, (unsigned long long)(reads.off[r + 1] - reads.off[r]), (unsigned long long)L);
-            return 2;
-        }
-    const uint64_t n = R * (L + 1);
+    const uint64_t R = reads.n_reads();
+    uint64_t L = 0;  // the longest read
+    bool equal = true;
+    for (uint64_t r = 0; r < R; ++r) {
+        const uint64_t l = reads.off[r + 1] - reads.off[r];
+        L = l > L ? l : L;
+        equal = equal && l == reads.off[1] - reads.off[0];
+    }
+    if (L == 0) {
+        printf("Error: every read of %s is empty.\n", input.c_str());
+        return 2;
+    }
+    const uint64_t n = reads.bases.size() + R;
     auto fits = [](uint64_t v, int nb) { return nb >= 8 || v < (uint64_t(1) << (8 * nb)); };
     if (!fits(R - 1, y) || !fits(L, z) || !fits(L, x))
-        printf("Warning: values do not fit the requested field widths and will be truncated (%llu reads, %llu bases).\n",
+        printf("Warning: values do not fit the requested field widths and will be truncated (%llu reads, longest %llu bases).\n",
                (unsigned long long)R, (unsigned long long)L);
     e2s_ctx* ctx = nullptr;
     if (e2s_ctx_create(0, &ctx) != E2S_OK) {
@@ -73,7 +78,9 @@ int main(int argc, char** argv) {
     }
     std::vector<uint32_t> lcp(n), text(n), suff(n);
     std::vector<uint8_t> bwt(n);
-    if (e2s_build_egsa(ctx, reads.bases.data(), R, uint32_t(L), lcp.data(), text.data(), suff.data(), bwt.data()) != E2S_OK) {
+    const int brc = equal ? e2s_build_egsa(ctx, reads.bases.data(), R, uint32_t(L), lcp.data(), text.data(), suff.data(), bwt.data())
+                          : e2s_build_egsa_ragged(ctx, reads.bases.data(), reads.off.data(), R, lcp.data(), text.data(), suff.data(), bwt.data());
+    if (brc != E2S_OK) {
         printf("Error: %s\n", e2s_last_error(ctx));
         e2s_ctx_destroy(ctx);
         return 3;

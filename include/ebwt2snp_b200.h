@@ -109,13 +109,22 @@ int e2s_shard_load_soa_dev(e2s_shard *sh, const uint32_t *d_lcp, const uint32_t 
  * n_reads reads of read_len ACGT bases each (DEVICE pointer, row-major ASCII, no separators) and writes the four arrays
  * of n = n_reads * (read_len + 1) records to DEVICE memory, ready for e2s_shard_load_soa_dev: one record per suffix
  * incl. the terminator suffix, `$` < A < C < G < T, equal suffixes by read id, lcp never extends over a terminator,
- * bwt = preceding base or `$` (0x24).  n must be < 2^32 per call.  Synchronises the context's stream. */
+ * bwt = preceding base or `$` (0x24).  The sort is the library's own radix sort (csrc/build_egsa.cu); suffix ids are
+ * 32-bit while n < 2^32 and 64-bit beyond (scratch: 24.5 / 32.5 bytes per suffix).  Synchronises the context's stream. */
 int e2s_build_egsa_dev(e2s_ctx *ctx, const uint8_t *d_reads, uint64_t n_reads, uint32_t read_len, uint32_t *d_lcp,
                        uint32_t *d_text, uint32_t *d_suff, uint8_t *d_bwt);
 
 /* Same from / to HOST memory (what ebwt2snp_b200/bin/build_gesa uses): device buffers are allocated and released inside. */
 int e2s_build_egsa(e2s_ctx *ctx, const uint8_t *reads, uint64_t n_reads, uint32_t read_len, uint32_t *lcp, uint32_t *text,
                    uint32_t *suff, uint8_t *bwt);
+
+/* Reads of ANY lengths, as the reference's FASTA parser accepts them (ref:clust2snp.cpp:147-212; empty reads included):
+ * d_bases = all reads back to back (DEVICE pointer), off = n_reads + 1 offsets into it in HOST memory (off[0] = 0,
+ * non-decreasing, every read shorter than 65536 bases).  n = off[n_reads] + n_reads records, same conventions. */
+int e2s_build_egsa_ragged_dev(e2s_ctx *ctx, const uint8_t *d_bases, const uint64_t *off, uint64_t n_reads, uint32_t *d_lcp,
+                              uint32_t *d_text, uint32_t *d_suff, uint8_t *d_bwt);
+int e2s_build_egsa_ragged(e2s_ctx *ctx, const uint8_t *bases, const uint64_t *off, uint64_t n_reads, uint32_t *lcp,
+                          uint32_t *text, uint32_t *suff, uint8_t *bwt);
 
 /* Layout of the index files the shard was loaded from: byte widths of lcp (x), text (y), suff (z) and whether it
  * was the BCR triple.  Only the reference's post-EOF phantom record depends on it.

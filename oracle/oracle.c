@@ -523,3 +523,53 @@ int oracle_build_egsa(const uint8_t *reads, uint64_t n_reads, uint32_t read_len,
     free(idx);
     return 0;
 }
+
+/* The same for reads of any lengths (the reference's FASTA parser accepts them, ref:clust2snp.cpp:147-212; empty reads
+ * included): bases = all reads back to back, off = n_reads + 1 offsets.  n = off[n_reads] + n_reads records.
+ * Checks e2s_build_egsa_ragged(_dev).  A suffix is (read << 32 | offset). */
+static const uint64_t *g_sort_off;
+
+static int ragged_cmp(const void *pa, const void *pb) {
+    const uint64_t a = *(const uint64_t *)pa, b = *(const uint64_t *)pb;
+    const uint64_t ra = a >> 32, rb = b >> 32;
+    const uint32_t oa = (uint32_t)a, ob = (uint32_t)b;
+    const uint8_t *sa = g_sort_reads + g_sort_off[ra] + oa, *sb = g_sort_reads + g_sort_off[rb] + ob;
+    const uint32_t la = (uint32_t)(g_sort_off[ra + 1] - g_sort_off[ra]) - oa, lb = (uint32_t)(g_sort_off[rb + 1] - g_sort_off[rb]) - ob;
+    const uint32_t lm = la < lb ? la : lb;
+    for (uint32_t i = 0; i < lm; ++i) {
+        if (sa[i] != sb[i]) return sa[i] < sb[i] ? -1 : 1;
+    }
+    if (la != lb) return la < lb ? -1 : 1;
+    return ra < rb ? -1 : (ra > rb ? 1 : 0);
+}
+
+int oracle_build_egsa_ragged(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, uint32_t *lcp, uint32_t *text,
+                             uint32_t *suff, uint8_t *bwt) {
+    const uint64_t n = off[n_reads] + n_reads;
+    uint64_t *idx = (uint64_t *)malloc((n ? n : 1) * sizeof *idx);
+    if (!idx) return -1;
+    uint64_t at = 0;
+    for (uint64_t r = 0; r < n_reads; ++r)
+        for (uint64_t o = 0; o <= off[r + 1] - off[r]; ++o) idx[at++] = (r << 32) | o;
+    g_sort_reads = bases;
+    g_sort_off = off;
+    qsort(idx, n, sizeof *idx, ragged_cmp);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t r = idx[i] >> 32;
+        const uint32_t o = (uint32_t)idx[i];
+        text[i] = (uint32_t)r;
+        suff[i] = o;
+        bwt[i] = o ? bases[off[r] + o - 1] : (uint8_t)'$';
+        uint32_t l = 0;
+        if (i) {
+            const uint64_t r0 = idx[i - 1] >> 32;
+            const uint32_t o0 = (uint32_t)idx[i - 1];
+            const uint32_t la = (uint32_t)(off[r + 1] - off[r]) - o, lb = (uint32_t)(off[r0 + 1] - off[r0]) - o0;
+            const uint32_t lm = la < lb ? la : lb;
+            while (l < lm && bases[off[r0] + o0 + l] == bases[off[r] + o + l]) ++l;
+        }
+        lcp[i] = l;
+    }
+    free(idx);
+    return 0;
+}

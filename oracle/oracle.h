@@ -109,6 +109,10 @@ void oracle_distance(const char *a, const char *b, int len, int max_gap, int *D,
 int oracle_build_egsa(const uint8_t *reads, uint64_t n_reads, uint32_t read_len, uint32_t *lcp, uint32_t *text,
                       uint32_t *suff, uint8_t *bwt);
 
+/* reads of any lengths: bases back to back, off = n_reads + 1 offsets; n = off[n_reads] + n_reads records */
+int oracle_build_egsa_ragged(const uint8_t *bases, const uint64_t *off, uint64_t n_reads, uint32_t *lcp, uint32_t *text,
+                             uint32_t *suff, uint8_t *bwt);
+
 void oracle_free(void *p);
 
 #ifdef __cplusplus

@@ -206,3 +206,23 @@ def build_egsa(reads: np.ndarray):
         raise MemoryError("oracle_build_egsa")
     out.update(n=n, L=L, R=R)
     return out
+
+
+def build_egsa_ragged(bases: np.ndarray, off: np.ndarray):
+    """oracle_build_egsa_ragged: reads of any lengths (bases back to back, off = R + 1 offsets); numpy dict as build_egsa."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8).reshape(-1)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    R = len(off) - 1
+    n = int(off[R]) + R
+    out = {k: np.empty(n, dtype=np.uint32) for k in ("lcp", "text", "suff")}
+    out["bwt"] = np.empty(n, dtype=np.uint8)
+    pad = bases if bases.size else np.zeros(1, dtype=np.uint8)
+    f = lib().oracle_build_egsa_ragged
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 4
+    rc = f(pad.ctypes.data, off.ctypes.data, R, out["lcp"].ctypes.data, out["text"].ctypes.data, out["suff"].ctypes.data,
+           out["bwt"].ctypes.data)
+    if rc:
+        raise MemoryError("oracle_build_egsa_ragged")
+    out.update(n=n, R=R)
+    return out

@@ -209,14 +209,6 @@ def test_build_gesa_cli_feeds_both_tool_chains(built, tmp_path):
         assert open(str(tmp_path / "b0" / "got" / "ALL.snp"), "rb").read() == mine_snp
 
 
-def test_build_gesa_cli_rejects_ragged_reads(built, tmp_path):
-    fa = str(tmp_path / "r.fasta")
-    open(fa, "w").write(">a\nACGT\n>b\nACG\n")
-    r = run("build_gesa", "-i", fa)
-    assert r.returncode == 2 and "equal-length" in r.stdout
-    assert not os.path.exists(fa + ".gesa")
-
-
 def test_reads_to_scores_with_the_tools_alone(built, tmp_path):
     """the reference's pipeline.sh end to end with this repository's tools only (ref:pipeline.sh:98-140): reads FASTA ->
     build_gesa (4/1/1, egsa's default layout) -> ebwt2clust -> clust2snp -> snp_vs_vcf against the planted truth.  The .snp

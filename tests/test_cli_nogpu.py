@@ -81,18 +81,18 @@ def test_fasta_reader_multiline_and_ragged(built, tmp_path):
 
 
 def test_build_gesa_decisions_before_gpu_work(built, tmp_path):
-    """build_gesa: help exits 0 like the reference's tools; unreadable input -> 1; ragged reads -> 2 (before any CUDA call);
-    without a GPU the library refuses loudly (exit 3, no index written) -- there is no CPU builder"""
+    """build_gesa: help exits 0 like the reference's tools; unreadable input -> 1; nothing but empty reads -> 2 (before any
+    CUDA call; ragged reads are fine: tests/test_builder_gpu.py); without a GPU the library refuses loudly (exit 3, no index written) -- there is no CPU builder"""
     for args in ([], ["-h"], ["-Q"], ["-x", "3", "-i", "x"]):
         r = run("build_gesa", *args)
         assert r.returncode == 0 and "build_gesa [options]" in r.stdout, args
     assert run("build_gesa", "-i", str(tmp_path / "missing.fasta")).returncode == 1
     fa = tmp_path / "r.fasta"
-    fa.write_text(">a\nACGT\n>b\nACG\n")
+    fa.write_text(">a\n\n>b\n")
     r = run("build_gesa", "-i", str(fa))
-    assert r.returncode == 2 and "equal-length" in r.stdout
+    assert r.returncode == 2 and "empty" in r.stdout
     import torch
     if not torch.cuda.is_available():
-        fa.write_text(">a\nACGT\n>b\nACGA\n")
+        fa.write_text(">a\nACGT\n>b\nACG\n")
         r = run("build_gesa", "-i", str(fa))
         assert r.returncode == 3 and "no CPU fallback" in r.stdout and not os.path.exists(str(fa) + ".gesa")
