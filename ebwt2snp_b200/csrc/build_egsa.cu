@@ -17,7 +17,9 @@
 //                  Ragged: id = (r << shift) | p in (read, offset) order, then one or two radix passes on the suffix
 //                  LENGTH bring it to the same shortest-first order.
 //   per key word w, last word first (zero padding orders a suffix before every longer one it prefixes because the sort is
-//   stable and starts shortest-first):
+//   stable and starts shortest-first).  A digit place moves only the suffixes long enough to have a symbol in it: the
+//   others have digit 0 there, are still a prefix of the shortest-first order and stay where they are (L = 100: 13 passes'
+//   worth of pairs instead of 25):
 //     k_keys_hist  symbols [p + 32 w, p + 32 w + 32) of every suffix as one 64-bit word (funnel shift of two packed
 //                  words) in the current id order, AND the 256-bin histograms of every 8-bit digit of that word in the
 //                  same pass (warp-aggregated shared-memory atomics: most suffixes are shorter than 32 w and share digit 0)
@@ -35,6 +37,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "common.cuh"
 #include "internal.h"
@@ -76,7 +80,19 @@ __device__ __forceinline__ uint32_t code2(uint32_t c) {  // ACGT / acgt -> 0..3 
     return uint32_t(u == 'C') + 2u * uint32_t(u == 'G') + 3u * uint32_t(u == 'T');
 }
 
-// one warp per read, lanes over the row's words (ceil(len / 32) + 1 of them, the last one all padding)
+// bits of x spread to the even positions of a 64-bit word
+__device__ __forceinline__ uint64_t spread_even(uint32_t x) {
+    uint64_t v = x;
+    v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+    v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+// one warp per read; per row word the lanes load 32 consecutive bases, two ballots collect the code bits, lane 0's symbol ends
+// up in the two most significant bits.  The row has ceil(len / 32) + 1 words, the last one all padding.
 // *bad is raised when a base is not one of ACGT / acgt: the 2-bit keys have no code for it (N would sort and compare as A)
 __global__ void k_pack_reads(ReadsView v, uint64_t* __restrict__ packed, uint32_t* __restrict__ bad) {
     const uint64_t r = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -86,18 +102,16 @@ __global__ void k_pack_reads(ReadsView v, uint64_t* __restrict__ packed, uint32_
     const uint32_t len = v.len(r), W = (len + 31) >> 5;
     uint64_t* row = packed + v.row(r, st);
     bool other = false;
-    for (uint32_t w = lane; w <= W; w += 32) {
-        uint64_t x = 0;
-        for (uint32_t j = 0; j < 32; ++j) {
-            const uint32_t s = 32 * w + j;
-            x <<= 2;
-            if (s < len) {
-                const uint32_t c = v.bases[st + s], u = c & 0xDFu;
-                other |= !(u == 'A' || u == 'C' || u == 'G' || u == 'T');
-                x |= code2(c);
-            }
+    for (uint32_t w = 0; w <= W; ++w) {
+        const uint32_t s = 32 * w + lane;
+        uint32_t code = 0;
+        if (s < len) {
+            const uint32_t c = v.bases[st + s], u = c & 0xDFu;
+            other |= !(u == 'A' || u == 'C' || u == 'G' || u == 'T');
+            code = code2(c);
         }
-        row[w] = x;
+        const uint32_t lo = __brev(__ballot_sync(0xffffffffu, code & 1u)), hi = __brev(__ballot_sync(0xffffffffu, code & 2u));
+        if (lane == 0) row[w] = (spread_even(hi) << 1) | spread_even(lo);
     }
     if (other) *bad = 1u;
 }
@@ -153,7 +167,8 @@ __device__ __forceinline__ uint64_t ld_status(const uint64_t* d) {
 template <typename IdT>
 __global__ void __launch_bounds__(256) k_keys_hist(ReadsView v, const uint64_t* __restrict__ packed, const IdT* __restrict__ ids,
                                                    uint64_t n, uint32_t w, uint32_t begin_bit, uint32_t places,
-                                                   uint64_t* __restrict__ keys, unsigned long long* __restrict__ hist) {
+                                                   uint64_t* __restrict__ keys, uint64_t* __restrict__ keys_alt, uint64_t dup,
+                                                   unsigned long long* __restrict__ hist) {
     __shared__ uint32_t s_hist[MAX_PLACES][256];
     for (uint32_t b = threadIdx.x; b < MAX_PLACES * 256; b += blockDim.x) (&s_hist[0][0])[b] = 0;
     __syncthreads();
@@ -170,11 +185,14 @@ __global__ void __launch_bounds__(256) k_keys_hist(ReadsView v, const uint64_t* 
             const uint32_t len = v.len(r);
             key = w == LEN_WORD ? uint64_t(len - p) : suffix_word(packed + v.row(r, st), len, p, w);
             keys[i] = key;
+            if (i < dup) keys_alt[i] = key;  // not moved by the first places: wanted in whichever buffer is current later
         }
         for (uint32_t j = 0; j < places; ++j) {
-            const uint32_t d = valid ? uint32_t(key >> (begin_bit + 8 * j)) & 0xffu : 256u + lane;
-            const uint32_t m = __match_any_sync(0xffffffffu, d);
-            if (valid && lane == uint32_t(__ffs(int(m)) - 1)) atomicAdd(&s_hist[j][d], uint32_t(__popc(m)));
+            // zero padding makes digit 0 the common one in the low places: one atomic per warp for it, plain ones for the rest
+            const uint32_t d = uint32_t(key >> (begin_bit + 8 * j)) & 0xffu;
+            const uint32_t z = __ballot_sync(0xffffffffu, valid && d == 0);
+            if (lane == 0 && z) atomicAdd(&s_hist[j][0], uint32_t(__popc(z)));
+            if (valid && d) atomicAdd(&s_hist[j][d], 1u);
         }
     }
     __syncthreads();
@@ -184,8 +202,12 @@ __global__ void __launch_bounds__(256) k_keys_hist(ReadsView v, const uint64_t* 
     }
 }
 
-// hist[place][bin] -> first output slot of the bin (exclusive scan per place); clears hist for the next word
-__global__ void k_scan_hist(unsigned long long* __restrict__ hist, uint64_t* __restrict__ bin_base) {
+struct PlaceSkip {
+    uint64_t n[MAX_PLACES];  // leading suffixes of the word's range that place j leaves alone (all of them have digit 0 there)
+};
+
+// hist[place][bin] -> first output slot of the bin among the suffixes the place sorts (exclusive scan per place); clears hist
+__global__ void k_scan_hist(unsigned long long* __restrict__ hist, uint64_t* __restrict__ bin_base, PlaceSkip skip) {
     __shared__ uint64_t s[MAX_PLACES][256];
     for (uint32_t b = threadIdx.x; b < MAX_PLACES * 256; b += blockDim.x) {
         (&s[0][0])[b] = hist[b];
@@ -195,7 +217,8 @@ __global__ void k_scan_hist(unsigned long long* __restrict__ hist, uint64_t* __r
     if (threadIdx.x < MAX_PLACES) {
         uint64_t sum = 0;
         for (int b = 0; b < 256; ++b) {
-            const uint64_t t = s[threadIdx.x][b];
+            uint64_t t = s[threadIdx.x][b];
+            if (b == 0) t = t > skip.n[threadIdx.x] ? t - skip.n[threadIdx.x] : 0;
             s[threadIdx.x][b] = sum;
             sum += t;
         }
@@ -204,25 +227,32 @@ __global__ void k_scan_hist(unsigned long long* __restrict__ hist, uint64_t* __r
     for (uint32_t b = threadIdx.x; b < MAX_PLACES * 256; b += blockDim.x) bin_base[b] = (&s[0][0])[b];
 }
 
+template <typename IdT>
+struct PassSmem {
+    uint64_t keys[RS_TILE];           // the tile's keys in output order
+    uint64_t gofs[256];               // output index of staged slot s of bin b = gofs[b] + s
+    IdT ids[RS_TILE];                 // the ids, same order
+    uint32_t whist[RS_WARPS][256];    // per-warp digit counts -> exclusive over the warps
+    uint32_t binstart[256];           // first staged slot of every bin
+    uint32_t wsum[RS_WARPS];
+    uint32_t tile;
+    uint8_t digit[RS_TILE];           // digit of every staged slot
+};
+
 // one stable pass on the digit (key >> shift) & 255
 template <typename IdT, bool WRITE_KEYS>
-__global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(const uint64_t* __restrict__ kin, const IdT* __restrict__ iin,
+__global__ void __launch_bounds__(RS_THREADS, sizeof(IdT) == 4 ? 3 : 2) k_radix_pass(const uint64_t* __restrict__ kin, const IdT* __restrict__ iin,
                                                            uint64_t* __restrict__ kout, IdT* __restrict__ iout, uint64_t n, uint32_t shift,
                                                            const uint64_t* __restrict__ bin_base, uint64_t* __restrict__ status,
                                                            uint32_t* __restrict__ ticket, uint32_t tag) {
-    __shared__ uint64_t s_buf[RS_TILE];            // the tile's keys, then its ids, in output order
-    __shared__ uint8_t s_digit[RS_TILE];           // digit of every staged slot
-    __shared__ uint32_t s_whist[RS_WARPS][256];    // per-warp digit counts -> exclusive over the warps
-    __shared__ uint32_t s_binstart[256];           // first staged slot of every bin
-    __shared__ uint64_t s_gofs[256];               // output index of staged slot s of bin b = s_gofs[b] + s
-    __shared__ uint32_t s_wsum[RS_WARPS];
-    __shared__ uint32_t s_tile;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PassSmem<IdT>& S = *reinterpret_cast<PassSmem<IdT>*>(smem_raw);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);  // tiles in ticket order: every earlier tile is running or done
-    for (uint32_t b = tid; b < RS_WARPS * 256; b += RS_THREADS) (&s_whist[0][0])[b] = 0;
+    if (tid == 0) S.tile = atomicAdd(ticket, 1u);  // tiles in ticket order: every earlier tile is running or done
+    for (uint32_t b = tid; b < RS_WARPS * 256; b += RS_THREADS) (&S.whist[0][0])[b] = 0;
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = S.tile;
     const uint64_t tile_base = uint64_t(tile) * RS_TILE;
     const uint32_t tile_n = n - tile_base < uint64_t(RS_TILE) ? uint32_t(n - tile_base) : uint32_t(RS_TILE);
     const uint32_t first = warp * RS_WARP_SPAN + lane;  // item j of this thread = tile slot first + 32 j (warp-striped)
@@ -233,22 +263,36 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(const uint64_t* __
         const uint32_t li = first + 32 * j;
         key[j] = li < tile_n ? kin[tile_base + li] : ~uint64_t(0);
     }
-    // rank of every item among the items of its warp with the same digit, in (item, lane) order
-    uint16_t rnk[RS_IPT];
+    // rank of every item among the items of its warp with the same digit, in (item, lane) order.  The running count of a
+    // digit is one shared-memory atomic by the first lane that holds it; the atomics of a warp are performed in program order,
+    // and nothing waits for a result before all sixteen are on their way (the results are picked up in a second loop).
+    uint32_t prevv[RS_IPT];      // leader lanes: the digit's count before this item
+    uint32_t lb[RS_IPT / 2];     // per item: lanes below with the same digit (bits 0-7), the leader lane (bits 8-15)
+    uint32_t* wh = S.whist[warp];
 #pragma unroll
     for (int j = 0; j < RS_IPT; ++j) {
         const bool valid = first + 32 * j < tile_n;
         const uint32_t d = valid ? uint32_t(key[j] >> shift) & 0xffu : 256u + lane;
         const uint32_t m = __match_any_sync(0xffffffffu, d);
         const uint32_t leader = uint32_t(__ffs(int(m)) - 1);
-        uint32_t prev = 0;
-        if (valid && lane == leader) {
-            prev = s_whist[warp][d];
-            s_whist[warp][d] = prev + uint32_t(__popc(m));
-        }
-        prev = __shfl_sync(0xffffffffu, prev, int(leader));
-        rnk[j] = uint16_t(prev + uint32_t(__popc(m & ((1u << lane) - 1u))));
-        __syncwarp();
+        prevv[j] = 0;
+        if (valid && lane == leader) prevv[j] = atomicAdd(wh + d, uint32_t(__popc(m)));
+        const uint32_t x = uint32_t(__popc(m & ((1u << lane) - 1u))) | (leader << 8);
+        lb[j >> 1] = (j & 1) ? (lb[j >> 1] | (x << 16)) : x;
+    }
+    uint32_t rnk[RS_IPT / 2];    // two 16-bit ranks per register
+#pragma unroll
+    for (int j = 0; j < RS_IPT; ++j) {
+        const uint32_t x = (j & 1) ? lb[j >> 1] >> 16 : lb[j >> 1] & 0xffffu;
+        const uint32_t rk = __shfl_sync(0xffffffffu, prevv[j], int(x >> 8)) + (x & 0xffu);
+        rnk[j >> 1] = (j & 1) ? (rnk[j >> 1] | (rk << 16)) : rk;
+    }
+    // the ids travel with the keys: asked for now, needed after the chained scan
+    IdT idv[RS_IPT];
+#pragma unroll
+    for (int j = 0; j < RS_IPT; ++j) {
+        const uint32_t li = first + 32 * j;
+        idv[j] = li < tile_n ? iin[tile_base + li] : IdT(0);
     }
     __syncthreads();
 
@@ -256,8 +300,8 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(const uint64_t* __
     uint32_t cnt = 0;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
-        const uint32_t t = s_whist[w][tid];
-        s_whist[w][tid] = cnt;
+        const uint32_t t = S.whist[w][tid];
+        S.whist[w][tid] = cnt;
         cnt += t;
     }
     uint64_t* st = status + uint64_t(tile) * 256 + tid;
@@ -270,54 +314,56 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(const uint64_t* __
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= uint32_t(o)) incl += t;
     }
-    if (lane == 31) s_wsum[warp] = incl;
+    if (lane == 31) S.wsum[warp] = incl;
     __syncthreads();
     uint32_t wbase = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) wbase += uint32_t(w) < warp ? s_wsum[w] : 0u;
+    for (int w = 0; w < RS_WARPS; ++w) wbase += uint32_t(w) < warp ? S.wsum[w] : 0u;
     const uint32_t binstart = wbase + incl - cnt;
-    s_binstart[tid] = binstart;
+    S.binstart[tid] = binstart;
     // chained scan: pairs of this bin in all earlier tiles
     uint64_t excl = 0;
     if (tile > 0) {
-        for (int64_t t = int64_t(tile) - 1;; --t) {
-            const uint64_t* pw = status + uint64_t(t) * 256 + tid;
-            uint64_t wv;
-            do {
-                wv = ld_status(pw);
-            } while ((wv >> TAG_SHIFT) != tag);
-            excl += wv & CNT_MASK;
-            if (wv & INCL_BIT) break;
+        int64_t t = int64_t(tile) - 1;
+        for (bool open = true; open;) {
+            // four earlier tiles asked for together (one round trip), taken in order
+            uint64_t wv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) wv[q] = t - q >= 0 ? ld_status(status + uint64_t(t - q) * 256 + tid) : 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (open && t - q >= 0) {
+                    uint64_t x = wv[q];
+                    while ((x >> TAG_SHIFT) != tag) x = ld_status(status + uint64_t(t - q) * 256 + tid);
+                    excl += x & CNT_MASK;
+                    if (x & INCL_BIT) open = false;
+                }
+            }
+            t -= 4;
         }
         st_status(st, tagw | INCL_BIT | (excl + cnt));
     }
-    s_gofs[tid] = bin_base[tid] + excl - binstart;
+    S.gofs[tid] = bin_base[tid] + excl - binstart;
     __syncthreads();
 
-    // keys into output order (shared), then out as one coalesced run per bin
+    // pairs into output order (shared), then out as one coalesced run per bin
 #pragma unroll
     for (int j = 0; j < RS_IPT; ++j) {
         if (first + 32 * j < tile_n) {
             const uint32_t d = uint32_t(key[j] >> shift) & 0xffu;
-            const uint32_t slot = s_binstart[d] + s_whist[warp][d] + rnk[j];
-            rnk[j] = uint16_t(slot);
-            s_digit[slot] = uint8_t(d);
-            if (WRITE_KEYS) s_buf[slot] = key[j];
+            const uint32_t rk = (j & 1) ? rnk[j >> 1] >> 16 : rnk[j >> 1] & 0xffffu;
+            const uint32_t slot = S.binstart[d] + S.whist[warp][d] + rk;
+            S.digit[slot] = uint8_t(d);
+            if (WRITE_KEYS) S.keys[slot] = key[j];
+            S.ids[slot] = idv[j];
         }
     }
     __syncthreads();
-    if (WRITE_KEYS) {
-        for (uint32_t i = tid; i < tile_n; i += RS_THREADS) kout[s_gofs[s_digit[i]] + i] = s_buf[i];
-        __syncthreads();
+    for (uint32_t i = tid; i < tile_n; i += RS_THREADS) {
+        const uint64_t g = S.gofs[S.digit[i]] + i;
+        if (WRITE_KEYS) kout[g] = S.keys[i];
+        iout[g] = S.ids[i];
     }
-    IdT* s_ids = reinterpret_cast<IdT*>(s_buf);
-#pragma unroll
-    for (int j = 0; j < RS_IPT; ++j) {
-        const uint32_t li = first + 32 * j;
-        if (li < tile_n) s_ids[rnk[j]] = iin[tile_base + li];
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i < tile_n; i += RS_THREADS) iout[s_gofs[s_digit[i]] + i] = s_ids[i];
 }
 
 template <typename IdT>
@@ -360,8 +406,8 @@ __global__ void k_egsa_finish(ReadsView v, const uint64_t* __restrict__ packed, 
 inline unsigned blocks_for(uint64_t n, int t) { return unsigned((n + uint64_t(t) - 1) / uint64_t(t)); }
 
 template <typename IdT>
-cudaError_t build_typed(ReadsView v, uint64_t n, uint64_t total_bases, uint32_t* d_lcp, uint32_t* d_text, uint32_t* d_suff,
-                        uint8_t* d_bwt, cudaStream_t stream, uint64_t* launches) {
+cudaError_t build_typed(ReadsView v, uint64_t n, uint64_t total_bases, const uint64_t* n_le, uint32_t* d_lcp, uint32_t* d_text,
+                        uint32_t* d_suff, uint8_t* d_bwt, cudaStream_t stream, uint64_t* launches) {
     const uint32_t W = (v.L + 31) / 32;
     const uint64_t tiles = (n + RS_TILE - 1) / RS_TILE;
     const uint32_t len_places = v.shift ? (v.L >= 256 ? 2u : 1u) : 0u;
@@ -405,9 +451,14 @@ cudaError_t build_typed(ReadsView v, uint64_t n, uint64_t total_bases, uint32_t*
         if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return done(e);
         if (h_bad) return done(cudaErrorInvalidValue);
     }
-    if (v.shift) k_init_ids_ragged<IdT><<<blocks_for(v.R * 32, 256), 256, 0, stream>>>(v, i0);
-    else k_init_ids_equal<IdT><<<blocks_for(n, 256), 256, 0, stream>>>(i0, n);
-    *launches += 1;
+    if (v.shift) {
+        k_init_ids_ragged<IdT><<<blocks_for(v.R * 32, 256), 256, 0, stream>>>(v, i0);
+        *launches += 1;
+    } else {  // both buffers: a word's passes leave the suffixes that are too short for it where they are, in either buffer
+        k_init_ids_equal<IdT><<<blocks_for(n, 256), 256, 0, stream>>>(i0, n);
+        k_init_ids_equal<IdT><<<blocks_for(n, 256), 256, 0, stream>>>(i1, n);
+        *launches += 2;
+    }
 
     uint64_t *kc = k0, *ka = k1;  // current / alternate
     IdT *ic = i0, *ia = i1;
@@ -415,26 +466,50 @@ cudaError_t build_typed(ReadsView v, uint64_t n, uint64_t total_bases, uint32_t*
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint64_t hist_blocks_want = (n + 255) / 256;
-    const unsigned hist_blocks = unsigned(hist_blocks_want < uint64_t(sms) * 8 ? hist_blocks_want : uint64_t(sms) * 8);
+    const int smem_bytes = int(sizeof(PassSmem<IdT>));
+    if ((e = cudaFuncSetAttribute(k_radix_pass<IdT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)) != cudaSuccess) return done(e);
+    if ((e = cudaFuncSetAttribute(k_radix_pass<IdT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)) != cudaSuccess) return done(e);
+    // Sorts the current order on `places` digit places of key word w (w_base = 32 w symbols before it; LEN_WORD: the length
+    // key, everything moves).  n_le[t] = suffixes of t symbols or fewer.  A suffix that ends before the symbols of a place has
+    // digit 0 there and is still where the shortest-first order put it (a prefix of the current order, identical in both
+    // buffers): place j moves only the suffixes longer than that, [first_j, n).
     auto sort_word = [&](uint32_t w, uint32_t begin_bit, uint32_t places) {
-        k_keys_hist<IdT><<<hist_blocks, 256, 0, stream>>>(v, packed, ic, n, w, begin_bit, places, kc, hist);
-        k_scan_hist<<<1, 256, 0, stream>>>(hist, bin_base);
+        uint64_t first_of[MAX_PLACES];
+        for (uint32_t j = 0; j < places; ++j) {
+            if (w == LEN_WORD) { first_of[j] = 0; continue; }
+            const int s_lo = 28 - int(begin_bit / 2) - 4 * int(j);  // first symbol of the word that place j holds
+            const uint64_t t = uint64_t(32) * w + uint64_t(s_lo > 0 ? s_lo : 0);
+            first_of[j] = n_le[t < v.L ? t : v.L];
+        }
+        const uint64_t first = first_of[places - 1];  // the widest range: what the word's keys are made for
+        const uint64_t m = n - first;
+        PlaceSkip skip;
+        for (uint32_t j = 0; j < MAX_PLACES; ++j) skip.n[j] = j < places ? first_of[j] - first : 0;
+        const uint64_t hist_blocks_want = (m + 255) / 256;
+        const unsigned hist_blocks = unsigned(hist_blocks_want < uint64_t(sms) * 8 ? hist_blocks_want : uint64_t(sms) * 8);
+        k_keys_hist<IdT><<<hist_blocks, 256, 0, stream>>>(v, packed, ic + first, m, w, begin_bit, places, kc + first, ka + first,
+                                                          first_of[0] - first, hist);
+        k_scan_hist<<<1, 256, 0, stream>>>(hist, bin_base, skip);
         *launches += 2;
         for (uint32_t j = 0; j < places; ++j, ++seq) {
             const uint32_t sh = begin_bit + 8 * j;
+            const uint64_t f = first_of[j], mj = n - f;
+            const unsigned tiles_j = unsigned((mj + RS_TILE - 1) / RS_TILE);
             if (j + 1 < places)
-                k_radix_pass<IdT, true><<<unsigned(tiles), RS_THREADS, 0, stream>>>(kc, ic, ka, ia, n, sh, bin_base + 256 * j, status,
-                                                                                    tickets + seq, seq + 1);
+                k_radix_pass<IdT, true><<<tiles_j, RS_THREADS, smem_bytes, stream>>>(kc + f, ic + f, ka + f, ia + f, mj, sh, bin_base + 256 * j,
+                                                                                     status, tickets + seq, seq + 1);
             else  // the keys of this word are not looked at again
-                k_radix_pass<IdT, false><<<unsigned(tiles), RS_THREADS, 0, stream>>>(kc, ic, ka, ia, n, sh, bin_base + 256 * j, status,
-                                                                                     tickets + seq, seq + 1);
+                k_radix_pass<IdT, false><<<tiles_j, RS_THREADS, smem_bytes, stream>>>(kc + f, ic + f, ka + f, ia + f, mj, sh, bin_base + 256 * j,
+                                                                                      status, tickets + seq, seq + 1);
             *launches += 1;
             uint64_t* tk = kc; kc = ka; ka = tk;
             IdT* ti = ic; ic = ia; ia = ti;
         }
     };
-    if (len_places) sort_word(LEN_WORD, 0, len_places);
+    if (len_places) {  // ragged: shortest first, then both buffers hold that order
+        sort_word(LEN_WORD, 0, len_places);
+        if ((e = cudaMemcpyAsync(ia, ic, n * sizeof(IdT), cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return done(e);
+    }
     for (int w = int(W) - 1; w >= 0; --w) {
         // symbols of this word that exist in the longest suffix: only those bits can differ
         const uint32_t syms = v.L - 32 * uint32_t(w) < 32 ? v.L - 32 * uint32_t(w) : 32;
@@ -449,10 +524,11 @@ cudaError_t build_typed(ReadsView v, uint64_t n, uint64_t total_bases, uint32_t*
 
 }  // namespace
 
-// d_off == nullptr: R reads of L bases each; else R + 1 DEVICE offsets, L = the longest read, total_bases = off[R].
+// d_off == nullptr: R reads of L bases each; else R + 1 DEVICE offsets (h_off = the same on the host), L = the longest read,
+// total_bases = off[R].
 // scratch (freed before returning): two key buffers + two id buffers + tile status = 24.5 (32-bit ids) / 32.5 bytes per suffix
-cudaError_t build_egsa(const uint8_t* d_reads, const uint64_t* d_off, uint64_t R, uint32_t L, uint64_t total_bases, uint32_t* d_lcp,
-                       uint32_t* d_text, uint32_t* d_suff, uint8_t* d_bwt, cudaStream_t stream, uint64_t* launches) {
+cudaError_t build_egsa(const uint8_t* d_reads, const uint64_t* d_off, const uint64_t* h_off, uint64_t R, uint32_t L, uint64_t total_bases,
+                       uint32_t* d_lcp, uint32_t* d_text, uint32_t* d_suff, uint8_t* d_bwt, cudaStream_t stream, uint64_t* launches) {
     ReadsView v;
     v.bases = d_reads;
     v.off = d_off;
@@ -460,19 +536,26 @@ cudaError_t build_egsa(const uint8_t* d_reads, const uint64_t* d_off, uint64_t R
     v.L = L;
     v.shift = 0;
     const uint64_t n = total_bases + R;
+    std::vector<uint64_t> n_le(size_t(L) + 1, 0);  // n_le[t] = suffixes of t symbols or fewer
     bool wide;
     if (d_off) {
-        if (L >= 65536) return cudaErrorInvalidConfiguration;
+        if (L >= 65536 || !h_off) return cudaErrorInvalidConfiguration;
         uint32_t bits = 1;
         while ((L >> bits) != 0) ++bits;  // p in [0, L]
         v.shift = bits;
         wide = R > (uint64_t(1) << (32 - bits));
+        std::vector<uint64_t> at_least(size_t(L) + 2, 0);  // reads of t bases or more
+        for (uint64_t r = 0; r < R; ++r) ++at_least[size_t(h_off[r + 1] - h_off[r])];
+        for (uint32_t t = L; t-- > 0;) at_least[t] += at_least[t + 1];
+        n_le[0] = R;
+        for (uint32_t t = 1; t <= L; ++t) n_le[t] = n_le[t - 1] + at_least[t];
     } else {
         wide = n > 0xffffffffull;
+        for (uint32_t t = 0; t <= L; ++t) n_le[t] = R * (uint64_t(t) + 1);
     }
     if (getenv("E2S_BUILD_IDS64")) wide = true;  // test hook: the 64-bit instantiation on small inputs
-    return wide ? build_typed<uint64_t>(v, n, total_bases, d_lcp, d_text, d_suff, d_bwt, stream, launches)
-                : build_typed<uint32_t>(v, n, total_bases, d_lcp, d_text, d_suff, d_bwt, stream, launches);
+    return wide ? build_typed<uint64_t>(v, n, total_bases, n_le.data(), d_lcp, d_text, d_suff, d_bwt, stream, launches)
+                : build_typed<uint32_t>(v, n, total_bases, n_le.data(), d_lcp, d_text, d_suff, d_bwt, stream, launches);
 }
 
 }  // namespace e2s

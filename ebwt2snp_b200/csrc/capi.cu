@@ -887,7 +887,7 @@ static int build_egsa_common(e2s_ctx* c, const char* who, const uint8_t* d_reads
             return cuda_fail(c, eo, "H2D read offsets");
         }
     }
-    cudaError_t e = build_egsa(d_reads, d_off, n_reads, longest, total, d_lcp, d_text, d_suff, d_bwt, c->stream, &c->launches);
+    cudaError_t e = build_egsa(d_reads, d_off, off, n_reads, longest, total, d_lcp, d_text, d_suff, d_bwt, c->stream, &c->launches);
     if (d_off) {
         cudaStreamSynchronize(c->stream);
         cudaFree(d_off);

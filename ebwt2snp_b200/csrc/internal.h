@@ -219,10 +219,10 @@ cudaError_t launch_fill_phantom(uint32_t* lcp, uint32_t* text, uint32_t* suff, u
 
 // ---- EGSA construction (build_egsa.cu) -----------------------------------------------------------
 // suffix sort of R reads (device pointer, no separators) -> lcp/text/suff/bwt device arrays of total_bases + R elements; synchronises.
-// d_off == nullptr: every read has L bases; else R + 1 DEVICE offsets and L = the longest read (< 65536).
+// d_off == nullptr: every read has L bases; else R + 1 DEVICE offsets (h_off: the same in host memory) and L = the longest read (< 65536).
 // cudaErrorInvalidValue = a base outside ACGT / acgt; cudaErrorInvalidConfiguration = a read of 65536 bases or more.
-cudaError_t build_egsa(const uint8_t* d_reads, const uint64_t* d_off, uint64_t R, uint32_t L, uint64_t total_bases, uint32_t* d_lcp,
-                       uint32_t* d_text, uint32_t* d_suff, uint8_t* d_bwt, cudaStream_t stream, uint64_t* launches);
+cudaError_t build_egsa(const uint8_t* d_reads, const uint64_t* d_off, const uint64_t* h_off, uint64_t R, uint32_t L, uint64_t total_bases,
+                       uint32_t* d_lcp, uint32_t* d_text, uint32_t* d_suff, uint8_t* d_bwt, cudaStream_t stream, uint64_t* launches);
 
 // ---- phase 2 -----------------------------------------------------------------------------------
 struct SnpDev {  // device counters of one e2s_find_events

@@ -83,7 +83,7 @@ int main(int argc, char** argv) {
     for (int it = 0; it < reps + 1; ++it) {
         for (int v = 0; v < 2; ++v) {
             cudaEventRecord(a, s);
-            cudaError_t e = v == 0 ? e2s::build_egsa(d_reads, nullptr, R, L, R * L, d_lcp[0], d_text[0], d_suff[0], d_bwt[0], s, &launches)
+            cudaError_t e = v == 0 ? e2s::build_egsa(d_reads, nullptr, nullptr, R, L, R * L, d_lcp[0], d_text[0], d_suff[0], d_bwt[0], s, &launches)
                                    : e2s::build_with_cub(d_reads, R, L, d_lcp[1], d_text[1], d_suff[1], d_bwt[1], s);
             cudaEventRecord(b, s);
             cudaEventSynchronize(b);
