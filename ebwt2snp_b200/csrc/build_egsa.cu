@@ -359,48 +359,72 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(IdT) == 4 ? 3 : 2) k_radix_
         }
     }
     __syncthreads();
-    for (uint32_t i = tid; i < tile_n; i += RS_THREADS) {
-        const uint64_t g = S.gofs[S.digit[i]] + i;
-        if (WRITE_KEYS) kout[g] = S.keys[i];
-        iout[g] = S.ids[i];
+    if (tile_n == uint32_t(RS_TILE)) {
+#pragma unroll
+        for (int j = 0; j < RS_IPT; ++j) {
+            const uint32_t i = tid + uint32_t(j) * RS_THREADS;
+            const uint64_t g = S.gofs[S.digit[i]] + i;
+            if (WRITE_KEYS) kout[g] = S.keys[i];
+            iout[g] = S.ids[i];
+        }
+    } else {
+        for (uint32_t i = tid; i < tile_n; i += RS_THREADS) {
+            const uint64_t g = S.gofs[S.digit[i]] + i;
+            if (WRITE_KEYS) kout[g] = S.keys[i];
+            iout[g] = S.ids[i];
+        }
     }
 }
 
+// one thread per record; the previous record's key words come from the lane below (lane 0 fetches them itself)
 template <typename IdT>
 __global__ void k_egsa_finish(ReadsView v, const uint64_t* __restrict__ packed, const IdT* __restrict__ ids, uint64_t n,
                               uint32_t* __restrict__ lcp, uint32_t* __restrict__ text, uint32_t* __restrict__ suff,
                               uint8_t* __restrict__ bwt) {
-    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t r;
-    uint32_t p;
-    v.decode(ids[i], r, p);
-    const uint64_t st = v.start(r);
-    const uint32_t len = v.len(r);
-    text[i] = uint32_t(r);
-    suff[i] = p;
-    bwt[i] = p ? v.bases[st + p - 1] : uint8_t('$');
-    uint32_t l = 0;
-    if (i) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;  // blockDim.x is a multiple of 32: whole warps leave together
+    const uint32_t lane = threadIdx.x & 31;
+    const bool valid = i < n;
+    uint64_t r = 0, st = 0;
+    uint32_t p = 0, len = 0;
+    if (valid) {
+        v.decode(ids[i], r, p);
+        st = v.start(r);
+        len = v.len(r);
+        text[i] = uint32_t(r);
+        suff[i] = p;
+        bwt[i] = p ? v.bases[st + p - 1] : uint8_t('$');
+    }
+    const uint64_t* row = packed + v.row(r, st);
+    const uint32_t la = len - p;
+    // the record before: the lane below's, or fetched (first lane of a warp)
+    uint32_t lb = __shfl_up_sync(0xffffffffu, la, 1);
+    const uint64_t* row0 = row;
+    uint32_t p0 = 0, len0 = 0;
+    const bool fetch = lane == 0 && valid && i > 0;
+    if (fetch) {
         uint64_t r0;
-        uint32_t p0;
         v.decode(ids[i - 1], r0, p0);
         const uint64_t st0 = v.start(r0);
-        const uint32_t len0 = v.len(r0);
-        const uint32_t la = len - p, lb = len0 - p0;
-        l = la < lb ? la : lb;  // the shorter of the two suffixes
-        const uint64_t* row = packed + v.row(r, st);
-        const uint64_t* row0 = packed + v.row(r0, st0);
-        for (uint32_t w = 0; 32 * w < l; ++w) {
-            const uint64_t x = suffix_word(row0, len0, p0, w) ^ suffix_word(row, len, p, w);
+        len0 = v.len(r0);
+        row0 = packed + v.row(r0, st0);
+        lb = len0 - p0;
+    }
+    uint32_t l = (valid && i > 0) ? (la < lb ? la : lb) : 0;  // the shorter of the two suffixes
+    bool open = l > 0;
+    for (uint32_t w = 0; __any_sync(0xffffffffu, open && 32 * w < l); ++w) {
+        const uint64_t mine = valid ? suffix_word(row, len, p, w) : 0;
+        uint64_t prev = __shfl_up_sync(0xffffffffu, mine, 1);
+        if (fetch) prev = suffix_word(row0, len0, p0, w);
+        if (open && 32 * w < l) {
+            const uint64_t x = prev ^ mine;
             if (x) {
                 const uint32_t d = 32 * w + uint32_t(__clzll(static_cast<long long>(x))) / 2;
                 l = d < l ? d : l;
-                break;
+                open = false;
             }
         }
     }
-    lcp[i] = l;
+    if (valid) lcp[i] = l;
 }
 
 inline unsigned blocks_for(uint64_t n, int t) { return unsigned((n + uint64_t(t) - 1) / uint64_t(t)); }
