@@ -380,7 +380,9 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(IdT) == 4 ? 3 : 2) k_radix_
 template <typename IdT>
 __global__ void k_egsa_finish(ReadsView v, const uint64_t* __restrict__ packed, const IdT* __restrict__ ids, uint64_t n,
                               uint32_t* __restrict__ lcp, uint32_t* __restrict__ text, uint32_t* __restrict__ suff,
-                              uint8_t* __restrict__ bwt) {
+                              uint8_t* __restrict__ bwt, uint64_t before) {
+    // before: the record that precedes record 0 in the whole index, text << 32 | suff (a key range that does not start the
+    // index); ~0 = none, lcp[0] = 0
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;  // blockDim.x is a multiple of 32: whole warps leave together
     const uint32_t lane = threadIdx.x & 31;
     const bool valid = i < n;
@@ -400,16 +402,22 @@ __global__ void k_egsa_finish(ReadsView v, const uint64_t* __restrict__ packed, 
     uint32_t lb = __shfl_up_sync(0xffffffffu, la, 1);
     const uint64_t* row0 = row;
     uint32_t p0 = 0, len0 = 0;
-    const bool fetch = lane == 0 && valid && i > 0;
+    const bool has_prev = valid && (i > 0 || before != ~uint64_t(0));
+    const bool fetch = lane == 0 && has_prev;
     if (fetch) {
         uint64_t r0;
-        v.decode(ids[i - 1], r0, p0);
+        if (i > 0) {
+            v.decode(ids[i - 1], r0, p0);
+        } else {
+            r0 = before >> 32;
+            p0 = uint32_t(before);
+        }
         const uint64_t st0 = v.start(r0);
         len0 = v.len(r0);
         row0 = packed + v.row(r0, st0);
         lb = len0 - p0;
     }
-    uint32_t l = (valid && i > 0) ? (la < lb ? la : lb) : 0;  // the shorter of the two suffixes
+    uint32_t l = has_prev ? (la < lb ? la : lb) : 0;  // the shorter of the two suffixes
     bool open = l > 0;
     for (uint32_t w = 0; __any_sync(0xffffffffu, open && 32 * w < l); ++w) {
         const uint64_t mine = valid ? suffix_word(row, len, p, w) : 0;
@@ -427,13 +435,132 @@ __global__ void k_egsa_finish(ReadsView v, const uint64_t* __restrict__ packed, 
     if (valid) lcp[i] = l;
 }
 
+// ---- one key range of the index (equal-length reads: the suffix ids are the iota, the length of suffix id i is i / R) ----------
+// The suffixes whose first key word (32 symbols, zero padded) lies in [lo, hi) are a contiguous range of the index: a GPU that
+// cannot hold the scratch of the whole collection, or one GPU of several, sorts only those.  Two sweeps over all suffix ids: count
+// per chunk of 4096 ids (+ how many lie below the range, + the selected per length), then a stable compaction into both id buffers.
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_IPT = 16;
+constexpr int SEL_CHUNK = SEL_THREADS * SEL_IPT;
+
+struct SelStats {
+    unsigned long long n_below;   // suffixes whose first key word is below lo = index position of the range's first record
+    unsigned long long n_sel;
+};
+
+template <typename IdT, bool WRITE>
+__global__ void __launch_bounds__(SEL_THREADS) k_range_select(ReadsView v, const uint64_t* __restrict__ packed, uint64_t n, uint64_t lo, uint64_t hi,
+                                                              uint64_t* __restrict__ chunk_cnt, unsigned long long* __restrict__ len_hist,
+                                                              SelStats* __restrict__ stats, IdT* __restrict__ out0, IdT* __restrict__ out1) {
+    __shared__ uint32_t s_w[SEL_THREADS / 32];
+    __shared__ uint32_t s_below, s_first_len_cnt;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t base = uint64_t(blockIdx.x) * SEL_CHUNK + uint64_t(tid) * SEL_IPT;
+    const uint64_t first_len = uint64_t(blockIdx.x) * SEL_CHUNK / v.R;  // the length of the chunk's first suffix
+    if (tid == 0) { s_below = 0; s_first_len_cnt = 0; }
+    __syncthreads();
+    uint32_t sel = 0, below = 0, at_first_len = 0;
+#pragma unroll 4
+    for (int j = 0; j < SEL_IPT; ++j) {
+        const uint64_t i = base + j;
+        if (i < n) {
+            uint64_t r;
+            uint32_t p;
+            v.decode(IdT(i), r, p);
+            const uint64_t key = suffix_word(packed + v.row(r, v.start(r)), v.L, p, 0);
+            if (key < lo) ++below;
+            else if (hi == 0 || key < hi) {
+                sel |= 1u << j;
+                if (!WRITE) {
+                    const uint64_t len = uint64_t(v.L - p);
+                    if (len == first_len) ++at_first_len;
+                    else atomicAdd(len_hist + len, 1ull);  // (a chunk seldom spans two lengths)
+                }
+            }
+        }
+    }
+    const uint32_t cnt = uint32_t(__popc(sel));
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= uint32_t(o)) inc += t;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    if (!WRITE) {
+        const uint32_t wb = __reduce_add_sync(0xffffffffu, below), wf = __reduce_add_sync(0xffffffffu, at_first_len);
+        if (lane == 0 && wb) atomicAdd(&s_below, wb);
+        if (lane == 0 && wf) atomicAdd(&s_first_len_cnt, wf);
+    }
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < SEL_THREADS / 32; ++w) {
+        wbase += uint32_t(w) < warp ? s_w[w] : 0u;
+        total += s_w[w];
+    }
+    if (!WRITE) {
+        if (tid == 0) {
+            chunk_cnt[blockIdx.x] = total;
+            if (s_below) atomicAdd(&stats->n_below, (unsigned long long)s_below);
+            if (total) atomicAdd(&stats->n_sel, (unsigned long long)total);
+            if (s_first_len_cnt) atomicAdd(len_hist + first_len, (unsigned long long)s_first_len_cnt);
+        }
+    } else {
+        uint64_t at = chunk_cnt[blockIdx.x] + wbase + inc - cnt;
+#pragma unroll 4
+        for (int j = 0; j < SEL_IPT; ++j)
+            if (sel & (1u << j)) {
+                out0[at] = IdT(base + j);
+                out1[at] = IdT(base + j);
+                ++at;
+            }
+    }
+}
+
+// in-place exclusive scan of cnt[0 .. nb) by one CTA
+__global__ void __launch_bounds__(1024) k_scan_chunks(uint64_t* __restrict__ cnt, uint64_t nb) {
+    __shared__ uint64_t s_part[1024];
+    const uint64_t per = (nb + 1023) / 1024;
+    const uint64_t a = uint64_t(threadIdx.x) * per, b = a + per < nb ? a + per : nb;
+    uint64_t sum = 0;
+    for (uint64_t i = a; i < b; ++i) sum += cnt[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (int t = 0; t < 1024; ++t) {
+            const uint64_t x = s_part[t];
+            s_part[t] = run;
+            run += x;
+        }
+    }
+    __syncthreads();
+    uint64_t run = s_part[threadIdx.x];
+    for (uint64_t i = a; i < b; ++i) {
+        const uint64_t x = cnt[i];
+        cnt[i] = run;
+        run += x;
+    }
+}
+
+struct KeyRange {              // host side: one key range of the index
+    uint64_t lo, hi;           // first key word in [lo, hi); hi == 0: no upper bound
+    uint64_t cap;              // records the output arrays hold
+    uint64_t before;           // the record before the range, text << 32 | suff; ~0 = none / not known
+    uint64_t n_out, first_out; // results: records written, index position of the first one
+};
+
 inline unsigned blocks_for(uint64_t n, int t) { return unsigned((n + uint64_t(t) - 1) / uint64_t(t)); }
 
 template <typename IdT>
-cudaError_t build_typed(ReadsView v, uint64_t n, uint64_t total_bases, const uint64_t* n_le, uint32_t* d_lcp, uint32_t* d_text,
-                        uint32_t* d_suff, uint8_t* d_bwt, cudaStream_t stream, uint64_t* launches) {
+cudaError_t build_typed(ReadsView v, uint64_t n_all, uint64_t total_bases, const uint64_t* n_le_all, KeyRange* range, uint32_t* d_lcp,
+                        uint32_t* d_text, uint32_t* d_suff, uint8_t* d_bwt, cudaStream_t stream, uint64_t* launches) {
     const uint32_t W = (v.L + 31) / 32;
-    const uint64_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    uint64_t n = n_all;                // suffixes this call sorts (a key range: known after the first sweep)
+    const uint64_t* n_le = n_le_all;
+    std::vector<uint64_t> n_le_sel;
+    uint64_t tiles = (n + RS_TILE - 1) / RS_TILE;
     const uint32_t len_places = v.shift ? (v.L >= 256 ? 2u : 1u) : 0u;
     uint32_t passes = len_places;
     for (uint32_t w = 0; w < W; ++w) {
@@ -442,27 +569,22 @@ cudaError_t build_typed(ReadsView v, uint64_t n, uint64_t total_bases, const uin
     }
     if (passes >= (1u << (64 - TAG_SHIFT)) - 1u || tiles >= (uint64_t(1) << 31)) return cudaErrorInvalidConfiguration;
     const uint64_t packed_words = (total_bases >> 5) + 2 * v.R + 2;
-    uint64_t *packed = nullptr, *k0 = nullptr, *k1 = nullptr, *status = nullptr, *misc = nullptr;
+    uint64_t *packed = nullptr, *k0 = nullptr, *k1 = nullptr, *status = nullptr, *misc = nullptr, *chunk_cnt = nullptr, *sel_misc = nullptr;
     IdT *i0 = nullptr, *i1 = nullptr;
     uint32_t* tickets = nullptr;
     cudaError_t e = cudaSuccess;
     auto done = [&](cudaError_t rc) {
         cudaFree(packed); cudaFree(k0); cudaFree(k1); cudaFree(i0); cudaFree(i1); cudaFree(status); cudaFree(misc); cudaFree(tickets);
+        cudaFree(chunk_cnt); cudaFree(sel_misc);
         return rc;
     };
     // misc: hist[8][256] | bin_base[8][256] | bad flag
     const size_t misc_bytes = size_t(2 * MAX_PLACES * 256 + 1) * 8;
     if ((e = cudaMalloc(reinterpret_cast<void**>(&misc), misc_bytes)) != cudaSuccess) return done(e);
     if ((e = cudaMalloc(reinterpret_cast<void**>(&tickets), size_t(passes + 1) * 4)) != cudaSuccess) return done(e);
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&status), tiles * 256 * 8)) != cudaSuccess) return done(e);
     if ((e = cudaMalloc(reinterpret_cast<void**>(&packed), packed_words * 8)) != cudaSuccess) return done(e);
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&k0), n * 8)) != cudaSuccess) return done(e);
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&k1), n * 8)) != cudaSuccess) return done(e);
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&i0), n * sizeof(IdT))) != cudaSuccess) return done(e);
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&i1), n * sizeof(IdT))) != cudaSuccess) return done(e);
     if ((e = cudaMemsetAsync(misc, 0, misc_bytes, stream)) != cudaSuccess) return done(e);
     if ((e = cudaMemsetAsync(tickets, 0, size_t(passes + 1) * 4, stream)) != cudaSuccess) return done(e);
-    if ((e = cudaMemsetAsync(status, 0, tiles * 256 * 8, stream)) != cudaSuccess) return done(e);  // tag 0 = no pass
     unsigned long long* hist = reinterpret_cast<unsigned long long*>(misc);
     uint64_t* bin_base = misc + MAX_PLACES * 256;
     uint32_t* d_bad = reinterpret_cast<uint32_t*>(misc + 2 * MAX_PLACES * 256);
@@ -475,7 +597,42 @@ cudaError_t build_typed(ReadsView v, uint64_t n, uint64_t total_bases, const uin
         if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return done(e);
         if (h_bad) return done(cudaErrorInvalidValue);
     }
-    if (v.shift) {
+    const uint64_t n_chunks = (n_all + SEL_CHUNK - 1) / SEL_CHUNK;
+    if (range) {  // first sweep: who is in the range
+        if (v.shift || n_chunks >= (uint64_t(1) << 31)) return done(cudaErrorInvalidConfiguration);
+        const size_t sel_bytes = (size_t(v.L) + 1) * 8 + sizeof(SelStats);
+        if ((e = cudaMalloc(reinterpret_cast<void**>(&chunk_cnt), n_chunks * 8)) != cudaSuccess) return done(e);
+        if ((e = cudaMalloc(reinterpret_cast<void**>(&sel_misc), sel_bytes)) != cudaSuccess) return done(e);
+        if ((e = cudaMemsetAsync(sel_misc, 0, sel_bytes, stream)) != cudaSuccess) return done(e);
+        unsigned long long* len_hist = reinterpret_cast<unsigned long long*>(sel_misc);
+        SelStats* stats = reinterpret_cast<SelStats*>(sel_misc + v.L + 1);
+        k_range_select<IdT, false><<<unsigned(n_chunks), SEL_THREADS, 0, stream>>>(v, packed, n_all, range->lo, range->hi, chunk_cnt, len_hist, stats,
+                                                                                   nullptr, nullptr);
+        k_scan_chunks<<<1, 1024, 0, stream>>>(chunk_cnt, n_chunks);
+        *launches += 2;
+        std::vector<uint64_t> h(size_t(v.L) + 1 + sizeof(SelStats) / 8);
+        if ((e = cudaMemcpyAsync(h.data(), sel_misc, sel_bytes, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return done(e);
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return done(e);
+        range->first_out = h[size_t(v.L) + 1];
+        n = h[size_t(v.L) + 2];
+        range->n_out = n;
+        if (n > range->cap) return done(cudaErrorInvalidPitchValue);  // (the caller's arrays are too small: n_out says by how much)
+        if (n == 0) return done(cudaSuccess);
+        n_le_sel.assign(size_t(v.L) + 1, 0);
+        for (uint32_t t = 0; t <= v.L; ++t) n_le_sel[t] = (t ? n_le_sel[t - 1] : 0) + h[t];
+        n_le = n_le_sel.data();
+        tiles = (n + RS_TILE - 1) / RS_TILE;
+    }
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&status), tiles * 256 * 8)) != cudaSuccess) return done(e);
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&k0), n * 8)) != cudaSuccess) return done(e);
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&k1), n * 8)) != cudaSuccess) return done(e);
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&i0), n * sizeof(IdT))) != cudaSuccess) return done(e);
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&i1), n * sizeof(IdT))) != cudaSuccess) return done(e);
+    if ((e = cudaMemsetAsync(status, 0, tiles * 256 * 8, stream)) != cudaSuccess) return done(e);  // tag 0 = no pass
+    if (range) {  // second sweep: the selected ids, in id order (= shortest first, then read id), into both buffers
+        k_range_select<IdT, true><<<unsigned(n_chunks), SEL_THREADS, 0, stream>>>(v, packed, n_all, range->lo, range->hi, chunk_cnt, nullptr, nullptr, i0, i1);
+        *launches += 1;
+    } else if (v.shift) {
         k_init_ids_ragged<IdT><<<blocks_for(v.R * 32, 256), 256, 0, stream>>>(v, i0);
         *launches += 1;
     } else {  // both buffers: a word's passes leave the suffixes that are too short for it where they are, in either buffer
@@ -539,7 +696,7 @@ cudaError_t build_typed(ReadsView v, uint64_t n, uint64_t total_bases, const uin
         const uint32_t syms = v.L - 32 * uint32_t(w) < 32 ? v.L - 32 * uint32_t(w) : 32;
         sort_word(uint32_t(w), 64 - 2 * syms, (2 * syms + 7) / 8);
     }
-    k_egsa_finish<IdT><<<blocks_for(n, 256), 256, 0, stream>>>(v, packed, ic, n, d_lcp, d_text, d_suff, d_bwt);
+    k_egsa_finish<IdT><<<blocks_for(n, 256), 256, 0, stream>>>(v, packed, ic, n, d_lcp, d_text, d_suff, d_bwt, range ? range->before : ~uint64_t(0));
     *launches += 1;
     if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return done(e);
@@ -578,8 +735,34 @@ cudaError_t build_egsa(const uint8_t* d_reads, const uint64_t* d_off, const uint
         for (uint32_t t = 0; t <= L; ++t) n_le[t] = R * (uint64_t(t) + 1);
     }
     if (getenv("E2S_BUILD_IDS64")) wide = true;  // test hook: the 64-bit instantiation on small inputs
-    return wide ? build_typed<uint64_t>(v, n, total_bases, n_le.data(), d_lcp, d_text, d_suff, d_bwt, stream, launches)
-                : build_typed<uint32_t>(v, n, total_bases, n_le.data(), d_lcp, d_text, d_suff, d_bwt, stream, launches);
+    return wide ? build_typed<uint64_t>(v, n, total_bases, n_le.data(), nullptr, d_lcp, d_text, d_suff, d_bwt, stream, launches)
+                : build_typed<uint32_t>(v, n, total_bases, n_le.data(), nullptr, d_lcp, d_text, d_suff, d_bwt, stream, launches);
+}
+
+// One key range of the index of R reads of L bases each: the records of the suffixes whose first key word (32 symbols at 2 bits,
+// A=0 C=1 G=2 T=3, most significant first, zero padded) lies in [key_lo, key_hi) (key_hi == 0: no upper bound) -- a contiguous range
+// of the index, *first_out = the index position of its first record, *n_out = how many there are (also set when they exceed
+// `cap`: cudaErrorInvalidPitchValue, nothing written).  before = the record that precedes the range (text << 32 | suff) for
+// lcp[0], ~0 = none / not known (lcp[0] = 0).  Scratch: 24.5 / 32.5 bytes per suffix OF THE RANGE + 8 bytes per 4096 suffixes.
+cudaError_t build_egsa_range(const uint8_t* d_reads, uint64_t R, uint32_t L, uint64_t key_lo, uint64_t key_hi, uint64_t before, uint64_t cap,
+                             uint32_t* d_lcp, uint32_t* d_text, uint32_t* d_suff, uint8_t* d_bwt, uint64_t* n_out, uint64_t* first_out,
+                             cudaStream_t stream, uint64_t* launches) {
+    ReadsView v;
+    v.bases = d_reads;
+    v.off = nullptr;
+    v.R = R;
+    v.L = L;
+    v.shift = 0;
+    const uint64_t n = R * (uint64_t(L) + 1);
+    std::vector<uint64_t> n_le(size_t(L) + 1, 0);
+    for (uint32_t t = 0; t <= L; ++t) n_le[t] = R * (uint64_t(t) + 1);
+    KeyRange range{key_lo, key_hi, cap, before, 0, 0};
+    const bool wide = n > 0xffffffffull || getenv("E2S_BUILD_IDS64");
+    const cudaError_t e = wide ? build_typed<uint64_t>(v, n, R * uint64_t(L), n_le.data(), &range, d_lcp, d_text, d_suff, d_bwt, stream, launches)
+                               : build_typed<uint32_t>(v, n, R * uint64_t(L), n_le.data(), &range, d_lcp, d_text, d_suff, d_bwt, stream, launches);
+    *n_out = range.n_out;
+    *first_out = range.first_out;
+    return e;
 }
 
 }  // namespace e2s

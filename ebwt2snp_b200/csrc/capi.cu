@@ -926,6 +926,40 @@ int e2s_build_egsa_ragged_dev(e2s_ctx* c, const uint8_t* d_bases, const uint64_t
     return build_egsa_common(c, "e2s_build_egsa_ragged_dev", d_bases, off, n_reads, 0, d_lcp, d_text, d_suff, d_bwt);
 }
 
+int e2s_build_egsa_range_dev(e2s_ctx* c, const uint8_t* d_reads, uint64_t n_reads, uint32_t read_len, uint64_t key_lo, uint64_t key_hi,
+                             uint32_t before_text, uint32_t before_suff, uint64_t capacity, uint32_t* d_lcp, uint32_t* d_text, uint32_t* d_suff,
+                             uint8_t* d_bwt, uint64_t* n_records, uint64_t* first_position) {
+    if (!c || !d_reads || !d_lcp || !d_text || !d_suff || !d_bwt || !n_records || !first_position)
+        return fail(c, E2S_ERR_ARG, "e2s_build_egsa_range_dev: NULL argument");
+    if (n_reads == 0 || read_len == 0) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_range_dev: empty read collection");
+    if (n_reads > 0xffffffffull) return fail(c, E2S_ERR_UNSUPPORTED, "e2s_build_egsa_range_dev: more than 2^32 - 1 reads (text is a 32-bit field)");
+    if (key_hi != 0 && key_hi <= key_lo) return fail(c, E2S_ERR_ARG, "e2s_build_egsa_range_dev: empty key range");
+    CU(c, cudaSetDevice(c->device));
+    const uint64_t before = before_text == 0xffffffffu ? ~uint64_t(0) : (uint64_t(before_text) << 32) | before_suff;
+    *n_records = 0;
+    *first_position = 0;
+    cudaError_t e = build_egsa_range(d_reads, n_reads, read_len, key_lo, key_hi, before, capacity, d_lcp, d_text, d_suff, d_bwt, n_records,
+                                     first_position, c->stream, &c->launches);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return fail(c, E2S_ERR_NOMEM, "e2s_build_egsa_range_dev: scratch buffers (24.5 / 32.5 bytes per suffix of the range)");
+    }
+    if (e == cudaErrorInvalidPitchValue) {
+        cudaGetLastError();
+        return fail(c, E2S_ERR_ARG, "e2s_build_egsa_range_dev: the key range holds more records than `capacity` (*n_records says how many)");
+    }
+    if (e == cudaErrorInvalidValue) {
+        cudaGetLastError();
+        return fail(c, E2S_ERR_UNSUPPORTED, "e2s_build_egsa_range_dev: a read holds a base outside ACGT/acgt");
+    }
+    if (e == cudaErrorInvalidConfiguration) {
+        cudaGetLastError();
+        return fail(c, E2S_ERR_UNSUPPORTED, "e2s_build_egsa_range_dev: the collection is outside what one call sorts");
+    }
+    if (e != cudaSuccess) return cuda_fail(c, e, "build_egsa_range");
+    return E2S_OK;
+}
+
 // host buffers in and out: device buffers allocated and released here
 static int build_egsa_host(e2s_ctx* c, const char* who, const uint8_t* reads, const uint64_t* off, uint64_t n_reads, uint32_t read_len,
                            uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt) {

@@ -126,6 +126,18 @@ int e2s_build_egsa_ragged_dev(e2s_ctx *ctx, const uint8_t *d_bases, const uint64
 int e2s_build_egsa_ragged(e2s_ctx *ctx, const uint8_t *bases, const uint64_t *off, uint64_t n_reads, uint32_t *lcp,
                           uint32_t *text, uint32_t *suff, uint8_t *bwt);
 
+/* ONE KEY RANGE of the index of n_reads equal-length reads: the suffixes whose first 32 symbols -- as a 64-bit word at 2 bits per
+ * base (A=0 C=1 G=2 T=3, first symbol most significant, zero padded past the end of the read) -- lie in [key_lo, key_hi)
+ * (key_hi = 0: no upper bound) are a contiguous range of the index.  Writes their records to the DEVICE arrays (capacity
+ * records each), *n_records = how many, *first_position = the index position of the first one.  What a collection too large for one
+ * call's scratch is built from (range after range on one GPU), and what each GPU of a box builds for its shard (the egsa / BCR run
+ * of ref:pipeline.sh:98-109 sharded by key).  (before_text, before_suff) = the record that precedes the range, for lcp[0];
+ * before_text = 0xFFFFFFFF: none / not known, lcp[0] = 0.  More records than capacity: E2S_ERR_ARG, nothing written, *n_records set.
+ * Scratch: 24.5 / 32.5 bytes per suffix of the RANGE.  Synchronises the context's stream. */
+int e2s_build_egsa_range_dev(e2s_ctx *ctx, const uint8_t *d_reads, uint64_t n_reads, uint32_t read_len, uint64_t key_lo,
+                             uint64_t key_hi, uint32_t before_text, uint32_t before_suff, uint64_t capacity, uint32_t *d_lcp,
+                             uint32_t *d_text, uint32_t *d_suff, uint8_t *d_bwt, uint64_t *n_records, uint64_t *first_position);
+
 /* Layout of the index files the shard was loaded from: byte widths of lcp (x), text (y), suff (z) and whether it
  * was the BCR triple.  Only the reference's post-EOF phantom record depends on it.
  * e2s_shard_load_gesa sets (x, y, z, 0) itself; SoA loads default to (4, 4, 4, 0).  Call before e2s_shard_seal. */

@@ -173,3 +173,51 @@ def test_ragged_reads_through_the_tool_chain(built, tmp_path):
                             capture_output=True, text=True, timeout=600)
         assert r2.returncode == 0
         assert open(snp, "rb").read() == mine_snp
+
+
+def key_of(prefix):
+    """the 64-bit first key word of a suffix that starts with `prefix` (bytes of ACGT), zero padded"""
+    v = 0
+    for ch in prefix:
+        v = (v << 2) | b"ACGT".index(ch)
+    return v << (64 - 2 * len(prefix))
+
+
+@pytest.mark.parametrize("ids64", [False, True])
+def test_key_ranges_concatenate_to_the_index(ctx, monkeypatch, ids64):
+    """e2s_build_egsa_range_dev: the index built range after range (each range told the last record of the one before) equals
+    the index built in one call; ranges built independently (predecessor not known) differ only in lcp[0]; first_position is the
+    range's place in the index; an empty range and a capacity that is too small answer as documented"""
+    if ids64:
+        monkeypatch.setenv("E2S_BUILD_IDS64", "1")
+    else:
+        monkeypatch.delenv("E2S_BUILD_IDS64", raising=False)
+    rs = synth.make_read_set(G=20_000, reads_per_sample=3_000, L=100, n_snps=40, n_indels=4, rc=True, seed=77)
+    whole = O.build_egsa(rs.reads)
+    n = whole["n"]
+    cuts = [0, key_of(b"AC"), key_of(b"CGT"), key_of(b"CGTA"), key_of(b"G"), key_of(b"TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT"), 0]
+    at, before = 0, None
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        part = ctx.build_egsa_range(rs.reads, lo, hi, before=before)
+        alone = ctx.build_egsa_range(rs.reads, lo, hi)
+        m = part["n"]
+        assert part["first"] == at and alone["first"] == at and alone["n"] == m, (hex(lo), hex(hi))
+        for key in ("text", "suff", "lcp", "bwt"):
+            got = part[key].cpu().numpy()
+            got = got.view(np.uint32) if key != "bwt" else got
+            assert np.array_equal(got, whole[key][at:at + m]), (key, hex(lo), hex(hi))
+            solo = alone[key].cpu().numpy()
+            solo = solo.view(np.uint32) if key != "bwt" else solo
+            if key == "lcp" and m:
+                assert solo[0] == 0 and np.array_equal(solo[1:], whole[key][at + 1:at + m])
+            else:
+                assert np.array_equal(solo, whole[key][at:at + m])
+        if m:
+            before = (int(whole["text"][at + m - 1]), int(whole["suff"][at + m - 1]))
+        at += m
+    assert at == n
+    empty = ctx.build_egsa_range(rs.reads, key_of(b"CGTA"), key_of(b"CGTA") + 1)
+    assert empty["n"] == 0
+    with pytest.raises(Exception) as ei:
+        ctx.build_egsa_range(rs.reads, 0, 0, capacity=n - 1)
+    assert "capacity" in str(ei.value)
