@@ -195,7 +195,7 @@ def test_key_ranges_concatenate_to_the_index(ctx, monkeypatch, ids64):
     rs = synth.make_read_set(G=20_000, reads_per_sample=3_000, L=100, n_snps=40, n_indels=4, rc=True, seed=77)
     whole = O.build_egsa(rs.reads)
     n = whole["n"]
-    cuts = [0, key_of(b"AC"), key_of(b"CGT"), key_of(b"CGTA"), key_of(b"G"), key_of(b"TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT"), 0]
+    cuts = [0, key_of(b"AC"), key_of(b"CGT"), key_of(b"CGTC"), key_of(b"G"), key_of(b"TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT"), 0]
     at, before = 0, None
     for lo, hi in zip(cuts[:-1], cuts[1:]):
         part = ctx.build_egsa_range(rs.reads, lo, hi, before=before)
@@ -216,7 +216,7 @@ def test_key_ranges_concatenate_to_the_index(ctx, monkeypatch, ids64):
             before = (int(whole["text"][at + m - 1]), int(whole["suff"][at + m - 1]))
         at += m
     assert at == n
-    empty = ctx.build_egsa_range(rs.reads, key_of(b"CGTA"), key_of(b"CGTA") + 1)
+    empty = ctx.build_egsa_range(rs.reads, key_of(b"CGTC") + 1, key_of(b"CGTC") + 2)
     assert empty["n"] == 0
     with pytest.raises(Exception) as ei:
         ctx.build_egsa_range(rs.reads, 0, 0, capacity=n - 1)
