@@ -960,6 +960,78 @@ int e2s_build_egsa_range_dev(e2s_ctx* c, const uint8_t* d_reads, uint64_t n_read
     return E2S_OK;
 }
 
+// Equal-length reads whose index does not fit one call's device memory (outputs 13 B + scratch 24.5 / 32.5 B per suffix): the
+// index key range by key range (e2s_build_egsa_range_dev), every range's records copied to their place in the host arrays.  A range
+// that turns out to hold more than `cap` records is cut in two.  E2S_BUILD_RANGE_RECORDS=<cap> forces this path (tests).
+static int build_egsa_host_ranges(e2s_ctx* c, const char* who, const uint8_t* d_reads, uint64_t n_reads, uint32_t read_len, uint64_t cap,
+                                  uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt) {
+    const uint64_t n = n_reads * (uint64_t(read_len) + 1);
+    uint8_t* d_bwt = nullptr;
+    uint32_t *d_lcp = nullptr, *d_text = nullptr, *d_suff = nullptr;
+    auto release = [&]() { cudaFree(d_bwt); cudaFree(d_lcp); cudaFree(d_text); cudaFree(d_suff); };
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_bwt), cap);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_lcp), cap * 4);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_text), cap * 4);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_suff), cap * 4);
+    if (e != cudaSuccess) {
+        release();
+        cudaGetLastError();
+        return fail(c, E2S_ERR_NOMEM, std::string(who) + ": device buffers of one key range");
+    }
+    // ranges as (lo, hi) with hi = 0 for "to the end of the key space", processed in key order from a stack
+    uint64_t parts = (n + cap - 1) / cap;
+    parts += parts / 4 + 1;
+    std::vector<std::pair<uint64_t, uint64_t>> todo;
+    for (uint64_t i = parts; i-- > 0;) {
+        const uint64_t lo = uint64_t((static_cast<unsigned __int128>(i) << 64) / parts);
+        const uint64_t hi = i + 1 == parts ? 0 : uint64_t((static_cast<unsigned __int128>(i + 1) << 64) / parts);
+        if (hi == 0 || hi > lo) todo.emplace_back(lo, hi);
+    }
+    uint64_t at = 0;
+    uint32_t before_text = 0xffffffffu, before_suff = 0;
+    int rc = E2S_OK;
+    while (!todo.empty() && rc == E2S_OK) {
+        const auto [lo, hi] = todo.back();
+        todo.pop_back();
+        uint64_t m = 0, first = 0;
+        rc = e2s_build_egsa_range_dev(c, d_reads, n_reads, read_len, lo, hi, before_text, before_suff, cap, d_lcp, d_text, d_suff, d_bwt, &m, &first);
+        if (rc == E2S_ERR_ARG && m > cap) {  // too many records for the buffers: two halves (a single key value cannot be cut)
+            const uint64_t width = hi - lo;  // (mod 2^64: right for hi = 0 as long as lo > 0 or the range is not the whole space)
+            if (width == 1 || (lo == 0 && hi == 0)) {
+                rc = fail(c, E2S_ERR_UNSUPPORTED, std::string(who) + ": one 32-symbol prefix is shared by more suffixes than fit the device");
+                break;
+            }
+            const uint64_t mid = lo + (width >> 1);
+            todo.emplace_back(mid, hi);
+            todo.emplace_back(lo, mid);
+            rc = E2S_OK;
+            continue;
+        }
+        if (rc != E2S_OK) break;
+        if (first != at || at + m > n) {
+            rc = fail(c, E2S_ERR_STATE, std::string(who) + ": key ranges do not tile the index");
+            break;
+        }
+        if (m) {
+            e = cudaMemcpyAsync(lcp + at, d_lcp, m * 4, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(text + at, d_text, m * 4, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(suff + at, d_suff, m * 4, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(bwt + at, d_bwt, m, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) {
+                rc = cuda_fail(c, e, "D2H index arrays of a key range");
+                break;
+            }
+            at += m;
+            before_text = text[at - 1];
+            before_suff = suff[at - 1];
+        }
+    }
+    if (rc == E2S_OK && at != n) rc = fail(c, E2S_ERR_STATE, std::string(who) + ": key ranges do not cover the index");
+    release();
+    return rc;
+}
+
 // host buffers in and out: device buffers allocated and released here
 static int build_egsa_host(e2s_ctx* c, const char* who, const uint8_t* reads, const uint64_t* off, uint64_t n_reads, uint32_t read_len,
                            uint32_t* lcp, uint32_t* text, uint32_t* suff, uint8_t* bwt) {
@@ -970,7 +1042,32 @@ static int build_egsa_host(e2s_ctx* c, const char* who, const uint8_t* reads, co
     uint32_t *d_lcp = nullptr, *d_text = nullptr, *d_suff = nullptr;
     auto release = [&]() { cudaFree(d_reads); cudaFree(d_bwt); cudaFree(d_lcp); cudaFree(d_text); cudaFree(d_suff); };
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_reads), total ? total : 1);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_bwt), n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, E2S_ERR_NOMEM, std::string(who) + ": the reads on the device");
+    }
+    if (!off) {  // does the whole index fit one call?  (13 B of outputs + up to 32.5 B of scratch per suffix, packed reads, slack)
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const uint64_t per_suffix = 13 + (n > 0xffffffffull ? 33 : 25);
+        uint64_t cap = 0;
+        if (const char* f = getenv("E2S_BUILD_RANGE_RECORDS")) cap = strtoull(f, nullptr, 10);
+        else if (double(n) * double(per_suffix) + double(total) / 2 > 0.92 * double(free_b)) {
+            const double room = 0.92 * double(free_b) - double(total) / 2 - double(n) / 512;
+            cap = room > 0 ? uint64_t(room / double(per_suffix)) : 0;
+            if (cap < 4096) {
+                release();
+                return fail(c, E2S_ERR_NOMEM, std::string(who) + ": not even one key range of the index fits the device");
+            }
+        }
+        if (cap) {
+            e = cudaMemcpyAsync(d_reads, reads, total, cudaMemcpyHostToDevice, c->stream);
+            const int rc = e == cudaSuccess ? build_egsa_host_ranges(c, who, d_reads, n_reads, read_len, cap, lcp, text, suff, bwt) : cuda_fail(c, e, "H2D reads");
+            release();
+            return rc;
+        }
+    }
+    e = cudaMalloc(reinterpret_cast<void**>(&d_bwt), n);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_lcp), n * 4);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_text), n * 4);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_suff), n * 4);

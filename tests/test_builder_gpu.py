@@ -128,8 +128,10 @@ def test_builder_refuses_what_it_cannot_key(ctx):
     assert "65536" in str(ei.value)
 
 
-def run(tool, *args):
-    return subprocess.run([os.path.join(BIN, tool), *[str(a) for a in args]], capture_output=True, text=True, timeout=600)
+def run(tool, *args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([os.path.join(BIN, tool), *[str(a) for a in args]], capture_output=True, text=True, timeout=600, env=e)
 
 
 def test_ragged_reads_through_the_tool_chain(built, tmp_path):
@@ -221,3 +223,20 @@ def test_key_ranges_concatenate_to_the_index(ctx, monkeypatch, ids64):
     with pytest.raises(Exception) as ei:
         ctx.build_egsa_range(rs.reads, 0, 0, capacity=n - 1)
     assert "capacity" in str(ei.value)
+
+
+def test_build_gesa_by_key_ranges_when_the_index_does_not_fit(built, tmp_path):
+    """e2s_build_egsa (host in / out, what build_gesa calls) builds the index key range by key range when one call's device memory
+    would not hold it; E2S_BUILD_RANGE_RECORDS forces that path with tiny ranges (some are cut in two on the way): same files"""
+    rs = synth.make_config("tiny", seed=21)
+    outs = []
+    for j, env in enumerate([None, {"E2S_BUILD_RANGE_RECORDS": "30000"}, {"E2S_BUILD_RANGE_RECORDS": "25000", "E2S_BUILD_IDS64": "1"}]):
+        d = tmp_path / f"v{j}"
+        os.makedirs(d)
+        fa = str(d / "ALL.fasta")
+        synth.write_fasta(fa, rs.reads)
+        r = run("build_gesa", "-i", fa, "-x", 1, "-y", 4, "-z", 1, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(open(fa + ".gesa", "rb").read())
+    assert len(outs[0]) == rs.reads.shape[0] * (rs.reads.shape[1] + 1) * 7
+    assert outs[1] == outs[0] and outs[2] == outs[0]
