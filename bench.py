@@ -168,8 +168,9 @@ def make_dataset(workload, seed, scale, device, builder="torch"):
             bctx.close()
     else:
         eg = synth.build_egsa(rs.reads, device=device)
+    eg["build_seconds"] = time.time() - t1
     log(f"[data] {workload} scale={scale} seed={seed}: reads={rs.reads.shape} in {t1 - t0:.1f}s, n={eg['n']} built on {device} "
-        f"by the {builder} builder in {time.time() - t1:.1f}s")
+        f"by the {builder} builder in {eg['build_seconds']:.1f}s")
     return rs, eg
 
 
@@ -601,7 +602,9 @@ def main():
     index_check = None
     if builder == "native":
         okc, nchk = check_egsa_sample(rs, eg)
-        index_check = {"builder": "e2s_build_egsa_dev", "sampled_records": nchk, "order_lcp_bwt_consistent": okc}
+        index_check = {"builder": "e2s_build_egsa_dev (the library's own radix sort)", "sampled_records": nchk, "order_lcp_bwt_consistent": okc,
+                       "suffixes": int(eg["n"]), "build_seconds_incl_h2d_of_the_reads": eg["build_seconds"],
+                       "suffixes_per_s": int(eg["n"]) / max(eg["build_seconds"], 1e-9)}
         log(f"[data] index property check on {nchk} sampled records: {okc}")
         if not okc:
             raise SystemExit("the index built by the library fails the order / LCP / BWT property check")

@@ -142,11 +142,7 @@ __global__ void k_init_ids_ragged(ReadsView v, IdT* __restrict__ ids) {
 }
 
 // ---- the radix sort ------------------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256;
-constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_IPT = 16;                      // pairs per thread
-constexpr int RS_TILE = RS_THREADS * RS_IPT;    // 4096 pairs per tile
-constexpr int RS_WARP_SPAN = 32 * RS_IPT;       // a warp's contiguous piece of the tile
+constexpr int RS_TILE = 4096;                   // pairs per tile (256 threads x 16 or 512 threads x 8)
 constexpr int MAX_PLACES = 8;                   // 8-bit digit places in a 64-bit word
 
 // tile status word of the chained scan: [63:45] tag of the pass (never 0), [44] inclusive, [43:0] count
@@ -227,50 +223,52 @@ __global__ void k_scan_hist(unsigned long long* __restrict__ hist, uint64_t* __r
     for (uint32_t b = threadIdx.x; b < MAX_PLACES * 256; b += blockDim.x) bin_base[b] = (&s[0][0])[b];
 }
 
-template <typename IdT>
+template <typename IdT, int THREADS>
 struct PassSmem {
-    uint64_t keys[RS_TILE];           // the tile's keys in output order
-    uint64_t gofs[256];               // output index of staged slot s of bin b = gofs[b] + s
-    IdT ids[RS_TILE];                 // the ids, same order
-    uint32_t whist[RS_WARPS][256];    // per-warp digit counts -> exclusive over the warps
-    uint32_t binstart[256];           // first staged slot of every bin
-    uint32_t wsum[RS_WARPS];
+    uint64_t keys[RS_TILE];              // the tile's keys in output order
+    uint64_t gofs[256];                  // output index of staged slot s of bin b = gofs[b] + s
+    IdT ids[RS_TILE];                    // the ids, same order
+    uint32_t whist[THREADS / 32][256];   // per-warp digit counts -> exclusive over the warps
+    uint32_t binstart[256];              // first staged slot of every bin
+    uint32_t wsum[8];
     uint32_t tile;
-    uint8_t digit[RS_TILE];           // digit of every staged slot
+    uint8_t digit[RS_TILE];              // digit of every staged slot
 };
 
-// one stable pass on the digit (key >> shift) & 255
-template <typename IdT, bool WRITE_KEYS>
-__global__ void __launch_bounds__(RS_THREADS, sizeof(IdT) == 4 ? 3 : 2) k_radix_pass(const uint64_t* __restrict__ kin, const IdT* __restrict__ iin,
-                                                           uint64_t* __restrict__ kout, IdT* __restrict__ iout, uint64_t n, uint32_t shift,
-                                                           const uint64_t* __restrict__ bin_base, uint64_t* __restrict__ status,
-                                                           uint32_t* __restrict__ ticket, uint32_t tag) {
+// one stable pass on the digit (key >> shift) & 255.  THREADS = 256 (16 pairs per thread, 3 CTAs per SM with 32-bit ids) or 512
+// (8 pairs per thread, 2 CTAs per SM): the tile is 4096 pairs either way; threads 0..255 own the bins.
+template <typename IdT, bool WRITE_KEYS, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : (sizeof(IdT) == 4 ? 3 : 2))
+k_radix_pass(const uint64_t* __restrict__ kin, const IdT* __restrict__ iin, uint64_t* __restrict__ kout, IdT* __restrict__ iout, uint64_t n,
+             uint32_t shift, const uint64_t* __restrict__ bin_base, uint64_t* __restrict__ status, uint32_t* __restrict__ ticket, uint32_t tag) {
+    constexpr int IPT = RS_TILE / THREADS;
+    constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PassSmem<IdT>& S = *reinterpret_cast<PassSmem<IdT>*>(smem_raw);
+    PassSmem<IdT, THREADS>& S = *reinterpret_cast<PassSmem<IdT, THREADS>*>(smem_raw);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) S.tile = atomicAdd(ticket, 1u);  // tiles in ticket order: every earlier tile is running or done
-    for (uint32_t b = tid; b < RS_WARPS * 256; b += RS_THREADS) (&S.whist[0][0])[b] = 0;
+    for (uint32_t b = tid; b < WARPS * 256; b += THREADS) (&S.whist[0][0])[b] = 0;
     __syncthreads();
     const uint32_t tile = S.tile;
     const uint64_t tile_base = uint64_t(tile) * RS_TILE;
     const uint32_t tile_n = n - tile_base < uint64_t(RS_TILE) ? uint32_t(n - tile_base) : uint32_t(RS_TILE);
-    const uint32_t first = warp * RS_WARP_SPAN + lane;  // item j of this thread = tile slot first + 32 j (warp-striped)
+    const uint32_t first = warp * (32 * IPT) + lane;  // item j of this thread = tile slot first + 32 j (warp-striped)
 
-    uint64_t key[RS_IPT];
+    uint64_t key[IPT];
 #pragma unroll
-    for (int j = 0; j < RS_IPT; ++j) {
+    for (int j = 0; j < IPT; ++j) {
         const uint32_t li = first + 32 * j;
         key[j] = li < tile_n ? kin[tile_base + li] : ~uint64_t(0);
     }
     // rank of every item among the items of its warp with the same digit, in (item, lane) order.  The running count of a
     // digit is one shared-memory atomic by the first lane that holds it; the atomics of a warp are performed in program order,
-    // and nothing waits for a result before all sixteen are on their way (the results are picked up in a second loop).
-    uint32_t prevv[RS_IPT];      // leader lanes: the digit's count before this item
-    uint32_t lb[RS_IPT / 2];     // per item: lanes below with the same digit (bits 0-7), the leader lane (bits 8-15)
+    // and nothing waits for a result before all of them are on their way (the results are picked up in a second loop).
+    uint32_t prevv[IPT];      // leader lanes: the digit's count before this item
+    uint32_t lb[IPT / 2];     // per item: lanes below with the same digit (bits 0-7), the leader lane (bits 8-15)
     uint32_t* wh = S.whist[warp];
 #pragma unroll
-    for (int j = 0; j < RS_IPT; ++j) {
+    for (int j = 0; j < IPT; ++j) {
         const bool valid = first + 32 * j < tile_n;
         const uint32_t d = valid ? uint32_t(key[j] >> shift) & 0xffu : 256u + lane;
         const uint32_t m = __match_any_sync(0xffffffffu, d);
@@ -280,75 +278,80 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(IdT) == 4 ? 3 : 2) k_radix_
         const uint32_t x = uint32_t(__popc(m & ((1u << lane) - 1u))) | (leader << 8);
         lb[j >> 1] = (j & 1) ? (lb[j >> 1] | (x << 16)) : x;
     }
-    uint32_t rnk[RS_IPT / 2];    // two 16-bit ranks per register
+    uint32_t rnk[IPT / 2];    // two 16-bit ranks per register
 #pragma unroll
-    for (int j = 0; j < RS_IPT; ++j) {
+    for (int j = 0; j < IPT; ++j) {
         const uint32_t x = (j & 1) ? lb[j >> 1] >> 16 : lb[j >> 1] & 0xffffu;
         const uint32_t rk = __shfl_sync(0xffffffffu, prevv[j], int(x >> 8)) + (x & 0xffu);
         rnk[j >> 1] = (j & 1) ? (rnk[j >> 1] | (rk << 16)) : rk;
     }
     // the ids travel with the keys: asked for now, needed after the chained scan
-    IdT idv[RS_IPT];
+    IdT idv[IPT];
 #pragma unroll
-    for (int j = 0; j < RS_IPT; ++j) {
+    for (int j = 0; j < IPT; ++j) {
         const uint32_t li = first + 32 * j;
         idv[j] = li < tile_n ? iin[tile_base + li] : IdT(0);
     }
     __syncthreads();
 
-    // thread b owns bin b: counts exclusive over the warps, the tile's count published for the tiles behind
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-        const uint32_t t = S.whist[w][tid];
-        S.whist[w][tid] = cnt;
-        cnt += t;
-    }
+    // thread b < 256 owns bin b: counts exclusive over the warps, the tile's count published for the tiles behind
+    const bool bin_thread = THREADS == 256 || tid < 256;  // (whole warps)
+    uint32_t cnt = 0, incl = 0;
     uint64_t* st = status + uint64_t(tile) * 256 + tid;
     const uint64_t tagw = uint64_t(tag) << TAG_SHIFT;
-    st_status(st, tagw | (tile == 0 ? INCL_BIT : 0) | cnt);
-    // first staged slot of the bin: block-wide exclusive scan of cnt
-    uint32_t incl = cnt;
+    if (bin_thread) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= uint32_t(o)) incl += t;
-    }
-    if (lane == 31) S.wsum[warp] = incl;
-    __syncthreads();
-    uint32_t wbase = 0;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) wbase += uint32_t(w) < warp ? S.wsum[w] : 0u;
-    const uint32_t binstart = wbase + incl - cnt;
-    S.binstart[tid] = binstart;
-    // chained scan: pairs of this bin in all earlier tiles
-    uint64_t excl = 0;
-    if (tile > 0) {
-        int64_t t = int64_t(tile) - 1;
-        for (bool open = true; open;) {
-            // four earlier tiles asked for together (one round trip), taken in order
-            uint64_t wv[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) wv[q] = t - q >= 0 ? ld_status(status + uint64_t(t - q) * 256 + tid) : 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (open && t - q >= 0) {
-                    uint64_t x = wv[q];
-                    while ((x >> TAG_SHIFT) != tag) x = ld_status(status + uint64_t(t - q) * 256 + tid);
-                    excl += x & CNT_MASK;
-                    if (x & INCL_BIT) open = false;
-                }
-            }
-            t -= 4;
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t t = S.whist[w][tid];
+            S.whist[w][tid] = cnt;
+            cnt += t;
         }
-        st_status(st, tagw | INCL_BIT | (excl + cnt));
+        st_status(st, tagw | (tile == 0 ? INCL_BIT : 0) | cnt);
+        // first staged slot of the bin: exclusive scan of cnt over the bins
+        incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= uint32_t(o)) incl += t;
+        }
+        if (lane == 31) S.wsum[warp] = incl;
     }
-    S.gofs[tid] = bin_base[tid] + excl - binstart;
+    __syncthreads();
+    if (bin_thread) {
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) wbase += uint32_t(w) < warp ? S.wsum[w] : 0u;
+        const uint32_t binstart = wbase + incl - cnt;
+        S.binstart[tid] = binstart;
+        // chained scan: pairs of this bin in all earlier tiles
+        uint64_t excl = 0;
+        if (tile > 0) {
+            int64_t t = int64_t(tile) - 1;
+            for (bool open = true; open;) {
+                // four earlier tiles asked for together (one round trip), taken in order
+                uint64_t wv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) wv[q] = t - q >= 0 ? ld_status(status + uint64_t(t - q) * 256 + tid) : 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (open && t - q >= 0) {
+                        uint64_t x = wv[q];
+                        while ((x >> TAG_SHIFT) != tag) x = ld_status(status + uint64_t(t - q) * 256 + tid);
+                        excl += x & CNT_MASK;
+                        if (x & INCL_BIT) open = false;
+                    }
+                }
+                t -= 4;
+            }
+            st_status(st, tagw | INCL_BIT | (excl + cnt));
+        }
+        S.gofs[tid] = bin_base[tid] + excl - binstart;
+    }
     __syncthreads();
 
     // pairs into output order (shared), then out as one coalesced run per bin
 #pragma unroll
-    for (int j = 0; j < RS_IPT; ++j) {
+    for (int j = 0; j < IPT; ++j) {
         if (first + 32 * j < tile_n) {
             const uint32_t d = uint32_t(key[j] >> shift) & 0xffu;
             const uint32_t rk = (j & 1) ? rnk[j >> 1] >> 16 : rnk[j >> 1] & 0xffffu;
@@ -361,14 +364,14 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(IdT) == 4 ? 3 : 2) k_radix_
     __syncthreads();
     if (tile_n == uint32_t(RS_TILE)) {
 #pragma unroll
-        for (int j = 0; j < RS_IPT; ++j) {
-            const uint32_t i = tid + uint32_t(j) * RS_THREADS;
+        for (int j = 0; j < IPT; ++j) {
+            const uint32_t i = tid + uint32_t(j) * THREADS;
             const uint64_t g = S.gofs[S.digit[i]] + i;
             if (WRITE_KEYS) kout[g] = S.keys[i];
             iout[g] = S.ids[i];
         }
     } else {
-        for (uint32_t i = tid; i < tile_n; i += RS_THREADS) {
+        for (uint32_t i = tid; i < tile_n; i += THREADS) {
             const uint64_t g = S.gofs[S.digit[i]] + i;
             if (WRITE_KEYS) kout[g] = S.keys[i];
             iout[g] = S.ids[i];
@@ -647,9 +650,16 @@ cudaError_t build_typed(ReadsView v, uint64_t n_all, uint64_t total_bases, const
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int smem_bytes = int(sizeof(PassSmem<IdT>));
-    if ((e = cudaFuncSetAttribute(k_radix_pass<IdT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)) != cudaSuccess) return done(e);
-    if ((e = cudaFuncSetAttribute(k_radix_pass<IdT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)) != cudaSuccess) return done(e);
+    // 256 threads x 16 pairs (3 CTAs per SM at 80 registers with 32-bit ids, 2 at 128 with 64-bit ids) or 512 threads x 8 pairs (2 CTAs
+    // per SM at 64 registers).  Measured on the C2-size index: 32-bit ids 128 ms / 139 ms, 64-bit ids 151 ms / 146 ms -- the default is
+    // the faster one of each; E2S_RADIX_THREADS overrides (tests run both).
+    int rs_threads = sizeof(IdT) == 4 ? 256 : 512;
+    if (const char* t = getenv("E2S_RADIX_THREADS")) rs_threads = atoi(t) == 512 ? 512 : 256;
+    const int smem_bytes = rs_threads == 512 ? int(sizeof(PassSmem<IdT, 512>)) : int(sizeof(PassSmem<IdT, 256>));
+    if ((e = cudaFuncSetAttribute(k_radix_pass<IdT, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(PassSmem<IdT, 256>)))) != cudaSuccess) return done(e);
+    if ((e = cudaFuncSetAttribute(k_radix_pass<IdT, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(PassSmem<IdT, 256>)))) != cudaSuccess) return done(e);
+    if ((e = cudaFuncSetAttribute(k_radix_pass<IdT, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(PassSmem<IdT, 512>)))) != cudaSuccess) return done(e);
+    if ((e = cudaFuncSetAttribute(k_radix_pass<IdT, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(PassSmem<IdT, 512>)))) != cudaSuccess) return done(e);
     // Sorts the current order on `places` digit places of key word w (w_base = 32 w symbols before it; LEN_WORD: the length
     // key, everything moves).  n_le[t] = suffixes of t symbols or fewer.  A suffix that ends before the symbols of a place has
     // digit 0 there and is still where the shortest-first order put it (a prefix of the current order, identical in both
@@ -676,12 +686,14 @@ cudaError_t build_typed(ReadsView v, uint64_t n_all, uint64_t total_bases, const
             const uint32_t sh = begin_bit + 8 * j;
             const uint64_t f = first_of[j], mj = n - f;
             const unsigned tiles_j = unsigned((mj + RS_TILE - 1) / RS_TILE);
-            if (j + 1 < places)
-                k_radix_pass<IdT, true><<<tiles_j, RS_THREADS, smem_bytes, stream>>>(kc + f, ic + f, ka + f, ia + f, mj, sh, bin_base + 256 * j,
-                                                                                     status, tickets + seq, seq + 1);
-            else  // the keys of this word are not looked at again
-                k_radix_pass<IdT, false><<<tiles_j, RS_THREADS, smem_bytes, stream>>>(kc + f, ic + f, ka + f, ia + f, mj, sh, bin_base + 256 * j,
-                                                                                      status, tickets + seq, seq + 1);
+            const bool wk = j + 1 < places;  // the keys of a word are not looked at again after its last place
+            if (rs_threads == 512) {
+                if (wk) k_radix_pass<IdT, true, 512><<<tiles_j, 512, smem_bytes, stream>>>(kc + f, ic + f, ka + f, ia + f, mj, sh, bin_base + 256 * j, status, tickets + seq, seq + 1);
+                else k_radix_pass<IdT, false, 512><<<tiles_j, 512, smem_bytes, stream>>>(kc + f, ic + f, ka + f, ia + f, mj, sh, bin_base + 256 * j, status, tickets + seq, seq + 1);
+            } else {
+                if (wk) k_radix_pass<IdT, true, 256><<<tiles_j, 256, smem_bytes, stream>>>(kc + f, ic + f, ka + f, ia + f, mj, sh, bin_base + 256 * j, status, tickets + seq, seq + 1);
+                else k_radix_pass<IdT, false, 256><<<tiles_j, 256, smem_bytes, stream>>>(kc + f, ic + f, ka + f, ia + f, mj, sh, bin_base + 256 * j, status, tickets + seq, seq + 1);
+            }
             *launches += 1;
             uint64_t* tk = kc; kc = ka; ka = tk;
             IdT* ti = ic; ic = ia; ia = ti;

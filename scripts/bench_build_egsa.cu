@@ -46,7 +46,7 @@ cudaError_t build_with_cub(const uint8_t* d_reads, uint64_t R, uint32_t L, uint3
         const uint32_t syms = L - 32 * uint32_t(w) < 32 ? L - 32 * uint32_t(w) : 32;
         cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, ids, n, int(64 - 2 * syms), 64, stream);
     }
-    k_egsa_finish<uint32_t><<<blocks_for(n, 256), 256, 0, stream>>>(v, packed, ids.Current(), n, d_lcp, d_text, d_suff, d_bwt);
+    k_egsa_finish<uint32_t><<<blocks_for(n, 256), 256, 0, stream>>>(v, packed, ids.Current(), n, d_lcp, d_text, d_suff, d_bwt, ~uint64_t(0));
     cudaError_t e = cudaStreamSynchronize(stream);
     cudaFree(packed); cudaFree(k0); cudaFree(k1); cudaFree(i0); cudaFree(i1); cudaFree(bad); cudaFree(tmp);
     return e;

@@ -81,13 +81,19 @@ def make_case(name):
     raise KeyError(name)
 
 
+@pytest.mark.parametrize("threads", [None, "256", "512"])
 @pytest.mark.parametrize("ids64", [False, True])
 @pytest.mark.parametrize("name", CASES)
-def test_ragged_builder_vs_oracle(ctx, monkeypatch, name, ids64):
+def test_ragged_builder_vs_oracle(ctx, monkeypatch, name, ids64, threads):
+    """both id widths x both shapes of the radix pass (256 threads x 16 pairs, 512 x 8; None = the default of the id width)"""
     if ids64:
         monkeypatch.setenv("E2S_BUILD_IDS64", "1")
     else:
         monkeypatch.delenv("E2S_BUILD_IDS64", raising=False)
+    if threads:
+        monkeypatch.setenv("E2S_RADIX_THREADS", threads)
+    else:
+        monkeypatch.delenv("E2S_RADIX_THREADS", raising=False)
     bases, off = make_case(name)
     check_ragged(ctx, bases, off, name)
 
