@@ -48,7 +48,7 @@ def check_ragged(ctx, bases, off, what):
         assert bad.size == 0, (what, key, int(bad[0]), g[bad[:4]], want[key][bad[:4]])
 
 
-CASES = ["tiny", "genome", "two_length_places", "skewed", "many_tiles"]
+CASES = ["tiny", "genome", "two_length_places", "skewed", "many_tiles", "skewed_many_tiles"]
 
 
 def make_case(name):
@@ -78,6 +78,14 @@ def make_case(name):
         return np.concatenate(parts), off
     if name == "many_tiles":  # 1.1 M suffixes = 270 tiles: the chained scan across many tiles
         return ragged_from_genome(rng, 200_000, 11_000, 60, 140)
+    if name == "skewed_many_tiles":  # 170 tiles in which one or two digits take everything: poly-A / poly-T reads and copies
+        parts = [np.full(int(l), ord("A"), dtype=np.uint8) for l in rng.integers(0, 150, size=5000)]
+        parts += [np.full(int(l), ord("T"), dtype=np.uint8) for l in rng.integers(0, 150, size=2000)]
+        one = BASES[rng.integers(0, 4, size=120)]
+        parts += [one[: int(l)] for l in rng.integers(100, 121, size=1500)]
+        off = np.zeros(len(parts) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(p) for p in parts])
+        return np.concatenate(parts), off
     raise KeyError(name)
 
 
@@ -99,7 +107,8 @@ def test_ragged_builder_vs_oracle(ctx, monkeypatch, name, ids64, threads):
 
 
 @pytest.mark.parametrize("ids64", [False, True])
-@pytest.mark.parametrize("R,L", [(1, 1), (3, 32), (700, 33), (2_000, 64), (1_500, 100), (900, 150), (40, 257)])
+@pytest.mark.parametrize("R,L", [(1, 1), (3, 32), (700, 33), (2_000, 64), (1_500, 100), (900, 150), (40, 257),
+                                 (64, 63), (65, 63), (128, 63), (32, 127), (1024, 31), (1023, 31)])  # n = whole tiles of 4096, one more, one less
 def test_equal_length_builder_vs_oracle(ctx, monkeypatch, R, L, ids64):
     """equal lengths take the arithmetic ids (no length pass): every word-count boundary, both id widths; the same reads
     through the ragged entry point give the same index"""
