@@ -49,6 +49,8 @@ __global__ void k_pack_exchange(const ClusterDev* res, uint64_t n_local, uint64_
 __global__ void __launch_bounds__(128) k_merge_stats(MergeParams p) {
     __shared__ e2s_cluster_summary sums[MERGE_MAX_SHARDS];
     __shared__ e2s_stats tot;
+    __shared__ unsigned long long s_cum[E2S_HIST_BINS];
+    __shared__ int s_status, s_mcl;
     const int tid = threadIdx.x;
     // the rows -> summaries (one thread per shard) and the sum of the shards' own-record histograms (one thread per bin):
     // everything the serial part below touches is then in shared memory
@@ -92,7 +94,17 @@ __global__ void __launch_bounds__(128) k_merge_stats(MergeParams p) {
             }
         }
         tot.last_len = last_len;
-        if (status == MERGE_OK) status = any ? stats_finish_core(&tot, last_len, p.mcov, p.pval) : MERGE_EMPTY;
+        if (status == MERGE_OK) status = any ? stats_finish_head(&tot, last_len, p.mcov) : MERGE_EMPTY;
+        s_status = status;
+        if (status == MERGE_OK) {  // the pval loop's running sum for every candidate max_clust_length (integers: cheap in one thread)
+            const int m0 = 2 * p.mcov;
+            unsigned long long cum = 0;
+            for (int i = m0; i <= E2S_MAX_C_LEN; ++i) {
+                cum += tot.hist[i] * (unsigned long long)i;
+                s_cum[i] = cum;
+            }
+            s_mcl = E2S_MAX_C_LEN;
+        }
         out->status = status;
         if (status == MERGE_OK && p.pf_list) {  // the records this shard adopts go to the exact test unconditionally
             for (uint32_t i = 0; i < out->mine.n_adopt; ++i) {
@@ -103,6 +115,17 @@ __global__ void __launch_bounds__(128) k_merge_stats(MergeParams p) {
         }
     }
     __syncthreads();
+    if (s_status == MERGE_OK) {
+        // the pval loop of statistics() (ref:clust2snp.cpp:938-946; stats_finish_core): max_clust_length = the first mcl >= 2 mcov
+        // whose cumulative / n_bases is not below pval (or the cap).  One IEEE double division per candidate, the same operation the
+        // serial loop performs, here one candidate per thread: a dependent chain of ~60 divisions took 10 us in one thread.
+        const int m0 = 2 * p.mcov;
+        for (int i = m0 + tid; i < E2S_MAX_C_LEN; i += blockDim.x)
+            if (!(double(s_cum[i]) / double(tot.n_bases) < p.pval)) atomicMin(&s_mcl, i);
+        __syncthreads();
+        if (tid == 0) tot.max_clust_length = s_mcl;
+        __syncthreads();
+    }
     {   // statistics() out, max_clust_length included (phase 2's exact test reads it from here)
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&tot);
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(&out->total);

@@ -110,7 +110,8 @@ E2S_HD inline int merge_core(const e2s_cluster_summary* all, int n_shards, int m
 
 // e2s_statistics_finish: the reference counts the last record twice, then runs the pval loop -- one IEEE double division
 // per step (ref:clust2snp.cpp:938-946; the device's division is the same correctly rounded operation)
-E2S_HD inline int stats_finish_core(e2s_stats* st, uint64_t last_len, int mcov_out, double pval) {
+// first half (serial, cheap): the double-counted last record, max_len, the mcov check
+E2S_HD inline int stats_finish_head(e2s_stats* st, uint64_t last_len, int mcov_out) {
     if (st->n_clust == 0) return MERGE_EMPTY;
     if (last_len <= E2S_MAX_C_LEN) st->hist[last_len]++;
     st->n_clust++;
@@ -118,8 +119,15 @@ E2S_HD inline int stats_finish_core(e2s_stats* st, uint64_t last_len, int mcov_o
     st->max_len = 0;
     for (int i = 0; i < E2S_HIST_BINS; ++i)
         if (st->hist[i]) st->max_len = uint64_t(i);
-    int mcl = 2 * mcov_out;
+    const int mcl = 2 * mcov_out;
     if (mcl < 0 || mcl > E2S_MAX_C_LEN) return MERGE_BAD_MCOV;
+    return MERGE_OK;
+}
+
+E2S_HD inline int stats_finish_core(e2s_stats* st, uint64_t last_len, int mcov_out, double pval) {
+    const int rc = stats_finish_head(st, last_len, mcov_out);
+    if (rc != MERGE_OK) return rc;
+    int mcl = 2 * mcov_out;
     uint64_t cumulative = st->hist[mcl] * uint64_t(mcl);
     while (double(cumulative) / double(st->n_bases) < pval && mcl < E2S_MAX_C_LEN) {
         mcl++;

@@ -601,11 +601,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_chunk_resolve(ResolveParams p) {
     if (c < 4) s_tot[c] = 0;
     __syncthreads();
     uint64_t X = p.init_state;
-    for (int j = c - 1; j >= 0; --j)
-        if (s_state[j]) {
-            X = s_state[j] >= OPEN_BIAS ? s_state[j] : OPEN_NONE;
-            break;
-        }
+    if (act && rec.head_end)  // (only a head END asks what was open before the chunk; the threads past the last chunk would walk all the way down)
+        for (int j = c - 1; j >= 0; --j)
+            if (s_state[j]) {
+                X = s_state[j] >= OPEN_BIAS ? s_state[j] : OPEN_NONE;
+                break;
+            }
     uint64_t h_start = 0;
     uint32_t h_len = 0, h_kept = 0;
     if (act && rec.head_end) {
