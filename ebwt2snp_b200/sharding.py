@@ -36,6 +36,45 @@ def shard_cuts(n, parts):
     return cuts
 
 
+def first_key_words(reads, rows, cols):
+    """the 64-bit first key word (32 symbols at 2 bits, A=0 C=1 G=2 T=3, first symbol most significant, zero padded) of the suffixes
+    (rows[i], cols[i]) of the (R, L) read matrix: what e2s_build_egsa_range_dev compares with its key range"""
+    reads = np.asarray(reads)
+    L = reads.shape[1]
+    code = np.zeros(256, dtype=np.uint64)
+    for c, v in ((b"C", 1), (b"c", 1), (b"G", 2), (b"g", 2), (b"T", 3), (b"t", 3)):
+        code[c[0]] = v
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
+    key = np.zeros(len(rows), dtype=np.uint64)
+    for j in range(32):
+        at = cols + j
+        inside = at < L
+        sym = np.where(inside, code[reads[rows, np.minimum(at, L - 1)]], np.uint64(0))
+        key = (key << np.uint64(2)) | sym
+    return key
+
+
+def key_range_cuts(parts, reads=None, sample=1 << 16, seed=0):
+    """`parts` key ranges [(lo, hi), ...] that tile the 64-bit key space (hi = 0 on the last one: no upper bound) -- one per rank (or
+    per pass) for e2s_build_egsa_range_dev.  Without reads: equal slices of the key space.  With the (R, L) read matrix: the cuts are
+    quantiles of the first key words of `sample` random suffixes, so the ranges hold about the same number of records whatever the
+    base composition (the terminator suffixes, 4/3 R records under key 0, stay in the first range)."""
+    parts = max(1, int(parts))
+    if reads is None:
+        cuts = [(i << 64) // parts for i in range(parts)]
+    else:
+        reads = np.asarray(reads)
+        R, L = reads.shape
+        rng = np.random.default_rng(seed)
+        m = int(min(sample, R * (L + 1)))
+        keys = np.sort(first_key_words(reads, rng.integers(0, R, size=m), rng.integers(0, L + 1, size=m)))
+        cuts = [0] + [int(keys[(i * m) // parts]) for i in range(1, parts)]
+        for i in range(1, parts):  # strictly increasing (a heavy key value cannot be cut: the ranges after it start past it)
+            cuts[i] = max(cuts[i], cuts[i - 1] + 1)
+    return [(cuts[i], cuts[i + 1] if i + 1 < parts else 0) for i in range(parts)]
+
+
 def _world(group=None):
     if not (dist.is_available() and dist.is_initialized()):
         return 0, 1

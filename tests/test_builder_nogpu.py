@@ -82,3 +82,26 @@ def test_reference_tools_on_ragged_reads_equal_the_oracle_port(tmp_path):
     otext, ores = O.find_events(e["lcp"], e["text"], e["suff"], e["bwt"], es, el, op, ost.max_clust_length, bases, off)
     snp = open(str(tmp_path / "ALL.snp"), "rb").read()
     assert ores.n_events > 0 and (otext if isinstance(otext, bytes) else otext.encode()) == snp
+
+
+def test_key_range_cuts_tile_the_key_space_and_balance_the_records():
+    """sharding.key_range_cuts: the ranges e2s_build_egsa_range_dev takes, one per rank.  They tile [0, 2^64); with the reads given
+    they are sample quantiles, and the oracle's index splits into nearly equal record counts by them (first_key_words = the key
+    the library compares, checked against the index order: keys are non-decreasing along the index)"""
+    from ebwt2snp_b200 import sharding
+    for parts in (1, 2, 3, 8):
+        cuts = sharding.key_range_cuts(parts)
+        assert cuts[0][0] == 0 and cuts[-1][1] == 0 and len(cuts) == parts
+        assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(cuts, cuts[1:]))
+    rs = synth.make_read_set(G=30_000, reads_per_sample=2_000, L=100, n_snps=30, n_indels=2, rc=True, seed=9)
+    e = O.build_egsa(rs.reads)
+    keys = sharding.first_key_words(rs.reads, e["text"], e["suff"])
+    assert np.all(keys[1:] >= keys[:-1])  # the first key word is the most significant part of the index order
+    n = e["n"]
+    for parts in (2, 4, 8):
+        cuts = sharding.key_range_cuts(parts, rs.reads, sample=1 << 14, seed=1)
+        assert cuts[0][0] == 0 and cuts[-1][1] == 0
+        assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(cuts, cuts[1:]))
+        counts = [int(np.count_nonzero((keys >= np.uint64(lo)) & ((keys < np.uint64(hi)) if hi else True))) for lo, hi in cuts]
+        assert sum(counts) == n
+        assert max(counts) < 1.25 * n / parts and min(counts) > 0.75 * n / parts, counts
