@@ -22,13 +22,16 @@
 //   worth of pairs instead of 25):
 //     k_keys_hist  symbols [p + 32 w, p + 32 w + 32) of every suffix as one 64-bit word (funnel shift of two packed
 //                  words) in the current id order, AND the 256-bin histograms of every 8-bit digit of that word in the
-//                  same pass (warp-aggregated shared-memory atomics: most suffixes are shorter than 32 w and share digit 0)
+//                  same pass (shared-memory atomics; digit 0, which the zero padding makes the common one, by one ballot and
+//                  one atomic per warp)
 //     k_scan_hist  exclusive scans -> first output slot of every (digit place, bin)
 //     k_radix_pass one launch per digit place that can differ (only the bits of symbols that exist in the longest read):
 //                  tiles of 4096 pairs dealt by a ticket, stable warp-level multisplit (match.any), chained-scan
-//                  decoupled look-back per bin (one 64-bit tagged word per tile and bin: no clearing between passes),
-//                  keys then ids staged through one shared buffer so every bin leaves as a coalesced run.  The last place
-//                  of a word moves the ids only.
+//                  decoupled look-back per bin, four tiles at a time (one 64-bit tagged word per tile and bin: no clearing
+//                  between passes), keys and ids staged together in shared memory in output order and written in one sweep,
+//                  so every bin leaves as a coalesced run.  The last place of a word moves the ids only.
+//   key ranges     (equal lengths) k_range_select / k_scan_chunks pick the suffixes whose first key word lies in [lo, hi) -- a
+//                  contiguous range of the index -- and the same sort runs on those alone (build_egsa_range).
 //   k_egsa_finish  decode (r, p); text, suff, bwt; lcp with the previous record = min(len_a - p_a, len_b - p_b, first
 //                  differing symbol) by clz on XORed key words.
 // Ids are 32-bit when they fit (equal lengths: n < 2^32; ragged: R << shift <= 2^32), else 64-bit.
