@@ -163,3 +163,41 @@ def test_place_skipping_radix_sort_model_equals_the_comparison_sort():
         assert np.array_equal(r_m, e["text"].astype(np.int64)) and np.array_equal(p_m, e["suff"].astype(np.int64))
         full = n * sum((2 * min(32, L - 32 * w) + 7) // 8 for w in range(W))
         assert moved < 0.62 * full, (moved, full)
+
+
+@pytest.mark.parametrize("threads", [256, 512])
+def test_radix_pass_slot_arithmetic_model(threads):
+    """k_radix_pass's index arithmetic restated in numpy (csrc/build_egsa.cu): warp-striped items, rank within (warp, digit) in
+    (item, lane) order, per-warp counts made exclusive over the warps, bins laid out by an exclusive scan of the tile's counts
+    -> the staged slot of every pair.  The slots must be the STABLE counting sort of the tile by digit, for full and ragged
+    tiles and for skewed digits; the output index = gofs[digit] + slot must continue the earlier tiles' bins."""
+    rng = np.random.default_rng(threads)
+    TILE, ipt, warps = 4096, 4096 // threads, threads // 32
+    for tile_n, skew in ((4096, False), (4096, True), (1000, False), (1, False), (4095, True)):
+        dig_all = rng.integers(0, 256, size=TILE) if not skew else rng.choice([0, 0, 0, 0, 255, 7], size=TILE)
+        slot = np.full(TILE, -1, dtype=np.int64)
+        whist = np.zeros((warps, 256), dtype=np.int64)
+        rank = np.zeros(TILE, dtype=np.int64)
+        for w in range(warps):
+            for j in range(ipt):
+                for lane in range(32):
+                    li = w * 32 * ipt + 32 * j + lane
+                    if li < tile_n:
+                        rank[li] = whist[w][dig_all[li]]
+                        whist[w][dig_all[li]] += 1
+        cnt = whist.sum(axis=0)
+        wexcl = np.cumsum(whist, axis=0) - whist
+        binstart = np.cumsum(cnt) - cnt
+        for li in range(tile_n):
+            w = li // (32 * ipt)
+            slot[li] = binstart[dig_all[li]] + wexcl[w][dig_all[li]] + rank[li]
+        want = np.argsort(dig_all[:tile_n], kind="stable")
+        assert np.array_equal(np.argsort(slot[:tile_n]), want) and sorted(slot[:tile_n]) == list(range(tile_n))
+        # output index: bin_base (all tiles) + pairs of the bin in the earlier tiles + place inside the tile's run of the bin
+        bin_base = rng.integers(0, 10 ** 6, size=256)
+        earlier = rng.integers(0, 5000, size=256)
+        gofs = bin_base + earlier - binstart
+        out = gofs[dig_all[:tile_n]] + slot[:tile_n]
+        for b in np.unique(dig_all[:tile_n]):
+            mine = np.sort(out[dig_all[:tile_n] == b])
+            assert mine[0] == bin_base[b] + earlier[b] and np.array_equal(mine, mine[0] + np.arange(len(mine)))
