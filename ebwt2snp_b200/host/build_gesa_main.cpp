@@ -8,6 +8,7 @@
 #include <getopt.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_io.hpp"
@@ -86,25 +87,41 @@ int main(int argc, char** argv) {
         return 3;
     }
     e2s_ctx_destroy(ctx);
+    // the records in file layout: disjoint ranges of the index, one host thread each
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : (nt > 32 ? 32 : nt);
+    if (n < (uint64_t(1) << 20)) nt = 1;
+    auto in_ranges = [&](auto&& body) {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) {
+            const uint64_t a = n / nt * t + (t < n % nt ? t : n % nt), b = a + n / nt + (t < n % nt ? 1 : 0);
+            th.emplace_back([&body, a, b]() { body(a, b); });
+        }
+        for (auto& x : th) x.join();
+    };
     bool wrote;
     if (!bcr) {
         const size_t rs = size_t(x + y + z + 1);
         std::vector<uint8_t> rec(n * rs);
-        for (uint64_t i = 0; i < n; ++i) {
-            uint8_t* p = rec.data() + i * rs;
-            put_le(p, text[i], y);
-            put_le(p + y, suff[i], z);
-            put_le(p + y + z, lcp[i], x);
-            p[y + z + x] = bwt[i];
-        }
+        in_ranges([&](uint64_t a, uint64_t b) {
+            for (uint64_t i = a; i < b; ++i) {
+                uint8_t* p = rec.data() + i * rs;
+                put_le(p, text[i], y);
+                put_le(p + y, suff[i], z);
+                put_le(p + y + z, lcp[i], x);
+                p[y + z + x] = bwt[i];
+            }
+        });
         wrote = host::write_all(input + ".gesa", rec.data(), rec.size());
     } else {
         std::vector<uint8_t> l(n * size_t(x)), g(n * size_t(z + y));
-        for (uint64_t i = 0; i < n; ++i) {
-            put_le(l.data() + i * x, lcp[i], x);
-            put_le(g.data() + i * (z + y), suff[i], z);  // suff(z) then text(y): ref:include.hpp:159-175
-            put_le(g.data() + i * (z + y) + z, text[i], y);
-        }
+        in_ranges([&](uint64_t a, uint64_t b) {
+            for (uint64_t i = a; i < b; ++i) {
+                put_le(l.data() + i * x, lcp[i], x);
+                put_le(g.data() + i * (z + y), suff[i], z);  // suff(z) then text(y): ref:include.hpp:159-175
+                put_le(g.data() + i * (z + y) + z, text[i], y);
+            }
+        });
         wrote = host::write_all(input + ".out", bwt.data(), bwt.size()) && host::write_all(input + ".out.lcp", l.data(), l.size()) &&
                 host::write_all(input + ".out.pairSA", g.data(), g.size());
     }
